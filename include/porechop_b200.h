@@ -1,0 +1,96 @@
+/*
+ * include/porechop_b200.h -- C-ABI of the B200 adapter-alignment engine (cpp_functions.so).
+ *
+ * Drop-in boundary: the library is loaded by ctypes exactly like the reference's
+ * porechop/cpp_functions.so (porechop/cpp_function_wrappers.py:21-39) and exports the reference's two
+ * symbols with the same signatures, ownership and string format, plus a batched entry point so that the
+ * host can submit every (read window, adapter) / (full read, adapter) pair in one call.
+ *
+ * Plain C types only (no torch / CUDA types): pointers, sizes, ints.  Every call runs on the CUDA
+ * device that is current for the calling thread (cudaSetDevice / torch.cuda.set_device /
+ * pb200SetDevice); there is NO CPU fallback -- without a usable sm_100 device the batch calls return
+ * PB200_ERR_NO_DEVICE and adapterAlignment() returns NULL after printing the reason to stderr.
+ */
+#ifndef PORECHOP_B200_H
+#define PORECHOP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- reference ABI, unchanged -------------------------------------------------------------------
+ * replaces porechop/include/adapter_align.h:13-14 (implemented in porechop/src/adapter_align.cpp:11-31).
+ * readSeq / adapterSeq: NUL-terminated ASCII, borrowed for the call.  Returns a malloc'd NUL-terminated
+ * string "readStart,readEnd,adapterStart,adapterEnd,rawScore,alignedRegion%ID,fullAdapter%ID"
+ * (ints "%d", doubles "%f"; ends are inclusive 0-based; "-1,0,-1,0,-2147483648,0.000000,0.000000" for an
+ * empty read or adapter).  Ownership passes to the caller, who releases it with freeCString().
+ * Thread-safe (calls are serialised on the device). */
+char *adapterAlignment(char *readSeq, char *adapterSeq, int matchScore, int mismatchScore, int gapOpenScore,
+                       int gapExtensionScore);
+
+/* replaces porechop/include/adapter_align.h:15 (porechop/src/adapter_align.cpp:34-36): free(p). */
+void freeCString(char *p);
+
+/* ---- batched entry points (new; SURVEY.md 8(b) "new batch export") --------------------------------
+ * One record of 9 int32 per alignment:
+ *   {readStart, readEnd, adapterStart, adapterEnd, rawScore, matchAligned, lenAligned, matchAdapter, lenAdapter}
+ * alignedRegion%ID = 100.0*matchAligned/lenAligned and fullAdapter%ID = 100.0*matchAdapter/lenAdapter in
+ * double, exactly the two divisions of porechop/src/alignment.cpp:82,90; an empty read or adapter gives
+ * {-1,0,-1,0,INT32_MIN,0,0,0,0}.  pb200FormatRecord() turns a record into the reference string.
+ *
+ * seqs/seq_off   : concatenated ASCII reads (or read windows); sequence s is seqs[seq_off[s] .. seq_off[s+1])
+ * adapters/ad_off: concatenated ASCII adapters, same convention (int32 offsets)
+ * pair_seq/pair_adapter (n_pairs each): the alignments to compute; both NULL = the full cross product in
+ *                  sequence-major order (n_pairs must equal n_seqs*n_adapters, record p = s*n_adapters + a)
+ * out            : n_pairs * 9 int32, caller-owned
+ * Returns 0 on success or a PB200_ERR_* code (pb200LastError() has the text).  Host pointers; pinned host
+ * memory lets the internal host<->device copies overlap with the kernels. */
+int adapterAlignmentBatch(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, const uint8_t *adapters,
+                          const int32_t *ad_off, int32_t n_adapters, const int32_t *pair_seq,
+                          const int32_t *pair_adapter, int64_t n_pairs, int matchScore, int mismatchScore,
+                          int gapOpenScore, int gapExtensionScore, int32_t *out);
+
+/* Same, with the bulk data already resident in device memory (d_seqs, d_seq_off, d_out are device pointers on
+ * the current device; adapters/ad_off stay host pointers -- a few KB).  Cross-product mode only.
+ * max_seq_len: length of the longest sequence, or -1 to let the library compute it on the device.
+ * The work is enqueued on `stream` (a cudaStream_t passed as void*, NULL = the library's own stream) and the
+ * call returns after enqueueing everything unless the score pass needs a host decision; call
+ * cudaStreamSynchronize / torch.cuda.synchronize before reading d_out. */
+int adapterAlignmentBatchDevice(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs,
+                                int64_t total_seq_bytes, int64_t max_seq_len, const uint8_t *adapters,
+                                const int32_t *ad_off, int32_t n_adapters, int matchScore, int mismatchScore,
+                                int gapOpenScore, int gapExtensionScore, int32_t *d_out, void *stream);
+
+/* Format one 9-int record as the reference string (alignment.cpp:113-121). Returns strlen, or -1 if buflen is
+ * too small (64 bytes always suffice). */
+int pb200FormatRecord(const int32_t *record, char *buf, int buflen);
+
+/* ---- device / diagnostics ------------------------------------------------------------------------------ */
+int pb200DeviceCount(void);               /* number of CUDA devices visible (0 if none / no driver) */
+int pb200SetDevice(int device);           /* cudaSetDevice for the calling thread */
+int pb200Synchronize(void);               /* wait for everything this library enqueued on the current device and
+                                             report deferred errors of adapterAlignmentBatchDevice calls */
+const char *pb200LastError(void);         /* text of the last error on this thread ("" if none) */
+long long pb200KernelLaunches(void);      /* kernels launched by this library since load (all threads) */
+/* Kernel timing with CUDA events on the launching stream: enable, run, then read back the accumulated
+ * duration and launch count of the DP kernels (trace_kernel + score_kernel) since the last reset. */
+void pb200TimingEnable(int on);
+int pb200TimingRead(double *dp_kernel_ms, long long *dp_kernel_launches, double *cells, int reset);
+/* Tunables (also read from the environment at first use): "trace" = "auto"|"smem"|"global";
+ * "direct_max" = longest sequence aligned in one pass; "chunk_tasks" = alignments per pipeline chunk. */
+int pb200SetOption(const char *name, const char *value);
+
+enum {
+    PB200_OK = 0,
+    PB200_ERR_NO_DEVICE = 100,   /* no CUDA device / driver, or device is not sm_100 */
+    PB200_ERR_CUDA = 101,        /* a CUDA call failed (see pb200LastError) */
+    PB200_ERR_ARG = 102,         /* invalid argument */
+    PB200_ERR_INTERNAL = 103     /* internal invariant violated (e.g. window bound) */
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PORECHOP_B200_H */

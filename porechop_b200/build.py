@@ -1,0 +1,52 @@
+"""Build cpp_functions.so (the CUDA engine behind the reference's ctypes boundary) in-tree with nvcc.
+
+    python -m porechop_b200.build            # builds porechop_b200/cpp_functions.so for sm_100a
+
+The file name and location mirror the reference (porechop/cpp_functions.so next to
+cpp_function_wrappers.py, Makefile:24 / cpp_function_wrappers.py:21-25 of the reference).
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+TARGET = os.path.join(HERE, 'cpp_functions.so')
+SOURCES = [os.path.join(CSRC, 'engine.cu')]
+DEPS = SOURCES + [os.path.join(CSRC, 'kernels.cuh'), os.path.join(CSRC, 'dp_core.cuh'),
+                  os.path.join(os.path.dirname(HERE), 'include', 'porechop_b200.h')]
+
+
+def nvcc_path():
+    for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError('nvcc not found')
+
+
+def needs_build():
+    if not os.path.exists(TARGET):
+        return True
+    t = os.path.getmtime(TARGET)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return TARGET
+    cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+           '-Xcompiler', '-fPIC', '-shared', '-o', TARGET] + SOURCES
+    if verbose:
+        cmd.insert(1, '-Xptxas')
+        cmd.insert(2, '-v')
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return TARGET
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

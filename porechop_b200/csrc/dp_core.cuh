@@ -1,0 +1,421 @@
+// porechop_b200/csrc/dp_core.cuh
+//
+// Core of the B200 adapter-alignment engine: the packed-int16 (s16x2, DPX) cell recurrence, the
+// per-lane wavefront step, best-end-cell tracking, traceback and alignment statistics.
+//
+// Semantics follow the reference hot path (paths relative to /root/reference, seqan/ =
+// porechop/include/seqan/) -- nothing here is ported code, only the arithmetic contract:
+//   cell        seqan/align/dp_formula_affine.h:459-495 ; linear case dp_formula_linear.h:156-188
+//   borders     seqan/align/dp_formula.h:204-220, dp_cell_affine.h:62-64
+//   scout       seqan/align/dp_scout.h:168-181, dp_meta_info.h:200-213
+//   traceback   seqan/align/dp_algorithm_impl.h:1354-1369, dp_traceback_impl.h:379-555
+//   statistics  porechop/src/alignment.cpp:6-110
+//
+// Everything in this header is `PB_HD` (host+device) so that tests/emu (a CPU emulation of one
+// sub-warp group, compiled with g++) runs exactly the code the kernels run; only warp shuffles,
+// shared-memory addressing and the launch glue live in kernels.cu.
+//
+// Mapping: a *slot* is two independent alignments carried in the two int16 halves of
+// every 32-bit register (half A = low 16 bits, half B = high 16 bits).  A slot is processed by a group
+// of G consecutive lanes; lane g owns adapter rows g*R+1 .. g*R+R and at step t computes read column
+// j = t-g+1 for those rows (anti-diagonal wavefront); the bottom row's (S, Vs) move to lane g+1 by
+// one warp shuffle per step.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PB_HD __host__ __device__ __forceinline__
+#else
+#define PB_HD inline
+#endif
+
+namespace pb {
+
+// ---- int16 domain constants -----------------------------------------------------------------------
+// Genuine DP values are bounded by |x| <= A*(m+2) <= PB_I16_LIMIT (checked on the host before the
+// int16 kernels are chosen), the "-infinity" of the borders is PB_NEG16; pseudo-infinite values of a
+// windowed pass stay in [PB_NEG16-PB_I16_LIMIT, PB_NEG16+PB_I16_LIMIT], i.e. always below every
+// genuine value and never wrapping an int16 even after one more add of a gap score.
+constexpr int PB_NEG16 = -16384;
+constexpr int PB_I16_LIMIT = 4000;
+constexpr int PB_LINEAR_EXT = -8192;   // "never extend" pseudo score used to run go==ge through the affine cell
+constexpr int PB_CODE_SHIFT = 12;      // base codes live in bits 12..14 of each half: x^y is 0 or >= 4096
+constexpr int PB_MAX_SUBW = 4096;      // ma - mi must not exceed this for the xor/addmax substitution trick
+constexpr uint8_t PB_PAD_H = 0x50;     // encoded-byte value (code<<4) for read padding (matches nothing)
+constexpr uint8_t PB_PAD_V = 0x60;     // encoded-byte value for adapter padding rows
+
+// record layout of one alignment (9 x int32): rs, re, as, ae, score, match_aln, len_aln, match_ad, len_ad
+constexpr int PB_REC = 9;
+constexpr int32_t PB_SCORE_EMPTY = (int32_t)0x80000000;
+
+PB_HD uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | (((uint32_t)hi & 0xFFFFu) << 16); }
+PB_HD int half16(uint32_t x, int h) { return (int)(int16_t)(h ? (x >> 16) : (x & 0xFFFFu)); }
+
+// ASCII -> encoded byte (Dna5 code << 4): A/a=0 C/c=1 G/g=2 T/t/U/u=3, every other byte = 4
+// (seqan/basic/alphabet_residue_tabs.h:113-140)
+PB_HD uint32_t encode_byte(uint32_t c) {
+    uint32_t u = c & 0xDFu;  // fold case
+    uint32_t code = 4u;
+    code = (u == 'A') ? 0u : code;
+    code = (u == 'C') ? 1u : code;
+    code = (u == 'G') ? 2u : code;
+    code = (u == 'T' || u == 'U') ? 3u : code;
+    return code << 4;
+}
+
+// ---- packed s16x2 primitives (Blackwell DPX: VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.S16x2 / VIMNMX3) ----
+PB_HD uint32_t add2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __vadd2(a, b);
+#else
+    return (((a & 0xFFFFu) + (b & 0xFFFFu)) & 0xFFFFu) | ((((a >> 16) + (b >> 16)) & 0xFFFFu) << 16);
+#endif
+}
+// max with "first operand wins ties" predicates: p = (a >= b) per half
+PB_HD uint32_t max2p(uint32_t a, uint32_t b, bool &plo, bool &phi) {
+#if defined(__CUDA_ARCH__)
+    return __vibmax_s16x2(a, b, &phi, &plo);
+#else
+    int al = half16(a, 0), bl = half16(b, 0), ah = half16(a, 1), bh = half16(b, 1);
+    plo = al >= bl; phi = ah >= bh;
+    return pack2(plo ? al : bl, phi ? ah : bh);
+#endif
+}
+PB_HD uint32_t max2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __vmaxs2(a, b);
+#else
+    bool p, q; return max2p(a, b, p, q);
+#endif
+}
+// max(a+b, c) per half
+PB_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __viaddmax_s16x2(a, b, c);
+#else
+    return max2(add2(a, b), c);
+#endif
+}
+PB_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    return __vimax3_s16x2(a, b, c);
+#else
+    return max2(max2(a, b), c);
+#endif
+}
+
+// ---- scoring scheme as the kernels see it --------------------------------------------------------------
+struct Scoring {
+    uint32_t go2;     // packed gap-open score (linear mode: the single gap score)
+    uint32_t ge2;     // packed gap-extension score (linear mode: PB_LINEAR_EXT, so an extension never wins)
+    uint32_t subA2;   // packed (match + 1)
+    uint32_t subF2;   // packed mismatch
+    int32_t linear;   // go == ge : NW recurrence of dp_formula_linear.h, no end-cell correction
+    int32_t ma, mi, go, ge;
+};
+
+PB_HD Scoring make_scoring(int ma, int mi, int go, int ge) {
+    Scoring s;
+    s.linear = (go == ge) ? 1 : 0;
+    s.ma = ma; s.mi = mi; s.go = go; s.ge = ge;
+    s.go2 = s.linear ? pack2(ge, ge) : pack2(go, go);
+    s.ge2 = s.linear ? pack2(PB_LINEAR_EXT, PB_LINEAR_EXT) : pack2(ge, ge);
+    s.subA2 = pack2(ma + 1, ma + 1);
+    s.subF2 = pack2(mi, mi);
+    return s;
+}
+
+// One alignment as the kernels see it (64 bytes).  `n` columns of the encoded read starting at seq_off
+// are aligned against `m` adapter rows.  A windowed task (second pass over a long read) starts at global
+// column col0 with a -infinity left boundary (unless col0 == 0) and has its end cell given.
+struct Task {
+    int64_t seq_off;     // offset of the first column's base in the encoded sequence buffer
+    int32_t n;           // number of columns (window length)
+    int32_t m;           // adapter length (rows)
+    int32_t ad_off;      // offset of the adapter in the encoded adapter buffer
+    int32_t out_idx;     // index of the 9-int result record
+    int32_t flags;       // TASK_* bits
+    int32_t end_j;       // given end cell: column local to the window (TASK_END_GIVEN)
+    int32_t end_i;       //                 row
+    int32_t end_corr;    // bit0: Vs* == S*, bit1: Hs* == S*   (dp_algorithm_impl.h:1354-1369)
+    int32_t end_score;
+    int32_t col0;        // global column of the window start (read coordinates = local + col0)
+    int32_t n_total;     // full read length
+    int32_t pad0, pad1, pad2;
+};
+static_assert(sizeof(Task) == 64, "Task must be 64 bytes");
+enum { TASK_LEFT_INF = 1, TASK_END_GIVEN = 2 };
+
+// End cell of one alignment found by the score pass.
+struct EndCell {
+    int32_t j, i, score, corr;
+};
+
+// ---- one lane of a group ------------------------------------------------------------------------------
+template <int R>
+struct Lane {
+    uint32_t Sl[R];   // S[j-1][row]   (packed halves), becomes S[j][row] after the step
+    uint32_t Hs[R];   // Hs[j-1][row]
+    uint32_t v2[R];   // adapter codes of the owned rows, << PB_CODE_SHIFT, packed halves
+    uint32_t Vr[R];   // Vs[j][row] of the step just computed (needed only when a best cell is recorded)
+    uint32_t prevRecvS;  // S[j-1][top-1]  (diagonal input of the top row)
+    uint32_t botS, botV; // S[j][bottom], Vs[j][bottom] -> shuffled to the next lane
+    // scout state, per half (scalar): last-row running best (meaningful in the lane owning row m) ...
+    int lrBest[2], lrJ[2], lrCorr[2];
+    // ... and the best of this lane's rows in the final column
+    int fcBest[2], fcI[2], fcCorr[2];
+};
+
+// geometry of one half of a slot
+struct HalfGeom {
+    int n, m;
+    int gl, rl;   // lane (within group) and local row owning the last row m; gl = -1 when m == 0
+};
+PB_HD HalfGeom make_geom(int n, int m, int R) {
+    HalfGeom h; h.n = n; h.m = m;
+    if (m > 0) { h.gl = (m - 1) / R; h.rl = (m - 1) % R; } else { h.gl = -1; h.rl = 0; }
+    return h;
+}
+
+// Encoded adapter byte for row i (1-based) of an m-row adapter, padding beyond m.
+PB_HD uint32_t adapter_byte(const uint8_t *ad, int m, int i) { return (i <= m) ? (uint32_t)ad[i - 1] : (uint32_t)PB_PAD_V; }
+
+template <int R>
+PB_HD void lane_init(Lane<R> &L, int g, const uint8_t *adA, int mA, bool leftInfA,
+                     const uint8_t *adB, int mB, bool leftInfB) {
+    const uint32_t zero_or_negA = leftInfA ? ((uint32_t)PB_NEG16 & 0xFFFFu) : 0u;
+    const uint32_t zero_or_negB = leftInfB ? (((uint32_t)PB_NEG16 & 0xFFFFu) << 16) : 0u;
+    const uint32_t col0 = zero_or_negA | zero_or_negB;      // S[0][i], i >= 1
+    const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int i = g * R + r + 1;
+        L.Sl[r] = col0;
+        L.Hs[r] = neg2;
+        L.Vr[r] = neg2;
+        uint32_t a = mA > 0 ? adapter_byte(adA, mA, i) : (uint32_t)PB_PAD_V;
+        uint32_t b = mB > 0 ? adapter_byte(adB, mB, i) : (uint32_t)PB_PAD_V;
+        L.v2[r] = (a << 8) | (b << 24);   // code<<4 in a byte -> code<<12 in the half
+    }
+    L.prevRecvS = (g == 0) ? 0u : col0;   // S[0][g*R] ; row 0 is always the zero border
+    L.botS = col0; L.botV = neg2;
+    for (int h = 0; h < 2; ++h) {
+        L.lrBest[h] = 0; L.lrJ[h] = 0; L.lrCorr[h] = 0;         // candidate (0, m): value 0
+        L.fcBest[h] = -0x40000000; L.fcI[h] = 0; L.fcCorr[h] = 0;
+    }
+}
+
+// One packed cell pair.  TRACE: also produce the 4 trace flags per half:
+//   bit0 tD : diagonal chosen          (g <= d,  ties -> diagonal)
+//   bit1 tM : vertical gap is the max  (vs >= hs, ties -> vertical)
+//   bit2 tV : vertical gap extended    (v_ext >= v_open, ties -> extend)
+//   bit3 tH : horizontal gap extended  (h_ext >= h_open, ties -> extend)
+// flags for half A are returned in bits 0..3 of `bits`, half B in bits 4..7.
+template <bool TRACE>
+PB_HD void cell(uint32_t &Sl, uint32_t &Hs, uint32_t &diag, uint32_t &upS, uint32_t &upV, uint32_t &vrow,
+                uint32_t h2, uint32_t v2, const Scoring &sc, uint32_t &bits) {
+    const uint32_t h_open = add2(Sl, sc.go2);
+    const uint32_t v_open = add2(upS, sc.go2);
+    // substitution score per half: codes equal -> ~(h^v) == -1 -> max(-1 + ma + 1, mi) = ma ; else <= mi
+    const uint32_t nx = ~(h2 ^ v2);
+    const uint32_t sub = addmax2(nx, sc.subA2, sc.subF2);
+    const uint32_t d = add2(diag, sub);
+    uint32_t hs, vs, s;
+    if (TRACE) {
+        bool pHl, pHh, pVl, pVh, pMl, pMh, pDl, pDh;
+        hs = max2p(add2(Hs, sc.ge2), h_open, pHl, pHh);
+        vs = max2p(add2(upV, sc.ge2), v_open, pVl, pVh);
+        const uint32_t gmx = max2p(vs, hs, pMl, pMh);
+        s = max2p(d, gmx, pDl, pDh);
+        bits = (pDl ? 1u : 0u) | (pMl ? 2u : 0u) | (pVl ? 4u : 0u) | (pHl ? 8u : 0u) |
+               (pDh ? 16u : 0u) | (pMh ? 32u : 0u) | (pVh ? 64u : 0u) | (pHh ? 128u : 0u);
+    } else {
+        hs = addmax2(Hs, sc.ge2, h_open);
+        vs = addmax2(upV, sc.ge2, v_open);
+        s = max3(d, vs, hs);
+        bits = 0;
+    }
+    diag = Sl;
+    Sl = s; Hs = hs; upS = s; upV = vs; vrow = vs;
+}
+
+// position of the nibble of (half h, local row r) in the per-step trace words of a lane
+template <int R> PB_HD int trace_word(int h, int r) { return (h * R + r) >> 3; }
+template <int R> PB_HD int trace_shift(int h, int r) { return ((h * R + r) & 7) * 4; }
+template <int R> struct TraceWords { static constexpr int value = (2 * R + 7) / 8; };
+
+// scout bookkeeping after a lane computed column j (1-based, local to the window)
+template <int R>
+PB_HD void lane_track(Lane<R> &L, int g, int j, const HalfGeom &A, const HalfGeom &B) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const HalfGeom &H = h ? B : A;
+        if (j < H.n) {
+            // last row of an inner column: strict '>' keeps the leftmost best (dp_scout.h:168-181)
+            if (g == H.gl) {
+                uint32_t s2 = L.Sl[0], v2 = L.Vr[0], h2 = L.Hs[0];
+#pragma unroll
+                for (int r = 1; r < R; ++r) if (H.rl == r) { s2 = L.Sl[r]; v2 = L.Vr[r]; h2 = L.Hs[r]; }
+                int c = half16(s2, h);
+                if (c > L.lrBest[h]) {
+                    L.lrBest[h] = c; L.lrJ[h] = j;
+                    L.lrCorr[h] = (half16(v2, h) == c ? 1 : 0) | (half16(h2, h) == c ? 2 : 0);
+                }
+            }
+        } else if (j == H.n) {
+            // final column: every row is a candidate, visited top to bottom
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                int i = g * R + r + 1;
+                if (i <= H.m) {
+                    int c = half16(L.Sl[r], h);
+                    if (c > L.fcBest[h]) {
+                        L.fcBest[h] = c; L.fcI[h] = i;
+                        L.fcCorr[h] = (half16(L.Vr[r], h) == c ? 1 : 0) | (half16(L.Hs[r], h) == c ? 2 : 0);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One wavefront step of one lane: column j with inputs from the lane above.
+//   recvS/recvV : S[j][top-1], Vs[j][top-1]  (for g == 0 the caller passes the row-0 border: 0 / NEG)
+//   h2          : read bases of column j, encoded << PB_CODE_SHIFT, packed halves
+//   tw          : trace words of this step (TRACE only), TraceWords<R>::value entries
+template <int R, bool TRACE>
+PB_HD void lane_step(Lane<R> &L, uint32_t recvS, uint32_t recvV, uint32_t h2, const Scoring &sc, uint32_t *tw) {
+    uint32_t diag = L.prevRecvS, upS = recvS, upV = recvV;
+    if (TRACE) {
+#pragma unroll
+        for (int w = 0; w < TraceWords<R>::value; ++w) tw[w] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        uint32_t bits;
+        cell<TRACE>(L.Sl[r], L.Hs[r], diag, upS, upV, L.Vr[r], h2, L.v2[r], sc, bits);
+        if (TRACE) {
+            tw[trace_word<R>(0, r)] |= (bits & 15u) << trace_shift<R>(0, r);
+            tw[trace_word<R>(1, r)] |= (bits >> 4) << trace_shift<R>(1, r);
+        }
+    }
+    L.prevRecvS = recvS;
+    L.botS = upS; L.botV = upV;
+}
+
+// Combine the per-lane scout state of a group into the end cell of half h.
+// `lanes` is indexable [g] -> const Lane<R>& (host: array; device: values gathered from shared memory).
+struct ScoutCand { int fcBest, fcI, fcCorr, lrBest, lrJ, lrCorr; };
+PB_HD EndCell scout_combine(const ScoutCand *c, int G, const HalfGeom &H) {
+    EndCell e;
+    if (H.n <= 0 || H.m <= 0) { e.j = 0; e.i = 0; e.score = PB_SCORE_EMPTY; e.corr = 0; return e; }
+    const ScoutCand &lr = c[H.gl];
+    int best = lr.lrBest, bj = lr.lrJ, bi = H.m, corr = lr.lrCorr;
+    for (int g = 0; g < G; ++g) {
+        if (c[g].fcBest > best) { best = c[g].fcBest; bj = H.n; bi = c[g].fcI; corr = c[g].fcCorr; }
+    }
+    e.j = bj; e.i = bi; e.score = best; e.corr = corr;
+    return e;
+}
+
+// ---- traceback + statistics ---------------------------------------------------------------------------
+// NibFn(jl, i) -> 4 trace flags of cell (local column jl >= 1, row i >= 1)
+// EqFn(jl, i)  -> read base of local column jl equals adapter base of row i (code equality, N == N)
+// Writes the 9-int record.  Returns 0, or 1 if the path ran into the left edge of a window with
+// col0 > 0 (window too small -- must never happen when the window bound of DESIGN.md holds).
+template <class NibFn, class EqFn>
+PB_HD int traceback_stats(NibFn nib, EqFn eq, const EndCell &end, bool linear, int col0, int n_total, int m,
+                          int32_t *rec) {
+    if (end.score == PB_SCORE_EMPTY) {
+        rec[0] = -1; rec[1] = 0; rec[2] = -1; rec[3] = 0; rec[4] = PB_SCORE_EMPTY;
+        rec[5] = 0; rec[6] = 0; rec[7] = 0; rec[8] = 0;
+        return 0;
+    }
+    int j = end.j, i = end.i;      // local column, row
+    int L = 0, matches = 0;
+    // events: first/last (in forward order) path operation that consumes a read / adapter base
+    bool haveR = false, haveA = false;
+    int lastR_k = 0, lastR_i = 0, lastR_uA = 0, firstR_k = 0, firstR_i = 0, firstR_uA = 0;
+    int lastA_k = 0, lastA_j = 0, lastA_uR = 0, firstA_k = 0, firstA_j = 0, firstA_uR = 0;
+    // direction of the current cell: 0 diag, 1 vertical, 2 horizontal
+    int dir;
+    uint32_t b = 0;
+    if (j > 0 && i > 0) {
+        b = nib(j, i);
+        dir = (b & 1u) ? 0 : ((b & 2u) ? 1 : 2);
+        if (!linear) {                                  // dp_algorithm_impl.h:1354-1369
+            if (end.corr & 1) dir = 1; else if (end.corr & 2) dir = 2;
+        }
+    } else {
+        dir = 0;
+    }
+    while (j > 0 && i > 0) {
+        if (dir == 0) {
+            if (eq(j, i)) ++matches;
+            if (!haveR) { haveR = true; lastR_k = L; lastR_i = i; lastR_uA = 1; }
+            firstR_k = L; firstR_i = i; firstR_uA = 1;
+            if (!haveA) { haveA = true; lastA_k = L; lastA_j = j; lastA_uR = 1; }
+            firstA_k = L; firstA_j = j; firstA_uR = 1;
+            ++L; --j; --i;
+        } else if (dir == 1) {
+            // vertical run: follow while the current cell says "extended" (dp_traceback_impl.h:225-295)
+            bool ext;
+            do {
+                ext = (b & 4u) && (i != 1) && !linear;
+                if (!haveA) { haveA = true; lastA_k = L; lastA_j = j; lastA_uR = 0; }
+                firstA_k = L; firstA_j = j; firstA_uR = 0;
+                ++L; --i;
+                if (i > 0) b = nib(j, i);
+            } while (ext);
+        } else {
+            bool ext;
+            do {
+                ext = (b & 8u) && (j != 1) && !linear;
+                if (!haveR) { haveR = true; lastR_k = L; lastR_i = i; lastR_uA = 0; }
+                firstR_k = L; firstR_i = i; firstR_uA = 0;
+                ++L; --j;
+                if (j > 0) b = nib(j, i);
+            } while (ext);
+        }
+        if (j > 0 && i > 0) {
+            // after a diagonal step the new cell's flags were not loaded yet
+            if (dir == 0) b = nib(j, i);
+            dir = (b & 1u) ? 0 : ((b & 2u) ? 1 : 2);
+        }
+    }
+    int status = (j == 0 && i > 0 && col0 > 0) ? 1 : 0;
+
+    // whole alignment = [H x a][V x bb] . path . [H x c][V x e]   (dp_traceback_impl.h:532-554)
+    const int a = col0 + j, bb = i;
+    const int jend = col0 + end.j;
+    const int c = n_total - jend, e = m - end.i;
+    const int Ltot = a + bb + L + c + e;
+#define PB_COL(k) (a + bb + (L - 1 - (k)))
+    // first column with a read base (r0) / adapter base (a0) and the bases of the OTHER sequence before it
+    int r0, AB_r0, a0, RB_a0;
+    if (a > 0) { r0 = 0; AB_r0 = 0; }
+    else if (haveR) { r0 = PB_COL(firstR_k); AB_r0 = firstR_i - firstR_uA; }
+    else { r0 = bb + L; AB_r0 = end.i; }
+    if (bb > 0) { a0 = 0; RB_a0 = 0; }
+    else if (haveA) { a0 = PB_COL(firstA_k); RB_a0 = col0 + firstA_j - firstA_uR; }
+    else { a0 = a + L + c; RB_a0 = n_total; }
+    int rs, as;
+    int start;
+    if (r0 >= a0) { start = r0; rs = 0; as = AB_r0; } else { start = a0; as = 0; rs = RB_a0; }
+    // last column with a read base (r1) / adapter base (a1)
+    int r1, AB_r1, a1, RB_a1;
+    if (c > 0) { r1 = Ltot - 1; AB_r1 = m; }
+    else if (haveR) { r1 = PB_COL(lastR_k); AB_r1 = lastR_i - lastR_uA; }
+    else { r1 = a - 1; AB_r1 = 0; }
+    if (e > 0) { a1 = Ltot - 1; RB_a1 = n_total; }
+    else if (haveA) { a1 = PB_COL(lastA_k); RB_a1 = col0 + lastA_j - lastA_uR; }
+    else { a1 = a + bb - 1; RB_a1 = 0; }
+#undef PB_COL
+    int re, ae, endc;
+    if (r1 <= a1) { endc = r1; re = n_total - 1; ae = AB_r1; } else { endc = a1; ae = m - 1; re = RB_a1; }
+    rec[0] = rs; rec[1] = re; rec[2] = as; rec[3] = ae; rec[4] = end.score;
+    rec[5] = matches; rec[6] = endc - start + 1; rec[7] = matches; rec[8] = a1 - a0 + 1;
+    return status;
+}
+
+}  // namespace pb

@@ -1,0 +1,788 @@
+// porechop_b200/csrc/engine.cu -- host engine + C-ABI (include/porechop_b200.h) of cpp_functions.so.
+//
+// Replaces, behind the same ctypes boundary, the reference's C shim + SeqAn DP + ScoredAlignment
+// (porechop/src/adapter_align.cpp:11-44, porechop/src/alignment.cpp:6-121, seqan/align/dp_*.h).
+// The host side only plans and pipelines: chunking, class selection by adapter length, host<->device
+// copies on a ring of streams, kernel launches.  All alignment arithmetic runs in the sm_100a kernels of
+// kernels.cuh; there is no CPU alignment path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/porechop_b200.h"
+#include "kernels.cuh"
+
+using namespace pb;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_timing{0};
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(PB200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(PB200_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Options {
+    int trace_mode = 0;            // 0 auto, 1 smem, 2 global
+    int64_t direct_max = 512;      // longest sequence aligned in a single (trace) pass
+    int64_t chunk_tasks = 8 << 20; // alignments per pipeline chunk
+    int64_t chunk_bytes = 1ll << 30;
+    int wpb = 0;                   // warps per block override for trace kernel (0 = auto)
+};
+Options g_opt;
+std::once_flag g_opt_once;
+void load_env_options() {
+    std::call_once(g_opt_once, [] {
+        if (const char *v = getenv("PB200_TRACE")) {
+            if (!strcmp(v, "smem")) g_opt.trace_mode = 1; else if (!strcmp(v, "global")) g_opt.trace_mode = 2;
+        }
+        if (const char *v = getenv("PB200_DIRECT_MAX")) g_opt.direct_max = atoll(v);
+        if (const char *v = getenv("PB200_CHUNK_TASKS")) g_opt.chunk_tasks = std::max(1ll, atoll(v));
+        if (const char *v = getenv("PB200_WPB")) g_opt.wpb = atoi(v);
+    });
+}
+
+constexpr int NSTAGE = 3;
+struct Stage {
+    cudaStream_t stream = nullptr;
+    DevBuf seq_raw, seq_codes, seq_off, tasks, tasks2, ends, out, order, pair_seq, pair_ad, gtrace, misc;
+};
+
+struct ClassPlan {
+    int cls = 0;                      // 0: m<=32, 1: <=64, 2: <=128, 3: <=256, 4: generic
+    std::vector<int32_t> ad_ids;      // adapters of the class, sorted by length
+    int m_max = 0;
+};
+
+struct TimedLaunch { cudaEvent_t a, b; };
+
+struct Engine {
+    int device = -1;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    std::mutex mu;
+    Stage st[NSTAGE];
+    DevBuf ad_raw, ad_codes, ad_off, cls_ad, gjobs, gscratch;
+    std::vector<TimedLaunch> timed;
+    double timed_cells = 0.0;
+    double timed_ms_acc = 0.0;
+    long long timed_n_acc = 0;
+    bool init_done = false;
+    int init() {
+        if (init_done) return 0;
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            return fail(PB200_ERR_NO_DEVICE, "device is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                                                 ", this library is built for sm_100a only");
+        sm_count = prop.multiProcessorCount;
+        smem_optin = prop.sharedMemPerBlockOptin;
+        for (int i = 0; i < NSTAGE; ++i) CK(cudaStreamCreateWithFlags(&st[i].stream, cudaStreamNonBlocking));
+        init_done = true;
+        return 0;
+    }
+};
+
+std::mutex g_engines_mu;
+std::map<int, std::unique_ptr<Engine>> g_engines;
+
+int get_engine(Engine **out) {
+    load_env_options();
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(PB200_ERR_NO_DEVICE, std::string("no CUDA device available: ") +
+                                             (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_engines_mu);
+    auto &slot = g_engines[dev];
+    if (!slot) { slot.reset(new Engine()); slot->device = dev; }
+    *out = slot.get();
+    return 0;
+}
+
+// ---- int16 domain checks and the window bound ------------------------------------------------------------
+struct SchemeInfo {
+    bool int16_ok_base;   // sign conventions allow the packed kernels at all
+    int A;                // max |score|
+    bool bounded;         // window bound exists (both gap scores negative)
+    int wnum, wden;       // W(m) = m + m*wnum/wden
+};
+SchemeInfo scheme_info(int ma, int mi, int go, int ge) {
+    SchemeInfo s;
+    auto ab = [](int x) { return x < 0 ? -(long long)x : (long long)x; };
+    long long A = std::max(std::max(ab(ma), ab(mi)), std::max(ab(go), ab(ge)));
+    s.A = (int)std::min<long long>(A, 1 << 30);
+    s.int16_ok_base = (ma >= mi) && ((long long)ma - mi <= PB_MAX_SUBW) && go <= 0 && ge <= 0 && A <= PB_I16_LIMIT;
+    s.bounded = (go < 0 && ge < 0);
+    s.wnum = std::max(std::max(ma, mi), 0);
+    s.wden = (int)std::min(ab(go), ab(ge));
+    if (s.wden == 0) s.wden = 1;
+    return s;
+}
+bool int16_ok(const SchemeInfo &s, int m) { return s.int16_ok_base && (long long)s.A * (m + 3) <= PB_I16_LIMIT; }
+int class_of(const SchemeInfo &s, int m) {
+    if (!int16_ok(s, m) || m > 256) return 4;
+    if (m <= 32) return 0;
+    if (m <= 64) return 1;
+    if (m <= 128) return 2;
+    return 3;
+}
+
+// ---- kernel launch helpers -----------------------------------------------------------------------------
+void timed_begin(Engine &E, cudaStream_t s, TimedLaunch &tl, bool &on) {
+    on = g_timing.load() != 0;
+    if (on) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); cudaEventRecord(tl.a, s); }
+}
+void timed_end(Engine &E, cudaStream_t s, TimedLaunch &tl, bool on) {
+    if (on) { cudaEventRecord(tl.b, s); E.timed.push_back(tl); }
+}
+
+template <int G, int R, bool SM>
+int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const Task *tasks, int64_t n_tasks, int max_n,
+                         const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int wpb,
+                         size_t smem_bytes, int blocks_per_sm, int *status) {
+    constexpr int SPW = 32 / G;
+    constexpr int WPS = TraceWords<R>::value;
+    const int max_steps = max_n + G - 1;
+    const int64_t n_slots = (n_tasks + 1) / 2;
+    const int64_t n_wslots = (n_slots + SPW - 1) / SPW;
+    int64_t blocks = (n_wslots + wpb - 1) / wpb;
+    blocks = std::min<int64_t>(blocks, (int64_t)blocks_per_sm * E.sm_count);
+    if (blocks <= 0) return 0;
+    uint32_t *gtrace = nullptr;
+    if (!SM) {
+        size_t bytes = (size_t)blocks * wpb * (size_t)max_steps * WPS * 32 * 4;
+        if (int rc = S.gtrace.ensure(bytes)) return rc;
+        gtrace = S.gtrace.as<uint32_t>();
+    }
+    auto kern = trace_kernel<G, R, SM>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    TimedLaunch tl; bool on;
+    timed_begin(E, stream, tl, on);
+    kern<<<(unsigned)blocks, wpb * 32, smem_bytes, stream>>>(tasks, n_tasks, seq_codes, ad_codes, sc, out, gtrace,
+                                                              max_steps, max_n, status);
+    timed_end(E, stream, tl, on);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int G, int R>
+int launch_trace(Engine &E, Stage &S, cudaStream_t stream, const Task *tasks, int64_t n_tasks, int max_n,
+                 const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
+    constexpr int SPW = 32 / G;
+    constexpr int WPS = TraceWords<R>::value;
+    if (max_n < 1) max_n = 1;
+    const int max_steps = max_n + G - 1;
+    const size_t common = (size_t)(SPW * max_n + PB_SCRATCH_WORDS) * 4;
+    const size_t per_warp_sm = (size_t)max_steps * WPS * 32 * 4 + common;
+    // pick warps/block for the shared-memory trace: maximise resident warps per SM
+    int best_w = 0, best_res = 0, best_bps = 0;
+    for (int w = PB_WARPS_PER_BLOCK; w >= 1; --w) {
+        if (g_opt.wpb && w != g_opt.wpb) continue;
+        size_t bytes = per_warp_sm * w;
+        if (bytes > E.smem_optin) continue;
+        int bps = 0;
+        auto kern = trace_kernel<G, R, true>;
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) continue;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, w * 32, bytes) != cudaSuccess) continue;
+        if (bps * w > best_res) { best_res = bps * w; best_w = w; best_bps = bps; }
+    }
+    bool use_sm = best_res >= 6;
+    if (g_opt.trace_mode == 1 && best_res > 0) use_sm = true;
+    if (g_opt.trace_mode == 2) use_sm = false;
+    if (use_sm)
+        return launch_trace_variant<G, R, true>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out,
+                                                best_w, per_warp_sm * best_w, best_bps, status);
+    int w = g_opt.wpb ? g_opt.wpb : PB_WARPS_PER_BLOCK;
+    size_t bytes = common * w;
+    if (bytes > E.smem_optin) return fail(PB200_ERR_ARG, "sequence too long for single-pass alignment");
+    int bps = 0;
+    auto kern = trace_kernel<G, R, false>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, w * 32, bytes));
+    if (bps < 1) bps = 1;
+    // bound the global trace scratch (~8 GB)
+    size_t region = (size_t)max_steps * WPS * 128;
+    int64_t max_warps = std::max<int64_t>(w, (int64_t)((8ull << 30) / std::max<size_t>(region, 1)));
+    while (bps > 1 && (int64_t)bps * E.sm_count * w > max_warps) --bps;
+    return launch_trace_variant<G, R, false>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, w,
+                                             bytes, bps, status);
+}
+
+int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const Task *tasks, int64_t n_tasks, int max_n,
+                       const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
+    switch (cls) {
+        case 0: return launch_trace<8, 4>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+        case 1: return launch_trace<16, 4>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+        case 2: return launch_trace<32, 4>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+        case 3: return launch_trace<32, 8>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+    }
+    return fail(PB200_ERR_INTERNAL, "bad class");
+}
+
+template <int G, int R>
+int launch_score(Engine &E, cudaStream_t stream, const Task *tasks, int64_t n_tasks, unsigned long long *counter,
+                 const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, EndCell *ends) {
+    auto kern = score_kernel<G, R>;
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, PB_WARPS_PER_BLOCK * 32, 0));
+    if (bps < 1) bps = 1;
+    constexpr int SPW = 32 / G;
+    const int64_t n_slots = (n_tasks + 1) / 2;
+    int64_t blocks = (n_slots + SPW * PB_WARPS_PER_BLOCK - 1) / (SPW * PB_WARPS_PER_BLOCK);
+    blocks = std::min<int64_t>(blocks, (int64_t)bps * E.sm_count);
+    if (blocks <= 0) return 0;
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    TimedLaunch tl; bool on;
+    timed_begin(E, stream, tl, on);
+    kern<<<(unsigned)blocks, PB_WARPS_PER_BLOCK * 32, 0, stream>>>(tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
+    timed_end(E, stream, tl, on);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+int launch_score_class(Engine &E, cudaStream_t stream, int cls, const Task *tasks, int64_t n_tasks,
+                       unsigned long long *counter, const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc,
+                       EndCell *ends) {
+    switch (cls) {
+        case 0: return launch_score<4, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
+        case 1: return launch_score<8, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
+        case 2: return launch_score<16, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
+        case 3: return launch_score<32, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
+    }
+    return fail(PB200_ERR_INTERNAL, "bad class");
+}
+
+int launch_encode(cudaStream_t stream, const uint8_t *in, uint8_t *out, int64_t n, int sm_count) {
+    if (n <= 0) return 0;
+    int64_t blocks = std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), (int64_t)sm_count * 16);
+    encode_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, out, n);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Run every task of one class: tasks[0..n_tasks) are already built on the device in slot order.
+int run_class_tasks(Engine &E, Stage &S, cudaStream_t stream, int cls, int m_max, int64_t n_tasks, int64_t max_n,
+                    const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, const SchemeInfo &si,
+                    int32_t *out, int *status, unsigned long long *counter) {
+    if (n_tasks <= 0) return 0;
+    Task *tasks = S.tasks.as<Task>();
+    int64_t W = si.bounded ? (int64_t)m_max + ((int64_t)m_max * si.wnum) / si.wden : (int64_t)1 << 40;
+    const bool two_pass = si.bounded && max_n > g_opt.direct_max && W + 1 < max_n;
+    if (!two_pass) return launch_trace_class(E, S, stream, cls, tasks, n_tasks, (int)max_n, seq_codes, ad_codes, sc, out, status);
+    if (int rc = S.ends.ensure((size_t)n_tasks * sizeof(EndCell))) return rc;
+    if (int rc = S.tasks2.ensure((size_t)n_tasks * sizeof(Task))) return rc;
+    if (int rc = launch_score_class(E, stream, cls, tasks, n_tasks, counter, seq_codes, ad_codes, sc, S.ends.as<EndCell>())) return rc;
+    {
+        int64_t blocks = (n_tasks + 255) / 256;
+        window_tasks_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tasks, S.ends.as<EndCell>(), S.tasks2.as<Task>(), n_tasks,
+                                                                   si.wnum, si.wden);
+        g_launches++;
+        CK(cudaGetLastError());
+    }
+    return launch_trace_class(E, S, stream, cls, S.tasks2.as<Task>(), n_tasks, (int)W, seq_codes, ad_codes, sc, out, status);
+}
+
+// Adapter-side planning shared by all entry points.
+struct AdapterPlan {
+    std::vector<ClassPlan> classes;   // non-empty classes only
+    SchemeInfo si;
+    Scoring sc;
+};
+int plan_adapters(Engine &E, cudaStream_t stream, const uint8_t *adapters, const int32_t *ad_off, int32_t n_adapters,
+                  int ma, int mi, int go, int ge, AdapterPlan &P) {
+    P.si = scheme_info(ma, mi, go, ge);
+    P.sc = make_scoring(ma, mi, go, ge);
+    std::vector<ClassPlan> cl(5);
+    for (int c = 0; c < 5; ++c) cl[c].cls = c;
+    for (int a = 0; a < n_adapters; ++a) {
+        int m = ad_off[a + 1] - ad_off[a];
+        if (m < 0) return fail(PB200_ERR_ARG, "adapter offsets not monotone");
+        int c = class_of(P.si, m);
+        cl[c].ad_ids.push_back(a);
+        cl[c].m_max = std::max(cl[c].m_max, m);
+    }
+    for (auto &c : cl) {
+        std::stable_sort(c.ad_ids.begin(), c.ad_ids.end(), [&](int x, int y) {
+            return (ad_off[x + 1] - ad_off[x]) > (ad_off[y + 1] - ad_off[y]);
+        });
+        if (!c.ad_ids.empty()) P.classes.push_back(c);
+    }
+    const size_t ad_bytes = (size_t)ad_off[n_adapters];
+    if (int rc = E.ad_raw.ensure(ad_bytes + 16)) return rc;
+    if (int rc = E.ad_codes.ensure(ad_bytes + 16)) return rc;
+    if (int rc = E.ad_off.ensure((size_t)(n_adapters + 1) * 4)) return rc;
+    if (ad_bytes) CK(cudaMemcpyAsync(E.ad_raw.p, adapters, ad_bytes, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(E.ad_off.p, ad_off, (size_t)(n_adapters + 1) * 4, cudaMemcpyHostToDevice, stream));
+    if (int rc = launch_encode(stream, E.ad_raw.as<uint8_t>(), E.ad_codes.as<uint8_t>(), (int64_t)ad_bytes, E.sm_count)) return rc;
+    // class adapter-id lists, concatenated
+    std::vector<int32_t> flat;
+    for (auto &c : P.classes) flat.insert(flat.end(), c.ad_ids.begin(), c.ad_ids.end());
+    if (int rc = E.cls_ad.ensure(flat.size() * 4 + 16)) return rc;
+    if (!flat.empty()) CK(cudaMemcpyAsync(E.cls_ad.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, stream));
+    // the host vectors above are pageable: the async copies have been staged by the driver before returning
+    CK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+// Generic (int32) class: jobs are planned on the host, which needs the sequence lengths there.
+int run_generic_cross(Engine &E, Stage &S, cudaStream_t stream, const ClassPlan &C, const int64_t *h_seq_off,
+                      int64_t s0, int64_t cnt, int64_t base_off, const int32_t *h_ad_off, int32_t n_adapters,
+                      const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out) {
+    std::vector<GenericJob> jobs;
+    const size_t budget = 2ull << 30;
+    size_t used = 0;
+    auto flush = [&]() -> int {
+        if (jobs.empty()) return 0;
+        if (int rc = E.gjobs.ensure(jobs.size() * sizeof(GenericJob))) return rc;
+        if (int rc = E.gscratch.ensure(used + 64)) return rc;
+        CK(cudaMemcpyAsync(E.gjobs.p, jobs.data(), jobs.size() * sizeof(GenericJob), cudaMemcpyHostToDevice, stream));
+        int nb = (int)((jobs.size() + 63) / 64);
+        generic_kernel<<<nb, 64, 0, stream>>>(E.gjobs.as<GenericJob>(), (int)jobs.size(), seq_codes, ad_codes, sc.ma, sc.mi,
+                                              sc.go, sc.ge, E.gscratch.as<uint8_t>(), out);
+        g_launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(stream));
+        jobs.clear(); used = 0;
+        return 0;
+    };
+    for (int64_t s = s0; s < s0 + cnt; ++s) {
+        for (int32_t a : C.ad_ids) {
+            GenericJob j;
+            j.seq_off = h_seq_off[s] - base_off;
+            j.n = (int32_t)(h_seq_off[s + 1] - h_seq_off[s]);
+            j.m = h_ad_off[a + 1] - h_ad_off[a];
+            j.ad_off = h_ad_off[a];
+            j.out_idx = (int32_t)((s - s0) * n_adapters + a);
+            size_t tb = (((size_t)(j.n + 1) * (size_t)(j.m + 1) + 3) & ~(size_t)3) + (size_t)(j.m + 1) * 8;
+            tb = (tb + 15) & ~(size_t)15;
+            if (tb > (64ull << 30)) return fail(PB200_ERR_ARG, "alignment too large for the generic int32 path");
+            if (used + tb > budget && !jobs.empty()) { if (int rc = flush()) return rc; }
+            j.scratch_off = (int64_t)used;
+            used += tb;
+            jobs.push_back(j);
+        }
+    }
+    return flush();
+}
+
+// Cross product of sequences [s0, s0+cnt) (already encoded on the device, offsets on the device) with all adapters.
+// d_seq_off points at the offset of sequence s0 (cnt+1 entries), base_off is subtracted from every offset.
+int run_cross_chunk(Engine &E, Stage &S, cudaStream_t stream, const AdapterPlan &P, const uint8_t *seq_codes,
+                    const int64_t *d_seq_off, int64_t cnt, int64_t base_off, int64_t max_n, int32_t n_adapters,
+                    int32_t *d_out, const int64_t *h_seq_off_abs, int64_t s0, const int32_t *h_ad_off) {
+    if (int rc = S.misc.ensure(64)) return rc;
+    int *status = S.misc.as<int>();
+    unsigned long long *counter = reinterpret_cast<unsigned long long *>(S.misc.as<char>() + 16);
+    size_t cls_pos = 0;
+    for (const ClassPlan &C : P.classes) {
+        const int32_t *d_cls = E.cls_ad.as<int32_t>() + cls_pos;
+        cls_pos += C.ad_ids.size();
+        if (C.cls == 4) {
+            if (!h_seq_off_abs) return fail(PB200_ERR_INTERNAL, "generic class needs host offsets");
+            if (int rc = run_generic_cross(E, S, stream, C, h_seq_off_abs, s0, cnt, base_off, h_ad_off, n_adapters, seq_codes,
+                                           E.ad_codes.as<uint8_t>(), P.sc, d_out)) return rc;
+            continue;
+        }
+        const int64_t n_tasks = cnt * (int64_t)C.ad_ids.size();
+        if (n_tasks == 0) continue;
+        if (int rc = S.tasks.ensure((size_t)n_tasks * sizeof(Task))) return rc;
+        {
+            int64_t blocks = (n_tasks + 255) / 256;
+            build_tasks_cross_kernel<<<(unsigned)blocks, 256, 0, stream>>>(S.tasks.as<Task>(), n_tasks, d_cls,
+                                                                            (int)C.ad_ids.size(), cnt, d_seq_off,
+                                                                            E.ad_off.as<int32_t>(), n_adapters);
+            g_launches++;
+            CK(cudaGetLastError());
+        }
+        (void)base_off;
+        if (int rc = run_class_tasks(E, S, stream, C.cls, C.m_max, n_tasks, max_n, seq_codes, E.ad_codes.as<uint8_t>(), P.sc,
+                                     P.si, d_out, status, counter)) return rc;
+    }
+    return 0;
+}
+
+int check_status(Stage &S, cudaStream_t stream) {
+    int st = 0;
+    CK(cudaMemcpyAsync(&st, S.misc.p, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if (st) return fail(PB200_ERR_INTERNAL, "traceback left its window (window bound violated)");
+    return 0;
+}
+
+// seq_off rebasing kernel: offsets of a chunk relative to its first byte
+__global__ void rebase_kernel(int64_t *off, int64_t n, int64_t base) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) off[i] -= base;
+}
+
+int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, const uint8_t *adapters,
+               const int32_t *ad_off, int32_t n_adapters, const int32_t *pair_seq, const int32_t *pair_adapter,
+               int64_t n_pairs, int ma, int mi, int go, int ge, int32_t *out) {
+    if (n_seqs < 0 || n_adapters < 0 || n_pairs < 0) return fail(PB200_ERR_ARG, "negative count");
+    if ((pair_seq == nullptr) != (pair_adapter == nullptr)) return fail(PB200_ERR_ARG, "pair_seq/pair_adapter must both be given or both NULL");
+    const bool cross = pair_seq == nullptr;
+    if (cross && n_pairs != n_seqs * (int64_t)n_adapters) return fail(PB200_ERR_ARG, "cross mode: n_pairs != n_seqs*n_adapters");
+    if (n_pairs == 0) return 0;
+    if (!seq_off || !ad_off || !out) return fail(PB200_ERR_ARG, "NULL pointer");
+    Engine *Ep = nullptr;
+    if (int rc = get_engine(&Ep)) return rc;
+    Engine &E = *Ep;
+    std::lock_guard<std::mutex> lk(E.mu);
+    if (int rc = E.init()) return rc;
+
+    AdapterPlan P;
+    if (int rc = plan_adapters(E, E.st[0].stream, adapters, ad_off, n_adapters, ma, mi, go, ge, P)) return rc;
+
+    for (int i = 0; i < NSTAGE; ++i) {
+        if (int rc = E.st[i].misc.ensure(64)) return rc;
+        CK(cudaMemsetAsync(E.st[i].misc.p, 0, 64, E.st[i].stream));
+    }
+    if (cross) {
+        // chunk over sequences; ring of NSTAGE streams so H2D / kernels / D2H of consecutive chunks overlap
+        int64_t s0 = 0;
+        int k = 0;
+        int rc_final = 0;
+        while (s0 < n_seqs) {
+            int64_t max_cnt = std::max<int64_t>(1, g_opt.chunk_tasks / std::max<int32_t>(n_adapters, 1));
+            int64_t s1 = std::min(n_seqs, s0 + max_cnt);
+            // limit bytes per chunk
+            while (s1 > s0 + 1 && seq_off[s1] - seq_off[s0] > g_opt.chunk_bytes) s1 = s0 + std::max<int64_t>(1, (s1 - s0) / 2);
+            const int64_t cnt = s1 - s0;
+            const int64_t base = seq_off[s0];
+            const int64_t bytes = seq_off[s1] - base;
+            int64_t max_n = 0;
+            for (int64_t s = s0; s < s1; ++s) max_n = std::max(max_n, seq_off[s + 1] - seq_off[s]);
+            if (max_n > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
+            Stage &S = E.st[k % NSTAGE];
+            cudaStream_t stream = S.stream;
+            CK(cudaStreamSynchronize(stream));   // previous use of this stage's buffers is complete
+            if (int rc = S.seq_raw.ensure((size_t)bytes + 16)) return rc;
+            if (int rc = S.seq_codes.ensure((size_t)bytes + 16)) return rc;
+            if (int rc = S.seq_off.ensure((size_t)(cnt + 1) * 8)) return rc;
+            if (int rc = S.out.ensure((size_t)cnt * n_adapters * PB_REC * 4)) return rc;
+            if (bytes) CK(cudaMemcpyAsync(S.seq_raw.p, seqs + base, (size_t)bytes, cudaMemcpyHostToDevice, stream));
+            CK(cudaMemcpyAsync(S.seq_off.p, seq_off + s0, (size_t)(cnt + 1) * 8, cudaMemcpyHostToDevice, stream));
+            rebase_kernel<<<(unsigned)((cnt + 1 + 255) / 256), 256, 0, stream>>>(S.seq_off.as<int64_t>(), cnt + 1, base);
+            g_launches++;
+            if (int rc = launch_encode(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
+            if (int rc = run_cross_chunk(E, S, stream, P, S.seq_codes.as<uint8_t>(), S.seq_off.as<int64_t>(), cnt, base, max_n,
+                                         n_adapters, S.out.as<int32_t>(), seq_off, s0, ad_off)) return rc;
+            CK(cudaMemcpyAsync(out + (size_t)s0 * n_adapters * PB_REC, S.out.p, (size_t)cnt * n_adapters * PB_REC * 4,
+                               cudaMemcpyDeviceToHost, stream));
+            s0 = s1;
+            ++k;
+        }
+        for (int i = 0; i < NSTAGE; ++i) {
+            if (E.st[i].misc.p) { if (int rc = check_status(E.st[i], E.st[i].stream)) rc_final = rc; }
+            CK(cudaStreamSynchronize(E.st[i].stream));
+        }
+        return rc_final;
+    }
+
+    // ---- pair-list mode: all sequences resident, pairs ordered per class on the host ----
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        if (pair_seq[p] < 0 || pair_seq[p] >= n_seqs || pair_adapter[p] < 0 || pair_adapter[p] >= n_adapters)
+            return fail(PB200_ERR_ARG, "pair index out of range");
+    }
+    if (n_pairs > 0x7fffffffll) return fail(PB200_ERR_ARG, "pair-list mode supports < 2^31 pairs per call");
+    Stage &S = E.st[0];
+    cudaStream_t stream = S.stream;
+    const int64_t bytes = seq_off[n_seqs];
+    if (int rc = S.seq_raw.ensure((size_t)bytes + 16)) return rc;
+    if (int rc = S.seq_codes.ensure((size_t)bytes + 16)) return rc;
+    if (int rc = S.seq_off.ensure((size_t)(n_seqs + 1) * 8)) return rc;
+    if (int rc = S.out.ensure((size_t)n_pairs * PB_REC * 4)) return rc;
+    if (int rc = S.pair_seq.ensure((size_t)n_pairs * 4)) return rc;
+    if (int rc = S.pair_ad.ensure((size_t)n_pairs * 4)) return rc;
+    if (int rc = S.order.ensure((size_t)n_pairs * 4)) return rc;
+    if (int rc = S.misc.ensure(64)) return rc;
+    CK(cudaMemsetAsync(S.misc.p, 0, 64, stream));
+    if (bytes) CK(cudaMemcpyAsync(S.seq_raw.p, seqs, (size_t)bytes, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(S.seq_off.p, seq_off, (size_t)(n_seqs + 1) * 8, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(S.pair_seq.p, pair_seq, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(S.pair_ad.p, pair_adapter, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, stream));
+    if (int rc = launch_encode(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
+    // class of every adapter, then per-class ordering (adapter, length) so that slot halves have similar shapes
+    std::vector<int> ad_class(n_adapters);
+    for (int a = 0; a < n_adapters; ++a) ad_class[a] = class_of(P.si, ad_off[a + 1] - ad_off[a]);
+    std::vector<std::vector<int32_t>> per_class(5);
+    for (int64_t p = 0; p < n_pairs; ++p) per_class[ad_class[pair_adapter[p]]].push_back((int32_t)p);
+    int *status = S.misc.as<int>();
+    unsigned long long *counter = reinterpret_cast<unsigned long long *>(S.misc.as<char>() + 16);
+    for (int c = 0; c < 5; ++c) {
+        auto &ord = per_class[c];
+        if (ord.empty()) continue;
+        int m_max = 0;
+        int64_t max_n = 0;
+        for (int32_t p : ord) {
+            m_max = std::max(m_max, ad_off[pair_adapter[p] + 1] - ad_off[pair_adapter[p]]);
+            max_n = std::max(max_n, seq_off[pair_seq[p] + 1] - seq_off[pair_seq[p]]);
+        }
+        if (max_n > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
+        if (c == 4) {
+            // generic: reuse the cross helper one pair at a time through a tiny job list
+            std::vector<GenericJob> jobs;
+            size_t used = 0;
+            const size_t budget = 2ull << 30;
+            auto flush = [&]() -> int {
+                if (jobs.empty()) return 0;
+                if (int rc = E.gjobs.ensure(jobs.size() * sizeof(GenericJob))) return rc;
+                if (int rc = E.gscratch.ensure(used + 64)) return rc;
+                CK(cudaMemcpyAsync(E.gjobs.p, jobs.data(), jobs.size() * sizeof(GenericJob), cudaMemcpyHostToDevice, stream));
+                int nb = (int)((jobs.size() + 63) / 64);
+                generic_kernel<<<nb, 64, 0, stream>>>(E.gjobs.as<GenericJob>(), (int)jobs.size(), S.seq_codes.as<uint8_t>(),
+                                                      E.ad_codes.as<uint8_t>(), ma, mi, go, ge, E.gscratch.as<uint8_t>(),
+                                                      S.out.as<int32_t>());
+                g_launches++;
+                CK(cudaGetLastError());
+                CK(cudaStreamSynchronize(stream));
+                jobs.clear(); used = 0;
+                return 0;
+            };
+            for (int32_t p : ord) {
+                GenericJob j;
+                int64_t s = pair_seq[p]; int a = pair_adapter[p];
+                j.seq_off = seq_off[s]; j.n = (int32_t)(seq_off[s + 1] - seq_off[s]);
+                j.m = ad_off[a + 1] - ad_off[a]; j.ad_off = ad_off[a]; j.out_idx = p;
+                size_t tb = (((size_t)(j.n + 1) * (size_t)(j.m + 1) + 3) & ~(size_t)3) + (size_t)(j.m + 1) * 8;
+                tb = (tb + 15) & ~(size_t)15;
+                if (tb > (64ull << 30)) return fail(PB200_ERR_ARG, "alignment too large for the generic int32 path");
+                if (used + tb > budget && !jobs.empty()) { if (int rc = flush()) return rc; }
+                j.scratch_off = (int64_t)used; used += tb;
+                jobs.push_back(j);
+            }
+            if (int rc = flush()) return rc;
+            continue;
+        }
+        std::sort(ord.begin(), ord.end(), [&](int32_t x, int32_t y) {
+            int ax = pair_adapter[x], ay = pair_adapter[y];
+            if (ax != ay) return ax < ay;
+            int64_t nx = seq_off[pair_seq[x] + 1] - seq_off[pair_seq[x]], ny = seq_off[pair_seq[y] + 1] - seq_off[pair_seq[y]];
+            if (nx != ny) return nx < ny;
+            return x < y;
+        });
+        const int64_t n_tasks = (int64_t)ord.size();
+        if (int rc = S.tasks.ensure((size_t)n_tasks * sizeof(Task))) return rc;
+        CK(cudaMemcpyAsync(S.order.p, ord.data(), (size_t)n_tasks * 4, cudaMemcpyHostToDevice, stream));
+        CK(cudaStreamSynchronize(stream));  // ord is pageable and reused per class
+        build_tasks_pairs_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, stream>>>(
+            S.tasks.as<Task>(), n_tasks, S.order.as<int32_t>(), S.pair_seq.as<int32_t>(), S.pair_ad.as<int32_t>(),
+            S.seq_off.as<int64_t>(), E.ad_off.as<int32_t>());
+        g_launches++;
+        CK(cudaGetLastError());
+        if (int rc = run_class_tasks(E, S, stream, c, m_max, n_tasks, max_n, S.seq_codes.as<uint8_t>(), E.ad_codes.as<uint8_t>(),
+                                     P.sc, P.si, S.out.as<int32_t>(), status, counter)) return rc;
+    }
+    CK(cudaMemcpyAsync(out, S.out.p, (size_t)n_pairs * PB_REC * 4, cudaMemcpyDeviceToHost, stream));
+    return check_status(S, stream);
+}
+
+int batch_device(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs, int64_t total_seq_bytes,
+                 int64_t max_seq_len, const uint8_t *adapters, const int32_t *ad_off, int32_t n_adapters, int ma, int mi,
+                 int go, int ge, int32_t *d_out, void *user_stream) {
+    if (n_seqs < 0 || n_adapters < 0 || total_seq_bytes < 0) return fail(PB200_ERR_ARG, "negative count");
+    if (n_seqs == 0 || n_adapters == 0) return 0;
+    if (!d_seq_off || !ad_off || !d_out) return fail(PB200_ERR_ARG, "NULL pointer");
+    Engine *Ep = nullptr;
+    if (int rc = get_engine(&Ep)) return rc;
+    Engine &E = *Ep;
+    std::lock_guard<std::mutex> lk(E.mu);
+    if (int rc = E.init()) return rc;
+    Stage &S = E.st[0];
+    cudaStream_t stream = user_stream ? (cudaStream_t)user_stream : S.stream;
+    AdapterPlan P;
+    if (int rc = plan_adapters(E, stream, adapters, ad_off, n_adapters, ma, mi, go, ge, P)) return rc;
+    if (int rc = S.seq_codes.ensure((size_t)total_seq_bytes + 16)) return rc;
+    if (int rc = launch_encode(stream, d_seqs, S.seq_codes.as<uint8_t>(), total_seq_bytes, E.sm_count)) return rc;
+    if (int rc = S.misc.ensure(64)) return rc;
+    CK(cudaMemsetAsync(S.misc.as<char>() + 16, 0, 48, stream));   // status word (offset 0) is sticky until pb200Synchronize
+    if (max_seq_len < 0) {
+        unsigned long long *d_max = reinterpret_cast<unsigned long long *>(S.misc.as<char>() + 32);
+        CK(cudaMemsetAsync(d_max, 0, 8, stream));
+        int64_t blocks = std::min<int64_t>((n_seqs + 255) / 256, 1024);
+        max_len_kernel<<<(unsigned)blocks, 256, 0, stream>>>(d_seq_off, n_seqs, d_max);
+        g_launches++;
+        unsigned long long h = 0;
+        CK(cudaMemcpyAsync(&h, d_max, 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        max_seq_len = (int64_t)h;
+    }
+    if (max_seq_len > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
+    std::vector<int64_t> h_off;   // only fetched when a generic class exists
+    for (auto &c : P.classes) if (c.cls == 4) {
+        h_off.resize((size_t)n_seqs + 1);
+        CK(cudaMemcpyAsync(h_off.data(), d_seq_off, (size_t)(n_seqs + 1) * 8, cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        break;
+    }
+    int64_t max_cnt = std::max<int64_t>(1, g_opt.chunk_tasks / std::max<int32_t>(n_adapters, 1));
+    for (int64_t s0 = 0; s0 < n_seqs; s0 += max_cnt) {
+        const int64_t cnt = std::min(max_cnt, n_seqs - s0);
+        if (int rc = run_cross_chunk(E, S, stream, P, S.seq_codes.as<uint8_t>(), d_seq_off + s0, cnt, 0, max_seq_len,
+                                     n_adapters, d_out + (size_t)s0 * n_adapters * PB_REC,
+                                     h_off.empty() ? nullptr : h_off.data(), s0, ad_off)) return rc;
+    }
+    return 0;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int adapterAlignmentBatch(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, const uint8_t *adapters,
+                          const int32_t *ad_off, int32_t n_adapters, const int32_t *pair_seq,
+                          const int32_t *pair_adapter, int64_t n_pairs, int ma, int mi, int go, int ge, int32_t *out) {
+    g_err.clear();
+    return batch_host(seqs, seq_off, n_seqs, adapters, ad_off, n_adapters, pair_seq, pair_adapter, n_pairs, ma, mi, go, ge, out);
+}
+
+int adapterAlignmentBatchDevice(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs, int64_t total_seq_bytes,
+                                int64_t max_seq_len, const uint8_t *adapters, const int32_t *ad_off, int32_t n_adapters,
+                                int ma, int mi, int go, int ge, int32_t *d_out, void *stream) {
+    g_err.clear();
+    return batch_device(d_seqs, d_seq_off, n_seqs, total_seq_bytes, max_seq_len, adapters, ad_off, n_adapters, ma, mi, go,
+                        ge, d_out, stream);
+}
+
+int pb200FormatRecord(const int32_t *r, char *buf, int buflen) {
+    int n;
+    if (r[0] == -1 && r[4] == PB_SCORE_EMPTY) {
+        n = snprintf(buf, (size_t)buflen, "-1,0,-1,0,-2147483648,0.000000,0.000000");
+    } else {
+        // the two divisions of porechop/src/alignment.cpp:82,90 in double; 0/0 prints "-nan" like the reference
+        volatile double c1 = (double)r[5], l1 = (double)r[6], c2 = (double)r[7], l2 = (double)r[8];
+        double p1 = 100.0 * c1 / l1, p2 = 100.0 * c2 / l2;
+        n = snprintf(buf, (size_t)buflen, "%d,%d,%d,%d,%d,%f,%f", r[0], r[1], r[2], r[3], r[4], p1, p2);
+    }
+    return (n < 0 || n >= buflen) ? -1 : n;
+}
+
+char *adapterAlignment(char *readSeq, char *adapterSeq, int ma, int mi, int go, int ge) {
+    g_err.clear();
+    const int64_t n = readSeq ? (int64_t)strlen(readSeq) : 0;
+    const int64_t m = adapterSeq ? (int64_t)strlen(adapterSeq) : 0;
+    int32_t rec[PB_REC];
+    if (n == 0 || m == 0) {
+        rec[0] = -1; rec[1] = 0; rec[2] = -1; rec[3] = 0; rec[4] = PB_SCORE_EMPTY; rec[5] = rec[6] = rec[7] = rec[8] = 0;
+    } else {
+        int64_t soff[2] = {0, n};
+        int32_t aoff[2] = {0, (int32_t)m};
+        int rc = batch_host((const uint8_t *)readSeq, soff, 1, (const uint8_t *)adapterSeq, aoff, 1, nullptr, nullptr, 1, ma, mi,
+                            go, ge, rec);
+        if (rc != 0) {
+            fprintf(stderr, "porechop_b200: adapterAlignment failed (%d): %s\n", rc, g_err.c_str());
+            return nullptr;
+        }
+    }
+    char *buf = (char *)malloc(96);
+    if (!buf) return nullptr;
+    if (pb200FormatRecord(rec, buf, 96) < 0) { free(buf); return nullptr; }
+    return buf;
+}
+
+void freeCString(char *p) { free(p); }
+
+int pb200DeviceCount(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int pb200SetDevice(int device) {
+    g_err.clear();
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return fail(PB200_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return 0;
+}
+const char *pb200LastError(void) { return g_err.c_str(); }
+long long pb200KernelLaunches(void) { return g_launches.load(); }
+void pb200TimingEnable(int on) { g_timing.store(on ? 1 : 0); }
+
+int pb200TimingRead(double *ms, long long *launches, double *cells, int reset) {
+    Engine *Ep = nullptr;
+    if (int rc = get_engine(&Ep)) return rc;
+    Engine &E = *Ep;
+    std::lock_guard<std::mutex> lk(E.mu);
+    for (auto &tl : E.timed) {
+        float f = 0.f;
+        if (cudaEventSynchronize(tl.b) == cudaSuccess && cudaEventElapsedTime(&f, tl.a, tl.b) == cudaSuccess) {
+            E.timed_ms_acc += f; E.timed_n_acc++;
+        }
+        cudaEventDestroy(tl.a); cudaEventDestroy(tl.b);
+    }
+    E.timed.clear();
+    if (ms) *ms = E.timed_ms_acc;
+    if (launches) *launches = E.timed_n_acc;
+    if (cells) *cells = E.timed_cells;
+    if (reset) { E.timed_ms_acc = 0; E.timed_n_acc = 0; E.timed_cells = 0; }
+    return 0;
+}
+
+int pb200Synchronize(void) {
+    g_err.clear();
+    Engine *Ep = nullptr;
+    if (int rc = get_engine(&Ep)) return rc;
+    Engine &E = *Ep;
+    std::lock_guard<std::mutex> lk(E.mu);
+    if (!E.init_done) return 0;
+    CK(cudaDeviceSynchronize());
+    int rc_final = 0;
+    for (int i = 0; i < NSTAGE; ++i) {
+        if (!E.st[i].misc.p) continue;
+        if (int rc = check_status(E.st[i], E.st[i].stream)) rc_final = rc;
+        CK(cudaMemsetAsync(E.st[i].misc.p, 0, 4, E.st[i].stream));
+        CK(cudaStreamSynchronize(E.st[i].stream));
+    }
+    return rc_final;
+}
+
+int pb200SetOption(const char *name, const char *value) {
+    load_env_options();
+    if (!name || !value) return PB200_ERR_ARG;
+    if (!strcmp(name, "trace")) {
+        g_opt.trace_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;
+    } else if (!strcmp(name, "direct_max")) g_opt.direct_max = atoll(value);
+    else if (!strcmp(name, "chunk_tasks")) g_opt.chunk_tasks = std::max(1ll, atoll(value));
+    else if (!strcmp(name, "wpb")) g_opt.wpb = atoi(value);
+    else return PB200_ERR_ARG;
+    return 0;
+}
+
+}  // extern "C"

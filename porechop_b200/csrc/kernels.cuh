@@ -1,0 +1,388 @@
+// porechop_b200/csrc/kernels.cuh -- sm_100a kernels of the adapter-alignment engine.
+//
+//   encode_kernel        ASCII -> Dna5 code (seqan/basic/alphabet_residue_tabs.h:113-140), HBM-bound
+//   build_tasks_*        (read, adapter) pairs -> Task records in slot order
+//   trace_kernel<G,R,S>  overlap DP *with* 4-bit trace + in-kernel traceback + statistics (windows)
+//   score_kernel<G,R>    streaming score-only overlap DP with exact scout (long reads), dynamic slot refill
+//   window_tasks_kernel  end cells of the score pass -> bounded-window tasks for trace_kernel
+//   generic_kernel       int32 thread-serial fallback for scoring schemes / adapters outside the int16 domain
+//
+// The arithmetic is in dp_core.cuh (shared with the CPU emulation used by the tests).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "dp_core.cuh"
+
+namespace pb {
+
+constexpr int PB_WARPS_PER_BLOCK = 4;
+constexpr int PB_SCRATCH_WORDS = 32 * 2 * 6;   // ScoutCand per lane per half
+
+// ---------------------------------------------------------------------------------------------------
+// encode: one byte in, one byte out (code << 4).  16 bytes per thread, fully coalesced.
+__device__ __forceinline__ uint32_t encode_word(uint32_t w) {
+    return encode_byte(w & 0xFFu) | (encode_byte((w >> 8) & 0xFFu) << 8) | (encode_byte((w >> 16) & 0xFFu) << 16) |
+           (encode_byte(w >> 24) << 24);
+}
+__global__ void encode_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int64_t n) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
+    for (; i < n; i += stride) {
+        if (i + 16 <= n && ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0) {
+            uint4 v = *reinterpret_cast<const uint4 *>(in + i);
+            v.x = encode_word(v.x); v.y = encode_word(v.y); v.z = encode_word(v.z); v.w = encode_word(v.w);
+            *reinterpret_cast<uint4 *>(out + i) = v;
+        } else {
+            for (int64_t k = i; k < n && k < i + 16; ++k) out[k] = (uint8_t)encode_byte(in[k]);
+        }
+    }
+}
+
+// max sequence length (for planning) -- one int64 atomicMax
+__global__ void max_len_kernel(const int64_t *__restrict__ off, int64_t n, unsigned long long *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0;
+    for (; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long l = (unsigned long long)(off[i + 1] - off[i]);
+        v = l > v ? l : v;
+    }
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Task construction.
+// Cross mode: every sequence x every adapter of one class.  `cls_ad` lists the class's adapter ids sorted
+// by length; adapters 2q and 2q+1 share a slot (same read, two adapters); an odd last adapter pairs two
+// consecutive reads instead.  Task index layout: pair q occupies [q*2*n_seqs, (q+1)*2*n_seqs) as
+// (s0,a),(s0,a'),(s1,a),(s1,a')...; the odd adapter occupies the tail [n_pairs*2*n_seqs, +n_seqs).
+__global__ void build_tasks_cross_kernel(Task *__restrict__ tasks, int64_t n_tasks, const int32_t *__restrict__ cls_ad,
+                                         int n_cls_ad, int64_t n_seqs, const int64_t *__restrict__ seq_off,
+                                         const int32_t *__restrict__ ad_off, int n_adapters) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_tasks) return;
+    const int n_full = n_cls_ad / 2;
+    const int64_t paired = (int64_t)n_full * 2 * n_seqs;
+    int64_t s; int a;
+    if (k < paired) {
+        int64_t q = k / (2 * n_seqs), rem = k % (2 * n_seqs);
+        s = rem >> 1; a = cls_ad[2 * q + (rem & 1)];
+    } else {
+        s = k - paired; a = cls_ad[n_cls_ad - 1];
+    }
+    Task t;
+    t.seq_off = seq_off[s];
+    t.n = (int32_t)(seq_off[s + 1] - seq_off[s]);
+    t.m = ad_off[a + 1] - ad_off[a];
+    t.ad_off = ad_off[a];
+    t.out_idx = (int32_t)(s * n_adapters + a);
+    t.flags = 0; t.end_j = 0; t.end_i = 0; t.end_corr = 0; t.end_score = 0;
+    t.col0 = 0; t.n_total = t.n; t.pad0 = t.pad1 = t.pad2 = 0;
+    tasks[k] = t;
+}
+// Pair-list mode: `order` is the host-computed slot order of pair indices for one class.
+__global__ void build_tasks_pairs_kernel(Task *__restrict__ tasks, int64_t n_tasks, const int32_t *__restrict__ order,
+                                         const int32_t *__restrict__ pair_seq, const int32_t *__restrict__ pair_ad,
+                                         const int64_t *__restrict__ seq_off, const int32_t *__restrict__ ad_off) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_tasks) return;
+    int32_t p = order[k];
+    int64_t s = pair_seq[p]; int a = pair_ad[p];
+    Task t;
+    t.seq_off = seq_off[s];
+    t.n = (int32_t)(seq_off[s + 1] - seq_off[s]);
+    t.m = ad_off[a + 1] - ad_off[a];
+    t.ad_off = ad_off[a];
+    t.out_idx = p;
+    t.flags = 0; t.end_j = 0; t.end_i = 0; t.end_corr = 0; t.end_score = 0;
+    t.col0 = 0; t.n_total = t.n; t.pad0 = t.pad1 = t.pad2 = 0;
+    tasks[k] = t;
+}
+
+// Score pass results -> windowed tasks.  The traced path has score >= 0, hence at most m diagonals and
+// floor(m*max(ma,mi,0)/min(|go|,|ge|)) read-only gap columns: it starts no further than `wbound(m)` columns
+// left of its end (DESIGN.md "window bound").  wnum/wden: W = m + (m*wnum)/wden.
+__global__ void window_tasks_kernel(const Task *__restrict__ in, const EndCell *__restrict__ ends, Task *__restrict__ out,
+                                    int64_t n_tasks, int wnum, int wden) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_tasks) return;
+    Task t = in[k];
+    EndCell e = ends[k];
+    if (t.n > 0 && t.m > 0) {
+        int64_t W = (int64_t)t.m + ((int64_t)t.m * wnum) / wden;
+        int64_t c0 = (int64_t)e.j - W;
+        if (c0 < 0) c0 = 0;
+        t.col0 = (int32_t)c0;
+        t.seq_off += c0;
+        t.n = e.j - (int32_t)c0;
+        t.flags = TASK_END_GIVEN | (c0 > 0 ? TASK_LEFT_INF : 0);
+        t.end_j = t.n; t.end_i = e.i; t.end_corr = e.corr; t.end_score = e.score;
+    }
+    out[k] = t;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Task load_task(const Task *__restrict__ tasks, int64_t idx, int64_t n_tasks) {
+    Task t;
+    if (idx < n_tasks) {
+        const int4 *p = reinterpret_cast<const int4 *>(tasks + idx);
+        int4 *q = reinterpret_cast<int4 *>(&t);
+        q[0] = __ldg(p); q[1] = __ldg(p + 1); q[2] = __ldg(p + 2); q[3] = __ldg(p + 3);
+    } else {
+        t.seq_off = 0; t.n = 0; t.m = 0; t.ad_off = 0; t.out_idx = -1; t.flags = 0; t.end_j = 0; t.end_i = 0;
+        t.end_corr = 0; t.end_score = 0; t.col0 = 0; t.n_total = 0; t.pad0 = t.pad1 = t.pad2 = 0;
+    }
+    return t;
+}
+
+__device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
+    // byte1 <- bA, byte3 <- bB (code<<4 in a byte becomes code<<12 in each half)
+    return __byte_perm(bA, bB, 0x4101);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// trace_kernel: one group of G lanes per slot (two alignments in the s16x2 halves), 32/G slots per warp.
+// Forward wavefront with a 4-bit trace per cell (one 32-bit word per lane per step for R=4) written to a
+// warp-private trace region (shared memory when it fits, else a per-warp global scratch region that stays
+// in L2), then traceback + statistics by two lanes of the group, 9-int record per alignment.
+// Grid-stride over "warp slots" so the trace scratch is bounded by the resident grid.
+template <int G, int R, bool SMEM_TRACE>
+__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32)
+trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__restrict__ seq,
+             const uint8_t *__restrict__ ads, Scoring sc, int32_t *__restrict__ out, uint32_t *__restrict__ gtrace,
+             int max_steps, int max_n, int *__restrict__ status) {
+    constexpr int SPW = 32 / G;
+    constexpr int WPS = TraceWords<R>::value;
+    extern __shared__ uint32_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, g = lane % G;
+    const int warps_per_block = blockDim.x >> 5;
+    const int64_t total_warps = (int64_t)gridDim.x * warps_per_block;
+    const int64_t wglobal = (int64_t)blockIdx.x * warps_per_block + warp;
+    const int64_t n_slots = (n_tasks + 1) / 2;
+    const int64_t n_wslots = (n_slots + SPW - 1) / SPW;
+
+    // shared memory layout per warp: [trace (SMEM_TRACE)] [base staging SPW*max_n words] [scratch]
+    const int trace_words = SMEM_TRACE ? max_steps * WPS * 32 : 0;
+    const int per_warp_words = trace_words + SPW * max_n + PB_SCRATCH_WORDS;
+    uint32_t *wsm = smem + (size_t)warp * per_warp_words;
+    uint32_t *tr = SMEM_TRACE ? wsm : gtrace + (size_t)wglobal * ((size_t)max_steps * WPS * 32);
+    uint32_t *hbuf = wsm + trace_words + grp * max_n;
+    ScoutCand *cand = reinterpret_cast<ScoutCand *>(wsm + trace_words + SPW * max_n);  // [half][lane]
+    const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
+
+    for (int64_t ws = wglobal; ws < n_wslots; ws += total_warps) {
+        const int64_t slot = ws * SPW + grp;
+        const Task tA = load_task(tasks, slot * 2, n_tasks);
+        const Task tB = load_task(tasks, slot * 2 + 1, n_tasks);
+        const HalfGeom gA = make_geom(tA.n, tA.m, R), gB = make_geom(tB.n, tB.m, R);
+        const int nmax = max(tA.n, tB.n);
+        const uint8_t *seqA = seq + tA.seq_off, *seqB = seq + tB.seq_off;
+        const uint8_t *adA = ads + tA.ad_off, *adB = ads + tB.ad_off;
+
+        // stage the packed read bases of the slot's columns (each lane builds every G-th column)
+        for (int c = g; c < nmax; c += G) {
+            uint32_t bA = (c < tA.n) ? (uint32_t)__ldg(seqA + c) : (uint32_t)PB_PAD_H;
+            uint32_t bB = (c < tB.n) ? (uint32_t)__ldg(seqB + c) : (uint32_t)PB_PAD_H;
+            hbuf[c] = pack_bases(bA, bB);
+        }
+        Lane<R> L;
+        lane_init<R>(L, g, adA, tA.m, (tA.flags & TASK_LEFT_INF) != 0, adB, tB.m, (tB.flags & TASK_LEFT_INF) != 0);
+        int T = nmax > 0 ? nmax + G - 1 : 0;
+        T = __reduce_max_sync(0xffffffffu, T);
+        __syncwarp();
+
+        for (int t = 0; t < T; ++t) {
+            uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botS, 1, G);
+            uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
+            if (g == 0) { recvS = 0u; recvV = neg2; }
+            const int j = t - g + 1;
+            if (j >= 1 && j <= nmax) {
+                uint32_t tw[WPS];
+                lane_step<R, true>(L, recvS, recvV, hbuf[j - 1], sc, tw);
+#pragma unroll
+                for (int w = 0; w < WPS; ++w) tr[((size_t)t * WPS + w) * 32 + lane] = tw[w];
+                lane_track<R>(L, g, j, gA, gB);
+            }
+        }
+        // scout candidates -> shared scratch, then lanes g==0 / g==1 finish halves A / B
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            ScoutCand c;
+            c.fcBest = L.fcBest[h]; c.fcI = L.fcI[h]; c.fcCorr = L.fcCorr[h];
+            c.lrBest = L.lrBest[h]; c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
+            cand[h * 32 + lane] = c;
+        }
+        __syncwarp();
+        if (g < 2) {
+            const int h = g;
+            const Task &tk = h ? tB : tA;
+            const HalfGeom &gh = h ? gB : gA;
+            if (tk.out_idx >= 0) {
+                EndCell end;
+                if (tk.flags & TASK_END_GIVEN) {
+                    end.j = tk.end_j; end.i = tk.end_i; end.score = tk.end_score; end.corr = tk.end_corr;
+                    if (tk.n_total <= 0 || tk.m <= 0) end.score = PB_SCORE_EMPTY;
+                } else {
+                    end = scout_combine(cand + h * 32 + grp * G, G, gh);
+                }
+                const uint8_t *sq = h ? seqB : seqA;
+                const uint8_t *ad = h ? adB : adA;
+                const int lane_base = grp * G;
+                auto nib = [&](int jl, int i) -> uint32_t {
+                    const int gg = (i - 1) / R, r = (i - 1) % R;
+                    const int t = jl - 1 + gg;
+                    const uint32_t w = tr[((size_t)t * WPS + trace_word<R>(h, r)) * 32 + lane_base + gg];
+                    return (w >> trace_shift<R>(h, r)) & 15u;
+                };
+                auto eq = [&](int jl, int i) -> bool { return __ldg(sq + jl - 1) == __ldg(ad + i - 1); };
+                int32_t rec[PB_REC];
+                int st = traceback_stats(nib, eq, end, sc.linear != 0, tk.col0, tk.n_total, tk.m, rec);
+                if (st) atomicOr(status, 1);
+                int32_t *o = out + (size_t)tk.out_idx * PB_REC;
+#pragma unroll
+                for (int k = 0; k < PB_REC; ++k) o[k] = rec[k];
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// score_kernel: streaming score-only pass for long reads.  Same wavefront, no trace (8 DPX ops per cell
+// pair), exact scout.  Groups pull slots from a global counter and refill independently, so a warp's
+// groups never wait for each other's read lengths.
+template <int G, int R>
+__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32)
+score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long *__restrict__ counter,
+             const uint8_t *__restrict__ seq, const uint8_t *__restrict__ ads, Scoring sc, EndCell *__restrict__ ends) {
+    __shared__ ScoutCand scratch[PB_WARPS_PER_BLOCK][2 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, g = lane % G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    const int64_t n_slots = (n_tasks + 1) / 2;
+    const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
+    ScoutCand *cand = scratch[warp];
+
+    Lane<R> L;
+    Task tA, tB;
+    HalfGeom gA, gB;
+    const uint8_t *seqA = seq, *seqB = seq;
+    int64_t slot = -1;
+    int nmax = 0, T = 0, t = 0;
+    bool exhausted = false;
+    tA.n = tB.n = 0;
+    L.botS = 0; L.botV = neg2;
+
+    for (;;) {
+        if (t >= T && !exhausted) {            // group-uniform: this group's slot is finished (or none yet)
+            if (slot >= 0) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    ScoutCand c;
+                    c.fcBest = L.fcBest[h]; c.fcI = L.fcI[h]; c.fcCorr = L.fcCorr[h];
+                    c.lrBest = L.lrBest[h]; c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
+                    cand[h * 32 + lane] = c;
+                }
+                __syncwarp(gmask);
+                if (g < 2) {
+                    const int64_t ti = slot * 2 + g;
+                    if (ti < n_tasks) ends[ti] = scout_combine(cand + g * 32 + grp * G, G, g ? gB : gA);
+                }
+                __syncwarp(gmask);
+            }
+            unsigned long long s = 0;
+            if (g == 0) s = atomicAdd(counter, 1ull);
+            s = __shfl_sync(gmask, s, 0, G);
+            if ((int64_t)s >= n_slots) {
+                exhausted = true; slot = -1; T = 0; t = 0; nmax = 0;
+            } else {
+                slot = (int64_t)s;
+                tA = load_task(tasks, slot * 2, n_tasks);
+                tB = load_task(tasks, slot * 2 + 1, n_tasks);
+                gA = make_geom(tA.n, tA.m, R); gB = make_geom(tB.n, tB.m, R);
+                nmax = max(tA.n, tB.n);
+                seqA = seq + tA.seq_off; seqB = seq + tB.seq_off;
+                lane_init<R>(L, g, ads + tA.ad_off, tA.m, false, ads + tB.ad_off, tB.m, false);
+                T = nmax + G - 1; t = 0;
+            }
+        }
+        if (__all_sync(0xffffffffu, exhausted)) break;
+        uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botS, 1, G);
+        uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
+        if (g == 0) { recvS = 0u; recvV = neg2; }
+        const int j = t - g + 1;
+        if (!exhausted && j >= 1 && j <= nmax) {
+            const int ja = min(j, tA.n) - 1, jb = min(j, tB.n) - 1;
+            uint32_t bA = (ja >= 0) ? (uint32_t)__ldg(seqA + ja) : (uint32_t)PB_PAD_H;
+            uint32_t bB = (jb >= 0) ? (uint32_t)__ldg(seqB + jb) : (uint32_t)PB_PAD_H;
+            lane_step<R, false>(L, recvS, recvV, pack_bases(bA, bB), sc, nullptr);
+            lane_track<R>(L, g, j, gA, gB);
+        }
+        ++t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic_kernel: int32, one thread per alignment, column sweep with S/Hs columns and a byte trace in
+// global scratch.  Only used for inputs outside the int16 domain (huge scores, positive gap scores,
+// adapters longer than 256) -- slow but exact for every scoring scheme the C-ABI accepts.
+struct GenericJob {
+    int64_t seq_off; int32_t n, m, ad_off, out_idx;
+    int64_t scratch_off;   // byte offset of this job's scratch: (n+1)*(m+1) trace bytes, then 2*(m+1) int32
+};
+__global__ void generic_kernel(const GenericJob *__restrict__ jobs, int n_jobs, const uint8_t *__restrict__ seq,
+                               const uint8_t *__restrict__ ads, int ma, int mi, int go, int ge,
+                               uint8_t *__restrict__ scratch, int32_t *__restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_jobs) return;
+    const GenericJob jb = jobs[k];
+    int32_t *o = out + (size_t)jb.out_idx * PB_REC;
+    const int n = jb.n, m = jb.m;
+    if (n <= 0 || m <= 0) {
+        o[0] = -1; o[1] = 0; o[2] = -1; o[3] = 0; o[4] = PB_SCORE_EMPTY; o[5] = o[6] = o[7] = o[8] = 0;
+        return;
+    }
+    const uint8_t *h = seq + jb.seq_off, *v = ads + jb.ad_off;
+    uint8_t *tr = scratch + jb.scratch_off;                       // [(j)*(m+1) + i], flags as in dp_core
+    size_t trbytes = ((size_t)(n + 1) * (size_t)(m + 1) + 3) & ~(size_t)3;
+    int32_t *S = reinterpret_cast<int32_t *>(tr + trbytes);
+    int32_t *Hs = S + (m + 1);
+    const int NEG = -(1 << 30);
+    const bool linear = (go == ge);
+    for (int i = 0; i <= m; ++i) { S[i] = 0; Hs[i] = NEG; }
+    int best = 0, bj = 0, bi = m, bcorr = 0;
+    for (int j = 1; j <= n; ++j) {
+        int diag = 0, up = 0, upV = NEG;
+        const uint8_t hb = h[j - 1];
+        uint8_t *tc = tr + (size_t)j * (m + 1);
+        for (int i = 1; i <= m; ++i) {
+            const int d = diag + ((hb == v[i - 1]) ? ma : mi);
+            int hs, vs, s; uint32_t bits = 0;
+            if (!linear) {
+                const int h_ext = Hs[i] + ge, h_open = S[i] + go;
+                if (h_ext >= h_open) { hs = h_ext; bits |= 8u; } else hs = h_open;
+                const int v_ext = upV + ge, v_open = up + go;
+                if (v_ext >= v_open) { vs = v_ext; bits |= 4u; } else vs = v_open;
+            } else {
+                hs = S[i] + ge; vs = up + ge;
+            }
+            int gm;
+            if (vs >= hs) { gm = vs; bits |= 2u; } else gm = hs;
+            if (d >= gm) { s = d; bits |= 1u; } else s = gm;
+            diag = S[i]; S[i] = s; Hs[i] = hs; up = s; upV = vs;
+            tc[i] = (uint8_t)bits;
+            if ((j == n) || (i == m)) {
+                if (s > best) { best = s; bj = j; bi = i; bcorr = (vs == s ? 1 : 0) | (hs == s ? 2 : 0); }
+            }
+        }
+    }
+    EndCell end; end.j = bj; end.i = bi; end.score = best; end.corr = bcorr;
+    auto nib = [&](int jl, int i) -> uint32_t { return tr[(size_t)jl * (m + 1) + i]; };
+    auto eq = [&](int jl, int i) -> bool { return h[jl - 1] == v[i - 1]; };
+    int32_t rec[PB_REC];
+    traceback_stats(nib, eq, end, linear, 0, n, m, rec);
+    for (int q = 0; q < PB_REC; ++q) o[q] = rec[q];
+}
+
+}  // namespace pb

@@ -1,0 +1,171 @@
+// tests/emu/emu_group.cpp -- CPU emulation of one sub-warp group of the CUDA kernels (TEST ONLY).
+//
+// Runs the *product's own* device code of porechop_b200/csrc/dp_core.cuh (lane_init / lane_step /
+// lane_track / scout_combine / traceback_stats compile as plain C++ here) lane by lane, replacing only the
+// warp shuffle and the shared-memory trace addressing of kernels.cuh.  This lets the no-GPU test tier check
+// the wavefront indexing, the 4-bit trace packing, the scout, the traceback and the statistics -- including
+// the two-pass (score pass + bounded window) scheme -- against the oracle.  It is not a CPU fallback: the
+// product never builds or loads this file.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "../../porechop_b200/csrc/dp_core.cuh"
+
+using namespace pb;
+
+namespace {
+
+struct Half {
+    std::vector<uint8_t> seq, ad;   // encoded
+    Task t;
+};
+
+template <int R>
+void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int32_t *recA, int32_t *recB, int *status) {
+    const int WPS = TraceWords<R>::value;
+    const Task &tA = A.t, &tB = B.t;
+    HalfGeom gA = make_geom(tA.n, tA.m, R), gB = make_geom(tB.n, tB.m, R);
+    const int nmax = std::max(tA.n, tB.n);
+    const int T = nmax > 0 ? nmax + G - 1 : 0;
+    const uint8_t *seqA = A.seq.data() + tA.seq_off, *seqB = B.seq.data() + tB.seq_off;
+    const uint8_t *adA = A.ad.data() + tA.ad_off, *adB = B.ad.data() + tB.ad_off;
+    std::vector<uint32_t> hbuf((size_t)std::max(nmax, 1));
+    for (int c = 0; c < nmax; ++c) {
+        uint32_t bA = c < tA.n ? seqA[c] : PB_PAD_H, bB = c < tB.n ? seqB[c] : PB_PAD_H;
+        hbuf[c] = (bA << 8) | (bB << 24);
+    }
+    std::vector<Lane<R>> L((size_t)G);
+    for (int g = 0; g < G; ++g)
+        lane_init<R>(L[g], g, adA, tA.m, (tA.flags & TASK_LEFT_INF) != 0, adB, tB.m, (tB.flags & TASK_LEFT_INF) != 0);
+    std::vector<uint32_t> tr((size_t)std::max(T, 1) * WPS * G, 0u);
+    const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
+    std::vector<uint32_t> sS((size_t)G), sV((size_t)G);
+    for (int t = 0; t < T; ++t) {
+        for (int g = 0; g < G; ++g) { sS[g] = L[g].botS; sV[g] = L[g].botV; }   // shuffle snapshot
+        for (int g = 0; g < G; ++g) {
+            uint32_t recvS = g ? sS[g - 1] : 0u, recvV = g ? sV[g - 1] : neg2;
+            int j = t - g + 1;
+            if (j >= 1 && j <= nmax) {
+                uint32_t tw[WPS];
+                lane_step<R, true>(L[g], recvS, recvV, hbuf[j - 1], sc, tw);
+                for (int w = 0; w < WPS; ++w) tr[((size_t)t * WPS + w) * G + g] = tw[w];
+                lane_track<R>(L[g], g, j, gA, gB);
+            }
+        }
+    }
+    for (int h = 0; h < 2; ++h) {
+        const Task &tk = h ? tB : tA;
+        const HalfGeom &gh = h ? gB : gA;
+        int32_t *rec = h ? recB : recA;
+        if (tk.out_idx < 0) continue;
+        std::vector<ScoutCand> cand((size_t)G);
+        for (int g = 0; g < G; ++g) {
+            cand[g].fcBest = L[g].fcBest[h]; cand[g].fcI = L[g].fcI[h]; cand[g].fcCorr = L[g].fcCorr[h];
+            cand[g].lrBest = L[g].lrBest[h]; cand[g].lrJ = L[g].lrJ[h]; cand[g].lrCorr = L[g].lrCorr[h];
+        }
+        EndCell end;
+        if (tk.flags & TASK_END_GIVEN) {
+            end.j = tk.end_j; end.i = tk.end_i; end.score = tk.end_score; end.corr = tk.end_corr;
+            if (tk.n_total <= 0 || tk.m <= 0) end.score = PB_SCORE_EMPTY;
+        } else {
+            end = scout_combine(cand.data(), G, gh);
+        }
+        const uint8_t *sq = h ? seqB : seqA;
+        const uint8_t *ad = h ? adB : adA;
+        auto nib = [&](int jl, int i) -> uint32_t {
+            const int gg = (i - 1) / R, r = (i - 1) % R;
+            const int t = jl - 1 + gg;
+            const uint32_t w = tr[((size_t)t * WPS + trace_word<R>(h, r)) * G + gg];
+            return (w >> trace_shift<R>(h, r)) & 15u;
+        };
+        auto eq = [&](int jl, int i) -> bool { return sq[jl - 1] == ad[i - 1]; };
+        int st = traceback_stats(nib, eq, end, sc.linear != 0, tk.col0, tk.n_total, tk.m, rec);
+        if (st) *status |= 1;
+    }
+}
+
+template <int R>
+void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, EndCell *eA, EndCell *eB) {
+    const Task &tA = A.t, &tB = B.t;
+    HalfGeom gA = make_geom(tA.n, tA.m, R), gB = make_geom(tB.n, tB.m, R);
+    const int nmax = std::max(tA.n, tB.n);
+    const int T = nmax + G - 1;
+    const uint8_t *seqA = A.seq.data() + tA.seq_off, *seqB = B.seq.data() + tB.seq_off;
+    std::vector<Lane<R>> L((size_t)G);
+    for (int g = 0; g < G; ++g)
+        lane_init<R>(L[g], g, A.ad.data() + tA.ad_off, tA.m, false, B.ad.data() + tB.ad_off, tB.m, false);
+    const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
+    std::vector<uint32_t> sS((size_t)G), sV((size_t)G);
+    for (int t = 0; t < T; ++t) {
+        for (int g = 0; g < G; ++g) { sS[g] = L[g].botS; sV[g] = L[g].botV; }
+        for (int g = 0; g < G; ++g) {
+            uint32_t recvS = g ? sS[g - 1] : 0u, recvV = g ? sV[g - 1] : neg2;
+            int j = t - g + 1;
+            if (j >= 1 && j <= nmax) {
+                int ja = std::min(j, tA.n) - 1, jb = std::min(j, tB.n) - 1;
+                uint32_t bA = ja >= 0 ? seqA[ja] : PB_PAD_H, bB = jb >= 0 ? seqB[jb] : PB_PAD_H;
+                lane_step<R, false>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr);
+                lane_track<R>(L[g], g, j, gA, gB);
+            }
+        }
+    }
+    for (int h = 0; h < 2; ++h) {
+        std::vector<ScoutCand> cand((size_t)G);
+        for (int g = 0; g < G; ++g) {
+            cand[g].fcBest = L[g].fcBest[h]; cand[g].fcI = L[g].fcI[h]; cand[g].fcCorr = L[g].fcCorr[h];
+            cand[g].lrBest = L[g].lrBest[h]; cand[g].lrJ = L[g].lrJ[h]; cand[g].lrCorr = L[g].lrCorr[h];
+        }
+        *(h ? eB : eA) = scout_combine(cand.data(), G, h ? gB : gA);
+    }
+}
+
+Half make_half(const char *seq, int n, const char *ad, int m, int out_idx) {
+    Half H;
+    H.seq.resize((size_t)std::max(n, 1)); H.ad.resize((size_t)std::max(m, 1));
+    for (int k = 0; k < n; ++k) H.seq[k] = (uint8_t)encode_byte((uint8_t)seq[k]);
+    for (int k = 0; k < m; ++k) H.ad[k] = (uint8_t)encode_byte((uint8_t)ad[k]);
+    Task &t = H.t;
+    memset(&t, 0, sizeof t);
+    t.seq_off = 0; t.n = n; t.m = m; t.ad_off = 0; t.out_idx = out_idx; t.n_total = n;
+    return H;
+}
+
+// same transformation as window_tasks_kernel (kernels.cuh)
+void to_window(Task &t, const EndCell &e, int wnum, int wden) {
+    if (t.n > 0 && t.m > 0) {
+        int64_t W = (int64_t)t.m + ((int64_t)t.m * wnum) / wden;
+        int64_t c0 = (int64_t)e.j - W;
+        if (c0 < 0) c0 = 0;
+        t.col0 = (int32_t)c0; t.seq_off += c0; t.n = e.j - (int32_t)c0;
+        t.flags = TASK_END_GIVEN | (c0 > 0 ? TASK_LEFT_INF : 0);
+        t.end_j = t.n; t.end_i = e.i; t.end_corr = e.corr; t.end_score = e.score;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// mode 0: single trace pass; mode 1: score pass + windowed trace pass (W = m + m*wnum/wden).
+// G in {4,8,16,32}, R in {4,8}; pass nB < 0 to leave half B empty.  Returns the status bit (window violated).
+int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char *seqB, int nB, const char *adB, int mB,
+                   int G, int R, int mode, int ma, int mi, int go, int ge, int wnum, int wden, int32_t *recA,
+                   int32_t *recB) {
+    Scoring sc = make_scoring(ma, mi, go, ge);
+    Half A = make_half(seqA, nA, adA, mA, 0);
+    Half B = nB >= 0 ? make_half(seqB, nB, adB, mB, 1) : make_half("", 0, "", 0, -1);
+    int status = 0;
+    if (mode == 1) {
+        EndCell eA, eB;
+        if (R == 8) run_score_group<8>(G, A, B, sc, &eA, &eB); else run_score_group<4>(G, A, B, sc, &eA, &eB);
+        to_window(A.t, eA, wnum, wden);
+        if (nB >= 0) to_window(B.t, eB, wnum, wden);
+        // the trace pass may use a different (G,R) than the score pass, as in the engine: keep R, G as given
+    }
+    if (R == 8) run_trace_group<8>(G, A, B, sc, recA, recB, &status);
+    else run_trace_group<4>(G, A, B, sc, recA, recB, &status);
+    return status;
+}
+
+}  // extern "C"
