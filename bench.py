@@ -1,0 +1,395 @@
+#!/usr/bin/env python3
+"""
+bench.py -- BASELINE.json metric on B200: reads/s (+ GCUPS) of the adapter-alignment hot path.
+
+Workload (default, BASELINE.json configs[1]): 1 M synthetic ~8 kb ONT reads (seed 20260923), adapter set
+SQK-NSK007 (= the LSK109 Y-adapter), end-trim only: per read the 150-nt start window vs Y_Top (28 nt) and the 150-nt
+end window vs Y_Bottom (22 nt) -> 2 alignments, 7 500 DP cells, 372 algorithmic bytes per read.  A "step" is one pass
+of the hot path over the whole batch (two batched C-ABI calls).  Other workloads: --workload demux (configs[2]) and
+--workload middle (configs[3] sample).
+
+  value   reads/s with the windows already resident in HBM (adapterAlignmentBatchDevice), CUDA-event timed
+  e2e     reads/s through the host-buffer C-ABI call (adapterAlignmentBatch, pinned host buffers): H2D + kernels +
+          D2H inside the timed region; at N>1 the shards' records are also re-gathered to rank 0 over NCCL
+  roofline   dominant kernel (trace_kernel) algorithmic bytes / CUDA-event duration vs the measured HBM peak --
+          reported because the north star asks for it; the kernel is integer-ALU (DPX) bound, see `alu`
+  cpu_baseline / --impl reference   the reference's own C++ (oracle/_ref/cpp_functions.so, falling back to the
+          oracle port) timed by the native harness on all host cores, on a bounded sample of the same pair list
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 via torchrun (one rank per GPU, weak scaling:
+every rank processes its own --reads batch).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='endtrim', choices=['endtrim', 'demux', 'middle'])
+    ap.add_argument('--reads', type=int, default=0, help='reads per rank (default: 1M endtrim, 32k demux, 20k middle)')
+    ap.add_argument('--cpu-sample-reads', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU during the timed regions (NVML; nvidia-smi as fallback)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.sm_max = None
+        self.stop_flag = False
+        self.active = False
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'hw_power_brake': 0x80,
+                 'sw_power_cap': 0x4}
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    try:
+                        r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:
+                        r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+            time.sleep(0.01)
+
+    def summary(self):
+        if not self.samples:
+            try:
+                out = subprocess.check_output(['nvidia-smi', '--query-gpu=clocks.sm,clocks.max.sm', '--format=csv,noheader,nounits',
+                                               '-i', str(self.index)], timeout=20).decode().strip().split(',')
+                return {'sm_mhz': float(out[0]), 'sm_max_mhz': float(out[1]), 'reasons': ['not sampled under load']}
+            except Exception:
+                return {'sm_mhz': None, 'sm_max_mhz': self.sm_max, 'reasons': ['unavailable']}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.sm_max, 'reasons': sorted(self.reasons),
+                'samples': len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def make_workload(args, rank):
+    """Returns a list of batches; each batch = (name, window matrix uint8[n, w] or (buf, off), adapter list)."""
+    from porechop_b200 import workloads as wl
+    seed = wl.SEED + rank
+    if args.workload == 'endtrim':
+        n = args.reads or 1000000
+        yt, yb = wl.nsk007()
+        L, sw, ew = wl.synth_end_windows(n, yt, yb, seed=seed)
+        batches = [('start', wl.windows_to_batch(sw), [yt]), ('end', wl.windows_to_batch(ew), [yb])]
+        desc = '%d synthetic ~8kb reads (lognormal, seed %d), SQK-NSK007 (LSK109 Y-adapter), end-trim: 150x28 + 150x22 per read' % (n, seed)
+    elif args.workload == 'demux':
+        n = args.reads or 32768
+        starts, ends = wl.demux_adapters()
+        L, sw, ew = wl.synth_end_windows(n, starts[100], ends[100], seed=seed)
+        batches = [('start', wl.windows_to_batch(sw), starts), ('end', wl.windows_to_batch(ew), ends)]
+        desc = '%d synthetic reads x 356 adapters (119 sets + 12 native-full + 96 rapid-full), demux end windows' % n
+    else:
+        n = args.reads or 20000
+        yt, yb = wl.nsk007()
+        buf, off = wl.synth_reads(n, yt, yb, seed=seed, chimera_p=0.05)
+        batches = [('middle', (buf, off), [yt, yb])]
+        desc = '%d synthetic full reads (5%% chimeras) x {Y_Top, Y_Bottom}, middle-adapter scan (two-pass)' % n
+    return n, batches, desc
+
+
+def batch_cells(batch):
+    (buf, off), ads = batch[1], batch[2]
+    return int(off[-1] - off[0]) * sum(len(a) for a in ads)
+
+
+def batch_alg_bytes(batch):
+    (buf, off), ads = batch[1], batch[2]
+    n = len(off) - 1
+    return int(off[-1] - off[0]) + sum(len(a) for a in ads) + 36 * n * len(ads)
+
+
+def run_reference_harness(batches, scoring, sample_reads, threads):
+    """Time the reference CPU path (oracle/_ref/cpp_functions.so via the native harness) on the first
+    `sample_reads` reads of every batch.  Returns (seconds, reads, cells, kind)."""
+    from porechop_b200 import workloads as wl
+    lib = os.path.join(ROOT, 'oracle', '_ref', 'cpp_functions.so')
+    kind = 'reference'
+    if not os.path.exists(lib):
+        lib = os.path.join(ROOT, 'oracle', 'liboracle.so')
+        kind = 'port'
+    harness = os.path.join(ROOT, 'oracle', '_ref', 'ref_harness')
+    if not os.path.exists(harness) or not os.path.exists(lib):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle'), 'liboracle.so', 'harness', 'ref'])
+    sec = 0.0
+    cells = 0
+    with tempfile.TemporaryDirectory() as d:
+        for name, (buf, off), ads in batches:
+            k = min(sample_reads, len(off) - 1)
+            abuf, aoff = wl.pack_adapters(ads)
+            p = os.path.join(d, name + '.bin')
+            wl.write_harness_file(p, buf[:off[k]], off[:k + 1], abuf, aoff, scoring)
+            info = json.loads(subprocess.check_output([harness, lib, p, str(threads)]).decode())
+            sec += info['seconds']
+            cells += info['cells']
+    return sec, min(sample_reads, len(batches[0][1][1]) - 1), cells, kind
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    from porechop_b200 import workloads as wl
+    scoring = wl.DEFAULT_SCORING
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        n, batches, desc = make_workload(args, 0)
+        cores = host_cores()
+        per_read_cells = sum(batch_cells(b) for b in batches) / n
+        # bounded sample: ~3 core-seconds per core per step at ~0.08 GCUPS/core
+        sample = args.cpu_sample_reads or int(max(64, min(n, 0.08e9 * 1.5 * cores / per_read_cells)))
+        times = []
+        cells = 0
+        for s in range(args.warmup + args.steps):
+            sec, reads, cells, kind = run_reference_harness(batches, scoring, sample, cores)
+            if s >= args.warmup:
+                times.append(sec)
+        t = float(np.mean(times))
+        value = sample / t
+        line = {'impl': 'reference', 'metric': 'reads/sec', 'value': value, 'unit': 'reads/s', 'n_gpus': args.gpus,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic',
+                'gcups': cells / t / 1e9,
+                'config': {'workload': desc, 'sample': 'first %d reads of the batch per step' % sample},
+                'cpu_baseline': {'value': value, 'unit': 'reads/s', 'cores': cores, 'kind': kind,
+                                 'sample': 'first %d reads (%d alignments) per step, %d threads, native harness over the reference C-ABI' %
+                                           (sample, sample * int(round(per_read_cells / 7500 * 2)) if args.workload == 'endtrim' else sample, cores)},
+                'e2e': {'value': value, 'unit': 'reads/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from porechop_b200 import cpp_function_wrappers as W
+
+    n, batches, desc = make_workload(args, rank)
+    K, Wm = args.steps, args.warmup
+
+    # ---- host (pinned) and device copies of the inputs ----
+    host, dev = [], []
+    for name, (buf, off), ads in batches:
+        abuf, aoff = wl.pack_adapters(ads)
+        hb = torch.empty(len(buf), dtype=torch.uint8, pin_memory=True)
+        hb.numpy()[:] = buf
+        ho = torch.empty(len(off), dtype=torch.int64, pin_memory=True)
+        ho.numpy()[:] = off
+        n_pairs = (len(off) - 1) * len(ads)
+        hout = torch.empty((n_pairs, 9), dtype=torch.int32, pin_memory=True)
+        host.append((hb, ho, abuf, aoff, hout))
+        db, do = hb.cuda(non_blocking=True), ho.cuda(non_blocking=True)
+        dout = torch.empty((n_pairs, 9), dtype=torch.int32, device='cuda')
+        max_len = int(np.max(np.diff(off))) if len(off) > 1 else 0
+        dev.append((db, do, abuf, aoff, dout, max_len))
+    torch.cuda.synchronize()
+    in_bytes = sum(h[0].numel() + h[1].numel() * 8 + len(h[2]) + len(h[3]) * 4 for h in host)
+    out_bytes = sum(h[4].numel() * 4 for h in host)
+    cells_per_step = sum(batch_cells(b) for b in batches)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        s = torch.cuda.current_stream().cuda_stream
+        for db, do, abuf, aoff, dout, max_len in dev:
+            W.adapter_alignment_batch_device(db.data_ptr(), do.data_ptr(), do.numel() - 1, db.numel(), max_len, abuf, aoff,
+                                             scoring, dout.data_ptr(), s)
+
+    gather_bufs = None
+    if world > 1:
+        # rank 0 receives every rank's records: device buckets + one pinned host buffer per batch
+        gather_bufs = []
+        for (hb, ho, abuf, aoff, hout), (db, do, _, _, dout, max_len) in zip(host, dev):
+            if rank == 0:
+                bucket = [torch.empty_like(dout) for _ in range(world)]
+                hall = torch.empty((world,) + tuple(dout.shape), dtype=torch.int32, pin_memory=True)
+            else:
+                bucket, hall = None, None
+            gather_bufs.append((bucket, hall))
+
+    def step_e2e():
+        if world == 1:
+            for hb, ho, abuf, aoff, hout in host:
+                W.adapter_alignment_batch(hb.numpy(), ho.numpy(), abuf, aoff, scoring, out=hout.numpy())
+            return
+        # N > 1: pinned host -> device, device C-ABI, NCCL re-gather of the records to rank 0, one D2H there
+        s = torch.cuda.current_stream().cuda_stream
+        for (hb, ho, abuf, aoff, hout), (db, do, _, _, dout, max_len), (bucket, hall) in zip(host, dev, gather_bufs):
+            db.copy_(hb, non_blocking=True)
+            do.copy_(ho, non_blocking=True)
+            W.adapter_alignment_batch_device(db.data_ptr(), do.data_ptr(), do.numel() - 1, db.numel(), max_len, abuf, aoff,
+                                             scoring, dout.data_ptr(), s)
+            dist.gather(dout, bucket, dst=0)
+            if rank == 0:
+                for r in range(world):
+                    hall[r].copy_(bucket[r], non_blocking=True)
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- value: device-resident ----
+    for _ in range(max(Wm, 3)):
+        step_device()
+    barrier()
+    W.synchronize()
+    W.timing_enable(True)
+    W.timing_read(reset=True)
+    l0 = W.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.active = True
+    barrier()
+    ev0.record()
+    for _ in range(K):
+        step_device()
+    ev1.record()
+    barrier()
+    sampler.active = False
+    launches = W.kernel_launches() - l0
+    dev_ms = ev0.elapsed_time(ev1)
+    W.synchronize()
+    dp_ms, dp_n = W.timing_read(reset=True)
+    W.timing_enable(False)
+
+    # ---- e2e: host buffers through the C-ABI ----
+    for _ in range(max(Wm, 3)):
+        step_e2e()
+    barrier()
+    sampler.active = True
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.active = False
+    sampler.stop_flag = True
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_reads = n * world
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    value = total_reads * K / (dev_ms / 1e3)
+    e2e_value = total_reads * K / (e2e_ms / 1e3)
+    # roofline of the dominant kernel (trace_kernel / score_kernel launches timed by CUDA events in the library)
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    else:
+        peak, peak_src = 6650.0, 'fallback'
+    alg_bytes_step = sum(batch_alg_bytes(b) for b in batches)
+    dp_launch_ms = dp_ms / max(dp_n, 1)
+    launches_per_step = dp_n / K
+    bytes_per_launch = alg_bytes_step / max(launches_per_step, 1e-9)
+    achieved = bytes_per_launch / (dp_launch_ms / 1e3) / 1e9 if dp_n else None
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload)
+        except Exception:
+            traffic = None
+    clocks = sampler.summary()
+    sm_mhz = clocks.get('sm_mhz') or 1965.0
+    gcups_kernel = cells_per_step * K / (dp_ms / 1e3) / 1e9 if dp_n else None
+    line = {
+        'metric': 'reads/sec', 'value': value, 'unit': 'reads/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
+        'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'int16 (s16x2 DPX)', 'data': 'synthetic',
+        'gcups': cells_per_step * world * K / (dev_ms / 1e3) / 1e9,
+        'config': {'workload': desc, 'reads_per_gpu': n, 'alignments_per_read': sum(len(b[2]) for b in batches),
+                   'cells_per_read': cells_per_step / n, 'scoring': list(scoring),
+                   'l2': 'inputs %.0f MB per step exceed the 126 MB L2' % (in_bytes / 1e6)},
+        'e2e': {'value': e2e_value, 'unit': 'reads/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': out_bytes,
+                'ms_per_step': e2e_ms / K, 'gcups': cells_per_step * world * K / (e2e_ms / 1e3) / 1e9,
+                'path': 'adapterAlignmentBatch (host buffers, pinned)' if world == 1 else
+                        'pinned H2D + adapterAlignmentBatchDevice + NCCL gather of records to rank 0 + D2H'},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': (achieved / peak) if achieved else None, 'traffic': traffic, 'peak_source': peak_src,
+                     'kernel': 'trace_kernel (s16x2 wavefront DP + in-kernel traceback)', 'launch_ms': dp_launch_ms,
+                     'launches_per_step': launches_per_step, 'algorithmic_bytes_per_launch': bytes_per_launch,
+                     'note': 'the kernel is integer-ALU (DPX) bound by construction (SURVEY 0.7); see alu'},
+        'alu': {'gcups_kernel': gcups_kernel, 'sm_mhz': sm_mhz,
+                'lane_instr_peak_per_s': 148 * 4 * 32 * sm_mhz * 1e6,
+                'cells_per_lane_instr': (gcups_kernel * 1e9) / (148 * 4 * 32 * sm_mhz * 1e6) if gcups_kernel else None},
+        'clocks': clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        per_read_cells = cells_per_step / n
+        sample = args.cpu_sample_reads or int(max(64, min(n, 0.08e9 * 1.0 * cores * 4 / per_read_cells)))
+        sec, reads, ccells, kind = run_reference_harness(batches, scoring, sample, cores)
+        line['cpu_baseline'] = {'value': sample / sec, 'unit': 'reads/s', 'cores': cores, 'kind': kind,
+                                'gcups': ccells / sec / 1e9,
+                                'sample': 'first %d reads of the same batch (all their alignments), %d threads, native harness '
+                                          'over the reference C-ABI (adapterAlignment+freeCString)' % (sample, cores)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,75 @@
+"""CPU tier: the C-ABI library loads, exports every symbol include/porechop_b200.h declares, formats records like the
+reference, and fails LOUDLY (no CPU fallback) when no CUDA device is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, load_golden, oracle_record
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, 'include', 'porechop_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b([A-Za-z_][A-Za-z0-9_]*)\s*\(', src)) - {'defined'})
+
+
+def test_library_exports_every_declared_symbol():
+    from porechop_b200 import cpp_function_wrappers as W
+    names = header_functions()
+    assert 'adapterAlignment' in names and 'freeCString' in names and 'adapterAlignmentBatch' in names
+    lib = ctypes.CDLL(W.SO_FILE_FULL)
+    for n in names:
+        assert hasattr(lib, n), 'missing export ' + n
+    assert sorted(W.EXPORTED_SYMBOLS) == names
+
+
+def test_format_record_matches_reference_strings():
+    from porechop_b200 import cpp_function_wrappers as W
+    from porechop_b200.align import record_string
+    for rd, ad, sc, exp in load_golden('golden_random.json')[:600]:
+        rec = oracle_record(rd, ad, sc)
+        assert W.format_record(rec) == exp
+        assert record_string(rec) == exp
+
+
+def test_scores_from_records_equal_reference_parse():
+    from porechop_b200.align import scores_from_records
+    cases = load_golden('golden_random.json')[:800]
+    recs = np.array([oracle_record(rd, ad, sc) for rd, ad, sc, _ in cases], dtype=np.int32)
+    full, part, rs, re_ = scores_from_records(recs)
+    for k, (_, _, _, exp) in enumerate(cases):
+        p = exp.split(',')
+        if int(p[0]) == -1:
+            assert (full[k], part[k], rs[k], re_[k]) == (0.0, 0.0, -1, 0)
+            continue
+        ef, ep = float(p[6]), float(p[5])
+        assert rs[k] == int(p[0]) and re_[k] == int(p[1]) + 1
+        assert (full[k] == ef) or (np.isnan(full[k]) and np.isnan(ef))
+        assert (part[k] == ep) or (np.isnan(part[k]) and np.isnan(ep))
+
+
+def _no_gpu():
+    from porechop_b200 import cpp_function_wrappers as W
+    return W.device_count() == 0
+
+
+@pytest.mark.skipif(not _no_gpu(), reason='a CUDA device is present')
+def test_no_device_fails_loudly_no_cpu_fallback():
+    from porechop_b200 import cpp_function_wrappers as W
+    with pytest.raises(W.EngineError):
+        W.adapter_alignment('ACGT', 'ACGT', [3, -6, -5, -2])
+    buf, off = W.pack_sequences(['ACGTACGT'])
+    abuf, aoff = W.pack_sequences(['ACGT'], offset_dtype=np.int32)
+    with pytest.raises(W.EngineError) as e:
+        W.adapter_alignment_batch(buf, off, abuf, aoff, [3, -6, -5, -2])
+    assert '100' in str(e.value)
+
+
+def test_empty_inputs_need_no_device():
+    # the -1 record of an empty read/adapter is produced without touching the device (reference: no DP either)
+    from porechop_b200 import cpp_function_wrappers as W
+    assert W.adapter_alignment('', 'ACGT', [3, -6, -5, -2]) == '-1,0,-1,0,-2147483648,0.000000,0.000000'
+    assert W.adapter_alignment('ACGT', '', [3, -6, -5, -2]) == '-1,0,-1,0,-2147483648,0.000000,0.000000'

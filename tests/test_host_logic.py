@@ -1,0 +1,100 @@
+"""CPU tier: host-side logic -- workloads, packing, the native reference harness, sharding + gather (gloo, 2 ranks)."""
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, oracle_batch, oracle_string
+
+
+def test_workload_determinism_and_shapes():
+    from porechop_b200 import workloads as W
+    yt, yb = W.nsk007()
+    assert (len(yt), len(yb)) == (28, 22)
+    L1, s1, e1 = W.synth_end_windows(2000, yt, yb)
+    L2, s2, e2 = W.synth_end_windows(2000, yt, yb)
+    assert np.array_equal(L1, L2) and np.array_equal(s1, s2) and np.array_equal(e1, e2)
+    assert s1.shape == (2000, 150) and set(np.unique(s1)) <= set(b'ACGT')
+    assert 6000 < L1.mean() < 10000
+    starts, ends = W.demux_adapters()
+    assert (len(starts), len(ends)) == (227, 129)
+    assert sum(map(len, starts)) + sum(map(len, ends)) == 17975
+    # implanted adapters are found by the oracle in most start windows
+    hits = 0
+    for k in range(60):
+        p = oracle_string(bytes(s1[k]).decode(), yt).split(',')
+        hits += float(p[5]) > 75.0 and int(p[0]) == 0
+    assert hits > 25
+
+
+def test_pack_sequences_roundtrip():
+    from porechop_b200.cpp_function_wrappers import pack_sequences
+    seqs = ['ACGT', '', 'NNNA', 'acgu-']
+    buf, off = pack_sequences(seqs)
+    assert [bytes(buf[off[i]:off[i + 1]]).decode() for i in range(4)] == seqs
+
+
+def test_reference_harness_matches_oracle_batch():
+    from porechop_b200 import workloads as W
+    yt, yb = W.nsk007()
+    _, sw, _ = W.synth_end_windows(64, yt, yb)
+    sbuf, soff = W.windows_to_batch(sw)
+    abuf, aoff = W.pack_adapters([yt, yb])
+    harness = os.path.join(ROOT, 'oracle', '_ref', 'ref_harness')
+    lib = os.path.join(ROOT, 'oracle', '_ref', 'cpp_functions.so')
+    if not os.path.exists(lib):
+        lib = os.path.join(ROOT, 'oracle', 'liboracle.so')
+    with tempfile.TemporaryDirectory() as d:
+        wl, ans = os.path.join(d, 'w.bin'), os.path.join(d, 'a.txt')
+        W.write_harness_file(wl, sbuf, soff, abuf, aoff, W.DEFAULT_SCORING)
+        out = subprocess.check_output([harness, lib, wl, '2', ans]).decode()
+        info = json.loads(out)
+        assert info['pairs'] == 128 and info['cells'] == 64 * 150 * 50
+        got = open(ans).read().split('\n')[:-1]
+    from porechop_b200.align import record_string
+    exp = [record_string(r) for r in oracle_batch(sbuf, soff, abuf, aoff, W.DEFAULT_SCORING)]
+    assert got == exp
+
+
+def test_shard_bounds():
+    from porechop_b200.distributed import shard_bounds, shard_bounds_by_bases
+    assert list(shard_bounds(10, 4)) == [0, 3, 6, 8, 10]
+    off = np.concatenate([[0], np.cumsum([100, 100, 100, 100, 400, 100, 100])])
+    b = shard_bounds_by_bases(off, 2)
+    assert b[0] == 0 and b[-1] == 7 and 4 <= b[1] <= 5
+
+
+def _gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from porechop_b200.distributed import gather_records, shard_bounds
+    n = 11
+    b = shard_bounds(n, world)
+    full = torch.arange(n * 9, dtype=torch.int32).reshape(n, 9)
+    local = full[b[rank]:b[rank + 1]].clone()
+    got = gather_records(local, [int(b[r + 1] - b[r]) for r in range(world)], dst=0)
+    if rank == 0:
+        q.put(bool(torch.equal(got, full)))
+    else:
+        q.put(got is None)
+    dist.destroy_process_group()
+
+
+def test_gather_records_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(res)
