@@ -117,6 +117,9 @@ __global__ void window_tasks_kernel(const Task *__restrict__ in, const EndCell *
         t.n = e.j - (int32_t)c0;
         t.flags = TASK_END_GIVEN | (c0 > 0 ? TASK_LEFT_INF : 0);
         t.end_j = t.n; t.end_i = e.i; t.end_corr = e.corr; t.end_score = e.score;
+    } else {
+        // empty read or adapter: no columns to compute, the trace pass only emits the -1 record
+        t.n = 0; t.flags = TASK_END_GIVEN; t.end_j = 0; t.end_i = 0; t.end_corr = 0; t.end_score = PB_SCORE_EMPTY;
     }
     out[k] = t;
 }

@@ -140,6 +140,8 @@ void to_window(Task &t, const EndCell &e, int wnum, int wden) {
         t.col0 = (int32_t)c0; t.seq_off += c0; t.n = e.j - (int32_t)c0;
         t.flags = TASK_END_GIVEN | (c0 > 0 ? TASK_LEFT_INF : 0);
         t.end_j = t.n; t.end_i = e.i; t.end_corr = e.corr; t.end_score = e.score;
+    } else {
+        t.n = 0; t.flags = TASK_END_GIVEN; t.end_j = 0; t.end_i = 0; t.end_corr = 0; t.end_score = PB_SCORE_EMPTY;
     }
 }
 
