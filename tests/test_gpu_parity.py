@@ -196,8 +196,8 @@ def test_full_size_properties(W):
     assert np.array_equal(a, b)
     assert (a[:, 4] >= 0).all() and (a[:, 6] >= 0).all() and (a[:, 5] <= np.maximum(a[:, 6], 0)).all()
     assert (a[:, 3] <= 27).all() and (a[:, 1] <= 149).all()
-    strong = a[:, 7] * 100 >= 90 * a[:, 8]
-    assert 0.2 < strong.mean() < 0.9          # ~80 % of reads carry a (mutated) start adapter
+    strong = a[:, 7] * 100 >= 60 * a[:, 8]
+    assert 0.7 < strong.mean() < 0.9          # ~80 % of reads carry a (mutated, truncated) start adapter
     idx = np.arange(0, n, 100)
     sub = sw[idx]
     s2, o2 = wl.windows_to_batch(sub)
