@@ -152,91 +152,101 @@ struct EndCell {
 };
 
 // ---- one lane of a group ------------------------------------------------------------------------------
+// Row layout: the G*R rows of a group are BOTTOM-aligned per half: real adapter row i (1..m) lives at group row
+// q = i + pad, pad = G*R - m, so the last row m is always the bottom row of lane G-1 (static register, no
+// per-step row selection for the scout).  The `pad` rows above row 1 reproduce the zero border row without
+// extra instructions: they use per-row score operands (gap-open = -inf, mismatch = 0, a code that matches
+// nothing), so they compute S = 0, Vs = Hs = -inf in every column -- exactly what row 0 presents to row 1.
 template <int R>
 struct Lane {
     uint32_t Sl[R];   // S[j-1][row]   (packed halves), becomes S[j][row] after the step
     uint32_t Hs[R];   // Hs[j-1][row]
-    uint32_t v2[R];   // adapter codes of the owned rows, << PB_CODE_SHIFT, packed halves
+    uint32_t v2[R];   // adapter code << PB_CODE_SHIFT of the owned rows, packed halves
+    uint32_t go2[R];  // per-row gap-open operand   (pad rows: PB_NEG16)
+    uint32_t sf2[R];  // per-row mismatch operand   (pad rows: 0)
     uint32_t Vr[R];   // Vs[j][row] of the step just computed (needed only when a best cell is recorded)
     uint32_t prevRecvS;  // S[j-1][top-1]  (diagonal input of the top row)
     uint32_t botS, botV; // S[j][bottom], Vs[j][bottom] -> shuffled to the next lane
-    // scout state, per half (scalar): last-row running best (meaningful in the lane owning row m) ...
-    int lrBest[2], lrJ[2], lrCorr[2];
-    // ... and the best of this lane's rows in the final column
+    // scout state: last-row running best, packed (meaningful in lane G-1 only) ...
+    uint32_t lrBest2;
+    int lrJ[2], lrCorr[2];
+    // ... and the best of this lane's rows in the final column, per half
     int fcBest[2], fcI[2], fcCorr[2];
 };
 
 // geometry of one half of a slot
 struct HalfGeom {
     int n, m;
-    int gl, rl;   // lane (within group) and local row owning the last row m; gl = -1 when m == 0
+    int pad;      // G*R - m : number of border-emulating rows above row 1
 };
-PB_HD HalfGeom make_geom(int n, int m, int R) {
-    HalfGeom h; h.n = n; h.m = m;
-    if (m > 0) { h.gl = (m - 1) / R; h.rl = (m - 1) % R; } else { h.gl = -1; h.rl = 0; }
+PB_HD HalfGeom make_geom(int n, int m, int G, int R) {
+    HalfGeom h; h.n = n; h.m = m; h.pad = G * R - m;
     return h;
 }
 
-// Encoded adapter byte for row i (1-based) of an m-row adapter, padding beyond m.
-PB_HD uint32_t adapter_byte(const uint8_t *ad, int m, int i) { return (i <= m) ? (uint32_t)ad[i - 1] : (uint32_t)PB_PAD_V; }
-
 template <int R>
-PB_HD void lane_init(Lane<R> &L, int g, const uint8_t *adA, int mA, bool leftInfA,
+PB_HD void lane_init(Lane<R> &L, int g, int G, const Scoring &sc, const uint8_t *adA, int mA, bool leftInfA,
                      const uint8_t *adB, int mB, bool leftInfB) {
-    const uint32_t zero_or_negA = leftInfA ? ((uint32_t)PB_NEG16 & 0xFFFFu) : 0u;
-    const uint32_t zero_or_negB = leftInfB ? (((uint32_t)PB_NEG16 & 0xFFFFu) << 16) : 0u;
-    const uint32_t col0 = zero_or_negA | zero_or_negB;      // S[0][i], i >= 1
+    const uint32_t negh = (uint32_t)PB_NEG16 & 0xFFFFu;
+    const int padA = G * R - mA, padB = G * R - mB;
     const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        int i = g * R + r + 1;
-        L.Sl[r] = col0;
+        const int q = g * R + r + 1;
+        const int iA = q - padA, iB = q - padB;      // real rows (>= 1) or pad rows (<= 0)
+        const bool realA = iA >= 1, realB = iB >= 1;
+        const uint32_t a = realA ? (uint32_t)adA[iA - 1] : (uint32_t)PB_PAD_V;
+        const uint32_t b = realB ? (uint32_t)adB[iB - 1] : (uint32_t)PB_PAD_V;
+        L.v2[r] = (a << 8) | (b << 24);               // code<<4 in a byte -> code<<12 in the half
+        L.go2[r] = (realA ? (sc.go2 & 0xFFFFu) : negh) | (realB ? (sc.go2 & 0xFFFF0000u) : (negh << 16));
+        L.sf2[r] = (realA ? (sc.subF2 & 0xFFFFu) : 0u) | (realB ? (sc.subF2 & 0xFFFF0000u) : 0u);
+        L.Sl[r] = ((realA && leftInfA) ? negh : 0u) | ((realB && leftInfB) ? (negh << 16) : 0u);   // S[0][row]
         L.Hs[r] = neg2;
         L.Vr[r] = neg2;
-        uint32_t a = mA > 0 ? adapter_byte(adA, mA, i) : (uint32_t)PB_PAD_V;
-        uint32_t b = mB > 0 ? adapter_byte(adB, mB, i) : (uint32_t)PB_PAD_V;
-        L.v2[r] = (a << 8) | (b << 24);   // code<<4 in a byte -> code<<12 in the half
     }
-    L.prevRecvS = (g == 0) ? 0u : col0;   // S[0][g*R] ; row 0 is always the zero border
-    L.botS = col0; L.botV = neg2;
+    {   // S[0][row above this lane's top row]: 0 for row 0 / pad rows, the column-0 value otherwise
+        const int q = g * R;
+        const bool realA = (q - padA) >= 1, realB = (q - padB) >= 1;
+        L.prevRecvS = ((realA && leftInfA) ? negh : 0u) | ((realB && leftInfB) ? (negh << 16) : 0u);
+    }
+    L.botS = L.Sl[R - 1]; L.botV = neg2;
+    L.lrBest2 = 0u;                                    // candidate (0, m): value 0
     for (int h = 0; h < 2; ++h) {
-        L.lrBest[h] = 0; L.lrJ[h] = 0; L.lrCorr[h] = 0;         // candidate (0, m): value 0
+        L.lrJ[h] = 0; L.lrCorr[h] = 0;
         L.fcBest[h] = -0x40000000; L.fcI[h] = 0; L.fcCorr[h] = 0;
     }
 }
 
-// One packed cell pair.  TRACE: also produce the 4 trace flags per half:
-//   bit0 tD : diagonal chosen          (g <= d,  ties -> diagonal)
-//   bit1 tM : vertical gap is the max  (vs >= hs, ties -> vertical)
-//   bit2 tV : vertical gap extended    (v_ext >= v_open, ties -> extend)
-//   bit3 tH : horizontal gap extended  (h_ext >= h_open, ties -> extend)
-// flags for half A are returned in bits 0..3 of `bits`, half B in bits 4..7.
-template <bool TRACE>
-PB_HD void cell(uint32_t &Sl, uint32_t &Hs, uint32_t &diag, uint32_t &upS, uint32_t &upV, uint32_t &vrow,
-                uint32_t h2, uint32_t v2, const Scoring &sc, uint32_t &bits) {
-    const uint32_t h_open = add2(Sl, sc.go2);
-    const uint32_t v_open = add2(upS, sc.go2);
-    // substitution score per half: codes equal -> ~(h^v) == -1 -> max(-1 + ma + 1, mi) = ma ; else <= mi
-    const uint32_t nx = ~(h2 ^ v2);
-    const uint32_t sub = addmax2(nx, sc.subA2, sc.subF2);
-    const uint32_t d = add2(diag, sub);
-    uint32_t hs, vs, s;
-    if (TRACE) {
-        bool pHl, pHh, pVl, pVh, pMl, pMh, pDl, pDh;
-        hs = max2p(add2(Hs, sc.ge2), h_open, pHl, pHh);
-        vs = max2p(add2(upV, sc.ge2), v_open, pVl, pVh);
-        const uint32_t gmx = max2p(vs, hs, pMl, pMh);
-        s = max2p(d, gmx, pDl, pDh);
-        bits = (pDl ? 1u : 0u) | (pMl ? 2u : 0u) | (pVl ? 4u : 0u) | (pHl ? 8u : 0u) |
-               (pDh ? 16u : 0u) | (pMh ? 32u : 0u) | (pVh ? 64u : 0u) | (pHh ? 128u : 0u);
-    } else {
-        hs = addmax2(Hs, sc.ge2, h_open);
-        vs = addmax2(upV, sc.ge2, v_open);
-        s = max3(d, vs, hs);
-        bits = 0;
-    }
-    diag = Sl;
-    Sl = s; Hs = hs; upS = s; upV = vs; vrow = vs;
+// ~(a ^ b) as ONE LOP3 (the compiler otherwise splits it into xor + not)
+PB_HD uint32_t xnor2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, 0, 0xC3;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+#else
+    return ~(a ^ b);
+#endif
+}
+
+// max(a, b) per half; adds `clo` / `chi` to acc when a >= b in the low / high half ("first operand wins ties").
+// Device: ptxas fuses this into one VIMNMX.S16x2 with two predicate outputs plus two predicated adds.
+PB_HD uint32_t max2acc(uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, uint32_t &accHi, uint32_t chi) {
+#if defined(__CUDA_ARCH__)
+    uint32_t val;
+    asm("{\n\t.reg .pred plo, phi;\n\t.reg .s16 a0, a1, b0, b1;\n\t"
+        "max.s16x2 %0, %3, %4;\n\t"
+        "mov.b32 {a0, a1}, %0;\n\tmov.b32 {b0, b1}, %3;\n\t"
+        "setp.eq.s16 plo, a0, b0;\n\tsetp.eq.s16 phi, a1, b1;\n\t"
+        "@plo add.u32 %1, %1, %5;\n\t@phi add.u32 %2, %2, %6;\n\t}"
+        : "=r"(val), "+r"(accLo), "+r"(accHi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+    return val;
+#else
+    bool plo, phi;
+    uint32_t v = max2p(a, b, plo, phi);
+    if (plo) accLo += clo;
+    if (phi) accHi += chi;
+    return v;
+#endif
 }
 
 // position of the nibble of (half h, local row r) in the per-step trace words of a lane
@@ -244,31 +254,88 @@ template <int R> PB_HD int trace_word(int h, int r) { return (h * R + r) >> 3; }
 template <int R> PB_HD int trace_shift(int h, int r) { return ((h * R + r) & 7) * 4; }
 template <int R> struct TraceWords { static constexpr int value = (2 * R + 7) / 8; };
 
-// scout bookkeeping after a lane computed column j (1-based, local to the window)
+// One wavefront step of one lane: column j with inputs from the lane above.
+//   recvS/recvV : S[j][top-1], Vs[j][top-1]  (for g == 0 the caller passes the row-0 border: 0 / NEG)
+//   h2          : read bases of column j, encoded << PB_CODE_SHIFT, packed halves
+//   tw          : trace words of this step (TRACE only), TraceWords<R>::value entries.  4 flags per cell:
+//       bit0 tD : diagonal chosen          (g <= d,  ties -> diagonal)
+//       bit1 tM : vertical gap is the max  (vs >= hs, ties -> vertical)
+//       bit2 tV : vertical gap extended    (v_ext >= v_open, ties -> extend)
+//       bit3 tH : horizontal gap extended  (h_ext >= h_open, ties -> extend)
+template <int R, bool TRACE>
+PB_HD void lane_step(Lane<R> &L, uint32_t recvS, uint32_t recvV, uint32_t h2, const Scoring &sc, uint32_t *tw) {
+    uint32_t diag = L.prevRecvS, upS = recvS, upV = recvV;
+    uint32_t accLo = 0u, accHi = 0u;     // R = 4: one word (A in bits 0..15, B in 16..31); R = 8: word 0 = A, word 1 = B
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t h_open = add2(L.Sl[r], L.go2[r]);
+        const uint32_t v_open = add2(upS, L.go2[r]);
+        // substitution score per half: codes equal -> ~(h ^ v) == -1 -> max(-1 + ma + 1, mi) = ma ; else <= mi
+        const uint32_t sub = addmax2(xnor2(h2, L.v2[r]), sc.subA2, L.sf2[r]);
+        const uint32_t d = add2(diag, sub);
+        uint32_t hs, vs, s;
+        if (TRACE) {
+            const uint32_t bl = 1u << trace_shift<R>(0, r);
+            const uint32_t bh = 1u << trace_shift<R>(1, r);
+            hs = max2acc(add2(L.Hs[r], sc.ge2), h_open, accLo, bl << 3, accHi, bh << 3);
+            vs = max2acc(add2(upV, sc.ge2), v_open, accLo, bl << 2, accHi, bh << 2);
+            const uint32_t gmx = max2acc(vs, hs, accLo, bl << 1, accHi, bh << 1);
+            s = max2acc(d, gmx, accLo, bl, accHi, bh);
+        } else {
+            hs = addmax2(L.Hs[r], sc.ge2, h_open);
+            vs = addmax2(upV, sc.ge2, v_open);
+            s = max3(d, vs, hs);
+        }
+        diag = L.Sl[r];
+        L.Sl[r] = s; L.Hs[r] = hs; L.Vr[r] = vs;
+        upS = s; upV = vs;
+    }
+    if (TRACE) {
+        if (TraceWords<R>::value == 1) tw[0] = accLo + accHi; else { tw[0] = accLo; tw[TraceWords<R>::value - 1] = accHi; }
+    }
+    L.prevRecvS = recvS;
+    L.botS = upS; L.botV = upV;
+}
+
+// Scout, fast path: inner columns (j < n for both halves).  Only the bottom row of lane G-1 is the last row, but every
+// lane may run this on its own bottom row -- scout_combine reads lane G-1 only.  One VIMNMX + a rarely taken branch.
 template <int R>
-PB_HD void lane_track(Lane<R> &L, int g, int j, const HalfGeom &A, const HalfGeom &B) {
+PB_HD void lane_track_lastrow(Lane<R> &L, int j) {
+    bool plo, phi;
+    const uint32_t nb = max2p(L.lrBest2, L.botS, plo, phi);     // p = (old best >= candidate): strict '>' replaces
+    if (!(plo && phi)) {
+        L.lrBest2 = nb;
+        if (!plo) {
+            const int c = half16(L.botS, 0);
+            L.lrJ[0] = j; L.lrCorr[0] = (half16(L.botV, 0) == c ? 1 : 0) | (half16(L.Hs[R - 1], 0) == c ? 2 : 0);
+        }
+        if (!phi) {
+            const int c = half16(L.botS, 1);
+            L.lrJ[1] = j; L.lrCorr[1] = (half16(L.botV, 1) == c ? 1 : 0) | (half16(L.Hs[R - 1], 1) == c ? 2 : 0);
+        }
+    }
+}
+
+// Scout, general path: handles halves of different lengths and the final column (every real row of the final
+// column is a candidate, visited top to bottom; dp_scout.h:168-181).
+template <int R>
+PB_HD void lane_track_general(Lane<R> &L, int g, int j, const HalfGeom &A, const HalfGeom &B) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const HalfGeom &H = h ? B : A;
         if (j < H.n) {
-            // last row of an inner column: strict '>' keeps the leftmost best (dp_scout.h:168-181)
-            if (g == H.gl) {
-                uint32_t s2 = L.Sl[0], v2 = L.Vr[0], h2 = L.Hs[0];
-#pragma unroll
-                for (int r = 1; r < R; ++r) if (H.rl == r) { s2 = L.Sl[r]; v2 = L.Vr[r]; h2 = L.Hs[r]; }
-                int c = half16(s2, h);
-                if (c > L.lrBest[h]) {
-                    L.lrBest[h] = c; L.lrJ[h] = j;
-                    L.lrCorr[h] = (half16(v2, h) == c ? 1 : 0) | (half16(h2, h) == c ? 2 : 0);
-                }
+            const int c = half16(L.botS, h);
+            if (c > half16(L.lrBest2, h)) {
+                L.lrBest2 = h ? ((L.lrBest2 & 0xFFFFu) | (L.botS & 0xFFFF0000u)) : ((L.lrBest2 & 0xFFFF0000u) | (L.botS & 0xFFFFu));
+                L.lrJ[h] = j;
+                L.lrCorr[h] = (half16(L.botV, h) == c ? 1 : 0) | (half16(L.Hs[R - 1], h) == c ? 2 : 0);
             }
         } else if (j == H.n) {
-            // final column: every row is a candidate, visited top to bottom
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                int i = g * R + r + 1;
-                if (i <= H.m) {
-                    int c = half16(L.Sl[r], h);
+                const int i = g * R + r + 1 - H.pad;
+                if (i >= 1) {
+                    const int c = half16(L.Sl[r], h);
                     if (c > L.fcBest[h]) {
                         L.fcBest[h] = c; L.fcI[h] = i;
                         L.fcCorr[h] = (half16(L.Vr[r], h) == c ? 1 : 0) | (half16(L.Hs[r], h) == c ? 2 : 0);
@@ -279,37 +346,19 @@ PB_HD void lane_track(Lane<R> &L, int g, int j, const HalfGeom &A, const HalfGeo
     }
 }
 
-// One wavefront step of one lane: column j with inputs from the lane above.
-//   recvS/recvV : S[j][top-1], Vs[j][top-1]  (for g == 0 the caller passes the row-0 border: 0 / NEG)
-//   h2          : read bases of column j, encoded << PB_CODE_SHIFT, packed halves
-//   tw          : trace words of this step (TRACE only), TraceWords<R>::value entries
-template <int R, bool TRACE>
-PB_HD void lane_step(Lane<R> &L, uint32_t recvS, uint32_t recvV, uint32_t h2, const Scoring &sc, uint32_t *tw) {
-    uint32_t diag = L.prevRecvS, upS = recvS, upV = recvV;
-    if (TRACE) {
-#pragma unroll
-        for (int w = 0; w < TraceWords<R>::value; ++w) tw[w] = 0;
-    }
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        uint32_t bits;
-        cell<TRACE>(L.Sl[r], L.Hs[r], diag, upS, upV, L.Vr[r], h2, L.v2[r], sc, bits);
-        if (TRACE) {
-            tw[trace_word<R>(0, r)] |= (bits & 15u) << trace_shift<R>(0, r);
-            tw[trace_word<R>(1, r)] |= (bits >> 4) << trace_shift<R>(1, r);
-        }
-    }
-    L.prevRecvS = recvS;
-    L.botS = upS; L.botV = upV;
-}
-
 // Combine the per-lane scout state of a group into the end cell of half h.
-// `lanes` is indexable [g] -> const Lane<R>& (host: array; device: values gathered from shared memory).
 struct ScoutCand { int fcBest, fcI, fcCorr, lrBest, lrJ, lrCorr; };
+template <int R>
+PB_HD ScoutCand make_cand(const Lane<R> &L, int h) {
+    ScoutCand c;
+    c.fcBest = L.fcBest[h]; c.fcI = L.fcI[h]; c.fcCorr = L.fcCorr[h];
+    c.lrBest = half16(L.lrBest2, h); c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
+    return c;
+}
 PB_HD EndCell scout_combine(const ScoutCand *c, int G, const HalfGeom &H) {
     EndCell e;
     if (H.n <= 0 || H.m <= 0) { e.j = 0; e.i = 0; e.score = PB_SCORE_EMPTY; e.corr = 0; return e; }
-    const ScoutCand &lr = c[H.gl];
+    const ScoutCand &lr = c[G - 1];
     int best = lr.lrBest, bj = lr.lrJ, bi = H.m, corr = lr.lrCorr;
     for (int g = 0; g < G; ++g) {
         if (c[g].fcBest > best) { best = c[g].fcBest; bj = H.n; bi = c[g].fcI; corr = c[g].fcCorr; }

@@ -57,9 +57,11 @@ struct DevBuf {
 struct Options {
     int trace_mode = 0;            // 0 auto, 1 smem, 2 global
     int64_t direct_max = 512;      // longest sequence aligned in a single (trace) pass
-    int64_t chunk_tasks = 8 << 20; // alignments per pipeline chunk
+    int64_t chunk_tasks = 1 << 17; // alignments per pipeline chunk (host-buffer API)
+    int64_t device_chunk_tasks = 8 << 20; // alignments per launch group (device-resident API)
     int64_t chunk_bytes = 1ll << 30;
     int wpb = 0;                   // warps per block override for trace kernel (0 = auto)
+    int trace_r8 = 1;              // 1: trace kernel uses 8 rows per lane (G = 4/8/16/32), 0: 4 rows per lane
 };
 Options g_opt;
 std::once_flag g_opt_once;
@@ -71,6 +73,7 @@ void load_env_options() {
         if (const char *v = getenv("PB200_DIRECT_MAX")) g_opt.direct_max = atoll(v);
         if (const char *v = getenv("PB200_CHUNK_TASKS")) g_opt.chunk_tasks = std::max(1ll, atoll(v));
         if (const char *v = getenv("PB200_WPB")) g_opt.wpb = atoi(v);
+        if (const char *v = getenv("PB200_TRACE_R8")) g_opt.trace_r8 = atoi(v);
     });
 }
 
@@ -246,6 +249,14 @@ int launch_trace(Engine &E, Stage &S, cudaStream_t stream, const Task *tasks, in
 
 int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const Task *tasks, int64_t n_tasks, int max_n,
                        const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
+    if (g_opt.trace_r8) {
+        switch (cls) {
+            case 0: return launch_trace<4, 8>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+            case 1: return launch_trace<8, 8>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+            case 2: return launch_trace<16, 8>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+            case 3: return launch_trace<32, 8>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+        }
+    }
     switch (cls) {
         case 0: return launch_trace<8, 4>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
         case 1: return launch_trace<16, 4>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
@@ -652,7 +663,7 @@ int batch_device(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs
         CK(cudaStreamSynchronize(stream));
         break;
     }
-    int64_t max_cnt = std::max<int64_t>(1, g_opt.chunk_tasks / std::max<int32_t>(n_adapters, 1));
+    int64_t max_cnt = std::max<int64_t>(1, g_opt.device_chunk_tasks / std::max<int32_t>(n_adapters, 1));
     for (int64_t s0 = 0; s0 < n_seqs; s0 += max_cnt) {
         const int64_t cnt = std::min(max_cnt, n_seqs - s0);
         if (int rc = run_cross_chunk(E, S, stream, P, S.seq_codes.as<uint8_t>(), d_seq_off + s0, cnt, 0, max_seq_len,
@@ -781,6 +792,7 @@ int pb200SetOption(const char *name, const char *value) {
     } else if (!strcmp(name, "direct_max")) g_opt.direct_max = atoll(value);
     else if (!strcmp(name, "chunk_tasks")) g_opt.chunk_tasks = std::max(1ll, atoll(value));
     else if (!strcmp(name, "wpb")) g_opt.wpb = atoi(value);
+    else if (!strcmp(name, "trace_r8")) g_opt.trace_r8 = atoi(value);
     else return PB200_ERR_ARG;
     return 0;
 }

@@ -178,7 +178,7 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
         const int64_t slot = ws * SPW + grp;
         const Task tA = load_task(tasks, slot * 2, n_tasks);
         const Task tB = load_task(tasks, slot * 2 + 1, n_tasks);
-        const HalfGeom gA = make_geom(tA.n, tA.m, R), gB = make_geom(tB.n, tB.m, R);
+        const HalfGeom gA = make_geom(tA.n, tA.m, G, R), gB = make_geom(tB.n, tB.m, G, R);
         const int nmax = max(tA.n, tB.n);
         const uint8_t *seqA = seq + tA.seq_off, *seqB = seq + tB.seq_off;
         const uint8_t *adA = ads + tA.ad_off, *adB = ads + tB.ad_off;
@@ -190,11 +190,16 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
             hbuf[c] = pack_bases(bA, bB);
         }
         Lane<R> L;
-        lane_init<R>(L, g, adA, tA.m, (tA.flags & TASK_LEFT_INF) != 0, adB, tB.m, (tB.flags & TASK_LEFT_INF) != 0);
+        lane_init<R>(L, g, G, sc, adA, tA.m, (tA.flags & TASK_LEFT_INF) != 0, adB, tB.m, (tB.flags & TASK_LEFT_INF) != 0);
+        // scout: fast path while both halves are in inner columns; an empty half never limits it
+        const bool emptyA = tA.n <= 0 || tA.m <= 0, emptyB = tB.n <= 0 || tB.m <= 0;
+        const int nmin = emptyA ? tB.n : (emptyB ? tA.n : min(tA.n, tB.n));
+        const bool need_track = !((tA.flags & TASK_END_GIVEN) && (tB.flags & TASK_END_GIVEN));
         int T = nmax > 0 ? nmax + G - 1 : 0;
         T = __reduce_max_sync(0xffffffffu, T);
         __syncwarp();
 
+#pragma unroll 2
         for (int t = 0; t < T; ++t) {
             uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botS, 1, G);
             uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
@@ -205,17 +210,15 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
                 lane_step<R, true>(L, recvS, recvV, hbuf[j - 1], sc, tw);
 #pragma unroll
                 for (int w = 0; w < WPS; ++w) tr[((size_t)t * WPS + w) * 32 + lane] = tw[w];
-                lane_track<R>(L, g, j, gA, gB);
+                if (need_track) {
+                    if (j < nmin) lane_track_lastrow<R>(L, j);
+                    else lane_track_general<R>(L, g, j, gA, gB);
+                }
             }
         }
         // scout candidates -> shared scratch, then lanes g==0 / g==1 finish halves A / B
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            ScoutCand c;
-            c.fcBest = L.fcBest[h]; c.fcI = L.fcI[h]; c.fcCorr = L.fcCorr[h];
-            c.lrBest = L.lrBest[h]; c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
-            cand[h * 32 + lane] = c;
-        }
+        cand[lane] = make_cand<R>(L, 0);
+        cand[32 + lane] = make_cand<R>(L, 1);
         __syncwarp();
         if (g < 2) {
             const int h = g;
@@ -233,7 +236,8 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
                 const uint8_t *ad = h ? adB : adA;
                 const int lane_base = grp * G;
                 auto nib = [&](int jl, int i) -> uint32_t {
-                    const int gg = (i - 1) / R, r = (i - 1) % R;
+                    const int q = i + gh.pad - 1;
+                    const int gg = q / R, r = q % R;
                     const int t = jl - 1 + gg;
                     const uint32_t w = tr[((size_t)t * WPS + trace_word<R>(h, r)) * 32 + lane_base + gg];
                     return (w >> trace_shift<R>(h, r)) & 15u;
@@ -272,7 +276,7 @@ score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long
     HalfGeom gA, gB;
     const uint8_t *seqA = seq, *seqB = seq;
     int64_t slot = -1;
-    int nmax = 0, T = 0, t = 0;
+    int nmax = 0, nmin = 0, T = 0, t = 0;
     bool exhausted = false;
     tA.n = tB.n = 0;
     L.botS = 0; L.botV = neg2;
@@ -280,13 +284,8 @@ score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long
     for (;;) {
         if (t >= T && !exhausted) {            // group-uniform: this group's slot is finished (or none yet)
             if (slot >= 0) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    ScoutCand c;
-                    c.fcBest = L.fcBest[h]; c.fcI = L.fcI[h]; c.fcCorr = L.fcCorr[h];
-                    c.lrBest = L.lrBest[h]; c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
-                    cand[h * 32 + lane] = c;
-                }
+                cand[lane] = make_cand<R>(L, 0);
+                cand[32 + lane] = make_cand<R>(L, 1);
                 __syncwarp(gmask);
                 if (g < 2) {
                     const int64_t ti = slot * 2 + g;
@@ -303,10 +302,14 @@ score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long
                 slot = (int64_t)s;
                 tA = load_task(tasks, slot * 2, n_tasks);
                 tB = load_task(tasks, slot * 2 + 1, n_tasks);
-                gA = make_geom(tA.n, tA.m, R); gB = make_geom(tB.n, tB.m, R);
+                gA = make_geom(tA.n, tA.m, G, R); gB = make_geom(tB.n, tB.m, G, R);
                 nmax = max(tA.n, tB.n);
                 seqA = seq + tA.seq_off; seqB = seq + tB.seq_off;
-                lane_init<R>(L, g, ads + tA.ad_off, tA.m, false, ads + tB.ad_off, tB.m, false);
+                lane_init<R>(L, g, G, sc, ads + tA.ad_off, tA.m, false, ads + tB.ad_off, tB.m, false);
+                {
+                    const bool emptyA = tA.n <= 0 || tA.m <= 0, emptyB = tB.n <= 0 || tB.m <= 0;
+                    nmin = emptyA ? tB.n : (emptyB ? tA.n : min(tA.n, tB.n));
+                }
                 T = nmax + G - 1; t = 0;
             }
         }
@@ -320,7 +323,8 @@ score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long
             uint32_t bA = (ja >= 0) ? (uint32_t)__ldg(seqA + ja) : (uint32_t)PB_PAD_H;
             uint32_t bB = (jb >= 0) ? (uint32_t)__ldg(seqB + jb) : (uint32_t)PB_PAD_H;
             lane_step<R, false>(L, recvS, recvV, pack_bases(bA, bB), sc, nullptr);
-            lane_track<R>(L, g, j, gA, gB);
+            if (j < nmin) lane_track_lastrow<R>(L, j);
+            else lane_track_general<R>(L, g, j, gA, gB);
         }
         ++t;
     }

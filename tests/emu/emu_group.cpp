@@ -25,7 +25,9 @@ template <int R>
 void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int32_t *recA, int32_t *recB, int *status) {
     const int WPS = TraceWords<R>::value;
     const Task &tA = A.t, &tB = B.t;
-    HalfGeom gA = make_geom(tA.n, tA.m, R), gB = make_geom(tB.n, tB.m, R);
+    HalfGeom gA = make_geom(tA.n, tA.m, G, R), gB = make_geom(tB.n, tB.m, G, R);
+    const bool emptyA = tA.n <= 0 || tA.m <= 0, emptyB = tB.n <= 0 || tB.m <= 0;
+    const int nmin = emptyA ? tB.n : (emptyB ? tA.n : std::min(tA.n, tB.n));
     const int nmax = std::max(tA.n, tB.n);
     const int T = nmax > 0 ? nmax + G - 1 : 0;
     const uint8_t *seqA = A.seq.data() + tA.seq_off, *seqB = B.seq.data() + tB.seq_off;
@@ -37,7 +39,7 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
     }
     std::vector<Lane<R>> L((size_t)G);
     for (int g = 0; g < G; ++g)
-        lane_init<R>(L[g], g, adA, tA.m, (tA.flags & TASK_LEFT_INF) != 0, adB, tB.m, (tB.flags & TASK_LEFT_INF) != 0);
+        lane_init<R>(L[g], g, G, sc, adA, tA.m, (tA.flags & TASK_LEFT_INF) != 0, adB, tB.m, (tB.flags & TASK_LEFT_INF) != 0);
     std::vector<uint32_t> tr((size_t)std::max(T, 1) * WPS * G, 0u);
     const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
     std::vector<uint32_t> sS((size_t)G), sV((size_t)G);
@@ -50,7 +52,7 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
                 uint32_t tw[WPS];
                 lane_step<R, true>(L[g], recvS, recvV, hbuf[j - 1], sc, tw);
                 for (int w = 0; w < WPS; ++w) tr[((size_t)t * WPS + w) * G + g] = tw[w];
-                lane_track<R>(L[g], g, j, gA, gB);
+                if (j < nmin) lane_track_lastrow<R>(L[g], j); else lane_track_general<R>(L[g], g, j, gA, gB);
             }
         }
     }
@@ -60,10 +62,7 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
         int32_t *rec = h ? recB : recA;
         if (tk.out_idx < 0) continue;
         std::vector<ScoutCand> cand((size_t)G);
-        for (int g = 0; g < G; ++g) {
-            cand[g].fcBest = L[g].fcBest[h]; cand[g].fcI = L[g].fcI[h]; cand[g].fcCorr = L[g].fcCorr[h];
-            cand[g].lrBest = L[g].lrBest[h]; cand[g].lrJ = L[g].lrJ[h]; cand[g].lrCorr = L[g].lrCorr[h];
-        }
+        for (int g = 0; g < G; ++g) cand[g] = make_cand<R>(L[g], h);
         EndCell end;
         if (tk.flags & TASK_END_GIVEN) {
             end.j = tk.end_j; end.i = tk.end_i; end.score = tk.end_score; end.corr = tk.end_corr;
@@ -74,7 +73,8 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
         const uint8_t *sq = h ? seqB : seqA;
         const uint8_t *ad = h ? adB : adA;
         auto nib = [&](int jl, int i) -> uint32_t {
-            const int gg = (i - 1) / R, r = (i - 1) % R;
+            const int q = i + gh.pad - 1;
+            const int gg = q / R, r = q % R;
             const int t = jl - 1 + gg;
             const uint32_t w = tr[((size_t)t * WPS + trace_word<R>(h, r)) * G + gg];
             return (w >> trace_shift<R>(h, r)) & 15u;
@@ -88,13 +88,15 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
 template <int R>
 void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, EndCell *eA, EndCell *eB) {
     const Task &tA = A.t, &tB = B.t;
-    HalfGeom gA = make_geom(tA.n, tA.m, R), gB = make_geom(tB.n, tB.m, R);
+    HalfGeom gA = make_geom(tA.n, tA.m, G, R), gB = make_geom(tB.n, tB.m, G, R);
+    const bool emptyA = tA.n <= 0 || tA.m <= 0, emptyB = tB.n <= 0 || tB.m <= 0;
+    const int nmin = emptyA ? tB.n : (emptyB ? tA.n : std::min(tA.n, tB.n));
     const int nmax = std::max(tA.n, tB.n);
     const int T = nmax + G - 1;
     const uint8_t *seqA = A.seq.data() + tA.seq_off, *seqB = B.seq.data() + tB.seq_off;
     std::vector<Lane<R>> L((size_t)G);
     for (int g = 0; g < G; ++g)
-        lane_init<R>(L[g], g, A.ad.data() + tA.ad_off, tA.m, false, B.ad.data() + tB.ad_off, tB.m, false);
+        lane_init<R>(L[g], g, G, sc, A.ad.data() + tA.ad_off, tA.m, false, B.ad.data() + tB.ad_off, tB.m, false);
     const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
     std::vector<uint32_t> sS((size_t)G), sV((size_t)G);
     for (int t = 0; t < T; ++t) {
@@ -106,16 +108,13 @@ void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, End
                 int ja = std::min(j, tA.n) - 1, jb = std::min(j, tB.n) - 1;
                 uint32_t bA = ja >= 0 ? seqA[ja] : PB_PAD_H, bB = jb >= 0 ? seqB[jb] : PB_PAD_H;
                 lane_step<R, false>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr);
-                lane_track<R>(L[g], g, j, gA, gB);
+                if (j < nmin) lane_track_lastrow<R>(L[g], j); else lane_track_general<R>(L[g], g, j, gA, gB);
             }
         }
     }
     for (int h = 0; h < 2; ++h) {
         std::vector<ScoutCand> cand((size_t)G);
-        for (int g = 0; g < G; ++g) {
-            cand[g].fcBest = L[g].fcBest[h]; cand[g].fcI = L[g].fcI[h]; cand[g].fcCorr = L[g].fcCorr[h];
-            cand[g].lrBest = L[g].lrBest[h]; cand[g].lrJ = L[g].lrJ[h]; cand[g].lrCorr = L[g].lrCorr[h];
-        }
+        for (int g = 0; g < G; ++g) cand[g] = make_cand<R>(L[g], h);
         *(h ? eB : eA) = scout_combine(cand.data(), G, h ? gB : gA);
     }
 }
