@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return TARGET
     cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-           '-Xcompiler', '-fPIC', '-shared', '-o', TARGET] + SOURCES
+           '-Xcompiler', '-fPIC', '-shared', '-o', TARGET] + os.environ.get('PB200_NVCC_FLAGS', '').split() + SOURCES
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')

@@ -164,7 +164,6 @@ struct Lane {
     uint32_t v2[R];   // adapter code << PB_CODE_SHIFT of the owned rows, packed halves
     uint32_t go2[R];  // per-row gap-open operand   (pad rows: PB_NEG16)
     uint32_t sf2[R];  // per-row mismatch operand   (pad rows: 0)
-    uint32_t Vr[R];   // Vs[j][row] of the step just computed (needed only when a best cell is recorded)
     uint32_t prevRecvS;  // S[j-1][top-1]  (diagonal input of the top row)
     uint32_t botS, botV; // S[j][bottom], Vs[j][bottom] -> shuffled to the next lane
     // scout state: last-row running best, packed (meaningful in lane G-1 only) ...
@@ -202,7 +201,6 @@ PB_HD void lane_init(Lane<R> &L, int g, int G, const Scoring &sc, const uint8_t 
         L.sf2[r] = (realA ? (sc.subF2 & 0xFFFFu) : 0u) | (realB ? (sc.subF2 & 0xFFFF0000u) : 0u);
         L.Sl[r] = ((realA && leftInfA) ? negh : 0u) | ((realB && leftInfB) ? (negh << 16) : 0u);   // S[0][row]
         L.Hs[r] = neg2;
-        L.Vr[r] = neg2;
     }
     {   // S[0][row above this lane's top row]: 0 for row 0 / pad rows, the column-0 value otherwise
         const int q = g * R;
@@ -250,9 +248,10 @@ PB_HD uint32_t max2acc(uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, ui
 }
 
 // position of the nibble of (half h, local row r) in the per-step trace words of a lane
-template <int R> PB_HD int trace_word(int h, int r) { return (h * R + r) >> 3; }
-template <int R> PB_HD int trace_shift(int h, int r) { return ((h * R + r) & 7) * 4; }
-template <int R> struct TraceWords { static constexpr int value = (2 * R + 7) / 8; };
+// R <= 4: one word per step (half A in bits 0..15, half B in bits 16..31); R = 5..8: word 0 = half A, word 1 = half B.
+template <int R> struct TraceWords { static constexpr int value = (R <= 4) ? 1 : 2; };
+template <int R> PB_HD int trace_word(int h, int r) { (void)r; return (R <= 4) ? 0 : h; }
+template <int R> PB_HD int trace_shift(int h, int r) { return (R <= 4) ? (4 * r + 16 * h) : 4 * r; }
 
 // One wavefront step of one lane: column j with inputs from the lane above.
 //   recvS/recvV : S[j][top-1], Vs[j][top-1]  (for g == 0 the caller passes the row-0 border: 0 / NEG)
@@ -262,8 +261,11 @@ template <int R> struct TraceWords { static constexpr int value = (2 * R + 7) / 
 //       bit1 tM : vertical gap is the max  (vs >= hs, ties -> vertical)
 //       bit2 tV : vertical gap extended    (v_ext >= v_open, ties -> extend)
 //       bit3 tH : horizontal gap extended  (h_ext >= h_open, ties -> extend)
-template <int R, bool TRACE>
-PB_HD void lane_step(Lane<R> &L, uint32_t recvS, uint32_t recvV, uint32_t h2, const Scoring &sc, uint32_t *tw) {
+//   vr          : KEEPV only -- Vs[j][row] of every owned row (the final-column scout needs it for the end-cell
+//                 correction flags); the hot path does not keep these 8 registers alive
+template <int R, bool TRACE, bool KEEPV = false>
+PB_HD void lane_step(Lane<R> &L, uint32_t recvS, uint32_t recvV, uint32_t h2, const Scoring &sc, uint32_t *tw,
+                     uint32_t *vr = nullptr) {
     uint32_t diag = L.prevRecvS, upS = recvS, upV = recvV;
     uint32_t accLo = 0u, accHi = 0u;     // R = 4: one word (A in bits 0..15, B in 16..31); R = 8: word 0 = A, word 1 = B
 #pragma unroll
@@ -287,7 +289,8 @@ PB_HD void lane_step(Lane<R> &L, uint32_t recvS, uint32_t recvV, uint32_t h2, co
             s = max3(d, vs, hs);
         }
         diag = L.Sl[r];
-        L.Sl[r] = s; L.Hs[r] = hs; L.Vr[r] = vs;
+        L.Sl[r] = s; L.Hs[r] = hs;
+        if (KEEPV) vr[r] = vs;
         upS = s; upV = vs;
     }
     if (TRACE) {
@@ -319,7 +322,7 @@ PB_HD void lane_track_lastrow(Lane<R> &L, int j) {
 // Scout, general path: handles halves of different lengths and the final column (every real row of the final
 // column is a candidate, visited top to bottom; dp_scout.h:168-181).
 template <int R>
-PB_HD void lane_track_general(Lane<R> &L, int g, int j, const HalfGeom &A, const HalfGeom &B) {
+PB_HD void lane_track_general(Lane<R> &L, int g, int j, const HalfGeom &A, const HalfGeom &B, const uint32_t *vr) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const HalfGeom &H = h ? B : A;
@@ -338,7 +341,7 @@ PB_HD void lane_track_general(Lane<R> &L, int g, int j, const HalfGeom &A, const
                     const int c = half16(L.Sl[r], h);
                     if (c > L.fcBest[h]) {
                         L.fcBest[h] = c; L.fcI[h] = i;
-                        L.fcCorr[h] = (half16(L.Vr[r], h) == c ? 1 : 0) | (half16(L.Hs[r], h) == c ? 2 : 0);
+                        L.fcCorr[h] = (half16(vr[r], h) == c ? 1 : 0) | (half16(L.Hs[r], h) == c ? 2 : 0);
                     }
                 }
             }

@@ -61,7 +61,7 @@ struct Options {
     int64_t device_chunk_tasks = 8 << 20; // alignments per launch group (device-resident API)
     int64_t chunk_bytes = 1ll << 30;
     int wpb = 0;                   // warps per block override for trace kernel (0 = auto)
-    int trace_r8 = 1;              // 1: trace kernel uses 8 rows per lane (G = 4/8/16/32), 0: 4 rows per lane
+    int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
 };
 Options g_opt;
 std::once_flag g_opt_once;
@@ -73,7 +73,7 @@ void load_env_options() {
         if (const char *v = getenv("PB200_DIRECT_MAX")) g_opt.direct_max = atoll(v);
         if (const char *v = getenv("PB200_CHUNK_TASKS")) g_opt.chunk_tasks = std::max(1ll, atoll(v));
         if (const char *v = getenv("PB200_WPB")) g_opt.wpb = atoi(v);
-        if (const char *v = getenv("PB200_TRACE_R8")) g_opt.trace_r8 = atoi(v);
+        if (const char *v = getenv("PB200_HBUF")) g_opt.hbuf_mode = !strcmp(v, "smem") ? 1 : !strcmp(v, "global") ? 2 : 0;
     });
 }
 
@@ -84,7 +84,7 @@ struct Stage {
 };
 
 struct ClassPlan {
-    int cls = 0;                      // 0: m<=32, 1: <=64, 2: <=128, 3: <=256, 4: generic
+    int cls = 0;                      // row-capacity class (class_of); GENERIC_CLASS = int32 fallback
     std::vector<int32_t> ad_ids;      // adapters of the class, sorted by length
     int m_max = 0;
 };
@@ -157,12 +157,17 @@ SchemeInfo scheme_info(int ma, int mi, int go, int ge) {
     return s;
 }
 bool int16_ok(const SchemeInfo &s, int m) { return s.int16_ok_base && (long long)s.A * (m + 3) <= PB_I16_LIMIT; }
+// Row capacity classes: G lanes x R rows per lane.  Class k: G = 4 << (k / 4), R = 5 + (k % 4)  -> capacities
+// 20,24,28,32, 40,48,56,64, 80,96,112,128, 160,192,224,256.  Class 16 = generic int32 fallback.
+constexpr int N_CLASSES = 17;
+constexpr int GENERIC_CLASS = 16;
+int class_G(int k) { return 4 << (k / 4); }
+int class_R(int k) { return 5 + (k % 4); }
 int class_of(const SchemeInfo &s, int m) {
-    if (!int16_ok(s, m) || m > 256) return 4;
-    if (m <= 32) return 0;
-    if (m <= 64) return 1;
-    if (m <= 128) return 2;
-    return 3;
+    if (!int16_ok(s, m) || m > 256) return GENERIC_CLASS;
+    for (int k = 0; k < GENERIC_CLASS; ++k)
+        if (m <= class_G(k) * class_R(k)) return k;
+    return GENERIC_CLASS;
 }
 
 // ---- kernel launch helpers -----------------------------------------------------------------------------
@@ -174,30 +179,33 @@ void timed_end(Engine &E, cudaStream_t s, TimedLaunch &tl, bool on) {
     if (on) { cudaEventRecord(tl.b, s); E.timed.push_back(tl); }
 }
 
-template <int G, int R, bool SM>
+template <int G, int R, bool HS>
 int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const Task *tasks, int64_t n_tasks, int max_n,
-                         const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int wpb,
-                         size_t smem_bytes, int blocks_per_sm, int *status) {
+                         const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
     constexpr int SPW = 32 / G;
     constexpr int WPS = TraceWords<R>::value;
     const int max_steps = max_n + G - 1;
+    const int wpb = PB_WARPS_PER_BLOCK;
+    const size_t smem_bytes = (size_t)wpb * ((HS ? (size_t)SPW * max_n : 0) + PB_SCRATCH_WORDS) * 4;
+    auto kern = trace_kernel<G, R, HS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    int bps = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem_bytes));
+    if (bps < 1) bps = 1;
+    const size_t gwarp_bytes = ((size_t)max_steps * WPS * 32 + (HS ? 0 : (size_t)SPW * max_n)) * 4;
+    // bound the scratch (~12 GB) for very long single-pass alignments
+    int64_t max_warps = std::max<int64_t>(wpb, (int64_t)((12ull << 30) / std::max<size_t>(gwarp_bytes, 1)));
+    while (bps > 1 && (int64_t)bps * E.sm_count * wpb > max_warps) --bps;
     const int64_t n_slots = (n_tasks + 1) / 2;
     const int64_t n_wslots = (n_slots + SPW - 1) / SPW;
     int64_t blocks = (n_wslots + wpb - 1) / wpb;
-    blocks = std::min<int64_t>(blocks, (int64_t)blocks_per_sm * E.sm_count);
+    blocks = std::min<int64_t>(blocks, (int64_t)bps * E.sm_count);
     if (blocks <= 0) return 0;
-    uint32_t *gtrace = nullptr;
-    if (!SM) {
-        size_t bytes = (size_t)blocks * wpb * (size_t)max_steps * WPS * 32 * 4;
-        if (int rc = S.gtrace.ensure(bytes)) return rc;
-        gtrace = S.gtrace.as<uint32_t>();
-    }
-    auto kern = trace_kernel<G, R, SM>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    if (int rc = S.gtrace.ensure((size_t)blocks * wpb * gwarp_bytes)) return rc;
     TimedLaunch tl; bool on;
     timed_begin(E, stream, tl, on);
-    kern<<<(unsigned)blocks, wpb * 32, smem_bytes, stream>>>(tasks, n_tasks, seq_codes, ad_codes, sc, out, gtrace,
-                                                              max_steps, max_n, status);
+    kern<<<(unsigned)blocks, wpb * 32, smem_bytes, stream>>>(tasks, n_tasks, seq_codes, ad_codes, sc, out,
+                                                              S.gtrace.as<uint32_t>(), max_steps, max_n, status);
     timed_end(E, stream, tl, on);
     g_launches++;
     CK(cudaGetLastError());
@@ -208,61 +216,24 @@ template <int G, int R>
 int launch_trace(Engine &E, Stage &S, cudaStream_t stream, const Task *tasks, int64_t n_tasks, int max_n,
                  const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
     constexpr int SPW = 32 / G;
-    constexpr int WPS = TraceWords<R>::value;
     if (max_n < 1) max_n = 1;
-    const int max_steps = max_n + G - 1;
-    const size_t common = (size_t)(SPW * max_n + PB_SCRATCH_WORDS) * 4;
-    const size_t per_warp_sm = (size_t)max_steps * WPS * 32 * 4 + common;
-    // pick warps/block for the shared-memory trace: maximise resident warps per SM
-    int best_w = 0, best_res = 0, best_bps = 0;
-    for (int w = PB_WARPS_PER_BLOCK; w >= 1; --w) {
-        if (g_opt.wpb && w != g_opt.wpb) continue;
-        size_t bytes = per_warp_sm * w;
-        if (bytes > E.smem_optin) continue;
-        int bps = 0;
-        auto kern = trace_kernel<G, R, true>;
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) continue;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, w * 32, bytes) != cudaSuccess) continue;
-        if (bps * w > best_res) { best_res = bps * w; best_w = w; best_bps = bps; }
-    }
-    bool use_sm = best_res >= 6;
-    if (g_opt.trace_mode == 1 && best_res > 0) use_sm = true;
-    if (g_opt.trace_mode == 2) use_sm = false;
-    if (use_sm)
-        return launch_trace_variant<G, R, true>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out,
-                                                best_w, per_warp_sm * best_w, best_bps, status);
-    int w = g_opt.wpb ? g_opt.wpb : PB_WARPS_PER_BLOCK;
-    size_t bytes = common * w;
-    if (bytes > E.smem_optin) return fail(PB200_ERR_ARG, "sequence too long for single-pass alignment");
-    int bps = 0;
-    auto kern = trace_kernel<G, R, false>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, w * 32, bytes));
-    if (bps < 1) bps = 1;
-    // bound the global trace scratch (~8 GB)
-    size_t region = (size_t)max_steps * WPS * 128;
-    int64_t max_warps = std::max<int64_t>(w, (int64_t)((8ull << 30) / std::max<size_t>(region, 1)));
-    while (bps > 1 && (int64_t)bps * E.sm_count * w > max_warps) --bps;
-    return launch_trace_variant<G, R, false>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, w,
-                                             bytes, bps, status);
+    // packed read bases of a slot are staged in shared memory when they fit (<= 12 KB per warp), else in global scratch
+    const bool hs = g_opt.hbuf_mode == 1 ? true : g_opt.hbuf_mode == 2 ? false : ((size_t)SPW * max_n * 4 <= 12288);
+    if (hs && (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + PB_SCRATCH_WORDS) * 4 <= E.smem_optin)
+        return launch_trace_variant<G, R, true>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+    return launch_trace_variant<G, R, false>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
 }
 
 int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const Task *tasks, int64_t n_tasks, int max_n,
                        const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
-    if (g_opt.trace_r8) {
-        switch (cls) {
-            case 0: return launch_trace<4, 8>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
-            case 1: return launch_trace<8, 8>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
-            case 2: return launch_trace<16, 8>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
-            case 3: return launch_trace<32, 8>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
-        }
-    }
+#define PB_CASE(K, GG, RR) case K: return launch_trace<GG, RR>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
     switch (cls) {
-        case 0: return launch_trace<8, 4>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
-        case 1: return launch_trace<16, 4>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
-        case 2: return launch_trace<32, 4>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
-        case 3: return launch_trace<32, 8>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+        PB_CASE(0, 4, 5) PB_CASE(1, 4, 6) PB_CASE(2, 4, 7) PB_CASE(3, 4, 8)
+        PB_CASE(4, 8, 5) PB_CASE(5, 8, 6) PB_CASE(6, 8, 7) PB_CASE(7, 8, 8)
+        PB_CASE(8, 16, 5) PB_CASE(9, 16, 6) PB_CASE(10, 16, 7) PB_CASE(11, 16, 8)
+        PB_CASE(12, 32, 5) PB_CASE(13, 32, 6) PB_CASE(14, 32, 7) PB_CASE(15, 32, 8)
     }
+#undef PB_CASE
     return fail(PB200_ERR_INTERNAL, "bad class");
 }
 
@@ -290,7 +261,7 @@ int launch_score(Engine &E, cudaStream_t stream, const Task *tasks, int64_t n_ta
 int launch_score_class(Engine &E, cudaStream_t stream, int cls, const Task *tasks, int64_t n_tasks,
                        unsigned long long *counter, const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc,
                        EndCell *ends) {
-    switch (cls) {
+    switch (cls / 4) {
         case 0: return launch_score<4, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
         case 1: return launch_score<8, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
         case 2: return launch_score<16, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
@@ -340,8 +311,8 @@ int plan_adapters(Engine &E, cudaStream_t stream, const uint8_t *adapters, const
                   int ma, int mi, int go, int ge, AdapterPlan &P) {
     P.si = scheme_info(ma, mi, go, ge);
     P.sc = make_scoring(ma, mi, go, ge);
-    std::vector<ClassPlan> cl(5);
-    for (int c = 0; c < 5; ++c) cl[c].cls = c;
+    std::vector<ClassPlan> cl(N_CLASSES);
+    for (int c = 0; c < N_CLASSES; ++c) cl[c].cls = c;
     for (int a = 0; a < n_adapters; ++a) {
         int m = ad_off[a + 1] - ad_off[a];
         if (m < 0) return fail(PB200_ERR_ARG, "adapter offsets not monotone");
@@ -425,7 +396,7 @@ int run_cross_chunk(Engine &E, Stage &S, cudaStream_t stream, const AdapterPlan 
     for (const ClassPlan &C : P.classes) {
         const int32_t *d_cls = E.cls_ad.as<int32_t>() + cls_pos;
         cls_pos += C.ad_ids.size();
-        if (C.cls == 4) {
+        if (C.cls == GENERIC_CLASS) {
             if (!h_seq_off_abs) return fail(PB200_ERR_INTERNAL, "generic class needs host offsets");
             if (int rc = run_generic_cross(E, S, stream, C, h_seq_off_abs, s0, cnt, base_off, h_ad_off, n_adapters, seq_codes,
                                            E.ad_codes.as<uint8_t>(), P.sc, d_out)) return rc;
@@ -553,11 +524,11 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
     // class of every adapter, then per-class ordering (adapter, length) so that slot halves have similar shapes
     std::vector<int> ad_class(n_adapters);
     for (int a = 0; a < n_adapters; ++a) ad_class[a] = class_of(P.si, ad_off[a + 1] - ad_off[a]);
-    std::vector<std::vector<int32_t>> per_class(5);
+    std::vector<std::vector<int32_t>> per_class(N_CLASSES);
     for (int64_t p = 0; p < n_pairs; ++p) per_class[ad_class[pair_adapter[p]]].push_back((int32_t)p);
     int *status = S.misc.as<int>();
     unsigned long long *counter = reinterpret_cast<unsigned long long *>(S.misc.as<char>() + 16);
-    for (int c = 0; c < 5; ++c) {
+    for (int c = 0; c < N_CLASSES; ++c) {
         auto &ord = per_class[c];
         if (ord.empty()) continue;
         int m_max = 0;
@@ -567,7 +538,7 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
             max_n = std::max(max_n, seq_off[pair_seq[p] + 1] - seq_off[pair_seq[p]]);
         }
         if (max_n > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
-        if (c == 4) {
+        if (c == GENERIC_CLASS) {
             // generic: reuse the cross helper one pair at a time through a tiny job list
             std::vector<GenericJob> jobs;
             size_t used = 0;
@@ -657,7 +628,7 @@ int batch_device(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs
     }
     if (max_seq_len > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
     std::vector<int64_t> h_off;   // only fetched when a generic class exists
-    for (auto &c : P.classes) if (c.cls == 4) {
+    for (auto &c : P.classes) if (c.cls == GENERIC_CLASS) {
         h_off.resize((size_t)n_seqs + 1);
         CK(cudaMemcpyAsync(h_off.data(), d_seq_off, (size_t)(n_seqs + 1) * 8, cudaMemcpyDeviceToHost, stream));
         CK(cudaStreamSynchronize(stream));
@@ -788,11 +759,11 @@ int pb200SetOption(const char *name, const char *value) {
     load_env_options();
     if (!name || !value) return PB200_ERR_ARG;
     if (!strcmp(name, "trace")) {
-        g_opt.trace_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;
+        g_opt.trace_mode = 0;   // kept for compatibility: the trace always lives in the L2-resident global scratch
     } else if (!strcmp(name, "direct_max")) g_opt.direct_max = atoll(value);
     else if (!strcmp(name, "chunk_tasks")) g_opt.chunk_tasks = std::max(1ll, atoll(value));
     else if (!strcmp(name, "wpb")) g_opt.wpb = atoi(value);
-    else if (!strcmp(name, "trace_r8")) g_opt.trace_r8 = atoi(value);
+    else if (!strcmp(name, "hbuf")) g_opt.hbuf_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;
     else return PB200_ERR_ARG;
     return 0;
 }

@@ -16,6 +16,9 @@
 namespace pb {
 
 constexpr int PB_WARPS_PER_BLOCK = 4;
+#ifndef PB_TRACE_MIN_BLOCKS
+#define PB_TRACE_MIN_BLOCKS 5
+#endif
 constexpr int PB_SCRATCH_WORDS = 32 * 2 * 6;   // ScoutCand per lane per half
 
 // ---------------------------------------------------------------------------------------------------
@@ -144,13 +147,13 @@ __device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// trace_kernel: one group of G lanes per slot (two alignments in the s16x2 halves), 32/G slots per warp.
-// Forward wavefront with a 4-bit trace per cell (one 32-bit word per lane per step for R=4) written to a
-// warp-private trace region (shared memory when it fits, else a per-warp global scratch region that stays
-// in L2), then traceback + statistics by two lanes of the group, 9-int record per alignment.
-// Grid-stride over "warp slots" so the trace scratch is bounded by the resident grid.
-template <int G, int R, bool SMEM_TRACE>
-__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32)
+// trace_kernel: one group of G lanes per slot (two alignments in the s16x2 halves), 32/G slots per warp, R adapter
+// rows per lane (G*R >= adapter length; R = 5..8 so common adapter lengths 22/24/28 waste no rows).
+// Forward wavefront with a 4-bit trace per cell (two 32-bit words per lane per step), then traceback + statistics
+// by two lanes of the group, 9-int record per alignment.  Grid-stride over "warp slots" so the trace scratch is
+// bounded by the resident grid and stays in L2.
+template <int G, int R, bool HBUF_SMEM>
+__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_TRACE_MIN_BLOCKS)
 trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__restrict__ seq,
              const uint8_t *__restrict__ ads, Scoring sc, int32_t *__restrict__ out, uint32_t *__restrict__ gtrace,
              int max_steps, int max_n, int *__restrict__ status) {
@@ -165,36 +168,45 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
     const int64_t n_slots = (n_tasks + 1) / 2;
     const int64_t n_wslots = (n_slots + SPW - 1) / SPW;
 
-    // shared memory layout per warp: [trace (SMEM_TRACE)] [base staging SPW*max_n words] [scratch]
-    const int trace_words = SMEM_TRACE ? max_steps * WPS * 32 : 0;
-    const int per_warp_words = trace_words + SPW * max_n + PB_SCRATCH_WORDS;
+    // The 4-bit trace goes to a warp-private region of a global scratch buffer that is sized by the RESIDENT grid
+    // (grid-stride loop): it is rewritten for every slot and lives in L2.  Layout of the per-warp scratch:
+    // [trace max_steps*WPS*32 words] [HBUF_SMEM ? nothing : packed bases SPW*max_n words].
+    // Shared memory per warp: [HBUF_SMEM ? packed bases SPW*max_n words : nothing] [scout scratch].
+    const size_t trace_words = (size_t)max_steps * WPS * 32;
+    const size_t gwarp_words = trace_words + (HBUF_SMEM ? 0 : (size_t)SPW * max_n);
+    uint32_t *gw = gtrace + (size_t)wglobal * gwarp_words;
+    uint32_t *tr = gw;
+    const int per_warp_words = (HBUF_SMEM ? SPW * max_n : 0) + PB_SCRATCH_WORDS;
     uint32_t *wsm = smem + (size_t)warp * per_warp_words;
-    uint32_t *tr = SMEM_TRACE ? wsm : gtrace + (size_t)wglobal * ((size_t)max_steps * WPS * 32);
-    uint32_t *hbuf = wsm + trace_words + grp * max_n;
-    ScoutCand *cand = reinterpret_cast<ScoutCand *>(wsm + trace_words + SPW * max_n);  // [half][lane]
+    uint32_t *hbuf = HBUF_SMEM ? (wsm + grp * max_n) : (gw + trace_words + (size_t)grp * max_n);
+    ScoutCand *cand = reinterpret_cast<ScoutCand *>(wsm + (HBUF_SMEM ? SPW * max_n : 0));  // [half][lane]
     const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
 
     for (int64_t ws = wglobal; ws < n_wslots; ws += total_warps) {
         const int64_t slot = ws * SPW + grp;
-        const Task tA = load_task(tasks, slot * 2, n_tasks);
-        const Task tB = load_task(tasks, slot * 2 + 1, n_tasks);
-        const HalfGeom gA = make_geom(tA.n, tA.m, G, R), gB = make_geom(tB.n, tB.m, G, R);
-        const int nmax = max(tA.n, tB.n);
-        const uint8_t *seqA = seq + tA.seq_off, *seqB = seq + tB.seq_off;
-        const uint8_t *adA = ads + tA.ad_off, *adB = ads + tB.ad_off;
-
-        // stage the packed read bases of the slot's columns (each lane builds every G-th column)
-        for (int c = g; c < nmax; c += G) {
-            uint32_t bA = (c < tA.n) ? (uint32_t)__ldg(seqA + c) : (uint32_t)PB_PAD_H;
-            uint32_t bB = (c < tB.n) ? (uint32_t)__ldg(seqB + c) : (uint32_t)PB_PAD_H;
-            hbuf[c] = pack_bases(bA, bB);
-        }
+        int nA, nB, mA, mB, nmax, nmin;
+        bool need_track;
         Lane<R> L;
-        lane_init<R>(L, g, G, sc, adA, tA.m, (tA.flags & TASK_LEFT_INF) != 0, adB, tB.m, (tB.flags & TASK_LEFT_INF) != 0);
-        // scout: fast path while both halves are in inner columns; an empty half never limits it
-        const bool emptyA = tA.n <= 0 || tA.m <= 0, emptyB = tB.n <= 0 || tB.m <= 0;
-        const int nmin = emptyA ? tB.n : (emptyB ? tA.n : min(tA.n, tB.n));
-        const bool need_track = !((tA.flags & TASK_END_GIVEN) && (tB.flags & TASK_END_GIVEN));
+        {
+            // everything that is only needed to set the slot up lives in this scope (keeps the loop's register set small)
+            const Task tA = load_task(tasks, slot * 2, n_tasks);
+            const Task tB = load_task(tasks, slot * 2 + 1, n_tasks);
+            nA = tA.n; nB = tB.n; mA = tA.m; mB = tB.m;
+            nmax = max(nA, nB);
+            const uint8_t *seqA = seq + tA.seq_off, *seqB = seq + tB.seq_off;
+            // stage the packed read bases of the slot's columns (each lane builds every G-th column)
+            for (int c = g; c < nmax; c += G) {
+                uint32_t bA = (c < nA) ? (uint32_t)__ldg(seqA + c) : (uint32_t)PB_PAD_H;
+                uint32_t bB = (c < nB) ? (uint32_t)__ldg(seqB + c) : (uint32_t)PB_PAD_H;
+                hbuf[c] = pack_bases(bA, bB);
+            }
+            lane_init<R>(L, g, G, sc, ads + tA.ad_off, mA, (tA.flags & TASK_LEFT_INF) != 0, ads + tB.ad_off, mB,
+                         (tB.flags & TASK_LEFT_INF) != 0);
+            // scout: fast path while both halves are in inner columns; an empty half never limits it
+            const bool emptyA = nA <= 0 || mA <= 0, emptyB = nB <= 0 || mB <= 0;
+            nmin = emptyA ? nB : (emptyB ? nA : min(nA, nB));
+            need_track = !((tA.flags & TASK_END_GIVEN) && (tB.flags & TASK_END_GIVEN));
+        }
         int T = nmax > 0 ? nmax + G - 1 : 0;
         T = __reduce_max_sync(0xffffffffu, T);
         __syncwarp();
@@ -207,13 +219,17 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
             const int j = t - g + 1;
             if (j >= 1 && j <= nmax) {
                 uint32_t tw[WPS];
-                lane_step<R, true>(L, recvS, recvV, hbuf[j - 1], sc, tw);
+                if (need_track && j >= nmin) {
+                    // final column of a half (or halves of different lengths): rare, general scout
+                    uint32_t vr[R];
+                    lane_step<R, true, true>(L, recvS, recvV, hbuf[j - 1], sc, tw, vr);
+                    lane_track_general<R>(L, g, j, make_geom(nA, mA, G, R), make_geom(nB, mB, G, R), vr);
+                } else {
+                    lane_step<R, true, false>(L, recvS, recvV, hbuf[j - 1], sc, tw);
+                    if (need_track) lane_track_lastrow<R>(L, j);
+                }
 #pragma unroll
                 for (int w = 0; w < WPS; ++w) tr[((size_t)t * WPS + w) * 32 + lane] = tw[w];
-                if (need_track) {
-                    if (j < nmin) lane_track_lastrow<R>(L, j);
-                    else lane_track_general<R>(L, g, j, gA, gB);
-                }
             }
         }
         // scout candidates -> shared scratch, then lanes g==0 / g==1 finish halves A / B
@@ -222,8 +238,8 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
         __syncwarp();
         if (g < 2) {
             const int h = g;
-            const Task &tk = h ? tB : tA;
-            const HalfGeom &gh = h ? gB : gA;
+            const Task tk = load_task(tasks, slot * 2 + h, n_tasks);
+            const HalfGeom gh = make_geom(tk.n, tk.m, G, R);
             if (tk.out_idx >= 0) {
                 EndCell end;
                 if (tk.flags & TASK_END_GIVEN) {
@@ -232,8 +248,8 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
                 } else {
                     end = scout_combine(cand + h * 32 + grp * G, G, gh);
                 }
-                const uint8_t *sq = h ? seqB : seqA;
-                const uint8_t *ad = h ? adB : adA;
+                const uint8_t *sq = seq + tk.seq_off;
+                const uint8_t *ad = ads + tk.ad_off;
                 const int lane_base = grp * G;
                 auto nib = [&](int jl, int i) -> uint32_t {
                     const int q = i + gh.pad - 1;
@@ -322,9 +338,14 @@ score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long
             const int ja = min(j, tA.n) - 1, jb = min(j, tB.n) - 1;
             uint32_t bA = (ja >= 0) ? (uint32_t)__ldg(seqA + ja) : (uint32_t)PB_PAD_H;
             uint32_t bB = (jb >= 0) ? (uint32_t)__ldg(seqB + jb) : (uint32_t)PB_PAD_H;
-            lane_step<R, false>(L, recvS, recvV, pack_bases(bA, bB), sc, nullptr);
-            if (j < nmin) lane_track_lastrow<R>(L, j);
-            else lane_track_general<R>(L, g, j, gA, gB);
+            if (j < nmin) {
+                lane_step<R, false, false>(L, recvS, recvV, pack_bases(bA, bB), sc, nullptr);
+                lane_track_lastrow<R>(L, j);
+            } else {
+                uint32_t vr[R];
+                lane_step<R, false, true>(L, recvS, recvV, pack_bases(bA, bB), sc, nullptr, vr);
+                lane_track_general<R>(L, g, j, gA, gB, vr);
+            }
         }
         ++t;
     }

@@ -50,9 +50,15 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
             int j = t - g + 1;
             if (j >= 1 && j <= nmax) {
                 uint32_t tw[WPS];
-                lane_step<R, true>(L[g], recvS, recvV, hbuf[j - 1], sc, tw);
+                if (j >= nmin) {
+                    uint32_t vr[R];
+                    lane_step<R, true, true>(L[g], recvS, recvV, hbuf[j - 1], sc, tw, vr);
+                    lane_track_general<R>(L[g], g, j, gA, gB, vr);
+                } else {
+                    lane_step<R, true, false>(L[g], recvS, recvV, hbuf[j - 1], sc, tw);
+                    lane_track_lastrow<R>(L[g], j);
+                }
                 for (int w = 0; w < WPS; ++w) tr[((size_t)t * WPS + w) * G + g] = tw[w];
-                if (j < nmin) lane_track_lastrow<R>(L[g], j); else lane_track_general<R>(L[g], g, j, gA, gB);
             }
         }
     }
@@ -107,8 +113,14 @@ void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, End
             if (j >= 1 && j <= nmax) {
                 int ja = std::min(j, tA.n) - 1, jb = std::min(j, tB.n) - 1;
                 uint32_t bA = ja >= 0 ? seqA[ja] : PB_PAD_H, bB = jb >= 0 ? seqB[jb] : PB_PAD_H;
-                lane_step<R, false>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr);
-                if (j < nmin) lane_track_lastrow<R>(L[g], j); else lane_track_general<R>(L[g], g, j, gA, gB);
+                if (j < nmin) {
+                    lane_step<R, false, false>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr);
+                    lane_track_lastrow<R>(L[g], j);
+                } else {
+                    uint32_t vr[R];
+                    lane_step<R, false, true>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, vr);
+                    lane_track_general<R>(L[g], g, j, gA, gB, vr);
+                }
             }
         }
     }
@@ -149,7 +161,7 @@ void to_window(Task &t, const EndCell &e, int wnum, int wden) {
 extern "C" {
 
 // mode 0: single trace pass; mode 1: score pass + windowed trace pass (W = m + m*wnum/wden).
-// G in {4,8,16,32}, R in {4,8}; pass nB < 0 to leave half B empty.  Returns the status bit (window violated).
+// G in {4,8,16,32}, R in {4..8}; pass nB < 0 to leave half B empty.  Returns the status bit (window violated).
 int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char *seqB, int nB, const char *adB, int mB,
                    int G, int R, int mode, int ma, int mi, int go, int ge, int wnum, int wden, int32_t *recA,
                    int32_t *recB) {
@@ -159,13 +171,24 @@ int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char
     int status = 0;
     if (mode == 1) {
         EndCell eA, eB;
-        if (R == 8) run_score_group<8>(G, A, B, sc, &eA, &eB); else run_score_group<4>(G, A, B, sc, &eA, &eB);
+        switch (R) {
+            case 5: run_score_group<5>(G, A, B, sc, &eA, &eB); break;
+            case 6: run_score_group<6>(G, A, B, sc, &eA, &eB); break;
+            case 7: run_score_group<7>(G, A, B, sc, &eA, &eB); break;
+            case 8: run_score_group<8>(G, A, B, sc, &eA, &eB); break;
+            default: run_score_group<4>(G, A, B, sc, &eA, &eB); break;
+        }
         to_window(A.t, eA, wnum, wden);
         if (nB >= 0) to_window(B.t, eB, wnum, wden);
         // the trace pass may use a different (G,R) than the score pass, as in the engine: keep R, G as given
     }
-    if (R == 8) run_trace_group<8>(G, A, B, sc, recA, recB, &status);
-    else run_trace_group<4>(G, A, B, sc, recA, recB, &status);
+    switch (R) {
+        case 5: run_trace_group<5>(G, A, B, sc, recA, recB, &status); break;
+        case 6: run_trace_group<6>(G, A, B, sc, recA, recB, &status); break;
+        case 7: run_trace_group<7>(G, A, B, sc, recA, recB, &status); break;
+        case 8: run_trace_group<8>(G, A, B, sc, recA, recB, &status); break;
+        default: run_trace_group<4>(G, A, B, sc, recA, recB, &status); break;
+    }
     return status;
 }
 

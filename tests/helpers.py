@@ -106,11 +106,10 @@ def load_golden(name):
 
 
 def class_geometry(m):
-    """(G, R) of the trace kernel the engine picks for an adapter of length m (engine.cu class_of)."""
-    if m <= 32:
-        return 8, 4
-    if m <= 64:
-        return 16, 4
-    if m <= 128:
-        return 32, 4
+    """(G, R) of the trace kernel the engine picks for an adapter of length m (engine.cu class_of):
+    the smallest capacity G*R >= m with G in {4,8,16,32}, R in {5,6,7,8}."""
+    for k in range(16):
+        G, R = 4 << (k // 4), 5 + (k % 4)
+        if m <= G * R:
+            return G, R
     return 32, 8

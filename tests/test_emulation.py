@@ -86,7 +86,7 @@ def _gen(rng, mmax, nlo, nhi):
 def test_emu_random_vs_oracle_all_geometries():
     rng = random.Random(4242)
     for it in range(2500):
-        G, R = rng.choice([(8, 4), (16, 4), (32, 4), (32, 8), (4, 8), (8, 8), (16, 8)])
+        G, R = rng.choice([(8, 4), (16, 4), (32, 4), (32, 8), (4, 8), (8, 8), (16, 8), (4, 5), (4, 6), (4, 7), (8, 5), (16, 6), (32, 7)])
         mode = rng.choice([0, 0, 1])
         sc = rng.choice(SCHEMES)
         lo, hi = (50, 700) if mode else (0, 260)
