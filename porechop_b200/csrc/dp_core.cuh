@@ -31,16 +31,25 @@
 
 namespace pb {
 
-// ---- int16 domain constants -----------------------------------------------------------------------
-// Genuine DP values are bounded by |x| <= A*(m+2) <= PB_I16_LIMIT (checked on the host before the
-// int16 kernels are chosen), the "-infinity" of the borders is PB_NEG16; pseudo-infinite values of a
-// windowed pass stay in [PB_NEG16-PB_I16_LIMIT, PB_NEG16+PB_I16_LIMIT], i.e. always below every
-// genuine value and never wrapping an int16 even after one more add of a gap score.
-constexpr int PB_NEG16 = -16384;
+#if !defined(__CUDA_ARCH__) && defined(PB_CHECK_RANGES)
+void pb_range_violation();   // defined by the CPU emulation: counts int16-domain violations
+#endif
+
+// ---- int16 domain ---------------------------------------------------------------------------------------
+// All DP values are kept BIASED by PB_BIAS so that every 16-bit half is a non-negative number: adding a
+// (negative) gap score to both halves is then ONE plain 32-bit subtraction of the packed magnitudes with no
+// borrow between the halves -- an instruction ptxas may place on either the ALU or the FMA pipe, which is what
+// balances the two pipes (the packed DPX max / add-max instructions only exist on the ALU pipe).
+//   genuine values   |x| <= PB_I16_LIMIT (+ one more score)      (host check: A*(m+3) <= PB_I16_LIMIT)
+//   "-infinity"      PB_NEG16 (borders, left edge of a windowed pass); pseudo-infinite values of a windowed
+//                    pass stay within PB_NEG16 +- PB_I16_LIMIT, below every genuine value
+//   smallest value ever formed: PB_NEG16 - PB_I16_LIMIT - PB_LINEAR_EXT  > -PB_BIAS   (no wrap, no borrow)
+constexpr int PB_BIAS = 24576;
+constexpr int PB_NEG16 = -14000;
 constexpr int PB_I16_LIMIT = 4000;
-constexpr int PB_LINEAR_EXT = -8192;   // "never extend" pseudo score used to run go==ge through the affine cell
+constexpr int PB_LINEAR_EXT = 4096;    // magnitude of the "never extend" pseudo score that runs go==ge through the affine cell
 constexpr int PB_CODE_SHIFT = 12;      // base codes live in bits 12..14 of each half: x^y is 0 or >= 4096
-constexpr int PB_MAX_SUBW = 4096;      // ma - mi must not exceed this for the xor/addmax substitution trick
+constexpr int PB_MAX_SUBW = 4096;      // ma - mi must not exceed this for the xnor/addmax substitution trick
 constexpr uint8_t PB_PAD_H = 0x50;     // encoded-byte value (code<<4) for read padding (matches nothing)
 constexpr uint8_t PB_PAD_V = 0x60;     // encoded-byte value for adapter padding rows
 
@@ -105,11 +114,19 @@ PB_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) {
 }
 
 // ---- scoring scheme as the kernels see it --------------------------------------------------------------
+// The state of a cell is X = S + go (+bias): it is what both the cell to the right (horizontal open) and the cell
+// below (vertical open) need, so the "+ go" is added once per cell; the diagonal use compensates by folding "- go"
+// into the substitution constants.
 struct Scoring {
-    uint32_t go2;     // packed gap-open score (linear mode: the single gap score)
-    uint32_t ge2;     // packed gap-extension score (linear mode: PB_LINEAR_EXT, so an extension never wins)
-    uint32_t subA2;   // packed (match + 1)
-    uint32_t subF2;   // packed mismatch
+    uint32_t goMag2;  // packed |go|  (linear mode: |ge|)            X = S_biased - goMag
+    uint32_t geMag2;  // packed |ge|  (linear mode: PB_LINEAR_EXT)   h_ext = Hs_biased - geMag   (trace pass)
+    uint32_t ge2;     // packed signed ge (linear: -PB_LINEAR_EXT)   for the fused add-max of the score pass
+    uint32_t subA2;   // packed (match + 1 - go)
+    uint32_t subF2;   // packed (mismatch - go)
+    uint32_t padF2;   // packed (-go): substitution operand of the border-emulating pad rows
+    uint32_t borderX2;// packed biased X of the zero border: 0 + go + bias
+    uint32_t negb2;   // packed biased -infinity
+    int32_t goEff;    // go (linear: ge)
     int32_t linear;   // go == ge : NW recurrence of dp_formula_linear.h, no end-cell correction
     int32_t ma, mi, go, ge;
 };
@@ -118,10 +135,17 @@ PB_HD Scoring make_scoring(int ma, int mi, int go, int ge) {
     Scoring s;
     s.linear = (go == ge) ? 1 : 0;
     s.ma = ma; s.mi = mi; s.go = go; s.ge = ge;
-    s.go2 = s.linear ? pack2(ge, ge) : pack2(go, go);
-    s.ge2 = s.linear ? pack2(PB_LINEAR_EXT, PB_LINEAR_EXT) : pack2(ge, ge);
-    s.subA2 = pack2(ma + 1, ma + 1);
-    s.subF2 = pack2(mi, mi);
+    const int goE = s.linear ? ge : go;
+    const int geE = s.linear ? -PB_LINEAR_EXT : ge;
+    s.goEff = goE;
+    s.goMag2 = pack2(-goE, -goE);
+    s.geMag2 = pack2(-geE, -geE);
+    s.ge2 = pack2(geE, geE);
+    s.subA2 = pack2(ma + 1 - goE, ma + 1 - goE);
+    s.subF2 = pack2(mi - goE, mi - goE);
+    s.padF2 = pack2(-goE, -goE);
+    s.borderX2 = pack2(PB_BIAS + goE, PB_BIAS + goE);
+    s.negb2 = pack2(PB_BIAS + PB_NEG16, PB_BIAS + PB_NEG16);
     return s;
 }
 
@@ -155,21 +179,21 @@ struct EndCell {
 // Row layout: the G*R rows of a group are BOTTOM-aligned per half: real adapter row i (1..m) lives at group row
 // q = i + pad, pad = G*R - m, so the last row m is always the bottom row of lane G-1 (static register, no
 // per-step row selection for the scout).  The `pad` rows above row 1 reproduce the zero border row without
-// extra instructions: they use per-row score operands (gap-open = -inf, mismatch = 0, a code that matches
-// nothing), so they compute S = 0, Vs = Hs = -inf in every column -- exactly what row 0 presents to row 1.
+// extra instructions: they carry a code that matches nothing and the substitution operand -go, so they compute
+// S = 0 in every column (d = 0 beats both gaps), and their gap values are never better than what the true
+// border would present to row 1.
 template <int R>
 struct Lane {
-    uint32_t Sl[R];   // S[j-1][row]   (packed halves), becomes S[j][row] after the step
-    uint32_t Hs[R];   // Hs[j-1][row]
+    uint32_t X[R];    // X[j-1][row] = S + go (biased, packed halves); becomes X[j][row] after the step
+    uint32_t Hs[R];   // Hs[j-1][row] (biased)
     uint32_t v2[R];   // adapter code << PB_CODE_SHIFT of the owned rows, packed halves
-    uint32_t go2[R];  // per-row gap-open operand   (pad rows: PB_NEG16)
-    uint32_t sf2[R];  // per-row mismatch operand   (pad rows: 0)
-    uint32_t prevRecvS;  // S[j-1][top-1]  (diagonal input of the top row)
-    uint32_t botS, botV; // S[j][bottom], Vs[j][bottom] -> shuffled to the next lane
-    // scout state: last-row running best, packed (meaningful in lane G-1 only) ...
+    uint32_t sf2[R];  // per-row mismatch operand (real rows: mi - go, pad rows: -go)
+    uint32_t prevRecvX;  // X[j-1][top-1]  (diagonal input of the top row)
+    uint32_t botX, botV; // X[j][bottom], Vs[j][bottom] -> shuffled to the next lane
+    // scout state: last-row running best (X domain), packed (meaningful in lane G-1 only) ...
     uint32_t lrBest2;
     int lrJ[2], lrCorr[2];
-    // ... and the best of this lane's rows in the final column, per half
+    // ... and the best of this lane's rows in the final column, per half (X domain, biased)
     int fcBest[2], fcI[2], fcCorr[2];
 };
 
@@ -183,12 +207,21 @@ PB_HD HalfGeom make_geom(int n, int m, int G, int R) {
     return h;
 }
 
+// x - P per half where P holds magnitudes and every half of x is >= the half of P: one plain 32-bit subtraction
+PB_HD uint32_t subm2(uint32_t x, uint32_t P) {
+#if !defined(__CUDA_ARCH__) && defined(PB_CHECK_RANGES)
+    if ((x & 0xFFFFu) < (P & 0xFFFFu) || (x >> 16) < (P >> 16) || (x & 0x80008000u)) pb_range_violation();
+#endif
+    return x - P;
+}
+
 template <int R>
 PB_HD void lane_init(Lane<R> &L, int g, int G, const Scoring &sc, const uint8_t *adA, int mA, bool leftInfA,
                      const uint8_t *adB, int mB, bool leftInfB) {
-    const uint32_t negh = (uint32_t)PB_NEG16 & 0xFFFFu;
     const int padA = G * R - mA, padB = G * R - mB;
-    const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
+    // column 0: X = S0 + go + bias with S0 = 0 (border / pad rows) or -inf (real rows of a windowed task)
+    const uint32_t x0 = sc.borderX2;
+    const uint32_t xinf = add2(sc.negb2, pack2(sc.goEff, sc.goEff));
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int q = g * R + r + 1;
@@ -197,21 +230,20 @@ PB_HD void lane_init(Lane<R> &L, int g, int G, const Scoring &sc, const uint8_t 
         const uint32_t a = realA ? (uint32_t)adA[iA - 1] : (uint32_t)PB_PAD_V;
         const uint32_t b = realB ? (uint32_t)adB[iB - 1] : (uint32_t)PB_PAD_V;
         L.v2[r] = (a << 8) | (b << 24);               // code<<4 in a byte -> code<<12 in the half
-        L.go2[r] = (realA ? (sc.go2 & 0xFFFFu) : negh) | (realB ? (sc.go2 & 0xFFFF0000u) : (negh << 16));
-        L.sf2[r] = (realA ? (sc.subF2 & 0xFFFFu) : 0u) | (realB ? (sc.subF2 & 0xFFFF0000u) : 0u);
-        L.Sl[r] = ((realA && leftInfA) ? negh : 0u) | ((realB && leftInfB) ? (negh << 16) : 0u);   // S[0][row]
-        L.Hs[r] = neg2;
+        L.sf2[r] = ((realA ? sc.subF2 : sc.padF2) & 0xFFFFu) | ((realB ? sc.subF2 : sc.padF2) & 0xFFFF0000u);
+        L.X[r] = (((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u);
+        L.Hs[r] = sc.negb2;
     }
-    {   // S[0][row above this lane's top row]: 0 for row 0 / pad rows, the column-0 value otherwise
+    {   // X[0][row above this lane's top row]
         const int q = g * R;
         const bool realA = (q - padA) >= 1, realB = (q - padB) >= 1;
-        L.prevRecvS = ((realA && leftInfA) ? negh : 0u) | ((realB && leftInfB) ? (negh << 16) : 0u);
+        L.prevRecvX = (((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u);
     }
-    L.botS = L.Sl[R - 1]; L.botV = neg2;
-    L.lrBest2 = 0u;                                    // candidate (0, m): value 0
+    L.botX = L.X[R - 1]; L.botV = sc.negb2;
+    L.lrBest2 = sc.borderX2;                           // candidate (0, m): S = 0
     for (int h = 0; h < 2; ++h) {
         L.lrJ[h] = 0; L.lrCorr[h] = 0;
-        L.fcBest[h] = -0x40000000; L.fcI[h] = 0; L.fcCorr[h] = 0;
+        L.fcBest[h] = -1; L.fcI[h] = 0; L.fcCorr[h] = 0;   // biased X values are >= 0
     }
 }
 
@@ -247,14 +279,13 @@ PB_HD uint32_t max2acc(uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, ui
 #endif
 }
 
-// position of the nibble of (half h, local row r) in the per-step trace words of a lane
 // R <= 4: one word per step (half A in bits 0..15, half B in bits 16..31); R = 5..8: word 0 = half A, word 1 = half B.
 template <int R> struct TraceWords { static constexpr int value = (R <= 4) ? 1 : 2; };
 template <int R> PB_HD int trace_word(int h, int r) { (void)r; return (R <= 4) ? 0 : h; }
 template <int R> PB_HD int trace_shift(int h, int r) { return (R <= 4) ? (4 * r + 16 * h) : 4 * r; }
 
 // One wavefront step of one lane: column j with inputs from the lane above.
-//   recvS/recvV : S[j][top-1], Vs[j][top-1]  (for g == 0 the caller passes the row-0 border: 0 / NEG)
+//   recvX/recvV : X[j][top-1], Vs[j][top-1]  (for g == 0 the caller passes the row-0 border: sc.borderX2 / sc.negb2)
 //   h2          : read bases of column j, encoded << PB_CODE_SHIFT, packed halves
 //   tw          : trace words of this step (TRACE only), TraceWords<R>::value entries.  4 flags per cell:
 //       bit0 tD : diagonal chosen          (g <= d,  ties -> diagonal)
@@ -262,86 +293,95 @@ template <int R> PB_HD int trace_shift(int h, int r) { return (R <= 4) ? (4 * r 
 //       bit2 tV : vertical gap extended    (v_ext >= v_open, ties -> extend)
 //       bit3 tH : horizontal gap extended  (h_ext >= h_open, ties -> extend)
 //   vr          : KEEPV only -- Vs[j][row] of every owned row (the final-column scout needs it for the end-cell
-//                 correction flags); the hot path does not keep these 8 registers alive
+//                 correction flags); the hot path does not keep these registers alive
+// Pipe balance of the trace pass (per row, sm_100a): VIMNMX x4, VIADDMNMX, LOP3, VIADD.16x2 run on the ALU pipe;
+// the 8 predicated flag adds and plain 32-bit subtractions run on the FMA pipe.  The two gap extensions use the
+// packed ALU add, the X update the plain subtraction: 9 ALU + 9 FMA instructions per row.
+#ifndef PB_EXT_ON_FMA
+#define PB_EXT(x) add2((x), sc.ge2)
+#else
+#define PB_EXT(x) subm2((x), sc.geMag2)
+#endif
 template <int R, bool TRACE, bool KEEPV = false>
-PB_HD void lane_step(Lane<R> &L, uint32_t recvS, uint32_t recvV, uint32_t h2, const Scoring &sc, uint32_t *tw,
+PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, const Scoring &sc, uint32_t *tw,
                      uint32_t *vr = nullptr) {
-    uint32_t diag = L.prevRecvS, upS = recvS, upV = recvV;
-    uint32_t accLo = 0u, accHi = 0u;     // R = 4: one word (A in bits 0..15, B in 16..31); R = 8: word 0 = A, word 1 = B
+    uint32_t diagX = L.prevRecvX, upX = recvX, upV = recvV;
+    uint32_t accLo = 0u, accHi = 0u;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-        const uint32_t h_open = add2(L.Sl[r], L.go2[r]);
-        const uint32_t v_open = add2(upS, L.go2[r]);
-        // substitution score per half: codes equal -> ~(h ^ v) == -1 -> max(-1 + ma + 1, mi) = ma ; else <= mi
+        // substitution (minus go) per half: codes equal -> ~(h^v) == -1 -> max(-1 + ma + 1 - go, mi - go) = ma - go
         const uint32_t sub = addmax2(xnor2(h2, L.v2[r]), sc.subA2, L.sf2[r]);
-        const uint32_t d = add2(diag, sub);
+        const uint32_t d = add2(diagX, sub);                       // S_diag + sub   (biased)
         uint32_t hs, vs, s;
         if (TRACE) {
             const uint32_t bl = 1u << trace_shift<R>(0, r);
             const uint32_t bh = 1u << trace_shift<R>(1, r);
-            hs = max2acc(add2(L.Hs[r], sc.ge2), h_open, accLo, bl << 3, accHi, bh << 3);
-            vs = max2acc(add2(upV, sc.ge2), v_open, accLo, bl << 2, accHi, bh << 2);
+            hs = max2acc(PB_EXT(L.Hs[r]), L.X[r], accLo, bl << 3, accHi, bh << 3);   // ext vs open (= X left)
+            vs = max2acc(PB_EXT(upV), upX, accLo, bl << 2, accHi, bh << 2);          // ext vs open (= X up)
             const uint32_t gmx = max2acc(vs, hs, accLo, bl << 1, accHi, bh << 1);
             s = max2acc(d, gmx, accLo, bl, accHi, bh);
         } else {
-            hs = addmax2(L.Hs[r], sc.ge2, h_open);
-            vs = addmax2(upV, sc.ge2, v_open);
+            hs = addmax2(L.Hs[r], sc.ge2, L.X[r]);
+            vs = addmax2(upV, sc.ge2, upX);
             s = max3(d, vs, hs);
         }
-        diag = L.Sl[r];
-        L.Sl[r] = s; L.Hs[r] = hs;
+        diagX = L.X[r];
+        const uint32_t xn = subm2(s, sc.goMag2);                    // X = S + go
+        L.X[r] = xn; L.Hs[r] = hs;
         if (KEEPV) vr[r] = vs;
-        upS = s; upV = vs;
+        upX = xn; upV = vs;
     }
     if (TRACE) {
-        if (TraceWords<R>::value == 1) tw[0] = accLo + accHi; else { tw[0] = accLo; tw[TraceWords<R>::value - 1] = accHi; }
+        if (TraceWords<R>::value == 1) tw[0] = accLo + accHi; else { tw[0] = accLo; tw[1] = accHi; }
     }
-    L.prevRecvS = recvS;
-    L.botS = upS; L.botV = upV;
+    L.prevRecvX = recvX;
+    L.botX = upX; L.botV = upV;
+}
+
+// end-cell correction flags of a cell (dp_algorithm_impl.h:1354-1369): bit0 Vs == S, bit1 Hs == S.
+// x = biased X (= S + go + bias), vs/hs biased.
+PB_HD int corr_flags(int x, int vs, int hs, int goEff) {
+    const int sb = x - goEff;      // biased S
+    return (vs == sb ? 1 : 0) | (hs == sb ? 2 : 0);
 }
 
 // Scout, fast path: inner columns (j < n for both halves).  Only the bottom row of lane G-1 is the last row, but every
 // lane may run this on its own bottom row -- scout_combine reads lane G-1 only.  One VIMNMX + a rarely taken branch.
 template <int R>
-PB_HD void lane_track_lastrow(Lane<R> &L, int j) {
+PB_HD void lane_track_lastrow(Lane<R> &L, int j, const Scoring &sc) {
     bool plo, phi;
-    const uint32_t nb = max2p(L.lrBest2, L.botS, plo, phi);     // p = (old best >= candidate): strict '>' replaces
+    const uint32_t nb = max2p(L.lrBest2, L.botX, plo, phi);     // p = (old best >= candidate): strict '>' replaces
     if (!(plo && phi)) {
         L.lrBest2 = nb;
-        if (!plo) {
-            const int c = half16(L.botS, 0);
-            L.lrJ[0] = j; L.lrCorr[0] = (half16(L.botV, 0) == c ? 1 : 0) | (half16(L.Hs[R - 1], 0) == c ? 2 : 0);
-        }
-        if (!phi) {
-            const int c = half16(L.botS, 1);
-            L.lrJ[1] = j; L.lrCorr[1] = (half16(L.botV, 1) == c ? 1 : 0) | (half16(L.Hs[R - 1], 1) == c ? 2 : 0);
-        }
+        if (!plo) { L.lrJ[0] = j; L.lrCorr[0] = corr_flags(half16(L.botX, 0), half16(L.botV, 0), half16(L.Hs[R - 1], 0), sc.goEff); }
+        if (!phi) { L.lrJ[1] = j; L.lrCorr[1] = corr_flags(half16(L.botX, 1), half16(L.botV, 1), half16(L.Hs[R - 1], 1), sc.goEff); }
     }
 }
 
 // Scout, general path: handles halves of different lengths and the final column (every real row of the final
 // column is a candidate, visited top to bottom; dp_scout.h:168-181).
 template <int R>
-PB_HD void lane_track_general(Lane<R> &L, int g, int j, const HalfGeom &A, const HalfGeom &B, const uint32_t *vr) {
+PB_HD void lane_track_general(Lane<R> &L, int g, int j, const HalfGeom &A, const HalfGeom &B, const uint32_t *vr,
+                              const Scoring &sc) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const HalfGeom &H = h ? B : A;
         if (j < H.n) {
-            const int c = half16(L.botS, h);
+            const int c = half16(L.botX, h);
             if (c > half16(L.lrBest2, h)) {
-                L.lrBest2 = h ? ((L.lrBest2 & 0xFFFFu) | (L.botS & 0xFFFF0000u)) : ((L.lrBest2 & 0xFFFF0000u) | (L.botS & 0xFFFFu));
+                L.lrBest2 = h ? ((L.lrBest2 & 0xFFFFu) | (L.botX & 0xFFFF0000u)) : ((L.lrBest2 & 0xFFFF0000u) | (L.botX & 0xFFFFu));
                 L.lrJ[h] = j;
-                L.lrCorr[h] = (half16(L.botV, h) == c ? 1 : 0) | (half16(L.Hs[R - 1], h) == c ? 2 : 0);
+                L.lrCorr[h] = corr_flags(c, half16(L.botV, h), half16(L.Hs[R - 1], h), sc.goEff);
             }
         } else if (j == H.n) {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int i = g * R + r + 1 - H.pad;
                 if (i >= 1) {
-                    const int c = half16(L.Sl[r], h);
+                    const int c = half16(L.X[r], h);
                     if (c > L.fcBest[h]) {
                         L.fcBest[h] = c; L.fcI[h] = i;
-                        L.fcCorr[h] = (half16(vr[r], h) == c ? 1 : 0) | (half16(L.Hs[r], h) == c ? 2 : 0);
+                        L.fcCorr[h] = corr_flags(c, half16(vr[r], h), half16(L.Hs[r], h), sc.goEff);
                     }
                 }
             }
@@ -349,13 +389,15 @@ PB_HD void lane_track_general(Lane<R> &L, int g, int j, const HalfGeom &A, const
     }
 }
 
-// Combine the per-lane scout state of a group into the end cell of half h.
+// Combine the per-lane scout state of a group into the end cell of half h.  Scores are converted from the biased
+// X domain (S + go + bias) back to raw scores here.
 struct ScoutCand { int fcBest, fcI, fcCorr, lrBest, lrJ, lrCorr; };
 template <int R>
-PB_HD ScoutCand make_cand(const Lane<R> &L, int h) {
+PB_HD ScoutCand make_cand(const Lane<R> &L, int h, const Scoring &sc) {
     ScoutCand c;
-    c.fcBest = L.fcBest[h]; c.fcI = L.fcI[h]; c.fcCorr = L.fcCorr[h];
-    c.lrBest = half16(L.lrBest2, h); c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
+    c.fcBest = L.fcBest[h] < 0 ? -0x40000000 : L.fcBest[h] - PB_BIAS - sc.goEff;
+    c.fcI = L.fcI[h]; c.fcCorr = L.fcCorr[h];
+    c.lrBest = half16(L.lrBest2, h) - PB_BIAS - sc.goEff; c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
     return c;
 }
 PB_HD EndCell scout_combine(const ScoutCand *c, int G, const HalfGeom &H) {

@@ -180,8 +180,6 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
     uint32_t *wsm = smem + (size_t)warp * per_warp_words;
     uint32_t *hbuf = HBUF_SMEM ? (wsm + grp * max_n) : (gw + trace_words + (size_t)grp * max_n);
     ScoutCand *cand = reinterpret_cast<ScoutCand *>(wsm + (HBUF_SMEM ? SPW * max_n : 0));  // [half][lane]
-    const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
-
     for (int64_t ws = wglobal; ws < n_wslots; ws += total_warps) {
         const int64_t slot = ws * SPW + grp;
         int nA, nB, mA, mB, nmax, nmin;
@@ -213,9 +211,9 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
 
 #pragma unroll 2
         for (int t = 0; t < T; ++t) {
-            uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botS, 1, G);
+            uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
             uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
-            if (g == 0) { recvS = 0u; recvV = neg2; }
+            if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
             const int j = t - g + 1;
             if (j >= 1 && j <= nmax) {
                 uint32_t tw[WPS];
@@ -223,19 +221,20 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
                     // final column of a half (or halves of different lengths): rare, general scout
                     uint32_t vr[R];
                     lane_step<R, true, true>(L, recvS, recvV, hbuf[j - 1], sc, tw, vr);
-                    lane_track_general<R>(L, g, j, make_geom(nA, mA, G, R), make_geom(nB, mB, G, R), vr);
+                    lane_track_general<R>(L, g, j, make_geom(nA, mA, G, R), make_geom(nB, mB, G, R), vr, sc);
                 } else {
                     lane_step<R, true, false>(L, recvS, recvV, hbuf[j - 1], sc, tw);
-                    if (need_track) lane_track_lastrow<R>(L, j);
+                    if (need_track) lane_track_lastrow<R>(L, j, sc);
                 }
 #pragma unroll
                 for (int w = 0; w < WPS; ++w) tr[((size_t)t * WPS + w) * 32 + lane] = tw[w];
             }
         }
         // scout candidates -> shared scratch, then lanes g==0 / g==1 finish halves A / B
-        cand[lane] = make_cand<R>(L, 0);
-        cand[32 + lane] = make_cand<R>(L, 1);
+        cand[lane] = make_cand<R>(L, 0, sc);
+        cand[32 + lane] = make_cand<R>(L, 1, sc);
         __syncwarp();
+#ifndef PB_EXPERIMENT_SKIP_TRACEBACK   // (profiling experiments only: measure the forward pass alone)
         if (g < 2) {
             const int h = g;
             const Task tk = load_task(tasks, slot * 2 + h, n_tasks);
@@ -248,7 +247,6 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
                 } else {
                     end = scout_combine(cand + h * 32 + grp * G, G, gh);
                 }
-                const uint8_t *sq = seq + tk.seq_off;
                 const uint8_t *ad = ads + tk.ad_off;
                 const int lane_base = grp * G;
                 auto nib = [&](int jl, int i) -> uint32_t {
@@ -258,7 +256,9 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
                     const uint32_t w = tr[((size_t)t * WPS + trace_word<R>(h, r)) * 32 + lane_base + gg];
                     return (w >> trace_shift<R>(h, r)) & 15u;
                 };
-                auto eq = [&](int jl, int i) -> bool { return __ldg(sq + jl - 1) == __ldg(ad + i - 1); };
+                auto eq = [&](int jl, int i) -> bool {   // the slot's packed bases are still staged in hbuf
+                    return ((hbuf[jl - 1] >> (8 + 16 * h)) & 0xFFu) == (uint32_t)__ldg(ad + i - 1);
+                };
                 int32_t rec[PB_REC];
                 int st = traceback_stats(nib, eq, end, sc.linear != 0, tk.col0, tk.n_total, tk.m, rec);
                 if (st) atomicOr(status, 1);
@@ -267,6 +267,7 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
                 for (int k = 0; k < PB_REC; ++k) o[k] = rec[k];
             }
         }
+#endif
         __syncwarp();
     }
 }
@@ -284,7 +285,6 @@ score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long
     const int grp = lane / G, g = lane % G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
     const int64_t n_slots = (n_tasks + 1) / 2;
-    const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
     ScoutCand *cand = scratch[warp];
 
     Lane<R> L;
@@ -295,13 +295,13 @@ score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long
     int nmax = 0, nmin = 0, T = 0, t = 0;
     bool exhausted = false;
     tA.n = tB.n = 0;
-    L.botS = 0; L.botV = neg2;
+    L.botX = sc.borderX2; L.botV = sc.negb2;
 
     for (;;) {
         if (t >= T && !exhausted) {            // group-uniform: this group's slot is finished (or none yet)
             if (slot >= 0) {
-                cand[lane] = make_cand<R>(L, 0);
-                cand[32 + lane] = make_cand<R>(L, 1);
+                cand[lane] = make_cand<R>(L, 0, sc);
+                cand[32 + lane] = make_cand<R>(L, 1, sc);
                 __syncwarp(gmask);
                 if (g < 2) {
                     const int64_t ti = slot * 2 + g;
@@ -330,9 +330,9 @@ score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long
             }
         }
         if (__all_sync(0xffffffffu, exhausted)) break;
-        uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botS, 1, G);
+        uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
         uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
-        if (g == 0) { recvS = 0u; recvV = neg2; }
+        if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
         const int j = t - g + 1;
         if (!exhausted && j >= 1 && j <= nmax) {
             const int ja = min(j, tA.n) - 1, jb = min(j, tB.n) - 1;
@@ -340,11 +340,11 @@ score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long
             uint32_t bB = (jb >= 0) ? (uint32_t)__ldg(seqB + jb) : (uint32_t)PB_PAD_H;
             if (j < nmin) {
                 lane_step<R, false, false>(L, recvS, recvV, pack_bases(bA, bB), sc, nullptr);
-                lane_track_lastrow<R>(L, j);
+                lane_track_lastrow<R>(L, j, sc);
             } else {
                 uint32_t vr[R];
                 lane_step<R, false, true>(L, recvS, recvV, pack_bases(bA, bB), sc, nullptr, vr);
-                lane_track_general<R>(L, g, j, gA, gB, vr);
+                lane_track_general<R>(L, g, j, gA, gB, vr, sc);
             }
         }
         ++t;

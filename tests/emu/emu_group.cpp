@@ -10,7 +10,11 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+#define PB_CHECK_RANGES 1
 #include "../../porechop_b200/csrc/dp_core.cuh"
+
+static long g_range_violations = 0;
+namespace pb { void pb_range_violation() { ++g_range_violations; } }
 
 using namespace pb;
 
@@ -41,22 +45,21 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
     for (int g = 0; g < G; ++g)
         lane_init<R>(L[g], g, G, sc, adA, tA.m, (tA.flags & TASK_LEFT_INF) != 0, adB, tB.m, (tB.flags & TASK_LEFT_INF) != 0);
     std::vector<uint32_t> tr((size_t)std::max(T, 1) * WPS * G, 0u);
-    const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
     std::vector<uint32_t> sS((size_t)G), sV((size_t)G);
     for (int t = 0; t < T; ++t) {
-        for (int g = 0; g < G; ++g) { sS[g] = L[g].botS; sV[g] = L[g].botV; }   // shuffle snapshot
+        for (int g = 0; g < G; ++g) { sS[g] = L[g].botX; sV[g] = L[g].botV; }   // shuffle snapshot
         for (int g = 0; g < G; ++g) {
-            uint32_t recvS = g ? sS[g - 1] : 0u, recvV = g ? sV[g - 1] : neg2;
+            uint32_t recvS = g ? sS[g - 1] : sc.borderX2, recvV = g ? sV[g - 1] : sc.negb2;
             int j = t - g + 1;
             if (j >= 1 && j <= nmax) {
                 uint32_t tw[WPS];
                 if (j >= nmin) {
                     uint32_t vr[R];
                     lane_step<R, true, true>(L[g], recvS, recvV, hbuf[j - 1], sc, tw, vr);
-                    lane_track_general<R>(L[g], g, j, gA, gB, vr);
+                    lane_track_general<R>(L[g], g, j, gA, gB, vr, sc);
                 } else {
                     lane_step<R, true, false>(L[g], recvS, recvV, hbuf[j - 1], sc, tw);
-                    lane_track_lastrow<R>(L[g], j);
+                    lane_track_lastrow<R>(L[g], j, sc);
                 }
                 for (int w = 0; w < WPS; ++w) tr[((size_t)t * WPS + w) * G + g] = tw[w];
             }
@@ -68,7 +71,7 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
         int32_t *rec = h ? recB : recA;
         if (tk.out_idx < 0) continue;
         std::vector<ScoutCand> cand((size_t)G);
-        for (int g = 0; g < G; ++g) cand[g] = make_cand<R>(L[g], h);
+        for (int g = 0; g < G; ++g) cand[g] = make_cand<R>(L[g], h, sc);
         EndCell end;
         if (tk.flags & TASK_END_GIVEN) {
             end.j = tk.end_j; end.i = tk.end_i; end.score = tk.end_score; end.corr = tk.end_corr;
@@ -103,30 +106,29 @@ void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, End
     std::vector<Lane<R>> L((size_t)G);
     for (int g = 0; g < G; ++g)
         lane_init<R>(L[g], g, G, sc, A.ad.data() + tA.ad_off, tA.m, false, B.ad.data() + tB.ad_off, tB.m, false);
-    const uint32_t neg2 = pack2(PB_NEG16, PB_NEG16);
     std::vector<uint32_t> sS((size_t)G), sV((size_t)G);
     for (int t = 0; t < T; ++t) {
-        for (int g = 0; g < G; ++g) { sS[g] = L[g].botS; sV[g] = L[g].botV; }
+        for (int g = 0; g < G; ++g) { sS[g] = L[g].botX; sV[g] = L[g].botV; }
         for (int g = 0; g < G; ++g) {
-            uint32_t recvS = g ? sS[g - 1] : 0u, recvV = g ? sV[g - 1] : neg2;
+            uint32_t recvS = g ? sS[g - 1] : sc.borderX2, recvV = g ? sV[g - 1] : sc.negb2;
             int j = t - g + 1;
             if (j >= 1 && j <= nmax) {
                 int ja = std::min(j, tA.n) - 1, jb = std::min(j, tB.n) - 1;
                 uint32_t bA = ja >= 0 ? seqA[ja] : PB_PAD_H, bB = jb >= 0 ? seqB[jb] : PB_PAD_H;
                 if (j < nmin) {
                     lane_step<R, false, false>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr);
-                    lane_track_lastrow<R>(L[g], j);
+                    lane_track_lastrow<R>(L[g], j, sc);
                 } else {
                     uint32_t vr[R];
                     lane_step<R, false, true>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, vr);
-                    lane_track_general<R>(L[g], g, j, gA, gB, vr);
+                    lane_track_general<R>(L[g], g, j, gA, gB, vr, sc);
                 }
             }
         }
     }
     for (int h = 0; h < 2; ++h) {
         std::vector<ScoutCand> cand((size_t)G);
-        for (int g = 0; g < G; ++g) cand[g] = make_cand<R>(L[g], h);
+        for (int g = 0; g < G; ++g) cand[g] = make_cand<R>(L[g], h, sc);
         *(h ? eB : eA) = scout_combine(cand.data(), G, h ? gB : gA);
     }
 }
@@ -189,7 +191,9 @@ int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char
         case 8: run_trace_group<8>(G, A, B, sc, recA, recB, &status); break;
         default: run_trace_group<4>(G, A, B, sc, recA, recB, &status); break;
     }
-    return status;
+    return status | (g_range_violations ? 2 : 0);
 }
+
+long emu_range_violations() { return g_range_violations; }
 
 }  // extern "C"
