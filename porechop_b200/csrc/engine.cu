@@ -192,7 +192,8 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const Task *t
     int bps = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem_bytes));
     if (bps < 1) bps = 1;
-    const size_t gwarp_bytes = ((size_t)max_steps * WPS * 32 + (HS ? 0 : (size_t)SPW * max_n)) * 4;
+    const size_t gwarp_bytes = ((size_t)((max_steps + PB_TCHUNK - 1) / PB_TCHUNK) * PB_TCHUNK * WPS * 32 +
+                                (HS ? 0 : (((size_t)SPW * max_n + 3) & ~(size_t)3))) * 4;
     // bound the scratch (~12 GB) for very long single-pass alignments
     int64_t max_warps = std::max<int64_t>(wpb, (int64_t)((12ull << 30) / std::max<size_t>(gwarp_bytes, 1)));
     while (bps > 1 && (int64_t)bps * E.sm_count * wpb > max_warps) --bps;

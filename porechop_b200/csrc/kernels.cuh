@@ -20,6 +20,7 @@ constexpr int PB_WARPS_PER_BLOCK = 4;
 #define PB_TRACE_MIN_BLOCKS 5
 #endif
 constexpr int PB_SCRATCH_WORDS = 32 * 2 * 6;   // ScoutCand per lane per half
+constexpr int PB_TCHUNK = 4;                   // trace steps per 128-bit store (must stay 4: uint4)
 
 // ---------------------------------------------------------------------------------------------------
 // encode: one byte in, one byte out (code << 4).  16 bytes per thread, fully coalesced.
@@ -172,8 +173,8 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
     // (grid-stride loop): it is rewritten for every slot and lives in L2.  Layout of the per-warp scratch:
     // [trace max_steps*WPS*32 words] [HBUF_SMEM ? nothing : packed bases SPW*max_n words].
     // Shared memory per warp: [HBUF_SMEM ? packed bases SPW*max_n words : nothing] [scout scratch].
-    const size_t trace_words = (size_t)max_steps * WPS * 32;
-    const size_t gwarp_words = trace_words + (HBUF_SMEM ? 0 : (size_t)SPW * max_n);
+    const size_t trace_words = (size_t)((max_steps + PB_TCHUNK - 1) / PB_TCHUNK) * PB_TCHUNK * WPS * 32;
+    const size_t gwarp_words = trace_words + (HBUF_SMEM ? 0 : (((size_t)SPW * max_n + 3) & ~(size_t)3));
     uint32_t *gw = gtrace + (size_t)wglobal * gwarp_words;
     uint32_t *tr = gw;
     const int per_warp_words = (HBUF_SMEM ? SPW * max_n : 0) + PB_SCRATCH_WORDS;
@@ -209,26 +210,70 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
         T = __reduce_max_sync(0xffffffffu, T);
         __syncwarp();
 
-#pragma unroll 2
-        for (int t = 0; t < T; ++t) {
-            uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
-            uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
-            if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
-            const int j = t - g + 1;
-            if (j >= 1 && j <= nmax) {
+        // PB_TCHUNK steps of trace words are collected in registers and written as one 128-bit store per lane:
+        // a warp store covers 512 contiguous bytes, and the traceback later gets 4 consecutive steps of a lane
+        // with a single (L2-latency) load.
+        // Phase 1 (hot, unrolled): the leading steps in which every lane of the warp is in an inner column -- only the
+        // fast scout.  Phase 2 (cold, not unrolled): the last G-1+ steps with the general scout (final columns).
+        const int T4 = (T + PB_TCHUNK - 1) & ~(PB_TCHUNK - 1);
+        int tfast = need_track ? max(nmin - 1, 0) : T4;
+        tfast = __reduce_min_sync(0xffffffffu, tfast) & ~(PB_TCHUNK - 1);
+        int t0 = 0;
+        for (; t0 < tfast; t0 += PB_TCHUNK) {
+            uint32_t buf[PB_TCHUNK][WPS];
+#pragma unroll
+            for (int u = 0; u < PB_TCHUNK; ++u) {
+                const int t = t0 + u;
+                uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
+                uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
+                if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
+                const int j = t - g + 1;
                 uint32_t tw[WPS];
-                if (need_track && j >= nmin) {
-                    // final column of a half (or halves of different lengths): rare, general scout
-                    uint32_t vr[R];
-                    lane_step<R, true, true>(L, recvS, recvV, hbuf[j - 1], sc, tw, vr);
-                    lane_track_general<R>(L, g, j, make_geom(nA, mA, G, R), make_geom(nB, mB, G, R), vr, sc);
-                } else {
+#pragma unroll
+                for (int w = 0; w < WPS; ++w) tw[w] = 0u;
+                if (j >= 1 && j <= nmax) {
                     lane_step<R, true, false>(L, recvS, recvV, hbuf[j - 1], sc, tw);
                     if (need_track) lane_track_lastrow<R>(L, j, sc);
                 }
 #pragma unroll
-                for (int w = 0; w < WPS; ++w) tr[((size_t)t * WPS + w) * 32 + lane] = tw[w];
+                for (int w = 0; w < WPS; ++w) buf[u][w] = tw[w];
             }
+#pragma unroll
+            for (int w = 0; w < WPS; ++w) {
+                uint4 v = make_uint4(buf[0][w], buf[1][w], buf[2][w], buf[3][w]);
+                *reinterpret_cast<uint4 *>(tr + (((size_t)(t0 / PB_TCHUNK) * WPS + w) * 32 + lane) * PB_TCHUNK) = v;
+            }
+        }
+        for (; t0 < T4; t0 += PB_TCHUNK) {
+            uint4 acc[WPS];
+#pragma unroll
+            for (int w = 0; w < WPS; ++w) acc[w] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+            for (int u = 0; u < PB_TCHUNK; ++u) {
+                const int t = t0 + u;
+                uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
+                uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
+                if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
+                const int j = t - g + 1;
+                uint32_t tw[WPS];
+#pragma unroll
+                for (int w = 0; w < WPS; ++w) tw[w] = 0u;
+                if (j >= 1 && j <= nmax) {
+                    uint32_t vr[R];
+                    lane_step<R, true, true>(L, recvS, recvV, hbuf[j - 1], sc, tw, vr);
+                    if (need_track) {
+                        if (j >= nmin) lane_track_general<R>(L, g, j, make_geom(nA, mA, G, R), make_geom(nB, mB, G, R), vr, sc);
+                        else lane_track_lastrow<R>(L, j, sc);
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < WPS; ++w) {
+                    if (u == 0) acc[w].x = tw[w]; else if (u == 1) acc[w].y = tw[w]; else if (u == 2) acc[w].z = tw[w]; else acc[w].w = tw[w];
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < WPS; ++w)
+                *reinterpret_cast<uint4 *>(tr + (((size_t)(t0 / PB_TCHUNK) * WPS + w) * 32 + lane) * PB_TCHUNK) = acc[w];
         }
         // scout candidates -> shared scratch, then lanes g==0 / g==1 finish halves A / B
         cand[lane] = make_cand<R>(L, 0, sc);
@@ -249,11 +294,18 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
                 }
                 const uint8_t *ad = ads + tk.ad_off;
                 const int lane_base = grp * G;
+                int cached_c = -1, cached_g = -1;
+                uint4 cv = make_uint4(0u, 0u, 0u, 0u);
                 auto nib = [&](int jl, int i) -> uint32_t {
                     const int q = i + gh.pad - 1;
                     const int gg = q / R, r = q % R;
                     const int t = jl - 1 + gg;
-                    const uint32_t w = tr[((size_t)t * WPS + trace_word<R>(h, r)) * 32 + lane_base + gg];
+                    const int c = t / PB_TCHUNK, u = t % PB_TCHUNK;
+                    if (c != cached_c || gg != cached_g) {     // one load serves up to PB_TCHUNK path steps
+                        cv = *reinterpret_cast<const uint4 *>(tr + (((size_t)c * WPS + trace_word<R>(h, r)) * 32 + lane_base + gg) * PB_TCHUNK);
+                        cached_c = c; cached_g = gg;
+                    }
+                    const uint32_t w = (u == 0) ? cv.x : (u == 1) ? cv.y : (u == 2) ? cv.z : cv.w;
                     return (w >> trace_shift<R>(h, r)) & 15u;
                 };
                 auto eq = [&](int jl, int i) -> bool {   // the slot's packed bases are still staged in hbuf
