@@ -59,7 +59,7 @@ struct Options {
     int64_t direct_max = 512;      // longest sequence aligned in a single (trace) pass
     int64_t chunk_tasks = 1 << 17; // alignments per pipeline chunk (host-buffer API)
     int64_t device_chunk_tasks = 8 << 20; // alignments per launch group (device-resident API)
-    int64_t chunk_bytes = 1ll << 30;
+    int64_t chunk_bytes = 64ll << 20;   // sequence bytes per pipeline chunk (host-buffer API)
     int wpb = 0;                   // warps per block override for trace kernel (0 = auto)
     int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
 };
@@ -314,19 +314,39 @@ int plan_adapters(Engine &E, cudaStream_t stream, const uint8_t *adapters, const
     P.sc = make_scoring(ma, mi, go, ge);
     std::vector<ClassPlan> cl(N_CLASSES);
     for (int c = 0; c < N_CLASSES; ++c) cl[c].cls = c;
+    // Slots pair two alignments.  In cross mode a slot is (one read, two adapters): sort the adapters by length and
+    // pair neighbours; the pair runs in the row-capacity class of its longer member, provided the shorter one would
+    // not waste more than ~1/3 of the rows (otherwise it stays single and pairs two consecutive reads instead).
+    std::vector<int32_t> order16;
     for (int a = 0; a < n_adapters; ++a) {
         int m = ad_off[a + 1] - ad_off[a];
         if (m < 0) return fail(PB200_ERR_ARG, "adapter offsets not monotone");
         int c = class_of(P.si, m);
-        cl[c].ad_ids.push_back(a);
-        cl[c].m_max = std::max(cl[c].m_max, m);
+        if (c == GENERIC_CLASS) { cl[c].ad_ids.push_back(a); cl[c].m_max = std::max(cl[c].m_max, m); }
+        else order16.push_back(a);
     }
-    for (auto &c : cl) {
-        std::stable_sort(c.ad_ids.begin(), c.ad_ids.end(), [&](int x, int y) {
-            return (ad_off[x + 1] - ad_off[x]) > (ad_off[y + 1] - ad_off[y]);
-        });
-        if (!c.ad_ids.empty()) P.classes.push_back(c);
+    auto len = [&](int a) { return ad_off[a + 1] - ad_off[a]; };
+    std::stable_sort(order16.begin(), order16.end(), [&](int x, int y) { return len(x) > len(y); });
+    std::vector<int32_t> single_of(N_CLASSES, -1);
+    for (size_t i = 0; i < order16.size();) {
+        const int a = order16[i], ca = class_of(P.si, len(a));
+        const int capa = class_G(ca) * class_R(ca);
+        if (i + 1 < order16.size()) {
+            const int b = order16[i + 1], cb = class_of(P.si, len(b));
+            const int capb = class_G(cb) * class_R(cb);
+            if (3 * capa <= 4 * capb) {            // cap ratio <= 1.33: share a slot
+                cl[ca].ad_ids.push_back(a); cl[ca].ad_ids.push_back(b);
+                cl[ca].m_max = std::max(cl[ca].m_max, len(a));
+                i += 2;
+                continue;
+            }
+        }
+        single_of[ca] = a;                          // at most one per class (it sits at the class's lower boundary)
+        cl[ca].m_max = std::max(cl[ca].m_max, len(a));
+        i += 1;
     }
+    for (int c = 0; c < GENERIC_CLASS; ++c) if (single_of[c] >= 0) cl[c].ad_ids.push_back(single_of[c]);
+    for (auto &c : cl) if (!c.ad_ids.empty()) P.classes.push_back(c);
     const size_t ad_bytes = (size_t)ad_off[n_adapters];
     if (int rc = E.ad_raw.ensure(ad_bytes + 16)) return rc;
     if (int rc = E.ad_codes.ensure(ad_bytes + 16)) return rc;
