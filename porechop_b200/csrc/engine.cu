@@ -61,6 +61,7 @@ struct Options {
     int64_t device_chunk_tasks = 8 << 20; // alignments per launch group (device-resident API)
     int64_t chunk_bytes = 64ll << 20;   // sequence bytes per pipeline chunk (host-buffer API)
     int wpb = 0;                   // warps per block override for trace kernel (0 = auto)
+    int scratch_mb = 128;          // cap on the resident trace scratch (MB); 72 keeps it L2-resident at ~10% lower speed
     int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
 };
 Options g_opt;
@@ -73,6 +74,7 @@ void load_env_options() {
         if (const char *v = getenv("PB200_DIRECT_MAX")) g_opt.direct_max = atoll(v);
         if (const char *v = getenv("PB200_CHUNK_TASKS")) g_opt.chunk_tasks = std::max(1ll, atoll(v));
         if (const char *v = getenv("PB200_WPB")) g_opt.wpb = atoi(v);
+        if (const char *v = getenv("PB200_SCRATCH_MB")) g_opt.scratch_mb = std::max(1, atoi(v));
         if (const char *v = getenv("PB200_HBUF")) g_opt.hbuf_mode = !strcmp(v, "smem") ? 1 : !strcmp(v, "global") ? 2 : 0;
     });
 }
@@ -180,7 +182,7 @@ void timed_end(Engine &E, cudaStream_t s, TimedLaunch &tl, bool on) {
 }
 
 template <int G, int R, bool HS>
-int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const Task *tasks, int64_t n_tasks, int max_n,
+int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, int max_n,
                          const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
     constexpr int SPW = 32 / G;
     constexpr int WPS = TraceWords<R>::value;
@@ -194,18 +196,24 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const Task *t
     if (bps < 1) bps = 1;
     const size_t gwarp_bytes = ((size_t)((max_steps + PB_TCHUNK - 1) / PB_TCHUNK) * PB_TCHUNK * WPS * 32 +
                                 (HS ? 0 : (((size_t)SPW * max_n + 3) & ~(size_t)3))) * 4;
-    // bound the scratch (~12 GB) for very long single-pass alignments
-    int64_t max_warps = std::max<int64_t>(wpb, (int64_t)((12ull << 30) / std::max<size_t>(gwarp_bytes, 1)));
-    while (bps > 1 && (int64_t)bps * E.sm_count * wpb > max_warps) --bps;
+    // The trace scratch of the resident grid is rewritten slot after slot and mostly lives in L2.  `scratch_mb` caps
+    // it (whole blocks per SM, never below 2): measured on B200 for 150x28 windows, 72 MB (3 blocks/SM) keeps the
+    // trace L2-resident (DRAM traffic 1.9x the algorithmic bytes) at ~10 % lower kernel throughput than the default
+    // 128 MB (5 blocks/SM), where ~1.1 GB of dead/dirty trace lines per launch are written back to HBM off the critical
+    // path (8 % of the HBM bandwidth).  See DESIGN.md, "trace scratch".
+    int64_t max_blocks = std::max<int64_t>(2 * E.sm_count, (int64_t)(((size_t)g_opt.scratch_mb << 20) / std::max<size_t>(gwarp_bytes * wpb, 1)));
+    max_blocks -= max_blocks % E.sm_count;     // whole blocks per SM: the grid-stride loop gives every block the same work
+    const int64_t n_tasks = ts.n_tasks;
     const int64_t n_slots = (n_tasks + 1) / 2;
     const int64_t n_wslots = (n_slots + SPW - 1) / SPW;
     int64_t blocks = (n_wslots + wpb - 1) / wpb;
-    blocks = std::min<int64_t>(blocks, (int64_t)bps * E.sm_count);
+    blocks = std::min<int64_t>(blocks, std::min<int64_t>((int64_t)bps * E.sm_count, max_blocks));
+    if ((size_t)blocks * wpb * gwarp_bytes > (24ull << 30)) blocks = std::max<int64_t>(1, (int64_t)((24ull << 30) / (gwarp_bytes * wpb)));
     if (blocks <= 0) return 0;
     if (int rc = S.gtrace.ensure((size_t)blocks * wpb * gwarp_bytes)) return rc;
     TimedLaunch tl; bool on;
     timed_begin(E, stream, tl, on);
-    kern<<<(unsigned)blocks, wpb * 32, smem_bytes, stream>>>(tasks, n_tasks, seq_codes, ad_codes, sc, out,
+    kern<<<(unsigned)blocks, wpb * 32, smem_bytes, stream>>>(ts, seq_codes, ad_codes, sc, out,
                                                               S.gtrace.as<uint32_t>(), max_steps, max_n, status);
     timed_end(E, stream, tl, on);
     g_launches++;
@@ -214,20 +222,20 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const Task *t
 }
 
 template <int G, int R>
-int launch_trace(Engine &E, Stage &S, cudaStream_t stream, const Task *tasks, int64_t n_tasks, int max_n,
+int launch_trace(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, int max_n,
                  const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
     constexpr int SPW = 32 / G;
     if (max_n < 1) max_n = 1;
     // packed read bases of a slot are staged in shared memory when they fit (<= 12 KB per warp), else in global scratch
     const bool hs = g_opt.hbuf_mode == 1 ? true : g_opt.hbuf_mode == 2 ? false : ((size_t)SPW * max_n * 4 <= 12288);
     if (hs && (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + PB_SCRATCH_WORDS) * 4 <= E.smem_optin)
-        return launch_trace_variant<G, R, true>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
-    return launch_trace_variant<G, R, false>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+        return launch_trace_variant<G, R, true>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
+    return launch_trace_variant<G, R, false>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
 }
 
-int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const Task *tasks, int64_t n_tasks, int max_n,
+int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const TaskSrc &ts, int max_n,
                        const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
-#define PB_CASE(K, GG, RR) case K: return launch_trace<GG, RR>(E, S, stream, tasks, n_tasks, max_n, seq_codes, ad_codes, sc, out, status);
+#define PB_CASE(K, GG, RR) case K: return launch_trace<GG, RR>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
     switch (cls) {
         PB_CASE(0, 4, 5) PB_CASE(1, 4, 6) PB_CASE(2, 4, 7) PB_CASE(3, 4, 8)
         PB_CASE(4, 8, 5) PB_CASE(5, 8, 6) PB_CASE(6, 8, 7) PB_CASE(7, 8, 8)
@@ -239,13 +247,14 @@ int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const 
 }
 
 template <int G, int R>
-int launch_score(Engine &E, cudaStream_t stream, const Task *tasks, int64_t n_tasks, unsigned long long *counter,
+int launch_score(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsigned long long *counter,
                  const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, EndCell *ends) {
     auto kern = score_kernel<G, R>;
     int bps = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, PB_WARPS_PER_BLOCK * 32, 0));
     if (bps < 1) bps = 1;
     constexpr int SPW = 32 / G;
+    const int64_t n_tasks = ts.n_tasks;
     const int64_t n_slots = (n_tasks + 1) / 2;
     int64_t blocks = (n_slots + SPW * PB_WARPS_PER_BLOCK - 1) / (SPW * PB_WARPS_PER_BLOCK);
     blocks = std::min<int64_t>(blocks, (int64_t)bps * E.sm_count);
@@ -253,20 +262,20 @@ int launch_score(Engine &E, cudaStream_t stream, const Task *tasks, int64_t n_ta
     CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
     TimedLaunch tl; bool on;
     timed_begin(E, stream, tl, on);
-    kern<<<(unsigned)blocks, PB_WARPS_PER_BLOCK * 32, 0, stream>>>(tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
+    kern<<<(unsigned)blocks, PB_WARPS_PER_BLOCK * 32, 0, stream>>>(ts, counter, seq_codes, ad_codes, sc, ends);
     timed_end(E, stream, tl, on);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
 }
-int launch_score_class(Engine &E, cudaStream_t stream, int cls, const Task *tasks, int64_t n_tasks,
+int launch_score_class(Engine &E, cudaStream_t stream, int cls, const TaskSrc &ts,
                        unsigned long long *counter, const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc,
                        EndCell *ends) {
     switch (cls / 4) {
-        case 0: return launch_score<4, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
-        case 1: return launch_score<8, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
-        case 2: return launch_score<16, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
-        case 3: return launch_score<32, 8>(E, stream, tasks, n_tasks, counter, seq_codes, ad_codes, sc, ends);
+        case 0: return launch_score<4, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
+        case 1: return launch_score<8, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
+        case 2: return launch_score<16, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
+        case 3: return launch_score<32, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
     }
     return fail(PB200_ERR_INTERNAL, "bad class");
 }
@@ -280,26 +289,27 @@ int launch_encode(cudaStream_t stream, const uint8_t *in, uint8_t *out, int64_t 
     return 0;
 }
 
-// Run every task of one class: tasks[0..n_tasks) are already built on the device in slot order.
-int run_class_tasks(Engine &E, Stage &S, cudaStream_t stream, int cls, int m_max, int64_t n_tasks, int64_t max_n,
+// Run every task of one class; `ts` describes the tasks in slot order (explicit records or the cross product).
+int run_class_tasks(Engine &E, Stage &S, cudaStream_t stream, int cls, int m_max, const TaskSrc &ts, int64_t max_n,
                     const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, const SchemeInfo &si,
                     int32_t *out, int *status, unsigned long long *counter) {
+    const int64_t n_tasks = ts.n_tasks;
     if (n_tasks <= 0) return 0;
-    Task *tasks = S.tasks.as<Task>();
     int64_t W = si.bounded ? (int64_t)m_max + ((int64_t)m_max * si.wnum) / si.wden : (int64_t)1 << 40;
     const bool two_pass = si.bounded && max_n > g_opt.direct_max && W + 1 < max_n;
-    if (!two_pass) return launch_trace_class(E, S, stream, cls, tasks, n_tasks, (int)max_n, seq_codes, ad_codes, sc, out, status);
+    if (!two_pass) return launch_trace_class(E, S, stream, cls, ts, (int)max_n, seq_codes, ad_codes, sc, out, status);
     if (int rc = S.ends.ensure((size_t)n_tasks * sizeof(EndCell))) return rc;
     if (int rc = S.tasks2.ensure((size_t)n_tasks * sizeof(Task))) return rc;
-    if (int rc = launch_score_class(E, stream, cls, tasks, n_tasks, counter, seq_codes, ad_codes, sc, S.ends.as<EndCell>())) return rc;
+    if (int rc = launch_score_class(E, stream, cls, ts, counter, seq_codes, ad_codes, sc, S.ends.as<EndCell>())) return rc;
     {
         int64_t blocks = (n_tasks + 255) / 256;
-        window_tasks_kernel<<<(unsigned)blocks, 256, 0, stream>>>(tasks, S.ends.as<EndCell>(), S.tasks2.as<Task>(), n_tasks,
-                                                                   si.wnum, si.wden);
+        window_tasks_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ts, S.ends.as<EndCell>(), S.tasks2.as<Task>(), si.wnum, si.wden);
         g_launches++;
         CK(cudaGetLastError());
     }
-    return launch_trace_class(E, S, stream, cls, S.tasks2.as<Task>(), n_tasks, (int)W, seq_codes, ad_codes, sc, out, status);
+    TaskSrc t2 = ts;
+    t2.tasks = S.tasks2.as<Task>();
+    return launch_trace_class(E, S, stream, cls, t2, (int)W, seq_codes, ad_codes, sc, out, status);
 }
 
 // Adapter-side planning shared by all entry points.
@@ -423,19 +433,14 @@ int run_cross_chunk(Engine &E, Stage &S, cudaStream_t stream, const AdapterPlan 
                                            E.ad_codes.as<uint8_t>(), P.sc, d_out)) return rc;
             continue;
         }
-        const int64_t n_tasks = cnt * (int64_t)C.ad_ids.size();
-        if (n_tasks == 0) continue;
-        if (int rc = S.tasks.ensure((size_t)n_tasks * sizeof(Task))) return rc;
-        {
-            int64_t blocks = (n_tasks + 255) / 256;
-            build_tasks_cross_kernel<<<(unsigned)blocks, 256, 0, stream>>>(S.tasks.as<Task>(), n_tasks, d_cls,
-                                                                            (int)C.ad_ids.size(), cnt, d_seq_off,
-                                                                            E.ad_off.as<int32_t>(), n_adapters);
-            g_launches++;
-            CK(cudaGetLastError());
-        }
+        TaskSrc ts;
+        ts.tasks = nullptr;                                  // cross product, synthesised in the kernels
+        ts.n_tasks = cnt * (int64_t)C.ad_ids.size();
+        ts.cls_ad = d_cls; ts.n_cls_ad = (int32_t)C.ad_ids.size(); ts.n_adapters = n_adapters;
+        ts.n_seqs = cnt; ts.seq_off = d_seq_off; ts.ad_off = E.ad_off.as<int32_t>();
+        if (ts.n_tasks == 0) continue;
         (void)base_off;
-        if (int rc = run_class_tasks(E, S, stream, C.cls, C.m_max, n_tasks, max_n, seq_codes, E.ad_codes.as<uint8_t>(), P.sc,
+        if (int rc = run_class_tasks(E, S, stream, C.cls, C.m_max, ts, max_n, seq_codes, E.ad_codes.as<uint8_t>(), P.sc,
                                      P.si, d_out, status, counter)) return rc;
     }
     return 0;
@@ -610,7 +615,11 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
             S.seq_off.as<int64_t>(), E.ad_off.as<int32_t>());
         g_launches++;
         CK(cudaGetLastError());
-        if (int rc = run_class_tasks(E, S, stream, c, m_max, n_tasks, max_n, S.seq_codes.as<uint8_t>(), E.ad_codes.as<uint8_t>(),
+        TaskSrc ts;
+        ts.tasks = S.tasks.as<Task>(); ts.n_tasks = n_tasks;
+        ts.cls_ad = nullptr; ts.n_cls_ad = 0; ts.n_adapters = n_adapters; ts.n_seqs = n_seqs;
+        ts.seq_off = S.seq_off.as<int64_t>(); ts.ad_off = E.ad_off.as<int32_t>();
+        if (int rc = run_class_tasks(E, S, stream, c, m_max, ts, max_n, S.seq_codes.as<uint8_t>(), E.ad_codes.as<uint8_t>(),
                                      P.sc, P.si, S.out.as<int32_t>(), status, counter)) return rc;
     }
     CK(cudaMemcpyAsync(out, S.out.p, (size_t)n_pairs * PB_REC * 4, cudaMemcpyDeviceToHost, stream));
@@ -784,6 +793,7 @@ int pb200SetOption(const char *name, const char *value) {
     } else if (!strcmp(name, "direct_max")) g_opt.direct_max = atoll(value);
     else if (!strcmp(name, "chunk_tasks")) g_opt.chunk_tasks = std::max(1ll, atoll(value));
     else if (!strcmp(name, "wpb")) g_opt.wpb = atoi(value);
+    else if (!strcmp(name, "scratch_mb")) g_opt.scratch_mb = std::max(1, atoi(value));
     else if (!strcmp(name, "hbuf")) g_opt.hbuf_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;
     else return PB200_ERR_ARG;
     return 0;

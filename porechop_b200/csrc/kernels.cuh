@@ -55,34 +55,44 @@ __global__ void max_len_kernel(const int64_t *__restrict__ off, int64_t n, unsig
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Task construction.
-// Cross mode: every sequence x every adapter of one class.  `cls_ad` lists the class's adapter ids sorted
-// by length; adapters 2q and 2q+1 share a slot (same read, two adapters); an odd last adapter pairs two
-// consecutive reads instead.  Task index layout: pair q occupies [q*2*n_seqs, (q+1)*2*n_seqs) as
-// (s0,a),(s0,a'),(s1,a),(s1,a')...; the odd adapter occupies the tail [n_pairs*2*n_seqs, +n_seqs).
-__global__ void build_tasks_cross_kernel(Task *__restrict__ tasks, int64_t n_tasks, const int32_t *__restrict__ cls_ad,
-                                         int n_cls_ad, int64_t n_seqs, const int64_t *__restrict__ seq_off,
-                                         const int32_t *__restrict__ ad_off, int n_adapters) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_tasks) return;
-    const int n_full = n_cls_ad / 2;
-    const int64_t paired = (int64_t)n_full * 2 * n_seqs;
+// Task sources.
+// Cross mode: every sequence x every adapter of one class; the Task records are never materialised -- the kernels
+// synthesise them from the offset arrays (saves 64 B written + 128 B read per alignment).  `cls_ad` lists the class's
+// adapter ids; adapters 2q and 2q+1 share a slot (same read, two adapters); an odd last adapter pairs two consecutive
+// reads instead.  Task index layout: pair q occupies [q*2*n_seqs, (q+1)*2*n_seqs) as (s0,a),(s0,a'),(s1,a),(s1,a')...;
+// the odd adapter occupies the tail [n_full*2*n_seqs, +n_seqs).
+struct TaskSrc {
+    const Task *tasks;        // explicit task records (pair-list mode, windowed second pass) or nullptr = cross mode
+    int64_t n_tasks;
+    const int32_t *cls_ad;    // cross mode: adapter ids of the class
+    int32_t n_cls_ad;
+    int32_t n_adapters;       // adapters per sequence in the caller's record layout (out index = s*n_adapters + a)
+    int64_t n_seqs;
+    const int64_t *seq_off;
+    const int32_t *ad_off;
+};
+
+__device__ __forceinline__ Task cross_task(const TaskSrc &ts, int64_t k) {
+    const int n_full = ts.n_cls_ad / 2;
+    const int64_t paired = (int64_t)n_full * 2 * ts.n_seqs;
     int64_t s; int a;
     if (k < paired) {
-        int64_t q = k / (2 * n_seqs), rem = k % (2 * n_seqs);
-        s = rem >> 1; a = cls_ad[2 * q + (rem & 1)];
+        int64_t q = k / (2 * ts.n_seqs), rem = k - q * (2 * ts.n_seqs);
+        s = rem >> 1; a = __ldg(ts.cls_ad + 2 * q + (rem & 1));
     } else {
-        s = k - paired; a = cls_ad[n_cls_ad - 1];
+        s = k - paired; a = __ldg(ts.cls_ad + ts.n_cls_ad - 1);
     }
     Task t;
-    t.seq_off = seq_off[s];
-    t.n = (int32_t)(seq_off[s + 1] - seq_off[s]);
-    t.m = ad_off[a + 1] - ad_off[a];
-    t.ad_off = ad_off[a];
-    t.out_idx = (int32_t)(s * n_adapters + a);
+    const int64_t o0 = __ldg(ts.seq_off + s), o1 = __ldg(ts.seq_off + s + 1);
+    const int32_t a0 = __ldg(ts.ad_off + a), a1 = __ldg(ts.ad_off + a + 1);
+    t.seq_off = o0;
+    t.n = (int32_t)(o1 - o0);
+    t.m = a1 - a0;
+    t.ad_off = a0;
+    t.out_idx = (int32_t)(s * ts.n_adapters + a);
     t.flags = 0; t.end_j = 0; t.end_i = 0; t.end_corr = 0; t.end_score = 0;
     t.col0 = 0; t.n_total = t.n; t.pad0 = t.pad1 = t.pad2 = 0;
-    tasks[k] = t;
+    return t;
 }
 // Pair-list mode: `order` is the host-computed slot order of pair indices for one class.
 __global__ void build_tasks_pairs_kernel(Task *__restrict__ tasks, int64_t n_tasks, const int32_t *__restrict__ order,
@@ -103,14 +113,30 @@ __global__ void build_tasks_pairs_kernel(Task *__restrict__ tasks, int64_t n_tas
     tasks[k] = t;
 }
 
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Task get_task(const TaskSrc &ts, int64_t idx) {
+    Task t;
+    if (idx < ts.n_tasks) {
+        if (ts.tasks == nullptr) return cross_task(ts, idx);
+        const int4 *p = reinterpret_cast<const int4 *>(ts.tasks + idx);
+        int4 *q = reinterpret_cast<int4 *>(&t);
+        q[0] = __ldcs(p); q[1] = __ldcs(p + 1); q[2] = __ldcs(p + 2); q[3] = __ldcs(p + 3);   // read once: evict-first in L2
+    } else {
+        t.seq_off = 0; t.n = 0; t.m = 0; t.ad_off = 0; t.out_idx = -1; t.flags = 0; t.end_j = 0; t.end_i = 0;
+        t.end_corr = 0; t.end_score = 0; t.col0 = 0; t.n_total = 0; t.pad0 = t.pad1 = t.pad2 = 0;
+    }
+    return t;
+}
+
 // Score pass results -> windowed tasks.  The traced path has score >= 0, hence at most m diagonals and
 // floor(m*max(ma,mi,0)/min(|go|,|ge|)) read-only gap columns: it starts no further than `wbound(m)` columns
 // left of its end (DESIGN.md "window bound").  wnum/wden: W = m + (m*wnum)/wden.
-__global__ void window_tasks_kernel(const Task *__restrict__ in, const EndCell *__restrict__ ends, Task *__restrict__ out,
-                                    int64_t n_tasks, int wnum, int wden) {
+__global__ void window_tasks_kernel(const TaskSrc ts, const EndCell *__restrict__ ends, Task *__restrict__ out,
+                                    int wnum, int wden) {
+    const int64_t n_tasks = ts.n_tasks;
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_tasks) return;
-    Task t = in[k];
+    Task t = get_task(ts, k);
     EndCell e = ends[k];
     if (t.n > 0 && t.m > 0) {
         int64_t W = (int64_t)t.m + ((int64_t)t.m * wnum) / wden;
@@ -128,19 +154,6 @@ __global__ void window_tasks_kernel(const Task *__restrict__ in, const EndCell *
     out[k] = t;
 }
 
-// ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ Task load_task(const Task *__restrict__ tasks, int64_t idx, int64_t n_tasks) {
-    Task t;
-    if (idx < n_tasks) {
-        const int4 *p = reinterpret_cast<const int4 *>(tasks + idx);
-        int4 *q = reinterpret_cast<int4 *>(&t);
-        q[0] = __ldg(p); q[1] = __ldg(p + 1); q[2] = __ldg(p + 2); q[3] = __ldg(p + 3);
-    } else {
-        t.seq_off = 0; t.n = 0; t.m = 0; t.ad_off = 0; t.out_idx = -1; t.flags = 0; t.end_j = 0; t.end_i = 0;
-        t.end_corr = 0; t.end_score = 0; t.col0 = 0; t.n_total = 0; t.pad0 = t.pad1 = t.pad2 = 0;
-    }
-    return t;
-}
 
 __device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
     // byte1 <- bA, byte3 <- bB (code<<4 in a byte becomes code<<12 in each half)
@@ -155,7 +168,7 @@ __device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
 // bounded by the resident grid and stays in L2.
 template <int G, int R, bool HBUF_SMEM>
 __global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_TRACE_MIN_BLOCKS)
-trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__restrict__ seq,
+trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
              const uint8_t *__restrict__ ads, Scoring sc, int32_t *__restrict__ out, uint32_t *__restrict__ gtrace,
              int max_steps, int max_n, int *__restrict__ status) {
     constexpr int SPW = 32 / G;
@@ -166,6 +179,7 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
     const int warps_per_block = blockDim.x >> 5;
     const int64_t total_warps = (int64_t)gridDim.x * warps_per_block;
     const int64_t wglobal = (int64_t)blockIdx.x * warps_per_block + warp;
+    const int64_t n_tasks = ts.n_tasks;
     const int64_t n_slots = (n_tasks + 1) / 2;
     const int64_t n_wslots = (n_slots + SPW - 1) / SPW;
 
@@ -188,15 +202,15 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
         Lane<R> L;
         {
             // everything that is only needed to set the slot up lives in this scope (keeps the loop's register set small)
-            const Task tA = load_task(tasks, slot * 2, n_tasks);
-            const Task tB = load_task(tasks, slot * 2 + 1, n_tasks);
+            const Task tA = get_task(ts, slot * 2);
+            const Task tB = get_task(ts, slot * 2 + 1);
             nA = tA.n; nB = tB.n; mA = tA.m; mB = tB.m;
             nmax = max(nA, nB);
             const uint8_t *seqA = seq + tA.seq_off, *seqB = seq + tB.seq_off;
             // stage the packed read bases of the slot's columns (each lane builds every G-th column)
             for (int c = g; c < nmax; c += G) {
-                uint32_t bA = (c < nA) ? (uint32_t)__ldg(seqA + c) : (uint32_t)PB_PAD_H;
-                uint32_t bB = (c < nB) ? (uint32_t)__ldg(seqB + c) : (uint32_t)PB_PAD_H;
+                uint32_t bA = (c < nA) ? (uint32_t)__ldcs(seqA + c) : (uint32_t)PB_PAD_H;
+                uint32_t bB = (c < nB) ? (uint32_t)__ldcs(seqB + c) : (uint32_t)PB_PAD_H;
                 hbuf[c] = pack_bases(bA, bB);
             }
             lane_init<R>(L, g, G, sc, ads + tA.ad_off, mA, (tA.flags & TASK_LEFT_INF) != 0, ads + tB.ad_off, mB,
@@ -282,7 +296,7 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
 #ifndef PB_EXPERIMENT_SKIP_TRACEBACK   // (profiling experiments only: measure the forward pass alone)
         if (g < 2) {
             const int h = g;
-            const Task tk = load_task(tasks, slot * 2 + h, n_tasks);
+            const Task tk = get_task(ts, slot * 2 + h);
             const HalfGeom gh = make_geom(tk.n, tk.m, G, R);
             if (tk.out_idx >= 0) {
                 EndCell end;
@@ -316,10 +330,15 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
                 if (st) atomicOr(status, 1);
                 int32_t *o = out + (size_t)tk.out_idx * PB_REC;
 #pragma unroll
-                for (int k = 0; k < PB_REC; ++k) o[k] = rec[k];
+                for (int k = 0; k < PB_REC; ++k) __stcs(o + k, rec[k]);
             }
         }
 #endif
+        __syncwarp();
+        // The slot's trace is dead now: drop its (dirty) L2 lines instead of letting them be written back to HBM
+        // when the next slots push them out -- the scratch of all resident warps is about as large as L2.
+        for (int l = lane; l < T4 * WPS; l += 32)
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(tr + (size_t)l * 32) : "memory");
         __syncwarp();
     }
 }
@@ -330,12 +349,13 @@ trace_kernel(const Task *__restrict__ tasks, int64_t n_tasks, const uint8_t *__r
 // groups never wait for each other's read lengths.
 template <int G, int R>
 __global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32)
-score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long *__restrict__ counter,
+score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
              const uint8_t *__restrict__ seq, const uint8_t *__restrict__ ads, Scoring sc, EndCell *__restrict__ ends) {
     __shared__ ScoutCand scratch[PB_WARPS_PER_BLOCK][2 * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, g = lane % G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    const int64_t n_tasks = ts.n_tasks;
     const int64_t n_slots = (n_tasks + 1) / 2;
     ScoutCand *cand = scratch[warp];
 
@@ -368,8 +388,8 @@ score_kernel(const Task *__restrict__ tasks, int64_t n_tasks, unsigned long long
                 exhausted = true; slot = -1; T = 0; t = 0; nmax = 0;
             } else {
                 slot = (int64_t)s;
-                tA = load_task(tasks, slot * 2, n_tasks);
-                tB = load_task(tasks, slot * 2 + 1, n_tasks);
+                tA = get_task(ts, slot * 2);
+                tB = get_task(ts, slot * 2 + 1);
                 gA = make_geom(tA.n, tA.m, G, R); gB = make_geom(tB.n, tB.m, G, R);
                 nmax = max(tA.n, tB.n);
                 seqA = seq + tA.seq_off; seqB = seq + tB.seq_off;
