@@ -82,7 +82,7 @@ void load_env_options() {
 constexpr int NSTAGE = 3;
 struct Stage {
     cudaStream_t stream = nullptr;
-    DevBuf seq_raw, seq_codes, seq_off, tasks, tasks2, ends, out, order, pair_seq, pair_ad, gtrace, misc;
+    DevBuf seq_raw, seq_codes, seq_off, tasks, tasks2, ends, out, order, bins, pair_seq, pair_ad, gtrace, misc;
 };
 
 struct ClassPlan {
@@ -423,6 +423,20 @@ int run_cross_chunk(Engine &E, Stage &S, cudaStream_t stream, const AdapterPlan 
     if (int rc = S.misc.ensure(64)) return rc;
     int *status = S.misc.as<int>();
     unsigned long long *counter = reinterpret_cast<unsigned long long *>(S.misc.as<char>() + 16);
+    // long reads (two-pass path): process sequences longest first
+    const int32_t *d_order = nullptr;
+    if (P.si.bounded && max_n > g_opt.direct_max && cnt > 1) {
+        if (int rc = S.order.ensure((size_t)cnt * 4)) return rc;
+        if (int rc = S.bins.ensure((size_t)PB_ORDER_BINS * 4)) return rc;
+        CK(cudaMemsetAsync(S.bins.p, 0, (size_t)PB_ORDER_BINS * 4, stream));
+        const unsigned nb = (unsigned)((cnt + 255) / 256);
+        order_hist_kernel<<<nb, 256, 0, stream>>>(d_seq_off, cnt, max_n, S.bins.as<unsigned>());
+        order_scan_kernel<<<1, 256, 0, stream>>>(S.bins.as<unsigned>());
+        order_scatter_kernel<<<nb, 256, 0, stream>>>(d_seq_off, cnt, max_n, S.bins.as<unsigned>(), S.order.as<int32_t>());
+        g_launches += 3;
+        CK(cudaGetLastError());
+        d_order = S.order.as<int32_t>();
+    }
     size_t cls_pos = 0;
     for (const ClassPlan &C : P.classes) {
         const int32_t *d_cls = E.cls_ad.as<int32_t>() + cls_pos;
@@ -438,6 +452,7 @@ int run_cross_chunk(Engine &E, Stage &S, cudaStream_t stream, const AdapterPlan 
         ts.n_tasks = cnt * (int64_t)C.ad_ids.size();
         ts.cls_ad = d_cls; ts.n_cls_ad = (int32_t)C.ad_ids.size(); ts.n_adapters = n_adapters;
         ts.n_seqs = cnt; ts.seq_off = d_seq_off; ts.ad_off = E.ad_off.as<int32_t>();
+        ts.seq_order = d_order;
         if (ts.n_tasks == 0) continue;
         (void)base_off;
         if (int rc = run_class_tasks(E, S, stream, C.cls, C.m_max, ts, max_n, seq_codes, E.ad_codes.as<uint8_t>(), P.sc,
@@ -491,7 +506,8 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
             int64_t max_cnt = std::max<int64_t>(1, g_opt.chunk_tasks / std::max<int32_t>(n_adapters, 1));
             int64_t s1 = std::min(n_seqs, s0 + max_cnt);
             // limit bytes per chunk
-            while (s1 > s0 + 1 && seq_off[s1] - seq_off[s0] > g_opt.chunk_bytes) s1 = s0 + std::max<int64_t>(1, (s1 - s0) / 2);
+            // limit bytes per chunk, but keep enough sequences in a chunk to fill the GPU (one wave of slots)
+            while (s1 - s0 > 32768 && seq_off[s1] - seq_off[s0] > g_opt.chunk_bytes) s1 = s0 + std::max<int64_t>(32768, (s1 - s0) / 2);
             const int64_t cnt = s1 - s0;
             const int64_t base = seq_off[s0];
             const int64_t bytes = seq_off[s1] - base;
@@ -618,7 +634,7 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
         TaskSrc ts;
         ts.tasks = S.tasks.as<Task>(); ts.n_tasks = n_tasks;
         ts.cls_ad = nullptr; ts.n_cls_ad = 0; ts.n_adapters = n_adapters; ts.n_seqs = n_seqs;
-        ts.seq_off = S.seq_off.as<int64_t>(); ts.ad_off = E.ad_off.as<int32_t>();
+        ts.seq_off = S.seq_off.as<int64_t>(); ts.ad_off = E.ad_off.as<int32_t>(); ts.seq_order = nullptr;
         if (int rc = run_class_tasks(E, S, stream, c, m_max, ts, max_n, S.seq_codes.as<uint8_t>(), E.ad_codes.as<uint8_t>(),
                                      P.sc, P.si, S.out.as<int32_t>(), status, counter)) return rc;
     }

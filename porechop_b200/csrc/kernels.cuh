@@ -55,6 +55,40 @@ __global__ void max_len_kernel(const int64_t *__restrict__ off, int64_t n, unsig
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Sequence order by decreasing length (bucket sort, PB_ORDER_BINS log-spaced-ish linear bins): used by the two-pass
+// path so that the dynamically scheduled score pass starts with the longest reads (no long tail) and neighbouring
+// slots have similar lengths.  Order inside a bin is arbitrary (atomics) -- results do not depend on it.
+constexpr int PB_ORDER_BINS = 2048;
+__device__ __forceinline__ int order_bin(int64_t len, int64_t max_len) {
+    int64_t b = (len * (PB_ORDER_BINS - 1)) / (max_len > 0 ? max_len : 1);
+    if (b > PB_ORDER_BINS - 1) b = PB_ORDER_BINS - 1;
+    return (PB_ORDER_BINS - 1) - (int)b;          // bin 0 = longest
+}
+__global__ void order_hist_kernel(const int64_t *__restrict__ off, int64_t n, int64_t max_len, unsigned *__restrict__ bins) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&bins[order_bin(off[i + 1] - off[i], max_len)], 1u);
+}
+__global__ void order_scan_kernel(unsigned *bins) {   // one block of PB_ORDER_BINS/2 threads: exclusive scan in place
+    __shared__ unsigned sh[PB_ORDER_BINS];
+    for (int i = threadIdx.x; i < PB_ORDER_BINS; i += blockDim.x) sh[i] = bins[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int i = 0; i < PB_ORDER_BINS; ++i) { unsigned v = sh[i]; sh[i] = run; run += v; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PB_ORDER_BINS; i += blockDim.x) bins[i] = sh[i];
+}
+__global__ void order_scatter_kernel(const int64_t *__restrict__ off, int64_t n, int64_t max_len, unsigned *__restrict__ bins,
+                                     int32_t *__restrict__ order) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        unsigned pos = atomicAdd(&bins[order_bin(off[i + 1] - off[i], max_len)], 1u);
+        order[pos] = (int32_t)i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Task sources.
 // Cross mode: every sequence x every adapter of one class; the Task records are never materialised -- the kernels
 // synthesise them from the offset arrays (saves 64 B written + 128 B read per alignment).  `cls_ad` lists the class's
@@ -70,6 +104,8 @@ struct TaskSrc {
     int64_t n_seqs;
     const int64_t *seq_off;
     const int32_t *ad_off;
+    const int32_t *seq_order; // cross mode, optional: sequence permutation (longest first) -- slot i of a pair region is
+                              // sequence seq_order[i]: balances the tail of the score pass and pairs similar lengths
 };
 
 __device__ __forceinline__ Task cross_task(const TaskSrc &ts, int64_t k) {
@@ -82,6 +118,7 @@ __device__ __forceinline__ Task cross_task(const TaskSrc &ts, int64_t k) {
     } else {
         s = k - paired; a = __ldg(ts.cls_ad + ts.n_cls_ad - 1);
     }
+    if (ts.seq_order) s = __ldg(ts.seq_order + s);
     Task t;
     const int64_t o0 = __ldg(ts.seq_off + s), o1 = __ldg(ts.seq_off + s + 1);
     const int32_t a0 = __ldg(ts.ad_off + a), a1 = __ldg(ts.ad_off + a + 1);
@@ -344,82 +381,147 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// score_kernel: streaming score-only pass for long reads.  Same wavefront, no trace (8 DPX ops per cell
-// pair), exact scout.  Groups pull slots from a global counter and refill independently, so a warp's
-// groups never wait for each other's read lengths.
+// score_kernel: streaming score-only pass for long reads.  Same wavefront, no trace (7 instructions per row:
+// 3x VIADDMNMX, LOP3, VIADDMNMX-fused diagonal, VIMNMX, X update), exact scout.  Groups pull slots from a global
+// counter and refill independently, so a warp's groups never wait for each other's read lengths.
+//
+// Read bases are streamed through a per-group shared-memory ring of packed columns (64 entries = two blocks of 32
+// columns).  A block is fetched with aligned 64/32-bit loads (funnel-shifted to the unaligned start) one block
+// ahead of its store, which is itself one block ahead of its use: the L2/HBM latency of the stream is never on the
+// critical path.  The step loop runs in 32-step segments aligned for the whole warp; refill and staging happen
+// only between segments.
+constexpr int PB_RING = 64;
+constexpr int PB_BLK = 32;
+
+// CPL consecutive encoded bytes starting at an arbitrary address, in the low bytes of the result
+template <int CPL>
+__device__ __forceinline__ uint64_t load_cols(const uint8_t *p) {
+    if (CPL == 8) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const unsigned long long *q = reinterpret_cast<const unsigned long long *>(a & ~(uintptr_t)7);
+        const unsigned sh = (unsigned)(a & 7) * 8;
+        const unsigned long long lo = __ldcs(q), hi = __ldcs(q + 1);
+        return sh ? ((lo >> sh) | (hi << (64 - sh))) : lo;
+    } else if (CPL == 4) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const unsigned *q = reinterpret_cast<const unsigned *>(a & ~(uintptr_t)3);
+        const unsigned sh = (unsigned)(a & 3) * 8;
+        const unsigned lo = __ldcs(q), hi = __ldcs(q + 1);
+        return (uint64_t)__funnelshift_r(lo, hi, sh);
+    } else {
+        uint64_t v = 0;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) v |= (uint64_t)__ldcs(p + c) << (8 * c);
+        return v;
+    }
+}
+
 template <int G, int R>
 __global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32)
 score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
              const uint8_t *__restrict__ seq, const uint8_t *__restrict__ ads, Scoring sc, EndCell *__restrict__ ends) {
+    constexpr int SPW = 32 / G;
+    constexpr int CPL = PB_BLK / G;          // columns of a block each lane fetches
     __shared__ ScoutCand scratch[PB_WARPS_PER_BLOCK][2 * 32];
+    __shared__ uint32_t rings[PB_WARPS_PER_BLOCK][SPW][PB_RING];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, g = lane % G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
     const int64_t n_tasks = ts.n_tasks;
     const int64_t n_slots = (n_tasks + 1) / 2;
     ScoutCand *cand = scratch[warp];
+    uint32_t *ring = rings[warp][grp];
 
     Lane<R> L;
-    Task tA, tB;
     HalfGeom gA, gB;
     const uint8_t *seqA = seq, *seqB = seq;
     int64_t slot = -1;
-    int nmax = 0, nmin = 0, T = 0, t = 0;
+    int nA = 0, nB = 0, nmax = 0, nmin = 0, T = 0, t = 0;
     bool exhausted = false;
-    tA.n = tB.n = 0;
+    uint64_t pendA = 0, pendB = 0;           // raw bytes of the block that will be stored at the next block boundary
+    gA = make_geom(0, 0, G, R); gB = gA;
     L.botX = sc.borderX2; L.botV = sc.negb2;
 
+    // fetch this lane's CPL columns of block `blk` (raw bytes; columns past the end are fixed up when stored)
+    auto fetch = [&](int blk) {
+        const int c0 = blk * PB_BLK + g * CPL;
+        pendA = (c0 < nA) ? load_cols<CPL>(seqA + c0) : 0ull;
+        pendB = (c0 < nB) ? load_cols<CPL>(seqB + c0) : 0ull;
+    };
+    // store the pending block into the ring as packed columns
+    auto store = [&](int blk) {
+        const int c0 = blk * PB_BLK + g * CPL;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const int col = c0 + c;
+            const uint32_t bA = (col < nA) ? (uint32_t)((pendA >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H;
+            const uint32_t bB = (col < nB) ? (uint32_t)((pendB >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H;
+            ring[col & (PB_RING - 1)] = pack_bases(bA, bB);
+        }
+    };
+
     for (;;) {
-        if (t >= T && !exhausted) {            // group-uniform: this group's slot is finished (or none yet)
-            if (slot >= 0) {
-                cand[lane] = make_cand<R>(L, 0, sc);
-                cand[32 + lane] = make_cand<R>(L, 1, sc);
-                __syncwarp(gmask);
-                if (g < 2) {
-                    const int64_t ti = slot * 2 + g;
-                    if (ti < n_tasks) ends[ti] = scout_combine(cand + g * 32 + grp * G, G, g ? gB : gA);
+        if (!exhausted) {
+            if (t >= T) {                      // group-uniform: this group's slot is finished (or none yet)
+                if (slot >= 0) {
+                    cand[lane] = make_cand<R>(L, 0, sc);
+                    cand[32 + lane] = make_cand<R>(L, 1, sc);
+                    __syncwarp(gmask);
+                    if (g < 2) {
+                        const int64_t ti = slot * 2 + g;
+                        if (ti < n_tasks) ends[ti] = scout_combine(cand + g * 32 + grp * G, G, g ? gB : gA);
+                    }
+                    __syncwarp(gmask);
                 }
-                __syncwarp(gmask);
-            }
-            unsigned long long s = 0;
-            if (g == 0) s = atomicAdd(counter, 1ull);
-            s = __shfl_sync(gmask, s, 0, G);
-            if ((int64_t)s >= n_slots) {
-                exhausted = true; slot = -1; T = 0; t = 0; nmax = 0;
-            } else {
-                slot = (int64_t)s;
-                tA = get_task(ts, slot * 2);
-                tB = get_task(ts, slot * 2 + 1);
-                gA = make_geom(tA.n, tA.m, G, R); gB = make_geom(tB.n, tB.m, G, R);
-                nmax = max(tA.n, tB.n);
-                seqA = seq + tA.seq_off; seqB = seq + tB.seq_off;
-                lane_init<R>(L, g, G, sc, ads + tA.ad_off, tA.m, false, ads + tB.ad_off, tB.m, false);
-                {
+                unsigned long long s = 0;
+                if (g == 0) s = atomicAdd(counter, 1ull);
+                s = __shfl_sync(gmask, s, 0, G);
+                if ((int64_t)s >= n_slots) {
+                    exhausted = true; slot = -1; T = 0; t = 0; nmax = 0; nmin = 0; nA = nB = 0;
+                } else {
+                    slot = (int64_t)s;
+                    const Task tA = get_task(ts, slot * 2);
+                    const Task tB = get_task(ts, slot * 2 + 1);
+                    nA = tA.n; nB = tB.n;
+                    gA = make_geom(tA.n, tA.m, G, R); gB = make_geom(tB.n, tB.m, G, R);
+                    nmax = max(nA, nB);
+                    seqA = seq + tA.seq_off; seqB = seq + tB.seq_off;
+                    lane_init<R>(L, g, G, sc, ads + tA.ad_off, tA.m, false, ads + tB.ad_off, tB.m, false);
                     const bool emptyA = tA.n <= 0 || tA.m <= 0, emptyB = tB.n <= 0 || tB.m <= 0;
-                    nmin = emptyA ? tB.n : (emptyB ? tA.n : min(tA.n, tB.n));
+                    nmin = emptyA ? nB : (emptyB ? nA : min(nA, nB));
+                    T = nmax + G - 1; t = 0;
+                    fetch(0); store(0);         // first block: its latency is exposed once per slot
+                    fetch(1);
                 }
-                T = nmax + G - 1; t = 0;
+            } else {                               // block boundary: publish block t/32, prefetch the next one
+                store(t / PB_BLK);
+                fetch(t / PB_BLK + 1);
             }
         }
+        __syncwarp();
         if (__all_sync(0xffffffffu, exhausted)) break;
-        uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
-        uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
-        if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
-        const int j = t - g + 1;
-        if (!exhausted && j >= 1 && j <= nmax) {
-            const int ja = min(j, tA.n) - 1, jb = min(j, tB.n) - 1;
-            uint32_t bA = (ja >= 0) ? (uint32_t)__ldg(seqA + ja) : (uint32_t)PB_PAD_H;
-            uint32_t bB = (jb >= 0) ? (uint32_t)__ldg(seqB + jb) : (uint32_t)PB_PAD_H;
-            if (j < nmin) {
-                lane_step<R, false, false>(L, recvS, recvV, pack_bases(bA, bB), sc, nullptr);
-                lane_track_lastrow<R>(L, j, sc);
-            } else {
-                uint32_t vr[R];
-                lane_step<R, false, true>(L, recvS, recvV, pack_bases(bA, bB), sc, nullptr, vr);
-                lane_track_general<R>(L, g, j, gA, gB, vr, sc);
+        // One segment = PB_BLK steps.  Every group of the warp starts its slots on a segment boundary (a group that
+        // finishes inside a segment idles for the < 32 remaining steps, ~0.2 % of an 8-kb read), so all block boundaries
+        // of the warp coincide and the step loop carries no refill / staging checks.
+#pragma unroll 2
+        for (int k = 0; k < PB_BLK; ++k) {
+            uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
+            uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
+            if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
+            const int j = t - g + 1;
+            if (j >= 1 && j <= nmax) {          // nmax == 0 for exhausted groups
+                const uint32_t h2 = ring[(j - 1) & (PB_RING - 1)];
+                if (j < nmin) {
+                    lane_step<R, false, false>(L, recvS, recvV, h2, sc, nullptr);
+                    lane_track_lastrow<R>(L, j, sc);
+                } else {
+                    uint32_t vr[R];
+                    lane_step<R, false, true>(L, recvS, recvV, h2, sc, nullptr, vr);
+                    lane_track_general<R>(L, g, j, gA, gB, vr, sc);
+                }
             }
+            ++t;
         }
-        ++t;
     }
 }
 

@@ -134,6 +134,23 @@ def test_long_reads_two_pass_vs_oracle(W):
     assert np.array_equal(got2, oracle_batch(masked, off, abuf, aoff, wl.DEFAULT_SCORING, ps, pa))
 
 
+def test_read_length_sweep_barcodes(W):
+    """BASELINE config 5 shape: read lengths 500 bp - 100 kb x forward barcode sequences (24 nt), full-read scan."""
+    from porechop_b200 import workloads as wl
+    rng = np.random.default_rng(5)
+    sets = [s for s in wl.load_adapter_sets()['sets'] if s['name'].endswith('(forward)')][:6]
+    ads = [s['start'][1] for s in sets] + [s['end'][1] for s in sets]
+    reads = []
+    for L in (500, 1000, 2000, 5000, 10000, 20000, 50000, 100000):
+        body = bytes(np.frombuffer(b'ACGT', dtype=np.uint8)[rng.integers(0, 4, L)]).decode()
+        p = int(rng.integers(0, L - 30))
+        reads.append(body[:p] + ads[int(rng.integers(len(ads)))] + body[p + 24:])
+    sbuf, soff = W.pack_sequences(reads)
+    abuf, aoff = wl.pack_adapters(ads)
+    got = W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
+    assert np.array_equal(got, oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
+
+
 def test_generic_int32_path(W):
     """Schemes / adapters outside the int16 domain take the int32 kernel: positive gap score, huge scores, m > 256."""
     rng = random.Random(8)
