@@ -264,62 +264,53 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
         // PB_TCHUNK steps of trace words are collected in registers and written as one 128-bit store per lane:
         // a warp store covers 512 contiguous bytes, and the traceback later gets 4 consecutive steps of a lane
         // with a single (L2-latency) load.
-        // Phase 1 (hot, unrolled): the leading steps in which every lane of the warp is in an inner column -- only the
-        // fast scout.  Phase 2 (cold, not unrolled): the last G-1+ steps with the general scout (final columns).
+        // Hot chunks (straight-line, 4 steps unrolled): every lane of the warp is inside its matrix (t >= G-1) and in an
+        // inner column (fast scout only) -- no per-step activity checks.  Careful chunks (not unrolled): the first
+        // G-1 ramp-up steps and the tail with the final columns (general scout, per-lane activity checks).
         const int T4 = (T + PB_TCHUNK - 1) & ~(PB_TCHUNK - 1);
-        int tfast = need_track ? max(nmin - 1, 0) : T4;
-        tfast = __reduce_min_sync(0xffffffffu, tfast) & ~(PB_TCHUNK - 1);
-        int t0 = 0;
-        for (; t0 < tfast; t0 += PB_TCHUNK) {
-            uint32_t buf[PB_TCHUNK][WPS];
+        constexpr int TWARM = (G - 1 + PB_TCHUNK - 1) & ~(PB_TCHUNK - 1);
+        int tfast = need_track ? (nmin - 1) : nmax;
+        tfast = __reduce_min_sync(0xffffffffu, max(tfast, 0)) & ~(PB_TCHUNK - 1);
+        for (int t0 = 0; t0 < T4; t0 += PB_TCHUNK) {
+            uint4 acc[WPS];
+            if (t0 >= TWARM && t0 < tfast) {
+                uint32_t buf[PB_TCHUNK][WPS];
 #pragma unroll
-            for (int u = 0; u < PB_TCHUNK; ++u) {
-                const int t = t0 + u;
-                uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
-                uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
-                if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
-                const int j = t - g + 1;
-                uint32_t tw[WPS];
-#pragma unroll
-                for (int w = 0; w < WPS; ++w) tw[w] = 0u;
-                if (j >= 1 && j <= nmax) {
-                    lane_step<R, true, false>(L, recvS, recvV, hbuf[j - 1], sc, tw);
+                for (int u = 0; u < PB_TCHUNK; ++u) {
+                    uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
+                    uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
+                    if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
+                    const int j = t0 + u - g + 1;
+                    lane_step<R, true, false>(L, recvS, recvV, hbuf[j - 1], sc, buf[u]);
                     if (need_track) lane_track_lastrow<R>(L, j, sc);
                 }
 #pragma unroll
-                for (int w = 0; w < WPS; ++w) buf[u][w] = tw[w];
-            }
+                for (int w = 0; w < WPS; ++w) acc[w] = make_uint4(buf[0][w], buf[1][w], buf[2][w], buf[3][w]);
+            } else {
 #pragma unroll
-            for (int w = 0; w < WPS; ++w) {
-                uint4 v = make_uint4(buf[0][w], buf[1][w], buf[2][w], buf[3][w]);
-                *reinterpret_cast<uint4 *>(tr + (((size_t)(t0 / PB_TCHUNK) * WPS + w) * 32 + lane) * PB_TCHUNK) = v;
-            }
-        }
-        for (; t0 < T4; t0 += PB_TCHUNK) {
-            uint4 acc[WPS];
-#pragma unroll
-            for (int w = 0; w < WPS; ++w) acc[w] = make_uint4(0u, 0u, 0u, 0u);
+                for (int w = 0; w < WPS; ++w) acc[w] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll 1
-            for (int u = 0; u < PB_TCHUNK; ++u) {
-                const int t = t0 + u;
-                uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
-                uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
-                if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
-                const int j = t - g + 1;
-                uint32_t tw[WPS];
+                for (int u = 0; u < PB_TCHUNK; ++u) {
+                    const int t = t0 + u;
+                    uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
+                    uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
+                    if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
+                    const int j = t - g + 1;
+                    uint32_t tw[WPS];
 #pragma unroll
-                for (int w = 0; w < WPS; ++w) tw[w] = 0u;
-                if (j >= 1 && j <= nmax) {
-                    uint32_t vr[R];
-                    lane_step<R, true, true>(L, recvS, recvV, hbuf[j - 1], sc, tw, vr);
-                    if (need_track) {
-                        if (j >= nmin) lane_track_general<R>(L, g, j, make_geom(nA, mA, G, R), make_geom(nB, mB, G, R), vr, sc);
-                        else lane_track_lastrow<R>(L, j, sc);
+                    for (int w = 0; w < WPS; ++w) tw[w] = 0u;
+                    if (j >= 1 && j <= nmax) {
+                        uint32_t vr[R];
+                        lane_step<R, true, true>(L, recvS, recvV, hbuf[j - 1], sc, tw, vr);
+                        if (need_track) {
+                            if (j >= nmin) lane_track_general<R>(L, g, j, make_geom(nA, mA, G, R), make_geom(nB, mB, G, R), vr, sc);
+                            else lane_track_lastrow<R>(L, j, sc);
+                        }
                     }
-                }
 #pragma unroll
-                for (int w = 0; w < WPS; ++w) {
-                    if (u == 0) acc[w].x = tw[w]; else if (u == 1) acc[w].y = tw[w]; else if (u == 2) acc[w].z = tw[w]; else acc[w].w = tw[w];
+                    for (int w = 0; w < WPS; ++w) {
+                        if (u == 0) acc[w].x = tw[w]; else if (u == 1) acc[w].y = tw[w]; else if (u == 2) acc[w].z = tw[w]; else acc[w].w = tw[w];
+                    }
                 }
             }
 #pragma unroll

@@ -35,6 +35,15 @@ def test_legacy_single_call_strings(W):
         assert W.adapter_alignment(rd, ad, sc) == exp
 
 
+def test_legacy_call_is_thread_safe(W):
+    """The reference calls adapterAlignment from a multiprocessing.dummy.Pool (porechop.py:312,496,579)."""
+    from multiprocessing.dummy import Pool
+    g = load_golden('golden_random.json')[300:700]
+    with Pool(8) as pool:
+        got = pool.map(lambda c: W.adapter_alignment(c[0], c[1], c[2]), g)
+    assert got == [c[3] for c in g]
+
+
 def test_golden_random_pair_list(W):
     g = load_golden('golden_random.json')
     by_scheme = {}
