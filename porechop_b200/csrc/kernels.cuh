@@ -494,24 +494,36 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
         // One segment = PB_BLK steps.  Every group of the warp starts its slots on a segment boundary (a group that
         // finishes inside a segment idles for the < 32 remaining steps, ~0.2 % of an 8-kb read), so all block boundaries
         // of the warp coincide and the step loop carries no refill / staging checks.
-#pragma unroll 2
-        for (int k = 0; k < PB_BLK; ++k) {
-            uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
-            uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
-            if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
-            const int j = t - g + 1;
-            if (j >= 1 && j <= nmax) {          // nmax == 0 for exhausted groups
-                const uint32_t h2 = ring[(j - 1) & (PB_RING - 1)];
-                if (j < nmin) {
-                    lane_step<R, false, false>(L, recvS, recvV, h2, sc, nullptr);
-                    lane_track_lastrow<R>(L, j, sc);
-                } else {
+        // A segment is "hot" when every lane of every (live) group stays inside its matrix and in inner columns for
+        // all 32 steps: straight-line code, fast scout only.  Exhausted groups just compute on dead state.
+        const bool hot = __all_sync(0xffffffffu, exhausted || (t >= G - 1 && t + PB_BLK < nmin));
+        if (hot) {
+#pragma unroll 4
+            for (int k = 0; k < PB_BLK; ++k) {
+                uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
+                uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
+                if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
+                const int j = t - g + 1;
+                lane_step<R, false, false>(L, recvS, recvV, ring[(j - 1) & (PB_RING - 1)], sc, nullptr);
+                lane_track_lastrow<R>(L, j, sc);
+                ++t;
+            }
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < PB_BLK; ++k) {
+                uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
+                uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
+                if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
+                const int j = t - g + 1;
+                if (j >= 1 && j <= nmax) {          // nmax == 0 for exhausted groups
+                    const uint32_t h2 = ring[(j - 1) & (PB_RING - 1)];
                     uint32_t vr[R];
                     lane_step<R, false, true>(L, recvS, recvV, h2, sc, nullptr, vr);
-                    lane_track_general<R>(L, g, j, gA, gB, vr, sc);
+                    if (j < nmin) lane_track_lastrow<R>(L, j, sc);
+                    else lane_track_general<R>(L, g, j, gA, gB, vr, sc);
                 }
+                ++t;
             }
-            ++t;
         }
     }
 }
