@@ -78,8 +78,11 @@ long long pb200KernelLaunches(void);      /* kernels launched by this library si
  * duration and launch count of the DP kernels (trace_kernel + score_kernel) since the last reset. */
 void pb200TimingEnable(int on);
 int pb200TimingRead(double *dp_kernel_ms, long long *dp_kernel_launches, double *cells, int reset);
-/* Tunables (also read from the environment at first use): "trace" = "auto"|"smem"|"global";
- * "direct_max" = longest sequence aligned in one pass; "chunk_tasks" = alignments per pipeline chunk. */
+/* Tunables (also read from the environment at first use, PB200_<NAME>):
+ *   "direct_max"  longest sequence aligned in one pass (default 512; longer ones take score pass + bounded window)
+ *   "chunk_tasks" alignments per pipeline chunk of the host-buffer API (default 131072)
+ *   "scratch_mb"  cap on the resident trace scratch in MB (default 128; 72 keeps it L2-resident)
+ *   "hbuf"        staging of a slot's packed bases: "auto" | "smem" | "global" */
 int pb200SetOption(const char *name, const char *value);
 
 enum {

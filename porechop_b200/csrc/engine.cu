@@ -55,12 +55,10 @@ struct DevBuf {
 };
 
 struct Options {
-    int trace_mode = 0;            // 0 auto, 1 smem, 2 global
     int64_t direct_max = 512;      // longest sequence aligned in a single (trace) pass
     int64_t chunk_tasks = 1 << 17; // alignments per pipeline chunk (host-buffer API)
     int64_t device_chunk_tasks = 8 << 20; // alignments per launch group (device-resident API)
     int64_t chunk_bytes = 64ll << 20;   // sequence bytes per pipeline chunk (host-buffer API)
-    int wpb = 0;                   // warps per block override for trace kernel (0 = auto)
     int scratch_mb = 128;          // cap on the resident trace scratch (MB); 72 keeps it L2-resident at ~10% lower speed
     int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
 };
@@ -68,12 +66,8 @@ Options g_opt;
 std::once_flag g_opt_once;
 void load_env_options() {
     std::call_once(g_opt_once, [] {
-        if (const char *v = getenv("PB200_TRACE")) {
-            if (!strcmp(v, "smem")) g_opt.trace_mode = 1; else if (!strcmp(v, "global")) g_opt.trace_mode = 2;
-        }
         if (const char *v = getenv("PB200_DIRECT_MAX")) g_opt.direct_max = atoll(v);
         if (const char *v = getenv("PB200_CHUNK_TASKS")) g_opt.chunk_tasks = std::max(1ll, atoll(v));
-        if (const char *v = getenv("PB200_WPB")) g_opt.wpb = atoi(v);
         if (const char *v = getenv("PB200_SCRATCH_MB")) g_opt.scratch_mb = std::max(1, atoi(v));
         if (const char *v = getenv("PB200_HBUF")) g_opt.hbuf_mode = !strcmp(v, "smem") ? 1 : !strcmp(v, "global") ? 2 : 0;
     });
@@ -804,11 +798,8 @@ int pb200Synchronize(void) {
 int pb200SetOption(const char *name, const char *value) {
     load_env_options();
     if (!name || !value) return PB200_ERR_ARG;
-    if (!strcmp(name, "trace")) {
-        g_opt.trace_mode = 0;   // kept for compatibility: the trace always lives in the L2-resident global scratch
-    } else if (!strcmp(name, "direct_max")) g_opt.direct_max = atoll(value);
+    if (!strcmp(name, "direct_max")) g_opt.direct_max = atoll(value);
     else if (!strcmp(name, "chunk_tasks")) g_opt.chunk_tasks = std::max(1ll, atoll(value));
-    else if (!strcmp(name, "wpb")) g_opt.wpb = atoi(value);
     else if (!strcmp(name, "scratch_mb")) g_opt.scratch_mb = std::max(1, atoi(value));
     else if (!strcmp(name, "hbuf")) g_opt.hbuf_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;
     else return PB200_ERR_ARG;

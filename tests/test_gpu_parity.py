@@ -172,21 +172,38 @@ def test_generic_int32_path(W):
         assert np.array_equal(got, oracle_batch(sbuf, soff, abuf, aoff, sc)), sc
 
 
-def test_trace_in_global_memory_variant(W):
-    """Force the global-memory trace variant of the trace kernel and a one-pass run over longer windows."""
+def test_single_pass_long_windows_and_global_staging(W):
+    """One-pass (no score pass) run over multi-kb sequences with the packed bases staged in global scratch."""
     from porechop_b200 import workloads as wl
     yt, yb = wl.nsk007()
     buf, off = wl.synth_reads(40, yt, yb, seed=21, max_len=3000)
     abuf, aoff = wl.pack_adapters([yt, yb])
     exp = oracle_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
     try:
-        W.set_option('trace', 'global')
+        W.set_option('hbuf', 'global')
         W.set_option('direct_max', 100000)
         got = W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
     finally:
-        W.set_option('trace', 'auto')
+        W.set_option('hbuf', 'auto')
         W.set_option('direct_max', 512)
     assert np.array_equal(got, exp)
+
+
+def test_scratch_cap_option_does_not_change_results(W):
+    from porechop_b200 import workloads as wl
+    yt, yb = wl.nsk007()
+    _, sw, _ = wl.synth_end_windows(300000, yt, yb, seed=123)
+    sbuf, soff = wl.windows_to_batch(sw)
+    abuf, aoff = wl.pack_adapters([yt])
+    a = W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
+    try:
+        W.set_option('scratch_mb', 72)
+        W.set_option('chunk_tasks', 50000)
+        b = W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
+    finally:
+        W.set_option('scratch_mb', 128)
+        W.set_option('chunk_tasks', 131072)
+    assert np.array_equal(a, b)
 
 
 def test_device_resident_api_equals_host_api(W):
