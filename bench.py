@@ -10,7 +10,8 @@ of the hot path over the whole batch (two batched C-ABI calls).  Other workloads
 
   value   reads/s with the windows already resident in HBM (adapterAlignmentBatchDevice), CUDA-event timed
   e2e     reads/s through the host-buffer C-ABI call (adapterAlignmentBatch, pinned host buffers): H2D + kernels +
-          D2H inside the timed region; at N>1 the shards' records are also re-gathered to rank 0 over NCCL
+          D2H inside the timed region, every rank on its own shard and PCIe link; the optional NCCL re-gather of the
+          36-byte records to rank 0 is timed separately (e2e.gather_records_to_rank0_ms)
   roofline   dominant kernel (trace_kernel) algorithmic bytes / CUDA-event duration vs the measured HBM peak --
           reported because the north star asks for it; the kernel is integer-ALU (DPX) bound, see `alu`
   cpu_baseline / --impl reference   the reference's own C++ (oracle/_ref/cpp_functions.so, falling back to the
@@ -251,35 +252,11 @@ def main():
             W.adapter_alignment_batch_device(db.data_ptr(), do.data_ptr(), do.numel() - 1, db.numel(), max_len, abuf, aoff,
                                              scoring, dout.data_ptr(), s)
 
-    gather_bufs = None
-    if world > 1:
-        # rank 0 receives every rank's records: device buckets + one pinned host buffer per batch
-        gather_bufs = []
-        for (hb, ho, abuf, aoff, hout), (db, do, _, _, dout, max_len) in zip(host, dev):
-            if rank == 0:
-                bucket = [torch.empty_like(dout) for _ in range(world)]
-                hall = torch.empty((world,) + tuple(dout.shape), dtype=torch.int32, pin_memory=True)
-            else:
-                bucket, hall = None, None
-            gather_bufs.append((bucket, hall))
-
     def step_e2e():
-        if world == 1:
-            for hb, ho, abuf, aoff, hout in host:
-                W.adapter_alignment_batch(hb.numpy(), ho.numpy(), abuf, aoff, scoring, out=hout.numpy())
-            return
-        # N > 1: pinned host -> device, device C-ABI, NCCL re-gather of the records to rank 0, one D2H there
-        s = torch.cuda.current_stream().cuda_stream
-        for (hb, ho, abuf, aoff, hout), (db, do, _, _, dout, max_len), (bucket, hall) in zip(host, dev, gather_bufs):
-            db.copy_(hb, non_blocking=True)
-            do.copy_(ho, non_blocking=True)
-            W.adapter_alignment_batch_device(db.data_ptr(), do.data_ptr(), do.numel() - 1, db.numel(), max_len, abuf, aoff,
-                                             scoring, dout.data_ptr(), s)
-            dist.gather(dout, bucket, dst=0)
-            if rank == 0:
-                for r in range(world):
-                    hall[r].copy_(bucket[r], non_blocking=True)
-        torch.cuda.synchronize()
+        # every rank pushes its own shard through the host-buffer C-ABI over its own PCIe link; the records stay
+        # rank-local (no data-path collective, prompt (5)); the optional re-gather to a writer rank is timed separately
+        for hb, ho, abuf, aoff, hout in host:
+            W.adapter_alignment_batch(hb.numpy(), ho.numpy(), abuf, aoff, scoring, out=hout.numpy())
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -320,10 +297,25 @@ def main():
     sampler.active = False
     sampler.stop_flag = True
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device='cuda')
+    # informational: NCCL re-gather of the 36-byte records of every rank to rank 0 (device -> device over NVLink)
+    gather_ms = None
+    if world > 1:
+        db, do, abuf, aoff, dout, max_len = dev[0]
+        bucket = [torch.empty_like(dout) for _ in range(world)] if rank == 0 else None
+        dist.gather(dout, bucket, dst=0)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _, _, _, _, d_o, _ in dev:
+            dist.gather(d_o, [torch.empty_like(d_o) for _ in range(world)] if rank == 0 else None, dst=0)
+        g1.record()
+        barrier()
+        gather_ms = g0.elapsed_time(g1)
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, gather_ms or 0.0], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, gather_ms = float(t[0]), float(t[1]), (float(t[2]) if world > 1 else None)
     total_reads = n * world
     if rank != 0:
         if world > 1:
@@ -363,8 +355,8 @@ def main():
                    'l2': 'inputs %.0f MB per step exceed the 126 MB L2' % (in_bytes / 1e6)},
         'e2e': {'value': e2e_value, 'unit': 'reads/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': out_bytes,
                 'ms_per_step': e2e_ms / K, 'gcups': cells_per_step * world * K / (e2e_ms / 1e3) / 1e9,
-                'path': 'adapterAlignmentBatch (host buffers, pinned)' if world == 1 else
-                        'pinned H2D + adapterAlignmentBatchDevice + NCCL gather of records to rank 0 + D2H'},
+                'path': 'adapterAlignmentBatch (host buffers, pinned), one call per batch per rank; records stay rank-local',
+                'gather_records_to_rank0_ms': gather_ms},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': (achieved / peak) if achieved else None, 'traffic': traffic, 'peak_source': peak_src,

@@ -94,6 +94,12 @@ struct Engine {
     std::mutex mu;
     Stage st[NSTAGE];
     DevBuf ad_raw, ad_codes, ad_off, cls_ad, gjobs, gscratch;
+    // adapter plan cache: repeated calls with the same adapters + scoring (the normal case) skip upload, encode and sync
+    std::vector<uint8_t> cache_ad;
+    std::vector<int32_t> cache_off;
+    int cache_sc[4] = {0, 0, 0, 0};
+    bool cache_valid = false;
+    std::shared_ptr<void> cache_plan;
     std::vector<TimedLaunch> timed;
     double timed_cells = 0.0;
     double timed_ms_acc = 0.0;
@@ -314,6 +320,20 @@ struct AdapterPlan {
 };
 int plan_adapters(Engine &E, cudaStream_t stream, const uint8_t *adapters, const int32_t *ad_off, int32_t n_adapters,
                   int ma, int mi, int go, int ge, AdapterPlan &P) {
+    {
+        const size_t nb = (size_t)ad_off[n_adapters];
+        if (E.cache_valid && E.cache_plan && E.cache_sc[0] == ma && E.cache_sc[1] == mi && E.cache_sc[2] == go &&
+            E.cache_sc[3] == ge && E.cache_off.size() == (size_t)n_adapters + 1 && E.cache_ad.size() == nb &&
+            memcmp(E.cache_off.data(), ad_off, E.cache_off.size() * 4) == 0 &&
+            (nb == 0 || memcmp(E.cache_ad.data(), adapters, nb) == 0)) {
+            P = *static_cast<AdapterPlan *>(E.cache_plan.get());
+            return 0;
+        }
+        E.cache_valid = false;
+        // the device copies are about to change: everything queued by earlier calls must be done with them
+        for (int i = 0; i < NSTAGE; ++i) CK(cudaStreamSynchronize(E.st[i].stream));
+        CK(cudaStreamSynchronize(stream));
+    }
     P.si = scheme_info(ma, mi, go, ge);
     P.sc = make_scoring(ma, mi, go, ge);
     std::vector<ClassPlan> cl(N_CLASSES);
@@ -365,6 +385,11 @@ int plan_adapters(Engine &E, cudaStream_t stream, const uint8_t *adapters, const
     if (!flat.empty()) CK(cudaMemcpyAsync(E.cls_ad.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, stream));
     // the host vectors above are pageable: the async copies have been staged by the driver before returning
     CK(cudaStreamSynchronize(stream));
+    E.cache_ad.assign(adapters, adapters + ad_bytes);
+    E.cache_off.assign(ad_off, ad_off + n_adapters + 1);
+    E.cache_sc[0] = ma; E.cache_sc[1] = mi; E.cache_sc[2] = go; E.cache_sc[3] = ge;
+    E.cache_plan = std::make_shared<AdapterPlan>(P);
+    E.cache_valid = true;
     return 0;
 }
 
