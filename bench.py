@@ -246,8 +246,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the device-resident path runs on an explicit (non-default) stream; the CUDA events that time it are recorded on
+    # the same stream.  (Handle 0 = "NULL" means "the library's own stream" to the C-ABI.)
+    bench_stream = torch.cuda.Stream()
+
     def step_device():
-        s = torch.cuda.current_stream().cuda_stream
+        s = bench_stream.cuda_stream
+        assert s != 0
         for db, do, abuf, aoff, dout, max_len in dev:
             W.adapter_alignment_batch_device(db.data_ptr(), do.data_ptr(), do.numel() - 1, db.numel(), max_len, abuf, aoff,
                                              scoring, dout.data_ptr(), s)
@@ -272,10 +277,10 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.active = True
     barrier()
-    ev0.record()
+    ev0.record(bench_stream)
     for _ in range(K):
         step_device()
-    ev1.record()
+    ev1.record(bench_stream)
     barrier()
     sampler.active = False
     launches = W.kernel_launches() - l0

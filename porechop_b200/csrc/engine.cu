@@ -93,13 +93,20 @@ struct Engine {
     size_t smem_optin = 0;
     std::mutex mu;
     Stage st[NSTAGE];
-    DevBuf ad_raw, ad_codes, ad_off, cls_ad, gjobs, gscratch;
-    // adapter plan cache: repeated calls with the same adapters + scoring (the normal case) skip upload, encode and sync
-    std::vector<uint8_t> cache_ad;
-    std::vector<int32_t> cache_off;
-    int cache_sc[4] = {0, 0, 0, 0};
-    bool cache_valid = false;
-    std::shared_ptr<void> cache_plan;
+    DevBuf gjobs, gscratch;
+    // adapter plan cache (4 entries, LRU): repeated calls with the same adapters + scoring (the normal case: Porechop
+    // alternates between its start-adapter and end-adapter lists) skip upload, encode and the host synchronisation
+    struct PlanEntry {
+        std::vector<uint8_t> ad;
+        std::vector<int32_t> off;
+        int sc[4] = {0, 0, 0, 0};
+        bool valid = false;
+        unsigned long long last_used = 0;
+        DevBuf ad_raw, ad_codes, ad_off, cls_ad;
+        std::shared_ptr<void> plan;
+    };
+    PlanEntry plans[4];
+    unsigned long long plan_clock = 0;
     std::vector<TimedLaunch> timed;
     double timed_cells = 0.0;
     double timed_ms_acc = 0.0;
@@ -317,23 +324,28 @@ struct AdapterPlan {
     std::vector<ClassPlan> classes;   // non-empty classes only
     SchemeInfo si;
     Scoring sc;
+    const uint8_t *d_ad_codes = nullptr;   // device copies owned by the engine's plan cache
+    const int32_t *d_ad_off = nullptr;
+    const int32_t *d_cls_ad = nullptr;
 };
 int plan_adapters(Engine &E, cudaStream_t stream, const uint8_t *adapters, const int32_t *ad_off, int32_t n_adapters,
                   int ma, int mi, int go, int ge, AdapterPlan &P) {
-    {
-        const size_t nb = (size_t)ad_off[n_adapters];
-        if (E.cache_valid && E.cache_plan && E.cache_sc[0] == ma && E.cache_sc[1] == mi && E.cache_sc[2] == go &&
-            E.cache_sc[3] == ge && E.cache_off.size() == (size_t)n_adapters + 1 && E.cache_ad.size() == nb &&
-            memcmp(E.cache_off.data(), ad_off, E.cache_off.size() * 4) == 0 &&
-            (nb == 0 || memcmp(E.cache_ad.data(), adapters, nb) == 0)) {
-            P = *static_cast<AdapterPlan *>(E.cache_plan.get());
+    const size_t nb = (size_t)ad_off[n_adapters];
+    Engine::PlanEntry *slot = nullptr;
+    for (auto &e : E.plans) {
+        if (e.valid && e.plan && e.sc[0] == ma && e.sc[1] == mi && e.sc[2] == go && e.sc[3] == ge &&
+            e.off.size() == (size_t)n_adapters + 1 && e.ad.size() == nb &&
+            memcmp(e.off.data(), ad_off, e.off.size() * 4) == 0 && (nb == 0 || memcmp(e.ad.data(), adapters, nb) == 0)) {
+            e.last_used = ++E.plan_clock;
+            P = *static_cast<AdapterPlan *>(e.plan.get());
             return 0;
         }
-        E.cache_valid = false;
-        // the device copies are about to change: everything queued by earlier calls must be done with them
-        for (int i = 0; i < NSTAGE; ++i) CK(cudaStreamSynchronize(E.st[i].stream));
-        CK(cudaStreamSynchronize(stream));
     }
+    for (auto &e : E.plans) if (!slot || !e.valid || (slot->valid && e.last_used < slot->last_used)) { slot = &e; if (!e.valid) break; }
+    slot->valid = false;
+    // the entry's device copies are about to change: everything queued by earlier calls must be done with them
+    CK(cudaDeviceSynchronize());
+    Engine::PlanEntry &PE = *slot;
     P.si = scheme_info(ma, mi, go, ge);
     P.sc = make_scoring(ma, mi, go, ge);
     std::vector<ClassPlan> cl(N_CLASSES);
@@ -372,24 +384,26 @@ int plan_adapters(Engine &E, cudaStream_t stream, const uint8_t *adapters, const
     for (int c = 0; c < GENERIC_CLASS; ++c) if (single_of[c] >= 0) cl[c].ad_ids.push_back(single_of[c]);
     for (auto &c : cl) if (!c.ad_ids.empty()) P.classes.push_back(c);
     const size_t ad_bytes = (size_t)ad_off[n_adapters];
-    if (int rc = E.ad_raw.ensure(ad_bytes + 16)) return rc;
-    if (int rc = E.ad_codes.ensure(ad_bytes + 16)) return rc;
-    if (int rc = E.ad_off.ensure((size_t)(n_adapters + 1) * 4)) return rc;
-    if (ad_bytes) CK(cudaMemcpyAsync(E.ad_raw.p, adapters, ad_bytes, cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(E.ad_off.p, ad_off, (size_t)(n_adapters + 1) * 4, cudaMemcpyHostToDevice, stream));
-    if (int rc = launch_encode(stream, E.ad_raw.as<uint8_t>(), E.ad_codes.as<uint8_t>(), (int64_t)ad_bytes, E.sm_count)) return rc;
+    if (int rc = PE.ad_raw.ensure(ad_bytes + 16)) return rc;
+    if (int rc = PE.ad_codes.ensure(ad_bytes + 16)) return rc;
+    if (int rc = PE.ad_off.ensure((size_t)(n_adapters + 1) * 4)) return rc;
+    if (ad_bytes) CK(cudaMemcpyAsync(PE.ad_raw.p, adapters, ad_bytes, cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(PE.ad_off.p, ad_off, (size_t)(n_adapters + 1) * 4, cudaMemcpyHostToDevice, stream));
+    if (int rc = launch_encode(stream, PE.ad_raw.as<uint8_t>(), PE.ad_codes.as<uint8_t>(), (int64_t)ad_bytes, E.sm_count)) return rc;
     // class adapter-id lists, concatenated
     std::vector<int32_t> flat;
     for (auto &c : P.classes) flat.insert(flat.end(), c.ad_ids.begin(), c.ad_ids.end());
-    if (int rc = E.cls_ad.ensure(flat.size() * 4 + 16)) return rc;
-    if (!flat.empty()) CK(cudaMemcpyAsync(E.cls_ad.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, stream));
+    if (int rc = PE.cls_ad.ensure(flat.size() * 4 + 16)) return rc;
+    if (!flat.empty()) CK(cudaMemcpyAsync(PE.cls_ad.p, flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, stream));
     // the host vectors above are pageable: the async copies have been staged by the driver before returning
     CK(cudaStreamSynchronize(stream));
-    E.cache_ad.assign(adapters, adapters + ad_bytes);
-    E.cache_off.assign(ad_off, ad_off + n_adapters + 1);
-    E.cache_sc[0] = ma; E.cache_sc[1] = mi; E.cache_sc[2] = go; E.cache_sc[3] = ge;
-    E.cache_plan = std::make_shared<AdapterPlan>(P);
-    E.cache_valid = true;
+    P.d_ad_codes = PE.ad_codes.as<uint8_t>(); P.d_ad_off = PE.ad_off.as<int32_t>(); P.d_cls_ad = PE.cls_ad.as<int32_t>();
+    PE.ad.assign(adapters, adapters + ad_bytes);
+    PE.off.assign(ad_off, ad_off + n_adapters + 1);
+    PE.sc[0] = ma; PE.sc[1] = mi; PE.sc[2] = go; PE.sc[3] = ge;
+    PE.plan = std::make_shared<AdapterPlan>(P);
+    PE.last_used = ++E.plan_clock;
+    PE.valid = true;
     return 0;
 }
 
@@ -458,23 +472,23 @@ int run_cross_chunk(Engine &E, Stage &S, cudaStream_t stream, const AdapterPlan 
     }
     size_t cls_pos = 0;
     for (const ClassPlan &C : P.classes) {
-        const int32_t *d_cls = E.cls_ad.as<int32_t>() + cls_pos;
+        const int32_t *d_cls = P.d_cls_ad + cls_pos;
         cls_pos += C.ad_ids.size();
         if (C.cls == GENERIC_CLASS) {
             if (!h_seq_off_abs) return fail(PB200_ERR_INTERNAL, "generic class needs host offsets");
             if (int rc = run_generic_cross(E, S, stream, C, h_seq_off_abs, s0, cnt, base_off, h_ad_off, n_adapters, seq_codes,
-                                           E.ad_codes.as<uint8_t>(), P.sc, d_out)) return rc;
+                                           P.d_ad_codes, P.sc, d_out)) return rc;
             continue;
         }
         TaskSrc ts;
         ts.tasks = nullptr;                                  // cross product, synthesised in the kernels
         ts.n_tasks = cnt * (int64_t)C.ad_ids.size();
         ts.cls_ad = d_cls; ts.n_cls_ad = (int32_t)C.ad_ids.size(); ts.n_adapters = n_adapters;
-        ts.n_seqs = cnt; ts.seq_off = d_seq_off; ts.ad_off = E.ad_off.as<int32_t>();
+        ts.n_seqs = cnt; ts.seq_off = d_seq_off; ts.ad_off = P.d_ad_off;
         ts.seq_order = d_order;
         if (ts.n_tasks == 0) continue;
         (void)base_off;
-        if (int rc = run_class_tasks(E, S, stream, C.cls, C.m_max, ts, max_n, seq_codes, E.ad_codes.as<uint8_t>(), P.sc,
+        if (int rc = run_class_tasks(E, S, stream, C.cls, C.m_max, ts, max_n, seq_codes, P.d_ad_codes, P.sc,
                                      P.si, d_out, status, counter)) return rc;
     }
     return 0;
@@ -611,7 +625,7 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
                 CK(cudaMemcpyAsync(E.gjobs.p, jobs.data(), jobs.size() * sizeof(GenericJob), cudaMemcpyHostToDevice, stream));
                 int nb = (int)((jobs.size() + 63) / 64);
                 generic_kernel<<<nb, 64, 0, stream>>>(E.gjobs.as<GenericJob>(), (int)jobs.size(), S.seq_codes.as<uint8_t>(),
-                                                      E.ad_codes.as<uint8_t>(), ma, mi, go, ge, E.gscratch.as<uint8_t>(),
+                                                      P.d_ad_codes, ma, mi, go, ge, E.gscratch.as<uint8_t>(),
                                                       S.out.as<int32_t>());
                 g_launches++;
                 CK(cudaGetLastError());
@@ -647,14 +661,14 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
         CK(cudaStreamSynchronize(stream));  // ord is pageable and reused per class
         build_tasks_pairs_kernel<<<(unsigned)((n_tasks + 255) / 256), 256, 0, stream>>>(
             S.tasks.as<Task>(), n_tasks, S.order.as<int32_t>(), S.pair_seq.as<int32_t>(), S.pair_ad.as<int32_t>(),
-            S.seq_off.as<int64_t>(), E.ad_off.as<int32_t>());
+            S.seq_off.as<int64_t>(), P.d_ad_off);
         g_launches++;
         CK(cudaGetLastError());
         TaskSrc ts;
         ts.tasks = S.tasks.as<Task>(); ts.n_tasks = n_tasks;
         ts.cls_ad = nullptr; ts.n_cls_ad = 0; ts.n_adapters = n_adapters; ts.n_seqs = n_seqs;
-        ts.seq_off = S.seq_off.as<int64_t>(); ts.ad_off = E.ad_off.as<int32_t>(); ts.seq_order = nullptr;
-        if (int rc = run_class_tasks(E, S, stream, c, m_max, ts, max_n, S.seq_codes.as<uint8_t>(), E.ad_codes.as<uint8_t>(),
+        ts.seq_off = S.seq_off.as<int64_t>(); ts.ad_off = P.d_ad_off; ts.seq_order = nullptr;
+        if (int rc = run_class_tasks(E, S, stream, c, m_max, ts, max_n, S.seq_codes.as<uint8_t>(), P.d_ad_codes,
                                      P.sc, P.si, S.out.as<int32_t>(), status, counter)) return rc;
     }
     CK(cudaMemcpyAsync(out, S.out.p, (size_t)n_pairs * PB_REC * 4, cudaMemcpyDeviceToHost, stream));

@@ -407,8 +407,11 @@ __device__ __forceinline__ uint64_t load_cols(const uint8_t *p) {
     }
 }
 
+#ifndef PB_SCORE_MIN_BLOCKS
+#define PB_SCORE_MIN_BLOCKS 4
+#endif
 template <int G, int R>
-__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_SCORE_MIN_BLOCKS)
 score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
              const uint8_t *__restrict__ seq, const uint8_t *__restrict__ ads, Scoring sc, EndCell *__restrict__ ends) {
     constexpr int SPW = 32 / G;

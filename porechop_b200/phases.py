@@ -77,29 +77,32 @@ def find_adapters_at_read_ends(reads, matching_sets, end_size, extra_trim_size, 
         # partial_score > end_threshold (NaN -> False), read_end != end_size, read_end - read_start >= min_trim_size
         with np.errstate(invalid='ignore'):
             ok = (part > end_threshold) & (re_ != end_size) & ((re_ - rs) >= min_trim_size)
-        for i, read in enumerate(reads):
-            for a, aset in enumerate(start_sets):
-                if ok[i, a]:
-                    trim_amount = int(re_[i, a]) + extra_trim_size
-                    read.start_trim_amount = max(read.start_trim_amount, trim_amount)
-                    read.start_adapter_alignments.append((aset, float(full[i, a]), float(part[i, a]), int(rs[i, a]),
-                                                          int(re_[i, a])))
-                if check_barcodes and aset.is_barcode() and aset.barcode_direction() == forward_or_reverse:
-                    read.start_barcode_scores[aset.get_barcode_name()] = float(full[i, a])
+        # only hits (and barcode scores) touch Python objects; np.nonzero is row-major = (read, adapter) order
+        for i, a in zip(*np.nonzero(ok)):
+            read, aset = reads[i], start_sets[a]
+            read.start_trim_amount = max(read.start_trim_amount, int(re_[i, a]) + extra_trim_size)
+            read.start_adapter_alignments.append((aset, float(full[i, a]), float(part[i, a]), int(rs[i, a]), int(re_[i, a])))
+        if check_barcodes:
+            cols = [a for a, s in enumerate(start_sets) if s.is_barcode() and s.barcode_direction() == forward_or_reverse]
+            names = [start_sets[a].get_barcode_name() for a in cols]
+            for i, read in enumerate(reads):
+                for a, nm in zip(cols, names):
+                    read.start_barcode_scores[nm] = float(full[i, a])
     if end_sets:
         full, part, rs, re_ = _cross([r.seq[-end_size:] for r in reads], [s.end_sequence[1] for s in end_sets],
                                      scoring_scheme_vals)
         with np.errstate(invalid='ignore'):
             ok = (part > end_threshold) & (rs != 0) & ((re_ - rs) >= min_trim_size)
-        for i, read in enumerate(reads):
-            for a, aset in enumerate(end_sets):
-                if ok[i, a]:
-                    trim_amount = (end_size - int(rs[i, a])) + extra_trim_size
-                    read.end_trim_amount = max(read.end_trim_amount, trim_amount)
-                    read.end_adapter_alignments.append((aset, float(full[i, a]), float(part[i, a]), int(rs[i, a]),
-                                                        int(re_[i, a])))
-                if check_barcodes and aset.is_barcode() and aset.barcode_direction() == forward_or_reverse:
-                    read.end_barcode_scores[aset.get_barcode_name()] = float(full[i, a])
+        for i, a in zip(*np.nonzero(ok)):
+            read, aset = reads[i], end_sets[a]
+            read.end_trim_amount = max(read.end_trim_amount, (end_size - int(rs[i, a])) + extra_trim_size)
+            read.end_adapter_alignments.append((aset, float(full[i, a]), float(part[i, a]), int(rs[i, a]), int(re_[i, a])))
+        if check_barcodes:
+            cols = [a for a, s in enumerate(end_sets) if s.is_barcode() and s.barcode_direction() == forward_or_reverse]
+            names = [end_sets[a].get_barcode_name() for a in cols]
+            for i, read in enumerate(reads):
+                for a, nm in zip(cols, names):
+                    read.end_barcode_scores[nm] = float(full[i, a])
 
 
 # ----------------------------------------------------------------------------------------------------------------
