@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='endtrim', choices=['endtrim', 'demux', 'middle'])
-    ap.add_argument('--reads', type=int, default=0, help='reads per rank (default: 1M endtrim, 32k demux, 64k middle)')
+    ap.add_argument('--reads', type=int, default=0, help='reads per rank (default: 1M endtrim, 32k demux, 256k middle)')
     ap.add_argument('--cpu-sample-reads', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
@@ -121,7 +121,7 @@ def make_workload(args, rank):
         batches = [('start', wl.windows_to_batch(sw), starts), ('end', wl.windows_to_batch(ew), ends)]
         desc = '%d synthetic reads x 356 adapters (119 sets + 12 native-full + 96 rapid-full), demux end windows' % n
     else:
-        n = args.reads or 65536
+        n = args.reads or 262144     # >= ~14 reads per resident group, so one 60-kb read is not the makespan
         yt, yb = wl.nsk007()
         buf, off = wl.synth_reads(n, yt, yb, seed=seed, chimera_p=0.05)
         batches = [('middle', (buf, off), [yt, yb])]
