@@ -129,21 +129,32 @@ struct Scoring {
     int32_t goEff;    // go (linear: ge)
     int32_t linear;   // go == ge : NW recurrence of dp_formula_linear.h, no end-cell correction
     int32_t ma, mi, go, ge;
+    // Row-offset domain of the score pass (ROWOFF): row q of a group carries the extra offset coff*q, chosen so that the
+    // substitution operand (sub - go + coff) is never negative: the diagonal add becomes a plain 32-bit add (FMA pipe)
+    // instead of a packed ALU add.  coff == 0 in the classic domain.
+    int32_t coff;
+    uint32_t c2;      // packed coff
 };
 
-PB_HD Scoring make_scoring(int ma, int mi, int go, int ge) {
+PB_HD int rowoff_c(int mi, int go, int ge) {      // smallest offset step that makes (mismatch - go + c) non-negative
+    const int goE = (go == ge) ? ge : go;
+    return (goE - mi) > 0 ? (goE - mi) : 0;
+}
+PB_HD Scoring make_scoring(int ma, int mi, int go, int ge, bool rowoff = false) {
     Scoring s;
     s.linear = (go == ge) ? 1 : 0;
     s.ma = ma; s.mi = mi; s.go = go; s.ge = ge;
     const int goE = s.linear ? ge : go;
     const int geE = s.linear ? -PB_LINEAR_EXT : ge;
+    const int c = rowoff ? rowoff_c(mi, go, ge) : 0;
+    s.coff = c; s.c2 = pack2(c, c);
     s.goEff = goE;
     s.goMag2 = pack2(-goE, -goE);
     s.geMag2 = pack2(-geE, -geE);
     s.ge2 = pack2(geE, geE);
-    s.subA2 = pack2(ma + 1 - goE, ma + 1 - goE);
-    s.subF2 = pack2(mi - goE, mi - goE);
-    s.padF2 = pack2(-goE, -goE);
+    s.subA2 = pack2(ma + 1 - goE + c, ma + 1 - goE + c);
+    s.subF2 = pack2(mi - goE + c, mi - goE + c);
+    s.padF2 = pack2(-goE + c, -goE + c);
     s.borderX2 = pack2(PB_BIAS + goE, PB_BIAS + goE);
     s.negb2 = pack2(PB_BIAS + PB_NEG16, PB_BIAS + PB_NEG16);
     return s;
@@ -188,6 +199,7 @@ struct Lane {
     uint32_t Hs[R];   // Hs[j-1][row] (biased)
     uint32_t v2[R];   // adapter code << PB_CODE_SHIFT of the owned rows, packed halves
     uint32_t sf2[R];  // per-row mismatch operand (real rows: mi - go, pad rows: -go)
+    int offBase;         // row-offset domain: offset of the row above this lane's top row (coff * g * R); 0 classic
     uint32_t prevRecvX;  // X[j-1][top-1]  (diagonal input of the top row)
     uint32_t botX, botV; // X[j][bottom], Vs[j][bottom] -> shuffled to the next lane
     // scout state: last-row running best (X domain), packed (meaningful in lane G-1 only) ...
@@ -215,13 +227,23 @@ PB_HD uint32_t subm2(uint32_t x, uint32_t P) {
     return x - P;
 }
 
+// x + P per half where both are non-negative and no half overflows 15 bits: one plain 32-bit addition
+PB_HD uint32_t addp2(uint32_t x, uint32_t P) {
+#if !defined(__CUDA_ARCH__) && defined(PB_CHECK_RANGES)
+    if (((x & 0xFFFFu) + (P & 0xFFFFu)) > 0x7FFFu || ((x >> 16) + (P >> 16)) > 0x7FFFu) pb_range_violation();
+#endif
+    return x + P;
+}
+
 template <int R>
 PB_HD void lane_init(Lane<R> &L, int g, int G, const Scoring &sc, const uint8_t *adA, int mA, bool leftInfA,
                      const uint8_t *adB, int mB, bool leftInfB) {
     const int padA = G * R - mA, padB = G * R - mB;
-    // column 0: X = S0 + go + bias with S0 = 0 (border / pad rows) or -inf (real rows of a windowed task)
+    // column 0: X = S0 + go + bias with S0 = 0 (border / pad rows) or -inf (real rows of a windowed task); in the
+    // row-offset domain every value of group row q additionally carries coff*q
     const uint32_t x0 = sc.borderX2;
     const uint32_t xinf = add2(sc.negb2, pack2(sc.goEff, sc.goEff));
+    L.offBase = sc.coff * g * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int q = g * R + r + 1;
@@ -229,18 +251,20 @@ PB_HD void lane_init(Lane<R> &L, int g, int G, const Scoring &sc, const uint8_t 
         const bool realA = iA >= 1, realB = iB >= 1;
         const uint32_t a = realA ? (uint32_t)adA[iA - 1] : (uint32_t)PB_PAD_V;
         const uint32_t b = realB ? (uint32_t)adB[iB - 1] : (uint32_t)PB_PAD_V;
+        const uint32_t oq = pack2(sc.coff * q, sc.coff * q);
         L.v2[r] = (a << 8) | (b << 24);               // code<<4 in a byte -> code<<12 in the half
         L.sf2[r] = ((realA ? sc.subF2 : sc.padF2) & 0xFFFFu) | ((realB ? sc.subF2 : sc.padF2) & 0xFFFF0000u);
-        L.X[r] = (((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u);
-        L.Hs[r] = sc.negb2;
+        L.X[r] = add2((((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u), oq);
+        L.Hs[r] = add2(sc.negb2, oq);
     }
     {   // X[0][row above this lane's top row]
         const int q = g * R;
         const bool realA = (q - padA) >= 1, realB = (q - padB) >= 1;
-        L.prevRecvX = (((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u);
+        L.prevRecvX = add2((((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u),
+                           pack2(sc.coff * q, sc.coff * q));
     }
-    L.botX = L.X[R - 1]; L.botV = sc.negb2;
-    L.lrBest2 = sc.borderX2;                           // candidate (0, m): S = 0
+    L.botX = L.X[R - 1]; L.botV = add2(sc.negb2, pack2(sc.coff * (g * R + R), sc.coff * (g * R + R)));
+    L.lrBest2 = add2(sc.borderX2, pack2(sc.coff * (g * R + R), sc.coff * (g * R + R)));   // candidate (0, m): S = 0
     for (int h = 0; h < 2; ++h) {
         L.lrJ[h] = 0; L.lrCorr[h] = 0;
         L.fcBest[h] = -1; L.fcI[h] = 0; L.fcCorr[h] = 0;   // biased X values are >= 0
@@ -302,7 +326,7 @@ template <int R> PB_HD int trace_shift(int h, int r) { return (R <= 4) ? (4 * r 
 #else
 #define PB_EXT(x) subm2((x), sc.geMag2)
 #endif
-template <int R, bool TRACE, bool KEEPV = false>
+template <int R, bool TRACE, bool KEEPV = false, bool ROWOFF = false>
 PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, const Scoring &sc, uint32_t *tw,
                      uint32_t *vr = nullptr) {
     uint32_t diagX = L.prevRecvX, upX = recvX, upV = recvV;
@@ -311,7 +335,8 @@ PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, co
     for (int r = 0; r < R; ++r) {
         // substitution (minus go) per half: codes equal -> ~(h^v) == -1 -> max(-1 + ma + 1 - go, mi - go) = ma - go
         const uint32_t sub = addmax2(xnor2(h2, L.v2[r]), sc.subA2, L.sf2[r]);
-        const uint32_t d = add2(diagX, sub);                       // S_diag + sub   (biased)
+        // S_diag + sub (biased).  ROWOFF: sub >= 0 by construction -> plain 32-bit add on the FMA pipe
+        const uint32_t d = ROWOFF ? addp2(diagX, sub) : add2(diagX, sub);
         uint32_t hs, vs, s;
         if (TRACE) {
             const uint32_t bl = 1u << trace_shift<R>(0, r);
@@ -323,6 +348,7 @@ PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, co
         } else {
             hs = addmax2(L.Hs[r], sc.ge2, L.X[r]);
             vs = addmax2(upV, sc.ge2, upX);
+            if (ROWOFF) vs = addp2(vs, sc.c2);                     // row above -> this row's offset domain
             s = max3(d, vs, hs);
         }
         diagX = L.X[r];
@@ -378,10 +404,11 @@ PB_HD void lane_track_general(Lane<R> &L, int g, int j, const HalfGeom &A, const
             for (int r = 0; r < R; ++r) {
                 const int i = g * R + r + 1 - H.pad;
                 if (i >= 1) {
-                    const int c = half16(L.X[r], h);
+                    const int co = half16(L.X[r], h);                       // row-offset domain value
+                    const int c = co - (L.offBase + sc.coff * (r + 1));     // comparable across rows
                     if (c > L.fcBest[h]) {
                         L.fcBest[h] = c; L.fcI[h] = i;
-                        L.fcCorr[h] = corr_flags(c, half16(vr[r], h), half16(L.Hs[r], h), sc.goEff);
+                        L.fcCorr[h] = corr_flags(co, half16(vr[r], h), half16(L.Hs[r], h), sc.goEff);
                     }
                 }
             }
@@ -397,7 +424,7 @@ PB_HD ScoutCand make_cand(const Lane<R> &L, int h, const Scoring &sc) {
     ScoutCand c;
     c.fcBest = L.fcBest[h] < 0 ? -0x40000000 : L.fcBest[h] - PB_BIAS - sc.goEff;
     c.fcI = L.fcI[h]; c.fcCorr = L.fcCorr[h];
-    c.lrBest = half16(L.lrBest2, h) - PB_BIAS - sc.goEff; c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
+    c.lrBest = half16(L.lrBest2, h) - PB_BIAS - sc.goEff - (L.offBase + sc.coff * R); c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
     return c;
 }
 PB_HD EndCell scout_combine(const ScoutCand *c, int G, const HalfGeom &H) {

@@ -59,6 +59,7 @@ struct Options {
     int64_t chunk_tasks = 1 << 17; // alignments per pipeline chunk (host-buffer API)
     int64_t device_chunk_tasks = 8 << 20; // alignments per launch group (device-resident API)
     int64_t chunk_bytes = 64ll << 20;   // sequence bytes per pipeline chunk (host-buffer API)
+    int rowoff = 1;                // score pass in the row-offset domain when it fits (0 = always classic)
     int scratch_mb = 128;          // cap on the resident trace scratch (MB); 72 keeps it L2-resident at ~10% lower speed
     int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
 };
@@ -69,6 +70,7 @@ void load_env_options() {
         if (const char *v = getenv("PB200_DIRECT_MAX")) g_opt.direct_max = atoll(v);
         if (const char *v = getenv("PB200_CHUNK_TASKS")) g_opt.chunk_tasks = std::max(1ll, atoll(v));
         if (const char *v = getenv("PB200_SCRATCH_MB")) g_opt.scratch_mb = std::max(1, atoi(v));
+        if (const char *v = getenv("PB200_ROWOFF")) g_opt.rowoff = atoi(v);
         if (const char *v = getenv("PB200_HBUF")) g_opt.hbuf_mode = !strcmp(v, "smem") ? 1 : !strcmp(v, "global") ? 2 : 0;
     });
 }
@@ -253,10 +255,10 @@ int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const 
     return fail(PB200_ERR_INTERNAL, "bad class");
 }
 
-template <int G, int R>
-int launch_score(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsigned long long *counter,
-                 const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, EndCell *ends) {
-    auto kern = score_kernel<G, R>;
+template <int G, int R, bool RO>
+int launch_score_variant(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsigned long long *counter,
+                         const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, EndCell *ends) {
+    auto kern = score_kernel<G, R, RO>;
     int bps = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, PB_WARPS_PER_BLOCK * 32, 0));
     if (bps < 1) bps = 1;
@@ -275,14 +277,25 @@ int launch_score(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsigned lon
     CK(cudaGetLastError());
     return 0;
 }
+// The score pass runs in the row-offset domain when the offsets (coff per group row) still fit the int16 domain.
+template <int G, int R>
+int launch_score(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsigned long long *counter, const uint8_t *seq_codes,
+                 const uint8_t *ad_codes, const Scoring &sc, const SchemeInfo &si, int m_max, EndCell *ends) {
+    const long long c = rowoff_c(sc.mi, sc.go, sc.ge);
+    if (g_opt.rowoff && (long long)si.A * (m_max + 3) + c * G * R <= PB_I16_LIMIT) {
+        const Scoring so = make_scoring(sc.ma, sc.mi, sc.go, sc.ge, true);
+        return launch_score_variant<G, R, true>(E, stream, ts, counter, seq_codes, ad_codes, so, ends);
+    }
+    return launch_score_variant<G, R, false>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
+}
 int launch_score_class(Engine &E, cudaStream_t stream, int cls, const TaskSrc &ts,
                        unsigned long long *counter, const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc,
-                       EndCell *ends) {
+                       const SchemeInfo &si, int m_max, EndCell *ends) {
     switch (cls / 4) {
-        case 0: return launch_score<4, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
-        case 1: return launch_score<8, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
-        case 2: return launch_score<16, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
-        case 3: return launch_score<32, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
+        case 0: return launch_score<4, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, si, m_max, ends);
+        case 1: return launch_score<8, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, si, m_max, ends);
+        case 2: return launch_score<16, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, si, m_max, ends);
+        case 3: return launch_score<32, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, si, m_max, ends);
     }
     return fail(PB200_ERR_INTERNAL, "bad class");
 }
@@ -307,7 +320,7 @@ int run_class_tasks(Engine &E, Stage &S, cudaStream_t stream, int cls, int m_max
     if (!two_pass) return launch_trace_class(E, S, stream, cls, ts, (int)max_n, seq_codes, ad_codes, sc, out, status);
     if (int rc = S.ends.ensure((size_t)n_tasks * sizeof(EndCell))) return rc;
     if (int rc = S.tasks2.ensure((size_t)n_tasks * sizeof(Task))) return rc;
-    if (int rc = launch_score_class(E, stream, cls, ts, counter, seq_codes, ad_codes, sc, S.ends.as<EndCell>())) return rc;
+    if (int rc = launch_score_class(E, stream, cls, ts, counter, seq_codes, ad_codes, sc, si, m_max, S.ends.as<EndCell>())) return rc;
     {
         int64_t blocks = (n_tasks + 255) / 256;
         window_tasks_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ts, S.ends.as<EndCell>(), S.tasks2.as<Task>(), si.wnum, si.wden);
@@ -840,6 +853,7 @@ int pb200SetOption(const char *name, const char *value) {
     if (!strcmp(name, "direct_max")) g_opt.direct_max = atoll(value);
     else if (!strcmp(name, "chunk_tasks")) g_opt.chunk_tasks = std::max(1ll, atoll(value));
     else if (!strcmp(name, "scratch_mb")) g_opt.scratch_mb = std::max(1, atoi(value));
+    else if (!strcmp(name, "rowoff")) g_opt.rowoff = atoi(value);
     else if (!strcmp(name, "hbuf")) g_opt.hbuf_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;
     else return PB200_ERR_ARG;
     return 0;

@@ -375,6 +375,8 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
 // score_kernel: streaming score-only pass for long reads.  Same wavefront, no trace (7 instructions per row:
 // 3x VIADDMNMX, LOP3, VIADDMNMX-fused diagonal, VIMNMX, X update), exact scout.  Groups pull slots from a global
 // counter and refill independently, so a warp's groups never wait for each other's read lengths.
+// RO = row-offset domain (dp_core.cuh): the diagonal add is a plain 32-bit add on the FMA pipe, leaving 5 ALU-pipe
+// instructions per row (the ALU pipe is this kernel's bound) -- used whenever the row offsets fit the int16 domain.
 //
 // Read bases are streamed through a per-group shared-memory ring of packed columns (64 entries = two blocks of 32
 // columns).  A block is fetched with aligned 64/32-bit loads (funnel-shifted to the unaligned start) one block
@@ -410,7 +412,7 @@ __device__ __forceinline__ uint64_t load_cols(const uint8_t *p) {
 #ifndef PB_SCORE_MIN_BLOCKS
 #define PB_SCORE_MIN_BLOCKS 4
 #endif
-template <int G, int R>
+template <int G, int R, bool RO>
 __global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_SCORE_MIN_BLOCKS)
 score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
              const uint8_t *__restrict__ seq, const uint8_t *__restrict__ ads, Scoring sc, EndCell *__restrict__ ends) {
@@ -507,7 +509,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                 uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
                 if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
                 const int j = t - g + 1;
-                lane_step<R, false, false>(L, recvS, recvV, ring[(j - 1) & (PB_RING - 1)], sc, nullptr);
+                lane_step<R, false, false, RO>(L, recvS, recvV, ring[(j - 1) & (PB_RING - 1)], sc, nullptr);
                 lane_track_lastrow<R>(L, j, sc);
                 ++t;
             }
@@ -521,7 +523,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                 if (j >= 1 && j <= nmax) {          // nmax == 0 for exhausted groups
                     const uint32_t h2 = ring[(j - 1) & (PB_RING - 1)];
                     uint32_t vr[R];
-                    lane_step<R, false, true>(L, recvS, recvV, h2, sc, nullptr, vr);
+                    lane_step<R, false, true, RO>(L, recvS, recvV, h2, sc, nullptr, vr);
                     if (j < nmin) lane_track_lastrow<R>(L, j, sc);
                     else lane_track_general<R>(L, g, j, gA, gB, vr, sc);
                 }

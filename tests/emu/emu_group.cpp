@@ -94,7 +94,7 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
     }
 }
 
-template <int R>
+template <int R, bool RO>
 void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, EndCell *eA, EndCell *eB) {
     const Task &tA = A.t, &tB = B.t;
     HalfGeom gA = make_geom(tA.n, tA.m, G, R), gB = make_geom(tB.n, tB.m, G, R);
@@ -116,11 +116,11 @@ void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, End
                 int ja = std::min(j, tA.n) - 1, jb = std::min(j, tB.n) - 1;
                 uint32_t bA = ja >= 0 ? seqA[ja] : PB_PAD_H, bB = jb >= 0 ? seqB[jb] : PB_PAD_H;
                 if (j < nmin) {
-                    lane_step<R, false, false>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr);
+                    lane_step<R, false, false, RO>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr);
                     lane_track_lastrow<R>(L[g], j, sc);
                 } else {
                     uint32_t vr[R];
-                    lane_step<R, false, true>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, vr);
+                    lane_step<R, false, true, RO>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, vr);
                     lane_track_general<R>(L[g], g, j, gA, gB, vr, sc);
                 }
             }
@@ -162,7 +162,8 @@ void to_window(Task &t, const EndCell &e, int wnum, int wden) {
 
 extern "C" {
 
-// mode 0: single trace pass; mode 1: score pass + windowed trace pass (W = m + m*wnum/wden).
+// mode 0: single trace pass; mode 1 / 2: score pass (classic / row-offset domain) + windowed trace pass
+// (W = m + m*wnum/wden).
 // G in {4,8,16,32}, R in {4..8}; pass nB < 0 to leave half B empty.  Returns the status bit (window violated).
 int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char *seqB, int nB, const char *adB, int mB,
                    int G, int R, int mode, int ma, int mi, int go, int ge, int wnum, int wden, int32_t *recA,
@@ -171,14 +172,27 @@ int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char
     Half A = make_half(seqA, nA, adA, mA, 0);
     Half B = nB >= 0 ? make_half(seqB, nB, adB, mB, 1) : make_half("", 0, "", 0, -1);
     int status = 0;
-    if (mode == 1) {
+    if (mode >= 1) {
         EndCell eA, eB;
-        switch (R) {
-            case 5: run_score_group<5>(G, A, B, sc, &eA, &eB); break;
-            case 6: run_score_group<6>(G, A, B, sc, &eA, &eB); break;
-            case 7: run_score_group<7>(G, A, B, sc, &eA, &eB); break;
-            case 8: run_score_group<8>(G, A, B, sc, &eA, &eB); break;
-            default: run_score_group<4>(G, A, B, sc, &eA, &eB); break;
+        // mode 1: classic score pass; mode 2: row-offset domain (plain-add diagonal), the engine's default when the
+        // offsets fit the int16 domain
+        const Scoring so = make_scoring(ma, mi, go, ge, mode == 2);
+        if (mode == 2) {
+            switch (R) {
+                case 5: run_score_group<5, true>(G, A, B, so, &eA, &eB); break;
+                case 6: run_score_group<6, true>(G, A, B, so, &eA, &eB); break;
+                case 7: run_score_group<7, true>(G, A, B, so, &eA, &eB); break;
+                case 8: run_score_group<8, true>(G, A, B, so, &eA, &eB); break;
+                default: run_score_group<4, true>(G, A, B, so, &eA, &eB); break;
+            }
+        } else {
+            switch (R) {
+                case 5: run_score_group<5, false>(G, A, B, so, &eA, &eB); break;
+                case 6: run_score_group<6, false>(G, A, B, so, &eA, &eB); break;
+                case 7: run_score_group<7, false>(G, A, B, so, &eA, &eB); break;
+                case 8: run_score_group<8, false>(G, A, B, so, &eA, &eB); break;
+                default: run_score_group<4, false>(G, A, B, so, &eA, &eB); break;
+            }
         }
         to_window(A.t, eA, wnum, wden);
         if (nB >= 0) to_window(B.t, eB, wnum, wden);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdint>
+#include <cuda_fp16.h>
 
 #define ITER 4096
 template <int OP>
@@ -32,6 +33,19 @@ __global__ void k(uint32_t *out, uint32_t seed, long long *cycles) {
             }
             if (OP == 6) { uint32_t d; asm("lop3.b32 %0, %1, %2, 0, 0xC3;" : "=r"(d) : "r"(a[i]), "r"(c2)); a[i] = d; }
             if (OP == 7) a[i] = a[i] * 3 + c1;                                         // IMAD
+            if (OP == 8) {                                                            // HMNMX2 (fp16x2 max on int patterns)
+                __half2 x = *reinterpret_cast<__half2 *>(&a[i]); uint32_t cc = (c2 + it) & 0x3fff3fffu;
+                __half2 y = *reinterpret_cast<__half2 *>(&cc);
+                x = __hmax2(x, y); a[i] = *reinterpret_cast<uint32_t *>(&x) + 1;
+            }
+            if (OP == 9) {                                                            // VIADDMNMX + HMNMX2 interleaved
+                if (i & 1) { a[i] = __viaddmax_s16x2(a[i], c1, c2); }
+                else { __half2 x = *reinterpret_cast<__half2 *>(&a[i]); uint32_t cc = (c2 + it) & 0x3fff3fffu;
+                       __half2 y = *reinterpret_cast<__half2 *>(&cc); x = __hmax2(x, y); a[i] = *reinterpret_cast<uint32_t *>(&x); }
+            }
+            if (OP == 10) {                                                           // VIADDMNMX + 32-bit sub interleaved
+                if (i & 1) a[i] = __viaddmax_s16x2(a[i], c1, c2); else a[i] = a[i] - (c1 + it);
+            }
         }
     }
     long long t1 = clock64();
@@ -62,5 +76,8 @@ int main() {
     run<5>("VIMNMX.P + 2 pred adds + add (4)", 4);
     run<6>("LOP3", 1);
     run<7>("IMAD", 1);
+    run<8>("HMNMX2 + add (2)", 2);
+    run<9>("VIADDMNMX / HMNMX2 alternating", 1);
+    run<10>("VIADDMNMX / 32-bit sub alternating", 1);
     return 0;
 }
