@@ -82,7 +82,8 @@ int pb200TimingRead(double *dp_kernel_ms, long long *dp_kernel_launches, double 
  *   "direct_max"  longest sequence aligned in one pass (default 512; longer ones take score pass + bounded window)
  *   "chunk_tasks" alignments per pipeline chunk of the host-buffer API (default 131072)
  *   "scratch_mb"  cap on the resident trace scratch in MB (default 128; 72 keeps it L2-resident)
- *   "hbuf"        staging of a slot's packed bases: "auto" | "smem" | "global" */
+ *   "hbuf"        staging of a slot's packed bases: "auto" | "smem" | "global"
+ *   "rowoff"      1 = score pass in the row-offset arithmetic domain when it fits (default 0; same results) */
 int pb200SetOption(const char *name, const char *value);
 
 enum {

@@ -59,7 +59,7 @@ struct Options {
     int64_t chunk_tasks = 1 << 17; // alignments per pipeline chunk (host-buffer API)
     int64_t device_chunk_tasks = 8 << 20; // alignments per launch group (device-resident API)
     int64_t chunk_bytes = 64ll << 20;   // sequence bytes per pipeline chunk (host-buffer API)
-    int rowoff = 1;                // score pass in the row-offset domain when it fits (0 = always classic)
+    int rowoff = 0;                // 1: score pass in the row-offset domain when it fits (measured: no gain)
     int scratch_mb = 128;          // cap on the resident trace scratch (MB); 72 keeps it L2-resident at ~10% lower speed
     int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
 };

@@ -161,22 +161,23 @@ def test_read_length_sweep_barcodes(W):
 
 
 def test_score_pass_classic_domain_option(W):
-    """The score pass has two arithmetic domains (row-offset = default when it fits, classic otherwise): same records."""
+    """The score pass has two arithmetic domains (classic = default, row-offset = option "rowoff"): same records."""
     from porechop_b200 import workloads as wl
     yt, yb = wl.nsk007()
     buf, off = wl.synth_reads(60, yt, yb, seed=31, chimera_p=0.3, max_len=9000)
     abuf, aoff = wl.pack_adapters([yt, yb])
     exp = oracle_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
+    got0 = W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
     try:
-        W.set_option('rowoff', 0)
-        got0 = W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
-    finally:
         W.set_option('rowoff', 1)
-    got1 = W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
+        got1 = W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
+        # a scheme whose offsets do not fit (large mismatch penalty) silently takes the classic domain
+        sc = [3, -120, -5, -2]
+        got2 = W.adapter_alignment_batch(buf, off, abuf, aoff, sc)
+    finally:
+        W.set_option('rowoff', 0)
     assert np.array_equal(got0, exp) and np.array_equal(got1, exp)
-    # a scheme whose offsets do not fit (large mismatch penalty) silently takes the classic domain
-    sc = [3, -120, -5, -2]
-    assert np.array_equal(W.adapter_alignment_batch(buf, off, abuf, aoff, sc), oracle_batch(buf, off, abuf, aoff, sc))
+    assert np.array_equal(got2, oracle_batch(buf, off, abuf, aoff, sc))
 
 
 def test_generic_int32_path(W):
