@@ -140,9 +140,10 @@ def batch_alg_bytes(batch):
     return int(off[-1] - off[0]) + sum(len(a) for a in ads) + 36 * n * len(ads)
 
 
-def run_reference_harness(batches, scoring, sample_reads, threads):
+def run_reference_harness(batches, scoring, sample_reads, threads, answers=None):
     """Time the reference CPU path (oracle/_ref/cpp_functions.so via the native harness) on the first
-    `sample_reads` reads of every batch.  Returns (seconds, reads, cells, kind)."""
+    `sample_reads` reads of every batch.  Returns (seconds, reads, cells, kind).  With `answers` (a list), the result
+    strings of every sampled pair (pair order = read-major) are appended per batch: the checker for the parity gate."""
     from porechop_b200 import workloads as wl
     lib = os.path.join(ROOT, 'oracle', '_ref', 'cpp_functions.so')
     kind = 'reference'
@@ -160,10 +161,30 @@ def run_reference_harness(batches, scoring, sample_reads, threads):
             abuf, aoff = wl.pack_adapters(ads)
             p = os.path.join(d, name + '.bin')
             wl.write_harness_file(p, buf[:off[k]], off[:k + 1], abuf, aoff, scoring)
-            info = json.loads(subprocess.check_output([harness, lib, p, str(threads)]).decode())
+            cmd = [harness, lib, p, str(threads)]
+            if answers is not None:
+                cmd.append(os.path.join(d, name + '.answers'))
+            info = json.loads(subprocess.check_output(cmd).decode())
             sec += info['seconds']
             cells += info['cells']
+            if answers is not None:
+                with open(cmd[-1]) as f:
+                    answers.append(f.read().split('\n')[:-1])
     return sec, min(sample_reads, len(batches[0][1][1]) - 1), cells, kind
+
+
+def parity_gate(records_per_batch, answers_per_batch, format_record):
+    """SURVEY 8(d) parity gate: the engine's records of the sampled pairs, rendered as the reference's result string,
+    must equal the CPU reference's strings.  (An empty alignment is compared on its first field only: the reference
+    leaves the others uninitialised.)  Returns {'checked': n, 'mismatches': k}."""
+    checked = bad = 0
+    for rec, ans in zip(records_per_batch, answers_per_batch):
+        for r, a in zip(rec[:len(ans)], ans):
+            g = format_record(r)
+            ok = (g == a) or (a.startswith('-1,') and g.startswith('-1,'))
+            checked += 1
+            bad += 0 if ok else 1
+    return {'checked': checked, 'mismatches': bad}
 
 
 def host_cores():
@@ -377,7 +398,13 @@ def main():
         cores = host_cores()
         per_read_cells = cells_per_step / n
         sample = args.cpu_sample_reads or int(max(64, min(n, 0.08e9 * 1.0 * cores * 4 / per_read_cells)))
-        sec, reads, ccells, kind = run_reference_harness(batches, scoring, sample, cores)
+        answers = []
+        sec, reads, ccells, kind = run_reference_harness(batches, scoring, sample, cores, answers)
+        try:    # parity gate on the same sample: records of the last e2e step vs the CPU reference's strings
+            line['parity'] = parity_gate([h[4].numpy() for h in host], answers, W.format_record)
+            line['parity']['against'] = kind
+        except Exception as e:      # never lose the bench line to the checker
+            line['parity'] = {'error': repr(e)}
         line['cpu_baseline'] = {'value': sample / sec, 'unit': 'reads/s', 'cores': cores, 'kind': kind,
                                 'gcups': ccells / sec / 1e9,
                                 'sample': 'first %d reads of the same batch (all their alignments), %d threads, native harness '

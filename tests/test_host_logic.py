@@ -98,3 +98,26 @@ def test_gather_records_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert all(res)
+
+
+def test_bench_parity_gate_against_harness_answers():
+    """bench.py's parity gate: harness answer strings vs records rendered by pb200FormatRecord.  Here the
+    records come from the oracle (no GPU in this tier); one record is then corrupted to see the gate fire."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    from porechop_b200 import workloads as wl
+    from porechop_b200 import cpp_function_wrappers as W
+    yt, yb = wl.nsk007()
+    L, sw, ew = wl.synth_end_windows(200, yt, yb, seed=7)
+    batches = [('start', wl.windows_to_batch(sw), [yt]), ('end', wl.windows_to_batch(ew), [yb])]
+    answers = []
+    sec, reads, cells, kind = bench.run_reference_harness(batches, wl.DEFAULT_SCORING, 150, 2, answers)
+    assert len(answers) == 2 and len(answers[0]) == 150 and sec > 0
+    recs = []
+    for name, (buf, off), ads in batches:
+        abuf, aoff = wl.pack_adapters(ads)
+        recs.append(oracle_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING))
+    assert bench.parity_gate(recs, answers, W.format_record) == {'checked': 300, 'mismatches': 0}
+    recs[1][3, 1] += 1
+    assert bench.parity_gate(recs, answers, W.format_record) == {'checked': 300, 'mismatches': 1}
