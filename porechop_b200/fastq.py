@@ -1,29 +1,46 @@
 """
-Bulk FASTQ ingest and end-trim decisions without per-read Python objects (host side).
+Flat-buffer FASTQ pipeline: bytes in -> trimmed / split FASTQ or FASTA bytes out, without per-read Python objects
+(host side).
 
-The reference loads every read into a Python `NanoporeRead` (misc.py:109-168) and decides trims read by read
-(nanopore_read.py:166-208).  For 10^6-10^7 reads that host work would hide the GPU gain, so this
-module keeps reads as flat numpy buffers end to end:
+The reference loads every read into a Python `NanoporeRead` (misc.py:151-168, nanopore_read.py:23-55), decides trims
+read by read (nanopore_read.py:166-243) and formats output strings read by read (nanopore_read.py:76-147).  For
+10^6-10^7 reads that host work would hide the GPU gain, so this module keeps reads as flat numpy
+buffers end to end:
 
-  parse_fastq(data)          4-line FASTQ bytes -> flat sequence / quality buffers + offsets (vectorised newline scan)
+  parse_fastq(data)          4-line FASTQ bytes -> FastqBatch (flat names / bases / qualities + offsets; bases
+                             upper-cased, RNA reads detected and stored as T, exactly as NanoporeRead.__init__ does)
   end_windows(...)           the `seq[:end_size]` / `seq[-end_size:]` windows of every read as one ragged batch
   end_trim_amounts(...)      the reference's start/end trim rule applied to whole record arrays at once
-  trim_end_adapters(...)     parse -> windows -> two batched engine calls -> trim amounts (a whole Phase B for one set list)
+  trim_end_adapters(...)     windows -> two batched engine calls -> trim amounts (a whole Phase B for fixed adapters)
+  trimmed_ranges(...)        the `seq[start_trim : len - end_trim]` slice of every read (Python slice semantics)
+  find_middle_hits(...)      Phase C on the trimmed reads: one cross-product submit, then only the reads with a hit
+                             are masked and re-submitted (the reference's sequential masking, nanopore_read.py:210-243)
+  middle_trim_ranges(...)    hits -> the ranges the reference adds to `middle_trim_positions`
+  emit(...)                  get_fastq / get_fasta of every read (split parts, numbering, --discard_middle,
+                             --min_split_read_size, RNA T->U) as one bytes object, assembled with vectorised scatters
+  trim_fastq(...)            all of the above for a fixed list of adapter sets: what `porechop -i x.fastq -o y.fastq`
+                             writes once Phase A has chosen the sets
 
-The alignment engine is case-insensitive and maps U to T itself (Dna5 table), so sequences are not rewritten; the
-`rna` flag / upper-casing of nanopore_read.py:26-31 only matter when reads are written back out.
+The alignment engine is case-insensitive and maps U to T itself (Dna5 table); normalising at parse time only matters
+because the reference writes the normalised bases back out.
 """
 import numpy as np
 
 from . import cpp_function_wrappers as W
 from .align import scores_from_records
 
+_WS = np.zeros(256, dtype=bool)
+_WS[[9, 10, 11, 12, 13, 32]] = True            # what str.strip() removes from an ASCII line
+
 
 class FastqBatch:
-    """Flat view of a FASTQ chunk: read i has name names[i], bases seq[seq_off[i]:seq_off[i+1]], same for qual."""
+    """Flat view of a FASTQ chunk: read i has name name_buf[name_off[i]:name_off[i+1]], bases
+    seq[seq_off[i]:seq_off[i+1]] (upper case, RNA stored as T with rna[i] set), qualities likewise."""
 
-    def __init__(self, names, seq, seq_off, qual, qual_off):
-        self.names, self.seq, self.seq_off, self.qual, self.qual_off = names, seq, seq_off, qual, qual_off
+    def __init__(self, name_buf, name_off, seq, seq_off, qual, qual_off, rna):
+        self.name_buf, self.name_off = name_buf, name_off
+        self.seq, self.seq_off, self.qual, self.qual_off, self.rna = seq, seq_off, qual, qual_off, rna
+        self._names = None
 
     def __len__(self):
         return len(self.seq_off) - 1
@@ -31,10 +48,35 @@ class FastqBatch:
     def lengths(self):
         return np.diff(self.seq_off)
 
+    @property
+    def names(self):
+        if self._names is None:
+            b, o = self.name_buf.tobytes(), self.name_off
+            self._names = [b[o[i]:o[i + 1]].decode('ascii', 'replace') for i in range(len(self))]
+        return self._names
+
+
+def _strip(buf, starts, ends):
+    """str.strip() of every line [starts, ends) -- vectorised; loops once per stripped character (normally 0 or 1)."""
+    starts, ends = starts.copy(), ends.copy()
+    while True:
+        m = (ends > starts) & _WS[buf[np.maximum(ends - 1, 0)]]
+        if not m.any():
+            break
+        ends -= m
+    while True:
+        m = (ends > starts) & _WS[buf[np.minimum(starts, len(buf) - 1)]]
+        if not m.any():
+            break
+        starts += m
+    return starts, ends
+
 
 def parse_fastq(data):
     """data: bytes / uint8 array of 4-line FASTQ records ('@name', bases, '+', qualities).  Returns a FastqBatch.
-    Multi-line records are not supported (the reference's loader assumes 4 lines as well, misc.py:143-168)."""
+    Lines are stripped like the reference's loader strips them (misc.py:160-166: `line.strip()`, name = header minus
+    its first character); multi-line records are not supported there either.  Qualities shorter than the bases are
+    padded with '+' (nanopore_read.py:34-36)."""
     buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
     if buf.size and buf[-1] != 10:
         buf = np.concatenate([buf, np.array([10], dtype=np.uint8)])
@@ -42,32 +84,77 @@ def parse_fastq(data):
     if len(nl) % 4 != 0:
         raise ValueError('FASTQ chunk is not a whole number of 4-line records')
     n = len(nl) // 4
+    z = np.zeros(0, dtype=np.uint8)
+    if n == 0:
+        o = np.zeros(1, dtype=np.int64)
+        return FastqBatch(z, o, z, o.copy(), z, o.copy(), np.zeros(0, dtype=bool))
     starts = np.concatenate([[0], nl[:-1] + 1])            # start of every line
-    ends = nl.copy()                                       # exclusive end of every line (at '\n'; strip '\r')
-    cr = (ends > starts) & (buf[np.maximum(ends - 1, 0)] == 13)
-    ends = ends - cr
-    if n and not (buf[starts[0::4]] == ord('@')).all():
+    starts, ends = _strip(buf, starts, nl)
+    if not ((ends[0::4] > starts[0::4]) & (buf[starts[0::4]] == ord('@'))).all():
         raise ValueError('FASTQ record does not start with @')
-    s0, s1 = starts[1::4], ends[1::4]
-    q0, q1 = starts[3::4], ends[3::4]
-    seq, seq_off = _gather_ranges(buf, s0, s1)
-    qual, qual_off = _gather_ranges(buf, q0, q1)
-    names = [bytes(buf[a + 1:b]).decode('ascii', 'replace') for a, b in zip(starts[0::4], ends[0::4])]
-    return FastqBatch(names, seq, seq_off, qual, qual_off)
+    name_buf, name_off = _gather_ranges(buf, starts[0::4] + 1, ends[0::4])
+    seq, seq_off = _gather_ranges(buf, starts[1::4], ends[1::4])
+    qual, qual_off = _gather_ranges(buf, starts[3::4], ends[3::4])
+    # seq.upper(); RNA if count('U') > count('T') -> stored as T (nanopore_read.py:26-31)
+    lower = (seq >= ord('a')) & (seq <= ord('z'))
+    seq = np.where(lower, seq - 32, seq).astype(np.uint8)
+    n_u = _segment_sums(seq == ord('U'), seq_off)
+    n_t = _segment_sums(seq == ord('T'), seq_off)
+    rna = n_u > n_t
+    if rna.any():
+        is_rna_base = np.repeat(rna, np.diff(seq_off))
+        seq = np.where(is_rna_base & (seq == ord('U')), ord('T'), seq).astype(np.uint8)
+    short = np.diff(seq_off) - np.diff(qual_off)
+    if (short > 0).any():
+        qual, qual_off = _pad_segments(qual, qual_off, np.maximum(short, 0), ord('+'))
+    return FastqBatch(name_buf, name_off, np.ascontiguousarray(seq), seq_off, qual, qual_off, rna)
+
+
+def _segment_sums(flags, off):
+    c = np.zeros(len(flags) + 1, dtype=np.int64)
+    np.cumsum(flags, out=c[1:])
+    return c[off[1:]] - c[off[:-1]]
+
+
+def _pad_segments(buf, off, pad, fill):
+    lens = np.diff(off) + pad
+    new_off = np.zeros(len(off), dtype=np.int64)
+    np.cumsum(lens, out=new_off[1:])
+    out = np.full(int(new_off[-1]), fill, dtype=np.uint8)
+    _scatter(out, new_off[:-1], buf, off[:-1], np.diff(off))
+    return out, new_off
+
+
+def _ramp(lens):
+    """concatenated arange(l) for l in lens, plus the segment id of every element."""
+    lens = np.asarray(lens, dtype=np.int64)
+    total = int(lens.sum())
+    first = np.zeros(len(lens), dtype=np.int64)
+    np.cumsum(lens[:-1], out=first[1:])
+    seg = np.repeat(np.arange(len(lens), dtype=np.int64), lens)
+    return np.arange(total, dtype=np.int64) - first[seg], seg
 
 
 def _gather_ranges(buf, a, b):
     """concatenate buf[a[i]:b[i]] for all i -> (flat uint8, int64 offsets) without a Python loop."""
-    lens = (b - a).astype(np.int64)
+    lens = np.maximum(np.asarray(b, dtype=np.int64) - np.asarray(a, dtype=np.int64), 0)
     off = np.zeros(len(lens) + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
-    total = int(off[-1])
-    if total == 0:
+    if int(off[-1]) == 0:
         return np.zeros(0, dtype=np.uint8), off
-    idx = np.arange(total, dtype=np.int64) - np.repeat(off[:-1] - a, lens)
-    return np.ascontiguousarray(buf[idx]), off
+    k, seg = _ramp(lens)
+    return np.ascontiguousarray(buf[np.asarray(a, dtype=np.int64)[seg] + k]), off
 
 
+def _scatter(out, dst_start, src, src_start, lens):
+    """out[dst_start[i] + k] = src[src_start[i] + k] for k < lens[i]."""
+    if len(lens) == 0 or int(np.sum(lens)) == 0:
+        return
+    k, seg = _ramp(lens)
+    out[np.asarray(dst_start, dtype=np.int64)[seg] + k] = src[np.asarray(src_start, dtype=np.int64)[seg] + k]
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def end_windows(seq, seq_off, end_size):
     """(start windows, end windows) as two ragged batches (buf, off): window length = min(end_size, read length),
     exactly `seq[:end_size]` and `seq[-end_size:]` of nanopore_read.py:172,194."""
@@ -83,7 +170,7 @@ def end_trim_amounts(start_records, end_records, end_size, extra_trim_size, end_
     shape [n_reads, n_adapters, 9].  Returns (start_trim[n], end_trim[n]) -- the max over the adapters that pass."""
     def one(rec, is_start):
         n, a = rec.shape[0], rec.shape[1]
-        if a == 0:
+        if a == 0 or n == 0:
             return np.zeros(n, dtype=np.int64)
         _, part, rs, re_ = scores_from_records(rec.reshape(-1, 9))
         part, rs, re_ = part.reshape(n, a), rs.reshape(n, a), re_.reshape(n, a)
@@ -114,3 +201,227 @@ def trim_end_adapters(batch, start_adapters, end_adapters, scoring_scheme_vals, 
     srec, erec = run(sbuf, soff, start_adapters), run(ebuf, eoff, end_adapters)
     st, et = end_trim_amounts(srec, erec, end_size, extra_trim_size, end_threshold, min_trim_size)
     return st, et, srec, erec
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def trimmed_ranges(lens, start_trim, end_trim):
+    """[a, b) of `x[start_trim : len(x) - end_trim]` for every read, with Python's slice semantics
+    (nanopore_read.py:57-63): an end position that goes negative (end trim larger than a short read) counts from the
+    END of the read again -- the reference's behaviour, reproduced on purpose.  Untrimmed reads keep [0, len)."""
+    lens = np.asarray(lens, dtype=np.int64)
+    st, et = np.asarray(start_trim, dtype=np.int64), np.asarray(end_trim, dtype=np.int64)
+    e = lens - et
+    e = np.where(e < 0, np.maximum(e + lens, 0), e)
+    a = np.minimum(st, lens)
+    b = np.maximum(np.minimum(e, lens), a)
+    untouched = (st == 0) & (et == 0)
+    return np.where(untouched, 0, a), np.where(untouched, lens, b)
+
+
+def find_middle_hits(batch, start_trim, end_trim, adapters, middle_threshold, scoring_scheme_vals):
+    """Phase C.  adapters: list of (name, sequence) in the reference's order (porechop.py:541-548).
+    Returns {read index: [(adapter position, read_start, read_end, full_score), ...]} in the order the reference finds
+    them; coordinates are in the trimmed read.  Round 0 is one cross product over all trimmed reads; only reads with
+    a hit are masked with '-' and re-submitted (as a pair list) from the adapter that hit."""
+    n, n_ad = len(batch), len(adapters)
+    hits = {}
+    if n == 0 or n_ad == 0:
+        return hits
+    a, b = trimmed_ranges(batch.lengths(), start_trim, end_trim)
+    tbuf, toff = _gather_ranges(batch.seq, batch.seq_off[:-1] + a, batch.seq_off[:-1] + b)
+    abuf, aoff = W.pack_sequences([x[1] for x in adapters], offset_dtype=np.int32)
+    rec = W.adapter_alignment_batch(tbuf, toff, abuf, aoff, scoring_scheme_vals)
+    full, _, rs, re_ = (x.reshape(n, n_ad) for x in scores_from_records(rec))
+    hit = full >= middle_threshold                           # NaN never hits, as in the reference
+    first = hit.argmax(axis=1)
+    active = []                                              # [read, masked bytearray, adapter position]
+    for i in np.flatnonzero(hit.any(axis=1)):
+        p = int(first[i])
+        x, y = int(rs[i, p]), int(re_[i, p])
+        masked = bytearray(tbuf[toff[i]:toff[i + 1]].tobytes())
+        masked[x:y] = b'-' * (y - x)
+        hits[int(i)] = [(p, x, y, float(full[i, p]))]
+        active.append([int(i), masked, p])
+    while active:
+        sbuf, soff = W.pack_sequences([bytes(m) for _, m, _ in active], offset_dtype=np.int64)
+        ps = np.concatenate([np.full(n_ad - p, k, dtype=np.int32) for k, (_, _, p) in enumerate(active)])
+        pa = np.concatenate([np.arange(p, n_ad, dtype=np.int32) for _, _, p in active])
+        rec = W.adapter_alignment_batch(sbuf, soff, abuf, aoff, scoring_scheme_vals, ps, pa)
+        full, _, rs, re_ = scores_from_records(rec)
+        base, still = 0, []
+        for i, masked, p in active:
+            cnt = n_ad - p
+            h = np.flatnonzero(full[base:base + cnt] >= middle_threshold)
+            if len(h):
+                q = base + int(h[0])
+                x, y = int(rs[q]), int(re_[q])
+                masked[x:y] = b'-' * (y - x)
+                hits[i].append((p + int(h[0]), x, y, float(full[q])))
+                still.append([i, masked, p + int(h[0])])
+            base += cnt
+        active = still
+    return hits
+
+
+def middle_trim_ranges(hits, adapters, start_sequence_names, end_sequence_names, extra_middle_trim_good_side=10,
+                       extra_middle_trim_bad_side=100):
+    """hits of find_middle_hits -> {read index: [(trim_start, trim_end), ...]}: the ranges the reference adds to
+    `middle_trim_positions` (nanopore_read.py:231-240), in trimmed-read coordinates (may stick out of the read)."""
+    out = {}
+    for i, hs in hits.items():
+        r = []
+        for p, x, y, _ in hs:
+            name = adapters[p][0]
+            r.append((x - (extra_middle_trim_bad_side if name in start_sequence_names else extra_middle_trim_good_side),
+                      y + (extra_middle_trim_bad_side if name in end_sequence_names else extra_middle_trim_good_side)))
+        out[i] = r
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _numbered_name(name, number):
+    # add_number_to_read_name (nanopore_read.py:494-498)
+    tag = b'_' + str(number).encode()
+    return name + tag if b' ' not in name else name.replace(b' ', tag + b' ', 1)
+
+
+def _split_parts(length, ranges, min_split_read_size):
+    """runs of positions of [0, length) outside every range, at least min_split_read_size long
+    (get_split_read_parts, nanopore_read.py:76-95)."""
+    keep = np.ones(length, dtype=bool)
+    for x, y in ranges:
+        x, y = max(x, 0), min(y, length)
+        if y > x:
+            keep[x:y] = False
+    edge = np.flatnonzero(np.diff(np.concatenate([[0], keep.view(np.int8), [0]])))
+    return [(int(s), int(e)) for s, e in zip(edge[0::2], edge[1::2]) if e - s >= min_split_read_size]
+
+
+def emit(batch, start_trim=None, end_trim=None, middle=None, fmt='fastq', min_split_read_size=1000,
+         discard_middle=False, untrimmed=False, select=None, chunk_bytes=64 << 20):
+    """What the reference writes for these reads, in read order, as bytes: get_fastq / get_fasta of every read
+    (nanopore_read.py:97-147).  middle: {read index: [(trim_start, trim_end), ...]} from middle_trim_ranges -- a read
+    listed there is split (or dropped with discard_middle); `select` (bool[n]) keeps a subset (e.g. one barcode bin).
+    Reads whose trimmed sequence is empty are not written.  fmt: 'fastq' or 'fasta' (70 columns, misc.py:327-338)."""
+    n = len(batch)
+    lens = batch.lengths()
+    z = np.zeros(n, dtype=np.int64)
+    st = z if start_trim is None else np.asarray(start_trim, dtype=np.int64)
+    et = z if end_trim is None else np.asarray(end_trim, dtype=np.int64)
+    a, b = trimmed_ranges(lens, st, et)
+    qlens = np.diff(batch.qual_off)
+    qa, qb = trimmed_ranges(qlens, st, et)
+    middle = middle or {}
+    plain = np.ones(n, dtype=bool)
+    if middle:
+        plain[np.fromiter(middle.keys(), dtype=np.int64, count=len(middle))] = False
+    if select is not None:
+        plain &= np.asarray(select, dtype=bool)
+    # ---- output records: (read, seq [s0, s1), first quality, name [n0, n1) in `names`) ----
+    names, name_off = batch.name_buf, batch.name_off
+    idx = np.flatnonzero(plain)
+    if untrimmed:
+        r_s0, r_s1, r_q0, r_ql = z[idx], lens[idx], z[idx], qlens[idx]
+    else:
+        r_s0, r_s1, r_q0, r_ql = a[idx], b[idx], qa[idx], (qb - qa)[idx]
+    r_read, r_n0, r_n1 = idx, name_off[idx], name_off[idx + 1]
+    order_key = idx.astype(np.float64)
+    if middle and not discard_middle:
+        x_read, x_s0, x_s1, x_q0, x_name, x_key = [], [], [], [], [], []
+        nb = names.tobytes()
+        for i in sorted(middle):
+            if select is not None and not select[i]:
+                continue
+            nm = nb[name_off[i]:name_off[i + 1]]
+            parts = _split_parts(int(b[i] - a[i]), middle[i], min_split_read_size)
+            for k, (s, e) in enumerate(parts):
+                x_read.append(i)
+                x_s0.append(int(a[i]) + s)
+                x_s1.append(int(a[i]) + e)
+                x_q0.append(int(qa[i]) + s)
+                x_name.append(_numbered_name(nm, k + 1))
+                x_key.append(i + (k + 1) / (len(parts) + 1.0))
+        if x_read:
+            extra, extra_off = W.pack_sequences(x_name, offset_dtype=np.int64)
+            base = len(names)
+            names = np.concatenate([names, extra])
+            r_read = np.concatenate([r_read, np.array(x_read, dtype=np.int64)])
+            r_s0 = np.concatenate([r_s0, np.array(x_s0, dtype=np.int64)])
+            r_s1 = np.concatenate([r_s1, np.array(x_s1, dtype=np.int64)])
+            r_q0 = np.concatenate([r_q0, np.array(x_q0, dtype=np.int64)])
+            r_ql = np.concatenate([r_ql, np.array(x_s1, dtype=np.int64) - np.array(x_s0, dtype=np.int64)])
+            r_n0 = np.concatenate([r_n0, base + extra_off[:-1]])
+            r_n1 = np.concatenate([r_n1, base + extra_off[1:]])
+            order_key = np.concatenate([order_key, np.array(x_key)])
+    keep = r_s1 > r_s0                                        # "Don't return empty sequences"
+    o = np.argsort(order_key[keep], kind='stable')
+    r_read, r_s0, r_s1, r_q0, r_ql, r_n0, r_n1 = (v[keep][o] for v in (r_read, r_s0, r_s1, r_q0, r_ql, r_n0, r_n1))
+    # ---- assemble, a bounded number of output bytes at a time ----
+    slen, nlen = r_s1 - r_s0, r_n1 - r_n0
+    if fmt == 'fastq':
+        rec_len = 1 + nlen + 1 + slen + 3 + r_ql + 1
+    elif fmt == 'fasta':
+        rec_len = 1 + nlen + 1 + slen + (slen + 69) // 70
+    else:
+        raise ValueError("fmt must be 'fastq' or 'fasta'")
+    pieces, lo = [], 0
+    csum = np.cumsum(rec_len)
+    while lo < len(rec_len):
+        hi = int(np.searchsorted(csum, (csum[lo - 1] if lo else 0) + chunk_bytes, side='right'))
+        hi = max(hi, lo + 1)
+        sl = slice(lo, hi)
+        pieces.append(_assemble(batch, names, fmt, r_read[sl], r_s0[sl], slen[sl], r_q0[sl], r_ql[sl], r_n0[sl], nlen[sl],
+                                rec_len[sl]))
+        lo = hi
+    return b''.join(pieces)
+
+
+def _assemble(batch, names, fmt, read, s0, slen, q0, qlen, n0, nlen, rec_len):
+    off = np.zeros(len(rec_len) + 1, dtype=np.int64)
+    np.cumsum(rec_len, out=off[1:])
+    out = np.full(int(off[-1]), 10, dtype=np.uint8)              # every byte not written below is a '\n'
+    p = off[:-1]
+    out[p] = ord('@') if fmt == 'fastq' else ord('>')
+    _scatter(out, p + 1, names, n0, nlen)
+    sp = p + 1 + nlen + 1                                       # first base
+    src0 = batch.seq_off[read] + s0
+    k, seg = _ramp(slen)
+    vals = batch.seq[src0[seg] + k]
+    if batch.rna[read].any():                                   # RNA reads go back out as U (nanopore_read.py:107,133)
+        vals = np.where(batch.rna[read][seg] & (vals == ord('T')), ord('U'), vals).astype(np.uint8)
+    if fmt == 'fastq':
+        out[sp[seg] + k] = vals
+        out[sp + slen + 1] = ord('+')
+        _scatter(out, sp + slen + 3, batch.qual, batch.qual_off[read] + q0, qlen)
+    else:
+        out[sp[seg] + k + k // 70] = vals                       # a '\n' after every 70 bases and after the last one
+    return out.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def trim_fastq(data, matching_sets, scoring_scheme_vals, end_size=150, extra_end_trim=2, end_threshold=75.0,
+               min_trim_size=4, no_split=False, middle_threshold=85.0, extra_middle_trim_good_side=10,
+               extra_middle_trim_bad_side=100, min_split_read_size=1000, discard_middle=False, fmt='fastq'):
+    """FASTQ bytes -> the bytes `porechop -i in.fastq -o out.<fmt>` writes once Phase A has chosen `matching_sets`
+    (porechop.py:54-79).  matching_sets: list of (start, end) with start / end = (name, sequence) or None -- the
+    `start_sequence` / `end_sequence` of the reference's Adapter objects (adapters.py:18-30).
+    Returns (output bytes, info dict with the per-read decisions)."""
+    batch = parse_fastq(data)
+    starts = [s[0][1] for s in matching_sets if s[0]]
+    ends = [s[1][1] for s in matching_sets if s[1]]
+    st, et, _, _ = trim_end_adapters(batch, starts, ends, scoring_scheme_vals, end_size, extra_end_trim, end_threshold,
+                                     min_trim_size)
+    middle = {}
+    if not no_split:
+        adapters = []
+        for s, e in matching_sets:                              # porechop.py:541-548
+            if s:
+                adapters.append(tuple(s))
+            if e and ((not s) or e[1] != s[1]):
+                adapters.append(tuple(e))
+        hits = find_middle_hits(batch, st, et, adapters, middle_threshold, scoring_scheme_vals)
+        middle = middle_trim_ranges(hits, adapters, {s[0][0] for s in matching_sets if s[0]},
+                                    {s[1][0] for s in matching_sets if s[1]}, extra_middle_trim_good_side,
+                                    extra_middle_trim_bad_side)
+    out = emit(batch, st, et, middle, fmt, min_split_read_size, discard_middle)
+    return out, {'start_trim': st, 'end_trim': et, 'middle': middle, 'n_reads': len(batch)}
