@@ -20,6 +20,9 @@ buffers end to end:
                              --min_split_read_size, RNA T->U) as one bytes object, assembled with vectorised scatters
   trim_fastq(...)            all of the above for a fixed list of adapter sets: what `porechop -i x.fastq -o y.fastq`
                              writes once Phase A has chosen the sets
+  call_barcodes(...)         determine_barcode (nanopore_read.py:399-470) on score matrices: best / second-best
+                             with the reference's tie order, threshold, difference, --require_two_barcodes
+  demux_fastq(...)           `porechop -i x.fastq -b dir`: trim + barcode call + one output per bin
 
 The alignment engine is case-insensitive and maps U to T itself (Dna5 table); normalising at parse time only matters
 because the reference writes the normalised bases back out.
@@ -399,6 +402,42 @@ def _assemble(batch, names, fmt, read, s0, slen, q0, qlen, n0, nlen, rec_len):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def _norm_sets(matching_sets):
+    """adapter sets as (name, start, end) with start / end = (name, sequence) or None; (start, end) pairs get name ''."""
+    out = []
+    for t in matching_sets:
+        name, s, e = t if len(t) == 3 else ('', t[0], t[1])
+        out.append((name, tuple(s) if s else None, tuple(e) if e else None))
+    return out
+
+
+def _middle_adapters(sets):
+    adapters = []
+    for _, s, e in sets:                                        # porechop.py:541-548
+        if s:
+            adapters.append(s)
+        if e and ((not s) or e[1] != s[1]):
+            adapters.append(e)
+    return adapters
+
+
+def _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim, end_threshold, min_trim_size, no_split,
+              middle_threshold, good_side, bad_side):
+    batch = parse_fastq(data)
+    sets = _norm_sets(matching_sets)
+    starts = [s[1] for _, s, _ in sets if s]
+    ends = [e[1] for _, _, e in sets if e]
+    st, et, srec, erec = trim_end_adapters(batch, starts, ends, scoring_scheme_vals, end_size, extra_end_trim,
+                                           end_threshold, min_trim_size)
+    middle = {}
+    if not no_split:
+        adapters = _middle_adapters(sets)
+        hits = find_middle_hits(batch, st, et, adapters, middle_threshold, scoring_scheme_vals)
+        middle = middle_trim_ranges(hits, adapters, {s[0] for _, s, _ in sets if s}, {e[0] for _, _, e in sets if e},
+                                    good_side, bad_side)
+    return batch, sets, st, et, srec, erec, middle
+
+
 def trim_fastq(data, matching_sets, scoring_scheme_vals, end_size=150, extra_end_trim=2, end_threshold=75.0,
                min_trim_size=4, no_split=False, middle_threshold=85.0, extra_middle_trim_good_side=10,
                extra_middle_trim_bad_side=100, min_split_read_size=1000, discard_middle=False, fmt='fastq'):
@@ -406,22 +445,111 @@ def trim_fastq(data, matching_sets, scoring_scheme_vals, end_size=150, extra_end
     (porechop.py:54-79).  matching_sets: list of (start, end) with start / end = (name, sequence) or None -- the
     `start_sequence` / `end_sequence` of the reference's Adapter objects (adapters.py:18-30).
     Returns (output bytes, info dict with the per-read decisions)."""
-    batch = parse_fastq(data)
-    starts = [s[0][1] for s in matching_sets if s[0]]
-    ends = [s[1][1] for s in matching_sets if s[1]]
-    st, et, _, _ = trim_end_adapters(batch, starts, ends, scoring_scheme_vals, end_size, extra_end_trim, end_threshold,
-                                     min_trim_size)
-    middle = {}
-    if not no_split:
-        adapters = []
-        for s, e in matching_sets:                              # porechop.py:541-548
-            if s:
-                adapters.append(tuple(s))
-            if e and ((not s) or e[1] != s[1]):
-                adapters.append(tuple(e))
-        hits = find_middle_hits(batch, st, et, adapters, middle_threshold, scoring_scheme_vals)
-        middle = middle_trim_ranges(hits, adapters, {s[0][0] for s in matching_sets if s[0]},
-                                    {s[1][0] for s in matching_sets if s[1]}, extra_middle_trim_good_side,
-                                    extra_middle_trim_bad_side)
+    batch, _, st, et, _, _, middle = _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim,
+                                               end_threshold, min_trim_size, no_split, middle_threshold,
+                                               extra_middle_trim_good_side, extra_middle_trim_bad_side)
     out = emit(batch, st, et, middle, fmt, min_split_read_size, discard_middle)
     return out, {'start_trim': st, 'end_trim': et, 'middle': middle, 'n_reads': len(batch)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _barcode_name(name, start, end):
+    # Adapter.get_barcode_name (adapters.py:40-52): the shortest of the set / start / end names (first on ties)
+    names = [name] + ([start[0]] if start else []) + ([end[0]] if end else [])
+    return sorted(names, key=len)[0].replace(' ', '_')
+
+
+def _dict_columns(names):
+    """the reference keeps barcode scores in a dict keyed by barcode name (nanopore_read.py:181-183): a repeated name
+    keeps its FIRST position and its LAST value.  Returns (unique names in insertion order, column holding the value)."""
+    last = {}
+    for j, nm in enumerate(names):
+        last[nm] = j
+    return list(last.keys()), [last[nm] for nm in last]
+
+
+def call_barcodes(start_scores, start_names, end_scores, end_names, barcode_threshold=75.0, barcode_diff=5.0,
+                  require_two_barcodes=False, albacore_calls=None):
+    """determine_barcode (nanopore_read.py:399-470) for all reads at once.  start_scores: float[n, len(start_names)]
+    = full-adapter identity of every read's start window against the barcode start sequences, columns in adapter
+    order (ties go to the earlier column, as Python's stable reverse sort does); same for the end.  Returns a list of
+    barcode names ('none' = unclassified)."""
+    start_scores, end_scores = np.asarray(start_scores, dtype=np.float64), np.asarray(end_scores, dtype=np.float64)
+    n = start_scores.shape[0] if start_scores.ndim == 2 else end_scores.shape[0]
+    s_names, s_cols = _dict_columns(start_names)
+    e_names, e_cols = _dict_columns(end_names)
+    S = start_scores[:, s_cols] if s_cols else np.zeros((n, 0))
+    E = end_scores[:, e_cols] if e_cols else np.zeros((n, 0))
+
+    def best_two(M, ids):
+        """(best column, best score, second score) per row; second = best score among columns with another id."""
+        if M.shape[1] == 0:
+            return np.full(n, -1), np.zeros(n), np.zeros(n)
+        bcol = M.argmax(axis=1)
+        bscore = M[np.arange(n), bcol]
+        other = np.where(ids[None, :] == ids[bcol][:, None], -np.inf, M)
+        sscore = other.max(axis=1) if M.shape[1] > 1 else np.full(n, -np.inf)
+        return bcol, bscore, np.where(np.isfinite(sscore), sscore, 0.0)      # ('none', 0.0) when there is no second
+
+    if require_two_barcodes:
+        sc, sb, ss = best_two(S, np.arange(len(s_names)))
+        ec, eb, es = best_two(E, np.arange(len(e_names)))
+        sn = np.array(s_names + ['none'], dtype=object)[sc]
+        en = np.array(e_names + ['none'], dtype=object)[ec]
+        ok = (sb >= barcode_threshold) & (eb >= barcode_threshold) & (sb >= ss + barcode_diff) & \
+             (eb >= es + barcode_diff) & (sn == en)
+        calls = np.where(ok, sn, 'none')
+    else:
+        all_names = list(dict.fromkeys(s_names + e_names))
+        ids = np.array([all_names.index(nm) for nm in s_names + e_names], dtype=np.int64)
+        C = np.concatenate([S, E], axis=1)
+        bc, bb, bs = best_two(C, ids)
+        best_id = ids[bc] if len(ids) else np.full(n, -1)           # -1 -> 'none' (no barcode column at all)
+        bn = np.array(all_names + ['none'], dtype=object)[best_id]
+        ok = (bb >= barcode_threshold) & (bb >= bs + barcode_diff)
+        calls = np.where(ok, bn, 'none')
+    calls = [str(c) for c in calls]
+    if albacore_calls is not None:                            # Porechop and Albacore must agree (nanopore_read.py:466-470)
+        calls = [c if (a is None or a == c) else 'none' for c, a in zip(calls, albacore_calls)]
+    return calls
+
+
+def demux_fastq(data, matching_sets, scoring_scheme_vals, forward_or_reverse='forward', end_size=150, extra_end_trim=2,
+                end_threshold=75.0, min_trim_size=4, no_split=False, middle_threshold=85.0,
+                extra_middle_trim_good_side=10, extra_middle_trim_bad_side=100, min_split_read_size=1000,
+                discard_middle=False, barcode_threshold=75.0, barcode_diff=5.0, require_two_barcodes=False,
+                discard_unassigned=False, untrimmed=False, fmt='fastq', albacore_calls=None):
+    """FASTQ bytes -> {bin name: bytes}: what `porechop -i in.fastq -b dir` writes into dir/<bin>.<fmt>
+    (porechop.py:54-79, 652-676) once Phase A has chosen `matching_sets` = [(set name, start, end), ...] and the
+    barcode direction.  A set is a barcode if its name starts with 'Barcode ' (adapters.py:31-32); its direction is
+    'reverse' if its start name contains '_rev' (adapters.py:34-38).  Returns (bins, info)."""
+    batch, sets, st, et, srec, erec, middle = _run_trim(data, matching_sets, scoring_scheme_vals, end_size,
+                                                        extra_end_trim, end_threshold, min_trim_size, no_split,
+                                                        middle_threshold, extra_middle_trim_good_side,
+                                                        extra_middle_trim_bad_side)
+    n = len(batch)
+
+    def is_bc(name, s):
+        return name.startswith('Barcode ') and (('reverse' if '_rev' in s[0] else 'forward') == forward_or_reverse)
+    s_sets = [t for t in sets if t[1]]
+    e_sets = [t for t in sets if t[2]]
+    s_cols = [j for j, (name, s, e) in enumerate(s_sets) if is_bc(name, s)]
+    e_cols = [j for j, (name, s, e) in enumerate(e_sets) if is_bc(name, s)]
+
+    def full(rec, cols):
+        if n == 0 or not cols:
+            return np.zeros((n, len(cols)))
+        f, _, _, _ = scores_from_records(rec[:, cols, :].reshape(-1, 9))
+        return f.reshape(n, len(cols))
+    calls = call_barcodes(full(srec, s_cols), [_barcode_name(*s_sets[j]) for j in s_cols],
+                          full(erec, e_cols), [_barcode_name(*e_sets[j]) for j in e_cols],
+                          barcode_threshold, barcode_diff, require_two_barcodes, albacore_calls)
+    calls_arr = np.array(calls, dtype=object)
+    bins = {}
+    for name in dict.fromkeys(calls):
+        if discard_unassigned and name == 'none':
+            continue
+        out = emit(batch, st, et, middle, fmt, min_split_read_size, discard_middle, untrimmed, select=(calls_arr == name))
+        if out:
+            bins[name] = out
+    return bins, {'start_trim': st, 'end_trim': et, 'middle': middle, 'calls': calls, 'n_reads': n}

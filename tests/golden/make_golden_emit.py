@@ -101,6 +101,80 @@ def make_fastq(seed=20260923):
     return ''.join(recs)
 
 
+def make_barcoded_fastq(seed=20260924):
+    """native-barcoding style reads (NBxx_start ... NBxx_end, sequences from tests/golden/adapters.json): clean and
+    noisy pairs, start-only / end-only, mismatched start/end barcodes, a near-tie between two barcodes, a chimera."""
+    rng = random.Random(seed)
+    full = {d['name']: d for d in json.load(open(os.path.join(HERE, 'adapters.json')))['full_barcode_sets']}
+    nb = {k: full['Native barcoding %d (full sequence)' % k] for k in (1, 2, 3, 4, 5)}
+    recs = []
+
+    def rand(n):
+        return ''.join(rng.choice('ACGT') for _ in range(n))
+
+    def add(name, seq):
+        q = ''.join(chr(rng.randint(35, 73)) for _ in range(len(seq)))
+        recs.append('@' + name + '\n' + seq + '\n+\n' + q + '\n')
+
+    for k in (1, 2, 3):
+        for j in range(3):
+            p = 0.0 if j == 0 else 0.06 * j
+            add('bc%d_pair_%d' % (k, j), mutate(rng, nb[k]['start'][1], p) + rand(rng.randint(400, 1500)) +
+                mutate(rng, nb[k]['end'][1], p))
+    add('bc4_start_only', nb[4]['start'][1] + rand(700))
+    add('bc4_end_only lonely', rand(650) + nb[4]['end'][1])
+    add('mismatch_1_start_2_end', nb[1]['start'][1] + rand(900) + nb[2]['end'][1])
+    add('mismatch_noisy', mutate(rng, nb[3]['start'][1], 0.1) + rand(500) + mutate(rng, nb[1]['end'][1], 0.1))
+    half = nb[2]['start'][1][:44] + nb[3]['start'][1][44:]
+    add('near_tie', half + rand(800))
+    add('no_barcode', rand(1000))
+    add('very_noisy', mutate(rng, nb[2]['start'][1], 0.25) + rand(600) + mutate(rng, nb[2]['end'][1], 0.25))
+    add('chimera_bc', nb[1]['start'][1] + rand(1200) + nb[1]['end'][1] + nb[1]['start'][1] + rand(1300) + nb[1]['end'][1])
+    add('short_bc', nb[5]['start'][1][10:] + rand(30))
+    return ''.join(recs)
+
+
+BARCODE_CASES = [
+    ('bins_default', 'fastq', []),
+    ('bins_two_barcodes', 'fastq', ['--require_two_barcodes', '--min_split_read_size', '100']),
+    ('bins_loose_discard', 'fastq', ['--discard_unassigned', '--barcode_diff', '1', '--barcode_threshold', '60',
+                                      '--discard_middle']),
+    ('bins_fasta_untrimmed', 'fasta', ['--untrimmed', '--format', 'fasta']),
+]
+
+
+def run_barcode_case(fastq_path, fmt, extra):
+    for a in A.ADAPTERS:
+        a.best_start_score, a.best_end_score = 0.0, 0.0
+    captured = {}
+    orig = P.find_adapters_at_read_ends
+
+    def spy(reads, matching_sets, *args, **kwargs):
+        captured['sets'] = [[s.name, list(s.start_sequence) if s.start_sequence else None,
+                             list(s.end_sequence) if s.end_sequence else None] for s in matching_sets]
+        captured['direction'] = args[-1]
+        return orig(reads, matching_sets, *args, **kwargs)
+    P.find_adapters_at_read_ends = spy
+    with tempfile.TemporaryDirectory() as d:
+        old = sys.argv
+        sys.argv = ['porechop', '-i', fastq_path, '-b', os.path.join(d, 'bins'), '-v', '0', '-t', '1'] + extra
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                P.main()
+            args = P.get_arguments()
+        finally:
+            sys.argv = old
+            P.find_adapters_at_read_ends = orig
+        bins = {f: open(os.path.join(d, 'bins', f)).read() for f in sorted(os.listdir(os.path.join(d, 'bins')))}
+    opts = {k: getattr(args, k) for k in ('end_size', 'extra_end_trim', 'end_threshold', 'min_trim_size', 'no_split',
+                                          'middle_threshold', 'extra_middle_trim_good_side', 'extra_middle_trim_bad_side',
+                                          'min_split_read_size', 'discard_middle', 'barcode_threshold', 'barcode_diff',
+                                          'require_two_barcodes', 'discard_unassigned', 'untrimmed')}
+    opts['fmt'] = fmt
+    opts['forward_or_reverse'] = captured['direction']
+    return {'matching_sets': captured['sets'], 'options': opts, 'scoring': list(args.scoring_scheme_vals), 'bins': bins}
+
+
 CASES = [
     ('default', 'o.fastq', []),
     ('small_parts', 'o.fastq', ['--min_split_read_size', '50', '--extra_end_trim', '5', '--middle_threshold', '80']),
@@ -148,7 +222,16 @@ def main():
         with open(p, 'w', newline='') as f:
             f.write(fq)
         cases = {name: run_case(p, out_name, extra) for name, out_name, extra in CASES}
-    json.dump({'input_fastq': fq, 'cases': cases}, open(os.path.join(HERE, 'golden_emit.json'), 'w'), indent=0)
+    bq = make_barcoded_fastq()
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, 'in.fastq')
+        with open(p, 'w', newline='') as f:
+            f.write(bq)
+        bcases = {name: run_barcode_case(p, fmt, extra) for name, fmt, extra in BARCODE_CASES}
+    json.dump({'input_fastq': fq, 'cases': cases, 'barcoded_fastq': bq, 'barcode_cases': bcases},
+              open(os.path.join(HERE, 'golden_emit.json'), 'w'), indent=0)
+    for k, c in bcases.items():
+        print(k, c['options']['forward_or_reverse'], len(c['matching_sets']), {f: len(t) for f, t in c['bins'].items()})
     for k, c in cases.items():
         print(k, len(c['output']), [s[0][0] if s[0] else s[1][0] for s in c['matching_sets']])
 

@@ -43,30 +43,76 @@ def test_trim_fastq_matches_reference_cli_gpu(case_name):
     _run(case_name)
 
 
-def test_trimmed_ranges_are_python_slices():
-    from porechop_b200.fastq import trimmed_ranges
-    rng = np.random.default_rng(5)
-    lens = rng.integers(0, 200, 500)
-    st = rng.integers(0, 160, 500) * (rng.random(500) < 0.7)
-    et = rng.integers(0, 160, 500) * (rng.random(500) < 0.7)
-    a, b = trimmed_ranges(lens, st, et)
-    for L, s, e, x, y in zip(lens, st, et, a, b):
-        ref = list(range(L)) if (not s and not e) else list(range(L))[s:L - e]
-        assert list(range(L))[x:y] == ref
+BARCODE_CASES = ['bins_default', 'bins_two_barcodes', 'bins_loose_discard', 'bins_fasta_untrimmed']
 
 
-def test_emit_chunking_and_select(monkeypatch):
-    """tiny chunk size (several assemble calls) and a bin selection give the same bytes as one pass / a filtered pass."""
-    from porechop_b200 import fastq
-    _oracle_engine(monkeypatch)
+def _run_demux(case_name):
+    from porechop_b200.fastq import demux_fastq
     g = load_golden('golden_emit.json')
-    b = fastq.parse_fastq(g['input_fastq'].encode())
-    st = np.arange(len(b)) % 7
-    et = np.arange(len(b)) % 5
-    whole = fastq.emit(b, st, et)
-    assert fastq.emit(b, st, et, chunk_bytes=300) == whole
-    sel = np.arange(len(b)) % 2 == 0
-    parts = [fastq.emit(b, st, et, select=(np.arange(len(b)) == i)) for i in range(len(b))]
-    assert b''.join(parts) == whole
-    assert fastq.emit(b, st, et, select=sel) == b''.join(p for i, p in enumerate(parts) if sel[i])
-    assert fastq.emit(b, untrimmed=True, fmt='fasta').count(b'>') == len(b) - 1      # the empty read is not written
+    c = g['barcode_cases'][case_name]
+    bins, info = demux_fastq(g['barcoded_fastq'].encode(), c['matching_sets'], c['scoring'], **c['options'])
+    fmt = c['options']['fmt']
+    assert sorted(k + '.' + fmt for k in bins) == sorted(c['bins'])
+    for k, v in bins.items():
+        assert v.decode() == c['bins'][k + '.' + fmt], k
+    return info
+
+
+@pytest.mark.parametrize('case_name', BARCODE_CASES)
+def test_demux_fastq_matches_reference_cli_oracle_engine(monkeypatch, case_name):
+    """`porechop -b dir`: every bin file of the reference CLI, byte for byte (barcode calls incl. --require_two_barcodes,
+    thresholds, --discard_unassigned, --untrimmed)."""
+    _oracle_engine(monkeypatch)
+    info = _run_demux(case_name)
+    assert len(info['calls']) == info['n_reads'] == 18
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case_name', BARCODE_CASES)
+def test_demux_fastq_matches_reference_cli_gpu(case_name):
+    _run_demux(case_name)
+
+
+def _call_one(start_items, end_items, thr, diff, two):
+    """scalar restatement of the reference's rule (nanopore_read.py:399-470) on (name, score) lists: the checker."""
+    sd, ed = {}, {}
+    for k, v in start_items:
+        sd[k] = v
+    for k, v in end_items:
+        ed[k] = v
+    ss = sorted(sd.items(), reverse=True, key=lambda x: x[1])
+    es = sorted(ed.items(), reverse=True, key=lambda x: x[1])
+    none = ('none', 0.0)
+    bs, b2s = (ss + [none, none])[0], (ss + [none, none])[1]
+    be, b2e = (es + [none, none])[0], (es + [none, none])[1]
+    if two:
+        ok = bs[1] >= thr and be[1] >= thr and bs[1] >= b2s[1] + diff and be[1] >= b2e[1] + diff and bs[0] == be[0]
+        return bs[0] if ok else 'none'
+    seen, merged = set(), []
+    for k, v in sorted(ss + es, reverse=True, key=lambda x: x[1]):
+        if k not in seen:
+            merged.append((k, v))
+            seen.add(k)
+    b, b2 = (merged + [none, none])[0], (merged + [none, none])[1]
+    return b[0] if (b[1] >= thr and b[1] >= b2[1] + diff) else 'none'
+
+
+def test_call_barcodes_against_scalar_rule():
+    """random score matrices from a small value set (many ties), repeated barcode names (dict semantics: first
+    position, last value), empty sides, all option combinations."""
+    from porechop_b200.fastq import call_barcodes
+    rng = np.random.default_rng(11)
+    vals = np.array([0.0, 55.0, 70.0, 75.0, 80.0, 85.0, 90.0, 100.0])
+    pool = ['BC01', 'BC02', 'BC03', 'BC04', 'BC05']
+    for trial in range(60):
+        ns, ne = int(rng.integers(0, 6)), int(rng.integers(0, 6))
+        s_names = [pool[i] for i in rng.integers(0, 5, ns)]
+        e_names = [pool[i] for i in rng.integers(0, 5, ne)]
+        S, E = vals[rng.integers(0, len(vals), (40, ns))], vals[rng.integers(0, len(vals), (40, ne))]
+        for thr, diff, two in [(75.0, 5.0, False), (75.0, 5.0, True), (60.0, 0.0, False), (85.0, 10.0, True)]:
+            got = call_barcodes(S, s_names, E, e_names, thr, diff, two)
+            want = [_call_one(list(zip(s_names, S[i])), list(zip(e_names, E[i])), thr, diff, two) for i in range(40)]
+            assert got == want, (trial, thr, diff, two)
+    assert call_barcodes(np.zeros((2, 0)), [], np.zeros((2, 0)), []) == ['none', 'none']
+    got = call_barcodes(np.array([[95.0], [95.0]]), ['BC01'], np.zeros((2, 0)), [], albacore_calls=['BC02', None])
+    assert got == ['none', 'BC01']
