@@ -1,0 +1,57 @@
+/*
+ * porechop_b200_io.h -- host-side FASTQ ingest / emit helpers (plain C, OpenMP; no CUDA, no torch types).
+ *
+ * the reference keeps every read as Python objects (porechop/misc.py:151-168 load_fastq,
+ * porechop/nanopore_read.py:23-55 NanoporeRead.__init__, :97-147 get_fasta/get_fastq).  These entry points do the same
+ * byte work on flat buffers so that 10^6-10^7 reads reach the alignment engine (include/porechop_b200.h) and leave it
+ * without per-read host objects.  Library: porechop_b200/libhostio.so (built by porechop_b200/build.py with gcc).
+ * Every function is a pure function of its arguments; buffers are caller-owned.
+ */
+#ifndef PORECHOP_B200_IO_H
+#define PORECHOP_B200_IO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBIO_OK 0
+#define PBIO_ERR_RECORDS 1   /* not a whole number of 4-line records */
+#define PBIO_ERR_HEADER 2    /* a record does not start with '@' (after stripping) */
+
+/* number of lines of buf[0..n): '\n' terminated, plus one if the last byte is not '\n' (misc.py:158 iterates lines) */
+int64_t pbioCountLines(const uint8_t *buf, int64_t n);
+
+/* line_end[k] = index of the '\n' ending line k (or n for an unterminated last line); n_lines from pbioCountLines */
+int pbioLineEnds(const uint8_t *buf, int64_t n, int64_t *line_end, int64_t n_lines);
+
+/* 4-line records (misc.py:158-166): every line stripped like str.strip(); name = header minus its first character.
+ * Writes the start and length of name / bases / qualities of each of the n_lines/4 records. */
+int pbioFastqIndex(const uint8_t *buf, int64_t n, const int64_t *line_end, int64_t n_lines,
+                   int64_t *name_a, int64_t *name_len, int64_t *seq_a, int64_t *seq_len,
+                   int64_t *qual_a, int64_t *qual_len);
+
+/* dst[dst_off[i] .. dst_off[i+1]) = src[src_a[i] .. src_a[i]+src_len[i]) followed by `fill` bytes (quality padding,
+ * nanopore_read.py:34-36); src_len may be NULL = exactly the destination length. */
+void pbioGather(uint8_t *dst, const int64_t *dst_off, const uint8_t *src, const int64_t *src_a,
+                const int64_t *src_len, int fill, int64_t n);
+
+/* NanoporeRead.__init__ (nanopore_read.py:26-31) on seq[off[i]..off[i+1]): upper-case; if count('U') > count('T')
+ * the read is RNA: rna[i] = 1 and every U becomes T. */
+void pbioNormalise(uint8_t *seq, const int64_t *off, int64_t n, uint8_t *rna);
+
+/* get_fastq / get_fasta (nanopore_read.py:97-147) of n_rec output records into out[out_off[r] .. out_off[r+1]):
+ *   fmt 0 (FASTQ): '@' name '\n' bases '\n+\n' qualities '\n'        length 1+nlen+1+slen+3+qlen+1
+ *   fmt 1 (FASTA): '>' name '\n' bases wrapped at 70 columns, every line '\n' terminated (misc.py:327-338)
+ *                                                                    length 1+nlen+1+slen+ceil(slen/70)
+ * rna[r] != 0 writes T as U (nanopore_read.py:107,133). */
+void pbioEmit(uint8_t *out, const int64_t *out_off, int64_t n_rec, int fmt,
+              const uint8_t *names, const int64_t *name_a, const int64_t *name_len,
+              const uint8_t *seq, const int64_t *seq_a, const int64_t *seq_len,
+              const uint8_t *qual, const int64_t *qual_a, const int64_t *qual_len, const uint8_t *rna);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -48,5 +48,24 @@ def build(force=False, verbose=False):
     return TARGET
 
 
+HOSTIO_TARGET = os.path.join(HERE, 'libhostio.so')
+HOSTIO_DEPS = [os.path.join(CSRC, 'hostio.c'), os.path.join(os.path.dirname(HERE), 'include', 'porechop_b200_io.h')]
+
+
+def build_hostio(force=False):
+    """libhostio.so: the host-side FASTQ ingest / emit helpers (plain C + OpenMP, gcc; no CUDA)."""
+    if not force and os.path.exists(HOSTIO_TARGET) and \
+            all(os.path.getmtime(d) <= os.path.getmtime(HOSTIO_TARGET) for d in HOSTIO_DEPS):
+        return HOSTIO_TARGET
+    base = [shutil.which('gcc') or 'gcc', '-O3', '-fPIC', '-shared', '-std=c11', '-Wall', '-Wextra', '-Wno-unknown-pragmas',
+            '-o', HOSTIO_TARGET, HOSTIO_DEPS[0]]
+    for cmd in (base[:2] + ['-fopenmp'] + base[2:], base):      # a gcc without libgomp still builds it, single-threaded
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode == 0:
+            return HOSTIO_TARGET
+    raise RuntimeError('gcc failed:\n' + ' '.join(cmd) + '\n' + r.stdout + r.stderr)
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_hostio(force='--force' in sys.argv))

@@ -1,0 +1,169 @@
+/*
+ * hostio.c -- flat-buffer FASTQ ingest / emit (include/porechop_b200_io.h).  Plain C + OpenMP, host only.
+ * Behaviour follows the reference's Python loader and writers byte for byte (file:line in the header); the numpy
+ * implementations in porechop_b200/fastq.py are the same functions in slow motion and are tested against these.
+ */
+#include "../../include/porechop_b200_io.h"
+
+#include <string.h>
+
+#define PBIO_BLOCK (1 << 20)
+
+static inline int is_ws(uint8_t c)            /* what str.strip() removes from an ASCII line */
+{
+    return c == ' ' || (c >= 9 && c <= 13);
+}
+
+static int64_t count_nl(const uint8_t *p, int64_t n)
+{
+    int64_t c = 0;
+    const uint8_t *e = p + n;
+    while (p < e) {
+        const uint8_t *q = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
+        if (!q) break;
+        ++c;
+        p = q + 1;
+    }
+    return c;
+}
+
+int64_t pbioCountLines(const uint8_t *buf, int64_t n)
+{
+    if (n <= 0) return 0;
+    int64_t blocks = (n + PBIO_BLOCK - 1) / PBIO_BLOCK, total = 0;
+#pragma omp parallel for reduction(+ : total) schedule(static)
+    for (int64_t b = 0; b < blocks; ++b) {
+        int64_t lo = b * PBIO_BLOCK, hi = lo + PBIO_BLOCK < n ? lo + PBIO_BLOCK : n;
+        total += count_nl(buf + lo, hi - lo);
+    }
+    return total + (buf[n - 1] != '\n');
+}
+
+int pbioLineEnds(const uint8_t *buf, int64_t n, int64_t *line_end, int64_t n_lines)
+{
+    /* one memchr pass (runs at memory bandwidth; the parallel work is in the per-record functions below) */
+    int64_t k = 0;
+    const uint8_t *p = buf, *e = buf + (n > 0 ? n : 0);
+    while (p < e) {
+        const uint8_t *q = (const uint8_t *)memchr(p, '\n', (size_t)(e - p));
+        if (!q) break;
+        if (k >= n_lines) return PBIO_ERR_RECORDS;
+        line_end[k++] = (int64_t)(q - buf);
+        p = q + 1;
+    }
+    if (n > 0 && buf[n - 1] != '\n') {
+        if (k >= n_lines) return PBIO_ERR_RECORDS;
+        line_end[k++] = n;
+    }
+    return k == n_lines ? PBIO_OK : PBIO_ERR_RECORDS;
+}
+
+static inline void strip(const uint8_t *buf, int64_t *a, int64_t *b)
+{
+    while (*b > *a && is_ws(buf[*b - 1])) --*b;
+    while (*a < *b && is_ws(buf[*a])) ++*a;
+}
+
+int pbioFastqIndex(const uint8_t *buf, int64_t n, const int64_t *line_end, int64_t n_lines,
+                   int64_t *name_a, int64_t *name_len, int64_t *seq_a, int64_t *seq_len,
+                   int64_t *qual_a, int64_t *qual_len)
+{
+    (void)n;
+    if (n_lines % 4 != 0) return PBIO_ERR_RECORDS;
+    int64_t n_rec = n_lines / 4;
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad)
+    for (int64_t r = 0; r < n_rec; ++r) {
+        int64_t k = 4 * r;
+        int64_t a0 = k ? line_end[k - 1] + 1 : 0, b0 = line_end[k];
+        int64_t a1 = line_end[k] + 1, b1 = line_end[k + 1];
+        int64_t a3 = line_end[k + 2] + 1, b3 = line_end[k + 3];
+        strip(buf, &a0, &b0);
+        strip(buf, &a1, &b1);
+        strip(buf, &a3, &b3);
+        if (b0 <= a0 || buf[a0] != '@') bad |= 1;
+        name_a[r] = a0 + 1;
+        name_len[r] = b0 > a0 ? b0 - a0 - 1 : 0;
+        seq_a[r] = a1;
+        seq_len[r] = b1 - a1;
+        qual_a[r] = a3;
+        qual_len[r] = b3 - a3;
+    }
+    return bad ? PBIO_ERR_HEADER : PBIO_OK;
+}
+
+void pbioGather(uint8_t *dst, const int64_t *dst_off, const uint8_t *src, const int64_t *src_a,
+                const int64_t *src_len, int fill, int64_t n)
+{
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t d = dst_off[i], len = dst_off[i + 1] - d;
+        int64_t cp = src_len ? (src_len[i] < len ? src_len[i] : len) : len;
+        if (cp < 0) cp = 0;
+        if (cp > 0) memcpy(dst + d, src + src_a[i], (size_t)cp);
+        if (len > cp) memset(dst + d + cp, fill, (size_t)(len - cp));
+    }
+}
+
+void pbioNormalise(uint8_t *seq, const int64_t *off, int64_t n, uint8_t *rna)
+{
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; ++i) {
+        uint8_t *p = seq + off[i];
+        int64_t len = off[i + 1] - off[i], n_u = 0, n_t = 0;
+        for (int64_t k = 0; k < len; ++k) {
+            uint8_t c = p[k];
+            if (c >= 'a' && c <= 'z') p[k] = c = (uint8_t)(c - 32);
+            n_u += c == 'U';
+            n_t += c == 'T';
+        }
+        rna[i] = n_u > n_t;
+        if (rna[i])
+            for (int64_t k = 0; k < len; ++k)
+                if (p[k] == 'U') p[k] = 'T';
+    }
+}
+
+static inline void copy_bases(uint8_t *d, const uint8_t *s, int64_t len, int rna)
+{
+    if (!rna) {
+        memcpy(d, s, (size_t)len);
+        return;
+    }
+    for (int64_t k = 0; k < len; ++k) d[k] = s[k] == 'T' ? 'U' : s[k];
+}
+
+void pbioEmit(uint8_t *out, const int64_t *out_off, int64_t n_rec, int fmt,
+              const uint8_t *names, const int64_t *name_a, const int64_t *name_len,
+              const uint8_t *seq, const int64_t *seq_a, const int64_t *seq_len,
+              const uint8_t *qual, const int64_t *qual_a, const int64_t *qual_len, const uint8_t *rna)
+{
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t r = 0; r < n_rec; ++r) {
+        uint8_t *p = out + out_off[r];
+        int64_t nl = name_len[r], sl = seq_len[r];
+        const uint8_t *s = seq + seq_a[r];
+        int is_rna = rna && rna[r];
+        *p++ = fmt == 0 ? '@' : '>';
+        memcpy(p, names + name_a[r], (size_t)nl);
+        p += nl;
+        *p++ = '\n';
+        if (fmt == 0) {
+            copy_bases(p, s, sl, is_rna);
+            p += sl;
+            *p++ = '\n';
+            *p++ = '+';
+            *p++ = '\n';
+            memcpy(p, qual + qual_a[r], (size_t)qual_len[r]);
+            p += qual_len[r];
+            *p++ = '\n';
+        } else {
+            for (int64_t k = 0; k < sl; k += 70) {
+                int64_t w = sl - k < 70 ? sl - k : 70;
+                copy_bases(p, s + k, w, is_rna);
+                p += w;
+                *p++ = '\n';
+            }
+        }
+    }
+}

@@ -30,6 +30,7 @@ because the reference writes the normalised bases back out.
 import numpy as np
 
 from . import cpp_function_wrappers as W
+from . import hostio
 from .align import scores_from_records
 
 _WS = np.zeros(256, dtype=bool)
@@ -80,7 +81,9 @@ def parse_fastq(data):
     Lines are stripped like the reference's loader strips them (misc.py:160-166: `line.strip()`, name = header minus
     its first character); multi-line records are not supported there either.  Qualities shorter than the bases are
     padded with '+' (nanopore_read.py:34-36)."""
-    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+    if hostio.LIB is not None:
+        return _parse_fastq_native(buf)
     if buf.size and buf[-1] != 10:
         buf = np.concatenate([buf, np.array([10], dtype=np.uint8)])
     nl = np.flatnonzero(buf == 10)
@@ -113,6 +116,16 @@ def parse_fastq(data):
     return FastqBatch(name_buf, name_off, np.ascontiguousarray(seq), seq_off, qual, qual_off, rna)
 
 
+def _parse_fastq_native(buf):
+    """parse_fastq through libhostio.so (include/porechop_b200_io.h): index the records, then parallel memcpy."""
+    name_a, name_len, seq_a, seq_len, qual_a, qual_len = hostio.fastq_index(buf)
+    name_buf, name_off = hostio.gather(buf, name_a, name_len)
+    seq, seq_off = hostio.gather(buf, seq_a, seq_len)
+    rna = hostio.normalise(seq, seq_off)
+    qual, qual_off = hostio.gather(buf, qual_a, np.maximum(qual_len, seq_len), src_len=qual_len, fill=ord('+'))
+    return FastqBatch(name_buf, name_off, seq, seq_off, qual, qual_off, rna)
+
+
 def _segment_sums(flags, off):
     c = np.zeros(len(flags) + 1, dtype=np.int64)
     np.cumsum(flags, out=c[1:])
@@ -141,6 +154,8 @@ def _ramp(lens):
 def _gather_ranges(buf, a, b):
     """concatenate buf[a[i]:b[i]] for all i -> (flat uint8, int64 offsets) without a Python loop."""
     lens = np.maximum(np.asarray(b, dtype=np.int64) - np.asarray(a, dtype=np.int64), 0)
+    if hostio.LIB is not None and buf.dtype == np.uint8 and buf.flags.c_contiguous:
+        return hostio.gather(buf, a, lens)
     off = np.zeros(len(lens) + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
     if int(off[-1]) == 0:
@@ -301,11 +316,13 @@ def _split_parts(length, ranges, min_split_read_size):
 
 
 def emit(batch, start_trim=None, end_trim=None, middle=None, fmt='fastq', min_split_read_size=1000,
-         discard_middle=False, untrimmed=False, select=None, chunk_bytes=64 << 20):
+         discard_middle=False, untrimmed=False, select=None, chunk_bytes=64 << 20, as_array=False):
     """What the reference writes for these reads, in read order, as bytes: get_fastq / get_fasta of every read
     (nanopore_read.py:97-147).  middle: {read index: [(trim_start, trim_end), ...]} from middle_trim_ranges -- a read
     listed there is split (or dropped with discard_middle); `select` (bool[n]) keeps a subset (e.g. one barcode bin).
-    Reads whose trimmed sequence is empty are not written.  fmt: 'fastq' or 'fasta' (70 columns, misc.py:327-338)."""
+    Reads whose trimmed sequence is empty are not written.  fmt: 'fastq' or 'fasta' (70 columns, misc.py:327-338).
+    as_array=True returns the uint8 array the C writer filled (file.write() takes it as is) instead of copying it
+    into a bytes object."""
     n = len(batch)
     lens = batch.lengths()
     z = np.zeros(n, dtype=np.int64)
@@ -367,6 +384,12 @@ def emit(batch, start_trim=None, end_trim=None, middle=None, fmt='fastq', min_sp
         rec_len = 1 + nlen + 1 + slen + (slen + 69) // 70
     else:
         raise ValueError("fmt must be 'fastq' or 'fasta'")
+    if hostio.LIB is not None:
+        out_off = np.zeros(len(rec_len) + 1, dtype=np.int64)
+        np.cumsum(rec_len, out=out_off[1:])
+        out = hostio.emit(out_off, fmt, np.ascontiguousarray(names), r_n0, nlen, batch.seq, batch.seq_off[r_read] + r_s0, slen,
+                          batch.qual, batch.qual_off[r_read] + r_q0, r_ql, batch.rna[r_read])
+        return out if as_array else out.tobytes()
     pieces, lo = [], 0
     csum = np.cumsum(rec_len)
     while lo < len(rec_len):
@@ -376,7 +399,8 @@ def emit(batch, start_trim=None, end_trim=None, middle=None, fmt='fastq', min_sp
         pieces.append(_assemble(batch, names, fmt, r_read[sl], r_s0[sl], slen[sl], r_q0[sl], r_ql[sl], r_n0[sl], nlen[sl],
                                 rec_len[sl]))
         lo = hi
-    return b''.join(pieces)
+    out = b''.join(pieces)
+    return np.frombuffer(out, dtype=np.uint8) if as_array else out
 
 
 def _assemble(batch, names, fmt, read, s0, slen, q0, qlen, n0, nlen, rec_len):

@@ -1,0 +1,88 @@
+"""ctypes binding of porechop_b200/libhostio.so (include/porechop_b200_io.h): flat-buffer FASTQ ingest / emit in C.
+
+`LIB` is None when the library has not been built (python -m porechop_b200.build); porechop_b200/fastq.py then uses its
+numpy implementations of the same functions (identical results, much slower on long reads).  This is host I/O only --
+the alignment engine itself has no fallback of any kind."""
+import os
+from ctypes import CDLL, c_int, c_int64, c_void_p
+
+import numpy as np
+
+_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libhostio.so')
+EXPORTED_SYMBOLS = ['pbioCountLines', 'pbioLineEnds', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit']
+
+
+def _load():
+    if not os.path.exists(_PATH) or os.environ.get('PB200_NO_HOSTIO'):
+        return None
+    lib = CDLL(_PATH)
+    lib.pbioCountLines.argtypes = [c_void_p, c_int64]
+    lib.pbioCountLines.restype = c_int64
+    lib.pbioLineEnds.argtypes = [c_void_p, c_int64, c_void_p, c_int64]
+    lib.pbioLineEnds.restype = c_int
+    lib.pbioFastqIndex.argtypes = [c_void_p, c_int64, c_void_p, c_int64] + [c_void_p] * 6
+    lib.pbioFastqIndex.restype = c_int
+    lib.pbioGather.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64]
+    lib.pbioGather.restype = None
+    lib.pbioNormalise.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
+    lib.pbioNormalise.restype = None
+    lib.pbioEmit.argtypes = [c_void_p, c_void_p, c_int64, c_int] + [c_void_p] * 10
+    lib.pbioEmit.restype = None
+    return lib
+
+
+LIB = _load()
+
+
+def _p(a):
+    return a.ctypes.data_as(c_void_p) if a is not None else None
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def fastq_index(buf):
+    """buf: contiguous uint8.  Returns (name_a, name_len, seq_a, seq_len, qual_a, qual_len) int64 arrays, or raises
+    ValueError exactly where the numpy parser does."""
+    n = len(buf)
+    n_lines = int(LIB.pbioCountLines(_p(buf), n))
+    if n_lines % 4 != 0:
+        raise ValueError('FASTQ chunk is not a whole number of 4-line records')
+    line_end = np.empty(n_lines, dtype=np.int64)
+    if LIB.pbioLineEnds(_p(buf), n, _p(line_end), n_lines) != 0:
+        raise ValueError('FASTQ chunk is not a whole number of 4-line records')
+    out = [np.empty(n_lines // 4, dtype=np.int64) for _ in range(6)]
+    rc = LIB.pbioFastqIndex(_p(buf), n, _p(line_end), n_lines, *[_p(x) for x in out])
+    if rc == 2:
+        raise ValueError('FASTQ record does not start with @')
+    if rc != 0:
+        raise ValueError('FASTQ chunk is not a whole number of 4-line records')
+    return out
+
+
+def gather(src, src_a, lens, src_len=None, fill=0):
+    """concatenate src[src_a[i] : src_a[i]+lens[i]] (short sources padded with `fill`) -> (flat uint8, int64 offsets)."""
+    lens = _i64(lens)
+    off = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    dst = np.empty(int(off[-1]), dtype=np.uint8)
+    src_a = _i64(src_a)
+    sl = _i64(src_len) if src_len is not None else None
+    LIB.pbioGather(_p(dst), _p(off), _p(src), _p(src_a), _p(sl), int(fill), len(lens))
+    return dst, off
+
+
+def normalise(seq, off):
+    rna = np.zeros(len(off) - 1, dtype=np.uint8)
+    LIB.pbioNormalise(_p(seq), _p(off), len(off) - 1, _p(rna))
+    return rna.astype(bool)
+
+
+def emit(out_off, fmt, names, name_a, name_len, seq, seq_a, seq_len, qual, qual_a, qual_len, rna):
+    out = np.empty(int(out_off[-1]), dtype=np.uint8)
+    arrs = [_i64(x) for x in (out_off, name_a, name_len, seq_a, seq_len, qual_a, qual_len)]
+    rna8 = np.ascontiguousarray(rna, dtype=np.uint8)
+    LIB.pbioEmit(_p(out), _p(arrs[0]), len(arrs[1]), 0 if fmt == 'fastq' else 1, _p(names), _p(arrs[1]), _p(arrs[2]),
+                 _p(seq), _p(arrs[3]), _p(arrs[4]), _p(qual), _p(arrs[5]), _p(arrs[6]), _p(rna8))
+    return out

@@ -41,4 +41,5 @@ def built():
         subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-Wno-unknown-pragmas', '-o', emu_so, emu_src])
     from porechop_b200 import build
     build.build()
+    build.build_hostio()
     return True

@@ -10,8 +10,8 @@ import pytest
 from helpers import ROOT, load_golden, oracle_record
 
 
-def header_functions():
-    src = open(os.path.join(ROOT, 'include', 'porechop_b200.h')).read()
+def header_functions(header='porechop_b200.h'):
+    src = open(os.path.join(ROOT, 'include', header)).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
     return sorted(set(re.findall(r'\b([A-Za-z_][A-Za-z0-9_]*)\s*\(', src)) - {'defined'})
 
@@ -24,6 +24,15 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), 'missing export ' + n
     assert sorted(W.EXPORTED_SYMBOLS) == names
+
+
+def test_hostio_library_exports_every_declared_symbol():
+    from porechop_b200 import hostio
+    names = header_functions('porechop_b200_io.h')
+    lib = ctypes.CDLL(hostio._PATH)
+    for n in names:
+        assert hasattr(lib, n), 'missing export ' + n
+    assert sorted(hostio.EXPORTED_SYMBOLS) == names
 
 
 def test_format_record_matches_reference_strings():

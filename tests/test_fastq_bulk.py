@@ -69,3 +69,49 @@ def test_bulk_end_trim_with_oracle_engine(monkeypatch, case_index):
 @pytest.mark.parametrize('case_index', [0, 2, 3])
 def test_bulk_end_trim_gpu(case_index):
     _check_case(case_index)
+
+
+def _messy_fastq(seed, n):
+    rng = np.random.default_rng(seed)
+    recs = []
+    for i in range(n):
+        L = int(rng.integers(0, 400))
+        alphabet = 'ACGTacgtUuNn' if i % 5 == 0 else 'ACGT'
+        seq = ''.join(rng.choice(list(alphabet), L))
+        ql = L if i % 7 else max(0, L - int(rng.integers(0, 20)))
+        qual = ''.join(chr(c) for c in rng.integers(33, 74, ql))
+        nl = '\r\n' if i % 11 == 0 else '\n'
+        pad = ' \t' if i % 13 == 0 else ''
+        recs.append('@r%d%s%s%s%s%s%s+%s%s%s' % (i, ' desc x' if i % 3 == 0 else '', pad, nl, seq, pad, nl, nl, qual, nl))
+    text = ''.join(recs)
+    return text[:-1] if seed % 2 else text            # odd seeds: no newline at the end of the file
+
+
+@pytest.mark.parametrize('seed', [1, 2, 3])
+def test_native_hostio_equals_numpy_implementation(monkeypatch, seed):
+    """libhostio.so (C) and the numpy implementations of parse / window gather / emit give identical buffers on messy
+    input: CRLF, blanks, lower case, RNA reads, short qualities, empty reads, missing final newline."""
+    from porechop_b200 import fastq, hostio
+    assert hostio.LIB is not None, 'libhostio.so not built (python -m porechop_b200.build)'
+    data = _messy_fastq(seed, 300).encode()
+    native = fastq.parse_fastq(data)
+    rng = np.random.default_rng(seed)
+    st, et = rng.integers(0, 60, len(native)) * (rng.random(len(native)) < 0.6), rng.integers(0, 160, len(native)) * (rng.random(len(native)) < 0.6)
+    middle = {int(i): [(int(a), int(a) + 30)] for i, a in zip(rng.choice(len(native), 40, replace=False), rng.integers(-10, 200, 40))}
+    outs = [fastq.emit(native, st, et, middle, fmt, 20) for fmt in ('fastq', 'fasta')]
+    wins = fastq.end_windows(native.seq, native.seq_off, 150)
+    arr = fastq.emit(native, st, et, middle, 'fastq', 20, as_array=True)
+    assert isinstance(arr, np.ndarray) and arr.tobytes() == outs[0]
+    monkeypatch.setattr(hostio, 'LIB', None)
+    slow = fastq.parse_fastq(data)
+    assert slow.names == native.names and (slow.rna == native.rna).all() and native.rna.any()
+    for k in ('seq', 'seq_off', 'qual', 'qual_off', 'name_buf', 'name_off'):
+        assert np.array_equal(getattr(slow, k), getattr(native, k)), k
+    assert [fastq.emit(slow, st, et, middle, fmt, 20) for fmt in ('fastq', 'fasta')] == outs
+    for (a, ao), (b, bo) in zip(wins, fastq.end_windows(slow.seq, slow.seq_off, 150)):
+        assert np.array_equal(a, b) and np.array_equal(ao, bo)
+    for bad in (b'@x\nACGT\n+\n', b'xx\nAC\n+\nII\n'):
+        for lib in (None, hostio._load()):
+            monkeypatch.setattr(hostio, 'LIB', lib)
+            with pytest.raises(ValueError):
+                fastq.parse_fastq(bad)
