@@ -18,6 +18,7 @@ buffers end to end:
   middle_trim_ranges(...)    hits -> the ranges the reference adds to `middle_trim_positions`
   emit(...)                  get_fastq / get_fasta of every read (split parts, numbering, --discard_middle,
                              --min_split_read_size, RNA T->U) as one bytes object, assembled with vectorised scatters
+  search_adapter_sets(...)   Phase A: best start / end identity of every adapter set over the check reads' windows
   trim_fastq(...)            all of the above for a fixed list of adapter sets: what `porechop -i x.fastq -o y.fastq`
                              writes once Phase A has chosen the sets
   call_barcodes(...)         determine_barcode (nanopore_read.py:399-470) on score matrices: best / second-best
@@ -426,6 +427,28 @@ def _assemble(batch, names, fmt, read, s0, slen, q0, qlen, n0, nlen, rec_len):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def search_adapter_sets(batch, adapter_sets, scoring_scheme_vals, check_reads=10000, end_size=150):
+    """Phase A (porechop.py:286-327, nanopore_read.py:149-164) on a FastqBatch: the best full-adapter identity of every
+    set's start / end sequence over the end windows of the first `check_reads` reads.  adapter_sets as for trim_fastq.
+    Returns (best_start_score[k], best_end_score[k]) (0.0 where a set has no such sequence); the caller applies the
+    reference's policy on top (`>= adapter_threshold`, porechop.py:327; 1D^2 fix-up, barcode kit choice)."""
+    sets = _norm_sets(adapter_sets)
+    k = min(int(check_reads), len(batch))
+    best_s, best_e = np.zeros(len(sets)), np.zeros(len(sets))
+    if k == 0:
+        return best_s, best_e
+    (sbuf, soff), (ebuf, eoff) = end_windows(batch.seq, batch.seq_off[:k + 1], end_size)
+    for which, buf, off, best in ((1, sbuf, soff, best_s), (2, ebuf, eoff, best_e)):
+        idx = [j for j, t in enumerate(sets) if t[which]]
+        if not idx:
+            continue
+        abuf, aoff = W.pack_sequences([sets[j][which][1] for j in idx], offset_dtype=np.int32)
+        rec = W.adapter_alignment_batch(buf, off, abuf, aoff, scoring_scheme_vals)
+        full, _, _, _ = scores_from_records(rec)
+        best[idx] = np.maximum(full.reshape(k, len(idx)).max(axis=0), 0.0)
+    return best_s, best_e
+
+
 def _norm_sets(matching_sets):
     """adapter sets as (name, start, end) with start / end = (name, sequence) or None; (start, end) pairs get name ''."""
     out = []
@@ -464,7 +487,7 @@ def _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim
 
 def trim_fastq(data, matching_sets, scoring_scheme_vals, end_size=150, extra_end_trim=2, end_threshold=75.0,
                min_trim_size=4, no_split=False, middle_threshold=85.0, extra_middle_trim_good_side=10,
-               extra_middle_trim_bad_side=100, min_split_read_size=1000, discard_middle=False, fmt='fastq'):
+               extra_middle_trim_bad_side=100, min_split_read_size=1000, discard_middle=False, fmt='fastq', as_array=False):
     """FASTQ bytes -> the bytes `porechop -i in.fastq -o out.<fmt>` writes once Phase A has chosen `matching_sets`
     (porechop.py:54-79).  matching_sets: list of (start, end) with start / end = (name, sequence) or None -- the
     `start_sequence` / `end_sequence` of the reference's Adapter objects (adapters.py:18-30).
@@ -472,7 +495,7 @@ def trim_fastq(data, matching_sets, scoring_scheme_vals, end_size=150, extra_end
     batch, _, st, et, _, _, middle = _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim,
                                                end_threshold, min_trim_size, no_split, middle_threshold,
                                                extra_middle_trim_good_side, extra_middle_trim_bad_side)
-    out = emit(batch, st, et, middle, fmt, min_split_read_size, discard_middle)
+    out = emit(batch, st, et, middle, fmt, min_split_read_size, discard_middle, as_array=as_array)
     return out, {'start_trim': st, 'end_trim': et, 'middle': middle, 'n_reads': len(batch)}
 
 
@@ -542,7 +565,7 @@ def demux_fastq(data, matching_sets, scoring_scheme_vals, forward_or_reverse='fo
                 end_threshold=75.0, min_trim_size=4, no_split=False, middle_threshold=85.0,
                 extra_middle_trim_good_side=10, extra_middle_trim_bad_side=100, min_split_read_size=1000,
                 discard_middle=False, barcode_threshold=75.0, barcode_diff=5.0, require_two_barcodes=False,
-                discard_unassigned=False, untrimmed=False, fmt='fastq', albacore_calls=None):
+                discard_unassigned=False, untrimmed=False, fmt='fastq', albacore_calls=None, as_array=False):
     """FASTQ bytes -> {bin name: bytes}: what `porechop -i in.fastq -b dir` writes into dir/<bin>.<fmt>
     (porechop.py:54-79, 652-676) once Phase A has chosen `matching_sets` = [(set name, start, end), ...] and the
     barcode direction.  A set is a barcode if its name starts with 'Barcode ' (adapters.py:31-32); its direction is
@@ -573,7 +596,8 @@ def demux_fastq(data, matching_sets, scoring_scheme_vals, forward_or_reverse='fo
     for name in dict.fromkeys(calls):
         if discard_unassigned and name == 'none':
             continue
-        out = emit(batch, st, et, middle, fmt, min_split_read_size, discard_middle, untrimmed, select=(calls_arr == name))
-        if out:
+        out = emit(batch, st, et, middle, fmt, min_split_read_size, discard_middle, untrimmed, select=(calls_arr == name),
+                   as_array=as_array)
+        if len(out):
             bins[name] = out
     return bins, {'start_trim': st, 'end_trim': et, 'middle': middle, 'calls': calls, 'n_reads': n}

@@ -55,6 +55,36 @@ def _check_case(case_index):
     assert list(et) == [r['end_trim_amount'] for r in case['reads']]
 
 
+def _check_search(case_index):
+    from porechop_b200.fastq import parse_fastq, search_adapter_sets
+    case = load_golden('golden_phases.json')[case_index]
+    ad = load_golden('adapters.json')
+    sets = [(d['name'], d['start'] or None, d['end'] or None) for d in ad['sets']]
+    b = parse_fastq(fastq_text(fixture(case['file'])))
+    bs, be = search_adapter_sets(b, sets, SC)
+    want = {nm: (s, e) for nm, s, e in case['set_scores']}
+    assert len(want) == len(sets)
+    for (nm, _, _), s, e in zip(sets, bs, be):
+        assert (s, e) == want[nm], nm
+
+
+@pytest.mark.parametrize('case_index', [0, 3])
+def test_search_adapter_sets_with_oracle_engine(monkeypatch, case_index):
+    """Phase A on flat buffers: best_start_score / best_end_score of all 119 table sets = the reference's."""
+    from porechop_b200 import fastq
+
+    def fake(seq_buf, seq_off, ad_buf, ad_off, scoring, pair_seq=None, pair_adapter=None, out=None):
+        return oracle_batch(seq_buf, seq_off, ad_buf, ad_off, scoring, pair_seq, pair_adapter)
+    monkeypatch.setattr(fastq.W, 'adapter_alignment_batch', fake)
+    _check_search(case_index)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case_index', [0, 3])
+def test_search_adapter_sets_gpu(case_index):
+    _check_search(case_index)
+
+
 @pytest.mark.parametrize('case_index', [0, 2, 3])
 def test_bulk_end_trim_with_oracle_engine(monkeypatch, case_index):
     from porechop_b200 import fastq
