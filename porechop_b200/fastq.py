@@ -470,7 +470,7 @@ def _middle_adapters(sets):
 
 def _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim, end_threshold, min_trim_size, no_split,
               middle_threshold, good_side, bad_side):
-    batch = parse_fastq(data)
+    batch = data if isinstance(data, FastqBatch) else parse_fastq(data)
     sets = _norm_sets(matching_sets)
     starts = [s[1] for _, s, _ in sets if s]
     ends = [e[1] for _, _, e in sets if e]

@@ -1,0 +1,76 @@
+"""CPU tier (authoring container only): `python -m porechop_b200.flat_cli` against the UNMODIFIED reference CLI.
+
+Both run in-process on the reference's fixture inputs and on this repo's synthetic edge-case FASTQs; every output file
+must be byte-identical (gz outputs are compared after decompression).  The flat CLI takes its argument parser, adapter
+table and policy functions from the reference package itself; only the data path differs (porechop_b200/fastq.py).
+The oracle stands in for the engine (tests only).  Skipped where /root/reference does not exist (the GPU box)."""
+import contextlib
+import gzip
+import io
+import os
+import sys
+
+import pytest
+
+from helpers import load_golden
+from test_patch_cli import REF, _oracle_engine, _run_cli, porechop_modules, pytestmark  # noqa: F401
+
+
+def _flat_cli(A, argv, out_dir):
+    from porechop_b200 import flat_cli
+    for a in A.ADAPTERS:
+        a.best_start_score, a.best_end_score = 0.0, 0.0
+    os.makedirs(out_dir, exist_ok=True)
+    old = sys.argv
+    sys.argv = ['porechop'] + argv
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            flat_cli.main()
+    finally:
+        sys.argv = old
+    files = {}
+    for d, _, names in os.walk(out_dir):
+        for nm in names:
+            files[os.path.relpath(os.path.join(d, nm), out_dir)] = open(os.path.join(d, nm), 'rb').read()
+    return files
+
+
+def _plain(files):
+    return {k: (gzip.decompress(v) if k.endswith('.gz') else v) for k, v in files.items()}
+
+
+CASES = [
+    ('one_set', 'test_one_adapter_set.fastq', ['-o', '{out}/o.fastq']),
+    ('one_set_fasta_lowmid', 'test_one_adapter_set.fastq', ['-o', '{out}/o.fasta', '--middle_threshold', '70',
+                                                            '--min_split_read_size', '10']),
+    ('two_sets', 'test_two_adapter_sets.fastq', ['-o', '{out}/o.fastq', '--discard_middle']),
+    ('barcodes', 'test_barcodes.fastq', ['-b', '{out}/bins']),
+    ('barcodes_two_untrimmed', 'test_barcodes.fastq', ['-b', '{out}/bins', '--require_two_barcodes', '--untrimmed',
+                                                       '--discard_unassigned']),
+    ('gz_in_gz_out', 'test_format.fastq.gz', ['-o', '{out}/o.fastq.gz', '--no_split']),
+    ('gz_in_bins', 'test_format_barcodes.fastq.gz', ['-b', '{out}/bins']),
+    ('synthetic_edges', 'GOLDEN:input_fastq', ['-o', '{out}/o.fastq', '--min_split_read_size', '50']),
+    ('synthetic_barcoded', 'GOLDEN:barcoded_fastq', ['-b', '{out}/bins', '--format', 'fasta']),
+]
+
+
+@pytest.mark.parametrize('name,input_name,argv', CASES, ids=[c[0] for c in CASES])
+def test_flat_cli_writes_the_reference_cli_files(name, input_name, argv, porechop_modules, monkeypatch, tmp_path):  # noqa: F811
+    porechop, P, A = porechop_modules
+    if input_name.startswith('GOLDEN:'):
+        inp = str(tmp_path / 'in.fastq')
+        with open(inp, 'w', newline='') as f:
+            f.write(load_golden('golden_emit.json')[input_name.split(':')[1]])
+    else:
+        inp = os.path.join(REF, 'test', input_name)
+
+    def args_for(out):
+        return ['-i', inp, '-v', '0', '-t', '1'] + [a.replace('{out}', out) for a in argv]
+    _, base = _run_cli(P, A, args_for(str(tmp_path / 'a')), str(tmp_path / 'a'))
+    _oracle_engine(monkeypatch)
+    monkeypatch.syspath_prepend(REF)            # flat_cli imports `porechop` like a user would (already in sys.modules)
+    got = _flat_cli(A, args_for(str(tmp_path / 'b')), str(tmp_path / 'b'))
+    base, got = _plain(base), _plain(got)
+    assert sorted(got) == sorted(base) and len(base) >= 1
+    for k in base:
+        assert got[k] == base[k], k
