@@ -9,6 +9,9 @@ decisions on arrays -> output bytes.  Output files are byte-identical to the ref
 (tests/test_flat_cli.py); the progress / verbose report is not reproduced -- use `python -m porechop_b200`
 (porechop_b200/patch.py) when that is wanted.
 
+The input is streamed in whole-record chunks (PB200_FLAT_CHUNK_BYTES, default 256 MB; the first chunk holds the check
+reads of Phase A), so memory is bounded by the chunk size, not the file size.
+
 Limits (the run exits with a message instead of guessing): input must be one FASTQ file (plain or .gz); FASTA input and
 Albacore directories go through `python -m porechop_b200`.
 """
@@ -19,17 +22,56 @@ import sys
 from . import fastq
 
 
-def _read_input(path):
+def _record_chunks(path, chunk_bytes, first_reads):
+    """Whole-record pieces of a FASTQ file (plain or .gz): the first piece holds at least `first_reads` reads (Phase A's
+    check reads, porechop.py:237), the others about chunk_bytes each, so a run's memory is bounded by the chunk size."""
     with open(path, 'rb') as f:
         magic = f.read(2)
     opener = gzip.open if magic == b'\x1f\x8b' else open
     with opener(path, 'rb') as f:
-        data = f.read()
-    # Python's text mode (misc.py:157 `open(..., 'rt')`) turns a lone '\r' into a line break as well; not supported here
-    first = data.lstrip()[:1]
-    if first != b'@':
-        sys.exit('porechop_b200.flat_cli: input is not FASTQ (FASTA / directories: use `python -m porechop_b200`)')
-    return data
+        pending, first = b'', True
+        while True:
+            block = f.read(chunk_bytes)
+            data = pending + block
+            if not block:
+                if data.strip() or first:
+                    yield data
+                return
+            if first and data.lstrip()[:1] not in (b'@', b''):
+                sys.exit('porechop_b200.flat_cli: input is not FASTQ (FASTA / directories: use `python -m porechop_b200`)')
+            cut = data.rfind(b'\n') + 1                     # drop the unterminated last line
+            n_nl = data.count(b'\n', 0, cut)
+            if first and n_nl < 4 * first_reads:
+                pending = data                              # keep reading until the check reads are all here
+                continue
+            for _ in range(n_nl % 4):                       # back to a multiple of four lines
+                cut = data.rfind(b'\n', 0, cut - 1) + 1
+            if cut == 0:
+                pending = data
+                continue
+            yield data[:cut]
+            pending, first = data[cut:], False
+
+
+class _Sink:
+    """one output stream (file, gz file or stdout), opened on first write like the reference's bin files"""
+
+    def __init__(self, path, gz):
+        self.path, self.gz, self.f = path, gz, None
+
+    def write(self, payload):
+        if not len(payload):
+            return
+        if self.f is None:
+            if self.path is None:
+                self.f = sys.stdout.buffer
+            else:   # gz: same bytes inside as the reference's `gzip -c`, different container timestamp
+                self.f = gzip.open(self.path, 'wb') if self.gz else open(self.path, 'wb')
+        self.f.write(payload)
+
+    def close(self):
+        if self.f is not None and self.path is not None:
+            self.f.close()
 
 
 def _out_format(args, read_type='fastq'):
@@ -47,15 +89,6 @@ def _out_format(args, read_type='fastq'):
     return (fmt[:-3] if fmt.endswith('.gz') else fmt), gz
 
 
-def _write(path, payload, gz):
-    if gz:
-        with gzip.open(path, 'wb') as f:        # same bytes inside as the reference's `gzip -c`, different container timestamp
-            f.write(payload)
-    else:
-        with open(path, 'wb') as f:
-            f.write(payload)
-
-
 def main():
     try:
         from porechop import porechop as P
@@ -65,7 +98,9 @@ def main():
     if os.path.isdir(args.input):
         sys.exit('porechop_b200.flat_cli: directory input is not supported (use `python -m porechop_b200`)')
     scoring = args.scoring_scheme_vals
-    batch = fastq.parse_fastq(_read_input(args.input))
+    chunk_bytes = int(os.environ.get('PB200_FLAT_CHUNK_BYTES', 256 << 20))
+    chunks = _record_chunks(args.input, chunk_bytes, args.check_reads)
+    batch = fastq.parse_fastq(next(chunks))
 
     # Phase A on flat buffers; the scores land on Porechop's own Adapter objects so that its policy code runs unchanged
     search = [a for a in P.ADAPTERS if '(full sequence)' not in a.name]                     # porechop.py:296
@@ -86,26 +121,38 @@ def main():
                   extra_middle_trim_good_side=args.extra_middle_trim_good_side,
                   extra_middle_trim_bad_side=args.extra_middle_trim_bad_side,
                   min_split_read_size=args.min_split_read_size, discard_middle=args.discard_middle, fmt=fmt, as_array=True)
+    sinks = {}
+
+    def sink(name):
+        if name not in sinks:
+            path = args.output if name is None else os.path.join(args.barcode_dir, name + '.' + fmt + ('.gz' if gz else ''))
+            sinks[name] = _Sink(path, gz)
+        return sinks[name]
     if args.barcode_dir is not None:
         os.makedirs(args.barcode_dir, exist_ok=True)
-        if sets:
-            bins, _ = fastq.demux_fastq(batch, sets, scoring, direction, barcode_threshold=args.barcode_threshold,
-                                        barcode_diff=args.barcode_diff, require_two_barcodes=args.require_two_barcodes,
-                                        discard_unassigned=args.discard_unassigned, untrimmed=args.untrimmed, **common)
+    while batch is not None:
+        if args.barcode_dir is not None:
+            if sets:
+                bins, _ = fastq.demux_fastq(batch, sets, scoring, direction, barcode_threshold=args.barcode_threshold,
+                                            barcode_diff=args.barcode_diff, require_two_barcodes=args.require_two_barcodes,
+                                            discard_unassigned=args.discard_unassigned, untrimmed=args.untrimmed, **common)
+            else:
+                out = fastq.emit(batch, fmt=fmt, untrimmed=args.untrimmed, as_array=True)
+                bins = {} if args.discard_unassigned else {'none': out}
+            for name, payload in bins.items():
+                sink(name).write(payload)
         else:
-            out = fastq.emit(batch, fmt=fmt, untrimmed=args.untrimmed, as_array=True)
-            bins = {} if (args.discard_unassigned or not len(out)) else {'none': out}
-        for name, payload in bins.items():
-            _write(os.path.join(args.barcode_dir, name + '.' + fmt + ('.gz' if gz else '')), payload, gz)
-    else:
-        if sets:
-            out, _ = fastq.trim_fastq(batch, sets, scoring, **common)
-        else:                       # "No adapters found - output reads are unchanged from input reads"
-            out = fastq.emit(batch, fmt=fmt, as_array=True)
-        if args.output is None:
-            sys.stdout.buffer.write(out)
-        else:
-            _write(args.output, out, gz)
+            if sets:
+                out, _ = fastq.trim_fastq(batch, sets, scoring, **common)
+            else:                   # "No adapters found - output reads are unchanged from input reads"
+                out = fastq.emit(batch, fmt=fmt, as_array=True)
+            sink(None).write(out)
+        nxt = next(chunks, None)
+        batch = fastq.parse_fastq(nxt) if nxt is not None else None
+    if args.barcode_dir is None and args.output is not None and None not in sinks:
+        sink(None).f = gzip.open(args.output, 'wb') if gz else open(args.output, 'wb')      # an empty result is still a file
+    for s_ in sinks.values():
+        s_.close()
     return 0
 
 

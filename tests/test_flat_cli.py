@@ -74,3 +74,13 @@ def test_flat_cli_writes_the_reference_cli_files(name, input_name, argv, porecho
     assert sorted(got) == sorted(base) and len(base) >= 1
     for k in base:
         assert got[k] == base[k], k
+
+
+@pytest.mark.parametrize('chunk', [3000, 20000])
+@pytest.mark.parametrize('input_name,argv', [('test_barcodes.fastq', ['-b', '{out}/bins', '--check_reads', '5']),
+                                             ('GOLDEN:input_fastq', ['-o', '{out}/o.fastq.gz', '--check_reads', '4',
+                                                                     '--min_split_read_size', '50'])])
+def test_flat_cli_streams_in_chunks(chunk, input_name, argv, porechop_modules, monkeypatch, tmp_path):  # noqa: F811
+    """tiny chunks (many whole-record pieces, bins appended piece by piece): same files as the reference CLI."""
+    monkeypatch.setenv('PB200_FLAT_CHUNK_BYTES', str(chunk))
+    test_flat_cli_writes_the_reference_cli_files('chunked', input_name, argv, porechop_modules, monkeypatch, tmp_path)
