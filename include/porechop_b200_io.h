@@ -26,6 +26,9 @@ int64_t pbioCountLines(const uint8_t *buf, int64_t n);
 /* line_end[k] = index of the '\n' ending line k (or n for an unterminated last line); n_lines from pbioCountLines */
 int pbioLineEnds(const uint8_t *buf, int64_t n, int64_t *line_end, int64_t n_lines);
 
+/* str.strip() of every line: span_a[k], span_len[k] = the stripped extent of line k (misc.py:139, 160-166) */
+void pbioLineSpans(const uint8_t *buf, const int64_t *line_end, int64_t n_lines, int64_t *span_a, int64_t *span_len);
+
 /* 4-line records (misc.py:158-166): every line stripped like str.strip(); name = header minus its first character.
  * Writes the start and length of name / bases / qualities of each of the n_lines/4 records. */
 int pbioFastqIndex(const uint8_t *buf, int64_t n, const int64_t *line_end, int64_t n_lines,

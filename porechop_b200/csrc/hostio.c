@@ -64,6 +64,17 @@ static inline void strip(const uint8_t *buf, int64_t *a, int64_t *b)
     while (*a < *b && is_ws(buf[*a])) ++*a;
 }
 
+void pbioLineSpans(const uint8_t *buf, const int64_t *line_end, int64_t n_lines, int64_t *span_a, int64_t *span_len)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < n_lines; ++k) {
+        int64_t a = k ? line_end[k - 1] + 1 : 0, b = line_end[k];
+        strip(buf, &a, &b);
+        span_a[k] = a;
+        span_len[k] = b - a;
+    }
+}
+
 int pbioFastqIndex(const uint8_t *buf, int64_t n, const int64_t *line_end, int64_t n_lines,
                    int64_t *name_a, int64_t *name_len, int64_t *seq_a, int64_t *seq_len,
                    int64_t *qual_a, int64_t *qual_len)

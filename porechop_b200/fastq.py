@@ -7,6 +7,7 @@ read by read (nanopore_read.py:166-243) and formats output strings read by read 
 10^6-10^7 reads that host work would hide the GPU gain, so this module keeps reads as flat numpy
 buffers end to end:
 
+  parse_fasta(data)          FASTA bytes (multi-line records) -> FastqBatch with '+' qualities
   parse_fastq(data)          4-line FASTQ bytes -> FastqBatch (flat names / bases / qualities + offsets; bases
                              upper-cased, RNA reads detected and stored as T, exactly as NanoporeRead.__init__ does)
   end_windows(...)           the `seq[:end_size]` / `seq[-end_size:]` windows of every read as one ragged batch
@@ -102,19 +103,79 @@ def parse_fastq(data):
     name_buf, name_off = _gather_ranges(buf, starts[0::4] + 1, ends[0::4])
     seq, seq_off = _gather_ranges(buf, starts[1::4], ends[1::4])
     qual, qual_off = _gather_ranges(buf, starts[3::4], ends[3::4])
-    # seq.upper(); RNA if count('U') > count('T') -> stored as T (nanopore_read.py:26-31)
-    lower = (seq >= ord('a')) & (seq <= ord('z'))
-    seq = np.where(lower, seq - 32, seq).astype(np.uint8)
-    n_u = _segment_sums(seq == ord('U'), seq_off)
-    n_t = _segment_sums(seq == ord('T'), seq_off)
-    rna = n_u > n_t
-    if rna.any():
-        is_rna_base = np.repeat(rna, np.diff(seq_off))
-        seq = np.where(is_rna_base & (seq == ord('U')), ord('T'), seq).astype(np.uint8)
+    seq, rna = _normalise(seq, seq_off)
     short = np.diff(seq_off) - np.diff(qual_off)
     if (short > 0).any():
         qual, qual_off = _pad_segments(qual, qual_off, np.maximum(short, 0), ord('+'))
-    return FastqBatch(name_buf, name_off, np.ascontiguousarray(seq), seq_off, qual, qual_off, rna)
+    return FastqBatch(name_buf, name_off, seq, seq_off, qual, qual_off, rna)
+
+
+def _line_spans(buf):
+    """stripped (start, length) of every line; lines end at '\\n' (the last one may be unterminated)."""
+    if hostio.LIB is not None:
+        return hostio.line_spans(buf)
+    if buf.size == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z.copy()
+    nl = np.flatnonzero(buf == 10)
+    if buf[-1] != 10:
+        nl = np.concatenate([nl, [len(buf)]])
+    starts = np.concatenate([[0], nl[:-1] + 1])
+    a, b = _strip(buf, starts, nl.copy())
+    return a.astype(np.int64), (b - a).astype(np.int64)
+
+
+def parse_fasta(data):
+    """FASTA bytes -> FastqBatch, following the reference's loader (misc.py:123-148: lines stripped, blank lines
+    skipped, a '>' line starts a record, sequence lines are concatenated; the read name is the whole header minus '>',
+    porechop.py:234) and NanoporeRead.__init__ (qualities of a FASTA read are '+' * len, nanopore_read.py:33-36).
+    Sequence before the first header or an empty header name is rejected here (the reference silently mangles both)."""
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data)
+    a, ln = _line_spans(buf)
+    keep = ln > 0
+    a, ln = a[keep], ln[keep]
+    z, o = np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64)
+    if len(a) == 0:
+        return FastqBatch(z, o, z, o.copy(), z, o.copy(), np.zeros(0, dtype=bool))
+    header = buf[a] == ord('>')
+    if not header[0]:
+        raise ValueError('FASTA does not start with a > line')
+    if (ln[header] < 2).any():
+        raise ValueError('FASTA record with an empty name')
+    rec = np.cumsum(header) - 1                                  # record of every kept line
+    n = int(rec[-1]) + 1
+    name_buf, name_off = _gather_ranges(buf, a[header] + 1, a[header] + ln[header])
+    body = ~header
+    seq, _ = _gather_ranges(buf, a[body], a[body] + ln[body])    # sequence lines are already in record order
+    seq_len = np.bincount(rec[body], weights=ln[body], minlength=n).astype(np.int64)
+    seq_off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(seq_len, out=seq_off[1:])
+    seq, rna = _normalise(seq, seq_off)
+    return FastqBatch(name_buf, name_off, seq, seq_off, np.full(len(seq), ord('+'), dtype=np.uint8), seq_off.copy(), rna)
+
+
+def _normalise(seq, seq_off):
+    """seq.upper(); RNA if count('U') > count('T') -> stored as T (nanopore_read.py:26-31).  Returns (seq, rna)."""
+    if hostio.LIB is not None:
+        seq = np.ascontiguousarray(seq)
+        return seq, hostio.normalise(seq, seq_off)
+    lower = (seq >= ord('a')) & (seq <= ord('z'))
+    seq = np.where(lower, seq - 32, seq).astype(np.uint8)
+    rna = _segment_sums(seq == ord('U'), seq_off) > _segment_sums(seq == ord('T'), seq_off)
+    if rna.any():
+        seq = np.where(np.repeat(rna, np.diff(seq_off)) & (seq == ord('U')), ord('T'), seq).astype(np.uint8)
+    return np.ascontiguousarray(seq), rna
+
+
+def parse_reads(data):
+    """FASTQ or FASTA by the first character of the data, like get_sequence_file_type (misc.py:84-106).
+    Returns (FastqBatch, 'fastq' | 'fasta')."""
+    head = bytes(data[:1])
+    if head == b'>':
+        return parse_fasta(data), 'fasta'
+    if head in (b'@', b''):
+        return parse_fastq(data), 'fastq'
+    raise ValueError('File is neither FASTA or FASTQ')
 
 
 def _parse_fastq_native(buf):

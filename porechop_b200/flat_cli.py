@@ -12,7 +12,7 @@ decisions on arrays -> output bytes.  Output files are byte-identical to the ref
 The input is streamed in whole-record chunks (PB200_FLAT_CHUNK_BYTES, default 256 MB; the first chunk holds the check
 reads of Phase A), so memory is bounded by the chunk size, not the file size.
 
-Limits (the run exits with a message instead of guessing): input must be one FASTQ file (plain or .gz); FASTA input and
+Limits (the run exits with a message instead of guessing): input must be one FASTQ or FASTA file (plain or .gz);
 Albacore directories go through `python -m porechop_b200`.
 """
 import gzip
@@ -23,33 +23,38 @@ from . import fastq
 
 
 def _record_chunks(path, chunk_bytes, first_reads):
-    """Whole-record pieces of a FASTQ file (plain or .gz): the first piece holds at least `first_reads` reads (Phase A's
-    check reads, porechop.py:237), the others about chunk_bytes each, so a run's memory is bounded by the chunk size."""
+    """Whole-record pieces of a FASTQ / FASTA file (plain or .gz): the first piece holds at least `first_reads` reads
+    (Phase A's check reads, porechop.py:237), the others about chunk_bytes each, so a run's memory is bounded by the
+    chunk size.  Yields (kind, bytes) with kind 'fastq' | 'fasta' from the file's first character (misc.py:84-106)."""
     with open(path, 'rb') as f:
         magic = f.read(2)
     opener = gzip.open if magic == b'\x1f\x8b' else open
     with opener(path, 'rb') as f:
-        pending, first = b'', True
+        pending, first, kind = b'', True, None
         while True:
             block = f.read(chunk_bytes)
             data = pending + block
+            if kind is None:
+                kind = {b'>': 'fasta', b'@': 'fastq', b'': 'fastq'}.get(data[:1])
+                if kind is None:
+                    sys.exit('porechop_b200.flat_cli: ' + path + ' is neither FASTA nor FASTQ')
             if not block:
                 if data.strip() or first:
-                    yield data
+                    yield kind, data
                 return
-            if first and data.lstrip()[:1] not in (b'@', b''):
-                sys.exit('porechop_b200.flat_cli: input is not FASTQ (FASTA / directories: use `python -m porechop_b200`)')
-            cut = data.rfind(b'\n') + 1                     # drop the unterminated last line
-            n_nl = data.count(b'\n', 0, cut)
-            if first and n_nl < 4 * first_reads:
-                pending = data                              # keep reading until the check reads are all here
+            if kind == 'fasta':                             # records start at a '>' that begins a line
+                cut = data.rfind(b'\n>') + 1
+                n_rec = data.count(b'\n>', 0, cut) + 1 if cut else 0
+            else:
+                cut = data.rfind(b'\n') + 1                 # drop the unterminated last line
+                n_nl = data.count(b'\n', 0, cut)
+                for _ in range(n_nl % 4):                   # back to a multiple of four lines
+                    cut = data.rfind(b'\n', 0, cut - 1) + 1
+                n_rec = n_nl // 4
+            if cut == 0 or (first and n_rec < first_reads):
+                pending = data                              # keep reading (Phase A wants its check reads in one piece)
                 continue
-            for _ in range(n_nl % 4):                       # back to a multiple of four lines
-                cut = data.rfind(b'\n', 0, cut - 1) + 1
-            if cut == 0:
-                pending = data
-                continue
-            yield data[:cut]
+            yield kind, data[:cut]
             pending, first = data[cut:], False
 
 
@@ -100,7 +105,9 @@ def main():
     scoring = args.scoring_scheme_vals
     chunk_bytes = int(os.environ.get('PB200_FLAT_CHUNK_BYTES', 256 << 20))
     chunks = _record_chunks(args.input, chunk_bytes, args.check_reads)
-    batch = fastq.parse_fastq(next(chunks))
+    read_type, first = next(chunks)
+    parse = fastq.parse_fasta if read_type == 'fasta' else fastq.parse_fastq
+    batch = parse(first)
 
     # Phase A on flat buffers; the scores land on Porechop's own Adapter objects so that its policy code runs unchanged
     search = [a for a in P.ADAPTERS if '(full sequence)' not in a.name]                     # porechop.py:296
@@ -115,7 +122,7 @@ def main():
     matching = P.add_full_barcode_adapter_sets(matching)
     sets = [as_tuple(a) for a in matching]
 
-    fmt, gz = _out_format(args)
+    fmt, gz = _out_format(args, read_type)
     common = dict(end_size=args.end_size, extra_end_trim=args.extra_end_trim, end_threshold=args.end_threshold,
                   min_trim_size=args.min_trim_size, no_split=args.no_split, middle_threshold=args.middle_threshold,
                   extra_middle_trim_good_side=args.extra_middle_trim_good_side,
@@ -148,7 +155,7 @@ def main():
                 out = fastq.emit(batch, fmt=fmt, as_array=True)
             sink(None).write(out)
         nxt = next(chunks, None)
-        batch = fastq.parse_fastq(nxt) if nxt is not None else None
+        batch = parse(nxt[1]) if nxt is not None else None
     if args.barcode_dir is None and args.output is not None and None not in sinks:
         sink(None).f = gzip.open(args.output, 'wb') if gz else open(args.output, 'wb')      # an empty result is still a file
     for s_ in sinks.values():

@@ -9,7 +9,7 @@ from ctypes import CDLL, c_int, c_int64, c_void_p
 import numpy as np
 
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libhostio.so')
-EXPORTED_SYMBOLS = ['pbioCountLines', 'pbioLineEnds', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit']
+EXPORTED_SYMBOLS = ['pbioCountLines', 'pbioLineEnds', 'pbioLineSpans', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit']
 
 
 def _load():
@@ -20,6 +20,8 @@ def _load():
     lib.pbioCountLines.restype = c_int64
     lib.pbioLineEnds.argtypes = [c_void_p, c_int64, c_void_p, c_int64]
     lib.pbioLineEnds.restype = c_int
+    lib.pbioLineSpans.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]
+    lib.pbioLineSpans.restype = None
     lib.pbioFastqIndex.argtypes = [c_void_p, c_int64, c_void_p, c_int64] + [c_void_p] * 6
     lib.pbioFastqIndex.restype = c_int
     lib.pbioGather.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64]
@@ -59,6 +61,18 @@ def fastq_index(buf):
     if rc != 0:
         raise ValueError('FASTQ chunk is not a whole number of 4-line records')
     return out
+
+
+def line_spans(buf):
+    """stripped extent (start, length) of every line of buf, as two int64 arrays."""
+    n = len(buf)
+    n_lines = int(LIB.pbioCountLines(_p(buf), n))
+    line_end = np.empty(n_lines, dtype=np.int64)
+    if LIB.pbioLineEnds(_p(buf), n, _p(line_end), n_lines) != 0:
+        raise ValueError('could not index the lines')
+    a, ln = np.empty(n_lines, dtype=np.int64), np.empty(n_lines, dtype=np.int64)
+    LIB.pbioLineSpans(_p(buf), _p(line_end), n_lines, _p(a), _p(ln))
+    return a, ln
 
 
 def gather(src, src_a, lens, src_len=None, fill=0):

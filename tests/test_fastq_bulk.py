@@ -145,3 +145,25 @@ def test_native_hostio_equals_numpy_implementation(monkeypatch, seed):
             monkeypatch.setattr(hostio, 'LIB', lib)
             with pytest.raises(ValueError):
                 fastq.parse_fastq(bad)
+
+
+def test_parse_fasta_multiline_native_and_numpy(monkeypatch):
+    """multi-line FASTA with blank lines, CRLF, padding, lower case and an RNA record; both implementations agree and
+    match a plain Python restatement of the loader."""
+    from porechop_b200 import fastq, hostio
+    text = ('>r1 first read\nACGTacgt\nGGGG\n\n>r2\r\n  TTTTAAAA  \r\nCC\r\n>rna one\nUUUUACGU\n>empty\n>last\nACGT')
+    want = [('r1 first read', 'ACGTACGTGGGG'), ('r2', 'TTTTAAAACC'), ('rna one', 'TTTTACGT'), ('empty', ''), ('last', 'ACGT')]
+    for lib in (hostio._load(), None):
+        monkeypatch.setattr(hostio, 'LIB', lib)
+        b = fastq.parse_fasta(text.encode())
+        got = [(nm, bytes(b.seq[b.seq_off[i]:b.seq_off[i + 1]]).decode()) for i, nm in enumerate(b.names)]
+        assert got == want and list(b.rna) == [False, False, True, False, False]
+        assert bytes(b.qual) == b'+' * len(b.seq) and np.array_equal(b.qual_off, b.seq_off)
+        assert fastq.emit(b, fmt='fasta') == b'>r1 first read\nACGTACGTGGGG\n>r2\nTTTTAAAACC\n>rna one\nUUUUACGU\n>last\nACGT\n'
+        assert fastq.parse_reads(text.encode())[1] == 'fasta' and fastq.parse_reads(b'@a\nA\n+\nI\n')[1] == 'fastq'
+        assert len(fastq.parse_fasta(b'')) == 0
+        for bad in (b'ACGT\n>x\nAC\n', b'>\nACGT\n'):
+            with pytest.raises(ValueError):
+                fastq.parse_fasta(bad)
+        with pytest.raises(ValueError):
+            fastq.parse_reads(b'xyz')

@@ -49,6 +49,10 @@ CASES = [
                                                        '--discard_unassigned']),
     ('gz_in_gz_out', 'test_format.fastq.gz', ['-o', '{out}/o.fastq.gz', '--no_split']),
     ('gz_in_bins', 'test_format_barcodes.fastq.gz', ['-b', '{out}/bins']),
+    ('fasta_in_fastq_out', 'test_format.fasta', ['-o', '{out}/o.fastq']),
+    ('fasta_gz_in_auto_out', 'test_format.fasta.gz', ['-o', '{out}/trimmed_reads', '--min_split_read_size', '100']),
+    ('fasta_in_bins', 'test_choose_barcodes_1.fasta', ['-b', '{out}/bins']),
+    ('fasta_gz_in_bins_gz', 'test_format_barcodes.fasta.gz', ['-b', '{out}/bins', '--discard_unassigned']),
     ('synthetic_edges', 'GOLDEN:input_fastq', ['-o', '{out}/o.fastq', '--min_split_read_size', '50']),
     ('synthetic_barcoded', 'GOLDEN:barcoded_fastq', ['-b', '{out}/bins', '--format', 'fasta']),
 ]
@@ -78,6 +82,7 @@ def test_flat_cli_writes_the_reference_cli_files(name, input_name, argv, porecho
 
 @pytest.mark.parametrize('chunk', [3000, 20000])
 @pytest.mark.parametrize('input_name,argv', [('test_barcodes.fastq', ['-b', '{out}/bins', '--check_reads', '5']),
+                                             ('test_format.fasta', ['-o', '{out}/o.fasta', '--check_reads', '7']),
                                              ('GOLDEN:input_fastq', ['-o', '{out}/o.fastq.gz', '--check_reads', '4',
                                                                      '--min_split_read_size', '50'])])
 def test_flat_cli_streams_in_chunks(chunk, input_name, argv, porechop_modules, monkeypatch, tmp_path):  # noqa: F811
