@@ -12,8 +12,7 @@ decisions on arrays -> output bytes.  Output files are byte-identical to the ref
 The input is streamed in whole-record chunks (PB200_FLAT_CHUNK_BYTES, default 256 MB; the first chunk holds the check
 reads of Phase A), so memory is bounded by the chunk size, not the file size.
 
-Limits (the run exits with a message instead of guessing): input must be one FASTQ or FASTA file (plain or .gz);
-Albacore directories go through `python -m porechop_b200`.
+Input: one FASTQ or FASTA file (plain or .gz), or an Albacore output directory of FASTQ files (porechop.py:224-273).
 """
 import gzip
 import os
@@ -100,21 +99,37 @@ def main():
     except ImportError:
         sys.exit('porechop_b200.flat_cli: no `porechop` package on sys.path (point PYTHONPATH at a Porechop checkout)')
     args = P.get_arguments()
-    if os.path.isdir(args.input):
-        sys.exit('porechop_b200.flat_cli: directory input is not supported (use `python -m porechop_b200`)')
     scoring = args.scoring_scheme_vals
     chunk_bytes = int(os.environ.get('PB200_FLAT_CHUNK_BYTES', 256 << 20))
-    chunks = _record_chunks(args.input, chunk_bytes, args.check_reads)
-    read_type, first = next(chunks)
-    parse = fastq.parse_fasta if read_type == 'fasta' else fastq.parse_fastq
-    batch = parse(first)
+    if os.path.isdir(args.input):
+        # an Albacore output directory (porechop.py:241-266): every *.fastq[.gz] below it in sorted order, the check
+        # reads spread over the files, and Albacore's own bin (from the path) must agree with the barcode call
+        inputs = sorted(os.path.join(d, f) for d, _, names in os.walk(args.input) for f in names
+                        if f.lower().endswith('.fastq') or f.lower().endswith('.fastq.gz'))
+        if not inputs:
+            sys.exit('Error: could not find fastq files in ' + args.input)
+        check_per_file = int(round(args.check_reads / len(inputs)))
+        albacore = [P.get_albacore_barcode_from_path(f) for f in inputs]
+    elif os.path.isfile(args.input):
+        inputs, check_per_file, albacore = [args.input], args.check_reads, [None]
+    else:
+        sys.exit('Error: could not find ' + args.input)
+    parsers = {'fasta': fastq.parse_fasta, 'fastq': fastq.parse_fastq}
 
     # Phase A on flat buffers; the scores land on Porechop's own Adapter objects so that its policy code runs unchanged
     search = [a for a in P.ADAPTERS if '(full sequence)' not in a.name]                     # porechop.py:296
     as_tuple = lambda a: (a.name, tuple(a.start_sequence) or None, tuple(a.end_sequence) or None)   # noqa: E731
-    best_s, best_e = fastq.search_adapter_sets(batch, [as_tuple(a) for a in search], scoring, args.check_reads, args.end_size)
-    for a, s, e in zip(search, best_s, best_e):
-        a.best_start_score, a.best_end_score = max(a.best_start_score, float(s)), max(a.best_end_score, float(e))
+    read_type = 'fastq'
+    for path in inputs:
+        kind, first = next(_record_chunks(path, chunk_bytes, check_per_file))
+        if len(inputs) == 1:
+            read_type = kind
+        if check_per_file <= 0:
+            continue
+        best_s, best_e = fastq.search_adapter_sets(parsers[kind](first), [as_tuple(a) for a in search], scoring,
+                                                   check_per_file, args.end_size)
+        for a, s, e in zip(search, best_s, best_e):
+            a.best_start_score, a.best_end_score = max(a.best_start_score, float(s)), max(a.best_end_score, float(e))
     matching = [a for a in search if a.best_start_or_end_score() >= args.adapter_threshold]  # porechop.py:327
     matching = P.fix_up_1d2_sets(matching)
     null = open(os.devnull, 'w')
@@ -137,25 +152,27 @@ def main():
         return sinks[name]
     if args.barcode_dir is not None:
         os.makedirs(args.barcode_dir, exist_ok=True)
-    while batch is not None:
-        if args.barcode_dir is not None:
-            if sets:
-                bins, _ = fastq.demux_fastq(batch, sets, scoring, direction, barcode_threshold=args.barcode_threshold,
-                                            barcode_diff=args.barcode_diff, require_two_barcodes=args.require_two_barcodes,
-                                            discard_unassigned=args.discard_unassigned, untrimmed=args.untrimmed, **common)
+    for path, albacore_call in zip(inputs, albacore):
+        for kind, data in _record_chunks(path, chunk_bytes, 0):
+            batch = parsers[kind](data)
+            if args.barcode_dir is not None:
+                calls = None if albacore_call is None else [albacore_call] * len(batch)
+                if sets:
+                    bins, _ = fastq.demux_fastq(batch, sets, scoring, direction, barcode_threshold=args.barcode_threshold,
+                                                barcode_diff=args.barcode_diff, require_two_barcodes=args.require_two_barcodes,
+                                                discard_unassigned=args.discard_unassigned, untrimmed=args.untrimmed,
+                                                albacore_calls=calls, **common)
+                else:
+                    out = fastq.emit(batch, fmt=fmt, untrimmed=args.untrimmed, as_array=True)
+                    bins = {} if args.discard_unassigned else {'none': out}
+                for name, payload in bins.items():
+                    sink(name).write(payload)
             else:
-                out = fastq.emit(batch, fmt=fmt, untrimmed=args.untrimmed, as_array=True)
-                bins = {} if args.discard_unassigned else {'none': out}
-            for name, payload in bins.items():
-                sink(name).write(payload)
-        else:
-            if sets:
-                out, _ = fastq.trim_fastq(batch, sets, scoring, **common)
-            else:                   # "No adapters found - output reads are unchanged from input reads"
-                out = fastq.emit(batch, fmt=fmt, as_array=True)
-            sink(None).write(out)
-        nxt = next(chunks, None)
-        batch = parse(nxt[1]) if nxt is not None else None
+                if sets:
+                    out, _ = fastq.trim_fastq(batch, sets, scoring, **common)
+                else:               # "No adapters found - output reads are unchanged from input reads"
+                    out = fastq.emit(batch, fmt=fmt, as_array=True)
+                sink(None).write(out)
     if args.barcode_dir is None and args.output is not None and None not in sinks:
         sink(None).f = gzip.open(args.output, 'wb') if gz else open(args.output, 'wb')      # an empty result is still a file
     for s_ in sinks.values():

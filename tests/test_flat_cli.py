@@ -53,6 +53,10 @@ CASES = [
     ('fasta_gz_in_auto_out', 'test_format.fasta.gz', ['-o', '{out}/trimmed_reads', '--min_split_read_size', '100']),
     ('fasta_in_bins', 'test_choose_barcodes_1.fasta', ['-b', '{out}/bins']),
     ('fasta_gz_in_bins_gz', 'test_format_barcodes.fasta.gz', ['-b', '{out}/bins', '--discard_unassigned']),
+    ('albacore_dir_bins', 'test_albacore_directory', ['-b', '{out}/bins']),
+    ('albacore_dir_bins_opts', 'test_albacore_directory', ['-b', '{out}/bins', '--check_reads', '6', '--barcode_diff', '1',
+                                                            '--discard_unassigned']),
+    ('albacore_dir_single_out', 'test_albacore_directory', ['-o', '{out}/all.fasta']),
     ('synthetic_edges', 'GOLDEN:input_fastq', ['-o', '{out}/o.fastq', '--min_split_read_size', '50']),
     ('synthetic_barcoded', 'GOLDEN:barcoded_fastq', ['-b', '{out}/bins', '--format', 'fasta']),
 ]
