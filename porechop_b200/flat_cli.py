@@ -57,6 +57,30 @@ def _record_chunks(path, chunk_bytes, first_reads):
             pending, first = data[cut:], False
 
 
+def _prefetch(it, depth=2):
+    """Run an iterator in a background thread, `depth` items ahead: reading, gunzipping and parsing the next chunk
+    (zlib, libhostio and the engine all release the GIL) overlaps the alignment and the writing of the current one."""
+    import queue
+    import threading
+    q, end = queue.Queue(maxsize=depth), object()
+
+    def work():
+        try:
+            for item in it:
+                q.put(item)
+            q.put(end)
+        except BaseException as e:          # re-raised in the consumer (sys.exit from the reader included)
+            q.put(e)
+    threading.Thread(target=work, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is end:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+
+
 class _Sink:
     """one output stream (file, gz file or stdout), opened on first write like the reference's bin files"""
 
@@ -152,27 +176,33 @@ def main():
         return sinks[name]
     if args.barcode_dir is not None:
         os.makedirs(args.barcode_dir, exist_ok=True)
-    for path, albacore_call in zip(inputs, albacore):
-        for kind, data in _record_chunks(path, chunk_bytes, 0):
-            batch = parsers[kind](data)
-            if args.barcode_dir is not None:
-                calls = None if albacore_call is None else [albacore_call] * len(batch)
-                if sets:
-                    bins, _ = fastq.demux_fastq(batch, sets, scoring, direction, barcode_threshold=args.barcode_threshold,
-                                                barcode_diff=args.barcode_diff, require_two_barcodes=args.require_two_barcodes,
-                                                discard_unassigned=args.discard_unassigned, untrimmed=args.untrimmed,
-                                                albacore_calls=calls, **common)
-                else:
-                    out = fastq.emit(batch, fmt=fmt, untrimmed=args.untrimmed, as_array=True)
-                    bins = {} if args.discard_unassigned else {'none': out}
-                for name, payload in bins.items():
-                    sink(name).write(payload)
-            else:
-                if sets:
-                    out, _ = fastq.trim_fastq(batch, sets, scoring, **common)
-                else:               # "No adapters found - output reads are unchanged from input reads"
-                    out = fastq.emit(batch, fmt=fmt, as_array=True)
-                sink(None).write(out)
+
+    def process(batch, albacore_call):
+        if args.barcode_dir is None:
+            if sets:
+                out, _ = fastq.trim_fastq(batch, sets, scoring, **common)
+            else:                   # "No adapters found - output reads are unchanged from input reads"
+                out = fastq.emit(batch, fmt=fmt, as_array=True)
+            sink(None).write(out)
+            return
+        if sets:
+            calls = None if albacore_call is None else [albacore_call] * len(batch)
+            bins, _ = fastq.demux_fastq(batch, sets, scoring, direction, barcode_threshold=args.barcode_threshold,
+                                        barcode_diff=args.barcode_diff, require_two_barcodes=args.require_two_barcodes,
+                                        discard_unassigned=args.discard_unassigned, untrimmed=args.untrimmed,
+                                        albacore_calls=calls, **common)
+        else:
+            out = fastq.emit(batch, fmt=fmt, untrimmed=args.untrimmed, as_array=True)
+            bins = {} if args.discard_unassigned else {'none': out}
+        for name, payload in bins.items():
+            sink(name).write(payload)
+
+    def batches():
+        for path, albacore_call in zip(inputs, albacore):
+            for kind, data in _record_chunks(path, chunk_bytes, 0):
+                yield parsers[kind](data), albacore_call
+    for batch, albacore_call in _prefetch(batches()):
+        process(batch, albacore_call)
     if args.barcode_dir is None and args.output is not None and None not in sinks:
         sink(None).f = gzip.open(args.output, 'wb') if gz else open(args.output, 'wb')      # an empty result is still a file
     for s_ in sinks.values():
