@@ -12,6 +12,10 @@ decisions on arrays -> output bytes.  Output files are byte-identical to the ref
 The input is streamed in whole-record chunks (PB200_FLAT_CHUNK_BYTES, default 256 MB; the first chunk holds the check
 reads of Phase A), so memory is bounded by the chunk size, not the file size.
 
+Multi-GPU: launched with torchrun (one process per GPU) chunk c is handled by rank c % world on its own device; ranks
+write self-contained pieces and rank 0 stitches them in chunk order after a barrier -- no data-path collective
+(SURVEY 8e).
+
 Input: one FASTQ or FASTA file (plain or .gz), or an Albacore output directory of FASTQ files (porechop.py:224-273).
 """
 import gzip
@@ -82,24 +86,63 @@ def _prefetch(it, depth=2):
 
 
 class _Sink:
-    """one output stream (file, gz file or stdout), opened on first write like the reference's bin files"""
+    """one output stream (file, gz file or stdout), opened on first write like the reference's bin files.
+    With world > 1 every rank writes its pieces to `<path>.rank<r>` as self-contained segments (one gzip member per
+    piece for .gz) and remembers (chunk index, offset, length); rank 0 stitches the pieces of all ranks together in
+    chunk order afterwards (`_merge_rank_files`)."""
 
-    def __init__(self, path, gz):
-        self.path, self.gz, self.f = path, gz, None
+    def __init__(self, path, gz, rank=0, world=1):
+        self.final, self.gz, self.f, self.ranked = path, gz, None, world > 1
+        self.path = path if not self.ranked else '%s.rank%d' % (path, rank)
+        self.index = []                                    # ranked mode: [chunk, offset, length]
 
-    def write(self, payload):
+    def write(self, payload, chunk=0):
         if not len(payload):
             return
         if self.f is None:
-            if self.path is None:
+            if self.final is None:
                 self.f = sys.stdout.buffer
+            elif self.ranked or not self.gz:
+                self.f = open(self.path, 'wb')
             else:   # gz: same bytes inside as the reference's `gzip -c`, different container timestamp
-                self.f = gzip.open(self.path, 'wb') if self.gz else open(self.path, 'wb')
-        self.f.write(payload)
+                self.f = gzip.open(self.path, 'wb')
+        if not self.ranked:
+            self.f.write(payload)
+            return
+        start = self.f.tell()
+        if self.gz:
+            with gzip.GzipFile(fileobj=self.f, mode='wb') as g:
+                g.write(payload)
+        else:
+            self.f.write(payload)
+        self.index.append([chunk, start, self.f.tell() - start])
 
     def close(self):
-        if self.f is not None and self.path is not None:
+        if self.f is not None and self.final is not None:
             self.f.close()
+
+
+def _merge_rank_files(final_paths, world):
+    """rank 0, after the barrier: final file = the pieces of all ranks in chunk order (a multi-member .gz is a valid
+    .gz of the concatenation); the per-rank files are removed."""
+    import json
+    for final in final_paths:
+        pieces = []
+        for r in range(world):
+            idx = '%s.rank%d.idx' % (final, r)
+            if os.path.exists(idx):
+                pieces += [(c, r, off, ln) for c, off, ln in json.load(open(idx))]
+                os.remove(idx)
+        if not pieces:
+            continue
+        files = {r: open('%s.rank%d' % (final, r), 'rb') for r in {p[1] for p in pieces}}
+        with open(final, 'wb') as out:
+            for c, r, off, ln in sorted(pieces):
+                files[r].seek(off)
+                out.write(files[r].read(ln))
+        for r, f in files.items():
+            f.close()
+            os.remove('%s.rank%d' % (final, r))
 
 
 def _out_format(args, read_type='fastq'):
@@ -125,6 +168,17 @@ def main():
     args = P.get_arguments()
     scoring = args.scoring_scheme_vals
     chunk_bytes = int(os.environ.get('PB200_FLAT_CHUNK_BYTES', 256 << 20))
+    # one process per GPU (torchrun): chunk c belongs to rank c % world; nothing but a final barrier is exchanged
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    if world > 1:
+        import torch.distributed as dist
+        from . import cpp_function_wrappers as W
+        if args.output is None and args.barcode_dir is None:
+            sys.exit('porechop_b200.flat_cli: multi-process runs need -o or -b (stdout cannot be stitched)')
+        n_dev = W.device_count()
+        if n_dev > 0:
+            W.set_device(int(os.environ.get('LOCAL_RANK', rank)) % n_dev)
+        dist.init_process_group('gloo')                   # host-side barrier only; the data path has no collective
     if os.path.isdir(args.input):
         # an Albacore output directory (porechop.py:241-266): every *.fastq[.gz] below it in sorted order, the check
         # reads spread over the files, and Albacore's own bin (from the path) must agree with the barcode call
@@ -172,18 +226,18 @@ def main():
     def sink(name):
         if name not in sinks:
             path = args.output if name is None else os.path.join(args.barcode_dir, name + '.' + fmt + ('.gz' if gz else ''))
-            sinks[name] = _Sink(path, gz)
+            sinks[name] = _Sink(path, gz, rank, world)
         return sinks[name]
     if args.barcode_dir is not None:
         os.makedirs(args.barcode_dir, exist_ok=True)
 
-    def process(batch, albacore_call):
+    def process(batch, albacore_call, chunk):
         if args.barcode_dir is None:
             if sets:
                 out, _ = fastq.trim_fastq(batch, sets, scoring, **common)
             else:                   # "No adapters found - output reads are unchanged from input reads"
                 out = fastq.emit(batch, fmt=fmt, as_array=True)
-            sink(None).write(out)
+            sink(None).write(out, chunk)
             return
         if sets:
             calls = None if albacore_call is None else [albacore_call] * len(batch)
@@ -195,18 +249,38 @@ def main():
             out = fastq.emit(batch, fmt=fmt, untrimmed=args.untrimmed, as_array=True)
             bins = {} if args.discard_unassigned else {'none': out}
         for name, payload in bins.items():
-            sink(name).write(payload)
+            sink(name).write(payload, chunk)
 
     def batches():
+        chunk = 0
         for path, albacore_call in zip(inputs, albacore):
             for kind, data in _record_chunks(path, chunk_bytes, 0):
-                yield parsers[kind](data), albacore_call
-    for batch, albacore_call in _prefetch(batches()):
-        process(batch, albacore_call)
-    if args.barcode_dir is None and args.output is not None and None not in sinks:
-        sink(None).f = gzip.open(args.output, 'wb') if gz else open(args.output, 'wb')      # an empty result is still a file
+                if chunk % world == rank:
+                    yield parsers[kind](data), albacore_call, chunk
+                chunk += 1
+    for batch, albacore_call, chunk in _prefetch(batches()):
+        process(batch, albacore_call, chunk)
+    if world == 1:
+        if args.barcode_dir is None and args.output is not None and None not in sinks:
+            sink(None).f = gzip.open(args.output, 'wb') if gz else open(args.output, 'wb')  # an empty result is still a file
+        for s_ in sinks.values():
+            s_.close()
+        return 0
+    import json
     for s_ in sinks.values():
         s_.close()
+        if s_.index:
+            json.dump(s_.index, open(s_.path + '.idx', 'w'))
+    finals = [None] * world                               # which output files exist anywhere (bins differ per rank)
+    dist.all_gather_object(finals, [s_.final for s_ in sinks.values()])
+    dist.barrier()
+    if rank == 0:
+        names = sorted({f for fs in finals for f in fs})
+        _merge_rank_files(names, world)
+        if args.barcode_dir is None and not os.path.exists(args.output):
+            (gzip.open if gz else open)(args.output, 'wb').close()
+    dist.barrier()
+    dist.destroy_process_group()
     return 0
 
 

@@ -93,3 +93,61 @@ def test_flat_cli_streams_in_chunks(chunk, input_name, argv, porechop_modules, m
     """tiny chunks (many whole-record pieces, bins appended piece by piece): same files as the reference CLI."""
     monkeypatch.setenv('PB200_FLAT_CHUNK_BYTES', str(chunk))
     test_flat_cli_writes_the_reference_cli_files('chunked', input_name, argv, porechop_modules, monkeypatch, tmp_path)
+
+
+def _rank_worker(rank, world, port, argv, q):
+    """one torchrun-style rank of the flat CLI on CPU: gloo for the barrier, the oracle as the engine (tests only)."""
+    import numpy as np
+    os.environ.update({'RANK': str(rank), 'LOCAL_RANK': str(rank), 'WORLD_SIZE': str(world), 'MASTER_ADDR': '127.0.0.1',
+                       'MASTER_PORT': str(port), 'PB200_FLAT_CHUNK_BYTES': '6000'})
+    try:
+        from helpers import oracle_batch
+        from test_patch_cli import load_reference
+        load_reference()
+        sys.path.insert(0, REF)
+        from porechop_b200 import cpp_function_wrappers as W
+        from porechop_b200 import flat_cli
+        W.adapter_alignment_batch = lambda sb, so, ab, ao, sc, ps=None, pa=None, out=None: oracle_batch(
+            np.asarray(sb), np.asarray(so), np.asarray(ab), np.asarray(ao), list(sc), ps, pa)
+        sys.argv = ['porechop'] + argv
+        with contextlib.redirect_stdout(io.StringIO()):
+            flat_cli.main()
+        q.put((rank, 'ok'))
+    except BaseException as e:      # noqa: BLE001 -- report to the parent instead of hanging it
+        q.put((rank, repr(e)))
+
+
+@pytest.mark.parametrize('argv', [['-b', '{out}/bins', '--check_reads', '5'], ['-o', '{out}/o.fastq.gz', '--check_reads', '5']],
+                         ids=['bins', 'single_gz'])
+def test_flat_cli_two_ranks_gloo(argv, porechop_modules, tmp_path):  # noqa: F811
+    """world_size 2 on CPU (gloo): chunks alternate between the ranks, rank 0 stitches the pieces -- same files as the
+    reference CLI, no leftovers."""
+    import socket
+    import torch.multiprocessing as mp
+    porechop, P, A = porechop_modules
+    inp = os.path.join(REF, 'test', 'test_barcodes.fastq')
+
+    def args_for(out):
+        return ['-i', inp, '-v', '0', '-t', '1'] + [a.replace('{out}', out) for a in argv]
+    _, base = _run_cli(P, A, args_for(str(tmp_path / 'a')), str(tmp_path / 'a'))
+    with socket.socket() as s_:
+        s_.bind(('127.0.0.1', 0))
+        port = s_.getsockname()[1]
+    os.makedirs(str(tmp_path / 'b'), exist_ok=True)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_worker, args=(r, 2, port, args_for(str(tmp_path / 'b')), q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    results = dict(q.get(timeout=300) for _ in procs)
+    for p_ in procs:
+        p_.join(timeout=60)
+    assert results == {0: 'ok', 1: 'ok'}
+    got = {}
+    for d, _, names in os.walk(str(tmp_path / 'b')):
+        for nm in names:
+            got[os.path.relpath(os.path.join(d, nm), str(tmp_path / 'b'))] = open(os.path.join(d, nm), 'rb').read()
+    base, got = _plain(base), _plain(got)
+    assert sorted(got) == sorted(base), sorted(got)
+    for k in base:
+        assert got[k] == base[k], k

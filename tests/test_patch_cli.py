@@ -29,8 +29,7 @@ pytestmark = pytest.mark.skipif(not (os.path.isdir(os.path.join(REF, 'porechop')
                                 reason='needs the reference checkout and oracle/_ref (authoring container)')
 
 
-@pytest.fixture(scope='module')
-def porechop_modules():
+def load_reference():
     """Import the reference package with `porechop.cpp_function_wrappers` bound to oracle/_ref/cpp_functions.so (the
     reference's wrapper insists on a .so inside its own read-only tree; nothing of the reference is modified)."""
     warnings.simplefilter('ignore')
@@ -56,6 +55,11 @@ def porechop_modules():
     finally:
         sys.path.remove(REF)
     return porechop, P, A
+
+
+@pytest.fixture(scope='module')
+def porechop_modules():
+    return load_reference()
 
 
 def _run_cli(P, A, argv, out_dir):
