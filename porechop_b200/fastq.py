@@ -29,6 +29,8 @@ buffers end to end:
 The alignment engine is case-insensitive and maps U to T itself (Dna5 table); normalising at parse time only matters
 because the reference writes the normalised bases back out.
 """
+import time
+
 import numpy as np
 
 from . import cpp_function_wrappers as W
@@ -531,19 +533,23 @@ def _middle_adapters(sets):
 
 def _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim, end_threshold, min_trim_size, no_split,
               middle_threshold, good_side, bad_side):
+    t0 = time.perf_counter()
     batch = data if isinstance(data, FastqBatch) else parse_fastq(data)
+    t1 = time.perf_counter()
     sets = _norm_sets(matching_sets)
     starts = [s[1] for _, s, _ in sets if s]
     ends = [e[1] for _, _, e in sets if e]
     st, et, srec, erec = trim_end_adapters(batch, starts, ends, scoring_scheme_vals, end_size, extra_end_trim,
                                            end_threshold, min_trim_size)
+    t2 = time.perf_counter()
     middle = {}
     if not no_split:
         adapters = _middle_adapters(sets)
         hits = find_middle_hits(batch, st, et, adapters, middle_threshold, scoring_scheme_vals)
         middle = middle_trim_ranges(hits, adapters, {s[0] for _, s, _ in sets if s}, {e[0] for _, _, e in sets if e},
                                     good_side, bad_side)
-    return batch, sets, st, et, srec, erec, middle
+    seconds = {'parse': t1 - t0, 'end_trim': t2 - t1, 'middle': time.perf_counter() - t2}
+    return batch, sets, st, et, srec, erec, middle, seconds
 
 
 def trim_fastq(data, matching_sets, scoring_scheme_vals, end_size=150, extra_end_trim=2, end_threshold=75.0,
@@ -553,11 +559,13 @@ def trim_fastq(data, matching_sets, scoring_scheme_vals, end_size=150, extra_end
     (porechop.py:54-79).  matching_sets: list of (start, end) with start / end = (name, sequence) or None -- the
     `start_sequence` / `end_sequence` of the reference's Adapter objects (adapters.py:18-30).
     Returns (output bytes, info dict with the per-read decisions)."""
-    batch, _, st, et, _, _, middle = _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim,
-                                               end_threshold, min_trim_size, no_split, middle_threshold,
-                                               extra_middle_trim_good_side, extra_middle_trim_bad_side)
+    batch, _, st, et, _, _, middle, seconds = _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim,
+                                                        end_threshold, min_trim_size, no_split, middle_threshold,
+                                                        extra_middle_trim_good_side, extra_middle_trim_bad_side)
+    t0 = time.perf_counter()
     out = emit(batch, st, et, middle, fmt, min_split_read_size, discard_middle, as_array=as_array)
-    return out, {'start_trim': st, 'end_trim': et, 'middle': middle, 'n_reads': len(batch)}
+    seconds['emit'] = time.perf_counter() - t0
+    return out, {'start_trim': st, 'end_trim': et, 'middle': middle, 'n_reads': len(batch), 'seconds': seconds}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -631,10 +639,11 @@ def demux_fastq(data, matching_sets, scoring_scheme_vals, forward_or_reverse='fo
     (porechop.py:54-79, 652-676) once Phase A has chosen `matching_sets` = [(set name, start, end), ...] and the
     barcode direction.  A set is a barcode if its name starts with 'Barcode ' (adapters.py:31-32); its direction is
     'reverse' if its start name contains '_rev' (adapters.py:34-38).  Returns (bins, info)."""
-    batch, sets, st, et, srec, erec, middle = _run_trim(data, matching_sets, scoring_scheme_vals, end_size,
-                                                        extra_end_trim, end_threshold, min_trim_size, no_split,
-                                                        middle_threshold, extra_middle_trim_good_side,
-                                                        extra_middle_trim_bad_side)
+    batch, sets, st, et, srec, erec, middle, seconds = _run_trim(data, matching_sets, scoring_scheme_vals, end_size,
+                                                                 extra_end_trim, end_threshold, min_trim_size, no_split,
+                                                                 middle_threshold, extra_middle_trim_good_side,
+                                                                 extra_middle_trim_bad_side)
+    t0 = time.perf_counter()
     n = len(batch)
 
     def is_bc(name, s):
@@ -661,4 +670,5 @@ def demux_fastq(data, matching_sets, scoring_scheme_vals, forward_or_reverse='fo
                    as_array=as_array)
         if len(out):
             bins[name] = out
-    return bins, {'start_trim': st, 'end_trim': et, 'middle': middle, 'calls': calls, 'n_reads': n}
+    seconds['call_and_emit'] = time.perf_counter() - t0
+    return bins, {'start_trim': st, 'end_trim': et, 'middle': middle, 'calls': calls, 'n_reads': n, 'seconds': seconds}

@@ -116,3 +116,16 @@ def test_call_barcodes_against_scalar_rule():
     assert call_barcodes(np.zeros((2, 0)), [], np.zeros((2, 0)), []) == ['none', 'none']
     got = call_barcodes(np.array([[95.0], [95.0]]), ['BC01'], np.zeros((2, 0)), [], albacore_calls=['BC02', None])
     assert got == ['none', 'BC01']
+
+
+def test_flat_pipeline_bench_tool_dry_run(monkeypatch):
+    """tools/flat_pipeline_bench.py (the GPU-side stage timer) runs end to end; here with the oracle as the engine."""
+    import importlib.util
+    import os
+    from helpers import ROOT
+    _oracle_engine(monkeypatch)
+    spec = importlib.util.spec_from_file_location('flat_pipeline_bench', os.path.join(ROOT, 'tools', 'flat_pipeline_bench.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    r = mod.run(24, 1)
+    assert r['reads'] == 24 and r['out_bytes'] > 0 and set(r['seconds']) == {'parse', 'end_trim', 'middle', 'emit'}
