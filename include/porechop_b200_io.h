@@ -54,6 +54,13 @@ void pbioEmit(uint8_t *out, const int64_t *out_off, int64_t n_rec, int fmt,
               const uint8_t *seq, const int64_t *seq_a, const int64_t *seq_len,
               const uint8_t *qual, const int64_t *qual_a, const int64_t *qual_len, const uint8_t *rna);
 
+/* align_adapter()'s parse of the result string (nanopore_read.py:476-491) for n records {rs, re, as, ae, score,
+ * match_aln, len_aln, match_ad, len_ad} (include/porechop_b200.h) without making the strings:
+ *   full[i] = strtod(sprintf("%f", 100.0 * match_ad / len_ad)), part[i] likewise from match_aln / len_aln (NaN for 0/0,
+ *   as float("-nan") is), read_start[i] = rs, read_end[i] = re + 1; a failed alignment (rs == -1, score == INT_MIN)
+ *   gives 0.0, 0.0, -1, 0.  The (count, length) -> value table is built once per call for the pairs that occur. */
+void pbioScores(const int32_t *records, int64_t n, double *full, double *part, int64_t *read_start, int64_t *read_end);
+
 #ifdef __cplusplus
 }
 #endif

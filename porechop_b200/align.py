@@ -47,6 +47,9 @@ def scores_from_records(records):
     Returns (full_score, partial_score, read_start, read_end) arrays with the exact values the reference's
     align_adapter() returns for each alignment (failed alignments: 0.0, 0.0, -1, 0).
     """
+    from . import hostio
+    if hostio.LIB is not None:
+        return hostio.scores(records)                # the same values, one parallel pass in C (libhostio.so)
     r = np.asarray(records, dtype=np.int32).reshape(-1, 9)
     failed = (r[:, 0] == -1) & (r[:, 4] == SCORE_EMPTY)
     full = _percent_exact(r[:, 7], r[:, 8])

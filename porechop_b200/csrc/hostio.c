@@ -5,6 +5,10 @@
  */
 #include "../../include/porechop_b200_io.h"
 
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define PBIO_BLOCK (1 << 20)
@@ -177,4 +181,63 @@ void pbioEmit(uint8_t *out, const int64_t *out_off, int64_t n_rec, int fmt,
             }
         }
     }
+}
+
+/* float("%f" % (100.0 * c / l)) exactly as the reference chain produces it: std::to_string(double) = sprintf("%f")
+ * (alignment.cpp:113-121) then Python's float() = strtod. */
+static double percent_exact(int32_t c, int32_t l)
+{
+    if (l == 0) return NAN;
+    char buf[64];
+    volatile double cd = (double)c, ld = (double)l;
+    snprintf(buf, sizeof buf, "%f", 100.0 * cd / ld);
+    return strtod(buf, NULL);
+}
+
+#define PBIO_TABLE_MAX 2048
+
+void pbioScores(const int32_t *records, int64_t n, double *full, double *part, int64_t *read_start, int64_t *read_end)
+{
+    int32_t lmax = 0;
+    int small = 1;
+#pragma omp parallel for schedule(static) reduction(max : lmax) reduction(& : small)
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t *r = records + 9 * i;
+        if (r[5] < 0 || r[6] < 0 || r[7] < 0 || r[8] < 0 || r[5] > r[6] || r[7] > r[8]) small = 0;
+        if (r[6] > lmax) lmax = r[6];
+        if (r[8] > lmax) lmax = r[8];
+    }
+    double *table = NULL;
+    uint8_t *present = NULL;
+    const int64_t L = (int64_t)lmax + 1;
+    if (small && lmax < PBIO_TABLE_MAX) {
+        table = (double *)malloc((size_t)(L * L) * sizeof(double));
+        present = (uint8_t *)calloc((size_t)(L * L), 1);
+        if (!table || !present) { free(table); free(present); table = NULL; present = NULL; }
+    }
+    if (table) {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            const int32_t *r = records + 9 * i;
+            present[(int64_t)r[5] * L + r[6]] = 1;          /* benign race: every writer stores 1 */
+            present[(int64_t)r[7] * L + r[8]] = 1;
+        }
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int64_t k = 0; k < L * L; ++k)
+            if (present[k]) table[k] = percent_exact((int32_t)(k / L), (int32_t)(k % L));
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t *r = records + 9 * i;
+        if (r[0] == -1 && r[4] == INT_MIN) {
+            full[i] = 0.0; part[i] = 0.0; read_start[i] = -1; read_end[i] = 0;
+            continue;
+        }
+        part[i] = table ? table[(int64_t)r[5] * L + r[6]] : percent_exact(r[5], r[6]);
+        full[i] = table ? table[(int64_t)r[7] * L + r[8]] : percent_exact(r[7], r[8]);
+        read_start[i] = r[0];
+        read_end[i] = (int64_t)r[1] + 1;
+    }
+    free(table);
+    free(present);
 }

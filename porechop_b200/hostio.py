@@ -9,7 +9,7 @@ from ctypes import CDLL, c_int, c_int64, c_void_p
 import numpy as np
 
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libhostio.so')
-EXPORTED_SYMBOLS = ['pbioCountLines', 'pbioLineEnds', 'pbioLineSpans', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit']
+EXPORTED_SYMBOLS = ['pbioCountLines', 'pbioLineEnds', 'pbioLineSpans', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit', 'pbioScores']
 
 
 def _load():
@@ -30,6 +30,8 @@ def _load():
     lib.pbioNormalise.restype = None
     lib.pbioEmit.argtypes = [c_void_p, c_void_p, c_int64, c_int] + [c_void_p] * 10
     lib.pbioEmit.restype = None
+    lib.pbioScores.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.pbioScores.restype = None
     return lib
 
 
@@ -100,3 +102,13 @@ def emit(out_off, fmt, names, name_a, name_len, seq, seq_a, seq_len, qual, qual_
     LIB.pbioEmit(_p(out), _p(arrs[0]), len(arrs[1]), 0 if fmt == 'fastq' else 1, _p(names), _p(arrs[1]), _p(arrs[2]),
                  _p(seq), _p(arrs[3]), _p(arrs[4]), _p(qual), _p(arrs[5]), _p(arrs[6]), _p(rna8))
     return out
+
+
+def scores(records):
+    """int32[n, 9] records -> (full, part, read_start, read_end) as align_adapter() would parse them."""
+    r = np.ascontiguousarray(records, dtype=np.int32).reshape(-1, 9)
+    n = len(r)
+    full, part = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.float64)
+    rs, re_ = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+    LIB.pbioScores(_p(r), n, _p(full), _p(part), _p(rs), _p(re_))
+    return full, part, rs, re_

@@ -82,3 +82,30 @@ def test_empty_inputs_need_no_device():
     from porechop_b200 import cpp_function_wrappers as W
     assert W.adapter_alignment('', 'ACGT', [3, -6, -5, -2]) == '-1,0,-1,0,-2147483648,0.000000,0.000000'
     assert W.adapter_alignment('ACGT', '', [3, -6, -5, -2]) == '-1,0,-1,0,-2147483648,0.000000,0.000000'
+
+
+def test_scores_native_equals_numpy(monkeypatch):
+    """libhostio's pbioScores and the numpy implementation of scores_from_records agree (incl. NaN for 0/0, failed
+    alignments, and lengths beyond the table bound, which take the per-record path)."""
+    from porechop_b200 import align, hostio
+    assert hostio.LIB is not None
+    rng = np.random.default_rng(3)
+    n = 20000
+    r = np.zeros((n, 9), dtype=np.int32)
+    r[:, 6] = rng.integers(0, 300, n)
+    r[:, 5] = (r[:, 6] * rng.random(n)).astype(np.int32)
+    r[:, 8] = rng.integers(0, 120, n)
+    r[:, 7] = (r[:, 8] * rng.random(n)).astype(np.int32)
+    r[:, 0] = rng.integers(0, 100, n)
+    r[:, 1] = r[:, 0] + rng.integers(0, 50, n)
+    r[::97, 0] = -1
+    r[::97, 4] = -2147483648
+    big = r[:500].copy()
+    big[:, 6] += 5000                                 # beyond the dense table: per-record formatting
+    for rec in (r, big, r[:0]):
+        native = align.scores_from_records(rec)
+        monkeypatch.setattr(hostio, 'LIB', None)
+        slow = align.scores_from_records(rec)
+        monkeypatch.undo()
+        for a, b in zip(native, slow):
+            assert a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
