@@ -61,6 +61,16 @@ void pbioEmit(uint8_t *out, const int64_t *out_off, int64_t n_rec, int fmt,
  *   gives 0.0, 0.0, -1, 0.  The (count, length) -> value table is built once per call for the pairs that occur. */
 void pbioScores(const int32_t *records, int64_t n, double *full, double *part, int64_t *read_start, int64_t *read_end);
 
+/* find_start_trim / find_end_trim (nanopore_read.py:166-208) for n reads x n_adapters records (read-major): per read
+ * the largest trim amount over the adapters whose alignment passes `partial > end_threshold`, the end_size / 0 edge
+ * test and `read_end - read_start >= min_trim_size`; 0 when none passes.  is_start selects the start or the end rule. */
+void pbioEndTrim(const int32_t *records, int64_t n, int64_t n_adapters, int is_start, int64_t end_size,
+                 int64_t extra_trim_size, double end_threshold, int64_t min_trim_size, int64_t *trim);
+
+/* out[i, k] = full-adapter identity (as pbioScores) of record (read i, adapter cols[k]): the barcode score columns
+ * (nanopore_read.py:181-183, 203-205) */
+void pbioFullScores(const int32_t *records, int64_t n, int64_t n_adapters, const int64_t *cols, int64_t n_cols, double *out);
+
 #ifdef __cplusplus
 }
 #endif

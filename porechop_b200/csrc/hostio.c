@@ -196,48 +196,106 @@ static double percent_exact(int32_t c, int32_t l)
 
 #define PBIO_TABLE_MAX 2048
 
-void pbioScores(const int32_t *records, int64_t n, double *full, double *part, int64_t *read_start, int64_t *read_end)
+/* value table of percent_exact over the (count, length) pairs that occur in columns ci / li of the records;
+ * t == NULL when the pairs do not fit a dense table (callers then format per record). */
+typedef struct { double *t; int64_t L; } PercentTable;
+
+static void table_build(const int32_t *records, int64_t n, int ci, int li, PercentTable *T)
 {
     int32_t lmax = 0;
     int small = 1;
+    T->t = NULL;
+    T->L = 0;
 #pragma omp parallel for schedule(static) reduction(max : lmax) reduction(& : small)
     for (int64_t i = 0; i < n; ++i) {
         const int32_t *r = records + 9 * i;
-        if (r[5] < 0 || r[6] < 0 || r[7] < 0 || r[8] < 0 || r[5] > r[6] || r[7] > r[8]) small = 0;
-        if (r[6] > lmax) lmax = r[6];
-        if (r[8] > lmax) lmax = r[8];
+        if (r[ci] < 0 || r[li] < 0 || r[ci] > r[li]) small = 0;
+        if (r[li] > lmax) lmax = r[li];
     }
-    double *table = NULL;
-    uint8_t *present = NULL;
+    if (!small || lmax >= PBIO_TABLE_MAX) return;
     const int64_t L = (int64_t)lmax + 1;
-    if (small && lmax < PBIO_TABLE_MAX) {
-        table = (double *)malloc((size_t)(L * L) * sizeof(double));
-        present = (uint8_t *)calloc((size_t)(L * L), 1);
-        if (!table || !present) { free(table); free(present); table = NULL; present = NULL; }
-    }
-    if (table) {
-#pragma omp parallel for schedule(static)
-        for (int64_t i = 0; i < n; ++i) {
-            const int32_t *r = records + 9 * i;
-            present[(int64_t)r[5] * L + r[6]] = 1;          /* benign race: every writer stores 1 */
-            present[(int64_t)r[7] * L + r[8]] = 1;
-        }
-#pragma omp parallel for schedule(dynamic, 64)
-        for (int64_t k = 0; k < L * L; ++k)
-            if (present[k]) table[k] = percent_exact((int32_t)(k / L), (int32_t)(k % L));
-    }
+    double *t = (double *)malloc((size_t)(L * L) * sizeof(double));
+    uint8_t *present = (uint8_t *)calloc((size_t)(L * L), 1);
+    if (!t || !present) { free(t); free(present); return; }
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
         const int32_t *r = records + 9 * i;
-        if (r[0] == -1 && r[4] == INT_MIN) {
+        present[(int64_t)r[ci] * L + r[li]] = 1;            /* benign race: every writer stores 1 */
+    }
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t k = 0; k < L * L; ++k)
+        if (present[k]) t[k] = percent_exact((int32_t)(k / L), (int32_t)(k % L));
+    free(present);
+    T->t = t;
+    T->L = L;
+}
+
+static inline double table_get(const PercentTable *T, int32_t c, int32_t l)
+{
+    return T->t ? T->t[(int64_t)c * T->L + l] : percent_exact(c, l);
+}
+
+static inline int rec_failed(const int32_t *r) { return r[0] == -1 && r[4] == INT_MIN; }
+
+void pbioScores(const int32_t *records, int64_t n, double *full, double *part, int64_t *read_start, int64_t *read_end)
+{
+    PercentTable P, F;
+    table_build(records, n, 5, 6, &P);
+    table_build(records, n, 7, 8, &F);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t *r = records + 9 * i;
+        if (rec_failed(r)) {
             full[i] = 0.0; part[i] = 0.0; read_start[i] = -1; read_end[i] = 0;
             continue;
         }
-        part[i] = table ? table[(int64_t)r[5] * L + r[6]] : percent_exact(r[5], r[6]);
-        full[i] = table ? table[(int64_t)r[7] * L + r[8]] : percent_exact(r[7], r[8]);
+        part[i] = table_get(&P, r[5], r[6]);
+        full[i] = table_get(&F, r[7], r[8]);
         read_start[i] = r[0];
         read_end[i] = (int64_t)r[1] + 1;
     }
-    free(table);
-    free(present);
+    free(P.t);
+    free(F.t);
+}
+
+void pbioEndTrim(const int32_t *records, int64_t n, int64_t n_adapters, int is_start, int64_t end_size,
+                 int64_t extra_trim_size, double end_threshold, int64_t min_trim_size, int64_t *trim)
+{
+    PercentTable P;
+    table_build(records, n * n_adapters, 5, 6, &P);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t best = 0;
+        for (int64_t a = 0; a < n_adapters; ++a) {
+            const int32_t *r = records + 9 * (i * n_adapters + a);
+            const int failed = rec_failed(r);
+            const double part = failed ? 0.0 : table_get(&P, r[5], r[6]);
+            const int64_t rs = failed ? -1 : r[0], re = failed ? 0 : (int64_t)r[1] + 1;
+            if (!(part > end_threshold) || re - rs < min_trim_size) continue;     /* NaN > x is false, as in Python */
+            int64_t amount;
+            if (is_start) {
+                if (re == end_size) continue;
+                amount = re + extra_trim_size;
+            } else {
+                if (rs == 0) continue;
+                amount = (end_size - rs) + extra_trim_size;
+            }
+            if (amount > best) best = amount;
+        }
+        trim[i] = best;
+    }
+    free(P.t);
+}
+
+void pbioFullScores(const int32_t *records, int64_t n, int64_t n_adapters, const int64_t *cols, int64_t n_cols, double *out)
+{
+    PercentTable F;
+    table_build(records, n * n_adapters, 7, 8, &F);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t k = 0; k < n_cols; ++k) {
+            const int32_t *r = records + 9 * (i * n_adapters + cols[k]);
+            out[i * n_cols + k] = rec_failed(r) ? 0.0 : table_get(&F, r[7], r[8]);
+        }
+    free(F.t);
 }

@@ -254,6 +254,8 @@ def end_trim_amounts(start_records, end_records, end_size, extra_trim_size, end_
         n, a = rec.shape[0], rec.shape[1]
         if a == 0 or n == 0:
             return np.zeros(n, dtype=np.int64)
+        if hostio.LIB is not None:                    # one parallel pass in C (libhostio.so), same rule
+            return hostio.end_trim(rec, is_start, end_size, extra_trim_size, end_threshold, min_trim_size)
         _, part, rs, re_ = scores_from_records(rec.reshape(-1, 9))
         part, rs, re_ = part.reshape(n, a), rs.reshape(n, a), re_.reshape(n, a)
         with np.errstate(invalid='ignore'):
@@ -656,6 +658,8 @@ def demux_fastq(data, matching_sets, scoring_scheme_vals, forward_or_reverse='fo
     def full(rec, cols):
         if n == 0 or not cols:
             return np.zeros((n, len(cols)))
+        if hostio.LIB is not None:
+            return hostio.full_scores(rec, cols)
         f, _, _, _ = scores_from_records(rec[:, cols, :].reshape(-1, 9))
         return f.reshape(n, len(cols))
     calls = call_barcodes(full(srec, s_cols), [_barcode_name(*s_sets[j]) for j in s_cols],

@@ -4,12 +4,13 @@
 numpy implementations of the same functions (identical results, much slower on long reads).  This is host I/O only --
 the alignment engine itself has no fallback of any kind."""
 import os
-from ctypes import CDLL, c_int, c_int64, c_void_p
+from ctypes import CDLL, c_double, c_int, c_int64, c_void_p
 
 import numpy as np
 
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libhostio.so')
-EXPORTED_SYMBOLS = ['pbioCountLines', 'pbioLineEnds', 'pbioLineSpans', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit', 'pbioScores']
+EXPORTED_SYMBOLS = ['pbioCountLines', 'pbioLineEnds', 'pbioLineSpans', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit', 'pbioScores', 'pbioEndTrim',
+                    'pbioFullScores']
 
 
 def _load():
@@ -32,6 +33,10 @@ def _load():
     lib.pbioEmit.restype = None
     lib.pbioScores.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.pbioScores.restype = None
+    lib.pbioEndTrim.argtypes = [c_void_p, c_int64, c_int64, c_int, c_int64, c_int64, c_double, c_int64, c_void_p]
+    lib.pbioEndTrim.restype = None
+    lib.pbioFullScores.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]
+    lib.pbioFullScores.restype = None
     return lib
 
 
@@ -112,3 +117,25 @@ def scores(records):
     rs, re_ = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
     LIB.pbioScores(_p(r), n, _p(full), _p(part), _p(rs), _p(re_))
     return full, part, rs, re_
+
+
+def end_trim(records, is_start, end_size, extra_trim_size, end_threshold, min_trim_size):
+    """records int32[n, a, 9] -> int64[n] trim amounts (the start or the end rule of nanopore_read.py:166-208)."""
+    r = np.ascontiguousarray(records, dtype=np.int32)
+    n, a = r.shape[0], r.shape[1]
+    out = np.zeros(n, dtype=np.int64)
+    if n and a:
+        LIB.pbioEndTrim(_p(r), n, a, 1 if is_start else 0, int(end_size), int(extra_trim_size), float(end_threshold),
+                        int(min_trim_size), _p(out))
+    return out
+
+
+def full_scores(records, cols):
+    """records int32[n, a, 9], cols: adapter indices -> float64[n, len(cols)] full-adapter identities."""
+    r = np.ascontiguousarray(records, dtype=np.int32)
+    n, a = r.shape[0], r.shape[1]
+    cols = _i64(cols)
+    out = np.zeros((n, len(cols)), dtype=np.float64)
+    if n and len(cols):
+        LIB.pbioFullScores(_p(r), n, a, _p(cols), len(cols), _p(out))
+    return out

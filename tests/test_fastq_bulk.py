@@ -167,3 +167,31 @@ def test_parse_fasta_multiline_native_and_numpy(monkeypatch):
                 fastq.parse_fasta(bad)
         with pytest.raises(ValueError):
             fastq.parse_reads(b'xyz')
+
+
+def test_end_trim_rule_native_equals_numpy(monkeypatch):
+    """pbioEndTrim / pbioFullScores against the numpy rule on random records that hit every branch: threshold ties,
+    read_end == end_size, read_start == 0, short alignments, 0/0 (NaN) and failed alignments."""
+    from porechop_b200 import fastq, hostio
+    assert hostio.LIB is not None
+    rng = np.random.default_rng(9)
+    n, a = 3000, 7
+    r = np.zeros((n, a, 9), dtype=np.int32)
+    r[..., 0] = rng.integers(0, 150, (n, a)) * (rng.random((n, a)) < 0.8)
+    r[..., 1] = np.minimum(r[..., 0] + rng.integers(0, 40, (n, a)), 149)
+    r[..., 6] = rng.integers(0, 40, (n, a))
+    r[..., 5] = np.minimum((r[..., 6] * rng.choice([0.5, 0.75, 0.8, 1.0], (n, a))).astype(np.int32), r[..., 6])
+    r[..., 8] = rng.integers(1, 30, (n, a))
+    r[..., 7] = (r[..., 8] * rng.random((n, a))).astype(np.int32)
+    fail = rng.random((n, a)) < 0.05
+    r[fail] = [-1, 0, -1, 0, -2147483648, 0, 0, 0, 0]
+    for thr, mts, extra in [(75.0, 4, 2), (80.0, 1, 0), (50.0, 10, 5)]:
+        native = fastq.end_trim_amounts(r, r[:, ::-1], 150, extra, thr, mts)
+        cols = [5, 0, 3]
+        nf = hostio.full_scores(r, cols)
+        monkeypatch.setattr(hostio, 'LIB', None)
+        slow = fastq.end_trim_amounts(r, r[:, ::-1], 150, extra, thr, mts)
+        sf = fastq.scores_from_records(r[:, cols, :].reshape(-1, 9))[0].reshape(n, len(cols))
+        monkeypatch.undo()
+        assert np.array_equal(native[0], slow[0]) and np.array_equal(native[1], slow[1]) and native[0].max() > 0
+        assert np.array_equal(nf, sf, equal_nan=True)
