@@ -71,6 +71,13 @@ void pbioEndTrim(const int32_t *records, int64_t n, int64_t n_adapters, int is_s
  * (nanopore_read.py:181-183, 203-205) */
 void pbioFullScores(const int32_t *records, int64_t n, int64_t n_adapters, const int64_t *cols, int64_t n_cols, double *out);
 
+/* Parallel gzip for the .gz outputs (the reference pipes through `pigz -p threads` or `gzip`, porechop.py:640-650,
+ * 683-690, 724-727): src is cut into `block`-byte pieces, each deflated as its own gzip member by one thread, members
+ * concatenated in order -- a valid .gz whose decompression is src.  dst must hold pbioGzipBound(n, block) bytes.
+ * Returns the compressed size, or -1 (also when the library was built without zlib: pbioGzipBound returns -1). */
+int64_t pbioGzipBound(int64_t n, int64_t block);
+int64_t pbioGzip(const uint8_t *src, int64_t n, int level, int64_t block, uint8_t *dst, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

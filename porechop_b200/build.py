@@ -59,7 +59,10 @@ def build_hostio(force=False):
         return HOSTIO_TARGET
     base = [shutil.which('gcc') or 'gcc', '-O3', '-fPIC', '-shared', '-std=c11', '-Wall', '-Wextra', '-Wno-unknown-pragmas',
             '-o', HOSTIO_TARGET, HOSTIO_DEPS[0]]
-    for cmd in (base[:2] + ['-fopenmp'] + base[2:], base):      # a gcc without libgomp still builds it, single-threaded
+    omp, zl = ['-fopenmp'], ['-DPBIO_HAVE_ZLIB', '-lz']
+    # preferred: OpenMP + zlib; a gcc without libgomp / zlib headers still builds it (single-threaded / Python gzip)
+    for extra_front, extra_back in ((omp, zl), (omp, []), ([], zl), ([], [])):
+        cmd = base[:2] + extra_front + [x for x in extra_back if x.startswith('-D')] + base[2:] + [x for x in extra_back if x.startswith('-l')]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode == 0:
             return HOSTIO_TARGET

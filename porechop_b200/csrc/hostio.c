@@ -299,3 +299,58 @@ void pbioFullScores(const int32_t *records, int64_t n, int64_t n_adapters, const
         }
     free(F.t);
 }
+
+/* ---- parallel gzip: independent members of `block` input bytes each, concatenated (a valid .gz of the whole) ---- */
+#ifdef PBIO_HAVE_ZLIB
+#include <zlib.h>
+
+int64_t pbioGzipBound(int64_t n, int64_t block)
+{
+    if (n <= 0) return 0;
+    if (block < 1024) block = 1024;
+    int64_t nb = (n + block - 1) / block;
+    return nb * ((int64_t)compressBound((uLong)block) + 64);
+}
+
+int64_t pbioGzip(const uint8_t *src, int64_t n, int level, int64_t block, uint8_t *dst, int64_t cap)
+{
+    if (n <= 0) return 0;
+    if (block < 1024) block = 1024;
+    const int64_t nb = (n + block - 1) / block;
+    const int64_t slot = (int64_t)compressBound((uLong)block) + 64;
+    if (cap < nb * slot) return -1;
+    int64_t *sizes = (int64_t *)malloc((size_t)nb * sizeof(int64_t));
+    if (!sizes) return -1;
+    int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(| : bad)
+    for (int64_t b = 0; b < nb; ++b) {
+        z_stream z;
+        memset(&z, 0, sizeof z);
+        sizes[b] = 0;
+        if (deflateInit2(&z, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) { bad |= 1; continue; }
+        int64_t lo = b * block, len = (lo + block <= n) ? block : n - lo;
+        z.next_in = (Bytef *)(src + lo);
+        z.avail_in = (uInt)len;
+        z.next_out = dst + b * slot;
+        z.avail_out = (uInt)slot;
+        if (deflate(&z, Z_FINISH) != Z_STREAM_END) bad |= 1;
+        sizes[b] = (int64_t)z.total_out;
+        deflateEnd(&z);
+    }
+    int64_t pos = 0;
+    if (!bad)
+        for (int64_t b = 0; b < nb; ++b) {              /* pack the members */
+            if (pos != b * slot) memmove(dst + pos, dst + b * slot, (size_t)sizes[b]);
+            pos += sizes[b];
+        }
+    free(sizes);
+    return bad ? -1 : pos;
+}
+#else
+int64_t pbioGzipBound(int64_t n, int64_t block) { (void)n; (void)block; return -1; }
+int64_t pbioGzip(const uint8_t *src, int64_t n, int level, int64_t block, uint8_t *dst, int64_t cap)
+{
+    (void)src; (void)n; (void)level; (void)block; (void)dst; (void)cap;
+    return -1;                                          /* built without zlib: callers use Python's gzip */
+}
+#endif

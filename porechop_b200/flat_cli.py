@@ -22,7 +22,7 @@ import gzip
 import os
 import sys
 
-from . import fastq
+from . import fastq, hostio
 
 
 def _record_chunks(path, chunk_bytes, first_reads):
@@ -87,9 +87,10 @@ def _prefetch(it, depth=2):
 
 class _Sink:
     """one output stream (file, gz file or stdout), opened on first write like the reference's bin files.
-    With world > 1 every rank writes its pieces to `<path>.rank<r>` as self-contained segments (one gzip member per
-    piece for .gz) and remembers (chunk index, offset, length); rank 0 stitches the pieces of all ranks together in
-    chunk order afterwards (`_merge_rank_files`)."""
+    A .gz stream is written as independent gzip members (block-parallel deflate in libhostio.so, or the gzip module):
+    the same bytes after decompression as the reference's `gzip -c` / `pigz`.
+    With world > 1 every rank writes its pieces to `<path>.rank<r>` and remembers (chunk index, offset, length);
+    rank 0 stitches the pieces of all ranks together in chunk order afterwards (`_merge_rank_files`)."""
 
     def __init__(self, path, gz, rank=0, world=1):
         self.final, self.gz, self.f, self.ranked = path, gz, None, world > 1
@@ -100,22 +101,15 @@ class _Sink:
         if not len(payload):
             return
         if self.f is None:
-            if self.final is None:
-                self.f = sys.stdout.buffer
-            elif self.ranked or not self.gz:
-                self.f = open(self.path, 'wb')
-            else:   # gz: same bytes inside as the reference's `gzip -c`, different container timestamp
-                self.f = gzip.open(self.path, 'wb')
-        if not self.ranked:
-            self.f.write(payload)
-            return
-        start = self.f.tell()
+            self.f = sys.stdout.buffer if self.final is None else open(self.path, 'wb')
         if self.gz:
-            with gzip.GzipFile(fileobj=self.f, mode='wb') as g:
-                g.write(payload)
-        else:
-            self.f.write(payload)
-        self.index.append([chunk, start, self.f.tell() - start])
+            level = int(os.environ.get('PB200_GZIP_LEVEL', 6))
+            packed = hostio.gzip_members(payload, level)
+            payload = packed if packed is not None else gzip.compress(bytes(payload), level)
+        start = self.f.tell() if self.ranked else 0
+        self.f.write(payload)
+        if self.ranked:
+            self.index.append([chunk, start, self.f.tell() - start])
 
     def close(self):
         if self.f is not None and self.final is not None:

@@ -10,13 +10,16 @@ import numpy as np
 
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libhostio.so')
 EXPORTED_SYMBOLS = ['pbioCountLines', 'pbioLineEnds', 'pbioLineSpans', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit', 'pbioScores', 'pbioEndTrim',
-                    'pbioFullScores']
+                    'pbioFullScores', 'pbioGzipBound', 'pbioGzip']
 
 
 def _load():
     if not os.path.exists(_PATH) or os.environ.get('PB200_NO_HOSTIO'):
         return None
-    lib = CDLL(_PATH)
+    try:
+        lib = CDLL(_PATH)
+    except OSError:                 # e.g. built against a libgomp / libz this machine lacks: numpy + gzip module instead
+        return None
     lib.pbioCountLines.argtypes = [c_void_p, c_int64]
     lib.pbioCountLines.restype = c_int64
     lib.pbioLineEnds.argtypes = [c_void_p, c_int64, c_void_p, c_int64]
@@ -37,6 +40,10 @@ def _load():
     lib.pbioEndTrim.restype = None
     lib.pbioFullScores.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]
     lib.pbioFullScores.restype = None
+    lib.pbioGzipBound.argtypes = [c_int64, c_int64]
+    lib.pbioGzipBound.restype = c_int64
+    lib.pbioGzip.argtypes = [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64]
+    lib.pbioGzip.restype = c_int64
     return lib
 
 
@@ -139,3 +146,19 @@ def full_scores(records, cols):
     if n and len(cols):
         LIB.pbioFullScores(_p(r), n, a, _p(cols), len(cols), _p(out))
     return out
+
+
+def gzip_members(payload, level=6, block=4 << 20):
+    """payload (bytes-like / uint8 array) -> memoryview of a multi-member .gz of it, compressed block-parallel in C;
+    None when the library has no zlib (the caller then uses Python's gzip)."""
+    if LIB is None:
+        return None
+    src = np.frombuffer(payload, dtype=np.uint8) if not isinstance(payload, np.ndarray) else np.ascontiguousarray(payload)
+    cap = int(LIB.pbioGzipBound(len(src), block))
+    if cap < 0:
+        return None
+    dst = np.empty(cap, dtype=np.uint8)
+    size = int(LIB.pbioGzip(_p(src), len(src), int(level), int(block), _p(dst), cap))
+    if size < 0:
+        return None
+    return memoryview(dst)[:size]

@@ -195,3 +195,16 @@ def test_end_trim_rule_native_equals_numpy(monkeypatch):
         monkeypatch.undo()
         assert np.array_equal(native[0], slow[0]) and np.array_equal(native[1], slow[1]) and native[0].max() > 0
         assert np.array_equal(nf, sf, equal_nan=True)
+
+
+def test_parallel_gzip_members_roundtrip():
+    """pbioGzip: block-parallel multi-member .gz; gunzip gives the input back for sizes around the block boundaries."""
+    import gzip
+    from porechop_b200 import hostio
+    assert hostio.LIB is not None
+    rng = np.random.default_rng(2)
+    for n, block in [(0, 4096), (1, 4096), (4095, 4096), (4096, 4096), (4097, 4096), (100000, 4096), (300000, 1 << 20)]:
+        data = rng.choice(np.frombuffer(b'ACGT5+@\n', dtype=np.uint8), n).tobytes()
+        z = hostio.gzip_members(data, 6, block)
+        assert z is not None and gzip.decompress(bytes(z)) == data
+        assert bytes(z).count(b'\x1f\x8b\x08') >= (n + block - 1) // block
