@@ -20,6 +20,10 @@ extern "C" {
 #define PBIO_ERR_RECORDS 1   /* not a whole number of 4-line records */
 #define PBIO_ERR_HEADER 2    /* a record does not start with '@' (after stripping) */
 
+/* worker threads of the functions below (n <= 0: leave unchanged); returns the current maximum.  torchrun exports
+ * OMP_NUM_THREADS=1 to its workers, so a multi-process run sets cores / local_world_size here instead. */
+int pbioSetThreads(int n);
+
 /* number of lines of buf[0..n): '\n' terminated, plus one if the last byte is not '\n' (misc.py:158 iterates lines) */
 int64_t pbioCountLines(const uint8_t *buf, int64_t n);
 

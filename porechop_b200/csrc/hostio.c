@@ -11,7 +11,22 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
 #define PBIO_BLOCK (1 << 20)
+
+int pbioSetThreads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 static inline int is_ws(uint8_t c)            /* what str.strip() removes from an ASCII line */
 {

@@ -9,7 +9,7 @@ from ctypes import CDLL, c_double, c_int, c_int64, c_void_p
 import numpy as np
 
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libhostio.so')
-EXPORTED_SYMBOLS = ['pbioCountLines', 'pbioLineEnds', 'pbioLineSpans', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit', 'pbioScores', 'pbioEndTrim',
+EXPORTED_SYMBOLS = ['pbioSetThreads', 'pbioCountLines', 'pbioLineEnds', 'pbioLineSpans', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit', 'pbioScores', 'pbioEndTrim',
                     'pbioFullScores', 'pbioGzipBound', 'pbioGzip']
 
 
@@ -20,6 +20,8 @@ def _load():
         lib = CDLL(_PATH)
     except OSError:                 # e.g. built against a libgomp / libz this machine lacks: numpy + gzip module instead
         return None
+    lib.pbioSetThreads.argtypes = [c_int]
+    lib.pbioSetThreads.restype = c_int
     lib.pbioCountLines.argtypes = [c_void_p, c_int64]
     lib.pbioCountLines.restype = c_int64
     lib.pbioLineEnds.argtypes = [c_void_p, c_int64, c_void_p, c_int64]
@@ -162,3 +164,8 @@ def gzip_members(payload, level=6, block=4 << 20):
     if size < 0:
         return None
     return memoryview(dst)[:size]
+
+
+def set_threads(n=0):
+    """set (n > 0) / query the number of worker threads of the C helpers; 1 when the library is absent."""
+    return int(LIB.pbioSetThreads(int(n))) if LIB is not None else 1
