@@ -5,7 +5,7 @@ import random
 import numpy as np
 import pytest
 
-from helpers import DEFAULT, load_golden, oracle_batch, oracle_record
+from helpers import DEFAULT, load_golden, oracle_batch
 from test_oracle import SURVEY_EDGE, rebuild_fullread_inputs
 
 pytestmark = pytest.mark.gpu

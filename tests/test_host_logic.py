@@ -5,7 +5,6 @@ import subprocess
 import tempfile
 
 import numpy as np
-import pytest
 
 from helpers import ROOT, oracle_batch, oracle_string
 

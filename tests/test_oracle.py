@@ -4,7 +4,7 @@ import random
 
 import pytest
 
-from helpers import DEFAULT, abi_string, load_golden, oracle_lib, oracle_record, oracle_string, ref_lib
+from helpers import abi_string, load_golden, oracle_lib, oracle_record, oracle_string, ref_lib
 
 # C-ABI strings captured from the reference build on test/test_one_adapter_set.fastq
 Y_TOP = 'AATGTACTTCGTTCAGTTACGTATTGCT'

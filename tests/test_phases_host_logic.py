@@ -2,7 +2,6 @@
 with the engine call replaced by the oracle -- so the scatter/ordering/masking logic is checked against the reference's
 own Python outputs (tests/golden/golden_phases.json) even without a GPU.  The GPU tier runs the same comparison through
 the real engine (tests/test_gpu_phases.py)."""
-import numpy as np
 import pytest
 
 from helpers import load_golden, oracle_batch
