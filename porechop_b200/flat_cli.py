@@ -256,11 +256,14 @@ def main():
                 chunk += 1
     for batch, albacore_call, chunk in _prefetch(batches()):
         process(batch, albacore_call, chunk)
+    def touch_output():                                   # an empty result is still a file (porechop.py:713-727)
+        with open(args.output, 'wb') as f:
+            f.write(gzip.compress(b'') if gz else b'')
     if world == 1:
-        if args.barcode_dir is None and args.output is not None and None not in sinks:
-            sink(None).f = gzip.open(args.output, 'wb') if gz else open(args.output, 'wb')  # an empty result is still a file
         for s_ in sinks.values():
             s_.close()
+        if args.barcode_dir is None and args.output is not None and (None not in sinks or sinks[None].f is None):
+            touch_output()
         return 0
     import json
     for s_ in sinks.values():
@@ -274,7 +277,7 @@ def main():
         names = sorted({f for fs in finals for f in fs})
         _merge_rank_files(names, world)
         if args.barcode_dir is None and not os.path.exists(args.output):
-            (gzip.open if gz else open)(args.output, 'wb').close()
+            touch_output()
     dist.barrier()
     dist.destroy_process_group()
     return 0

@@ -57,6 +57,8 @@ CASES = [
     ('albacore_dir_bins_opts', 'test_albacore_directory', ['-b', '{out}/bins', '--check_reads', '6', '--barcode_diff', '1',
                                                             '--discard_unassigned']),
     ('albacore_dir_single_out', 'test_albacore_directory', ['-o', '{out}/all.fasta']),
+    ('empty_result_gz', 'INLINE:@only\n\n+\n\n', ['-o', '{out}/o.fastq.gz']),
+    ('empty_result_plain', 'INLINE:@only\n\n+\n\n', ['-o', '{out}/o.fasta']),
     ('synthetic_edges', 'GOLDEN:input_fastq', ['-o', '{out}/o.fastq', '--min_split_read_size', '50']),
     ('synthetic_barcoded', 'GOLDEN:barcoded_fastq', ['-b', '{out}/bins', '--format', 'fasta']),
 ]
@@ -65,10 +67,10 @@ CASES = [
 @pytest.mark.parametrize('name,input_name,argv', CASES, ids=[c[0] for c in CASES])
 def test_flat_cli_writes_the_reference_cli_files(name, input_name, argv, porechop_modules, monkeypatch, tmp_path):  # noqa: F811
     porechop, P, A = porechop_modules
-    if input_name.startswith('GOLDEN:'):
+    if input_name.startswith('GOLDEN:') or input_name.startswith('INLINE:'):
         inp = str(tmp_path / 'in.fastq')
         with open(inp, 'w', newline='') as f:
-            f.write(load_golden('golden_emit.json')[input_name.split(':')[1]])
+            f.write(input_name[7:] if input_name.startswith('INLINE:') else load_golden('golden_emit.json')[input_name.split(':')[1]])
     else:
         inp = os.path.join(REF, 'test', input_name)
 
