@@ -521,6 +521,51 @@ __global__ void rebase_kernel(int64_t *off, int64_t n, int64_t base) {
     if (i < n) off[i] -= base;
 }
 
+// One pipeline chunk of the host-buffer API: sequences [s0, s1), longest sequence max_n.
+struct HostChunk { int64_t s0, s1, max_n; };
+
+// Pure host work done before the device is touched: argument validation (so a bad call fails the same way with or
+// without a device) and the chunk plan of the cross-product pipeline (one pass over the offsets).
+int validate_and_plan(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, const uint8_t *adapters,
+                      const int32_t *ad_off, int32_t n_adapters, const int32_t *pair_seq, const int32_t *pair_adapter,
+                      int64_t n_pairs, bool cross, std::vector<HostChunk> &chunks) {
+    for (int32_t a = 0; a < n_adapters; ++a)
+        if (ad_off[a + 1] < ad_off[a]) return fail(PB200_ERR_ARG, "adapter offsets not monotone");
+    if (n_adapters > 0 && ad_off[0] < 0) return fail(PB200_ERR_ARG, "negative adapter offset");
+    if (n_adapters > 0 && ad_off[n_adapters] > 0 && !adapters) return fail(PB200_ERR_ARG, "NULL adapter buffer");
+    if (n_seqs > 0 && seq_off[n_seqs] > seq_off[0] && !seqs) return fail(PB200_ERR_ARG, "NULL sequence buffer");
+    if (!cross) {
+        if (n_pairs > 0x7fffffffll) return fail(PB200_ERR_ARG, "pair-list mode supports < 2^31 pairs per call");
+        if (n_seqs > 0 && seq_off[0] < 0) return fail(PB200_ERR_ARG, "negative sequence offset");
+        for (int64_t s = 0; s < n_seqs; ++s) {
+            const int64_t len = seq_off[s + 1] - seq_off[s];
+            if (len < 0) return fail(PB200_ERR_ARG, "sequence offsets not monotone");
+            if (len > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
+        }
+        for (int64_t p = 0; p < n_pairs; ++p)
+            if (pair_seq[p] < 0 || pair_seq[p] >= n_seqs || pair_adapter[p] < 0 || pair_adapter[p] >= n_adapters)
+                return fail(PB200_ERR_ARG, "pair index out of range");
+        return 0;
+    }
+    const int64_t max_cnt = std::max<int64_t>(1, g_opt.chunk_tasks / std::max<int32_t>(n_adapters, 1));
+    int64_t s0 = 0;
+    while (s0 < n_seqs) {
+        int64_t s1 = std::min(n_seqs, s0 + max_cnt);
+        // limit bytes per chunk, but keep enough sequences in a chunk to fill the GPU (one wave of slots)
+        while (s1 - s0 > 32768 && seq_off[s1] - seq_off[s0] > g_opt.chunk_bytes) s1 = s0 + std::max<int64_t>(32768, (s1 - s0) / 2);
+        HostChunk c{s0, s1, 0};
+        for (int64_t s = s0; s < s1; ++s) {
+            const int64_t len = seq_off[s + 1] - seq_off[s];
+            if (len < 0) return fail(PB200_ERR_ARG, "sequence offsets not monotone");
+            c.max_n = std::max(c.max_n, len);
+        }
+        if (c.max_n > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
+        chunks.push_back(c);
+        s0 = s1;
+    }
+    return 0;
+}
+
 int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, const uint8_t *adapters,
                const int32_t *ad_off, int32_t n_adapters, const int32_t *pair_seq, const int32_t *pair_adapter,
                int64_t n_pairs, int ma, int mi, int go, int ge, int32_t *out) {
@@ -530,6 +575,10 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
     if (cross && n_pairs != n_seqs * (int64_t)n_adapters) return fail(PB200_ERR_ARG, "cross mode: n_pairs != n_seqs*n_adapters");
     if (n_pairs == 0) return 0;
     if (!seq_off || !ad_off || !out) return fail(PB200_ERR_ARG, "NULL pointer");
+    load_env_options();
+    std::vector<HostChunk> chunks;
+    if (int rc = validate_and_plan(seqs, seq_off, n_seqs, adapters, ad_off, n_adapters, pair_seq, pair_adapter, n_pairs, cross,
+                                   chunks)) return rc;
     Engine *Ep = nullptr;
     if (int rc = get_engine(&Ep)) return rc;
     Engine &E = *Ep;
@@ -544,23 +593,11 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
         CK(cudaMemsetAsync(E.st[i].misc.p, 0, 64, E.st[i].stream));
     }
     if (cross) {
-        // chunk over sequences; ring of NSTAGE streams so H2D / kernels / D2H of consecutive chunks overlap
-        int64_t s0 = 0;
-        int k = 0;
-        int rc_final = 0;
-        while (s0 < n_seqs) {
-            int64_t max_cnt = std::max<int64_t>(1, g_opt.chunk_tasks / std::max<int32_t>(n_adapters, 1));
-            int64_t s1 = std::min(n_seqs, s0 + max_cnt);
-            // limit bytes per chunk
-            // limit bytes per chunk, but keep enough sequences in a chunk to fill the GPU (one wave of slots)
-            while (s1 - s0 > 32768 && seq_off[s1] - seq_off[s0] > g_opt.chunk_bytes) s1 = s0 + std::max<int64_t>(32768, (s1 - s0) / 2);
-            const int64_t cnt = s1 - s0;
+        // ring of NSTAGE streams so H2D / kernels / D2H of consecutive chunks overlap
+        auto submit = [&](const HostChunk &c, Stage &S) -> int {
+            const int64_t s0 = c.s0, cnt = c.s1 - c.s0;
             const int64_t base = seq_off[s0];
-            const int64_t bytes = seq_off[s1] - base;
-            int64_t max_n = 0;
-            for (int64_t s = s0; s < s1; ++s) max_n = std::max(max_n, seq_off[s + 1] - seq_off[s]);
-            if (max_n > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
-            Stage &S = E.st[k % NSTAGE];
+            const int64_t bytes = seq_off[c.s1] - base;
             cudaStream_t stream = S.stream;
             CK(cudaStreamSynchronize(stream));   // previous use of this stage's buffers is complete
             if (int rc = S.seq_raw.ensure((size_t)bytes + 16)) return rc;
@@ -572,26 +609,27 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
             rebase_kernel<<<(unsigned)((cnt + 1 + 255) / 256), 256, 0, stream>>>(S.seq_off.as<int64_t>(), cnt + 1, base);
             g_launches++;
             if (int rc = launch_encode(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
-            if (int rc = run_cross_chunk(E, S, stream, P, S.seq_codes.as<uint8_t>(), S.seq_off.as<int64_t>(), cnt, base, max_n,
+            if (int rc = run_cross_chunk(E, S, stream, P, S.seq_codes.as<uint8_t>(), S.seq_off.as<int64_t>(), cnt, base, c.max_n,
                                          n_adapters, S.out.as<int32_t>(), seq_off, s0, ad_off)) return rc;
             CK(cudaMemcpyAsync(out + (size_t)s0 * n_adapters * PB_REC, S.out.p, (size_t)cnt * n_adapters * PB_REC * 4,
                                cudaMemcpyDeviceToHost, stream));
-            s0 = s1;
-            ++k;
-        }
+            return 0;
+        };
+        int rc_final = 0;
+        for (size_t k = 0; k < chunks.size() && !rc_final; ++k) rc_final = submit(chunks[k], E.st[k % NSTAGE]);
+        // Whatever happened, nothing may still be writing into the caller's `out` (or reading `seqs`) when we return.
+        const std::string first_err = g_err;
         for (int i = 0; i < NSTAGE; ++i) {
-            if (E.st[i].misc.p) { if (int rc = check_status(E.st[i], E.st[i].stream)) rc_final = rc; }
-            CK(cudaStreamSynchronize(E.st[i].stream));
+            if (!rc_final && E.st[i].misc.p) rc_final = check_status(E.st[i], E.st[i].stream);
+            cudaError_t e = cudaStreamSynchronize(E.st[i].stream);
+            if (e != cudaSuccess && !rc_final) rc_final = fail(PB200_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
         }
+        if (rc_final && !first_err.empty()) g_err = first_err;
         return rc_final;
     }
 
     // ---- pair-list mode: all sequences resident, pairs ordered per class on the host ----
-    for (int64_t p = 0; p < n_pairs; ++p) {
-        if (pair_seq[p] < 0 || pair_seq[p] >= n_seqs || pair_adapter[p] < 0 || pair_adapter[p] >= n_adapters)
-            return fail(PB200_ERR_ARG, "pair index out of range");
-    }
-    if (n_pairs > 0x7fffffffll) return fail(PB200_ERR_ARG, "pair-list mode supports < 2^31 pairs per call");
+    auto run_pairs = [&]() -> int {
     Stage &S = E.st[0];
     cudaStream_t stream = S.stream;
     const int64_t bytes = seq_off[n_seqs];
@@ -686,6 +724,14 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
     }
     CK(cudaMemcpyAsync(out, S.out.p, (size_t)n_pairs * PB_REC * 4, cudaMemcpyDeviceToHost, stream));
     return check_status(S, stream);
+    };
+    const int rc_pairs = run_pairs();
+    if (rc_pairs) {                         // nothing may still be reading the caller's buffers when we return
+        const std::string first_err = g_err;
+        cudaStreamSynchronize(E.st[0].stream);
+        g_err = first_err;
+    }
+    return rc_pairs;
 }
 
 int batch_device(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs, int64_t total_seq_bytes,

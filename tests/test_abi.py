@@ -77,6 +77,34 @@ def test_no_device_fails_loudly_no_cpu_fallback():
     assert '100' in str(e.value)
 
 
+def test_invalid_arguments_are_rejected_before_the_device_is_touched():
+    """Argument validation is pure host code (engine.cu validate_and_plan): a bad call fails with PB200_ERR_ARG (102)
+    whether or not a device is present."""
+    from porechop_b200 import cpp_function_wrappers as W
+    sc = [3, -6, -5, -2]
+    buf, off = W.pack_sequences(['ACGTACGT', 'ACGT', 'TTTTTT'])
+    abuf, aoff = W.pack_sequences(['ACGT', 'GG'], offset_dtype=np.int32)
+
+    def err(*a, **k):
+        with pytest.raises(W.EngineError) as e:
+            W.adapter_alignment_batch(*a, **k)
+        return str(e.value)
+
+    bad_off = off.copy(); bad_off[1], bad_off[2] = off[2], off[1]
+    assert 'error 102' in err(buf, bad_off, abuf, aoff, sc) and 'not monotone' in err(buf, bad_off, abuf, aoff, sc)
+    bad_aoff = aoff.copy(); bad_aoff[1] = 7
+    assert 'error 102' in err(buf, off, abuf, bad_aoff, sc)
+    assert 'error 102' in err(buf, off, abuf, aoff, sc, pair_seq=[0, 3], pair_adapter=[0, 1])      # sequence index out of range
+    assert 'error 102' in err(buf, off, abuf, aoff, sc, pair_seq=[0, 1], pair_adapter=[0, -1])
+    assert 'error 102' in err(buf, bad_off, abuf, aoff, sc, pair_seq=[0, 1], pair_adapter=[0, 1])
+    rc = W.C_LIB.adapterAlignmentBatch(None, None, 1, None, None, 1, None, None, 1, 3, -6, -5, -2, None)
+    assert rc == 102                                                                              # NULL pointers
+    rc = W.C_LIB.adapterAlignmentBatch(None, None, 2, None, None, 2, None, None, 3, 3, -6, -5, -2, None)
+    assert rc == 102                                                                              # cross mode: n_pairs != n_seqs*n_adapters
+    if _no_gpu():
+        assert 'error 100' in err(buf, off, abuf, aoff, sc)                                       # valid call: only the device is missing
+
+
 def test_empty_inputs_need_no_device():
     # the -1 record of an empty read/adapter is produced without touching the device (reference: no DP either)
     from porechop_b200 import cpp_function_wrappers as W
