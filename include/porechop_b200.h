@@ -67,6 +67,12 @@ int adapterAlignmentBatchDevice(const uint8_t *d_seqs, const int64_t *d_seq_off,
  * too small (64 bytes always suffice). */
 int pb200FormatRecord(const int32_t *record, char *buf, int buflen);
 
+/* Host-side Dna5 conversion of the packed upload path (option "h2d_pack"): n ASCII bases -> (n+1)/2 bytes, the code
+ * of base 2k (A/a=0 C/c=1 G/g=2 T/t/U/u=3, anything else 4: seqan/basic/alphabet_residue_tabs.h:113-140) in the low
+ * nibble of byte k and base 2k+1 in the high nibble.  Pure host code (AVX2 when the CPU has it, OpenMP; threads <= 0 =
+ * the OpenMP default); exported so that tests and hosts that already hold packed reads can use the same packer. */
+int pb200PackNibbles(const uint8_t *ascii, int64_t n, uint8_t *packed, int threads);
+
 /* ---- device / diagnostics ------------------------------------------------------------------------------ */
 int pb200DeviceCount(void);               /* number of CUDA devices visible (0 if none / no driver) */
 int pb200SetDevice(int device);           /* cudaSetDevice for the calling thread */
@@ -83,7 +89,11 @@ int pb200TimingRead(double *dp_kernel_ms, long long *dp_kernel_launches, double 
  *   "chunk_tasks" alignments per pipeline chunk of the host-buffer API (default 131072)
  *   "scratch_mb"  cap on the resident trace scratch in MB (default 128; 72 keeps it L2-resident)
  *   "hbuf"        staging of a slot's packed bases: "auto" | "smem" | "global"
- *   "rowoff"      1 = score pass in the row-offset arithmetic domain when it fits (default 0; same results) */
+ *   "rowoff"      1 = score pass in the row-offset arithmetic domain when it fits (default 0; same results)
+ *   "h2d_pack"    1 = adapterAlignmentBatch converts the sequences to 4-bit codes on the host cores and uploads half
+ *                 the bytes (default 0; same results; "pack_threads" = host threads of the packer, 0 = OpenMP default)
+ *   "tight_window" 1 = second-pass windows sized per alignment from the end cell's row and score instead of the
+ *                 per-adapter worst case (default 0; same results, fewer traced columns) */
 int pb200SetOption(const char *name, const char *value);
 
 enum {

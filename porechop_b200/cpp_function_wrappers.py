@@ -55,10 +55,12 @@ C_LIB.pb200TimingRead.argtypes = [POINTER(c_double), POINTER(c_longlong), POINTE
 C_LIB.pb200TimingRead.restype = c_int
 C_LIB.pb200SetOption.argtypes = [c_char_p, c_char_p]
 C_LIB.pb200SetOption.restype = c_int
+C_LIB.pb200PackNibbles.argtypes = [c_void_p, c_int64, c_void_p, c_int]
+C_LIB.pb200PackNibbles.restype = c_int
 
 EXPORTED_SYMBOLS = ['adapterAlignment', 'freeCString', 'adapterAlignmentBatch', 'adapterAlignmentBatchDevice',
                     'pb200FormatRecord', 'pb200DeviceCount', 'pb200SetDevice', 'pb200Synchronize', 'pb200LastError',
-                    'pb200KernelLaunches', 'pb200TimingEnable', 'pb200TimingRead', 'pb200SetOption']
+                    'pb200KernelLaunches', 'pb200TimingEnable', 'pb200TimingRead', 'pb200SetOption', 'pb200PackNibbles']
 
 RECORD_INTS = 9
 SCORE_EMPTY = -2147483648
@@ -181,6 +183,14 @@ def timing_read(reset=True):
     ms, n, cells = c_double(0), c_longlong(0), c_double(0)
     _check(C_LIB.pb200TimingRead(ms, n, cells, 1 if reset else 0))
     return ms.value, n.value
+
+
+def pack_nibbles(ascii_buf, threads=0):
+    """uint8 ASCII bases -> uint8[(n+1)//2], two 4-bit Dna5 codes per byte (the host half of option h2d_pack)."""
+    a = np.ascontiguousarray(ascii_buf, dtype=np.uint8)
+    out = np.zeros((len(a) + 1) // 2, dtype=np.uint8)
+    _check(C_LIB.pb200PackNibbles(_ptr(a), len(a), _ptr(out), int(threads)))
+    return out
 
 
 def set_option(name, value):

@@ -72,6 +72,22 @@ PB_HD uint32_t encode_byte(uint32_t c) {
     return code << 4;
 }
 
+// Packed upload path (option h2d_pack): the host converts ASCII to Dna5 codes itself and ships two 4-bit codes per byte
+// (hostpack.cpp: base 2k in the low nibble of byte k, base 2k+1 in the high nibble).  One packed 32-bit word = 8 bases ->
+// the same 8 encoded bytes (code << 4) encode_byte would have produced, as two words in memory order.
+PB_HD void unpack_nibbles8(uint32_t w, uint32_t &first4, uint32_t &next4) {
+    const uint32_t e = (w & 0x0F0F0F0Fu) << 4;      // even bases of the 4 packed bytes, already code << 4
+    const uint32_t o = w & 0xF0F0F0F0u;             // odd bases
+#if defined(__CUDA_ARCH__)
+    first4 = __byte_perm(e, o, 0x5140);
+    next4 = __byte_perm(e, o, 0x7362);
+#else
+    first4 = (e & 0xFFu) | ((o & 0xFFu) << 8) | ((e & 0xFF00u) << 8) | ((o & 0xFF00u) << 16);
+    next4 = ((e >> 16) & 0xFFu) | (((o >> 16) & 0xFFu) << 8) | (((e >> 24) & 0xFFu) << 16) | ((o >> 24) << 24);
+#endif
+}
+PB_HD uint32_t unpack_nibble1(uint32_t packed_byte, int odd) { return odd ? (packed_byte & 0xF0u) : ((packed_byte & 0x0Fu) << 4); }
+
 // ---- packed s16x2 primitives (Blackwell DPX: VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.S16x2 / VIMNMX3) ----
 PB_HD uint32_t add2(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
@@ -185,6 +201,23 @@ enum { TASK_LEFT_INF = 1, TASK_END_GIVEN = 2 };
 struct EndCell {
     int32_t j, i, score, corr;
 };
+
+// Window of the second pass of a long read: how many columns left of its end cell (j*, i*) the traced path can reach.
+// The path has score S* >= 0 and consumes at most i* adapter rows, hence d <= i* diagonals, each worth at most
+// wnum = max(ma, mi, 0); every read-only gap column costs at least wden = min(|go|, |ge|) > 0 and every vertical step
+// costs something, so  S* <= wnum*d - wden*hg  and the path spans  d + hg <= i* + (wnum*i* - S*)/wden  columns -- with
+// strict inequality as soon as it contains a vertical step, which is what lets the -infinity left edge of the window
+// stand in for the real column (DESIGN.md "two-pass scheme").
+//   classic bound (tight == false): i* <= m, S* >= 0  ->  W(m) = m + m*wnum/wden, the same for every alignment of an adapter
+//   tight bound: uses the end cell the score pass found; never larger than the classic one.
+PB_HD int64_t window_cols(int m, int end_i, int end_score, int wnum, int wden, bool tight) {
+    const int64_t wc = (int64_t)m + ((int64_t)m * wnum) / wden;
+    if (!tight) return wc;
+    int64_t num = (int64_t)wnum * end_i - (int64_t)end_score;
+    if (num < 0) num = 0;
+    const int64_t wt = (int64_t)end_i + num / wden;
+    return wt < wc ? wt : wc;
+}
 
 // ---- one lane of a group ------------------------------------------------------------------------------
 // Row layout: the G*R rows of a group are BOTTOM-aligned per half: real adapter row i (1..m) lives at group row

@@ -24,6 +24,9 @@
 
 using namespace pb;
 
+// hostpack.cpp (g++): ASCII -> two 4-bit Dna5 codes per byte on the host cores
+extern "C" void pb_pack_nibbles(const uint8_t *in, int64_t n, uint8_t *out, int threads);
+
 namespace {
 
 thread_local std::string g_err;
@@ -54,6 +57,21 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// pinned host staging memory (packed upload path)
+struct HostBuf {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&p), want, cudaHostAllocDefault);
+        if (e != cudaSuccess) { p = nullptr; return fail(PB200_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+        cap = want;
+        return 0;
+    }
+};
+
 struct Options {
     int64_t direct_max = 512;      // longest sequence aligned in a single (trace) pass
     int64_t chunk_tasks = 1 << 17; // alignments per pipeline chunk (host-buffer API)
@@ -61,6 +79,9 @@ struct Options {
     int64_t chunk_bytes = 64ll << 20;   // sequence bytes per pipeline chunk (host-buffer API)
     int rowoff = 0;                // 1: score pass in the row-offset domain when it fits (measured: no gain)
     int scratch_mb = 128;          // cap on the resident trace scratch (MB); 72 keeps it L2-resident at ~10% lower speed
+    int tight_window = 0;          // 1: second-pass windows sized per alignment from the end cell's row and score (window_cols)
+    int h2d_pack = 0;              // 1: host-buffer API converts to 4-bit codes on the host cores and uploads half the bytes
+    int pack_threads = 0;          // host threads of the packer (0 = OpenMP default)
     int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
 };
 Options g_opt;
@@ -71,6 +92,9 @@ void load_env_options() {
         if (const char *v = getenv("PB200_CHUNK_TASKS")) g_opt.chunk_tasks = std::max(1ll, atoll(v));
         if (const char *v = getenv("PB200_SCRATCH_MB")) g_opt.scratch_mb = std::max(1, atoi(v));
         if (const char *v = getenv("PB200_ROWOFF")) g_opt.rowoff = atoi(v);
+        if (const char *v = getenv("PB200_TIGHT_WINDOW")) g_opt.tight_window = atoi(v);
+        if (const char *v = getenv("PB200_H2D_PACK")) g_opt.h2d_pack = atoi(v);
+        if (const char *v = getenv("PB200_PACK_THREADS")) g_opt.pack_threads = atoi(v);
         if (const char *v = getenv("PB200_HBUF")) g_opt.hbuf_mode = !strcmp(v, "smem") ? 1 : !strcmp(v, "global") ? 2 : 0;
     });
 }
@@ -79,6 +103,7 @@ constexpr int NSTAGE = 3;
 struct Stage {
     cudaStream_t stream = nullptr;
     DevBuf seq_raw, seq_codes, seq_off, tasks, tasks2, ends, out, order, bins, pair_seq, pair_ad, gtrace, misc;
+    HostBuf h_pack;                // pinned staging of the packed upload path
 };
 
 struct ClassPlan {
@@ -300,6 +325,15 @@ int launch_score_class(Engine &E, cudaStream_t stream, int cls, const TaskSrc &t
     return fail(PB200_ERR_INTERNAL, "bad class");
 }
 
+int launch_unpack(cudaStream_t stream, const uint8_t *in, uint8_t *out, int64_t n, int sm_count) {
+    if (n <= 0) return 0;
+    int64_t blocks = std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), (int64_t)sm_count * 16);
+    unpack_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, out, n);
+    g_launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int launch_encode(cudaStream_t stream, const uint8_t *in, uint8_t *out, int64_t n, int sm_count) {
     if (n <= 0) return 0;
     int64_t blocks = std::min<int64_t>((n + 256 * 16 - 1) / (256 * 16), (int64_t)sm_count * 16);
@@ -323,7 +357,7 @@ int run_class_tasks(Engine &E, Stage &S, cudaStream_t stream, int cls, int m_max
     if (int rc = launch_score_class(E, stream, cls, ts, counter, seq_codes, ad_codes, sc, si, m_max, S.ends.as<EndCell>())) return rc;
     {
         int64_t blocks = (n_tasks + 255) / 256;
-        window_tasks_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ts, S.ends.as<EndCell>(), S.tasks2.as<Task>(), si.wnum, si.wden);
+        window_tasks_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ts, S.ends.as<EndCell>(), S.tasks2.as<Task>(), si.wnum, si.wden, g_opt.tight_window);
         g_launches++;
         CK(cudaGetLastError());
     }
@@ -604,11 +638,26 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
             if (int rc = S.seq_codes.ensure((size_t)bytes + 16)) return rc;
             if (int rc = S.seq_off.ensure((size_t)(cnt + 1) * 8)) return rc;
             if (int rc = S.out.ensure((size_t)cnt * n_adapters * PB_REC * 4)) return rc;
-            if (bytes) CK(cudaMemcpyAsync(S.seq_raw.p, seqs + base, (size_t)bytes, cudaMemcpyHostToDevice, stream));
+            const bool packed = g_opt.h2d_pack != 0 && bytes > 0;
+            if (packed) {
+                // Dna5 conversion on the host cores, two codes per byte: half the bytes cross PCIe (the e2e bound).  The
+                // host packs chunk k+1 while the device works on chunk k; the stage's pinned buffer is free again because
+                // the stage's stream was synchronised above.
+                const size_t pbytes = ((size_t)bytes + 1) / 2;
+                if (int rc = S.h_pack.ensure(pbytes)) return rc;
+                pb_pack_nibbles(seqs + base, bytes, S.h_pack.p, g_opt.pack_threads);
+                CK(cudaMemcpyAsync(S.seq_raw.p, S.h_pack.p, pbytes, cudaMemcpyHostToDevice, stream));
+            } else if (bytes) {
+                CK(cudaMemcpyAsync(S.seq_raw.p, seqs + base, (size_t)bytes, cudaMemcpyHostToDevice, stream));
+            }
             CK(cudaMemcpyAsync(S.seq_off.p, seq_off + s0, (size_t)(cnt + 1) * 8, cudaMemcpyHostToDevice, stream));
             rebase_kernel<<<(unsigned)((cnt + 1 + 255) / 256), 256, 0, stream>>>(S.seq_off.as<int64_t>(), cnt + 1, base);
             g_launches++;
-            if (int rc = launch_encode(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
+            if (packed) {
+                if (int rc = launch_unpack(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
+            } else {
+                if (int rc = launch_encode(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
+            }
             if (int rc = run_cross_chunk(E, S, stream, P, S.seq_codes.as<uint8_t>(), S.seq_off.as<int64_t>(), cnt, base, c.max_n,
                                          n_adapters, S.out.as<int32_t>(), seq_off, s0, ad_off)) return rc;
             CK(cudaMemcpyAsync(out + (size_t)s0 * n_adapters * PB_REC, S.out.p, (size_t)cnt * n_adapters * PB_REC * 4,
@@ -815,6 +864,12 @@ int pb200FormatRecord(const int32_t *r, char *buf, int buflen) {
     return (n < 0 || n >= buflen) ? -1 : n;
 }
 
+int pb200PackNibbles(const uint8_t *ascii, int64_t n, uint8_t *packed, int threads) {
+    if (n < 0 || (n > 0 && (!ascii || !packed))) return PB200_ERR_ARG;
+    pb_pack_nibbles(ascii, n, packed, threads);
+    return 0;
+}
+
 char *adapterAlignment(char *readSeq, char *adapterSeq, int ma, int mi, int go, int ge) {
     g_err.clear();
     const int64_t n = readSeq ? (int64_t)strlen(readSeq) : 0;
@@ -900,6 +955,9 @@ int pb200SetOption(const char *name, const char *value) {
     else if (!strcmp(name, "chunk_tasks")) g_opt.chunk_tasks = std::max(1ll, atoll(value));
     else if (!strcmp(name, "scratch_mb")) g_opt.scratch_mb = std::max(1, atoi(value));
     else if (!strcmp(name, "rowoff")) g_opt.rowoff = atoi(value);
+    else if (!strcmp(name, "tight_window")) g_opt.tight_window = atoi(value);
+    else if (!strcmp(name, "h2d_pack")) g_opt.h2d_pack = atoi(value);
+    else if (!strcmp(name, "pack_threads")) g_opt.pack_threads = atoi(value);
     else if (!strcmp(name, "hbuf")) g_opt.hbuf_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;
     else return PB200_ERR_ARG;
     return 0;

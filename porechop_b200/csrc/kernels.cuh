@@ -1,6 +1,7 @@
 // porechop_b200/csrc/kernels.cuh -- sm_100a kernels of the adapter-alignment engine.
 //
 //   encode_kernel        ASCII -> Dna5 code (seqan/basic/alphabet_residue_tabs.h:113-140), HBM-bound
+//   unpack_kernel        host-packed 4-bit codes -> the same code bytes (option h2d_pack)
 //   build_tasks_*        (read, adapter) pairs -> Task records in slot order
 //   trace_kernel<G,R,S>  overlap DP *with* 4-bit trace + in-kernel traceback + statistics (windows)
 //   score_kernel<G,R>    streaming score-only overlap DP with exact scout (long reads), dynamic slot refill
@@ -38,6 +39,24 @@ __global__ void encode_kernel(const uint8_t *__restrict__ in, uint8_t *__restric
             *reinterpret_cast<uint4 *>(out + i) = v;
         } else {
             for (int64_t k = i; k < n && k < i + 16; ++k) out[k] = (uint8_t)encode_byte(in[k]);
+        }
+    }
+}
+
+// unpack (option h2d_pack): 4-bit codes packed by the host (hostpack.cpp) -> the code bytes encode_kernel produces.
+// 8 packed bytes in, 16 bytes out per thread; `n` = number of bases.  HBM-bound, 1.5 B/base of traffic.
+__global__ void unpack_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int64_t n) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 16;
+    for (; i < n; i += stride) {
+        if (i + 16 <= n && ((((uintptr_t)in) & 7) | (((uintptr_t)out) & 15)) == 0) {
+            const uint2 p = *reinterpret_cast<const uint2 *>(in + (i >> 1));
+            uint4 v;
+            unpack_nibbles8(p.x, v.x, v.y);
+            unpack_nibbles8(p.y, v.z, v.w);
+            *reinterpret_cast<uint4 *>(out + i) = v;
+        } else {
+            for (int64_t k = i; k < n && k < i + 16; ++k) out[k] = (uint8_t)unpack_nibble1(in[k >> 1], (int)(k & 1));
         }
     }
 }
@@ -167,16 +186,17 @@ __device__ __forceinline__ Task get_task(const TaskSrc &ts, int64_t idx) {
 
 // Score pass results -> windowed tasks.  The traced path has score >= 0, hence at most m diagonals and
 // floor(m*max(ma,mi,0)/min(|go|,|ge|)) read-only gap columns: it starts no further than `wbound(m)` columns
-// left of its end (DESIGN.md "window bound").  wnum/wden: W = m + (m*wnum)/wden.
+// left of its end (DESIGN.md "window bound").  wnum/wden: W = m + (m*wnum)/wden; `tight` = the per-alignment bound
+// of dp_core.cuh window_cols() that also uses the end cell's row and score.
 __global__ void window_tasks_kernel(const TaskSrc ts, const EndCell *__restrict__ ends, Task *__restrict__ out,
-                                    int wnum, int wden) {
+                                    int wnum, int wden, int tight) {
     const int64_t n_tasks = ts.n_tasks;
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_tasks) return;
     Task t = get_task(ts, k);
     EndCell e = ends[k];
     if (t.n > 0 && t.m > 0) {
-        int64_t W = (int64_t)t.m + ((int64_t)t.m * wnum) / wden;
+        const int64_t W = window_cols(t.m, e.i, e.score, wnum, wden, tight != 0);
         int64_t c0 = (int64_t)e.j - W;
         if (c0 < 0) c0 = 0;
         t.col0 = (int32_t)c0;

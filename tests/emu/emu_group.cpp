@@ -145,9 +145,9 @@ Half make_half(const char *seq, int n, const char *ad, int m, int out_idx) {
 }
 
 // same transformation as window_tasks_kernel (kernels.cuh)
-void to_window(Task &t, const EndCell &e, int wnum, int wden) {
+void to_window(Task &t, const EndCell &e, int wnum, int wden, bool tight) {
     if (t.n > 0 && t.m > 0) {
-        int64_t W = (int64_t)t.m + ((int64_t)t.m * wnum) / wden;
+        int64_t W = window_cols(t.m, e.i, e.score, wnum, wden, tight);
         int64_t c0 = (int64_t)e.j - W;
         if (c0 < 0) c0 = 0;
         t.col0 = (int32_t)c0; t.seq_off += c0; t.n = e.j - (int32_t)c0;
@@ -163,7 +163,7 @@ void to_window(Task &t, const EndCell &e, int wnum, int wden) {
 extern "C" {
 
 // mode 0: single trace pass; mode 1 / 2: score pass (classic / row-offset domain) + windowed trace pass
-// (W = m + m*wnum/wden).
+// (W = m + m*wnum/wden); mode | 4: the windows use the per-alignment bound (dp_core.cuh window_cols, tight).
 // G in {4,8,16,32}, R in {4..8}; pass nB < 0 to leave half B empty.  Returns the status bit (window violated).
 int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char *seqB, int nB, const char *adB, int mB,
                    int G, int R, int mode, int ma, int mi, int go, int ge, int wnum, int wden, int32_t *recA,
@@ -172,6 +172,8 @@ int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char
     Half A = make_half(seqA, nA, adA, mA, 0);
     Half B = nB >= 0 ? make_half(seqB, nB, adB, mB, 1) : make_half("", 0, "", 0, -1);
     int status = 0;
+    const bool tight = (mode & 4) != 0;
+    mode &= 3;
     if (mode >= 1) {
         EndCell eA, eB;
         // mode 1: classic score pass; mode 2: row-offset domain (plain-add diagonal), the engine's default when the
@@ -194,8 +196,8 @@ int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char
                 default: run_score_group<4, false>(G, A, B, so, &eA, &eB); break;
             }
         }
-        to_window(A.t, eA, wnum, wden);
-        if (nB >= 0) to_window(B.t, eB, wnum, wden);
+        to_window(A.t, eA, wnum, wden, tight);
+        if (nB >= 0) to_window(B.t, eB, wnum, wden, tight);
         // the trace pass may use a different (G,R) than the score pass, as in the engine: keep R, G as given
     }
     switch (R) {
@@ -209,5 +211,26 @@ int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char
 }
 
 long emu_range_violations() { return g_range_violations; }
+
+// unpack_kernel (kernels.cuh) run serially: the same per-thread body (16 output bytes from 8 packed bytes through
+// unpack_nibbles8, byte-wise tail through unpack_nibble1) over the whole buffer.
+void emu_unpack(const uint8_t *in, uint8_t *out, int64_t n) {
+    for (int64_t i = 0; i < n; i += 16) {
+        if (i + 16 <= n) {
+            uint32_t p[2], v[4];
+            memcpy(p, in + (i >> 1), 8);
+            unpack_nibbles8(p[0], v[0], v[1]);
+            unpack_nibbles8(p[1], v[2], v[3]);
+            memcpy(out + i, v, 16);
+        } else {
+            for (int64_t k = i; k < n && k < i + 16; ++k) out[k] = (uint8_t)unpack_nibble1(in[k >> 1], (int)(k & 1));
+        }
+    }
+}
+
+// encode_kernel's per-byte mapping, for comparison
+void emu_encode(const uint8_t *in, uint8_t *out, int64_t n) {
+    for (int64_t k = 0; k < n; ++k) out[k] = (uint8_t)encode_byte(in[k]);
+}
 
 }  // extern "C"

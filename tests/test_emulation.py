@@ -99,6 +99,36 @@ def test_emu_random_vs_oracle_all_geometries():
             assert rb == oracle_record(b[0], b[1], sc), (G, R, mode, sc, b)
 
 
+def test_emu_tight_window_bound_vs_oracle():
+    """The per-alignment window bound (dp_core.cuh window_cols, option tight_window): never larger than the classic
+    bound, and the windowed traceback still reproduces the oracle's records -- also for gappy hits whose paths span many
+    read-only columns and for schemes with cheap gaps."""
+    rng = random.Random(99)
+    cheap = [[5, -4, -8, -1], [10, -20, -15, -7], [3, -6, -5, -2], [4, -1, -2, -1], [12, -3, -1, -1], [3, -6, -5, -5]]
+    for it in range(1200):
+        G, R = rng.choice([(4, 5), (4, 6), (4, 7), (4, 8), (8, 8), (16, 6), (32, 7)])
+        sc = rng.choice(cheap)
+        if max(abs(x) for x in sc) * (G * R + 3) > 4000:
+            continue
+        slots = []
+        for _ in range(2):
+            rd, ad = _gen(rng, G * R, 50, 600)
+            if ad and rng.random() < 0.7:           # a gappy copy of the adapter: many read-only gap columns
+                al = sorted(set(rd + ad)) or ['A']
+                ins = []
+                for c in ad:
+                    ins.append(c)
+                    while rng.random() < 0.35:
+                        ins.append(rng.choice(al))
+                p = rng.randint(0, len(rd))
+                rd = rd[:p] + ''.join(ins) + rd[p:]
+            slots.append((rd, ad))
+        st, ra, rb = emu_slot(slots[0], slots[1], G, R, 5, sc)
+        assert st == 0
+        assert ra == oracle_record(slots[0][0], slots[0][1], sc), (G, R, sc, slots[0])
+        assert rb == oracle_record(slots[1][0], slots[1][1], sc), (G, R, sc, slots[1])
+
+
 def test_emu_window_clips_real_adapter_lengths():
     """Two-pass with real adapter lengths (22-111) on multi-kb reads: the window really clips."""
     rng = random.Random(7)

@@ -1,0 +1,84 @@
+"""GPU tier (pytest -m gpu), opt-in engine options added after the round-1 GPU budget was spent -- their arithmetic is
+covered on the CPU tier (tests/test_emulation.py::test_emu_tight_window_bound_vs_oracle,
+tests/test_host_logic.py::test_packed_upload_path_host_pack_and_device_unpack_equal_encode); these tests are their first
+runs on hardware.  Both options are OFF by default and must not change a single record.  The file sorts last on purpose."""
+import random
+
+import numpy as np
+import pytest
+
+from helpers import oracle_batch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def W():
+    from porechop_b200 import cpp_function_wrappers as w
+    assert w.device_count() > 0
+    return w
+
+
+def _with(W, opts, fn):
+    defaults = {'h2d_pack': 0, 'tight_window': 0, 'direct_max': 512, 'chunk_tasks': 131072, 'pack_threads': 0}
+    try:
+        for k, v in opts.items():
+            W.set_option(k, v)
+        return fn()
+    finally:
+        for k in opts:
+            W.set_option(k, defaults[k])
+
+
+def test_packed_upload_windows_ragged_and_long_reads(W):
+    """h2d_pack: Dna5 conversion + 4-bit packing on the host, unpack_kernel on the device -- same records as the oracle
+    for end windows (several pipeline chunks), ragged / non-ACGT / empty inputs and long reads (two-pass path)."""
+    from porechop_b200 import workloads as wl
+    yt, yb = wl.nsk007()
+    _, sw, ew = wl.synth_end_windows(30000, yt, yb, seed=77)
+    sbuf, soff = wl.windows_to_batch(sw)
+    abuf, aoff = wl.pack_adapters([yt, yb])
+    exp = oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
+    for opts in ({'h2d_pack': 1}, {'h2d_pack': 1, 'chunk_tasks': 9000, 'pack_threads': 3}):
+        got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
+        assert np.array_equal(got, exp), opts
+    rng = random.Random(5)
+    reads = ['', 'A', 'N' * 21, '-' * 20, 'acgu' * 10, yt, yt[5:], 'GG' + yt + 'GG', 'ACGT' * 301]
+    reads += [''.join(rng.choice('ACGTNacgtu-*') for _ in range(rng.randint(1, 401))) for _ in range(300)]
+    rbuf, roff = W.pack_sequences(reads)
+    got = _with(W, {'h2d_pack': 1}, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, wl.DEFAULT_SCORING))
+    assert np.array_equal(got, oracle_batch(rbuf, roff, abuf, aoff, wl.DEFAULT_SCORING))
+    lbuf, loff = wl.synth_reads(40, yt, yb, seed=12, chimera_p=0.4, max_len=15000)
+    got = _with(W, {'h2d_pack': 1}, lambda: W.adapter_alignment_batch(lbuf, loff, abuf, aoff, wl.DEFAULT_SCORING))
+    assert np.array_equal(got, oracle_batch(lbuf, loff, abuf, aoff, wl.DEFAULT_SCORING))
+
+
+def test_tight_window_long_reads_and_forced_two_pass_windows(W):
+    """tight_window: second-pass windows sized from the end cell's row and score (dp_core.cuh window_cols).  Long reads
+    with 22 / 28 / 111-nt adapters, a masked re-alignment round, cheap-gap schemes, and 150-column windows forced
+    through the two-pass path (direct_max = 100) -- identical to the oracle, and to the default windows."""
+    from porechop_b200 import workloads as wl
+    yt, yb = wl.nsk007()
+    full = wl.demux_adapters()[0][-1]
+    buf, off = wl.synth_reads(80, yt, yb, seed=41, chimera_p=0.4, max_len=16000)
+    abuf, aoff = wl.pack_adapters([yt, yb, full])
+    for sc in (wl.DEFAULT_SCORING, (5, -4, -8, -1), (3, -6, -5, -5)):
+        exp = oracle_batch(buf, off, abuf, aoff, sc)
+        got = _with(W, {'tight_window': 1}, lambda: W.adapter_alignment_batch(buf, off, abuf, aoff, sc))
+        assert np.array_equal(got, exp), sc
+    masked = buf.copy()
+    recs = exp.reshape(80, 3, 9)
+    for r in range(80):
+        rs, re_ = recs[r, 0, 0], recs[r, 0, 1] + 1
+        if rs >= 0:
+            masked[off[r] + rs: off[r] + re_] = ord('-')
+    got = _with(W, {'tight_window': 1}, lambda: W.adapter_alignment_batch(masked, off, abuf, aoff, (3, -6, -5, -5)))
+    assert np.array_equal(got, oracle_batch(masked, off, abuf, aoff, (3, -6, -5, -5)))
+    _, sw, ew = wl.synth_end_windows(20000, yt, yb, seed=9)
+    for win, ad in ((sw, yt), (ew, yb)):
+        sbuf, soff = wl.windows_to_batch(win)
+        a1, o1 = wl.pack_adapters([ad])
+        exp = oracle_batch(sbuf, soff, a1, o1, wl.DEFAULT_SCORING)
+        for opts in ({'direct_max': 100}, {'direct_max': 100, 'tight_window': 1}):
+            got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, a1, o1, wl.DEFAULT_SCORING))
+            assert np.array_equal(got, exp), opts

@@ -120,3 +120,36 @@ def test_bench_parity_gate_against_harness_answers():
     assert bench.parity_gate(recs, answers, W.format_record) == {'checked': 300, 'mismatches': 0}
     recs[1][3, 1] += 1
     assert bench.parity_gate(recs, answers, W.format_record) == {'checked': 300, 'mismatches': 1}
+
+
+def test_packed_upload_path_host_pack_and_device_unpack_equal_encode():
+    """Option h2d_pack: pb200PackNibbles (hostpack.cpp, AVX2 + scalar tail, any thread count) followed by the device's
+    unpack arithmetic (dp_core.cuh unpack_nibbles8 / unpack_nibble1, run on the host by tests/emu) gives exactly the
+    code bytes of encode_byte -- for every byte value, every length around the SIMD / work-item boundaries, odd lengths."""
+    import ctypes
+    from helpers import emu_lib
+    from porechop_b200 import cpp_function_wrappers as W
+    emu = emu_lib()
+    emu.emu_unpack.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    emu.emu_encode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    emu.emu_unpack.restype = emu.emu_encode.restype = None
+    rng = np.random.default_rng(11)
+    every = np.arange(256, dtype=np.uint8)
+    cases = [every, every[::-1].copy(), np.zeros(0, dtype=np.uint8)]
+    for n in [1, 2, 3, 15, 16, 17, 31, 32, 33, 63, 64, 65, 1000, 65535, 65536, 65537, 3 * 65536 + 5, 1 << 20]:
+        kind = rng.integers(0, 3)
+        if kind == 0:
+            a = rng.integers(0, 256, n).astype(np.uint8)
+        else:
+            a = np.frombuffer(b'ACGTUacgtuNn-*', dtype=np.uint8)[rng.integers(0, 14, n)]
+        cases.append(np.ascontiguousarray(a))
+    for a in cases:
+        n = len(a)
+        exp = np.zeros(n, dtype=np.uint8)
+        emu.emu_encode(a.ctypes.data, exp.ctypes.data, n)
+        for threads in (1, 3, 0):
+            pk = W.pack_nibbles(a, threads)
+            assert len(pk) == (n + 1) // 2
+            got = np.zeros(n, dtype=np.uint8)
+            emu.emu_unpack(pk.ctypes.data, got.ctypes.data, n)
+            assert np.array_equal(got, exp), (n, threads)
