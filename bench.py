@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument('--reads', type=int, default=0, help='reads per rank (default: 1M endtrim, 32k demux, 256k middle)')
     ap.add_argument('--cpu-sample-reads', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-multi', action='store_true',
+                    help="e2e: the step's batches in ONE adapterAlignmentBatchMulti submit instead of one call per batch")
+    ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE',
+                    help='engine option for this run (pb200SetOption), e.g. --opt h2d_pack=1 --opt tight_window=1')
     return ap.parse_args()
 
 
@@ -241,6 +245,9 @@ def main():
 
     n, batches, desc = make_workload(args, rank)
     K, Wm = args.steps, args.warmup
+    for kv in args.opt:
+        name, _, val = kv.partition('=')
+        W.set_option(name, val)
 
     # ---- host (pinned) and device copies of the inputs ----
     host, dev = [], []
@@ -281,6 +288,10 @@ def main():
     def step_e2e():
         # every rank pushes its own shard through the host-buffer C-ABI over its own PCIe link; the records stay
         # rank-local (no data-path collective, prompt (5)); the optional re-gather to a writer rank is timed separately
+        if args.e2e_multi:
+            W.adapter_alignment_batch_multi([(hb.numpy(), ho.numpy(), abuf, aoff, hout.numpy()) for hb, ho, abuf, aoff, hout in host],
+                                            scoring)
+            return
         for hb, ho, abuf, aoff, hout in host:
             W.adapter_alignment_batch(hb.numpy(), ho.numpy(), abuf, aoff, scoring, out=hout.numpy())
 
@@ -381,7 +392,9 @@ def main():
                    'l2': 'inputs %.0f MB per step exceed the 126 MB L2' % (in_bytes / 1e6)},
         'e2e': {'value': e2e_value, 'unit': 'reads/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': out_bytes,
                 'ms_per_step': e2e_ms / K, 'gcups': cells_per_step * world * K / (e2e_ms / 1e3) / 1e9,
-                'path': 'adapterAlignmentBatch (host buffers, pinned), one call per batch per rank; records stay rank-local',
+                'path': ('adapterAlignmentBatchMulti (host buffers, pinned), one submit per step per rank' if args.e2e_multi else
+                         'adapterAlignmentBatch (host buffers, pinned), one call per batch per rank') + '; records stay rank-local',
+                'options': args.opt,
                 'gather_records_to_rank0_ms': gather_ms},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

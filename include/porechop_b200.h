@@ -52,6 +52,20 @@ int adapterAlignmentBatch(const uint8_t *seqs, const int64_t *seq_off, int64_t n
                           const int32_t *pair_adapter, int64_t n_pairs, int matchScore, int mismatchScore,
                           int gapOpenScore, int gapExtensionScore, int32_t *out);
 
+/* Several independent cross-product batches in ONE submit -- e.g. the two batches of Porechop's end-trim phase
+ * (find_start_trim: start windows x start adapters, find_end_trim: end windows x end adapters,
+ * porechop/nanopore_read.py:166-208) -- pipelined through the same ring of streams, so the upload of the second batch
+ * overlaps the kernels of the first and the copy pipeline fills and drains once per submit instead of once per batch.
+ * Each batch has the cross-product semantics of adapterAlignmentBatch (records in sequence-major order in its own
+ * `out`); batches with no sequences or no adapters are skipped.  Same scoring scheme for all batches. */
+typedef struct {
+    const uint8_t *seqs; const int64_t *seq_off; int64_t n_seqs;        /* as in adapterAlignmentBatch */
+    const uint8_t *adapters; const int32_t *ad_off; int32_t n_adapters;
+    int32_t *out;                                                       /* n_seqs * n_adapters * 9 int32 */
+} pb200_batch_t;
+int adapterAlignmentBatchMulti(const pb200_batch_t *batches, int n_batches, int matchScore, int mismatchScore,
+                               int gapOpenScore, int gapExtensionScore);
+
 /* Same, with the bulk data already resident in device memory (d_seqs, d_seq_off, d_out are device pointers on
  * the current device; adapters/ad_off stay host pointers -- a few KB).  Cross-product mode only.
  * max_seq_len: length of the longest sequence, or -1 to let the library compute it on the device.

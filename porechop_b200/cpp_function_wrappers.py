@@ -12,7 +12,7 @@ There is no CPU fallback: if cpp_functions.so is missing the import exits like t
 
 import os
 import sys
-from ctypes import CDLL, POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_longlong, c_void_p, cast, \
+from ctypes import CDLL, POINTER, Structure, c_char_p, c_double, c_int, c_int32, c_int64, c_longlong, c_void_p, cast, \
     create_string_buffer
 
 import numpy as np
@@ -38,6 +38,16 @@ C_LIB.freeCString.restype = None
 C_LIB.adapterAlignmentBatch.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                         c_int64, c_int, c_int, c_int, c_int, c_void_p]
 C_LIB.adapterAlignmentBatch.restype = c_int
+
+
+class BatchDesc(Structure):
+    """pb200_batch_t (include/porechop_b200.h)"""
+    _fields_ = [('seqs', c_void_p), ('seq_off', c_void_p), ('n_seqs', c_int64),
+                ('adapters', c_void_p), ('ad_off', c_void_p), ('n_adapters', c_int32), ('out', c_void_p)]
+
+
+C_LIB.adapterAlignmentBatchMulti.argtypes = [POINTER(BatchDesc), c_int, c_int, c_int, c_int, c_int]
+C_LIB.adapterAlignmentBatchMulti.restype = c_int
 C_LIB.adapterAlignmentBatchDevice.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                               c_int32, c_int, c_int, c_int, c_int, c_void_p, c_void_p]
 C_LIB.adapterAlignmentBatchDevice.restype = c_int
@@ -58,7 +68,8 @@ C_LIB.pb200SetOption.restype = c_int
 C_LIB.pb200PackNibbles.argtypes = [c_void_p, c_int64, c_void_p, c_int]
 C_LIB.pb200PackNibbles.restype = c_int
 
-EXPORTED_SYMBOLS = ['adapterAlignment', 'freeCString', 'adapterAlignmentBatch', 'adapterAlignmentBatchDevice',
+EXPORTED_SYMBOLS = ['adapterAlignment', 'freeCString', 'adapterAlignmentBatch', 'adapterAlignmentBatchMulti',
+                    'adapterAlignmentBatchDevice',
                     'pb200FormatRecord', 'pb200DeviceCount', 'pb200SetDevice', 'pb200Synchronize', 'pb200LastError',
                     'pb200KernelLaunches', 'pb200TimingEnable', 'pb200TimingRead', 'pb200SetOption', 'pb200PackNibbles']
 
@@ -140,6 +151,30 @@ def adapter_alignment_batch(seq_buf, seq_off, ad_buf, ad_off, scoring_scheme_val
     _check(C_LIB.adapterAlignmentBatch(_ptr(seq_buf), _ptr(seq_off), n_seqs, _ptr(ad_buf), _ptr(ad_off), n_ad,
                                        _ptr(pair_seq), _ptr(pair_adapter), n_pairs, ma, mi, go, ge, _ptr(out)))
     return out
+
+
+def adapter_alignment_batch_multi(batches, scoring_scheme_vals):
+    """
+    Several cross-product batches in one submit (adapterAlignmentBatchMulti): `batches` is a list of
+    (seq_buf, seq_off, ad_buf, ad_off) or (seq_buf, seq_off, ad_buf, ad_off, out) tuples with the array conventions of
+    adapter_alignment_batch.  Returns the list of int32[n_seqs * n_adapters, 9] record arrays, one per batch.
+    """
+    descs = (BatchDesc * max(len(batches), 1))()
+    keep, outs = [], []
+    for k, b in enumerate(batches):
+        seq_buf = np.ascontiguousarray(b[0], dtype=np.uint8)
+        seq_off = np.ascontiguousarray(b[1], dtype=np.int64)
+        ad_buf = np.ascontiguousarray(b[2], dtype=np.uint8)
+        ad_off = np.ascontiguousarray(b[3], dtype=np.int32)
+        n_seqs, n_ad = len(seq_off) - 1, len(ad_off) - 1
+        out = b[4] if len(b) > 4 and b[4] is not None else np.empty((n_seqs * n_ad, RECORD_INTS), dtype=np.int32)
+        keep.append((seq_buf, seq_off, ad_buf, ad_off, out))
+        outs.append(out)
+        descs[k] = BatchDesc(seq_buf.ctypes.data, seq_off.ctypes.data, n_seqs, ad_buf.ctypes.data, ad_off.ctypes.data, n_ad,
+                             out.ctypes.data)
+    ma, mi, go, ge = [int(x) for x in scoring_scheme_vals]
+    _check(C_LIB.adapterAlignmentBatchMulti(descs, len(batches), ma, mi, go, ge))
+    return outs
 
 
 def adapter_alignment_batch_device(d_seqs_ptr, d_seq_off_ptr, n_seqs, total_seq_bytes, max_seq_len, ad_buf, ad_off,

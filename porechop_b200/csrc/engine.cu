@@ -600,6 +600,80 @@ int validate_and_plan(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seq
     return 0;
 }
 
+// One cross-product job of the host-buffer API (all sequences x all adapters of one call / one batch of a multi call).
+struct CrossJob {
+    const uint8_t *seqs; const int64_t *seq_off; int64_t n_seqs;
+    const uint8_t *adapters; const int32_t *ad_off; int32_t n_adapters;
+    int32_t *out;
+    std::vector<HostChunk> chunks;
+};
+
+// Chunks of every job flow through ONE ring of NSTAGE streams (H2D / kernels / D2H of consecutive chunks overlap, also
+// across job boundaries: no fill / drain bubble between the start-window and the end-window batch of an end-trim step).
+// Caller holds E.mu and has run E.init().
+int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int go, int ge) {
+    for (int i = 0; i < NSTAGE; ++i) {
+        if (int rc = E.st[i].misc.ensure(64)) return rc;
+        CK(cudaMemsetAsync(E.st[i].misc.p, 0, 64, E.st[i].stream));
+    }
+    auto submit = [&](const CrossJob &J, const AdapterPlan &P, const HostChunk &c, Stage &S) -> int {
+        const int64_t s0 = c.s0, cnt = c.s1 - c.s0;
+        const int64_t base = J.seq_off[s0];
+        const int64_t bytes = J.seq_off[c.s1] - base;
+        cudaStream_t stream = S.stream;
+        CK(cudaStreamSynchronize(stream));   // previous use of this stage's buffers is complete
+        if (int rc = S.seq_raw.ensure((size_t)bytes + 16)) return rc;
+        if (int rc = S.seq_codes.ensure((size_t)bytes + 16)) return rc;
+        if (int rc = S.seq_off.ensure((size_t)(cnt + 1) * 8)) return rc;
+        if (int rc = S.out.ensure((size_t)cnt * J.n_adapters * PB_REC * 4)) return rc;
+        const bool packed = g_opt.h2d_pack != 0 && bytes > 0;
+        if (packed) {
+            // Dna5 conversion on the host cores, two codes per byte: half the bytes cross PCIe (the e2e bound).  The
+            // host packs chunk k+1 while the device works on chunk k; the stage's pinned buffer is free again because
+            // the stage's stream was synchronised above.
+            const size_t pbytes = ((size_t)bytes + 1) / 2;
+            if (int rc = S.h_pack.ensure(pbytes)) return rc;
+            pb_pack_nibbles(J.seqs + base, bytes, S.h_pack.p, g_opt.pack_threads);
+            CK(cudaMemcpyAsync(S.seq_raw.p, S.h_pack.p, pbytes, cudaMemcpyHostToDevice, stream));
+        } else if (bytes) {
+            CK(cudaMemcpyAsync(S.seq_raw.p, J.seqs + base, (size_t)bytes, cudaMemcpyHostToDevice, stream));
+        }
+        CK(cudaMemcpyAsync(S.seq_off.p, J.seq_off + s0, (size_t)(cnt + 1) * 8, cudaMemcpyHostToDevice, stream));
+        rebase_kernel<<<(unsigned)((cnt + 1 + 255) / 256), 256, 0, stream>>>(S.seq_off.as<int64_t>(), cnt + 1, base);
+        g_launches++;
+        if (packed) {
+            if (int rc = launch_unpack(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
+        } else {
+            if (int rc = launch_encode(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
+        }
+        if (int rc = run_cross_chunk(E, S, stream, P, S.seq_codes.as<uint8_t>(), S.seq_off.as<int64_t>(), cnt, base, c.max_n,
+                                     J.n_adapters, S.out.as<int32_t>(), J.seq_off, s0, J.ad_off)) return rc;
+        CK(cudaMemcpyAsync(J.out + (size_t)s0 * J.n_adapters * PB_REC, S.out.p, (size_t)cnt * J.n_adapters * PB_REC * 4,
+                           cudaMemcpyDeviceToHost, stream));
+        return 0;
+    };
+    int rc_final = 0;
+    size_t k = 0;
+    for (size_t j = 0; j < jobs.size() && !rc_final; ++j) {
+        const CrossJob &J = jobs[j];
+        if (J.chunks.empty()) continue;
+        // The adapter plan is made (or found in the 4-entry cache) right before the job's first chunk: a miss waits for the
+        // device to go idle before it recycles an entry, so chunks of earlier jobs never lose their adapter copies.
+        AdapterPlan P;
+        rc_final = plan_adapters(E, E.st[k % NSTAGE].stream, J.adapters, J.ad_off, J.n_adapters, ma, mi, go, ge, P);
+        for (size_t c = 0; c < J.chunks.size() && !rc_final; ++c, ++k) rc_final = submit(J, P, J.chunks[c], E.st[k % NSTAGE]);
+    }
+    // Whatever happened, nothing may still be writing into the caller's `out` (or reading `seqs`) when we return.
+    const std::string first_err = g_err;
+    for (int i = 0; i < NSTAGE; ++i) {
+        if (!rc_final && E.st[i].misc.p) rc_final = check_status(E.st[i], E.st[i].stream);
+        cudaError_t e = cudaStreamSynchronize(E.st[i].stream);
+        if (e != cudaSuccess && !rc_final) rc_final = fail(PB200_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    }
+    if (rc_final && !first_err.empty()) g_err = first_err;
+    return rc_final;
+}
+
 int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, const uint8_t *adapters,
                const int32_t *ad_off, int32_t n_adapters, const int32_t *pair_seq, const int32_t *pair_adapter,
                int64_t n_pairs, int ma, int mi, int go, int ge, int32_t *out) {
@@ -610,71 +684,22 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
     if (n_pairs == 0) return 0;
     if (!seq_off || !ad_off || !out) return fail(PB200_ERR_ARG, "NULL pointer");
     load_env_options();
-    std::vector<HostChunk> chunks;
+    std::vector<CrossJob> jobs(1);
+    jobs[0] = CrossJob{seqs, seq_off, n_seqs, adapters, ad_off, n_adapters, out, {}};
     if (int rc = validate_and_plan(seqs, seq_off, n_seqs, adapters, ad_off, n_adapters, pair_seq, pair_adapter, n_pairs, cross,
-                                   chunks)) return rc;
+                                   jobs[0].chunks)) return rc;
     Engine *Ep = nullptr;
     if (int rc = get_engine(&Ep)) return rc;
     Engine &E = *Ep;
     std::lock_guard<std::mutex> lk(E.mu);
     if (int rc = E.init()) return rc;
+    if (cross) return run_cross_jobs(E, jobs, ma, mi, go, ge);
 
     AdapterPlan P;
     if (int rc = plan_adapters(E, E.st[0].stream, adapters, ad_off, n_adapters, ma, mi, go, ge, P)) return rc;
-
     for (int i = 0; i < NSTAGE; ++i) {
         if (int rc = E.st[i].misc.ensure(64)) return rc;
         CK(cudaMemsetAsync(E.st[i].misc.p, 0, 64, E.st[i].stream));
-    }
-    if (cross) {
-        // ring of NSTAGE streams so H2D / kernels / D2H of consecutive chunks overlap
-        auto submit = [&](const HostChunk &c, Stage &S) -> int {
-            const int64_t s0 = c.s0, cnt = c.s1 - c.s0;
-            const int64_t base = seq_off[s0];
-            const int64_t bytes = seq_off[c.s1] - base;
-            cudaStream_t stream = S.stream;
-            CK(cudaStreamSynchronize(stream));   // previous use of this stage's buffers is complete
-            if (int rc = S.seq_raw.ensure((size_t)bytes + 16)) return rc;
-            if (int rc = S.seq_codes.ensure((size_t)bytes + 16)) return rc;
-            if (int rc = S.seq_off.ensure((size_t)(cnt + 1) * 8)) return rc;
-            if (int rc = S.out.ensure((size_t)cnt * n_adapters * PB_REC * 4)) return rc;
-            const bool packed = g_opt.h2d_pack != 0 && bytes > 0;
-            if (packed) {
-                // Dna5 conversion on the host cores, two codes per byte: half the bytes cross PCIe (the e2e bound).  The
-                // host packs chunk k+1 while the device works on chunk k; the stage's pinned buffer is free again because
-                // the stage's stream was synchronised above.
-                const size_t pbytes = ((size_t)bytes + 1) / 2;
-                if (int rc = S.h_pack.ensure(pbytes)) return rc;
-                pb_pack_nibbles(seqs + base, bytes, S.h_pack.p, g_opt.pack_threads);
-                CK(cudaMemcpyAsync(S.seq_raw.p, S.h_pack.p, pbytes, cudaMemcpyHostToDevice, stream));
-            } else if (bytes) {
-                CK(cudaMemcpyAsync(S.seq_raw.p, seqs + base, (size_t)bytes, cudaMemcpyHostToDevice, stream));
-            }
-            CK(cudaMemcpyAsync(S.seq_off.p, seq_off + s0, (size_t)(cnt + 1) * 8, cudaMemcpyHostToDevice, stream));
-            rebase_kernel<<<(unsigned)((cnt + 1 + 255) / 256), 256, 0, stream>>>(S.seq_off.as<int64_t>(), cnt + 1, base);
-            g_launches++;
-            if (packed) {
-                if (int rc = launch_unpack(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
-            } else {
-                if (int rc = launch_encode(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
-            }
-            if (int rc = run_cross_chunk(E, S, stream, P, S.seq_codes.as<uint8_t>(), S.seq_off.as<int64_t>(), cnt, base, c.max_n,
-                                         n_adapters, S.out.as<int32_t>(), seq_off, s0, ad_off)) return rc;
-            CK(cudaMemcpyAsync(out + (size_t)s0 * n_adapters * PB_REC, S.out.p, (size_t)cnt * n_adapters * PB_REC * 4,
-                               cudaMemcpyDeviceToHost, stream));
-            return 0;
-        };
-        int rc_final = 0;
-        for (size_t k = 0; k < chunks.size() && !rc_final; ++k) rc_final = submit(chunks[k], E.st[k % NSTAGE]);
-        // Whatever happened, nothing may still be writing into the caller's `out` (or reading `seqs`) when we return.
-        const std::string first_err = g_err;
-        for (int i = 0; i < NSTAGE; ++i) {
-            if (!rc_final && E.st[i].misc.p) rc_final = check_status(E.st[i], E.st[i].stream);
-            cudaError_t e = cudaStreamSynchronize(E.st[i].stream);
-            if (e != cudaSuccess && !rc_final) rc_final = fail(PB200_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
-        }
-        if (rc_final && !first_err.empty()) g_err = first_err;
-        return rc_final;
     }
 
     // ---- pair-list mode: all sequences resident, pairs ordered per class on the host ----
@@ -783,6 +808,28 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
     return rc_pairs;
 }
 
+int batch_host_multi(const pb200_batch_t *batches, int n_batches, int ma, int mi, int go, int ge) {
+    if (n_batches < 0 || (n_batches > 0 && !batches)) return fail(PB200_ERR_ARG, "bad batch list");
+    load_env_options();
+    std::vector<CrossJob> jobs;
+    for (int b = 0; b < n_batches; ++b) {
+        const pb200_batch_t &B = batches[b];
+        if (B.n_seqs < 0 || B.n_adapters < 0) return fail(PB200_ERR_ARG, "negative count");
+        if (B.n_seqs == 0 || B.n_adapters == 0) continue;
+        if (!B.seq_off || !B.ad_off || !B.out) return fail(PB200_ERR_ARG, "NULL pointer");
+        jobs.push_back(CrossJob{B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, B.out, {}});
+        if (int rc = validate_and_plan(B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, nullptr, nullptr,
+                                       B.n_seqs * (int64_t)B.n_adapters, true, jobs.back().chunks)) return rc;
+    }
+    if (jobs.empty()) return 0;
+    Engine *Ep = nullptr;
+    if (int rc = get_engine(&Ep)) return rc;
+    Engine &E = *Ep;
+    std::lock_guard<std::mutex> lk(E.mu);
+    if (int rc = E.init()) return rc;
+    return run_cross_jobs(E, jobs, ma, mi, go, ge);
+}
+
 int batch_device(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs, int64_t total_seq_bytes,
                  int64_t max_seq_len, const uint8_t *adapters, const int32_t *ad_off, int32_t n_adapters, int ma, int mi,
                  int go, int ge, int32_t *d_out, void *user_stream) {
@@ -841,6 +888,11 @@ int adapterAlignmentBatch(const uint8_t *seqs, const int64_t *seq_off, int64_t n
                           const int32_t *pair_adapter, int64_t n_pairs, int ma, int mi, int go, int ge, int32_t *out) {
     g_err.clear();
     return batch_host(seqs, seq_off, n_seqs, adapters, ad_off, n_adapters, pair_seq, pair_adapter, n_pairs, ma, mi, go, ge, out);
+}
+
+int adapterAlignmentBatchMulti(const pb200_batch_t *batches, int n_batches, int ma, int mi, int go, int ge) {
+    g_err.clear();
+    return batch_host_multi(batches, n_batches, ma, mi, go, ge);
 }
 
 int adapterAlignmentBatchDevice(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs, int64_t total_seq_bytes,

@@ -103,6 +103,17 @@ def test_invalid_arguments_are_rejected_before_the_device_is_touched():
     assert rc == 102                                                                              # cross mode: n_pairs != n_seqs*n_adapters
     if _no_gpu():
         assert 'error 100' in err(buf, off, abuf, aoff, sc)                                       # valid call: only the device is missing
+    # the multi-batch submit validates every batch the same way
+    with pytest.raises(W.EngineError) as e:
+        W.adapter_alignment_batch_multi([(buf, off, abuf, aoff), (buf, bad_off, abuf, aoff)], sc)
+    assert 'error 102' in str(e.value)
+    assert W.adapter_alignment_batch_multi([], sc) == []
+    empty = W.adapter_alignment_batch_multi([(buf[:0], off[:1], abuf, aoff)], sc)                 # no sequences: nothing to do
+    assert len(empty) == 1 and empty[0].shape == (0, 9)
+    if _no_gpu():
+        with pytest.raises(W.EngineError) as e:
+            W.adapter_alignment_batch_multi([(buf, off, abuf, aoff), (buf, off, abuf, aoff)], sc)
+        assert 'error 100' in str(e.value)
 
 
 def test_empty_inputs_need_no_device():

@@ -82,3 +82,34 @@ def test_tight_window_long_reads_and_forced_two_pass_windows(W):
         for opts in ({'direct_max': 100}, {'direct_max': 100, 'tight_window': 1}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, a1, o1, wl.DEFAULT_SCORING))
             assert np.array_equal(got, exp), opts
+
+
+def test_multi_batch_submit_equals_single_calls(W):
+    """adapterAlignmentBatchMulti: several cross-product batches through one ring of streams -- same records as one
+    adapterAlignmentBatch call per batch (and the oracle); more distinct adapter lists than the 4-entry plan cache;
+    batches of very different sizes; an empty batch in the middle."""
+    from porechop_b200 import workloads as wl
+    yt, yb = wl.nsk007()
+    starts, ends = wl.demux_adapters()
+    _, sw, ew = wl.synth_end_windows(150000, yt, yb, seed=3)
+    _, sw2, ew2 = wl.synth_end_windows(700, starts[7], ends[7], seed=4)
+    lbuf, loff = wl.synth_reads(24, yt, yb, seed=6, chimera_p=0.5, max_len=9000)
+    batches = [wl.windows_to_batch(sw) + wl.pack_adapters([yt]),
+               wl.windows_to_batch(ew) + wl.pack_adapters([yb]),
+               wl.windows_to_batch(sw2) + wl.pack_adapters(starts[:40]),
+               (np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64)) + wl.pack_adapters([yt]),
+               wl.windows_to_batch(ew2) + wl.pack_adapters(ends[:33]),
+               (lbuf, loff) + wl.pack_adapters([yt, yb]),
+               wl.windows_to_batch(sw2) + wl.pack_adapters(starts[40:47])]
+    got = W.adapter_alignment_batch_multi(batches, wl.DEFAULT_SCORING)
+    assert len(got) == len(batches)
+    for b, g in zip(batches, got):
+        single = W.adapter_alignment_batch(b[0], b[1], b[2], b[3], wl.DEFAULT_SCORING)
+        assert np.array_equal(g, single)
+    for k in (1, 2, 4, 5, 6):
+        b = batches[k]
+        assert np.array_equal(got[k], oracle_batch(b[0], b[1], b[2], b[3], wl.DEFAULT_SCORING)), k
+    # all options together
+    got2 = _with(W, {'h2d_pack': 1, 'tight_window': 1}, lambda: W.adapter_alignment_batch_multi(batches, wl.DEFAULT_SCORING))
+    for a, b in zip(got, got2):
+        assert np.array_equal(a, b)
