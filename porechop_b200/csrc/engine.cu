@@ -79,6 +79,7 @@ struct Options {
     int64_t chunk_bytes = 64ll << 20;   // sequence bytes per pipeline chunk (host-buffer API)
     int rowoff = 0;                // 1: score pass in the row-offset domain when it fits (measured: no gain)
     int scratch_mb = 128;          // cap on the resident trace scratch (MB); 72 keeps it L2-resident at ~10% lower speed
+    int short2p = 0;               // 1: short sequences (<= direct_max) also go score pass -> bounded window (score-only trace_kernel)
     int tight_window = 0;          // 1: second-pass windows sized per alignment from the end cell's row and score (window_cols)
     int h2d_pack = 0;              // 1: host-buffer API converts to 4-bit codes on the host cores and uploads half the bytes
     int pack_threads = 0;          // host threads of the packer (0 = OpenMP default)
@@ -94,6 +95,7 @@ void load_env_options() {
         if (const char *v = getenv("PB200_ROWOFF")) g_opt.rowoff = atoi(v);
         if (const char *v = getenv("PB200_TIGHT_WINDOW")) g_opt.tight_window = atoi(v);
         if (const char *v = getenv("PB200_H2D_PACK")) g_opt.h2d_pack = atoi(v);
+        if (const char *v = getenv("PB200_SHORT2P")) g_opt.short2p = atoi(v);
         if (const char *v = getenv("PB200_PACK_THREADS")) g_opt.pack_threads = atoi(v);
         if (const char *v = getenv("PB200_HBUF")) g_opt.hbuf_mode = !strcmp(v, "smem") ? 1 : !strcmp(v, "global") ? 2 : 0;
     });
@@ -215,21 +217,23 @@ void timed_end(Engine &E, cudaStream_t s, TimedLaunch &tl, bool on) {
     if (on) { cudaEventRecord(tl.b, s); E.timed.push_back(tl); }
 }
 
-template <int G, int R, bool HS>
+template <int G, int R, bool HS, bool SO = false>
 int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, int max_n,
-                         const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
+                         const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status,
+                         EndCell *ends = nullptr) {
     constexpr int SPW = 32 / G;
     constexpr int WPS = TraceWords<R>::value;
     const int max_steps = max_n + G - 1;
     const int wpb = PB_WARPS_PER_BLOCK;
     const size_t smem_bytes = (size_t)wpb * ((HS ? (size_t)SPW * max_n : 0) + PB_SCRATCH_WORDS) * 4;
-    auto kern = trace_kernel<G, R, HS>;
+    auto kern = trace_kernel<G, R, HS, SO>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int bps = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem_bytes));
     if (bps < 1) bps = 1;
-    const size_t gwarp_bytes = ((size_t)((max_steps + PB_TCHUNK - 1) / PB_TCHUNK) * PB_TCHUNK * WPS * 32 +
-                                (HS ? 0 : (((size_t)SPW * max_n + 3) & ~(size_t)3))) * 4;
+    // (the score-only variant writes no trace: no scratch, the grid is bounded by the occupancy alone)
+    const size_t gwarp_bytes = SO ? 0 : ((size_t)((max_steps + PB_TCHUNK - 1) / PB_TCHUNK) * PB_TCHUNK * WPS * 32 +
+                                         (HS ? 0 : (((size_t)SPW * max_n + 3) & ~(size_t)3))) * 4;
     // The trace scratch of the resident grid is rewritten slot after slot and mostly lives in L2.  `scratch_mb` caps
     // it (whole blocks per SM, never below 2): measured on B200 for 150x28 windows, 72 MB (3 blocks/SM) keeps the
     // trace L2-resident (DRAM traffic 1.9x the algorithmic bytes) at ~10 % lower kernel throughput than the default
@@ -242,24 +246,37 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc
     const int64_t n_wslots = (n_slots + SPW - 1) / SPW;
     int64_t blocks = (n_wslots + wpb - 1) / wpb;
     blocks = std::min<int64_t>(blocks, std::min<int64_t>((int64_t)bps * E.sm_count, max_blocks));
-    if ((size_t)blocks * wpb * gwarp_bytes > (24ull << 30)) blocks = std::max<int64_t>(1, (int64_t)((24ull << 30) / (gwarp_bytes * wpb)));
+    if (!SO && (size_t)blocks * wpb * gwarp_bytes > (24ull << 30)) blocks = std::max<int64_t>(1, (int64_t)((24ull << 30) / (gwarp_bytes * wpb)));
     if (blocks <= 0) return 0;
-    if (int rc = S.gtrace.ensure((size_t)blocks * wpb * gwarp_bytes)) return rc;
+    if (!SO) { if (int rc = S.gtrace.ensure((size_t)blocks * wpb * gwarp_bytes)) return rc; }
     TimedLaunch tl; bool on;
     timed_begin(E, stream, tl, on);
     kern<<<(unsigned)blocks, wpb * 32, smem_bytes, stream>>>(ts, seq_codes, ad_codes, sc, out,
-                                                              S.gtrace.as<uint32_t>(), max_steps, max_n, status);
+                                                              SO ? nullptr : S.gtrace.as<uint32_t>(), max_steps, max_n, status, ends);
     timed_end(E, stream, tl, on);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
+// does a slot's staging of packed bases fit shared memory (the only staging the score-only variant has)?
+template <int G>
+bool hbuf_fits_smem(const Engine &E, int max_n) {
+    constexpr int SPW = 32 / G;
+    return (size_t)SPW * max_n * 4 <= 12288 &&
+           (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + PB_SCRATCH_WORDS) * 4 <= E.smem_optin;
+}
+
 template <int G, int R>
 int launch_trace(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, int max_n,
-                 const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
+                 const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status,
+                 EndCell *ends) {
     constexpr int SPW = 32 / G;
     if (max_n < 1) max_n = 1;
+    if (ends) {                                   // score-only first pass of the short two-pass scheme
+        if (!hbuf_fits_smem<G>(E, max_n)) return fail(PB200_ERR_INTERNAL, "score-only pass needs shared-memory staging");
+        return launch_trace_variant<G, R, true, true>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
+    }
     // packed read bases of a slot are staged in shared memory when they fit (<= 12 KB per warp), else in global scratch
     const bool hs = g_opt.hbuf_mode == 1 ? true : g_opt.hbuf_mode == 2 ? false : ((size_t)SPW * max_n * 4 <= 12288);
     if (hs && (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + PB_SCRATCH_WORDS) * 4 <= E.smem_optin)
@@ -267,9 +284,11 @@ int launch_trace(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, in
     return launch_trace_variant<G, R, false>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
 }
 
+// ends != nullptr: score-only pass writing the end cells instead of records (out may be nullptr)
 int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const TaskSrc &ts, int max_n,
-                       const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
-#define PB_CASE(K, GG, RR) case K: return launch_trace<GG, RR>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
+                       const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status,
+                       EndCell *ends = nullptr) {
+#define PB_CASE(K, GG, RR) case K: return launch_trace<GG, RR>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
     switch (cls) {
         PB_CASE(0, 4, 5) PB_CASE(1, 4, 6) PB_CASE(2, 4, 7) PB_CASE(3, 4, 8)
         PB_CASE(4, 8, 5) PB_CASE(5, 8, 6) PB_CASE(6, 8, 7) PB_CASE(7, 8, 8)
@@ -278,6 +297,15 @@ int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const 
     }
 #undef PB_CASE
     return fail(PB200_ERR_INTERNAL, "bad class");
+}
+bool class_hbuf_fits_smem(const Engine &E, int cls, int max_n) {
+    switch (cls / 4) {
+        case 0: return hbuf_fits_smem<4>(E, max_n);
+        case 1: return hbuf_fits_smem<8>(E, max_n);
+        case 2: return hbuf_fits_smem<16>(E, max_n);
+        case 3: return hbuf_fits_smem<32>(E, max_n);
+    }
+    return false;
 }
 
 template <int G, int R, bool RO>
@@ -351,10 +379,20 @@ int run_class_tasks(Engine &E, Stage &S, cudaStream_t stream, int cls, int m_max
     if (n_tasks <= 0) return 0;
     int64_t W = si.bounded ? (int64_t)m_max + ((int64_t)m_max * si.wnum) / si.wden : (int64_t)1 << 40;
     const bool two_pass = si.bounded && max_n > g_opt.direct_max && W + 1 < max_n;
-    if (!two_pass) return launch_trace_class(E, S, stream, cls, ts, (int)max_n, seq_codes, ad_codes, sc, out, status);
+    // Short two-pass (option "short2p"): windows that would take the single trace pass are first swept score-only by the
+    // same slot loop (7 instead of 18 instructions per row, no trace traffic), then only the bounded window left of each
+    // end cell is traced.  Worth it when the traced window is clearly shorter than the sequence.
+    const bool short2p = !two_pass && g_opt.short2p != 0 && si.bounded && W + 8 < max_n &&
+                         class_hbuf_fits_smem(E, cls, (int)max_n);
+    if (!two_pass && !short2p) return launch_trace_class(E, S, stream, cls, ts, (int)max_n, seq_codes, ad_codes, sc, out, status);
     if (int rc = S.ends.ensure((size_t)n_tasks * sizeof(EndCell))) return rc;
     if (int rc = S.tasks2.ensure((size_t)n_tasks * sizeof(Task))) return rc;
-    if (int rc = launch_score_class(E, stream, cls, ts, counter, seq_codes, ad_codes, sc, si, m_max, S.ends.as<EndCell>())) return rc;
+    if (short2p) {
+        if (int rc = launch_trace_class(E, S, stream, cls, ts, (int)max_n, seq_codes, ad_codes, sc, nullptr, status,
+                                        S.ends.as<EndCell>())) return rc;
+    } else {
+        if (int rc = launch_score_class(E, stream, cls, ts, counter, seq_codes, ad_codes, sc, si, m_max, S.ends.as<EndCell>())) return rc;
+    }
     {
         int64_t blocks = (n_tasks + 255) / 256;
         window_tasks_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ts, S.ends.as<EndCell>(), S.tasks2.as<Task>(), si.wnum, si.wden, g_opt.tight_window);
@@ -1009,6 +1047,7 @@ int pb200SetOption(const char *name, const char *value) {
     else if (!strcmp(name, "rowoff")) g_opt.rowoff = atoi(value);
     else if (!strcmp(name, "tight_window")) g_opt.tight_window = atoi(value);
     else if (!strcmp(name, "h2d_pack")) g_opt.h2d_pack = atoi(value);
+    else if (!strcmp(name, "short2p")) g_opt.short2p = atoi(value);
     else if (!strcmp(name, "pack_threads")) g_opt.pack_threads = atoi(value);
     else if (!strcmp(name, "hbuf")) g_opt.hbuf_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;
     else return PB200_ERR_ARG;

@@ -223,11 +223,17 @@ __device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
 // Forward wavefront with a 4-bit trace per cell (two 32-bit words per lane per step), then traceback + statistics
 // by two lanes of the group, 9-int record per alignment.  Grid-stride over "warp slots" so the trace scratch is
 // bounded by the resident grid and stays in L2.
-template <int G, int R, bool HBUF_SMEM>
+//
+// SCORE_ONLY = the same slot loop without the trace: the forward pass runs the 7-instruction score cell, nothing is
+// written to the scratch, and instead of the traceback the group's scout result goes to `ends` -- the first pass of the
+// short two-pass scheme (option "short2p": end cells first, then only the bounded window left of each end cell is
+// traced; engine.cu run_class_tasks).  Requires HBUF_SMEM (no global scratch is allocated).
+template <int G, int R, bool HBUF_SMEM, bool SCORE_ONLY = false>
 __global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_TRACE_MIN_BLOCKS)
 trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
              const uint8_t *__restrict__ ads, Scoring sc, int32_t *__restrict__ out, uint32_t *__restrict__ gtrace,
-             int max_steps, int max_n, int *__restrict__ status) {
+             int max_steps, int max_n, int *__restrict__ status, EndCell *__restrict__ ends) {
+    static_assert(!SCORE_ONLY || HBUF_SMEM, "the score-only variant has no global scratch");
     constexpr int SPW = 32 / G;
     constexpr int WPS = TraceWords<R>::value;
     extern __shared__ uint32_t smem[];
@@ -301,11 +307,13 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                     uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
                     if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
                     const int j = t0 + u - g + 1;
-                    lane_step<R, true, false>(L, recvS, recvV, hbuf[j - 1], sc, buf[u]);
+                    lane_step<R, !SCORE_ONLY, false>(L, recvS, recvV, hbuf[j - 1], sc, buf[u]);
                     if (need_track) lane_track_lastrow<R>(L, j, sc);
                 }
+                if (!SCORE_ONLY) {
 #pragma unroll
-                for (int w = 0; w < WPS; ++w) acc[w] = make_uint4(buf[0][w], buf[1][w], buf[2][w], buf[3][w]);
+                    for (int w = 0; w < WPS; ++w) acc[w] = make_uint4(buf[0][w], buf[1][w], buf[2][w], buf[3][w]);
+                }
             } else {
 #pragma unroll
                 for (int w = 0; w < WPS; ++w) acc[w] = make_uint4(0u, 0u, 0u, 0u);
@@ -321,7 +329,7 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                     for (int w = 0; w < WPS; ++w) tw[w] = 0u;
                     if (j >= 1 && j <= nmax) {
                         uint32_t vr[R];
-                        lane_step<R, true, true>(L, recvS, recvV, hbuf[j - 1], sc, tw, vr);
+                        lane_step<R, !SCORE_ONLY, true>(L, recvS, recvV, hbuf[j - 1], sc, tw, vr);
                         if (need_track) {
                             if (j >= nmin) lane_track_general<R>(L, g, j, make_geom(nA, mA, G, R), make_geom(nB, mB, G, R), vr, sc);
                             else lane_track_lastrow<R>(L, j, sc);
@@ -333,14 +341,26 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                     }
                 }
             }
+            if (!SCORE_ONLY) {
 #pragma unroll
-            for (int w = 0; w < WPS; ++w)
-                *reinterpret_cast<uint4 *>(tr + (((size_t)(t0 / PB_TCHUNK) * WPS + w) * 32 + lane) * PB_TCHUNK) = acc[w];
+                for (int w = 0; w < WPS; ++w)
+                    *reinterpret_cast<uint4 *>(tr + (((size_t)(t0 / PB_TCHUNK) * WPS + w) * 32 + lane) * PB_TCHUNK) = acc[w];
+            }
         }
         // scout candidates -> shared scratch, then lanes g==0 / g==1 finish halves A / B
         cand[lane] = make_cand<R>(L, 0, sc);
         cand[32 + lane] = make_cand<R>(L, 1, sc);
         __syncwarp();
+        if (SCORE_ONLY) {
+            // first pass of the short two-pass scheme: the end cells of the slot's two alignments
+            if (g < 2) {
+                const int64_t ti = slot * 2 + g;
+                if (ti < n_tasks)
+                    ends[ti] = scout_combine(cand + g * 32 + grp * G, G, g ? make_geom(nB, mB, G, R) : make_geom(nA, mA, G, R));
+            }
+            __syncwarp();
+            continue;
+        }
 #ifndef PB_EXPERIMENT_SKIP_TRACEBACK   // (profiling experiments only: measure the forward pass alone)
         if (g < 2) {
             const int h = g;

@@ -20,7 +20,7 @@ def W():
 
 
 def _with(W, opts, fn):
-    defaults = {'h2d_pack': 0, 'tight_window': 0, 'direct_max': 512, 'chunk_tasks': 131072, 'pack_threads': 0}
+    defaults = {'h2d_pack': 0, 'tight_window': 0, 'short2p': 0, 'direct_max': 512, 'chunk_tasks': 131072, 'pack_threads': 0}
     try:
         for k, v in opts.items():
             W.set_option(k, v)
@@ -113,3 +113,39 @@ def test_multi_batch_submit_equals_single_calls(W):
     got2 = _with(W, {'h2d_pack': 1, 'tight_window': 1}, lambda: W.adapter_alignment_batch_multi(batches, wl.DEFAULT_SCORING))
     for a, b in zip(got, got2):
         assert np.array_equal(a, b)
+
+
+def test_short_two_pass_windows_equal_oracle(W):
+    """short2p: 150-column windows go score-only sweep (trace_kernel<.., SCORE_ONLY>) -> bounded windows -> trace pass.
+    End-trim windows, the demux cross product (all 356 adapters: every row-capacity class, paired and odd adapters),
+    ragged / empty / non-ACGT inputs, classic and per-alignment (tight) windows, several scoring schemes."""
+    from porechop_b200 import workloads as wl
+    yt, yb = wl.nsk007()
+    _, sw, ew = wl.synth_end_windows(40000, yt, yb, seed=19)
+    for win, ad in ((sw, yt), (ew, yb)):
+        sbuf, soff = wl.windows_to_batch(win)
+        a1, o1 = wl.pack_adapters([ad])
+        exp = oracle_batch(sbuf, soff, a1, o1, wl.DEFAULT_SCORING)
+        for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}):
+            got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, a1, o1, wl.DEFAULT_SCORING))
+            assert np.array_equal(got, exp), opts
+    starts, ends = wl.demux_adapters()
+    _, sw, ew = wl.synth_end_windows(200, starts[5], ends[5], seed=6)
+    for win, ads in ((sw, starts), (ew, ends)):
+        sbuf, soff = wl.windows_to_batch(win)
+        abuf, aoff = wl.pack_adapters(ads)
+        exp = oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
+        got = _with(W, {'short2p': 1, 'tight_window': 1},
+                    lambda: W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
+        assert np.array_equal(got, exp)
+    rng = random.Random(17)
+    reads = ['', 'A', 'N' * 120, '-' * 130, 'acgu' * 40, yt, 'GG' + yt + 'GG', 'ACGT' * 100]
+    reads += [''.join(rng.choice('ACGTN') for _ in range(rng.randint(1, 500))) for _ in range(300)]
+    ads = ['', 'A', yt, yb, 'ACGT' * 10, 'N' * 5, 'ACGT' * 30]
+    rbuf, roff = W.pack_sequences(reads)
+    abuf, aoff = W.pack_sequences(ads, offset_dtype=np.int32)
+    for sc in ([3, -6, -5, -2], [3, -6, -5, -5], [5, -4, -8, -1]):
+        exp = oracle_batch(rbuf, roff, abuf, aoff, sc)
+        for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}):
+            got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
+            assert np.array_equal(got, exp), (sc, opts)
