@@ -66,6 +66,37 @@ typedef struct {
 int adapterAlignmentBatchMulti(const pb200_batch_t *batches, int n_batches, int matchScore, int mismatchScore,
                                int gapOpenScore, int gapExtensionScore);
 
+/* End-trim DECISIONS on the device.  Each batch is one cross product of read-end windows x
+ * adapters (as in adapterAlignmentBatchMulti); the 9-int records stay on the device and a second kernel reduces them per
+ * read to what Porechop's host logic consumes:
+ *   trim[s]         find_start_trim / find_end_trim (porechop/nanopore_read.py:166-208): the largest trim amount over the
+ *                   adapters whose alignment passes `aligned-region identity > end_threshold`, the end_size / 0 edge test
+ *                   and `read_end - read_start >= min_trim_size`; 0 when none passes
+ *   score_pairs     for every adapter index listed in score_cols (the barcode adapters, nanopore_read.py:181-183,
+ *                   203-205): (matchAdapter, lenAdapter) as two uint16 -- full-adapter identity =
+ *                   float("%f" % (100.0 * matchAdapter / lenAdapter)) on the host; a failed alignment gives (0, 1) = 0.0
+ * so 4 + 4*n_score_cols bytes per read come back instead of 36 per alignment.  The identity test is exact: the host
+ * builds, with the reference's own snprintf("%f") / strtod chain, the smallest passing match count per aligned length
+ * (pb200TrimThresholdTable) and the kernel compares integers.  end_threshold must be >= 0.  batch.out may be NULL (records
+ * not copied back) or a buffer for the full records. */
+typedef struct {
+    pb200_batch_t batch;
+    int32_t is_start;                 /* 1 = find_start_trim rule (start windows), 0 = find_end_trim rule (end windows) */
+    int32_t end_size;                 /* --end_size (porechop.py:130), the window length the edge tests refer to */
+    int32_t extra_trim_size;          /* --extra_end_trim */
+    int32_t min_trim_size;            /* --min_trim_size */
+    double end_threshold;             /* --end_threshold */
+    const int32_t *score_cols;        /* adapter indices whose full-adapter identity is wanted (may be NULL if none) */
+    int32_t n_score_cols;
+    int32_t *trim;                    /* out: n_seqs */
+    uint16_t *score_pairs;            /* out: n_seqs * n_score_cols * 2 */
+} pb200_end_batch_t;
+int adapterEndDecisions(const pb200_end_batch_t *batches, int n_batches, int matchScore, int mismatchScore,
+                        int gapOpenScore, int gapExtensionScore);
+/* cmin[l], l = 0 .. len-1: the smallest match count c for which float("%f" % (100.0*c/l)) > end_threshold, or l+1 if
+ * none does (cmin[0] = INT32_MAX: 0/0 is NaN and never passes).  Pure host code. */
+int pb200TrimThresholdTable(double end_threshold, int32_t len, int32_t *cmin);
+
 /* Same, with the bulk data already resident in device memory (d_seqs, d_seq_off, d_out are device pointers on
  * the current device; adapters/ad_off stay host pointers -- a few KB).  Cross-product mode only.
  * max_seq_len: length of the longest sequence, or -1 to let the library compute it on the device.

@@ -46,6 +46,17 @@ class BatchDesc(Structure):
                 ('adapters', c_void_p), ('ad_off', c_void_p), ('n_adapters', c_int32), ('out', c_void_p)]
 
 
+class EndBatchDesc(Structure):
+    """pb200_end_batch_t (include/porechop_b200.h)"""
+    _fields_ = [('batch', BatchDesc), ('is_start', c_int32), ('end_size', c_int32), ('extra_trim_size', c_int32),
+                ('min_trim_size', c_int32), ('end_threshold', c_double), ('score_cols', c_void_p), ('n_score_cols', c_int32),
+                ('trim', c_void_p), ('score_pairs', c_void_p)]
+
+
+C_LIB.adapterEndDecisions.argtypes = [POINTER(EndBatchDesc), c_int, c_int, c_int, c_int, c_int]
+C_LIB.adapterEndDecisions.restype = c_int
+C_LIB.pb200TrimThresholdTable.argtypes = [c_double, c_int32, c_void_p]
+C_LIB.pb200TrimThresholdTable.restype = c_int
 C_LIB.adapterAlignmentBatchMulti.argtypes = [POINTER(BatchDesc), c_int, c_int, c_int, c_int, c_int]
 C_LIB.adapterAlignmentBatchMulti.restype = c_int
 C_LIB.adapterAlignmentBatchDevice.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
@@ -69,7 +80,7 @@ C_LIB.pb200PackNibbles.argtypes = [c_void_p, c_int64, c_void_p, c_int]
 C_LIB.pb200PackNibbles.restype = c_int
 
 EXPORTED_SYMBOLS = ['adapterAlignment', 'freeCString', 'adapterAlignmentBatch', 'adapterAlignmentBatchMulti',
-                    'adapterAlignmentBatchDevice',
+                    'adapterAlignmentBatchDevice', 'adapterEndDecisions', 'pb200TrimThresholdTable',
                     'pb200FormatRecord', 'pb200DeviceCount', 'pb200SetDevice', 'pb200Synchronize', 'pb200LastError',
                     'pb200KernelLaunches', 'pb200TimingEnable', 'pb200TimingRead', 'pb200SetOption', 'pb200PackNibbles']
 
@@ -175,6 +186,47 @@ def adapter_alignment_batch_multi(batches, scoring_scheme_vals):
     ma, mi, go, ge = [int(x) for x in scoring_scheme_vals]
     _check(C_LIB.adapterAlignmentBatchMulti(descs, len(batches), ma, mi, go, ge))
     return outs
+
+
+def adapter_end_decisions(batches, scoring_scheme_vals, end_size, extra_trim_size, end_threshold, min_trim_size,
+                          want_records=False):
+    """
+    End-trim decisions on the device (adapterEndDecisions): `batches` is a list of
+    (seq_buf, seq_off, ad_buf, ad_off, is_start, score_cols) -- windows x adapters, which trim rule, and the adapter
+    indices whose full-adapter identity the host still needs (barcode columns; may be empty).
+    Returns one (trim int32[n], pairs uint16[n, n_cols, 2], records or None) per batch.
+    """
+    descs = (EndBatchDesc * max(len(batches), 1))()
+    keep, outs = [], []
+    for k, b in enumerate(batches):
+        seq_buf = np.ascontiguousarray(b[0], dtype=np.uint8)
+        seq_off = np.ascontiguousarray(b[1], dtype=np.int64)
+        ad_buf = np.ascontiguousarray(b[2], dtype=np.uint8)
+        ad_off = np.ascontiguousarray(b[3], dtype=np.int32)
+        cols = np.ascontiguousarray(b[5] if b[5] is not None else [], dtype=np.int32)
+        n_seqs, n_ad = len(seq_off) - 1, len(ad_off) - 1
+        trim = np.zeros(n_seqs, dtype=np.int32)
+        pairs = np.zeros((n_seqs, len(cols), 2), dtype=np.uint16)
+        rec = np.empty((n_seqs * n_ad, RECORD_INTS), dtype=np.int32) if want_records else None
+        keep.append((seq_buf, seq_off, ad_buf, ad_off, cols))
+        outs.append((trim, pairs, rec))
+        descs[k] = EndBatchDesc(BatchDesc(seq_buf.ctypes.data, seq_off.ctypes.data, n_seqs, ad_buf.ctypes.data,
+                                          ad_off.ctypes.data, n_ad, rec.ctypes.data if rec is not None else None),
+                                1 if b[4] else 0, int(end_size), int(extra_trim_size), int(min_trim_size), float(end_threshold),
+                                cols.ctypes.data if len(cols) else None, len(cols), trim.ctypes.data,
+                                pairs.ctypes.data if len(cols) else None)
+    ma, mi, go, ge = [int(x) for x in scoring_scheme_vals]
+    _check(C_LIB.adapterEndDecisions(descs, len(batches), ma, mi, go, ge))
+    return outs
+
+
+def trim_threshold_table(end_threshold, length):
+    """cmin[l] of pb200TrimThresholdTable: smallest match count whose float("%f") identity exceeds end_threshold."""
+    t = np.zeros(length, dtype=np.int32)
+    rc = C_LIB.pb200TrimThresholdTable(float(end_threshold), int(length), _ptr(t))
+    if rc != 0:
+        raise EngineError('pb200TrimThresholdTable: error %d' % rc)
+    return t
 
 
 def adapter_alignment_batch_device(d_seqs_ptr, d_seq_off_ptr, n_seqs, total_seq_bytes, max_seq_len, ad_buf, ad_off,

@@ -572,4 +572,30 @@ PB_HD int traceback_stats(NibFn nib, EqFn eq, const EndCell &end, bool linear, i
     return status;
 }
 
+// ---- end-trim decisions on the device ------------------------------------------------------
+// find_start_trim / find_end_trim (porechop/nanopore_read.py:166-208) for one record: the trim amount this adapter asks
+// for, or 0.  The reference compares  float("%f" % (100.0*match_aln/len_aln)) > end_threshold ; printf's rounding and
+// strtod are monotone, so for every len_aln there is a smallest match count that passes: cmin[len_aln], built on the
+// host with the very same snprintf/strtod chain (engine.cu pb200TrimThresholdTable).  A failed alignment (empty read or
+// adapter) parses as 0.0 / read_start -1 / read_end 0 in the reference (nanopore_read.py:479-485).
+PB_HD int32_t end_trim_candidate(const int32_t *r, int is_start, int32_t end_size, int32_t extra_trim, int32_t min_trim,
+                                 const int32_t *cmin, int32_t cmin_len, int *overflow) {
+    const bool failed = r[0] == -1 && r[4] == PB_SCORE_EMPTY;
+    if (failed) return 0;                                   // 0.0 > threshold only for negative thresholds: see host check
+    const int32_t l = r[6], c = r[5];
+    if (l < 0 || l >= cmin_len) { *overflow = 1; return 0; }
+    if (c < cmin[l]) return 0;                              // partial identity does not pass (also 0/0 = NaN: cmin[0] is huge)
+    const int32_t rs = r[0], re = r[1] + 1;
+    if (re - rs < min_trim) return 0;
+    if (is_start) return (re == end_size) ? 0 : re + extra_trim;
+    return (rs == 0) ? 0 : (end_size - rs) + extra_trim;
+}
+// barcode score column of a record: (match_ad, len_ad) as two uint16 -- the host turns the pair into the exact double
+// the reference parses (full-adapter identity); a failed alignment scores 0.0 = the pair (0, 1).
+PB_HD uint32_t score_pair(const int32_t *r, int *overflow) {
+    if (r[0] == -1 && r[4] == PB_SCORE_EMPTY) return 1u << 16;
+    if ((uint32_t)r[7] > 0xFFFFu || (uint32_t)r[8] > 0xFFFFu) { *overflow = 1; return 0u; }
+    return (uint32_t)r[7] | ((uint32_t)r[8] << 16);
+}
+
 }  // namespace pb

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -106,6 +107,7 @@ struct Stage {
     cudaStream_t stream = nullptr;
     DevBuf seq_raw, seq_codes, seq_off, tasks, tasks2, ends, out, order, bins, pair_seq, pair_ad, gtrace, misc;
     HostBuf h_pack;                // pinned staging of the packed upload path
+    DevBuf dec_trim, dec_pairs;    // per-chunk outputs of decide_kernel
 };
 
 struct ClassPlan {
@@ -123,6 +125,8 @@ struct Engine {
     std::mutex mu;
     Stage st[NSTAGE];
     DevBuf gjobs, gscratch;
+    static constexpr int MAX_DEC_JOBS = 8;
+    DevBuf dec_cmin[MAX_DEC_JOBS], dec_cols[MAX_DEC_JOBS];   // threshold table + score columns of the decision jobs of a call
     // adapter plan cache (4 entries, LRU): repeated calls with the same adapters + scoring (the normal case: Porechop
     // alternates between its start-adapter and end-adapter lists) skip upload, encode and the host synchronisation
     struct PlanEntry {
@@ -583,7 +587,8 @@ int check_status(Stage &S, cudaStream_t stream) {
     int st = 0;
     CK(cudaMemcpyAsync(&st, S.misc.p, 4, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
-    if (st) return fail(PB200_ERR_INTERNAL, "traceback left its window (window bound violated)");
+    if (st & 1) return fail(PB200_ERR_INTERNAL, "traceback left its window (window bound violated)");
+    if (st & 2) return fail(PB200_ERR_INTERNAL, "decision kernel: value outside its table (len_aln >= table length or count > 65535)");
     return 0;
 }
 
@@ -644,6 +649,10 @@ struct CrossJob {
     const uint8_t *adapters; const int32_t *ad_off; int32_t n_adapters;
     int32_t *out;
     std::vector<HostChunk> chunks;
+    // decisions on the device (adapterEndDecisions): records are reduced per read before anything is copied back
+    const pb200_end_batch_t *dec = nullptr;
+    const int32_t *d_cmin = nullptr; int32_t cmin_len = 0;
+    const int32_t *d_cols = nullptr;
 };
 
 // Chunks of every job flow through ONE ring of NSTAGE streams (H2D / kernels / D2H of consecutive chunks overlap, also
@@ -686,8 +695,27 @@ int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int g
         }
         if (int rc = run_cross_chunk(E, S, stream, P, S.seq_codes.as<uint8_t>(), S.seq_off.as<int64_t>(), cnt, base, c.max_n,
                                      J.n_adapters, S.out.as<int32_t>(), J.seq_off, s0, J.ad_off)) return rc;
-        CK(cudaMemcpyAsync(J.out + (size_t)s0 * J.n_adapters * PB_REC, S.out.p, (size_t)cnt * J.n_adapters * PB_REC * 4,
-                           cudaMemcpyDeviceToHost, stream));
+        if (J.dec) {
+            const pb200_end_batch_t &D = *J.dec;
+            if (int rc = S.dec_trim.ensure((size_t)cnt * 4)) return rc;
+            if (int rc = S.dec_pairs.ensure((size_t)cnt * std::max<int32_t>(D.n_score_cols, 1) * 4)) return rc;
+            DecideArgs a;
+            a.records = S.out.as<int32_t>(); a.n = cnt; a.n_adapters = J.n_adapters;
+            a.is_start = D.is_start; a.end_size = D.end_size; a.extra_trim = D.extra_trim_size; a.min_trim = D.min_trim_size;
+            a.cmin = J.d_cmin; a.cmin_len = J.cmin_len; a.cols = J.d_cols; a.n_cols = D.n_score_cols;
+            a.trim = S.dec_trim.as<int32_t>(); a.pairs = S.dec_pairs.as<uint32_t>();
+            const int64_t blocks = std::min<int64_t>((cnt + 3) / 4, (int64_t)E.sm_count * 16);
+            decide_kernel<<<(unsigned)blocks, 128, 0, stream>>>(a, S.misc.as<int>());
+            g_launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(D.trim + s0, S.dec_trim.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, stream));
+            if (D.n_score_cols > 0)
+                CK(cudaMemcpyAsync(D.score_pairs + (size_t)s0 * D.n_score_cols * 2, S.dec_pairs.p,
+                                   (size_t)cnt * D.n_score_cols * 4, cudaMemcpyDeviceToHost, stream));
+        }
+        if (J.out)
+            CK(cudaMemcpyAsync(J.out + (size_t)s0 * J.n_adapters * PB_REC, S.out.p, (size_t)cnt * J.n_adapters * PB_REC * 4,
+                               cudaMemcpyDeviceToHost, stream));
         return 0;
     };
     int rc_final = 0;
@@ -868,6 +896,82 @@ int batch_host_multi(const pb200_batch_t *batches, int n_batches, int ma, int mi
     return run_cross_jobs(E, jobs, ma, mi, go, ge);
 }
 
+// float("%f" % (100.0*c/l)) exactly as the reference chain produces it: std::to_string(double) = sprintf("%f")
+// (porechop/src/alignment.cpp:113-121), then Python's float() = strtod (nanopore_read.py:488-489)
+double percent_exact(int32_t c, int32_t l) {
+    char buf[64];
+    volatile double cd = (double)c, ld = (double)l;
+    snprintf(buf, sizeof buf, "%f", 100.0 * cd / ld);
+    return strtod(buf, nullptr);
+}
+void trim_threshold_table(double thr, int32_t len, int32_t *cmin) {
+    if (len > 0) cmin[0] = INT32_MAX;
+    for (int32_t l = 1; l < len; ++l) {
+        // percent_exact(., l) is non-decreasing: binary search for the first c with value > thr
+        int32_t lo = 0, hi = l + 1;
+        while (lo < hi) {
+            const int32_t mid = lo + (hi - lo) / 2;
+            if (percent_exact(mid, l) > thr) hi = mid; else lo = mid + 1;
+        }
+        cmin[l] = lo;
+    }
+}
+
+int batch_end_decisions(const pb200_end_batch_t *batches, int n_batches, int ma, int mi, int go, int ge) {
+    if (n_batches < 0 || (n_batches > 0 && !batches)) return fail(PB200_ERR_ARG, "bad batch list");
+    load_env_options();
+    std::vector<CrossJob> jobs;
+    std::vector<std::vector<int32_t>> tables;
+    for (int b = 0; b < n_batches; ++b) {
+        const pb200_end_batch_t &D = batches[b];
+        const pb200_batch_t &B = D.batch;
+        if (B.n_seqs < 0 || B.n_adapters < 0 || D.n_score_cols < 0) return fail(PB200_ERR_ARG, "negative count");
+        if (B.n_seqs == 0) continue;
+        if (!D.trim || (D.n_score_cols > 0 && (!D.score_pairs || !D.score_cols))) return fail(PB200_ERR_ARG, "NULL pointer");
+        if (!(D.end_threshold >= 0.0)) return fail(PB200_ERR_ARG, "end_threshold must be >= 0 for the device decisions");
+        for (int32_t k = 0; k < D.n_score_cols; ++k)
+            if (D.score_cols[k] < 0 || D.score_cols[k] >= B.n_adapters) return fail(PB200_ERR_ARG, "score column out of range");
+        if (B.n_adapters == 0) {                 // no adapters: nothing aligns, nothing is trimmed
+            memset(D.trim, 0, (size_t)B.n_seqs * 4);
+            continue;
+        }
+        if (!B.seq_off || !B.ad_off) return fail(PB200_ERR_ARG, "NULL pointer");
+        CrossJob J{B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, B.out, {}};
+        if (int rc = validate_and_plan(B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, nullptr, nullptr,
+                                       B.n_seqs * (int64_t)B.n_adapters, true, J.chunks)) return rc;
+        // aligned length <= window + adapter: size the threshold table for the longest of both in this batch
+        int64_t max_n = 0, m_max = 0;
+        for (const HostChunk &c : J.chunks) max_n = std::max(max_n, c.max_n);
+        for (int32_t a = 0; a < B.n_adapters; ++a) m_max = std::max<int64_t>(m_max, B.ad_off[a + 1] - B.ad_off[a]);
+        if (max_n + m_max + 2 > 65535) return fail(PB200_ERR_ARG, "windows too long for the device decisions (use the record API)");
+        J.dec = &D;
+        J.cmin_len = (int32_t)(max_n + m_max + 2);
+        tables.emplace_back((size_t)J.cmin_len);
+        trim_threshold_table(D.end_threshold, J.cmin_len, tables.back().data());
+        jobs.push_back(std::move(J));
+    }
+    if (jobs.empty()) return 0;
+    if ((int)jobs.size() > Engine::MAX_DEC_JOBS) return fail(PB200_ERR_ARG, "too many decision batches in one call");
+    Engine *Ep = nullptr;
+    if (int rc = get_engine(&Ep)) return rc;
+    Engine &E = *Ep;
+    std::lock_guard<std::mutex> lk(E.mu);
+    if (int rc = E.init()) return rc;
+    cudaStream_t s0 = E.st[0].stream;
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        const pb200_end_batch_t &D = *jobs[j].dec;
+        if (int rc = E.dec_cmin[j].ensure((size_t)jobs[j].cmin_len * 4)) return rc;
+        if (int rc = E.dec_cols[j].ensure((size_t)std::max<int32_t>(D.n_score_cols, 1) * 4)) return rc;
+        CK(cudaMemcpyAsync(E.dec_cmin[j].p, tables[j].data(), (size_t)jobs[j].cmin_len * 4, cudaMemcpyHostToDevice, s0));
+        if (D.n_score_cols > 0)
+            CK(cudaMemcpyAsync(E.dec_cols[j].p, D.score_cols, (size_t)D.n_score_cols * 4, cudaMemcpyHostToDevice, s0));
+        jobs[j].d_cmin = E.dec_cmin[j].as<int32_t>();
+        jobs[j].d_cols = E.dec_cols[j].as<int32_t>();
+    }
+    CK(cudaStreamSynchronize(s0));               // tables are in place before any stage's stream uses them
+    return run_cross_jobs(E, jobs, ma, mi, go, ge);
+}
+
 int batch_device(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs, int64_t total_seq_bytes,
                  int64_t max_seq_len, const uint8_t *adapters, const int32_t *ad_off, int32_t n_adapters, int ma, int mi,
                  int go, int ge, int32_t *d_out, void *user_stream) {
@@ -931,6 +1035,17 @@ int adapterAlignmentBatch(const uint8_t *seqs, const int64_t *seq_off, int64_t n
 int adapterAlignmentBatchMulti(const pb200_batch_t *batches, int n_batches, int ma, int mi, int go, int ge) {
     g_err.clear();
     return batch_host_multi(batches, n_batches, ma, mi, go, ge);
+}
+
+int adapterEndDecisions(const pb200_end_batch_t *batches, int n_batches, int ma, int mi, int go, int ge) {
+    g_err.clear();
+    return batch_end_decisions(batches, n_batches, ma, mi, go, ge);
+}
+
+int pb200TrimThresholdTable(double end_threshold, int32_t len, int32_t *cmin) {
+    if (len < 0 || (len > 0 && !cmin) || !(end_threshold >= 0.0)) return PB200_ERR_ARG;
+    trim_threshold_table(end_threshold, len, cmin);
+    return 0;
 }
 
 int adapterAlignmentBatchDevice(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs, int64_t total_seq_bytes,

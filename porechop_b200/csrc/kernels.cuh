@@ -6,6 +6,7 @@
 //   trace_kernel<G,R,S>  overlap DP *with* 4-bit trace + in-kernel traceback + statistics (windows)
 //   score_kernel<G,R>    streaming score-only overlap DP with exact scout (long reads), dynamic slot refill
 //   window_tasks_kernel  end cells of the score pass -> bounded-window tasks for trace_kernel
+//   decide_kernel        records -> per-read end-trim amounts + barcode score pairs (decisions stay on the device)
 //   generic_kernel       int32 thread-serial fallback for scoring schemes / adapters outside the int16 domain
 //
 // The arithmetic is in dp_core.cuh (shared with the CPU emulation used by the tests).
@@ -571,6 +572,44 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decide_kernel: records of one chunk (n reads x n_adapters, read-major, still in HBM/L2 from the DP kernels) -> per read
+// the end-trim amount (max over the adapters that pass, 0 if none) and the (match_ad, len_ad) pairs of the barcode score
+// columns.  One warp per read; 4 + 4*n_cols bytes per read leave the device instead of 36*n_adapters.
+struct DecideArgs {
+    const int32_t *records; int64_t n; int32_t n_adapters;
+    int32_t is_start, end_size, extra_trim, min_trim;
+    const int32_t *cmin; int32_t cmin_len;
+    const int32_t *cols; int32_t n_cols;
+    int32_t *trim; uint32_t *pairs;
+};
+__global__ void decide_kernel(const DecideArgs a, int *__restrict__ status) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int ovf = 0;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.n; i += warps) {
+        const int32_t *rec = a.records + (size_t)i * a.n_adapters * PB_REC;
+        int32_t best = 0;
+        for (int32_t k = lane; k < a.n_adapters; k += 32) {
+            int32_t r[PB_REC];
+#pragma unroll
+            for (int q = 0; q < PB_REC; ++q) r[q] = rec[(size_t)k * PB_REC + q];
+            const int32_t t = end_trim_candidate(r, a.is_start, a.end_size, a.extra_trim, a.min_trim, a.cmin, a.cmin_len, &ovf);
+            best = t > best ? t : best;
+        }
+        best = __reduce_max_sync(0xffffffffu, best);
+        if (lane == 0) a.trim[i] = best;
+        for (int32_t k = lane; k < a.n_cols; k += 32) {
+            const int32_t *r = rec + (size_t)a.cols[k] * PB_REC;
+            int32_t rr[PB_REC];
+#pragma unroll
+            for (int q = 0; q < PB_REC; ++q) rr[q] = r[q];
+            a.pairs[(size_t)i * a.n_cols + k] = score_pair(rr, &ovf);
+        }
+    }
+    if (ovf) atomicOr(status, 2);
 }
 
 // ---------------------------------------------------------------------------------------------------

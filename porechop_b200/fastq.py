@@ -29,6 +29,7 @@ buffers end to end:
 The alignment engine is case-insensitive and maps U to T itself (Dna5 table); normalising at parse time only matters
 because the reference writes the normalised bases back out.
 """
+import os
 import time
 
 import numpy as np
@@ -270,12 +271,45 @@ def end_trim_amounts(start_records, end_records, end_size, extra_trim_size, end_
     return one(np.asarray(start_records), True), one(np.asarray(end_records), False)
 
 
+# Decisions on the device (include/porechop_b200.h adapterEndDecisions): the engine reduces the records
+# of the end windows to per-read trim amounts + the barcode score pairs before anything is copied back.  Off by default.
+DEVICE_DECISIONS = os.environ.get('PB200_DEVICE_DECISIONS', '0') == '1'
+
+
+class PairScores:
+    """Barcode score columns as the device returns them: (match_ad, len_ad) uint16 pairs for the requested adapter
+    columns.  full(cols) gives the same doubles as the record path (float("%f" % (100.0 * match / len)))."""
+
+    def __init__(self, cols, pairs):
+        self.cols = [int(c) for c in cols]
+        self.pairs = pairs                            # uint16[n, len(cols), 2]
+
+    def full(self, cols):
+        assert [int(c) for c in cols] == self.cols
+        if self.pairs.shape[1] == 0:
+            return np.zeros((self.pairs.shape[0], 0))
+        from .align import _percent_exact
+        return _percent_exact(self.pairs[:, :, 0], self.pairs[:, :, 1])
+
+
 def trim_end_adapters(batch, start_adapters, end_adapters, scoring_scheme_vals, end_size=150, extra_trim_size=2,
-                      end_threshold=75.0, min_trim_size=4):
+                      end_threshold=75.0, min_trim_size=4, device_decisions=None, score_cols=None):
     """Phase B for a FastqBatch and fixed adapter lists (sequences): returns (start_trim, end_trim, start_records,
-    end_records).  Two batched engine calls, no per-read Python."""
+    end_records).  Two batched engine calls, no per-read Python.
+    device_decisions (default: the module switch DEVICE_DECISIONS): one adapterEndDecisions submit instead -- the trim
+    rule runs on the device and the last two results are PairScores for score_cols = (start columns, end columns)."""
     (sbuf, soff), (ebuf, eoff) = end_windows(batch.seq, batch.seq_off, end_size)
     n = len(batch)
+    if device_decisions is None:
+        device_decisions = DEVICE_DECISIONS
+    if device_decisions and n > 0 and end_threshold >= 0 and (start_adapters or end_adapters):
+        scols, ecols = score_cols if score_cols is not None else ((), ())
+        sa, so = W.pack_sequences(start_adapters, offset_dtype=np.int32)
+        ea, eo = W.pack_sequences(end_adapters, offset_dtype=np.int32)
+        (st, sp, _), (et, ep, _) = W.adapter_end_decisions(
+            [(sbuf, soff, sa, so, True, list(scols)), (ebuf, eoff, ea, eo, False, list(ecols))], scoring_scheme_vals,
+            end_size, extra_trim_size, end_threshold, min_trim_size)
+        return st.astype(np.int64), et.astype(np.int64), PairScores(scols, sp), PairScores(ecols, ep)
 
     def run(buf, off, adapters):
         if not adapters or n == 0:
@@ -534,7 +568,7 @@ def _middle_adapters(sets):
 
 
 def _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim, end_threshold, min_trim_size, no_split,
-              middle_threshold, good_side, bad_side):
+              middle_threshold, good_side, bad_side, score_cols=None):
     t0 = time.perf_counter()
     batch = data if isinstance(data, FastqBatch) else parse_fastq(data)
     t1 = time.perf_counter()
@@ -542,7 +576,7 @@ def _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim
     starts = [s[1] for _, s, _ in sets if s]
     ends = [e[1] for _, _, e in sets if e]
     st, et, srec, erec = trim_end_adapters(batch, starts, ends, scoring_scheme_vals, end_size, extra_end_trim,
-                                           end_threshold, min_trim_size)
+                                           end_threshold, min_trim_size, score_cols=score_cols)
     t2 = time.perf_counter()
     middle = {}
     if not no_split:
@@ -641,23 +675,25 @@ def demux_fastq(data, matching_sets, scoring_scheme_vals, forward_or_reverse='fo
     (porechop.py:54-79, 652-676) once Phase A has chosen `matching_sets` = [(set name, start, end), ...] and the
     barcode direction.  A set is a barcode if its name starts with 'Barcode ' (adapters.py:31-32); its direction is
     'reverse' if its start name contains '_rev' (adapters.py:34-38).  Returns (bins, info)."""
-    batch, sets, st, et, srec, erec, middle, seconds = _run_trim(data, matching_sets, scoring_scheme_vals, end_size,
-                                                                 extra_end_trim, end_threshold, min_trim_size, no_split,
-                                                                 middle_threshold, extra_middle_trim_good_side,
-                                                                 extra_middle_trim_bad_side)
-    t0 = time.perf_counter()
-    n = len(batch)
-
     def is_bc(name, s):
         return name.startswith('Barcode ') and (('reverse' if '_rev' in s[0] else 'forward') == forward_or_reverse)
+    sets = _norm_sets(matching_sets)
     s_sets = [t for t in sets if t[1]]
     e_sets = [t for t in sets if t[2]]
     s_cols = [j for j, (name, s, e) in enumerate(s_sets) if is_bc(name, s)]
     e_cols = [j for j, (name, s, e) in enumerate(e_sets) if is_bc(name, s)]
+    batch, sets, st, et, srec, erec, middle, seconds = _run_trim(data, matching_sets, scoring_scheme_vals, end_size,
+                                                                 extra_end_trim, end_threshold, min_trim_size, no_split,
+                                                                 middle_threshold, extra_middle_trim_good_side,
+                                                                 extra_middle_trim_bad_side, score_cols=(s_cols, e_cols))
+    t0 = time.perf_counter()
+    n = len(batch)
 
     def full(rec, cols):
         if n == 0 or not cols:
             return np.zeros((n, len(cols)))
+        if isinstance(rec, PairScores):               # decisions came from the device: only the score pairs exist
+            return rec.full(cols)
         if hostio.LIB is not None:
             return hostio.full_scores(rec, cols)
         f, _, _, _ = scores_from_records(rec[:, cols, :].reshape(-1, 9))

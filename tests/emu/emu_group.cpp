@@ -228,6 +228,25 @@ void emu_unpack(const uint8_t *in, uint8_t *out, int64_t n) {
     }
 }
 
+// decide_kernel (kernels.cuh) run serially: the same per-record core functions (dp_core.cuh end_trim_candidate /
+// score_pair), max over the adapters of a read, pairs of the listed columns.  Returns the overflow flag.
+int emu_decide(const int32_t *records, int64_t n, int32_t n_adapters, int is_start, int32_t end_size, int32_t extra_trim,
+               int32_t min_trim, const int32_t *cmin, int32_t cmin_len, const int32_t *cols, int32_t n_cols, int32_t *trim,
+               uint32_t *pairs) {
+    int ovf = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t *rec = records + (size_t)i * n_adapters * PB_REC;
+        int32_t best = 0;
+        for (int32_t k = 0; k < n_adapters; ++k) {
+            const int32_t t = end_trim_candidate(rec + (size_t)k * PB_REC, is_start, end_size, extra_trim, min_trim, cmin, cmin_len, &ovf);
+            best = t > best ? t : best;
+        }
+        trim[i] = best;
+        for (int32_t k = 0; k < n_cols; ++k) pairs[(size_t)i * n_cols + k] = score_pair(rec + (size_t)cols[k] * PB_REC, &ovf);
+    }
+    return ovf;
+}
+
 // encode_kernel's per-byte mapping, for comparison
 void emu_encode(const uint8_t *in, uint8_t *out, int64_t n) {
     for (int64_t k = 0; k < n; ++k) out[k] = (uint8_t)encode_byte(in[k]);

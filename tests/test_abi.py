@@ -116,6 +116,27 @@ def test_invalid_arguments_are_rejected_before_the_device_is_touched():
         assert 'error 100' in str(e.value)
 
 
+def test_end_decisions_arguments_validated_on_the_host():
+    from porechop_b200 import cpp_function_wrappers as W
+    sc = [3, -6, -5, -2]
+    buf, off = W.pack_sequences(['ACGTACGT', 'ACGT', 'TTTTTT'])
+    abuf, aoff = W.pack_sequences(['ACGT', 'GG'], offset_dtype=np.int32)
+
+    def err(batches, thr=75.0):
+        with pytest.raises(W.EngineError) as e:
+            W.adapter_end_decisions(batches, sc, 150, 2, thr, 4)
+        return str(e.value)
+    assert 'error 102' in err([(buf, off, abuf, aoff, True, [0, 2])])            # score column out of range
+    assert 'error 102' in err([(buf, off, abuf, aoff, True, [])], thr=-1.0)      # negative threshold: host rule only
+    bad_off = off.copy(); bad_off[1], bad_off[2] = off[2], off[1]
+    assert 'error 102' in err([(buf, off, abuf, aoff, True, []), (buf, bad_off, abuf, aoff, False, [1])])
+    # no adapters: nothing aligns, nothing is trimmed -- decided without a device
+    (trim, pairs, rec), = W.adapter_end_decisions([(buf, off, abuf[:0], aoff[:1], True, [])], sc, 150, 2, 75.0, 4)
+    assert trim.tolist() == [0, 0, 0] and pairs.shape == (3, 0, 2) and rec is None
+    if _no_gpu():
+        assert 'error 100' in err([(buf, off, abuf, aoff, True, [1])])
+
+
 def test_empty_inputs_need_no_device():
     # the -1 record of an empty read/adapter is produced without touching the device (reference: no DP either)
     from porechop_b200 import cpp_function_wrappers as W

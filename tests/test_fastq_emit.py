@@ -29,6 +29,63 @@ def _oracle_engine(monkeypatch):
     monkeypatch.setattr(fastq.W, 'adapter_alignment_batch', fake)
 
 
+def _oracle_decisions(monkeypatch):
+    """adapterEndDecisions stand-in for the CPU tier: oracle records reduced by the decision kernel's own core functions
+    (dp_core.cuh end_trim_candidate / score_pair through tests/emu) with the product's threshold table."""
+    import ctypes
+    from helpers import emu_lib
+    from porechop_b200 import fastq
+    emu = emu_lib()
+    emu.emu_decide.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
+                               ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
+                               ctypes.c_void_p]
+    emu.emu_decide.restype = ctypes.c_int
+    calls = []
+
+    def fake(batches, scoring, end_size, extra_trim_size, end_threshold, min_trim_size, want_records=False):
+        outs = []
+        for seq_buf, seq_off, ad_buf, ad_off, is_start, cols in batches:
+            seq_off, ad_off = np.asarray(seq_off, dtype=np.int64), np.asarray(ad_off, dtype=np.int32)
+            n, na = len(seq_off) - 1, len(ad_off) - 1
+            cols = np.ascontiguousarray(cols, dtype=np.int32)
+            trim = np.zeros(n, dtype=np.int32)
+            pairs = np.zeros((n, len(cols)), dtype=np.uint32)
+            if n and na:
+                rec = np.ascontiguousarray(oracle_batch(np.asarray(seq_buf), seq_off, np.asarray(ad_buf), ad_off, list(scoring)))
+                L = int(np.diff(seq_off).max()) + int(np.diff(ad_off).max()) + 2
+                cmin = fastq.W.trim_threshold_table(end_threshold, L)
+                ovf = emu.emu_decide(rec.ctypes.data, n, na, 1 if is_start else 0, end_size, extra_trim_size, min_trim_size,
+                                     cmin.ctypes.data, L, cols.ctypes.data, len(cols), trim.ctypes.data, pairs.ctypes.data)
+                assert ovf == 0
+            p16 = np.stack([(pairs & 0xFFFF).astype(np.uint16), (pairs >> 16).astype(np.uint16)], axis=-1)
+            outs.append((trim, p16, None))
+        calls.append(len(batches))
+        return outs
+    monkeypatch.setattr(fastq.W, 'adapter_end_decisions', fake)
+    monkeypatch.setattr(fastq, 'DEVICE_DECISIONS', True)
+    return calls
+
+
+@pytest.mark.parametrize('case_name', CASES)
+def test_trim_fastq_device_decisions_match_reference_cli(monkeypatch, case_name):
+    """The flat pipeline with the end-trim decisions taken by the device path (adapterEndDecisions; here its core
+    functions on oracle records): output files still byte-identical to the reference CLI."""
+    _oracle_engine(monkeypatch)
+    calls = _oracle_decisions(monkeypatch)
+    _run(case_name)
+    assert calls == [2]                                   # one submit: start + end windows
+
+
+@pytest.mark.parametrize('case_name', BARCODE_CASES if 'BARCODE_CASES' in globals() else
+                         ['bins_default', 'bins_two_barcodes', 'bins_loose_discard', 'bins_fasta_untrimmed'])
+def test_demux_fastq_device_decisions_match_reference_cli(monkeypatch, case_name):
+    """Barcode bins from the device's score pairs instead of the full records: every bin file byte-identical."""
+    _oracle_engine(monkeypatch)
+    calls = _oracle_decisions(monkeypatch)
+    info = _run_demux(case_name)
+    assert calls == [2] and len(info['calls']) == info['n_reads'] == 18
+
+
 @pytest.mark.parametrize('case_name', CASES)
 def test_trim_fastq_matches_reference_cli_oracle_engine(monkeypatch, case_name):
     _oracle_engine(monkeypatch)

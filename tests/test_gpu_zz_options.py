@@ -149,3 +149,52 @@ def test_short_two_pass_windows_equal_oracle(W):
         for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
             assert np.array_equal(got, exp), (sc, opts)
+
+
+def test_end_decisions_on_device_equal_host_rule(W):
+    """adapterEndDecisions (decide_kernel): per-read trim amounts and barcode score pairs computed on the device equal
+    libhostio's pbioEndTrim / pbioFullScores applied to the records of the ordinary call -- start and end rule, empty and
+    short windows, several chunks, several thresholds; optional record copy-back identical too."""
+    from porechop_b200 import hostio, workloads as wl
+    from porechop_b200.align import _percent_exact
+    starts, ends = wl.demux_adapters()
+    ads_s = [starts[0], starts[3], starts[100], starts[150], 'ACGT', starts[-1]]
+    ads_e = [ends[0], ends[100], ends[-1]]
+    _, sw, ew = wl.synth_end_windows(60000, starts[100], ends[100], seed=8)
+    rng = np.random.default_rng(4)
+
+    def ragged(win):
+        buf, off = wl.windows_to_batch(win)
+        lens = np.diff(off).copy()
+        lens[::37] = 0
+        lens[5::41] = rng.integers(1, 60, len(lens[5::41]))
+        off2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        keep = np.repeat(np.arange(len(lens)) * 150, lens) + (np.arange(int(lens.sum())) - np.repeat(off2[:-1], lens))
+        return np.ascontiguousarray(buf[keep]), off2
+    (sb, so), (eb, eo) = ragged(sw), ragged(ew)
+    sa, sao = wl.pack_adapters(ads_s)
+    ea, eao = wl.pack_adapters(ads_e)
+    srec = W.adapter_alignment_batch(sb, so, sa, sao, wl.DEFAULT_SCORING).reshape(-1, len(ads_s), 9)
+    erec = W.adapter_alignment_batch(eb, eo, ea, eao, wl.DEFAULT_SCORING).reshape(-1, len(ads_e), 9)
+    scols, ecols = [2, 0, 5, 2], [1]
+    for end_size, extra, thr, min_trim, opts in ((150, 2, 75.0, 4, {}), (150, 0, 90.0, 1, {'chunk_tasks': 50000}),
+                                                 (100, 5, 50.0, 10, {'h2d_pack': 1}), (150, 2, 0.0, 4, {})):
+        outs = _with(W, opts, lambda: W.adapter_end_decisions(
+            [(sb, so, sa, sao, True, scols), (eb, eo, ea, eao, False, ecols)], wl.DEFAULT_SCORING, end_size, extra, thr,
+            min_trim, want_records=True))
+        for (trim, pairs, rec), full_rec, is_start, cols in ((outs[0], srec, True, scols), (outs[1], erec, False, ecols)):
+            assert np.array_equal(rec.reshape(full_rec.shape), full_rec)
+            assert np.array_equal(trim.astype(np.int64), hostio.end_trim(full_rec, is_start, end_size, extra, thr, min_trim))
+            got = _percent_exact(pairs[:, :, 0], pairs[:, :, 1])
+            assert np.array_equal(got, hostio.full_scores(full_rec, cols), equal_nan=True)
+
+
+def test_flat_pipeline_with_device_decisions_matches_reference_cli(W, monkeypatch):
+    """trim_fastq / demux_fastq goldens (reference CLI output files) with the end-trim decisions taken on the device."""
+    from porechop_b200 import fastq
+    import test_fastq_emit as T
+    monkeypatch.setattr(fastq, 'DEVICE_DECISIONS', True)
+    for case in T.CASES:
+        T._run(case)
+    for case in T.BARCODE_CASES:
+        T._run_demux(case)

@@ -153,3 +153,63 @@ def test_packed_upload_path_host_pack_and_device_unpack_equal_encode():
             got = np.zeros(n, dtype=np.uint8)
             emu.emu_unpack(pk.ctypes.data, got.ctypes.data, n)
             assert np.array_equal(got, exp), (n, threads)
+
+
+def test_trim_threshold_table_is_the_exact_float_rule():
+    """pb200TrimThresholdTable: `c >= cmin[l]` is exactly the reference's `float("%f" % (100.0*c/l)) > end_threshold`
+    (alignment.cpp:113-121 + nanopore_read.py:488) for every count and aligned length, also at thresholds that sit on
+    printf's rounding boundaries."""
+    from porechop_b200 import cpp_function_wrappers as W
+    for thr in (75.0, 90.0, 0.0, 100.0, 50.0, 33.333333, 33.3333335, 66.666667, 66.6666665, 99.999999, 14.285714, 85.5):
+        L = 420
+        cmin = W.trim_threshold_table(thr, L)
+        assert cmin[0] == 2 ** 31 - 1
+        for l in range(1, L):
+            vals = np.array([float('%f' % (100.0 * c / l)) for c in range(l + 1)])
+            ok = vals > thr
+            first = int(np.argmax(ok)) if ok.any() else l + 1
+            assert cmin[l] == first, (thr, l)
+            assert np.array_equal(ok, np.arange(l + 1) >= cmin[l])
+
+
+def test_device_decision_core_equals_host_trim_rule_and_barcode_scores():
+    """The decision kernel's per-record core (dp_core.cuh end_trim_candidate / score_pair, run serially by tests/emu) on
+    oracle records: trim amounts equal libhostio's pbioEndTrim (and the numpy rule), and the (match, length) pairs give the
+    same doubles as pbioFullScores -- start and end rule, empty windows, several thresholds / window sizes."""
+    import ctypes
+    from helpers import emu_lib
+    from porechop_b200 import cpp_function_wrappers as W, hostio, workloads as wl
+    from porechop_b200.align import _percent_exact
+    emu = emu_lib()
+    emu.emu_decide.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int, ctypes.c_int32, ctypes.c_int32,
+                               ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p,
+                               ctypes.c_void_p]
+    emu.emu_decide.restype = ctypes.c_int
+    starts, ends = wl.demux_adapters()
+    ads = [starts[0], starts[3], starts[100], starts[150], ends[100], 'ACGT', starts[-1]]
+    _, sw, ew = wl.synth_end_windows(600, starts[100], ends[100], seed=8)
+    rng = np.random.default_rng(2)
+    for win, is_start in ((sw, 1), (ew, 0)):
+        sbuf, soff = wl.windows_to_batch(win)
+        # a few empty and short windows (reads shorter than end_size)
+        lens = np.diff(soff).copy()
+        lens[::37] = 0
+        lens[5::41] = rng.integers(1, 60, len(lens[5::41]))
+        off2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        buf2 = np.concatenate([sbuf[soff[i]:soff[i] + lens[i]] for i in range(len(lens))]) if len(lens) else sbuf[:0]
+        abuf, aoff = wl.pack_adapters(ads)
+        rec = oracle_batch(buf2, off2, abuf, aoff, wl.DEFAULT_SCORING).reshape(len(lens), len(ads), 9)
+        cols = np.array([2, 0, 6, 2], dtype=np.int32)
+        for end_size, extra, thr, min_trim in ((150, 2, 75.0, 4), (150, 0, 90.0, 1), (100, 5, 50.0, 10), (150, 2, 0.0, 4)):
+            L = 150 + max(len(a) for a in ads) + 2
+            cmin = W.trim_threshold_table(thr, L)
+            trim = np.zeros(len(lens), dtype=np.int32)
+            pairs = np.zeros((len(lens), len(cols)), dtype=np.uint32)
+            flat = np.ascontiguousarray(rec.reshape(-1, 9))
+            ovf = emu.emu_decide(flat.ctypes.data, len(lens), len(ads), is_start, end_size, extra, min_trim, cmin.ctypes.data, L,
+                                 cols.ctypes.data, len(cols), trim.ctypes.data, pairs.ctypes.data)
+            assert ovf == 0
+            exp = hostio.end_trim(rec, bool(is_start), end_size, extra, thr, min_trim)
+            assert np.array_equal(trim.astype(np.int64), exp), (is_start, end_size, thr)
+            full = _percent_exact(pairs & 0xFFFF, pairs >> 16)
+            assert np.array_equal(full, hostio.full_scores(rec, [int(c) for c in cols]), equal_nan=True)
