@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-multi', action='store_true',
                     help="e2e: the step's batches in ONE adapterAlignmentBatchMulti submit instead of one call per batch")
+    ap.add_argument('--e2e-decisions', action='store_true',
+                    help='e2e (endtrim / demux): adapterEndDecisions -- trim amounts + barcode score pairs decided on the '
+                         'device, 4 + 4*adapters bytes per window come back instead of 36 per alignment')
     ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE',
                     help='engine option for this run (pb200SetOption), e.g. --opt h2d_pack=1 --opt tight_window=1')
     return ap.parse_args()
@@ -285,9 +288,25 @@ def main():
             W.adapter_alignment_batch_device(db.data_ptr(), do.data_ptr(), do.numel() - 1, db.numel(), max_len, abuf, aoff,
                                              scoring, dout.data_ptr(), s)
 
+    dec_out = None
+    if args.e2e_decisions:
+        assert args.workload in ('endtrim', 'demux'), '--e2e-decisions applies to the end-window workloads'
+        dec_out = []
+        for (name, _, ads), (hb, ho, abuf, aoff, hout) in zip(batches, host):
+            nw, na = ho.numel() - 1, len(ads)
+            dec_out.append((torch.empty(nw, dtype=torch.int32, pin_memory=True),
+                            torch.empty((nw, na, 2), dtype=torch.uint16, pin_memory=True)))
+        out_bytes_dec = sum(t.numel() * 4 + p.numel() * 2 for t, p in dec_out)
+
     def step_e2e():
         # every rank pushes its own shard through the host-buffer C-ABI over its own PCIe link; the records stay
         # rank-local (no data-path collective, prompt (5)); the optional re-gather to a writer rank is timed separately
+        if args.e2e_decisions:
+            # every adapter is a score column (upper bound of what barcode calling needs)
+            W.adapter_end_decisions([(hb.numpy(), ho.numpy(), abuf, aoff, b[0] == 'start', list(range(len(b[2]))))
+                                     for b, (hb, ho, abuf, aoff, hout) in zip(batches, host)], scoring, wl.END_SIZE, 2, 75.0, 4,
+                                    out_arrays=[(t.numpy(), p.numpy(), None) for t, p in dec_out])
+            return
         if args.e2e_multi:
             W.adapter_alignment_batch_multi([(hb.numpy(), ho.numpy(), abuf, aoff, hout.numpy()) for hb, ho, abuf, aoff, hout in host],
                                             scoring)
@@ -333,6 +352,18 @@ def main():
     e2e_s = time.perf_counter() - t0
     sampler.active = False
     sampler.stop_flag = True
+    if args.e2e_decisions:
+        # the in-run parity gate needs the records themselves: one more (untimed) step through the record call, and the
+        # decisions of the timed steps are checked against the host rule on those records
+        from porechop_b200 import hostio
+        out_bytes = out_bytes_dec
+        dec_bad = 0
+        for b, (hb, ho, abuf, aoff, hout), (t, p) in zip(batches, host, dec_out):
+            W.adapter_alignment_batch(hb.numpy(), ho.numpy(), abuf, aoff, scoring, out=hout.numpy())
+            rec = hout.numpy().reshape(ho.numel() - 1, len(b[2]), 9)
+            exp = hostio.end_trim(rec, b[0] == 'start', wl.END_SIZE, 2, 75.0, 4)
+            dec_bad += int(np.count_nonzero(exp != t.numpy()))
+            dec_bad += int(np.count_nonzero(p.numpy()[:, :, 0] != rec[:, :, 7].astype(np.uint16)))
 
     # informational: NCCL re-gather of the 36-byte records of every rank to rank 0 (device -> device over NVLink)
     gather_ms = None
@@ -392,9 +423,11 @@ def main():
                    'l2': 'inputs %.0f MB per step exceed the 126 MB L2' % (in_bytes / 1e6)},
         'e2e': {'value': e2e_value, 'unit': 'reads/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': out_bytes,
                 'ms_per_step': e2e_ms / K, 'gcups': cells_per_step * world * K / (e2e_ms / 1e3) / 1e9,
-                'path': ('adapterAlignmentBatchMulti (host buffers, pinned), one submit per step per rank' if args.e2e_multi else
+                'path': ('adapterEndDecisions (host buffers, pinned), one submit per step per rank, decisions come back' if args.e2e_decisions else
+                         'adapterAlignmentBatchMulti (host buffers, pinned), one submit per step per rank' if args.e2e_multi else
                          'adapterAlignmentBatch (host buffers, pinned), one call per batch per rank') + '; records stay rank-local',
                 'options': args.opt,
+                'decisions': ({'mismatches_vs_host_rule': dec_bad} if args.e2e_decisions else None),
                 'gather_records_to_rank0_ms': gather_ms},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

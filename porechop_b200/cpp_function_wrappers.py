@@ -189,12 +189,13 @@ def adapter_alignment_batch_multi(batches, scoring_scheme_vals):
 
 
 def adapter_end_decisions(batches, scoring_scheme_vals, end_size, extra_trim_size, end_threshold, min_trim_size,
-                          want_records=False):
+                          want_records=False, out_arrays=None):
     """
     End-trim decisions on the device (adapterEndDecisions): `batches` is a list of
     (seq_buf, seq_off, ad_buf, ad_off, is_start, score_cols) -- windows x adapters, which trim rule, and the adapter
     indices whose full-adapter identity the host still needs (barcode columns; may be empty).
     Returns one (trim int32[n], pairs uint16[n, n_cols, 2], records or None) per batch.
+    out_arrays: optional preallocated [(trim, pairs, records-or-None), ...] (e.g. views of pinned memory) to write into.
     """
     descs = (EndBatchDesc * max(len(batches), 1))()
     keep, outs = [], []
@@ -205,9 +206,14 @@ def adapter_end_decisions(batches, scoring_scheme_vals, end_size, extra_trim_siz
         ad_off = np.ascontiguousarray(b[3], dtype=np.int32)
         cols = np.ascontiguousarray(b[5] if b[5] is not None else [], dtype=np.int32)
         n_seqs, n_ad = len(seq_off) - 1, len(ad_off) - 1
-        trim = np.zeros(n_seqs, dtype=np.int32)
-        pairs = np.zeros((n_seqs, len(cols), 2), dtype=np.uint16)
-        rec = np.empty((n_seqs * n_ad, RECORD_INTS), dtype=np.int32) if want_records else None
+        if out_arrays is not None:
+            trim, pairs, rec = out_arrays[k]
+            assert trim.dtype == np.int32 and len(trim) == n_seqs and pairs.dtype == np.uint16 and \
+                pairs.shape == (n_seqs, len(cols), 2) and trim.flags.c_contiguous and pairs.flags.c_contiguous
+        else:
+            trim = np.zeros(n_seqs, dtype=np.int32)
+            pairs = np.zeros((n_seqs, len(cols), 2), dtype=np.uint16)
+            rec = np.empty((n_seqs * n_ad, RECORD_INTS), dtype=np.int32) if want_records else None
         keep.append((seq_buf, seq_off, ad_buf, ad_off, cols))
         outs.append((trim, pairs, rec))
         descs[k] = EndBatchDesc(BatchDesc(seq_buf.ctypes.data, seq_off.ctypes.data, n_seqs, ad_buf.ctypes.data,
