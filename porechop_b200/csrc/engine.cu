@@ -602,44 +602,46 @@ __global__ void rebase_kernel(int64_t *off, int64_t n, int64_t base) {
 struct HostChunk { int64_t s0, s1, max_n; };
 
 // Pure host work done before the device is touched: argument validation (so a bad call fails the same way with or
-// without a device) and the chunk plan of the cross-product pipeline (one pass over the offsets).
-int validate_and_plan(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, const uint8_t *adapters,
-                      const int32_t *ad_off, int32_t n_adapters, const int32_t *pair_seq, const int32_t *pair_adapter,
-                      int64_t n_pairs, bool cross, std::vector<HostChunk> &chunks) {
+// without a device).  Pair-list mode checks everything here; in cross mode the sequence offsets are checked chunk by chunk
+// while the pipeline runs (next_chunk), so that the scan of chunk k+1 hides behind the device's work on chunk k.
+int validate_args(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, const uint8_t *adapters,
+                  const int32_t *ad_off, int32_t n_adapters, const int32_t *pair_seq, const int32_t *pair_adapter,
+                  int64_t n_pairs, bool cross) {
     for (int32_t a = 0; a < n_adapters; ++a)
         if (ad_off[a + 1] < ad_off[a]) return fail(PB200_ERR_ARG, "adapter offsets not monotone");
     if (n_adapters > 0 && ad_off[0] < 0) return fail(PB200_ERR_ARG, "negative adapter offset");
     if (n_adapters > 0 && ad_off[n_adapters] > 0 && !adapters) return fail(PB200_ERR_ARG, "NULL adapter buffer");
     if (n_seqs > 0 && seq_off[n_seqs] > seq_off[0] && !seqs) return fail(PB200_ERR_ARG, "NULL sequence buffer");
-    if (!cross) {
-        if (n_pairs > 0x7fffffffll) return fail(PB200_ERR_ARG, "pair-list mode supports < 2^31 pairs per call");
-        if (n_seqs > 0 && seq_off[0] < 0) return fail(PB200_ERR_ARG, "negative sequence offset");
-        for (int64_t s = 0; s < n_seqs; ++s) {
-            const int64_t len = seq_off[s + 1] - seq_off[s];
-            if (len < 0) return fail(PB200_ERR_ARG, "sequence offsets not monotone");
-            if (len > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
-        }
-        for (int64_t p = 0; p < n_pairs; ++p)
-            if (pair_seq[p] < 0 || pair_seq[p] >= n_seqs || pair_adapter[p] < 0 || pair_adapter[p] >= n_adapters)
-                return fail(PB200_ERR_ARG, "pair index out of range");
-        return 0;
+    if (cross) return 0;
+    if (n_pairs > 0x7fffffffll) return fail(PB200_ERR_ARG, "pair-list mode supports < 2^31 pairs per call");
+    if (n_seqs > 0 && seq_off[0] < 0) return fail(PB200_ERR_ARG, "negative sequence offset");
+    for (int64_t s = 0; s < n_seqs; ++s) {
+        const int64_t len = seq_off[s + 1] - seq_off[s];
+        if (len < 0) return fail(PB200_ERR_ARG, "sequence offsets not monotone");
+        if (len > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
     }
+    for (int64_t p = 0; p < n_pairs; ++p)
+        if (pair_seq[p] < 0 || pair_seq[p] >= n_seqs || pair_adapter[p] < 0 || pair_adapter[p] >= n_adapters)
+            return fail(PB200_ERR_ARG, "pair index out of range");
+    return 0;
+}
+
+// The pipeline chunk that starts at sequence s0 of a cross-product job: chunk_tasks alignments, at most chunk_bytes of
+// sequence (but enough sequences to fill the GPU), its longest sequence, offsets checked.
+int next_chunk(const int64_t *seq_off, int64_t n_seqs, int32_t n_adapters, int64_t s0, HostChunk &c) {
     const int64_t max_cnt = std::max<int64_t>(1, g_opt.chunk_tasks / std::max<int32_t>(n_adapters, 1));
-    int64_t s0 = 0;
-    while (s0 < n_seqs) {
-        int64_t s1 = std::min(n_seqs, s0 + max_cnt);
-        // limit bytes per chunk, but keep enough sequences in a chunk to fill the GPU (one wave of slots)
-        while (s1 - s0 > 32768 && seq_off[s1] - seq_off[s0] > g_opt.chunk_bytes) s1 = s0 + std::max<int64_t>(32768, (s1 - s0) / 2);
-        HostChunk c{s0, s1, 0};
-        for (int64_t s = s0; s < s1; ++s) {
-            const int64_t len = seq_off[s + 1] - seq_off[s];
-            if (len < 0) return fail(PB200_ERR_ARG, "sequence offsets not monotone");
-            c.max_n = std::max(c.max_n, len);
-        }
-        if (c.max_n > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
-        chunks.push_back(c);
-        s0 = s1;
+    int64_t s1 = std::min(n_seqs, s0 + max_cnt);
+    while (s1 - s0 > 32768 && seq_off[s1] - seq_off[s0] > g_opt.chunk_bytes) s1 = s0 + std::max<int64_t>(32768, (s1 - s0) / 2);
+    c = HostChunk{s0, s1, 0};
+    int64_t mx = 0, mn = 0;
+    for (int64_t s = s0; s < s1; ++s) {
+        const int64_t len = seq_off[s + 1] - seq_off[s];
+        mx = std::max(mx, len);
+        mn = std::min(mn, len);
     }
+    if (mn < 0) return fail(PB200_ERR_ARG, "sequence offsets not monotone");
+    if (mx > 0x7fff0000ll) return fail(PB200_ERR_ARG, "sequence longer than 2^31");
+    c.max_n = mx;
     return 0;
 }
 
@@ -648,11 +650,11 @@ struct CrossJob {
     const uint8_t *seqs; const int64_t *seq_off; int64_t n_seqs;
     const uint8_t *adapters; const int32_t *ad_off; int32_t n_adapters;
     int32_t *out;
-    std::vector<HostChunk> chunks;
     // decisions on the device (adapterEndDecisions): records are reduced per read before anything is copied back
     const pb200_end_batch_t *dec = nullptr;
     const int32_t *d_cmin = nullptr; int32_t cmin_len = 0;
     const int32_t *d_cols = nullptr;
+    int64_t max_seq_len = 0;          // decision jobs: longest window the threshold table covers
 };
 
 // Chunks of every job flow through ONE ring of NSTAGE streams (H2D / kernels / D2H of consecutive chunks overlap, also
@@ -722,12 +724,19 @@ int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int g
     size_t k = 0;
     for (size_t j = 0; j < jobs.size() && !rc_final; ++j) {
         const CrossJob &J = jobs[j];
-        if (J.chunks.empty()) continue;
+        if (J.n_seqs <= 0 || J.n_adapters <= 0) continue;
         // The adapter plan is made (or found in the 4-entry cache) right before the job's first chunk: a miss waits for the
         // device to go idle before it recycles an entry, so chunks of earlier jobs never lose their adapter copies.
         AdapterPlan P;
         rc_final = plan_adapters(E, E.st[k % NSTAGE].stream, J.adapters, J.ad_off, J.n_adapters, ma, mi, go, ge, P);
-        for (size_t c = 0; c < J.chunks.size() && !rc_final; ++c, ++k) rc_final = submit(J, P, J.chunks[c], E.st[k % NSTAGE]);
+        for (int64_t s0 = 0; s0 < J.n_seqs && !rc_final; ++k) {
+            HostChunk c;
+            rc_final = next_chunk(J.seq_off, J.n_seqs, J.n_adapters, s0, c);
+            if (!rc_final && J.dec && c.max_n > J.max_seq_len)
+                rc_final = fail(PB200_ERR_ARG, "decision batches take windows of at most end_size bases");
+            if (!rc_final) rc_final = submit(J, P, c, E.st[k % NSTAGE]);
+            s0 = c.s1;
+        }
     }
     // Whatever happened, nothing may still be writing into the caller's `out` (or reading `seqs`) when we return.
     const std::string first_err = g_err;
@@ -751,9 +760,8 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
     if (!seq_off || !ad_off || !out) return fail(PB200_ERR_ARG, "NULL pointer");
     load_env_options();
     std::vector<CrossJob> jobs(1);
-    jobs[0] = CrossJob{seqs, seq_off, n_seqs, adapters, ad_off, n_adapters, out, {}};
-    if (int rc = validate_and_plan(seqs, seq_off, n_seqs, adapters, ad_off, n_adapters, pair_seq, pair_adapter, n_pairs, cross,
-                                   jobs[0].chunks)) return rc;
+    jobs[0] = CrossJob{seqs, seq_off, n_seqs, adapters, ad_off, n_adapters, out};
+    if (int rc = validate_args(seqs, seq_off, n_seqs, adapters, ad_off, n_adapters, pair_seq, pair_adapter, n_pairs, cross)) return rc;
     Engine *Ep = nullptr;
     if (int rc = get_engine(&Ep)) return rc;
     Engine &E = *Ep;
@@ -883,9 +891,9 @@ int batch_host_multi(const pb200_batch_t *batches, int n_batches, int ma, int mi
         if (B.n_seqs < 0 || B.n_adapters < 0) return fail(PB200_ERR_ARG, "negative count");
         if (B.n_seqs == 0 || B.n_adapters == 0) continue;
         if (!B.seq_off || !B.ad_off || !B.out) return fail(PB200_ERR_ARG, "NULL pointer");
-        jobs.push_back(CrossJob{B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, B.out, {}});
-        if (int rc = validate_and_plan(B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, nullptr, nullptr,
-                                       B.n_seqs * (int64_t)B.n_adapters, true, jobs.back().chunks)) return rc;
+        jobs.push_back(CrossJob{B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, B.out});
+        if (int rc = validate_args(B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, nullptr, nullptr,
+                                   B.n_seqs * (int64_t)B.n_adapters, true)) return rc;
     }
     if (jobs.empty()) return 0;
     Engine *Ep = nullptr;
@@ -917,11 +925,26 @@ void trim_threshold_table(double thr, int32_t len, int32_t *cmin) {
     }
 }
 
+// threshold tables are pure functions of (threshold, length): built once, reused by every later call
+std::shared_ptr<const std::vector<int32_t>> cached_threshold_table(double thr, int32_t len) {
+    static std::mutex mu;
+    static std::map<std::pair<double, int32_t>, std::shared_ptr<const std::vector<int32_t>>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    const auto key = std::make_pair(thr, len);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    auto t = std::make_shared<std::vector<int32_t>>((size_t)len);
+    trim_threshold_table(thr, len, t->data());
+    if (cache.size() >= 64) cache.clear();                     // growth guard (thresholds are few in practice)
+    cache[key] = t;
+    return t;
+}
+
 int batch_end_decisions(const pb200_end_batch_t *batches, int n_batches, int ma, int mi, int go, int ge) {
     if (n_batches < 0 || (n_batches > 0 && !batches)) return fail(PB200_ERR_ARG, "bad batch list");
     load_env_options();
     std::vector<CrossJob> jobs;
-    std::vector<std::vector<int32_t>> tables;
+    std::vector<std::shared_ptr<const std::vector<int32_t>>> tables;
     for (int b = 0; b < n_batches; ++b) {
         const pb200_end_batch_t &D = batches[b];
         const pb200_batch_t &B = D.batch;
@@ -936,18 +959,19 @@ int batch_end_decisions(const pb200_end_batch_t *batches, int n_batches, int ma,
             continue;
         }
         if (!B.seq_off || !B.ad_off) return fail(PB200_ERR_ARG, "NULL pointer");
-        CrossJob J{B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, B.out, {}};
-        if (int rc = validate_and_plan(B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, nullptr, nullptr,
-                                       B.n_seqs * (int64_t)B.n_adapters, true, J.chunks)) return rc;
-        // aligned length <= window + adapter: size the threshold table for the longest of both in this batch
-        int64_t max_n = 0, m_max = 0;
-        for (const HostChunk &c : J.chunks) max_n = std::max(max_n, c.max_n);
+        CrossJob J{B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, B.out};
+        if (int rc = validate_args(B.seqs, B.seq_off, B.n_seqs, B.adapters, B.ad_off, B.n_adapters, nullptr, nullptr,
+                                   B.n_seqs * (int64_t)B.n_adapters, true)) return rc;
+        // a window is seq[:end_size] / seq[-end_size:] (nanopore_read.py:172,194) and the aligned region is at most
+        // window + adapter columns long: that sizes the threshold table (windows are checked chunk by chunk)
+        if (D.end_size < 0) return fail(PB200_ERR_ARG, "negative end_size");
+        int64_t m_max = 0;
         for (int32_t a = 0; a < B.n_adapters; ++a) m_max = std::max<int64_t>(m_max, B.ad_off[a + 1] - B.ad_off[a]);
-        if (max_n + m_max + 2 > 65535) return fail(PB200_ERR_ARG, "windows too long for the device decisions (use the record API)");
+        if ((int64_t)D.end_size + m_max + 2 > 65535) return fail(PB200_ERR_ARG, "windows too long for the device decisions (use the record API)");
         J.dec = &D;
-        J.cmin_len = (int32_t)(max_n + m_max + 2);
-        tables.emplace_back((size_t)J.cmin_len);
-        trim_threshold_table(D.end_threshold, J.cmin_len, tables.back().data());
+        J.max_seq_len = D.end_size;
+        J.cmin_len = (int32_t)(D.end_size + m_max + 2);
+        tables.push_back(cached_threshold_table(D.end_threshold, J.cmin_len));
         jobs.push_back(std::move(J));
     }
     if (jobs.empty()) return 0;
@@ -962,7 +986,7 @@ int batch_end_decisions(const pb200_end_batch_t *batches, int n_batches, int ma,
         const pb200_end_batch_t &D = *jobs[j].dec;
         if (int rc = E.dec_cmin[j].ensure((size_t)jobs[j].cmin_len * 4)) return rc;
         if (int rc = E.dec_cols[j].ensure((size_t)std::max<int32_t>(D.n_score_cols, 1) * 4)) return rc;
-        CK(cudaMemcpyAsync(E.dec_cmin[j].p, tables[j].data(), (size_t)jobs[j].cmin_len * 4, cudaMemcpyHostToDevice, s0));
+        CK(cudaMemcpyAsync(E.dec_cmin[j].p, tables[j]->data(), (size_t)jobs[j].cmin_len * 4, cudaMemcpyHostToDevice, s0));
         if (D.n_score_cols > 0)
             CK(cudaMemcpyAsync(E.dec_cols[j].p, D.score_cols, (size_t)D.n_score_cols * 4, cudaMemcpyHostToDevice, s0));
         jobs[j].d_cmin = E.dec_cmin[j].as<int32_t>();

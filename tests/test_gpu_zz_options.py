@@ -178,7 +178,7 @@ def test_end_decisions_on_device_equal_host_rule(W):
     erec = W.adapter_alignment_batch(eb, eo, ea, eao, wl.DEFAULT_SCORING).reshape(-1, len(ads_e), 9)
     scols, ecols = [2, 0, 5, 2], [1]
     for end_size, extra, thr, min_trim, opts in ((150, 2, 75.0, 4, {}), (150, 0, 90.0, 1, {'chunk_tasks': 50000}),
-                                                 (100, 5, 50.0, 10, {'h2d_pack': 1}), (150, 2, 0.0, 4, {})):
+                                                 (150, 5, 50.0, 10, {'h2d_pack': 1}), (150, 2, 0.0, 4, {})):
         outs = _with(W, opts, lambda: W.adapter_end_decisions(
             [(sb, so, sa, sao, True, scols), (eb, eo, ea, eao, False, ecols)], wl.DEFAULT_SCORING, end_size, extra, thr,
             min_trim, want_records=True))
@@ -198,3 +198,24 @@ def test_flat_pipeline_with_device_decisions_matches_reference_cli(W, monkeypatc
         T._run(case)
     for case in T.BARCODE_CASES:
         T._run_demux(case)
+
+
+def test_bad_sequence_offsets_fail_cleanly_mid_pipeline(W):
+    """Cross mode checks the sequence offsets chunk by chunk while the pipeline runs: a non-monotone offset in a late
+    chunk returns PB200_ERR_ARG after the earlier chunks were submitted, the streams are drained, and the next call works;
+    a decision batch with a window longer than end_size is refused the same way."""
+    from porechop_b200 import workloads as wl
+    yt, yb = wl.nsk007()
+    _, sw, _ = wl.synth_end_windows(300000, yt, yb, seed=5)
+    sbuf, soff = wl.windows_to_batch(sw)
+    abuf, aoff = wl.pack_adapters([yt])
+    bad = soff.copy()
+    bad[290001] = bad[290000] - 5
+    with pytest.raises(W.EngineError) as e:
+        W.adapter_alignment_batch(sbuf, bad, abuf, aoff, wl.DEFAULT_SCORING)
+    assert 'error 102' in str(e.value) and 'not monotone' in str(e.value)
+    good = W.adapter_alignment_batch(sbuf[:150 * 2000], soff[:2001], abuf, aoff, wl.DEFAULT_SCORING)
+    assert np.array_equal(good, oracle_batch(sbuf[:150 * 2000], soff[:2001], abuf, aoff, wl.DEFAULT_SCORING))
+    with pytest.raises(W.EngineError) as e:
+        W.adapter_end_decisions([(sbuf, soff, abuf, aoff, True, [])], wl.DEFAULT_SCORING, 100, 2, 75.0, 4)
+    assert 'error 102' in str(e.value)
