@@ -137,6 +137,8 @@ int pb200TimingRead(double *dp_kernel_ms, long long *dp_kernel_launches, double 
  *   "rowoff"      1 = score pass in the row-offset arithmetic domain when it fits (default 0; same results)
  *   "h2d_pack"    1 = adapterAlignmentBatch converts the sequences to 4-bit codes on the host cores and uploads half
  *                 the bytes (default 0; same results; "pack_threads" = host threads of the packer, 0 = OpenMP default)
+ *   "profile"     1 = the score pass of long reads takes its substitution operands from a shared-memory query profile
+ *                 when every slot is (one read, two adapters): two ALU-pipe instructions per row less (default 0; same results)
  *   "short2p"     1 = sequences up to direct_max also take two passes: a score-only sweep of the same slot loop finds
  *                 the end cells, then only the bounded window left of each end cell is traced (default 0; same results)
  *   "tight_window" 1 = second-pass windows sized per alignment from the end cell's row and score instead of the

@@ -336,6 +336,24 @@ PB_HD uint32_t max2acc(uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, ui
 #endif
 }
 
+// Query profile (option "profile"): when both halves of a slot align the SAME read (cross mode pairs two adapters on one
+// read), the substitution operand of group row q depends only on the read base b -- six possible values per row (codes
+// 0..4 and the read padding code 5).  The kernels keep those words in shared memory and fetch a column's R operands with
+// two 128-bit loads instead of computing them with LOP3 + VIADDMNMX per row.  The word is produced by the very expression
+// lane_step uses, so both paths are identical by construction.
+PB_HD uint32_t profile_word(int q, uint32_t bcode, const Scoring &sc, const uint8_t *adA, int mA, int padA, const uint8_t *adB,
+                            int mB, int padB) {
+    const int iA = q - padA, iB = q - padB;
+    const bool realA = iA >= 1 && iA <= mA, realB = iB >= 1 && iB <= mB;
+    const uint32_t a = realA ? (uint32_t)adA[iA - 1] : (uint32_t)PB_PAD_V;
+    const uint32_t b = realB ? (uint32_t)adB[iB - 1] : (uint32_t)PB_PAD_V;
+    const uint32_t v2 = (a << 8) | (b << 24);
+    const uint32_t sf2 = ((realA ? sc.subF2 : sc.padF2) & 0xFFFFu) | ((realB ? sc.subF2 : sc.padF2) & 0xFFFF0000u);
+    const uint32_t hb = (bcode & 7u) << 4;                       // encoded byte (code << 4), the same base in both halves
+    const uint32_t h2 = (hb << 8) | (hb << 24);
+    return addmax2(xnor2(h2, v2), sc.subA2, sf2);
+}
+
 // R <= 4: one word per step (half A in bits 0..15, half B in bits 16..31); R = 5..8: word 0 = half A, word 1 = half B.
 template <int R> struct TraceWords { static constexpr int value = (R <= 4) ? 1 : 2; };
 template <int R> PB_HD int trace_word(int h, int r) { (void)r; return (R <= 4) ? 0 : h; }
@@ -359,15 +377,17 @@ template <int R> PB_HD int trace_shift(int h, int r) { return (R <= 4) ? (4 * r 
 #else
 #define PB_EXT(x) subm2((x), sc.geMag2)
 #endif
-template <int R, bool TRACE, bool KEEPV = false, bool ROWOFF = false>
+//   PROF / subs : the R substitution operands of this column are given (query profile, see profile_word) instead of being
+//                 computed from h2 -- two ALU-pipe instructions per row less; only when both halves read the same base
+template <int R, bool TRACE, bool KEEPV = false, bool ROWOFF = false, bool PROF = false>
 PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, const Scoring &sc, uint32_t *tw,
-                     uint32_t *vr = nullptr) {
+                     uint32_t *vr = nullptr, const uint32_t *subs = nullptr) {
     uint32_t diagX = L.prevRecvX, upX = recvX, upV = recvV;
     uint32_t accLo = 0u, accHi = 0u;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         // substitution (minus go) per half: codes equal -> ~(h^v) == -1 -> max(-1 + ma + 1 - go, mi - go) = ma - go
-        const uint32_t sub = addmax2(xnor2(h2, L.v2[r]), sc.subA2, L.sf2[r]);
+        const uint32_t sub = PROF ? subs[r] : addmax2(xnor2(h2, L.v2[r]), sc.subA2, L.sf2[r]);
         // S_diag + sub (biased).  ROWOFF: sub >= 0 by construction -> plain 32-bit add on the FMA pipe
         const uint32_t d = ROWOFF ? addp2(diagX, sub) : add2(diagX, sub);
         uint32_t hs, vs, s;

@@ -80,6 +80,7 @@ struct Options {
     int64_t chunk_bytes = 64ll << 20;   // sequence bytes per pipeline chunk (host-buffer API)
     int rowoff = 0;                // 1: score pass in the row-offset domain when it fits (measured: no gain)
     int scratch_mb = 128;          // cap on the resident trace scratch (MB); 72 keeps it L2-resident at ~10% lower speed
+    int profile = 0;               // 1: score pass fetches the substitution operands from a shared-memory query profile (same-read slots)
     int short2p = 0;               // 1: short sequences (<= direct_max) also go score pass -> bounded window (score-only trace_kernel)
     int tight_window = 0;          // 1: second-pass windows sized per alignment from the end cell's row and score (window_cols)
     int h2d_pack = 0;              // 1: host-buffer API converts to 4-bit codes on the host cores and uploads half the bytes
@@ -97,6 +98,7 @@ void load_env_options() {
         if (const char *v = getenv("PB200_TIGHT_WINDOW")) g_opt.tight_window = atoi(v);
         if (const char *v = getenv("PB200_H2D_PACK")) g_opt.h2d_pack = atoi(v);
         if (const char *v = getenv("PB200_SHORT2P")) g_opt.short2p = atoi(v);
+        if (const char *v = getenv("PB200_PROFILE")) g_opt.profile = atoi(v);
         if (const char *v = getenv("PB200_PACK_THREADS")) g_opt.pack_threads = atoi(v);
         if (const char *v = getenv("PB200_HBUF")) g_opt.hbuf_mode = !strcmp(v, "smem") ? 1 : !strcmp(v, "global") ? 2 : 0;
     });
@@ -312,10 +314,10 @@ bool class_hbuf_fits_smem(const Engine &E, int cls, int max_n) {
     return false;
 }
 
-template <int G, int R, bool RO>
+template <int G, int R, bool RO, bool PROF = false>
 int launch_score_variant(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsigned long long *counter,
                          const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, EndCell *ends) {
-    auto kern = score_kernel<G, R, RO>;
+    auto kern = score_kernel<G, R, RO, PROF>;
     int bps = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, PB_WARPS_PER_BLOCK * 32, 0));
     if (bps < 1) bps = 1;
@@ -339,10 +341,14 @@ template <int G, int R>
 int launch_score(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsigned long long *counter, const uint8_t *seq_codes,
                  const uint8_t *ad_codes, const Scoring &sc, const SchemeInfo &si, int m_max, EndCell *ends) {
     const long long c = rowoff_c(sc.mi, sc.go, sc.ge);
+    // query profile: every slot is (one read, two adapters) -- cross mode with an even number of adapters in the class
+    const bool prof = g_opt.profile != 0 && ts.tasks == nullptr && ts.n_cls_ad > 0 && (ts.n_cls_ad % 2) == 0;
     if (g_opt.rowoff && (long long)si.A * (m_max + 3) + c * G * R <= PB_I16_LIMIT) {
         const Scoring so = make_scoring(sc.ma, sc.mi, sc.go, sc.ge, true);
+        if (prof) return launch_score_variant<G, R, true, true>(E, stream, ts, counter, seq_codes, ad_codes, so, ends);
         return launch_score_variant<G, R, true>(E, stream, ts, counter, seq_codes, ad_codes, so, ends);
     }
+    if (prof) return launch_score_variant<G, R, false, true>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
     return launch_score_variant<G, R, false>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
 }
 int launch_score_class(Engine &E, cudaStream_t stream, int cls, const TaskSrc &ts,
@@ -1187,6 +1193,7 @@ int pb200SetOption(const char *name, const char *value) {
     else if (!strcmp(name, "tight_window")) g_opt.tight_window = atoi(value);
     else if (!strcmp(name, "h2d_pack")) g_opt.h2d_pack = atoi(value);
     else if (!strcmp(name, "short2p")) g_opt.short2p = atoi(value);
+    else if (!strcmp(name, "profile")) g_opt.profile = atoi(value);
     else if (!strcmp(name, "pack_threads")) g_opt.pack_threads = atoi(value);
     else if (!strcmp(name, "hbuf")) g_opt.hbuf_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;
     else return PB200_ERR_ARG;

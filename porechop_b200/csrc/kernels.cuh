@@ -453,14 +453,25 @@ __device__ __forceinline__ uint64_t load_cols(const uint8_t *p) {
 #ifndef PB_SCORE_MIN_BLOCKS
 #define PB_SCORE_MIN_BLOCKS 4
 #endif
-template <int G, int R, bool RO>
+// PROF = query profile (dp_core.cuh profile_word; option "profile"): every slot aligns ONE read against two adapters
+// (cross mode, even number of adapters in the class), so the R substitution operands of a column are fetched from a
+// per-group table in shared memory (6 base codes x G*R rows, two 128-bit loads per step) instead of being computed
+// (LOP3 + VIADDMNMX per row): 5 instead of 7 instructions per row, 4 instead of 6 on the ALU pipe -- the pipe that bounds
+// this kernel.  The ring then holds the table offset of a column's base instead of the packed bases.
+template <int G, int R> struct ProfGeom {
+    static constexpr int ROWS = G * R;
+    static constexpr int STRIDE = 6 * ROWS + 16;        // words per group; +64 B so neighbouring groups start in other banks
+};
+template <int G, int R, bool RO, bool PROF = false>
 __global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_SCORE_MIN_BLOCKS)
 score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
              const uint8_t *__restrict__ seq, const uint8_t *__restrict__ ads, Scoring sc, EndCell *__restrict__ ends) {
     constexpr int SPW = 32 / G;
     constexpr int CPL = PB_BLK / G;          // columns of a block each lane fetches
+    static_assert(!PROF || R == 8, "the profile variant fetches 8 operands per step");
     __shared__ ScoutCand scratch[PB_WARPS_PER_BLOCK][2 * 32];
     __shared__ uint32_t rings[PB_WARPS_PER_BLOCK][SPW][PB_RING];
+    __shared__ __align__(16) uint32_t profs[PROF ? PB_WARPS_PER_BLOCK * SPW * ProfGeom<G, R>::STRIDE : 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, g = lane % G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
@@ -468,6 +479,8 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
     const int64_t n_slots = (n_tasks + 1) / 2;
     ScoutCand *cand = scratch[warp];
     uint32_t *ring = rings[warp][grp];
+    // this lane's rows of the group's profile table (PROF): word [b * ROWS + r] = operand of row g*R + r + 1 for base code b
+    uint32_t *myprof = profs + (PROF ? ((size_t)(warp * SPW + grp) * ProfGeom<G, R>::STRIDE + g * R) : 0);
 
     Lane<R> L;
     HalfGeom gA, gB;
@@ -478,6 +491,10 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
     uint64_t pendA = 0, pendB = 0;           // raw bytes of the block that will be stored at the next block boundary
     gA = make_geom(0, 0, G, R); gB = gA;
     L.botX = sc.borderX2; L.botV = sc.negb2;
+    if (PROF) {      // a group that never gets a slot still runs the hot segments on dead state: its ring must hold valid offsets
+        for (int c = g; c < PB_RING; c += G) ring[c] = 0u;
+        __syncwarp();
+    }
 
     // fetch this lane's CPL columns of block `blk` (raw bytes; columns past the end are fixed up when stored)
     auto fetch = [&](int blk) {
@@ -493,7 +510,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
             const int col = c0 + c;
             const uint32_t bA = (col < nA) ? (uint32_t)((pendA >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H;
             const uint32_t bB = (col < nB) ? (uint32_t)((pendB >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H;
-            ring[col & (PB_RING - 1)] = pack_bases(bA, bB);
+            ring[col & (PB_RING - 1)] = PROF ? (bA >> 4) * (uint32_t)ProfGeom<G, R>::ROWS : pack_bases(bA, bB);
         }
     };
 
@@ -524,6 +541,16 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                     nmax = max(nA, nB);
                     seqA = seq + tA.seq_off; seqB = seq + tB.seq_off;
                     lane_init<R>(L, g, G, sc, ads + tA.ad_off, tA.m, false, ads + tB.ad_off, tB.m, false);
+                    if (PROF) {
+                        // both halves read sequence A (the launcher guarantees same-read slots); every lane fills, and later
+                        // reads, only its own rows of the table -- no synchronisation needed
+#pragma unroll
+                        for (int b = 0; b < 6; ++b)
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+                                myprof[b * ProfGeom<G, R>::ROWS + r] =
+                                    profile_word(g * R + r + 1, (uint32_t)b, sc, ads + tA.ad_off, tA.m, gA.pad, ads + tB.ad_off, tB.m, gB.pad);
+                    }
                     const bool emptyA = tA.n <= 0 || tA.m <= 0, emptyB = tB.n <= 0 || tB.m <= 0;
                     nmin = emptyA ? nB : (emptyB ? nA : min(nA, nB));
                     T = nmax + G - 1; t = 0;
@@ -550,7 +577,15 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                 uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
                 if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
                 const int j = t - g + 1;
-                lane_step<R, false, false, RO>(L, recvS, recvV, ring[(j - 1) & (PB_RING - 1)], sc, nullptr);
+                const uint32_t hx = ring[(j - 1) & (PB_RING - 1)];      // packed bases, or (PROF) the table offset of the base
+                if (PROF) {
+                    const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + hx);
+                    const uint4 p0 = pp[0], p1 = pp[1];
+                    const uint32_t subs[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                    lane_step<R, false, false, RO, true>(L, recvS, recvV, 0u, sc, nullptr, nullptr, subs);
+                } else {
+                    lane_step<R, false, false, RO>(L, recvS, recvV, hx, sc, nullptr);
+                }
                 lane_track_lastrow<R>(L, j, sc);
                 ++t;
             }
@@ -564,7 +599,14 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                 if (j >= 1 && j <= nmax) {          // nmax == 0 for exhausted groups
                     const uint32_t h2 = ring[(j - 1) & (PB_RING - 1)];
                     uint32_t vr[R];
-                    lane_step<R, false, true, RO>(L, recvS, recvV, h2, sc, nullptr, vr);
+                    if (PROF) {
+                        const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + h2);
+                        const uint4 p0 = pp[0], p1 = pp[1];
+                        const uint32_t subs[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                        lane_step<R, false, true, RO, true>(L, recvS, recvV, 0u, sc, nullptr, vr, subs);
+                    } else {
+                        lane_step<R, false, true, RO>(L, recvS, recvV, h2, sc, nullptr, vr);
+                    }
                     if (j < nmin) lane_track_lastrow<R>(L, j, sc);
                     else lane_track_general<R>(L, g, j, gA, gB, vr, sc);
                 }

@@ -94,7 +94,9 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
     }
 }
 
-template <int R, bool RO>
+// PROF: the query-profile variant of score_kernel -- per lane a table [6 base codes][R rows] of substitution operands built
+// with profile_word, the step fetches its R operands by the base code of the column (both halves read sequence A).
+template <int R, bool RO, bool PROF = false>
 void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, EndCell *eA, EndCell *eB) {
     const Task &tA = A.t, &tB = B.t;
     HalfGeom gA = make_geom(tA.n, tA.m, G, R), gB = make_geom(tB.n, tB.m, G, R);
@@ -106,6 +108,13 @@ void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, End
     std::vector<Lane<R>> L((size_t)G);
     for (int g = 0; g < G; ++g)
         lane_init<R>(L[g], g, G, sc, A.ad.data() + tA.ad_off, tA.m, false, B.ad.data() + tB.ad_off, tB.m, false);
+    std::vector<uint32_t> prof((size_t)G * 6 * R);           // [lane][base code][row]
+    if (PROF)
+        for (int g = 0; g < G; ++g)
+            for (int b = 0; b < 6; ++b)
+                for (int r = 0; r < R; ++r)
+                    prof[((size_t)g * 6 + b) * R + r] = profile_word(g * R + r + 1, (uint32_t)b, sc, A.ad.data() + tA.ad_off, tA.m,
+                                                                     gA.pad, B.ad.data() + tB.ad_off, tB.m, gB.pad);
     std::vector<uint32_t> sS((size_t)G), sV((size_t)G);
     for (int t = 0; t < T; ++t) {
         for (int g = 0; g < G; ++g) { sS[g] = L[g].botX; sV[g] = L[g].botV; }
@@ -115,12 +124,15 @@ void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, End
             if (j >= 1 && j <= nmax) {
                 int ja = std::min(j, tA.n) - 1, jb = std::min(j, tB.n) - 1;
                 uint32_t bA = ja >= 0 ? seqA[ja] : PB_PAD_H, bB = jb >= 0 ? seqB[jb] : PB_PAD_H;
+                if (j > tA.n) bA = PB_PAD_H;
+                if (j > tB.n) bB = PB_PAD_H;
+                const uint32_t *subs = PROF ? &prof[((size_t)g * 6 + (bA >> 4)) * R] : nullptr;    // kernel: ring holds (bA >> 4) * ROWS
                 if (j < nmin) {
-                    lane_step<R, false, false, RO>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr);
+                    lane_step<R, false, false, RO, PROF>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, nullptr, subs);
                     lane_track_lastrow<R>(L[g], j, sc);
                 } else {
                     uint32_t vr[R];
-                    lane_step<R, false, true, RO>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, vr);
+                    lane_step<R, false, true, RO, PROF>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, vr, subs);
                     lane_track_general<R>(L[g], g, j, gA, gB, vr, sc);
                 }
             }
@@ -173,13 +185,17 @@ int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char
     Half B = nB >= 0 ? make_half(seqB, nB, adB, mB, 1) : make_half("", 0, "", 0, -1);
     int status = 0;
     const bool tight = (mode & 4) != 0;
+    const bool prof = (mode & 8) != 0;            // query-profile score pass (R = 8, both halves the same read)
     mode &= 3;
     if (mode >= 1) {
         EndCell eA, eB;
         // mode 1: classic score pass; mode 2: row-offset domain (plain-add diagonal), the engine's default when the
         // offsets fit the int16 domain
         const Scoring so = make_scoring(ma, mi, go, ge, mode == 2);
-        if (mode == 2) {
+        if (prof && R == 8) {
+            if (mode == 2) run_score_group<8, true, true>(G, A, B, so, &eA, &eB);
+            else run_score_group<8, false, true>(G, A, B, so, &eA, &eB);
+        } else if (mode == 2) {
             switch (R) {
                 case 5: run_score_group<5, true>(G, A, B, so, &eA, &eB); break;
                 case 6: run_score_group<6, true>(G, A, B, so, &eA, &eB); break;

@@ -129,6 +129,36 @@ def test_emu_tight_window_bound_vs_oracle():
         assert rb == oracle_record(slots[1][0], slots[1][1], sc), (G, R, sc, slots[1])
 
 
+def test_emu_query_profile_score_pass_vs_oracle():
+    """Option "profile": the score pass takes its substitution operands from the query profile (dp_core.cuh profile_word,
+    lane_step<.., PROF>) -- one read against two adapters per slot, classic and row-offset domain, classic and tight
+    windows, all four group widths at R = 8; records equal the oracle's."""
+    rng = random.Random(515)
+    n_rowoff = 0
+    for it in range(700):
+        G = rng.choice([4, 8, 16, 32])
+        sc = rng.choice(SCHEMES)
+        if max(abs(x) for x in sc) * (G * 8 + 3) > 4000 or not (sc[2] < 0 and sc[3] < 0):
+            continue
+        rd, adA = _gen(rng, G * 8, 50, 700)
+        al = sorted(set(rd + adA)) or ['A']
+        adB = ''.join(rng.choice(al) for _ in range(rng.randint(0 if rng.random() < 0.05 else 1, G * 8)))
+        if adB and rng.random() < 0.6:
+            p = rng.randint(0, len(rd))
+            rd = rd[:p] + _mut(rng, adB, al) + rd[p:]
+        mode = 1
+        c = max(0, (sc[3] if sc[2] == sc[3] else sc[2]) - sc[1])          # row-offset step (dp_core.cuh rowoff_c)
+        if rng.random() < 0.4 and max(abs(x) for x in sc) * (G * 8 + 3) + c * G * 8 <= 4000:
+            mode = 2
+            n_rowoff += 1
+        mode |= 8 | (4 if rng.random() < 0.5 else 0)
+        st, ra, rb = emu_slot((rd, adA), (rd, adB), G, 8, mode, sc)
+        assert st == 0
+        assert ra == oracle_record(rd, adA, sc), (G, mode, sc, rd, adA)
+        assert rb == oracle_record(rd, adB, sc), (G, mode, sc, rd, adB)
+    assert n_rowoff > 20
+
+
 def test_emu_window_clips_real_adapter_lengths():
     """Two-pass with real adapter lengths (22-111) on multi-kb reads: the window really clips."""
     rng = random.Random(7)

@@ -20,7 +20,7 @@ def W():
 
 
 def _with(W, opts, fn):
-    defaults = {'h2d_pack': 0, 'tight_window': 0, 'short2p': 0, 'direct_max': 512, 'chunk_tasks': 131072, 'pack_threads': 0}
+    defaults = {'h2d_pack': 0, 'tight_window': 0, 'short2p': 0, 'profile': 0, 'rowoff': 0, 'direct_max': 512, 'chunk_tasks': 131072, 'pack_threads': 0}
     try:
         for k, v in opts.items():
             W.set_option(k, v)
@@ -219,3 +219,26 @@ def test_bad_sequence_offsets_fail_cleanly_mid_pipeline(W):
     with pytest.raises(W.EngineError) as e:
         W.adapter_end_decisions([(sbuf, soff, abuf, aoff, True, [])], wl.DEFAULT_SCORING, 100, 2, 75.0, 4)
     assert 'error 102' in str(e.value)
+
+
+def test_query_profile_score_pass_equals_oracle(W):
+    """profile: score_kernel<.., PROF> (substitution operands from a shared-memory query profile) for classes with an even
+    number of adapters, the classic kernel for the others in the same call; with the row-offset domain and tight windows;
+    ragged lengths incl. reads shorter than a segment; a masked re-alignment round through the pair list (classic path)."""
+    from porechop_b200 import workloads as wl
+    yt, yb = wl.nsk007()
+    full = wl.demux_adapters()[0][-1]
+    sets = [s_ for s_ in wl.load_adapter_sets()['sets'] if s_['name'].endswith('(forward)')][:5]
+    bcs = [s_['start'][1] for s_ in sets] + [s_['end'][1] for s_ in sets]
+    buf, off = wl.synth_reads(90, yt, yb, seed=23, chimera_p=0.4, max_len=14000)
+    rng = random.Random(2)
+    short = [''.join(rng.choice('ACGTN') for _ in range(rng.randint(520, 900))) for _ in range(30)] + ['', 'ACGT' * 200]
+    sb2, so2 = W.pack_sequences(short)
+    buf2 = np.concatenate([buf, sb2]); off2 = np.concatenate([off, so2[1:] + off[-1]])
+    for ads in ([yt, yb], [yt, yb, full], bcs, [yt, yb, full, bcs[0]]):
+        abuf, aoff = wl.pack_adapters(ads)
+        for sc in (wl.DEFAULT_SCORING, (3, -6, -5, -5)):
+            exp = oracle_batch(buf2, off2, abuf, aoff, sc)
+            for opts in ({'profile': 1}, {'profile': 1, 'rowoff': 1, 'tight_window': 1}):
+                got = _with(W, opts, lambda: W.adapter_alignment_batch(buf2, off2, abuf, aoff, sc))
+                assert np.array_equal(got, exp), (len(ads), sc, opts)

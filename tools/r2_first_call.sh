@@ -38,5 +38,8 @@ run demux_decisions --workload demux --e2e-decisions
 run demux_short2p_tight --workload demux --opt short2p=1 --opt tight_window=1
 run middle_default --workload middle
 run middle_tight --workload middle --opt tight_window=1
+run middle_profile --workload middle --opt profile=1
+run middle_profile_rowoff --workload middle --opt profile=1 --opt rowoff=1
+run middle_profile_tight_pack --workload middle --opt profile=1 --opt tight_window=1 --opt h2d_pack=1
 run middle_tight_pack --workload middle --opt tight_window=1 --opt h2d_pack=1
 cat $out/summary.txt
