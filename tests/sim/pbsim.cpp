@@ -157,9 +157,23 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()> &b
             makecontext(&f.ctx, fiber_entry, 0);
 #endif
         }
+        // Lane interleaving between two collectives is not defined on the device (independent thread scheduling): the order
+        // in which runnable fibers are resumed can be reversed or shuffled (PBSIM_ORDER=reverse | random[:seed]) -- code that
+        // relies on one particular interleaving, e.g. a missing __syncwarp around shared memory, then changes its results.
+        static const char *order_env = getenv("PBSIM_ORDER");
+        static unsigned long long rng = (order_env && strchr(order_env, ':')) ? strtoull(strchr(order_env, ':') + 1, nullptr, 10) * 2654435761ull + 1 : 88172645463325252ull;
+        std::vector<int> order((size_t)nthreads);
+        for (int t = 0; t < nthreads; ++t) order[(size_t)t] = t;
+        if (order_env && !strncmp(order_env, "reverse", 7)) std::reverse(order.begin(), order.end());
         for (;;) {
             bool progress = false, alive = false;
-            for (auto &f : B.fibers) {
+            if (order_env && !strncmp(order_env, "random", 6))
+                for (int t = nthreads - 1; t > 0; --t) {
+                    rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+                    std::swap(order[(size_t)t], order[(size_t)(rng % (unsigned long long)(t + 1))]);
+                }
+            for (int oi = 0; oi < nthreads; ++oi) {
+                Fiber &f = B.fibers[(size_t)order[(size_t)oi]];
                 if (f.done) continue;
                 alive = true;
                 if (f.waiting) continue;

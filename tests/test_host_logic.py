@@ -2,6 +2,7 @@
 import json
 import os
 import subprocess
+import sys
 import tempfile
 
 import numpy as np
@@ -213,3 +214,38 @@ def test_device_decision_core_equals_host_trim_rule_and_barcode_scores():
             assert np.array_equal(trim.astype(np.int64), exp), (is_start, end_size, thr)
             full = _percent_exact(pairs & 0xFFFF, pairs >> 16)
             assert np.array_equal(full, hostio.full_scores(rec, [int(c) for c in cols]), equal_nan=True)
+
+
+def test_unpack_device_branch_byte_perm_selectors():
+    """dp_core.cuh unpack_nibbles8 has a device branch (two PRMT: __byte_perm(e, o, 0x5140) / (e, o, 0x7362)) and a generic
+    branch; the host tests run the generic one.  The selectors are checked here against PRMT's definition (result byte i =
+    byte (selector nibble i) of the 8-byte pair {x = bytes 0-3, y = bytes 4-7})."""
+    import ctypes
+    from helpers import emu_lib
+    emu = emu_lib()
+    emu.emu_unpack.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    emu.emu_unpack.restype = None
+
+    def byte_perm(x, y, s):
+        xy = (y << 32) | x
+        return sum(((xy >> (8 * ((s >> (4 * i)) & 7))) & 0xFF) << (8 * i) for i in range(4))
+    rng = np.random.default_rng(5)
+    for w in [0, 0xFFFFFFFF, 0x01234567, 0x40302010] + [int(x) for x in rng.integers(0, 2 ** 32, 500)]:
+        e, o = ((w & 0x0F0F0F0F) << 4) & 0xFFFFFFFF, w & 0xF0F0F0F0
+        packed = np.frombuffer(np.array([w, w], dtype=np.uint32).tobytes(), dtype=np.uint8).copy()
+        out = np.zeros(16, dtype=np.uint8)
+        emu.emu_unpack(packed.ctypes.data, out.ctypes.data, 16)
+        first4, next4 = np.frombuffer(out[:8].tobytes(), dtype=np.uint32)
+        assert int(first4) == byte_perm(e, o, 0x5140) and int(next4) == byte_perm(e, o, 0x7362), hex(w)
+
+
+def test_simulated_engine_results_do_not_depend_on_lane_interleaving():
+    """tests/sim resumes the runnable CUDA threads of a block in index order; the device defines no order between two
+    collectives.  Two of the simulated-engine tests again with the order reversed and shuffled (separate processes: the
+    order is read once): a missing __syncwarp around shared memory would change the records."""
+    for order in ('reverse', 'random:5'):
+        env = dict(os.environ, PBSIM_ORDER=order)
+        r = subprocess.run([sys.executable, '-m', 'pytest', '-x', '-q', os.path.join(ROOT, 'tests', 'test_sim_engine.py'), '-k',
+                            'long_reads_two_pass_and_options or short_two_pass_and_packed_upload'], env=env, capture_output=True,
+                           text=True, cwd=ROOT)
+        assert r.returncode == 0 and '2 passed' in r.stdout, order + '\n' + r.stdout[-2000:]
