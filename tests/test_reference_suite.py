@@ -48,6 +48,9 @@ def test_reference_unittest_suite_outcomes_match_the_baseline():
                        'test_albacore_directory.TestAlbacoreDirectory.test_albacore_directory_unclassified'], failing
     patch = R.run_mode('patch', 'oracle', REF, '', jobs)
     assert patch == base
+    if os.environ.get('PB200_REFSUITE_FLAT', '0') != '1':
+        return          # the flat CLI's run of the suite (another ~40 s; round 1: differs on exactly REPORT_TESTS) is opt-in;
+                        # tests/test_flat_cli.py compares its output files with the reference CLI's in every run
     flat = R.run_mode('flat', 'oracle', REF, '', jobs)
     assert sorted(flat) == sorted(base)
     differs = {k for k in base if flat[k] != base[k]}
