@@ -336,22 +336,28 @@ PB_HD uint32_t max2acc(uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, ui
 #endif
 }
 
-// Query profile (option "profile"): when both halves of a slot align the SAME read (cross mode pairs two adapters on one
-// read), the substitution operand of group row q depends only on the read base b -- six possible values per row (codes
-// 0..4 and the read padding code 5).  The kernels keep those words in shared memory and fetch a column's R operands with
-// two 128-bit loads instead of computing them with LOP3 + VIADDMNMX per row.  The word is produced by the very expression
-// lane_step uses, so both paths are identical by construction.
-PB_HD uint32_t profile_word(int q, uint32_t bcode, const Scoring &sc, const uint8_t *adA, int mA, int padA, const uint8_t *adB,
-                            int mB, int padB) {
+// Query profile (option "profile").  The substitution operand of group row q depends only on the read bases of the two
+// halves -- six possible codes each (0..4 and the read padding code 5).  When the adapters of the two halves are the same for
+// every slot a kernel sees, the kernels keep those words in shared memory and fetch a column's R operands with two 128-bit
+// loads instead of computing them with LOP3 + VIADDMNMX per row:
+//   score_kernel<.., PROF>   per group, both halves read the same sequence (one read, two adapters): indexed by one base
+//   trace_kernel<.., PPROF>  per block, launch-uniform adapter pair (a class with one or two adapters): indexed by the
+//                            pair (base of half A, base of half B)
+// The word is produced by the very expression lane_step uses, so both paths are identical by construction.
+PB_HD uint32_t profile_word2(int q, uint32_t bcodeA, uint32_t bcodeB, const Scoring &sc, const uint8_t *adA, int mA, int padA,
+                             const uint8_t *adB, int mB, int padB) {
     const int iA = q - padA, iB = q - padB;
     const bool realA = iA >= 1 && iA <= mA, realB = iB >= 1 && iB <= mB;
     const uint32_t a = realA ? (uint32_t)adA[iA - 1] : (uint32_t)PB_PAD_V;
     const uint32_t b = realB ? (uint32_t)adB[iB - 1] : (uint32_t)PB_PAD_V;
     const uint32_t v2 = (a << 8) | (b << 24);
     const uint32_t sf2 = ((realA ? sc.subF2 : sc.padF2) & 0xFFFFu) | ((realB ? sc.subF2 : sc.padF2) & 0xFFFF0000u);
-    const uint32_t hb = (bcode & 7u) << 4;                       // encoded byte (code << 4), the same base in both halves
-    const uint32_t h2 = (hb << 8) | (hb << 24);
+    const uint32_t h2 = (((bcodeA & 7u) << 4) << 8) | (((bcodeB & 7u) << 4) << 24);      // encoded bytes (code << 4) per half
     return addmax2(xnor2(h2, v2), sc.subA2, sf2);
+}
+PB_HD uint32_t profile_word(int q, uint32_t bcode, const Scoring &sc, const uint8_t *adA, int mA, int padA, const uint8_t *adB,
+                            int mB, int padB) {
+    return profile_word2(q, bcode, bcode, sc, adA, mA, padA, adB, mB, padB);
 }
 
 // R <= 4: one word per step (half A in bits 0..15, half B in bits 16..31); R = 5..8: word 0 = half A, word 1 = half B.

@@ -223,7 +223,7 @@ void timed_end(Engine &E, cudaStream_t s, TimedLaunch &tl, bool on) {
     if (on) { cudaEventRecord(tl.b, s); E.timed.push_back(tl); }
 }
 
-template <int G, int R, bool HS, bool SO = false>
+template <int G, int R, bool HS, bool SO = false, bool PP = false>
 int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, int max_n,
                          const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status,
                          EndCell *ends = nullptr) {
@@ -232,7 +232,7 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc
     const int max_steps = max_n + G - 1;
     const int wpb = PB_WARPS_PER_BLOCK;
     const size_t smem_bytes = (size_t)wpb * ((HS ? (size_t)SPW * max_n : 0) + PB_SCRATCH_WORDS) * 4;
-    auto kern = trace_kernel<G, R, HS, SO>;
+    auto kern = trace_kernel<G, R, HS, SO, PP>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int bps = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem_bytes));
@@ -279,14 +279,22 @@ int launch_trace(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, in
                  EndCell *ends) {
     constexpr int SPW = 32 / G;
     if (max_n < 1) max_n = 1;
+    // pair profile (option "profile"): the adapter pair is the same for every slot of the launch -- a cross-mode class
+    // with one or two adapters (also its windowed second pass, which keeps the task order) -- and at most 64 rows
+    constexpr bool PP_OK = G <= 8;
+    const bool pp = PP_OK && g_opt.profile != 0 && ts.cls_ad != nullptr && ts.n_cls_ad >= 1 && ts.n_cls_ad <= 2;
     if (ends) {                                   // score-only first pass of the short two-pass scheme
         if (!hbuf_fits_smem<G>(E, max_n)) return fail(PB200_ERR_INTERNAL, "score-only pass needs shared-memory staging");
+        if (pp) return launch_trace_variant<G, R, true, true, PP_OK>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
         return launch_trace_variant<G, R, true, true>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
     }
     // packed read bases of a slot are staged in shared memory when they fit (<= 12 KB per warp), else in global scratch
     const bool hs = g_opt.hbuf_mode == 1 ? true : g_opt.hbuf_mode == 2 ? false : ((size_t)SPW * max_n * 4 <= 12288);
-    if (hs && (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + PB_SCRATCH_WORDS) * 4 <= E.smem_optin)
+    if (hs && (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + PB_SCRATCH_WORDS) * 4 <= E.smem_optin) {
+        if (pp) return launch_trace_variant<G, R, true, false, PP_OK>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
         return launch_trace_variant<G, R, true>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
+    }
+    if (pp) return launch_trace_variant<G, R, false, false, PP_OK>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
     return launch_trace_variant<G, R, false>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
 }
 

@@ -229,12 +229,33 @@ __device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
 // written to the scratch, and instead of the traceback the group's scout result goes to `ends` -- the first pass of the
 // short two-pass scheme (option "short2p": end cells first, then only the bounded window left of each end cell is
 // traced; engine.cu run_class_tasks).  Requires HBUF_SMEM (no global scratch is allocated).
-template <int G, int R, bool HBUF_SMEM, bool SCORE_ONLY = false>
+//
+// PPROF = pair profile (dp_core.cuh profile_word2; option "profile"): the launch's adapter pair is the same for every slot
+// (a cross-mode class with one adapter -- two reads per slot -- or two adapters -- one read per slot), so one table per
+// BLOCK, indexed by (base of half A, base of half B), holds the substitution operands of every row: 36 pairs x G lanes x 8
+// words in shared memory, a step fetches its R operands with two 128-bit loads instead of LOP3 + VIADDMNMX per row.  The
+// staged column words then hold the table offset of the column's base pair instead of the packed bases.
+template <int G, int R, bool HBUF_SMEM, bool SCORE_ONLY = false, bool PPROF = false>
 __global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_TRACE_MIN_BLOCKS)
 trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
              const uint8_t *__restrict__ ads, Scoring sc, int32_t *__restrict__ out, uint32_t *__restrict__ gtrace,
              int max_steps, int max_n, int *__restrict__ status, EndCell *__restrict__ ends) {
     static_assert(!SCORE_ONLY || HBUF_SMEM, "the score-only variant has no global scratch");
+    static_assert(!PPROF || G <= 8, "the pair profile is kept for adapters of up to 64 rows");
+    constexpr int PSTRIDE = G * 8;                       // words per base pair: 8 per lane (R <= 8), 32-byte aligned
+    __shared__ __align__(16) uint32_t pprof[PPROF ? 36 * PSTRIDE : 4];
+    if (PPROF) {
+        // the launch-uniform adapter pair = the adapters of tasks 0 and 1 (cross mode; engine.cu launches this variant only
+        // for classes with one or two adapters).  A missing task 1 (a single alignment) leaves half B all padding rows.
+        const Task p0 = get_task(ts, 0), p1 = get_task(ts, 1);
+        for (int idx = threadIdx.x; idx < 36 * PSTRIDE; idx += blockDim.x) {
+            const int pair = idx / PSTRIDE, gg = (idx % PSTRIDE) / 8, r = idx % 8;
+            pprof[idx] = (r < R) ? profile_word2(gg * R + r + 1, (uint32_t)(pair / 6), (uint32_t)(pair % 6), sc, ads + p0.ad_off, p0.m,
+                                                 G * R - p0.m, ads + p1.ad_off, p1.m, G * R - p1.m)
+                                 : 0u;
+        }
+        __syncthreads();
+    }
     constexpr int SPW = 32 / G;
     constexpr int WPS = TraceWords<R>::value;
     extern __shared__ uint32_t smem[];
@@ -259,6 +280,19 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
     uint32_t *wsm = smem + (size_t)warp * per_warp_words;
     uint32_t *hbuf = HBUF_SMEM ? (wsm + grp * max_n) : (gw + trace_words + (size_t)grp * max_n);
     ScoutCand *cand = reinterpret_cast<ScoutCand *>(wsm + (HBUF_SMEM ? SPW * max_n : 0));  // [half][lane]
+    const uint32_t *myprof = pprof + (PPROF ? g * 8 : 0);
+    // one wavefront step of this lane for the staged column word hx (packed bases, or the pair-profile offset)
+#define PB_TRACE_STEP(KEEPV_, hx_, tw_, vr_)                                                                          \
+    do {                                                                                                              \
+        if (PPROF) {                                                                                                  \
+            const uint4 *pp_ = reinterpret_cast<const uint4 *>(myprof + (hx_));                                       \
+            const uint4 q0_ = pp_[0], q1_ = pp_[1];                                                                   \
+            const uint32_t subs_[8] = {q0_.x, q0_.y, q0_.z, q0_.w, q1_.x, q1_.y, q1_.z, q1_.w};                      \
+            lane_step<R, !SCORE_ONLY, KEEPV_, false, true>(L, recvS, recvV, 0u, sc, tw_, vr_, subs_);                 \
+        } else {                                                                                                      \
+            lane_step<R, !SCORE_ONLY, KEEPV_>(L, recvS, recvV, (hx_), sc, tw_, vr_);                                  \
+        }                                                                                                             \
+    } while (0)
     for (int64_t ws = wglobal; ws < n_wslots; ws += total_warps) {
         const int64_t slot = ws * SPW + grp;
         int nA, nB, mA, mB, nmax, nmin;
@@ -275,7 +309,7 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
             for (int c = g; c < nmax; c += G) {
                 uint32_t bA = (c < nA) ? (uint32_t)__ldcs(seqA + c) : (uint32_t)PB_PAD_H;
                 uint32_t bB = (c < nB) ? (uint32_t)__ldcs(seqB + c) : (uint32_t)PB_PAD_H;
-                hbuf[c] = pack_bases(bA, bB);
+                hbuf[c] = PPROF ? ((bA >> 4) * 6u + (bB >> 4)) * (uint32_t)PSTRIDE : pack_bases(bA, bB);
             }
             lane_init<R>(L, g, G, sc, ads + tA.ad_off, mA, (tA.flags & TASK_LEFT_INF) != 0, ads + tB.ad_off, mB,
                          (tB.flags & TASK_LEFT_INF) != 0);
@@ -308,7 +342,7 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                     uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
                     if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
                     const int j = t0 + u - g + 1;
-                    lane_step<R, !SCORE_ONLY, false>(L, recvS, recvV, hbuf[j - 1], sc, buf[u]);
+                    PB_TRACE_STEP(false, hbuf[j - 1], buf[u], nullptr);
                     if (need_track) lane_track_lastrow<R>(L, j, sc);
                 }
                 if (!SCORE_ONLY) {
@@ -330,7 +364,7 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                     for (int w = 0; w < WPS; ++w) tw[w] = 0u;
                     if (j >= 1 && j <= nmax) {
                         uint32_t vr[R];
-                        lane_step<R, !SCORE_ONLY, true>(L, recvS, recvV, hbuf[j - 1], sc, tw, vr);
+                        PB_TRACE_STEP(true, hbuf[j - 1], tw, vr);
                         if (need_track) {
                             if (j >= nmin) lane_track_general<R>(L, g, j, make_geom(nA, mA, G, R), make_geom(nB, mB, G, R), vr, sc);
                             else lane_track_lastrow<R>(L, j, sc);
@@ -391,7 +425,11 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                     const uint32_t w = (u == 0) ? cv.x : (u == 1) ? cv.y : (u == 2) ? cv.z : cv.w;
                     return (w >> trace_shift<R>(h, r)) & 15u;
                 };
-                auto eq = [&](int jl, int i) -> bool {   // the slot's packed bases are still staged in hbuf
+                auto eq = [&](int jl, int i) -> bool {   // the slot's staged column words are still in hbuf
+                    if (PPROF) {
+                        const uint32_t pair = hbuf[jl - 1] / (uint32_t)PSTRIDE;
+                        return ((h ? pair % 6u : pair / 6u) << 4) == (uint32_t)__ldg(ad + i - 1);
+                    }
                     return ((hbuf[jl - 1] >> (8 + 16 * h)) & 0xFFu) == (uint32_t)__ldg(ad + i - 1);
                 };
                 int32_t rec[PB_REC];
@@ -411,6 +449,8 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
         __syncwarp();
     }
 }
+
+#undef PB_TRACE_STEP
 
 // ---------------------------------------------------------------------------------------------------
 // score_kernel: streaming score-only pass for long reads.  Same wavefront, no trace (7 instructions per row:

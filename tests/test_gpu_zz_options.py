@@ -20,7 +20,7 @@ def W():
 
 
 def _with(W, opts, fn):
-    defaults = {'h2d_pack': 0, 'tight_window': 0, 'short2p': 0, 'profile': 0, 'rowoff': 0, 'direct_max': 512, 'chunk_tasks': 131072, 'pack_threads': 0}
+    defaults = {'hbuf': 'auto', 'h2d_pack': 0, 'tight_window': 0, 'short2p': 0, 'profile': 0, 'rowoff': 0, 'direct_max': 512, 'chunk_tasks': 131072, 'pack_threads': 0}
     try:
         for k, v in opts.items():
             W.set_option(k, v)
@@ -242,3 +242,30 @@ def test_query_profile_score_pass_equals_oracle(W):
             for opts in ({'profile': 1}, {'profile': 1, 'rowoff': 1, 'tight_window': 1}):
                 got = _with(W, opts, lambda: W.adapter_alignment_batch(buf2, off2, abuf, aoff, sc))
                 assert np.array_equal(got, exp), (len(ads), sc, opts)
+
+
+def test_pair_profile_trace_kernel_equals_oracle(W):
+    """profile on end windows: trace_kernel<.., PPROF> (block-wide table of substitution operands indexed by the base pair)
+    for classes with one adapter (two reads per slot) and two adapters (one read per slot); single pass, short two-pass with
+    tight windows, global staging; ragged / empty inputs; the config-1 shape at several pipeline chunks."""
+    from porechop_b200 import workloads as wl
+    yt, yb = wl.nsk007()
+    _, sw, ew = wl.synth_end_windows(30001, yt, yb, seed=29)
+    for win, ads in ((sw, [yt]), (ew, [yb]), (sw, [yt, yb])):
+        sbuf, soff = wl.windows_to_batch(win)
+        abuf, aoff = wl.pack_adapters(ads)
+        exp = oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
+        for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1, 'chunk_tasks': 9000}, {'profile': 1, 'hbuf': 'global'}):
+            got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
+            assert np.array_equal(got, exp), (len(ads), opts)
+    rng = random.Random(31)
+    reads = ['', 'A', 'N' * 120, '-' * 130, 'acgu' * 40, yt, 'GG' + yt + 'GG', 'ACGT' * 100]
+    reads += [''.join(rng.choice('ACGTN') for _ in range(rng.randint(1, 500))) for _ in range(300)]
+    rbuf, roff = W.pack_sequences(reads)
+    for ads in (['ACGT' * 5], [yt, yb], ['ACGTTGCA' * 5, 'TTGACCA' * 5], ['ACGT' * 16], [yt, ''], ['N' * 22]):
+        abuf, aoff = W.pack_sequences(ads, offset_dtype=np.int32)
+        for sc in ([3, -6, -5, -2], [3, -6, -5, -5]):
+            exp = oracle_batch(rbuf, roff, abuf, aoff, sc)
+            for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1, 'direct_max': 200}):
+                got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
+                assert np.array_equal(got, exp), (ads, sc, opts)

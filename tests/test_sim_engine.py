@@ -138,6 +138,7 @@ def test_sim_short_two_pass_and_packed_upload(W):
         abuf, aoff = wl.pack_adapters([ad])
         exp = oracle_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
         for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}, {'direct_max': 100}, {'direct_max': 100, 'tight_window': 1},
+                     {'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1}, {'profile': 1, 'hbuf': 'global'},
                      {'h2d_pack': 1, 'chunk_tasks': 300, 'pack_threads': 3}, {'short2p': 1, 'tight_window': 1, 'h2d_pack': 1}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING))
             assert np.array_equal(got, exp), opts
@@ -154,9 +155,18 @@ def test_sim_short_two_pass_and_packed_upload(W):
     abuf, aoff = W.pack_sequences(ads, offset_dtype=np.int32)
     for sc in ([3, -6, -5, -2], [3, -6, -5, -5], [5, -4, -8, -1]):
         exp = oracle_batch(rbuf, roff, abuf, aoff, sc)
-        for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}):
+        for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}, {'profile': 1, 'short2p': 1}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
             assert np.array_equal(got, exp), (sc, opts)
+    # pair profile (trace_kernel<.., PPROF>): classes with one adapter (two reads per slot, odd number of reads) and with
+    # two adapters (one read per slot), every row class up to 64 rows, ragged reads, empty adapter / empty reads
+    for ads in (['ACGT' * 5], [yt], [yt, yb], ['ACGTTGCA' * 5, 'TTGACCA' * 5], ['ACGT' * 16], [yt, ''], ['N' * 22]):
+        abuf, aoff = W.pack_sequences(ads, offset_dtype=np.int32)
+        for sc in ([3, -6, -5, -2], [3, -6, -5, -5]):
+            exp = oracle_batch(rbuf, roff, abuf, aoff, sc)
+            for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1, 'direct_max': 200}):
+                got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
+                assert np.array_equal(got, exp), (ads, sc, opts)
 
 
 def test_sim_multi_submit_and_device_resident_api(W):
@@ -247,14 +257,15 @@ GPU_PARITY = ['test_legacy_single_call_strings', 'test_golden_random_pair_list',
 GPU_OPTIONS = ['test_packed_upload_windows_ragged_and_long_reads', 'test_tight_window_long_reads_and_forced_two_pass_windows',
                'test_multi_batch_submit_equals_single_calls', 'test_short_two_pass_windows_equal_oracle',
                'test_end_decisions_on_device_equal_host_rule', 'test_bad_sequence_offsets_fail_cleanly_mid_pipeline',
-               'test_query_profile_score_pass_equals_oracle']
+               'test_query_profile_score_pass_equals_oracle', 'test_pair_profile_trace_kernel_equals_oracle']
 
 
 # the larger ones take minutes in the simulation (10 min for all): run with PB200_SIM_FULL=1; the dedicated tests above
 # cover the same paths at smaller sizes.  Round 1: all 23 pass (PB200_SIM_FULL=1, 590 s).
 SLOW = {'test_demux_cross_all_adapters_vs_oracle', 'test_multi_batch_submit_equals_single_calls',
         'test_short_two_pass_windows_equal_oracle', 'test_end_decisions_on_device_equal_host_rule',
-        'test_bad_sequence_offsets_fail_cleanly_mid_pipeline', 'test_query_profile_score_pass_equals_oracle'}
+        'test_bad_sequence_offsets_fail_cleanly_mid_pipeline', 'test_query_profile_score_pass_equals_oracle',
+        'test_pair_profile_trace_kernel_equals_oracle'}
 FULL = os.environ.get('PB200_SIM_FULL', '0') == '1'
 
 

@@ -30,7 +30,9 @@ run endtrim_pack_multi --opt h2d_pack=1 --e2e-multi
 run endtrim_pack16_multi --opt h2d_pack=1 --opt pack_threads=16 --e2e-multi
 run endtrim_short2p --opt short2p=1
 run endtrim_short2p_tight --opt short2p=1 --opt tight_window=1
-run endtrim_all --opt short2p=1 --opt tight_window=1 --opt h2d_pack=1 --e2e-multi
+run endtrim_profile --opt profile=1
+run endtrim_profile_short2p_tight --opt profile=1 --opt short2p=1 --opt tight_window=1
+run endtrim_all --opt profile=1 --opt short2p=1 --opt tight_window=1 --opt h2d_pack=1 --e2e-multi
 run endtrim_decisions --e2e-decisions
 run endtrim_decisions_pack --e2e-decisions --opt h2d_pack=1
 run demux_default --workload demux
