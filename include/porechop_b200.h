@@ -136,7 +136,8 @@ int pb200TimingRead(double *dp_kernel_ms, long long *dp_kernel_launches, double 
  *   "hbuf"        staging of a slot's packed bases: "auto" | "smem" | "global"
  *   "rowoff"      1 = score pass in the row-offset arithmetic domain when it fits (default 0; same results)
  *   "h2d_pack"    1 = adapterAlignmentBatch converts the sequences to 4-bit codes on the host cores and uploads half
- *                 the bytes (default 0; same results; "pack_threads" = host threads of the packer, 0 = OpenMP default)
+ *                 the bytes (default 0; same results; "pack_threads" = host threads of the packer, default = hardware threads /
+ *                 LOCAL_WORLD_SIZE, at most 32)
  *   "profile"     1 = the score pass of long reads takes its substitution operands from a shared-memory query profile
  *                 when every slot is (one read, two adapters): two ALU-pipe instructions per row less (default 0; same results)
  *   "short2p"     1 = sequences up to direct_max also take two passes: a score-only sweep of the same slot loop finds

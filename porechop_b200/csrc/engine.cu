@@ -18,6 +18,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/porechop_b200.h"
@@ -84,7 +85,7 @@ struct Options {
     int short2p = 0;               // 1: short sequences (<= direct_max) also go score pass -> bounded window (score-only trace_kernel)
     int tight_window = 0;          // 1: second-pass windows sized per alignment from the end cell's row and score (window_cols)
     int h2d_pack = 0;              // 1: host-buffer API converts to 4-bit codes on the host cores and uploads half the bytes
-    int pack_threads = 0;          // host threads of the packer (0 = OpenMP default)
+    int pack_threads = 0;          // host threads of the packer (default: hardware threads / ranks on the node, at most 32)
     int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
 };
 Options g_opt;
@@ -100,6 +101,13 @@ void load_env_options() {
         if (const char *v = getenv("PB200_SHORT2P")) g_opt.short2p = atoi(v);
         if (const char *v = getenv("PB200_PROFILE")) g_opt.profile = atoi(v);
         if (const char *v = getenv("PB200_PACK_THREADS")) g_opt.pack_threads = atoi(v);
+        if (g_opt.pack_threads <= 0) {
+            // packer threads: the host's hardware threads shared by the ranks of this node (torchrun exports
+            // LOCAL_WORLD_SIZE, and OMP_NUM_THREADS=1 -- which would otherwise leave the packer single-threaded), at most 32
+            const unsigned hw = std::thread::hardware_concurrency();
+            const int lw = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
+            g_opt.pack_threads = (int)std::min<unsigned>(32u, std::max<unsigned>(1u, hw / (unsigned)lw));
+        }
         if (const char *v = getenv("PB200_HBUF")) g_opt.hbuf_mode = !strcmp(v, "smem") ? 1 : !strcmp(v, "global") ? 2 : 0;
     });
 }
@@ -1202,7 +1210,7 @@ int pb200SetOption(const char *name, const char *value) {
     else if (!strcmp(name, "h2d_pack")) g_opt.h2d_pack = atoi(value);
     else if (!strcmp(name, "short2p")) g_opt.short2p = atoi(value);
     else if (!strcmp(name, "profile")) g_opt.profile = atoi(value);
-    else if (!strcmp(name, "pack_threads")) g_opt.pack_threads = atoi(value);
+    else if (!strcmp(name, "pack_threads")) { if (atoi(value) > 0) g_opt.pack_threads = atoi(value); }
     else if (!strcmp(name, "hbuf")) g_opt.hbuf_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;
     else return PB200_ERR_ARG;
     return 0;

@@ -19,7 +19,7 @@ from test_oracle import SURVEY_EDGE, rebuild_fullread_inputs
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'sim'))
 
 OPTION_DEFAULTS = {'h2d_pack': 0, 'tight_window': 0, 'short2p': 0, 'profile': 0, 'rowoff': 0, 'direct_max': 512,
-                   'chunk_tasks': 131072, 'pack_threads': 0, 'scratch_mb': 128, 'hbuf': 'auto'}
+                   'chunk_tasks': 131072, 'pack_threads': 8, 'scratch_mb': 128, 'hbuf': 'auto'}
 
 
 @pytest.fixture(scope='module')
