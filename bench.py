@@ -41,7 +41,10 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='endtrim', choices=['endtrim', 'demux', 'middle'])
+    ap.add_argument('--workload', default='endtrim', choices=['endtrim', 'demux', 'middle', 'sweep'])
+    ap.add_argument('--sweep-lengths', default='500,1000,2000,5000,10000,20000,50000,100000',
+                    help='--workload sweep: read lengths (one batch each, --sweep-bases bases per batch)')
+    ap.add_argument('--sweep-bases', type=float, default=2e8, help='--workload sweep: bases per length point and rank')
     ap.add_argument('--reads', type=int, default=0, help='reads per rank (default: 1M endtrim, 32k demux, 256k middle)')
     ap.add_argument('--cpu-sample-reads', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -127,6 +130,19 @@ def make_workload(args, rank):
         L, sw, ew = wl.synth_end_windows(n, starts[100], ends[100], seed=seed)
         batches = [('start', wl.windows_to_batch(sw), starts), ('end', wl.windows_to_batch(ew), ends)]
         desc = '%d synthetic reads x 356 adapters (119 sets + 12 native-full + 96 rapid-full), demux end windows' % n
+    elif args.workload == 'sweep':
+        # BASELINE configs[4]: read-length sweep x the 192 sequences of the 96 forward barcode sets, full-read scan; the same
+        # number of bases at every length so the points are comparable (one batch per length; run one length at a time with
+        # --sweep-lengths L to get a per-length number)
+        bcs = wl.forward_barcode_sequences()
+        lengths = [int(x) for x in args.sweep_lengths.split(',')]
+        batches, n = [], 0
+        for L in lengths:
+            k = max(1, int(args.sweep_bases // L))
+            batches.append(('L%d' % L, wl.synth_fixed_length_reads(k, L, bcs, seed=seed + L), bcs))
+            n += k
+        desc = 'read-length sweep %s x 192 forward barcode sequences (24 nt), %.0e bases per length, full-read scan' % (
+            args.sweep_lengths, args.sweep_bases)
     else:
         n = args.reads or 262144     # >= ~14 reads per resident group, so one 60-kb read is not the makespan
         yt, yb = wl.nsk007()

@@ -165,6 +165,27 @@ def synth_reads(n_reads, start_adapter, end_adapter, seed=SEED, chimera_p=0.0, m
     return np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0, np.uint8), off
 
 
+def forward_barcode_sequences():
+    """Config 5: the 192 sequences (24 nt each) of the 96 forward barcode sets, start sequences then end sequences."""
+    sets = [s for s in load_adapter_sets()['sets'] if s['name'].endswith('(forward)')]
+    return [s['start'][1] for s in sets] + [s['end'][1] for s in sets]
+
+
+def synth_fixed_length_reads(n_reads, length, barcodes, seed=SEED):
+    """BASELINE config 5 (read-length sweep): n_reads reads of exactly `length` bases, iid ACGT, each with one randomly
+    chosen barcode sequence written over a random position (so every read has a real hit somewhere)."""
+    rng = np.random.default_rng(seed)
+    buf = _ACGT[rng.integers(0, 4, size=n_reads * length, dtype=np.uint8)]
+    bc = [np.frombuffer(b.encode(), dtype=np.uint8) for b in barcodes]
+    which = rng.integers(0, len(bc), n_reads)
+    for r in range(n_reads):
+        b = bc[int(which[r])]
+        if length >= len(b):
+            p = int(rng.integers(0, length - len(b) + 1))
+            buf[r * length + p: r * length + p + len(b)] = b
+    return np.ascontiguousarray(buf), np.arange(n_reads + 1, dtype=np.int64) * length
+
+
 def windows_to_batch(windows):
     """uint8[n, w] -> (flat buffer, int64 offsets) for the C-ABI."""
     n, w = windows.shape

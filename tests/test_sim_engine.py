@@ -122,6 +122,15 @@ def test_sim_long_reads_two_pass_and_options(W):
                          {'h2d_pack': 1, 'chunk_tasks': 10}):
                 got = _with(W, opts, lambda: W.adapter_alignment_batch(buf, off, abuf, aoff, scheme))
                 assert np.array_equal(got, exp), (len(ads), scheme, opts)
+    # BASELINE config 5 shape (bench.py --workload sweep): fixed-length reads x the 192 forward barcode sequences
+    bcs = wl.forward_barcode_sequences()
+    a5, o5 = wl.pack_adapters(bcs)
+    for L in (500, 2000, 6000):
+        b5, f5 = wl.synth_fixed_length_reads(3, L, bcs, seed=L)
+        exp = oracle_batch(b5, f5, a5, o5, wl.DEFAULT_SCORING)
+        for opts in ({}, {'profile': 1, 'tight_window': 1}):
+            got = _with(W, opts, lambda: W.adapter_alignment_batch(b5, f5, a5, o5, wl.DEFAULT_SCORING))
+            assert np.array_equal(got, exp), (L, opts)
     # one pass over multi-kb sequences with the bases staged in global scratch (no score pass)
     abuf, aoff = wl.pack_adapters([yt, yb])
     got = _with(W, {'hbuf': 'global', 'direct_max': 100000}, lambda: W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING))

@@ -44,3 +44,7 @@ run middle_default --workload middle
 run middle_profile_tight --workload middle --opt profile=1 --opt tight_window=1
 run middle_profile_tight_pack --workload middle --opt profile=1 --opt tight_window=1 --opt h2d_pack=1
 cat $out/summary.txt
+# config 5 (read-length sweep x 192 barcodes), aggregate over the lengths
+run sweep_default --workload sweep
+run sweep_profile_tight --workload sweep --opt profile=1 --opt tight_window=1
+cat $out/summary.txt
