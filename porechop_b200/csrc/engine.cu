@@ -260,9 +260,13 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc
     const int64_t n_wslots = (n_slots + SPW - 1) / SPW;
     int64_t blocks = (n_wslots + wpb - 1) / wpb;
     blocks = std::min<int64_t>(blocks, std::min<int64_t>((int64_t)bps * E.sm_count, max_blocks));
-    if (!SO && (size_t)blocks * wpb * gwarp_bytes > (24ull << 30)) blocks = std::max<int64_t>(1, (int64_t)((24ull << 30) / (gwarp_bytes * wpb)));
+    if constexpr (!SO) {
+        if ((size_t)blocks * wpb * gwarp_bytes > (24ull << 30)) blocks = std::max<int64_t>(1, (int64_t)((24ull << 30) / (gwarp_bytes * wpb)));
+    }
     if (blocks <= 0) return 0;
-    if (!SO) { if (int rc = S.gtrace.ensure((size_t)blocks * wpb * gwarp_bytes)) return rc; }
+    if constexpr (!SO) {
+        if (int rc = S.gtrace.ensure((size_t)blocks * wpb * gwarp_bytes)) return rc;
+    }
     TimedLaunch tl; bool on;
     timed_begin(E, stream, tl, on);
     kern<<<(unsigned)blocks, wpb * 32, smem_bytes, stream>>>(ts, seq_codes, ad_codes, sc, out,
