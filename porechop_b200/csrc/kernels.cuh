@@ -225,6 +225,7 @@ __device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
 // by two lanes of the group, 9-int record per alignment.  Grid-stride over "warp slots" so the trace scratch is
 // bounded by the resident grid and stays in L2.
 //
+// (score-only variants need fewer registers -- 68-80 -- and are compiled for 6 instead of 5 resident blocks per SM)
 // SCORE_ONLY = the same slot loop without the trace: the forward pass runs the 7-instruction score cell, nothing is
 // written to the scratch, and instead of the traceback the group's scout result goes to `ends` -- the first pass of the
 // short two-pass scheme (option "short2p": end cells first, then only the bounded window left of each end cell is
@@ -236,7 +237,7 @@ __device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
 // words in shared memory, a step fetches its R operands with two 128-bit loads instead of LOP3 + VIADDMNMX per row.  The
 // staged column words then hold the table offset of the column's base pair instead of the packed bases.
 template <int G, int R, bool HBUF_SMEM, bool SCORE_ONLY = false, bool PPROF = false>
-__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, SCORE_ONLY ? 6 : PB_TRACE_MIN_BLOCKS)
 trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
              const uint8_t *__restrict__ ads, Scoring sc, int32_t *__restrict__ out, uint32_t *__restrict__ gtrace,
              int max_steps, int max_n, int *__restrict__ status, EndCell *__restrict__ ends) {
