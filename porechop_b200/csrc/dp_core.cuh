@@ -529,6 +529,34 @@ PB_HD int traceback_stats(NibFn nib, EqFn eq, const EndCell &end, bool linear, i
     } else {
         dir = 0;
     }
+#ifdef PB_TRACEBACK_V2
+    // Experimental formulation (compile with -DPB_TRACEBACK_V2; same path, same statistics): ONE path step per loop
+    // iteration with the step kind as data instead of three code paths with inner gap-run loops -- the 16 lanes of a warp
+    // that trace at the same time then run the same instruction stream instead of serialising diagonal / vertical /
+    // horizontal branches and waiting for each other's gap runs.
+    while (j > 0 && i > 0) {
+        const bool isD = dir == 0, isV = dir == 1;
+        const bool consR = !isV, consA = dir != 2;          // the step consumes a read base / an adapter base
+        if (isD && eq(j, i)) ++matches;
+        if (consR) {
+            if (!haveR) { haveR = true; lastR_k = L; lastR_i = i; lastR_uA = isD ? 1 : 0; }
+            firstR_k = L; firstR_i = i; firstR_uA = isD ? 1 : 0;
+        }
+        if (consA) {
+            if (!haveA) { haveA = true; lastA_k = L; lastA_j = j; lastA_uR = isD ? 1 : 0; }
+            firstA_k = L; firstA_j = j; firstA_uR = isD ? 1 : 0;
+        }
+        // a gap run continues while the current cell says "extended" (dp_traceback_impl.h:225-341)
+        const bool ext = !linear && (isV ? ((b & 4u) && i != 1) : (dir == 2 && (b & 8u) && j != 1));
+        ++L;
+        if (consR) --j;
+        if (consA) --i;
+        if (j > 0 && i > 0) {
+            b = nib(j, i);
+            if (!ext) dir = (b & 1u) ? 0 : ((b & 2u) ? 1 : 2);
+        }
+    }
+#else
     while (j > 0 && i > 0) {
         if (dir == 0) {
             if (eq(j, i)) ++matches;
@@ -563,6 +591,7 @@ PB_HD int traceback_stats(NibFn nib, EqFn eq, const EndCell &end, bool linear, i
             dir = (b & 1u) ? 0 : ((b & 2u) ? 1 : 2);
         }
     }
+#endif
     int status = (j == 0 && i > 0 && col0 > 0) ? 1 : 0;
 
     // whole alignment = [H x a][V x bb] . path . [H x c][V x e]   (dp_traceback_impl.h:532-554)

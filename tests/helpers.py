@@ -46,7 +46,7 @@ def ref_lib():
 
 def emu_lib():
     if 'e' not in _cache:
-        lib = ctypes.CDLL(os.path.join(ROOT, 'tests', 'emu', 'libemu.so'))
+        lib = ctypes.CDLL(os.environ.get('PB200_EMU_LIB') or os.path.join(ROOT, 'tests', 'emu', 'libemu.so'))
         lib.emu_align_slot.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
                                        ctypes.c_char_p, ctypes.c_int] + [ctypes.c_int] * 9 + [ctypes.POINTER(ctypes.c_int32)] * 2
         _cache['e'] = lib

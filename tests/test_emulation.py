@@ -178,3 +178,19 @@ def test_emu_window_clips_real_adapter_lengths():
         G = 4 if m <= 32 else 8 if m <= 64 else 16
         st, ra, _ = emu_slot((rd, ad), None, G, 8, 1, [3, -6, -5, -2])
         assert st == 0 and ra == oracle_record(rd, ad)
+
+
+def test_emu_single_step_traceback_variant_vs_oracle():
+    """-DPB_TRACEBACK_V2 (dp_core.cuh traceback_stats: one path step per loop iteration, an experiment for round 2 that is not
+    compiled into the product by default): the same records as the oracle on the golden and two-pass cases."""
+    import os
+    import subprocess
+    import sys
+    from helpers import ROOT
+    so = os.path.join(ROOT, 'tests', 'emu', 'libemu_v2.so')
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-Wno-unknown-pragmas', '-DPB_TRACEBACK_V2', '-o', so,
+                           os.path.join(ROOT, 'tests', 'emu', 'emu_group.cpp')])
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-x', '-q', os.path.join(ROOT, 'tests', 'test_emulation.py'), '-k',
+                        'golden or tight_window or window_clips'], env=dict(os.environ, PB200_EMU_LIB=so), capture_output=True,
+                       text=True, cwd=ROOT)
+    assert r.returncode == 0 and '5 passed' in r.stdout, r.stdout[-2000:]

@@ -48,3 +48,10 @@ cat $out/summary.txt
 run sweep_default --workload sweep
 run sweep_profile_tight --workload sweep --opt profile=1 --opt tight_window=1
 cat $out/summary.txt
+# compile-time experiment: single-step traceback (rebuilds the library; keep this last)
+PB200_NVCC_FLAGS=-DPB_TRACEBACK_V2 python -m porechop_b200.build --force > $out/build_v2.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > $out/pytest_gpu_v2.log 2>&1; echo "gpu parity with PB_TRACEBACK_V2 rc=$?" | tee -a $out/summary.txt
+run endtrim_tracebackv2
+run endtrim_tracebackv2_all --opt profile=1 --opt short2p=1 --opt tight_window=1
+python -m porechop_b200.build --force > /dev/null 2>&1
+cat $out/summary.txt
