@@ -46,12 +46,13 @@ def build(force=False):
     with open(os.path.join(BUILD, 'include', 'porechop_b200.h'), 'w') as o:
         o.write(open(os.path.join(ROOT, 'include', 'porechop_b200.h')).read())
     cmd = ['g++', '-O2', '-g', '-std=c++17', '-fPIC', '-shared', '-fopenmp', '-Wno-unknown-pragmas', '-Wno-unused-value',
-           '-I', HERE, '-o', TARGET,
+           '-I', HERE, '-o', TARGET + '.tmp%d' % os.getpid(),
            os.path.join(BUILD, 'porechop_b200', 'csrc', 'engine_sim.cpp'), os.path.join(HERE, 'pbsim.cpp'),
            os.path.join(CSRC, 'hostpack.cpp')]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('g++ failed on the simulated engine:\n' + r.stdout + r.stderr[-6000:])
+    os.replace(TARGET + '.tmp%d' % os.getpid(), TARGET)      # atomic: a concurrent loader never sees a half-written library
     return TARGET
 
 
