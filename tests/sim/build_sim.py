@@ -5,6 +5,7 @@ The sources are taken as they are; three textual substitutions make them host C+
     #include <cuda_runtime.h>                ->  #include "pbsim_cuda.h"
     kernel<<<grid, block, smem, stream>>>(   ->  pbsim::launch(kernel, grid, block, smem, stream,
     extern __shared__ uint32_t smem[];       ->  uint32_t *smem = pbsim::dynamic_smem();
+    __shared__ T name[N];                    ->  static T name[N]; pbsim::poison_shared(name, sizeof(name));
 and the one inline-PTX statement outside dp_core.cuh's #if __CUDA_ARCH__ branches (discard.global.L2, a cache hint) is
 dropped.  Nothing else changes: the kernels' control flow, shared-memory staging, shuffles and the host engine's launch
 sequences are the product's own.
@@ -24,6 +25,10 @@ def transform(src):
     src = src.replace('#include <cuda_runtime.h>', '#include "pbsim_cuda.h"')
     src, n = re.subn(r'(\b[A-Za-z_]\w*)<<<(.*?)>>>\(', lambda m: 'pbsim::launch(%s, %s, ' % (m.group(1), m.group(2)), src, flags=re.S)
     src = src.replace('extern __shared__ uint32_t smem[];', 'uint32_t *smem = pbsim::dynamic_smem();')
+    # static shared arrays: poisoned at the start of every block (the device gives no initial value either)
+    src = re.sub(r'^(\s*)__shared__\s+([^;\n]+?)\s+(\w+)((?:\[[^\n;]*\])+);',
+                 lambda m: '%sstatic %s %s%s; pbsim::poison_shared(%s, sizeof(%s));' % (m.group(1), m.group(2), m.group(3), m.group(4),
+                                                                                  m.group(3), m.group(3)), src, flags=re.M)
     src = re.sub(r'asm volatile\("discard\.global\.L2.*?"memory"\);', '(void)0;', src)
     return src, n
 

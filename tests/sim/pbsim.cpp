@@ -34,6 +34,19 @@ namespace pbsim {
 
 Block *g_block = nullptr;
 
+void poison_shared(void *p, size_t bytes) {
+    static std::vector<std::pair<void *, unsigned long long>> seen;      // (array, epoch of its last poisoning)
+    for (auto &e : seen)
+        if (e.first == p) {
+            if (e.second == g_block->epoch) return;
+            e.second = g_block->epoch;
+            memset(p, 0xA5, bytes);
+            return;
+        }
+    seen.emplace_back(p, g_block->epoch);
+    memset(p, 0xA5, bytes);
+}
+
 static inline void to_scheduler(Fiber *f) {
 #ifdef PBSIM_FAST_SWITCH
     pbsim_swap(&f->sp, g_block->sched_sp);
@@ -135,6 +148,9 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()> &b
     g_block = &B;
     for (unsigned b = 0; b < grid.x; ++b) {
         B.bid = dim3(b, 0, 0);
+        static unsigned long long epoch_counter = 0;
+        B.epoch = ++epoch_counter;
+        std::fill(B.dyn_smem.begin(), B.dyn_smem.end(), 0xDEADBEEFu);
         B.fibers.clear();
         B.fibers.resize((size_t)nthreads);
         for (int t = 0; t < nthreads; ++t) {

@@ -104,10 +104,14 @@ struct Block {
     dim3 bid, bdim, gdim;
     std::function<void()> body;
     std::vector<uint32_t> dyn_smem;
+    unsigned long long epoch = 0;           // one per block: static shared arrays are poisoned once per epoch
 };
 extern Block *g_block;
 
 inline uint32_t *dynamic_smem() { return g_block->dyn_smem.data(); }
+// static __shared__ arrays are function-local statics here; the first thread of every block that reaches the declaration
+// fills the array with a poison pattern -- shared memory has no defined initial contents on the device
+void poison_shared(void *p, size_t bytes);
 
 // a fiber calls this at every collective: park, let the scheduler run the others, return the collective's result
 unsigned long long collective(Op op, unsigned mask, unsigned long long val, int arg, int width);
