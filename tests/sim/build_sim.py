@@ -61,5 +61,19 @@ def build(force=False):
     return TARGET
 
 
+def build_asan():
+    """the same sources with -fsanitize=address (portable ucontext switch: ASan cannot follow the hand-written one)"""
+    build()
+    target = os.path.join(BUILD, 'libengine_sim_asan.so')
+    cmd = ['g++', '-O1', '-g', '-std=c++17', '-fPIC', '-shared', '-fopenmp', '-fsanitize=address', '-fno-omit-frame-pointer',
+           '-DPBSIM_NO_FAST_SWITCH', '-Wno-unknown-pragmas', '-Wno-unused-value', '-I', HERE, '-o', target,
+           os.path.join(BUILD, 'porechop_b200', 'csrc', 'engine_sim.cpp'), os.path.join(HERE, 'pbsim.cpp'),
+           os.path.join(CSRC, 'hostpack.cpp')]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('g++ -fsanitize=address failed:\n' + r.stderr[-4000:])
+    return target
+
+
 if __name__ == '__main__':
     print(build(force=True))

@@ -1,7 +1,7 @@
 // tests/sim/pbsim.cpp -- block scheduler of the host CUDA stand-in (see pbsim_cuda.h).  TESTS ONLY.
 #include "pbsim_cuda.h"
 
-#if defined(__x86_64__)
+#if defined(__x86_64__) && !defined(PBSIM_NO_FAST_SWITCH)
 // swapcontext() saves and restores the signal mask with a system call on every switch; a fiber switch here only needs the
 // callee-saved registers and the stack pointer.
 extern "C" void pbsim_swap(void **save_sp, void *load_sp);

@@ -303,3 +303,17 @@ def test_sim_runs_gpu_phase_drivers(W, monkeypatch, case_index):
     from porechop_b200 import phases
     monkeypatch.setattr(phases, 'W', W)
     T.test_phases_match_reference(case_index)
+
+
+@pytest.mark.skipif(os.environ.get('PB200_SIM_ASAN', '0') != '1', reason='2 minutes: set PB200_SIM_ASAN=1 (round 1: clean)')
+def test_sim_engine_under_address_sanitizer():
+    """tests/sim/asan_check.py: the simulated engine compiled with -fsanitize=address, default and opt-in paths once -- no
+    out-of-bounds access of any kernel on the "device" heap blocks, the shared-memory arrays or the stacks."""
+    import subprocess
+    import build_sim
+    lib = build_sim.build_asan()
+    asan = subprocess.check_output(['gcc', '-print-file-name=libasan.so']).decode().strip()
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS='detect_leaks=0:detect_stack_use_after_return=0', PB200_SIM_ASAN_LIB=lib)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'sim', 'asan_check.py')], env=env, capture_output=True, text=True)
+    assert r.returncode == 0 and 'ASAN RUN COMPLETE' in r.stdout and 'DIFFERENT' not in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+    assert 'ERROR: AddressSanitizer' not in r.stderr
