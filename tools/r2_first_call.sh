@@ -48,6 +48,11 @@ cat $out/summary.txt
 run sweep_default --workload sweep
 run sweep_profile_tight --workload sweep --opt profile=1 --opt tight_window=1
 cat $out/summary.txt
+# hardware-side sanitizers on tiny inputs (every path once)
+for tool in memcheck racecheck; do
+    timeout 900 compute-sanitizer --tool $tool python tools/r2_sanitize.py > $out/sanitize_$tool.log 2>&1
+    echo "compute-sanitizer $tool rc=$? : $(grep -c 'ERROR SUMMARY' $out/sanitize_$tool.log) summaries, $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $out/sanitize_$tool.log | tail -n 1)" | tee -a $out/summary.txt
+done
 # compile-time experiment: single-step traceback (rebuilds the library; keep this last)
 PB200_NVCC_FLAGS=-DPB_TRACEBACK_V2 python -m porechop_b200.build --force > $out/build_v2.log 2>&1
 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > $out/pytest_gpu_v2.log 2>&1; echo "gpu parity with PB_TRACEBACK_V2 rc=$?" | tee -a $out/summary.txt
