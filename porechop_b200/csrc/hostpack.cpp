@@ -6,9 +6,10 @@
 // host cores instead and packs two 4-bit codes per byte: half the bytes over the link, and the device unpacks
 // (kernels.cuh unpack_kernel) into exactly the code bytes encode_kernel would have produced.
 //
-// Plain C++ (g++), linked into cpp_functions.so by build.py; AVX2 body selected at run time, scalar table otherwise.
+// Plain C++ (g++), linked into cpp_functions.so by build.py; AVX-512BW / AVX2 body selected at run time, scalar table otherwise.
 // No alignment arithmetic here -- only the alphabet conversion.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #if defined(__x86_64__)
@@ -67,10 +68,34 @@ bool have_avx2() {
     static const bool v = __builtin_cpu_supports("avx2");
     return v;
 }
+// the same conversion 64 bases at a time (AVX-512BW: byte shuffles per 128-bit lane, compare into a mask, vpmovwb)
+__attribute__((target("avx512f,avx512bw"))) void pack_avx512(const uint8_t *in, int64_t i0, int64_t i1, int64_t n, uint8_t *out) {
+    const __m512i tchar = _mm512_broadcast_i32x4(_mm_setr_epi8((char)0xFF, 0x41, (char)0xFF, 0x43, 0x54, 0x55, (char)0xFF, 0x47, (char)0xFF,
+                                                               (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF, (char)0xFF));
+    const __m512i tcode = _mm512_broadcast_i32x4(_mm_setr_epi8(4, 0, 4, 1, 3, 3, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4));
+    const __m512i fold = _mm512_set1_epi8((char)0xDF), lo4 = _mm512_set1_epi8(0x0F), four = _mm512_set1_epi8(4);
+    const __m512i w = _mm512_set1_epi16(0x1001);
+    int64_t i = i0;
+    for (; i + 64 <= i1; i += 64) {
+        const __m512i x = _mm512_loadu_si512(reinterpret_cast<const void *>(in + i));
+        const __m512i f = _mm512_and_si512(x, fold);
+        const __m512i nib = _mm512_and_si512(f, lo4);
+        const __mmask64 ok = _mm512_cmpeq_epi8_mask(_mm512_shuffle_epi8(tchar, nib), f);
+        const __m512i code = _mm512_mask_blend_epi8(ok, four, _mm512_shuffle_epi8(tcode, nib));
+        const __m512i pr = _mm512_maddubs_epi16(code, w);                  // 32 x (c0 + 16*c1)
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(out + (i >> 1)), _mm512_cvtepi16_epi8(pr));
+    }
+    if (i < i1) pack_avx2(in, i, i1, n, out);
+}
+bool have_avx512() {
+    static const bool v = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && !getenv("PB200_PACK_NO_AVX512");
+    return v;
+}
 #endif
 
 void pack_range(const uint8_t *in, int64_t i0, int64_t i1, int64_t n, uint8_t *out) {
 #if defined(__x86_64__)
+    if (have_avx512()) { pack_avx512(in, i0, i1, n, out); return; }
     if (have_avx2()) { pack_avx2(in, i0, i1, n, out); return; }
 #endif
     pack_scalar(in, i0, i1, n, out);

@@ -154,6 +154,10 @@ def test_packed_upload_path_host_pack_and_device_unpack_equal_encode():
             got = np.zeros(n, dtype=np.uint8)
             emu.emu_unpack(pk.ctypes.data, got.ctypes.data, n)
             assert np.array_equal(got, exp), (n, threads)
+    if not os.environ.get('PB200_PACK_NO_AVX512'):          # the AVX2 body on machines that would pick the AVX-512 one
+        r = subprocess.run([sys.executable, '-m', 'pytest', '-x', '-q', __file__, '-k', 'packed_upload_path'],
+                           env=dict(os.environ, PB200_PACK_NO_AVX512='1'), capture_output=True, text=True, cwd=ROOT)
+        assert r.returncode == 0, r.stdout[-1500:]
 
 
 def test_trim_threshold_table_is_the_exact_float_rule():
