@@ -6,7 +6,8 @@ oracle, all 16 row-capacity geometries, fixed + random scoring schemes, single-p
 `tight`: every two-pass slot uses the per-alignment window bound (dp_core.cuh window_cols) and reads are seeded with
 gappy adapter copies (many read-only gap columns = the paths that span the most columns for their score).
 
-Round 1: seeds 201-206 x 1 000 000 iterations (5.47 M slots, ~9.8 M alignments): 0 mismatches."""
+Round 1: seeds 201-206 x 1 000 000 iterations (5.47 M slots, ~9.8 M alignments): 0 mismatches; `tight` seeds 301-303 x
+300 000: 0 mismatches; with PB200_EMU_LIB pointing at a -DPB_TRACEBACK_V2 build, seeds 41-42 x 300 000: 0 mismatches."""
 import sys, random, time
 import os
 HERE = os.path.dirname(os.path.abspath(__file__))
