@@ -32,6 +32,7 @@ run endtrim_default
 run endtrim_multi --e2e-multi
 run endtrim_pack_multi --opt h2d_pack=1 --e2e-multi
 run endtrim_profile --opt profile=1
+run endtrim_profile_scratch160 --opt profile=1 --opt scratch_mb=160      # 85 registers allow 6 blocks/SM; the 128 MB scratch cap holds it at 5
 run endtrim_short2p_tight --opt short2p=1 --opt tight_window=1
 run endtrim_profile_short2p_tight --opt profile=1 --opt short2p=1 --opt tight_window=1
 run endtrim_all --opt profile=1 --opt short2p=1 --opt tight_window=1 --opt h2d_pack=1 --e2e-multi
