@@ -8,7 +8,7 @@
 and report, per mode, which tests pass.  The parity target is the BASELINE'S outcome set (three of the reference's tests
 fail against the reference itself at this commit), not "all green".
 
-    python tests/refsuite/run_reference_suite.py [--modes reference,patch,flat] [--engine oracle|cuda] [-k substring] [--jobs N]
+    python tests/refsuite/run_reference_suite.py [--modes reference,patch,flat] [--engine oracle|sim|cuda] [-k substring] [--jobs N]
 
 The suite is copied to a scratch directory (the reference tree is read-only and the tests write next to themselves);
 `porechop-runner.py` there is tests/refsuite/runner.py.  Needs the reference checkout: authoring container only.
@@ -65,7 +65,7 @@ def run_mode(mode, engine, ref, pattern, jobs):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--modes', default='reference,patch,flat')
-    ap.add_argument('--engine', default='oracle', choices=['oracle', 'cuda'])
+    ap.add_argument('--engine', default='oracle', choices=['oracle', 'sim', 'cuda'])
     ap.add_argument('--ref', default='/root/reference')
     ap.add_argument('-k', default='')
     ap.add_argument('--jobs', type=int, default=max(1, (os.cpu_count() or 2) // 2))

@@ -6,6 +6,7 @@ PB200_SUITE_MODE   reference  the unmodified CLI on the reference's own C++ (ora
                    patch      the unmodified CLI with porechop_b200.patch installed (phases prefetched as batches)
                    flat       porechop_b200.flat_cli (flat-buffer data path, Porechop's own parser / policy)
 PB200_SUITE_ENGINE oracle     (CPU container) the C restatement stands in for the CUDA engine -- checker only
+                   sim        (CPU container) the product's own engine.cu + kernels.cuh in the host simulation (tests/sim)
                    cuda       the real engine (GPU box with a reference checkout)
 """
 import ctypes
@@ -40,7 +41,15 @@ stub = types.ModuleType('porechop.cpp_function_wrappers')
 if mode == 'reference':
     stub.adapter_alignment = ref_adapter_alignment()
 else:
-    from porechop_b200 import cpp_function_wrappers as W
+    if engine == 'sim':
+        sys.path.insert(0, os.path.join(REPO, 'tests', 'sim'))
+        import sim_engine
+        import porechop_b200
+        W = sim_engine.load()
+        sys.modules['porechop_b200.cpp_function_wrappers'] = W        # patch.py / fastq.py / flat_cli.py bind this module
+        porechop_b200.cpp_function_wrappers = W
+    else:
+        from porechop_b200 import cpp_function_wrappers as W
     if engine == 'oracle':
         import numpy as np
         from helpers import oracle_batch, oracle_string

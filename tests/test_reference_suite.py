@@ -1,7 +1,8 @@
 """CPU tier (authoring container only): the REFERENCE'S OWN unittest suite (/root/reference/test/*.py, 85 CLI-level
 tests -- SURVEY.md section 4) run against the two drop-ins, with the reference CLI on its own C++ as the baseline
-(tests/refsuite/run_reference_suite.py; the oracle stands in for the CUDA engine here, `--engine cuda` on a GPU box
-that has a checkout).
+(tests/refsuite/run_reference_suite.py).  The engine under the drop-ins is the product's own engine.cu + kernels.cuh in the
+host simulation of tests/sim (`--engine sim`; `--engine oracle` uses the C restatement instead, `--engine cuda` the real
+device on a GPU box that has a checkout).
 
   patch  (python -m porechop_b200)            every one of the 85 tests has the baseline's outcome -- including the three
                                               tests that fail against the reference itself at this commit
@@ -46,12 +47,12 @@ def test_reference_unittest_suite_outcomes_match_the_baseline():
     assert failing == ['test_albacore_directory.TestAlbacoreDirectory.test_albacore_directory_3',
                        'test_albacore_directory.TestAlbacoreDirectory.test_albacore_directory_all',
                        'test_albacore_directory.TestAlbacoreDirectory.test_albacore_directory_unclassified'], failing
-    patch = R.run_mode('patch', 'oracle', REF, '', jobs)
+    patch = R.run_mode('patch', 'sim', REF, '', jobs)         # the product's own engine code, in the host simulation (tests/sim)
     assert patch == base
     if os.environ.get('PB200_REFSUITE_FLAT', '0') != '1':
         return          # the flat CLI's run of the suite (another ~40 s; round 1: differs on exactly REPORT_TESTS) is opt-in;
                         # tests/test_flat_cli.py compares its output files with the reference CLI's in every run
-    flat = R.run_mode('flat', 'oracle', REF, '', jobs)
+    flat = R.run_mode('flat', 'sim', REF, '', jobs)
     assert sorted(flat) == sorted(base)
     differs = {k for k in base if flat[k] != base[k]}
     assert differs <= REPORT_TESTS, sorted(differs - REPORT_TESTS)
