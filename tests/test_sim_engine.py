@@ -318,3 +318,29 @@ def test_sim_engine_under_address_sanitizer():
     r = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'sim', 'asan_check.py')], env=env, capture_output=True, text=True)
     assert r.returncode == 0 and 'ASAN RUN COMPLETE' in r.stdout and 'DIFFERENT' not in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
     assert 'ERROR: AddressSanitizer' not in r.stderr
+
+
+# ---- the two CLI drop-ins on the simulated engine (the other CPU tests of these files use the oracle as the engine) ----
+def _sim_as_engine(W):
+    def install(monkeypatch):
+        from porechop_b200 import cpp_function_wrappers as real
+        for name in ('adapter_alignment_batch', 'adapter_alignment', 'adapter_alignment_batch_multi', 'adapter_end_decisions'):
+            monkeypatch.setattr(real, name, getattr(W, name))
+    return install
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/porechop'), reason='needs the reference checkout (authoring container)')
+def test_sim_engine_under_the_unmodified_cli_and_the_flat_cli(W, monkeypatch, tmp_path):
+    """tests/test_patch_cli.py and tests/test_flat_cli.py compare the drop-ins with the reference CLI byte for byte, with the
+    oracle standing in for the engine; here the same comparisons run on the product's engine code (host simulation): the
+    reference's stdout + output files under `python -m porechop_b200`, the output files of the flat CLI."""
+    import test_flat_cli as F
+    import test_patch_cli as P
+    mods = P.load_reference()
+    install = _sim_as_engine(W)
+    monkeypatch.setattr(P, '_oracle_engine', install)
+    monkeypatch.setattr(F, '_oracle_engine', install)
+    for k, case in enumerate(P.CASES[:4]):
+        P.test_reference_cli_identical_with_patch(case[0], case[1], mods, monkeypatch, tmp_path / ('p%d' % k))
+    for k, case in enumerate(F.CASES[:5]):
+        F.test_flat_cli_writes_the_reference_cli_files(case[0], case[1], case[2], mods, monkeypatch, tmp_path / ('f%d' % k))
