@@ -231,7 +231,7 @@ void timed_end(Engine &E, cudaStream_t s, TimedLaunch &tl, bool on) {
     if (on) { cudaEventRecord(tl.b, s); E.timed.push_back(tl); }
 }
 
-template <int G, int R, bool HS, bool SO = false, bool PP = false>
+template <int G, int R, bool HS, bool SO = false, int PM = 0>
 int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, int max_n,
                          const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status,
                          EndCell *ends = nullptr) {
@@ -239,8 +239,9 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc
     constexpr int WPS = TraceWords<R>::value;
     const int max_steps = max_n + G - 1;
     const int wpb = PB_WARPS_PER_BLOCK;
-    const size_t smem_bytes = (size_t)wpb * ((HS ? (size_t)SPW * max_n : 0) + PB_SCRATCH_WORDS) * 4;
-    auto kern = trace_kernel<G, R, HS, SO, PP>;
+    const size_t hb_words = HS ? (PM == 2 ? (((size_t)SPW * max_n + 3) & ~(size_t)3) : (size_t)SPW * max_n) : 0;
+    const size_t smem_bytes = (size_t)wpb * (hb_words + PB_SCRATCH_WORDS + (PM == 2 ? PB_GPROF_WORDS : 0)) * 4;
+    auto kern = trace_kernel<G, R, HS, SO, PM>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     int bps = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem_bytes));
@@ -282,7 +283,7 @@ template <int G>
 bool hbuf_fits_smem(const Engine &E, int max_n) {
     constexpr int SPW = 32 / G;
     return (size_t)SPW * max_n * 4 <= 12288 &&
-           (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + PB_SCRATCH_WORDS) * 4 <= E.smem_optin;
+           (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + 4 + PB_SCRATCH_WORDS + PB_GPROF_WORDS) * 4 <= E.smem_optin;
 }
 
 template <int G, int R>
@@ -291,22 +292,32 @@ int launch_trace(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, in
                  EndCell *ends) {
     constexpr int SPW = 32 / G;
     if (max_n < 1) max_n = 1;
-    // pair profile (option "profile"): the adapter pair is the same for every slot of the launch -- a cross-mode class
-    // with one or two adapters (also its windowed second pass, which keeps the task order) -- and at most 64 rows
+    // query profiles (option "profile"), cross mode only (also the windowed second pass, which keeps the task order):
+    //   pair profile (1)      the adapter pair is the same for every slot -- a class with one or two adapters, <= 64 rows
+    //   per-group profile (2) every slot is one read x its own two adapters -- an even number of adapters (an odd class is
+    //                         split by run_class_tasks into its paired part and the single-adapter tail); not for the
+    //                         windowed second pass, whose two halves sit at different columns of the read
     constexpr bool PP_OK = G <= 8;
-    const bool pp = PP_OK && g_opt.profile != 0 && ts.cls_ad != nullptr && ts.n_cls_ad >= 1 && ts.n_cls_ad <= 2;
+    const bool prof = g_opt.profile != 0 && ts.cls_ad != nullptr && ts.n_cls_ad >= 1;
+    const bool pp = prof && PP_OK && ts.n_cls_ad <= 2;
+    const bool gp = prof && !pp && (ts.n_cls_ad % 2) == 0 && ts.tasks == nullptr;    // (windowed halves read different columns)
+    constexpr int PM1 = PP_OK ? 1 : 0;
+    const size_t gp_words = gp ? (size_t)PB_GPROF_WORDS : 0;
     if (ends) {                                   // score-only first pass of the short two-pass scheme
         if (!hbuf_fits_smem<G>(E, max_n)) return fail(PB200_ERR_INTERNAL, "score-only pass needs shared-memory staging");
-        if (pp) return launch_trace_variant<G, R, true, true, PP_OK>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
+        if (pp) return launch_trace_variant<G, R, true, true, PM1>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
+        if (gp) return launch_trace_variant<G, R, true, true, 2>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
         return launch_trace_variant<G, R, true, true>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
     }
     // packed read bases of a slot are staged in shared memory when they fit (<= 12 KB per warp), else in global scratch
     const bool hs = g_opt.hbuf_mode == 1 ? true : g_opt.hbuf_mode == 2 ? false : ((size_t)SPW * max_n * 4 <= 12288);
-    if (hs && (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + PB_SCRATCH_WORDS) * 4 <= E.smem_optin) {
-        if (pp) return launch_trace_variant<G, R, true, false, PP_OK>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
+    if (hs && (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + 4 + PB_SCRATCH_WORDS + gp_words) * 4 <= E.smem_optin) {
+        if (pp) return launch_trace_variant<G, R, true, false, PM1>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
+        if (gp) return launch_trace_variant<G, R, true, false, 2>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
         return launch_trace_variant<G, R, true>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
     }
-    if (pp) return launch_trace_variant<G, R, false, false, PP_OK>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
+    if (pp) return launch_trace_variant<G, R, false, false, PM1>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
+    if (gp) return launch_trace_variant<G, R, false, false, 2>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
     return launch_trace_variant<G, R, false>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
 }
 
@@ -407,6 +418,18 @@ int run_class_tasks(Engine &E, Stage &S, cudaStream_t stream, int cls, int m_max
                     int32_t *out, int *status, unsigned long long *counter) {
     const int64_t n_tasks = ts.n_tasks;
     if (n_tasks <= 0) return 0;
+    if (g_opt.profile != 0 && ts.tasks == nullptr && ts.cls_ad != nullptr && ts.n_cls_ad >= 3 && (ts.n_cls_ad & 1)) {
+        // profiles need uniform slots: the paired adapters (one read, two adapters per slot) and the odd last adapter (two
+        // reads per slot) run as two launches; cross_task() indexes both exactly as it does inside the whole class
+        TaskSrc paired = ts, tail = ts;
+        paired.n_cls_ad = ts.n_cls_ad - 1;
+        paired.n_tasks = ts.n_seqs * (int64_t)paired.n_cls_ad;
+        tail.cls_ad = ts.cls_ad + (ts.n_cls_ad - 1);
+        tail.n_cls_ad = 1;
+        tail.n_tasks = ts.n_seqs;
+        if (int rc = run_class_tasks(E, S, stream, cls, m_max, paired, max_n, seq_codes, ad_codes, sc, si, out, status, counter)) return rc;
+        return run_class_tasks(E, S, stream, cls, m_max, tail, max_n, seq_codes, ad_codes, sc, si, out, status, counter);
+    }
     int64_t W = si.bounded ? (int64_t)m_max + ((int64_t)m_max * si.wnum) / si.wden : (int64_t)1 << 40;
     const bool two_pass = si.bounded && max_n > g_opt.direct_max && W + 1 < max_n;
     // Short two-pass (option "short2p"): windows that would take the single trace pass are first swept score-only by the

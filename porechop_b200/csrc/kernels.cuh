@@ -236,12 +236,18 @@ __device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
 // BLOCK, indexed by (base of half A, base of half B), holds the substitution operands of every row: 36 pairs x G lanes x 8
 // words in shared memory, a step fetches its R operands with two 128-bit loads instead of LOP3 + VIADDMNMX per row.  The
 // staged column words then hold the table offset of the column's base pair instead of the packed bases.
-template <int G, int R, bool HBUF_SMEM, bool SCORE_ONLY = false, bool PPROF = false>
+//
+// PMODE: 0 = no profile, 1 = the pair profile above (PPROF), 2 = a profile per GROUP (GPROF): every slot aligns one read
+// against its own two adapters (cross mode, even number of adapters in the launch -- the demux cross product), the group's
+// lanes keep 6 base codes x 8 words each in the warp's dynamic shared memory (6 KB per warp), refilled per slot.
+constexpr int PB_GPROF_WORDS = 6 * 32 * 8;       // per warp: SPW groups x 6 codes x G lanes x 8 words
+template <int G, int R, bool HBUF_SMEM, bool SCORE_ONLY = false, int PMODE = 0>
 __global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, SCORE_ONLY ? 6 : PB_TRACE_MIN_BLOCKS)
 trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
              const uint8_t *__restrict__ ads, Scoring sc, int32_t *__restrict__ out, uint32_t *__restrict__ gtrace,
              int max_steps, int max_n, int *__restrict__ status, EndCell *__restrict__ ends) {
     static_assert(!SCORE_ONLY || HBUF_SMEM, "the score-only variant has no global scratch");
+    constexpr bool PPROF = PMODE == 1, GPROF = PMODE == 2, ANYPROF = PMODE != 0;
     static_assert(!PPROF || G <= 8, "the pair profile is kept for adapters of up to 64 rows");
     constexpr int PSTRIDE = G * 8;                       // words per base pair: 8 per lane (R <= 8), 32-byte aligned
     __shared__ __align__(16) uint32_t pprof[PPROF ? 36 * PSTRIDE : 4];
@@ -277,15 +283,19 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
     const size_t gwarp_words = trace_words + (HBUF_SMEM ? 0 : (((size_t)SPW * max_n + 3) & ~(size_t)3));
     uint32_t *gw = gtrace + (size_t)wglobal * gwarp_words;
     uint32_t *tr = gw;
-    const int per_warp_words = (HBUF_SMEM ? SPW * max_n : 0) + PB_SCRATCH_WORDS;
+    // (GPROF rounds the staging area up to 16 bytes so that the group tables behind it can be read with 128-bit loads)
+    const int hb_words = HBUF_SMEM ? (GPROF ? ((SPW * max_n + 3) & ~3) : SPW * max_n) : 0;
+    const int per_warp_words = hb_words + PB_SCRATCH_WORDS + (GPROF ? PB_GPROF_WORDS : 0);
     uint32_t *wsm = smem + (size_t)warp * per_warp_words;
     uint32_t *hbuf = HBUF_SMEM ? (wsm + grp * max_n) : (gw + trace_words + (size_t)grp * max_n);
-    ScoutCand *cand = reinterpret_cast<ScoutCand *>(wsm + (HBUF_SMEM ? SPW * max_n : 0));  // [half][lane]
-    const uint32_t *myprof = pprof + (PPROF ? g * 8 : 0);
+    ScoutCand *cand = reinterpret_cast<ScoutCand *>(wsm + hb_words);  // [half][lane]
+    // this lane's 8 words per base (pair): block table (PPROF) or the group's table in the warp's shared memory (GPROF)
+    uint32_t *gtab = wsm + hb_words + PB_SCRATCH_WORDS + grp * (6 * PSTRIDE) + g * 8;
+    const uint32_t *myprof = GPROF ? gtab : (pprof + (PPROF ? g * 8 : 0));
     // one wavefront step of this lane for the staged column word hx (packed bases, or the pair-profile offset)
 #define PB_TRACE_STEP(KEEPV_, hx_, tw_, vr_)                                                                          \
     do {                                                                                                              \
-        if (PPROF) {                                                                                                  \
+        if (ANYPROF) {                                                                                                \
             const uint4 *pp_ = reinterpret_cast<const uint4 *>(myprof + (hx_));                                       \
             const uint4 q0_ = pp_[0], q1_ = pp_[1];                                                                   \
             const uint32_t subs_[8] = {q0_.x, q0_.y, q0_.z, q0_.w, q1_.x, q1_.y, q1_.z, q1_.w};                      \
@@ -310,10 +320,23 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
             for (int c = g; c < nmax; c += G) {
                 uint32_t bA = (c < nA) ? (uint32_t)__ldcs(seqA + c) : (uint32_t)PB_PAD_H;
                 uint32_t bB = (c < nB) ? (uint32_t)__ldcs(seqB + c) : (uint32_t)PB_PAD_H;
-                hbuf[c] = PPROF ? ((bA >> 4) * 6u + (bB >> 4)) * (uint32_t)PSTRIDE : pack_bases(bA, bB);
+                hbuf[c] = PPROF ? ((bA >> 4) * 6u + (bB >> 4)) * (uint32_t)PSTRIDE
+                                : GPROF ? (bA >> 4) * (uint32_t)PSTRIDE : pack_bases(bA, bB);
             }
             lane_init<R>(L, g, G, sc, ads + tA.ad_off, mA, (tA.flags & TASK_LEFT_INF) != 0, ads + tB.ad_off, mB,
                          (tB.flags & TASK_LEFT_INF) != 0);
+            if (GPROF) {
+                // both halves read sequence A (same-read slots); every lane fills, and later reads, only its own 48 words
+                // (the adapter pair changes from slot to slot in a grid-stride walk over a cross product, so the table is
+                // rebuilt per slot: ~3 % of a 150-column slot's instructions)
+#pragma unroll 1
+                for (int b = 0; b < 6; ++b)
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        gtab[b * PSTRIDE + r] = (r < R) ? profile_word(g * R + r + 1, (uint32_t)b, sc, ads + tA.ad_off, mA, G * R - mA,
+                                                                       ads + tB.ad_off, mB, G * R - mB)
+                                                        : 0u;
+            }
             // scout: fast path while both halves are in inner columns; an empty half never limits it
             const bool emptyA = nA <= 0 || mA <= 0, emptyB = nB <= 0 || mB <= 0;
             nmin = emptyA ? nB : (emptyB ? nA : min(nA, nB));
@@ -431,6 +454,7 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                         const uint32_t pair = hbuf[jl - 1] / (uint32_t)PSTRIDE;
                         return ((h ? pair % 6u : pair / 6u) << 4) == (uint32_t)__ldg(ad + i - 1);
                     }
+                    if (GPROF) return ((hbuf[jl - 1] / (uint32_t)PSTRIDE) << 4) == (uint32_t)__ldg(ad + i - 1);
                     return ((hbuf[jl - 1] >> (8 + 16 * h)) & 0xFFu) == (uint32_t)__ldg(ad + i - 1);
                 };
                 int32_t rec[PB_REC];

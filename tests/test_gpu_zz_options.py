@@ -269,3 +269,25 @@ def test_pair_profile_trace_kernel_equals_oracle(W):
             for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1, 'direct_max': 200}):
                 got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
                 assert np.array_equal(got, exp), (ads, sc, opts)
+
+
+def test_per_group_profile_demux_cross_product_equals_oracle(W):
+    """profile on multi-adapter classes: trace_kernel PMODE 2 (a profile per lane group, rebuilt per slot) for the paired
+    adapters, the pair profile for an odd class's last adapter (run_class_tasks splits the class); the whole demux cross
+    product (227 start / 129 end sequences), small odd and even sets, long reads with an odd number of adapters."""
+    from porechop_b200 import workloads as wl
+    yt, yb = wl.nsk007()
+    starts, ends = wl.demux_adapters()
+    _, sw, ew = wl.synth_end_windows(300, starts[5], ends[5], seed=6)
+    for win, ads in ((sw, starts), (ew, ends), (sw, starts[:4]), (sw, starts[:5]), (ew, [yt, yb, starts[-1]])):
+        sbuf, soff = wl.windows_to_batch(win)
+        abuf, aoff = wl.pack_adapters(ads)
+        exp = oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
+        for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1}, {'profile': 1, 'hbuf': 'global'}):
+            got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
+            assert np.array_equal(got, exp), (len(ads), opts)
+    lbuf, loff = wl.synth_reads(30, yt, yb, seed=2, chimera_p=0.5, max_len=9000)
+    for ads in ([yt, yb, starts[-1]], starts[:5], starts[:6]):
+        abuf, aoff = wl.pack_adapters(ads)
+        got = _with(W, {'profile': 1, 'tight_window': 1}, lambda: W.adapter_alignment_batch(lbuf, loff, abuf, aoff, wl.DEFAULT_SCORING))
+        assert np.array_equal(got, oracle_batch(lbuf, loff, abuf, aoff, wl.DEFAULT_SCORING)), len(ads)

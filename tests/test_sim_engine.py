@@ -167,6 +167,15 @@ def test_sim_short_two_pass_and_packed_upload(W):
         for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}, {'profile': 1, 'short2p': 1}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
             assert np.array_equal(got, exp), (sc, opts)
+    # per-group profile (trace_kernel PMODE 2) and the odd-class split: the demux cross product and small odd / even sets
+    starts, ends = wl.demux_adapters()
+    (sb5, so5), _ = _windows(12, 6, (starts[5], ends[5]))
+    for ads in (starts, ends[:40], starts[:4], starts[:5], [yt, yb, starts[-1]]):
+        abuf, aoff = wl.pack_adapters(ads)
+        exp = oracle_batch(sb5, so5, abuf, aoff, wl.DEFAULT_SCORING)
+        for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1}):
+            got = _with(W, opts, lambda: W.adapter_alignment_batch(sb5, so5, abuf, aoff, wl.DEFAULT_SCORING))
+            assert np.array_equal(got, exp), (len(ads), opts)
     # pair profile (trace_kernel<.., PPROF>): classes with one adapter (two reads per slot, odd number of reads) and with
     # two adapters (one read per slot), every row class up to 64 rows, ragged reads, empty adapter / empty reads
     for ads in (['ACGT' * 5], [yt], [yt, yb], ['ACGTTGCA' * 5, 'TTGACCA' * 5], ['ACGT' * 16], [yt, ''], ['N' * 22]):
@@ -266,7 +275,7 @@ GPU_PARITY = ['test_legacy_single_call_strings', 'test_golden_random_pair_list',
 GPU_OPTIONS = ['test_packed_upload_windows_ragged_and_long_reads', 'test_tight_window_long_reads_and_forced_two_pass_windows',
                'test_multi_batch_submit_equals_single_calls', 'test_short_two_pass_windows_equal_oracle',
                'test_end_decisions_on_device_equal_host_rule', 'test_bad_sequence_offsets_fail_cleanly_mid_pipeline',
-               'test_query_profile_score_pass_equals_oracle', 'test_pair_profile_trace_kernel_equals_oracle']
+               'test_query_profile_score_pass_equals_oracle', 'test_pair_profile_trace_kernel_equals_oracle', 'test_per_group_profile_demux_cross_product_equals_oracle']
 
 
 # the larger ones take minutes in the simulation (10 min for all): run with PB200_SIM_FULL=1; the dedicated tests above
@@ -275,7 +284,7 @@ GPU_OPTIONS = ['test_packed_upload_windows_ragged_and_long_reads', 'test_tight_w
 SLOW = {'test_demux_cross_all_adapters_vs_oracle', 'test_multi_batch_submit_equals_single_calls',
         'test_short_two_pass_windows_equal_oracle', 'test_end_decisions_on_device_equal_host_rule',
         'test_bad_sequence_offsets_fail_cleanly_mid_pipeline', 'test_query_profile_score_pass_equals_oracle',
-        'test_pair_profile_trace_kernel_equals_oracle'}
+        'test_pair_profile_trace_kernel_equals_oracle', 'test_per_group_profile_demux_cross_product_equals_oracle'}
 FULL = os.environ.get('PB200_SIM_FULL', '0') == '1'
 
 

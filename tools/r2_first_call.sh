@@ -40,6 +40,8 @@ run endtrim_all_decisions --opt profile=1 --opt short2p=1 --opt tight_window=1 -
 # config 3 (demux) and config 4 (middle scan)
 run demux_default --workload demux
 run demux_short2p_tight --workload demux --opt short2p=1 --opt tight_window=1
+run demux_profile --workload demux --opt profile=1
+run demux_profile_short2p_tight --workload demux --opt profile=1 --opt short2p=1 --opt tight_window=1
 run demux_decisions --workload demux --e2e-decisions
 run middle_default --workload middle
 run middle_profile_tight --workload middle --opt profile=1 --opt tight_window=1

@@ -55,6 +55,7 @@ for opts in ({}, {'profile': 1, 'tight_window': 1}, {'profile': 1, 'rowoff': 1},
 a3, o3 = wl.pack_adapters(starts)
 run('demux', {}, cross(sbuf[:150 * 12], soff[:13], a3, o3))
 run('demux', {'short2p': 1, 'tight_window': 1}, cross(sbuf[:150 * 12], soff[:13], a3, o3))
+run('demux', {'profile': 1, 'short2p': 1, 'tight_window': 1}, cross(sbuf[:150 * 12], soff[:13], a3, o3))
 outs = W.adapter_end_decisions([(sbuf, soff, a2, o2, True, [0, 1])], wl.DEFAULT_SCORING, 150, 2, 75.0, 4)
 print('decisions', outs[0][0][:6].tolist(), flush=True)
 got = W.adapter_alignment_batch_multi([(sbuf, soff, a1, o1), (lbuf, loff, a2, o2)], wl.DEFAULT_SCORING)
