@@ -344,16 +344,26 @@ PB_HD uint32_t max2acc(uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, ui
 //   trace_kernel<.., PPROF>  per block, launch-uniform adapter pair (a class with one or two adapters): indexed by the
 //                            pair (base of half A, base of half B)
 // The word is produced by the very expression lane_step uses, so both paths are identical by construction.
-PB_HD uint32_t profile_word2(int q, uint32_t bcodeA, uint32_t bcodeB, const Scoring &sc, const uint8_t *adA, int mA, int padA,
-                             const uint8_t *adB, int mB, int padB) {
+// the two base-independent operands of a group row (adapter codes and mismatch operands, as lane_init sets them up) ...
+PB_HD void profile_row(int q, const Scoring &sc, const uint8_t *adA, int mA, int padA, const uint8_t *adB, int mB, int padB,
+                       uint32_t &v2, uint32_t &sf2) {
     const int iA = q - padA, iB = q - padB;
     const bool realA = iA >= 1 && iA <= mA, realB = iB >= 1 && iB <= mB;
     const uint32_t a = realA ? (uint32_t)adA[iA - 1] : (uint32_t)PB_PAD_V;
     const uint32_t b = realB ? (uint32_t)adB[iB - 1] : (uint32_t)PB_PAD_V;
-    const uint32_t v2 = (a << 8) | (b << 24);
-    const uint32_t sf2 = ((realA ? sc.subF2 : sc.padF2) & 0xFFFFu) | ((realB ? sc.subF2 : sc.padF2) & 0xFFFF0000u);
+    v2 = (a << 8) | (b << 24);
+    sf2 = ((realA ? sc.subF2 : sc.padF2) & 0xFFFFu) | ((realB ? sc.subF2 : sc.padF2) & 0xFFFF0000u);
+}
+// ... and the operand for one pair of read base codes: exactly lane_step's expression
+PB_HD uint32_t profile_from(uint32_t v2, uint32_t sf2, uint32_t bcodeA, uint32_t bcodeB, const Scoring &sc) {
     const uint32_t h2 = (((bcodeA & 7u) << 4) << 8) | (((bcodeB & 7u) << 4) << 24);      // encoded bytes (code << 4) per half
     return addmax2(xnor2(h2, v2), sc.subA2, sf2);
+}
+PB_HD uint32_t profile_word2(int q, uint32_t bcodeA, uint32_t bcodeB, const Scoring &sc, const uint8_t *adA, int mA, int padA,
+                             const uint8_t *adB, int mB, int padB) {
+    uint32_t v2, sf2;
+    profile_row(q, sc, adA, mA, padA, adB, mB, padB, v2, sf2);
+    return profile_from(v2, sf2, bcodeA, bcodeB, sc);
 }
 PB_HD uint32_t profile_word(int q, uint32_t bcode, const Scoring &sc, const uint8_t *adA, int mA, int padA, const uint8_t *adB,
                             int mB, int padB) {

@@ -328,14 +328,17 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
             if (GPROF) {
                 // both halves read sequence A (same-read slots); every lane fills, and later reads, only its own 48 words
                 // (the adapter pair changes from slot to slot in a grid-stride walk over a cross product, so the table is
-                // rebuilt per slot: ~3 % of a 150-column slot's instructions)
-#pragma unroll 1
-                for (int b = 0; b < 6; ++b)
+                // rebuilt per slot, ~0.5 % of a 150-column slot's instructions: lane_init has just set up the row operands
+                // (L.v2, L.sf2); per base code 8 words = two 128-bit stores)
 #pragma unroll
-                    for (int r = 0; r < 8; ++r)
-                        gtab[b * PSTRIDE + r] = (r < R) ? profile_word(g * R + r + 1, (uint32_t)b, sc, ads + tA.ad_off, mA, G * R - mA,
-                                                                       ads + tB.ad_off, mB, G * R - mB)
-                                                        : 0u;
+                for (int b = 0; b < 6; ++b) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) w[r] = (r < R) ? profile_from(L.v2[r < R ? r : 0], L.sf2[r < R ? r : 0], (uint32_t)b, (uint32_t)b, sc) : 0u;
+                    uint4 *dst = reinterpret_cast<uint4 *>(gtab + b * PSTRIDE);
+                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                }
             }
             // scout: fast path while both halves are in inner columns; an empty half never limits it
             const bool emptyA = nA <= 0 || mA <= 0, emptyB = nB <= 0 || mB <= 0;
