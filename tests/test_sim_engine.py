@@ -279,8 +279,8 @@ GPU_OPTIONS = ['test_packed_upload_windows_ragged_and_long_reads', 'test_tight_w
 
 
 # the larger ones take minutes in the simulation (10 min for all): run with PB200_SIM_FULL=1; the dedicated tests above
-# cover the same paths at smaller sizes.  Round 1, final build: all 31 tests of this file pass with PB200_SIM_FULL=1
-# PB200_SIM_ASAN=1 (943 s).
+# cover the same paths at smaller sizes.  Round 1, final build: all 33 tests of this file pass with PB200_SIM_FULL=1
+# PB200_SIM_ASAN=1 (915 s).
 SLOW = {'test_demux_cross_all_adapters_vs_oracle', 'test_multi_batch_submit_equals_single_calls',
         'test_short_two_pass_windows_equal_oracle', 'test_end_decisions_on_device_equal_host_rule',
         'test_bad_sequence_offsets_fail_cleanly_mid_pipeline', 'test_query_profile_score_pass_equals_oracle',
