@@ -138,8 +138,9 @@ int pb200TimingRead(double *dp_kernel_ms, long long *dp_kernel_launches, double 
  *   "h2d_pack"    1 = adapterAlignmentBatch converts the sequences to 4-bit codes on the host cores and uploads half
  *                 the bytes (default 0; same results; "pack_threads" = host threads of the packer, default = hardware threads /
  *                 LOCAL_WORLD_SIZE, at most 32)
- *   "profile"     1 = the score pass of long reads takes its substitution operands from a shared-memory query profile
- *                 when every slot is (one read, two adapters): two ALU-pipe instructions per row less (default 0; same results)
+ *   "profile"     1 = query profiles in shared memory instead of computing the substitution score per cell (cross-product
+ *                 mode only): a table per block for classes with one or two adapters, a table per lane group for larger
+ *                 classes, and in the long-read score pass (default 0; same results)
  *   "short2p"     1 = sequences up to direct_max also take two passes: a score-only sweep of the same slot loop finds
  *                 the end cells, then only the bounded window left of each end cell is traced (default 0; same results)
  *   "tight_window" 1 = second-pass windows sized per alignment from the end cell's row and score instead of the
