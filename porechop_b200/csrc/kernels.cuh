@@ -613,11 +613,14 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                         // both halves read sequence A (the launcher guarantees same-read slots); every lane fills, and later
                         // reads, only its own rows of the table -- no synchronisation needed
 #pragma unroll
-                        for (int b = 0; b < 6; ++b)
+                        for (int b = 0; b < 6; ++b) {       // from the row operands lane_init has just set up: two 128-bit stores
+                            uint32_t w[8];
 #pragma unroll
-                            for (int r = 0; r < R; ++r)
-                                myprof[b * ProfGeom<G, R>::ROWS + r] =
-                                    profile_word(g * R + r + 1, (uint32_t)b, sc, ads + tA.ad_off, tA.m, gA.pad, ads + tB.ad_off, tB.m, gB.pad);
+                            for (int r = 0; r < 8; ++r) w[r] = profile_from(L.v2[r], L.sf2[r], (uint32_t)b, (uint32_t)b, sc);
+                            uint4 *dst = reinterpret_cast<uint4 *>(myprof + b * ProfGeom<G, R>::ROWS);
+                            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        }
                     }
                     const bool emptyA = tA.n <= 0 || tA.m <= 0, emptyB = tB.n <= 0 || tB.m <= 0;
                     nmin = emptyA ? nB : (emptyB ? nA : min(nA, nB));
