@@ -248,7 +248,7 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc
     if (bps < 1) bps = 1;
     // (the score-only variant writes no trace: no scratch, the grid is bounded by the occupancy alone)
     const size_t gwarp_bytes = SO ? 0 : ((size_t)((max_steps + PB_TCHUNK - 1) / PB_TCHUNK) * PB_TCHUNK * WPS * 32 +
-                                         (HS ? 0 : (((size_t)SPW * max_n + 3) & ~(size_t)3))) * 4;
+                                         (HS ? 0 : (((size_t)SPW * max_n + 31) & ~(size_t)31))) * 4;   // 128-byte lines per warp (kernels.cuh)
     // The trace scratch of the resident grid is rewritten slot after slot and mostly lives in L2.  `scratch_mb` caps
     // it (whole blocks per SM, never below 2): measured on B200 for 150x28 windows, 72 MB (3 blocks/SM) keeps the
     // trace L2-resident (DRAM traffic 1.9x the algorithmic bytes) at ~10 % lower kernel throughput than the default
@@ -661,9 +661,9 @@ int validate_args(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, c
     if (n_adapters > 0 && ad_off[0] < 0) return fail(PB200_ERR_ARG, "negative adapter offset");
     if (n_adapters > 0 && ad_off[n_adapters] > 0 && !adapters) return fail(PB200_ERR_ARG, "NULL adapter buffer");
     if (n_seqs > 0 && seq_off[n_seqs] > seq_off[0] && !seqs) return fail(PB200_ERR_ARG, "NULL sequence buffer");
+    if (n_seqs > 0 && seq_off[0] < 0) return fail(PB200_ERR_ARG, "negative sequence offset");
     if (cross) return 0;
     if (n_pairs > 0x7fffffffll) return fail(PB200_ERR_ARG, "pair-list mode supports < 2^31 pairs per call");
-    if (n_seqs > 0 && seq_off[0] < 0) return fail(PB200_ERR_ARG, "negative sequence offset");
     for (int64_t s = 0; s < n_seqs; ++s) {
         const int64_t len = seq_off[s + 1] - seq_off[s];
         if (len < 0) return fail(PB200_ERR_ARG, "sequence offsets not monotone");

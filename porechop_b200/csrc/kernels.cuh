@@ -280,7 +280,9 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
     // [trace max_steps*WPS*32 words] [HBUF_SMEM ? nothing : packed bases SPW*max_n words].
     // Shared memory per warp: [HBUF_SMEM ? packed bases SPW*max_n words : nothing] [scout scratch].
     const size_t trace_words = (size_t)((max_steps + PB_TCHUNK - 1) / PB_TCHUNK) * PB_TCHUNK * WPS * 32;
-    const size_t gwarp_words = trace_words + (HBUF_SMEM ? 0 : (((size_t)SPW * max_n + 3) & ~(size_t)3));
+    // (the staging area is rounded up to 32 words so that every warp's region starts on a 128-byte line: the
+    // discard.global.L2 below needs 128-byte aligned addresses and must never touch a neighbour's staged bases)
+    const size_t gwarp_words = trace_words + (HBUF_SMEM ? 0 : (((size_t)SPW * max_n + 31) & ~(size_t)31));
     uint32_t *gw = gtrace + (size_t)wglobal * gwarp_words;
     uint32_t *tr = gw;
     // (GPROF rounds the staging area up to 16 bytes so that the group tables behind it can be read with 128-bit loads)

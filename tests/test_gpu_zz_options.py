@@ -291,3 +291,23 @@ def test_per_group_profile_demux_cross_product_equals_oracle(W):
         abuf, aoff = wl.pack_adapters(ads)
         got = _with(W, {'profile': 1, 'tight_window': 1}, lambda: W.adapter_alignment_batch(lbuf, loff, abuf, aoff, wl.DEFAULT_SCORING))
         assert np.array_equal(got, oracle_batch(lbuf, loff, abuf, aoff, wl.DEFAULT_SCORING)), len(ads)
+
+
+def test_global_staging_under_load_every_window_length_mod_4(W):
+    """hbuf=global (a slot's packed bases staged in the warp's global scratch behind its trace): the per-warp scratch
+    stride must be a whole number of 128-byte lines for every window length -- discard.global.L2 needs aligned
+    addresses and must not drop a neighbouring warp's staged bases (round-1 hardware failure at max_n = 150 with the
+    stride rounded to 16 bytes only).  >= 30 000 uniform windows so every resident warp loops, window lengths
+    150 / 149 / 151 / 153 / 146 (all residues mod 4), with and without the pair profile, one and two adapters."""
+    from porechop_b200 import workloads as wl
+    yt, yb = wl.nsk007()
+    _, sw, ew = wl.synth_end_windows(30011, yt, yb, seed=37)
+    full = np.concatenate([sw, ew[:, :10]], axis=1)           # 160 columns to cut from
+    for n_cols in (150, 149, 151, 153, 146):
+        sbuf, soff = wl.windows_to_batch(np.ascontiguousarray(full[:, :n_cols]))
+        for ads in ([yt], [yt, yb]):
+            abuf, aoff = wl.pack_adapters(ads)
+            exp = oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
+            for opts in ({'hbuf': 'global'}, {'hbuf': 'global', 'profile': 1}):
+                got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
+                assert np.array_equal(got, exp), (n_cols, len(ads), opts)
