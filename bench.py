@@ -2,23 +2,32 @@
 """
 bench.py -- BASELINE.json metric on B200: reads/s (+ GCUPS) of the adapter-alignment hot path.
 
-Workload (default, BASELINE.json configs[1]): 1 M synthetic ~8 kb ONT reads (seed 20260923), adapter set
-SQK-NSK007 (= the LSK109 Y-adapter), end-trim only: per read the 150-nt start window vs Y_Top (28 nt) and the 150-nt
-end window vs Y_Bottom (22 nt) -> 2 alignments, 7 500 DP cells, 372 algorithmic bytes per read.  A "step" is one pass
-of the hot path over the whole batch (two batched C-ABI calls).  Other workloads: --workload demux (configs[2]) and
---workload middle (configs[3] sample).
+Main line (default --workload endtrim = BASELINE.json configs[1]): 1 M synthetic ~8 kb ONT reads (seed 20260923, SURVEY
+8(d)), adapter set SQK-NSK007 (= the LSK109 Y-adapter), end-trim only: per read the 150-nt start window vs Y_Top (28 nt)
+and the 150-nt end window vs Y_Bottom (22 nt) -> 2 alignments, 7 500 DP cells, 372 algorithmic bytes per read.  A "step"
+is one pass of the hot path over the whole batch.
 
-  value   reads/s with the windows already resident in HBM (adapterAlignmentBatchDevice), CUDA-event timed
-  e2e     reads/s through the host-buffer C-ABI call (adapterAlignmentBatch, pinned host buffers): H2D + kernels +
-          D2H inside the timed region, every rank on its own shard and PCIe link; the optional NCCL re-gather of the
-          36-byte records to rank 0 is timed separately (e2e.gather_records_to_rank0_ms)
-  roofline   dominant kernel (trace_kernel) algorithmic bytes / CUDA-event duration vs the measured HBM peak --
-          reported because the north star asks for it; the kernel is integer-ALU (DPX) bound, see `alu`
-  cpu_baseline / --impl reference   the reference's own C++ (oracle/_ref/cpp_functions.so, falling back to the
-          oracle port) timed by the native harness on all host cores, on a bounded sample of the same pair list
+The same JSON line carries a `configs` block with a reduced-step run of the other BASELINE configs (each with its own
+value / e2e / roofline / parity gate / cpu_baseline):
+  demux   configs[2]  1 M reads x 356 adapter sequences (all 119 sets + 12 native-full + 96 rapid-full), end windows
+  middle  configs[3]  full-read middle-adapter scan, 5 % chimeras: 10 M reads over 8 GPUs = 1.25 M reads per GPU
+  sweep   configs[4]  read-length sweep 500 bp - 100 kb x the 192 forward-barcode sequences, 2.5e8 bases per length and GPU
+(--configs none skips them, --workload X makes X the main line.)
 
-Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 via torchrun (one rank per GPU, weak scaling:
-every rank processes its own --reads batch).
+  value   reads/s with the inputs already resident in HBM (adapterAlignmentBatchDevice), CUDA-event timed
+  e2e     reads/s through the host-buffer C-ABI call (adapterAlignmentBatchMulti, pinned host buffers): H2D + kernels +
+          D2H inside the timed region, every rank on its own shard and PCIe link; `e2e_with_gather` (N > 1) adds the NCCL
+          gather of all records to rank 0 and rank 0's copy to its host memory
+  roofline      dominant DP kernel: algorithmic bytes / CUDA-event duration vs the measured HBM peak (the north star asks
+                for it; the kernel is integer-issue bound, so `roofline_alu` is the binding one)
+  roofline_alu  cells/s of the dominant kernel vs the int16x2 issue peak: SMs x 4 schedulers x 32 lanes x clock x 2 cells
+                / instructions per row-step (counted from SASS, profiles/sass_counts.json)
+  cpu_baseline / --impl reference   the reference's own C++ (oracle/_ref/cpp_functions.so, else the oracle port) timed
+          by the native harness on the host cores: 1 thread and a sweep over {nproc/4, nproc/2, nproc} threads and nproc
+          processes (separate heaps), best kept, on a bounded sample of the same pair list
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N>1 via torchrun (one rank per GPU).  --scaling weak
+(default): every rank processes its own full-size batch; --scaling strong: the batch is split over the ranks.
 """
 import argparse
 import json
@@ -34,6 +43,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+DEFAULT_READS = {'endtrim': 1000000, 'demux': 1000000, 'middle': 1250000, 'sweep': 0}
+SWEEP_LENGTHS = '500,1000,2000,5000,10000,20000,50000,100000'
+OUT_CAP_BYTES = 320 << 20          # e2e: records copied back per call (larger batches go through the ABI in read chunks)
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -42,19 +55,20 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='endtrim', choices=['endtrim', 'demux', 'middle', 'sweep'])
-    ap.add_argument('--sweep-lengths', default='500,1000,2000,5000,10000,20000,50000,100000',
-                    help='--workload sweep: read lengths (one batch each, --sweep-bases bases per batch)')
-    ap.add_argument('--sweep-bases', type=float, default=2e8, help='--workload sweep: bases per length point and rank')
-    ap.add_argument('--reads', type=int, default=0, help='reads per rank (default: 1M endtrim, 32k demux, 256k middle)')
+    ap.add_argument('--configs', default='all', help="other BASELINE configs measured into the line's `configs` block: "
+                                                     "all | none | comma list of demux,middle,sweep")
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--sweep-lengths', default=SWEEP_LENGTHS)
+    ap.add_argument('--sweep-bases', type=float, default=2.5e8, help='sweep: bases per length point and rank')
+    ap.add_argument('--reads', type=int, default=0, help='reads of the main workload (per rank if weak, total if strong)')
+    ap.add_argument('--config-reads', default='', help='reads of the `configs` entries, e.g. demux=65536,middle=131072')
     ap.add_argument('--cpu-sample-reads', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-multi', action='store_true',
-                    help="e2e: the step's batches in ONE adapterAlignmentBatchMulti submit instead of one call per batch")
     ap.add_argument('--e2e-decisions', action='store_true',
                     help='e2e (endtrim / demux): adapterEndDecisions -- trim amounts + barcode score pairs decided on the '
                          'device, 4 + 4*adapters bytes per window come back instead of 36 per alignment')
     ap.add_argument('--opt', action='append', default=[], metavar='NAME=VALUE',
-                    help='engine option for this run (pb200SetOption), e.g. --opt h2d_pack=1 --opt tight_window=1')
+                    help='engine option for this run (pb200SetOption), e.g. --opt scratch_mb=72')
     return ap.parse_args()
 
 
@@ -112,102 +126,88 @@ class ClockSampler(threading.Thread):
         return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.sm_max, 'reasons': sorted(self.reasons),
                 'samples': len(self.samples)}
 
+    def take(self):
+        """summary of the samples since the last take()"""
+        s = self.summary()
+        self.samples, self.reasons = [], set()
+        return s
+
 
 # ------------------------------------------------------------------------------------------------------------------
-def make_workload(args, rank):
-    """Returns a list of batches; each batch = (name, window matrix uint8[n, w] or (buf, off), adapter list)."""
-    from porechop_b200 import workloads as wl
+class Workload:
+    """name, desc (nominal, arm-independent), n reads on this rank, batches = [(name, buf uint8, off int64, adapters)]"""
+
+    def __init__(self, name, desc, n, nominal_reads, batches):
+        self.name, self.desc, self.n, self.nominal_reads, self.batches = name, desc, n, nominal_reads, batches
+        self.cells = sum(int(off[-1] - off[0]) * sum(len(a) for a in ads) for _, _, off, ads in batches)
+        self.alg_bytes = sum(int(off[-1] - off[0]) + sum(len(a) for a in ads) + 36 * (len(off) - 1) * len(ads)
+                             for _, _, off, ads in batches)
+        self.alignments_per_read = sum(len(ads) for _, _, _, ads in batches) if name != 'sweep' else len(batches[0][3])
+
+    def config(self, scaling):
+        """identical in both arms (the driver compares the dicts): nominal parameters only"""
+        return {'workload': self.desc, 'reads_per_gpu' if scaling == 'weak' else 'reads_total': self.nominal_reads,
+                'alignments_per_read': self.alignments_per_read, 'scoring': list(_wl().DEFAULT_SCORING), 'scaling': scaling}
+
+
+def _wl():
+    from porechop_b200 import workloads
+    return workloads
+
+
+def nominal_reads(name, args, main):
+    if main and args.reads:
+        return args.reads
+    for kv in args.config_reads.split(','):
+        k, _, v = kv.partition('=')
+        if k == name and v:
+            return int(v)
+    return DEFAULT_READS[name]
+
+
+def make_workload(name, args, rank, world, main, limit=None, alloc=None):
+    """The batch of `rank`.  limit: only the first `limit` reads (the generators are prefix-consistent: the CPU arm times a
+    prefix of exactly the batch the GPU arm aligns).  alloc(nbytes) -> uint8 array to generate large buffers into."""
+    wl = _wl()
     seed = wl.SEED + rank
-    if args.workload == 'endtrim':
-        n = args.reads or 1000000
+    nom = nominal_reads(name, args, main)
+    n = nom if args.scaling == 'weak' else (nom // world + (1 if rank < nom % world else 0))
+    if args.scaling == 'strong':
+        seed = wl.SEED + 1000 + rank
+    if limit is not None:
+        n = min(n, limit)
+    big = (lambda nbytes: alloc(nbytes)) if alloc else (lambda nbytes: None)
+    if name == 'endtrim':
         yt, yb = wl.nsk007()
         L, sw, ew = wl.synth_end_windows(n, yt, yb, seed=seed)
-        batches = [('start', wl.windows_to_batch(sw), [yt]), ('end', wl.windows_to_batch(ew), [yb])]
-        desc = '%d synthetic ~8kb reads (lognormal, seed %d), SQK-NSK007 (LSK109 Y-adapter), end-trim: 150x28 + 150x22 per read' % (n, seed)
-    elif args.workload == 'demux':
-        n = args.reads or 32768
+        batches = [('start',) + wl.windows_to_batch(sw) + ([yt],), ('end',) + wl.windows_to_batch(ew) + ([yb],)]
+        desc = '%d synthetic ~8kb reads (lognormal, seed %d+rank), SQK-NSK007 (LSK109 Y-adapter), end-trim: 150x28 + 150x22 per read' % (nom, wl.SEED)
+    elif name == 'demux':
         starts, ends = wl.demux_adapters()
         L, sw, ew = wl.synth_end_windows(n, starts[100], ends[100], seed=seed)
-        batches = [('start', wl.windows_to_batch(sw), starts), ('end', wl.windows_to_batch(ew), ends)]
-        desc = '%d synthetic reads x 356 adapters (119 sets + 12 native-full + 96 rapid-full), demux end windows' % n
-    elif args.workload == 'sweep':
-        # BASELINE configs[4]: read-length sweep x the 192 sequences of the 96 forward barcode sets, full-read scan; the same
-        # number of bases at every length so the points are comparable (one batch per length; run one length at a time with
-        # --sweep-lengths L to get a per-length number)
+        batches = [('start',) + wl.windows_to_batch(sw) + (starts,), ('end',) + wl.windows_to_batch(ew) + (ends,)]
+        desc = '%d synthetic reads x 356 adapter sequences (119 sets + 12 native-full + 96 rapid-full: 227 start + 129 end), demux end windows' % nom
+    elif name == 'sweep':
         bcs = wl.forward_barcode_sequences()
         lengths = [int(x) for x in args.sweep_lengths.split(',')]
-        batches, n = [], 0
-        for L in lengths:
-            k = max(1, int(args.sweep_bases // L))
-            batches.append(('L%d' % L, wl.synth_fixed_length_reads(k, L, bcs, seed=seed + L), bcs))
+        batches, n, nom = [], 0, 0
+        for Ln in lengths:
+            k_nom = max(1, int(args.sweep_bases // Ln))
+            k = k_nom if args.scaling == 'weak' else max(1, k_nom // world)
+            if limit is not None:
+                k = min(k, max(1, int(limit * 8000 // Ln)))          # `limit` is given in 8-kb read equivalents
+            buf, off = wl.synth_fixed_length_reads(k, Ln, bcs, seed=seed + Ln, out=big(k * Ln))
+            batches.append(('L%d' % Ln, buf, off, bcs))
             n += k
-        desc = 'read-length sweep %s x 192 forward barcode sequences (24 nt), %.0e bases per length, full-read scan' % (
+            nom += k_nom
+        desc = 'read-length sweep %s x 192 forward barcode sequences (24 nt), %.1e bases per length, full-read scan' % (
             args.sweep_lengths, args.sweep_bases)
     else:
-        n = args.reads or 262144     # >= ~14 reads per resident group, so one 60-kb read is not the makespan
         yt, yb = wl.nsk007()
-        buf, off = wl.synth_reads(n, yt, yb, seed=seed, chimera_p=0.05)
-        batches = [('middle', (buf, off), [yt, yb])]
-        desc = '%d synthetic full reads (5%% chimeras) x {Y_Top, Y_Bottom}, middle-adapter scan (two-pass)' % n
-    return n, batches, desc
-
-
-def batch_cells(batch):
-    (buf, off), ads = batch[1], batch[2]
-    return int(off[-1] - off[0]) * sum(len(a) for a in ads)
-
-
-def batch_alg_bytes(batch):
-    (buf, off), ads = batch[1], batch[2]
-    n = len(off) - 1
-    return int(off[-1] - off[0]) + sum(len(a) for a in ads) + 36 * n * len(ads)
-
-
-def run_reference_harness(batches, scoring, sample_reads, threads, answers=None):
-    """Time the reference CPU path (oracle/_ref/cpp_functions.so via the native harness) on the first
-    `sample_reads` reads of every batch.  Returns (seconds, reads, cells, kind).  With `answers` (a list), the result
-    strings of every sampled pair (pair order = read-major) are appended per batch: the checker for the parity gate."""
-    from porechop_b200 import workloads as wl
-    lib = os.path.join(ROOT, 'oracle', '_ref', 'cpp_functions.so')
-    kind = 'reference'
-    if not os.path.exists(lib):
-        lib = os.path.join(ROOT, 'oracle', 'liboracle.so')
-        kind = 'port'
-    harness = os.path.join(ROOT, 'oracle', '_ref', 'ref_harness')
-    if not os.path.exists(harness) or not os.path.exists(lib):
-        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle'), 'liboracle.so', 'harness', 'ref'])
-    sec = 0.0
-    cells = 0
-    with tempfile.TemporaryDirectory() as d:
-        for name, (buf, off), ads in batches:
-            k = min(sample_reads, len(off) - 1)
-            abuf, aoff = wl.pack_adapters(ads)
-            p = os.path.join(d, name + '.bin')
-            wl.write_harness_file(p, buf[:off[k]], off[:k + 1], abuf, aoff, scoring)
-            cmd = [harness, lib, p, str(threads)]
-            if answers is not None:
-                cmd.append(os.path.join(d, name + '.answers'))
-            info = json.loads(subprocess.check_output(cmd).decode())
-            sec += info['seconds']
-            cells += info['cells']
-            if answers is not None:
-                with open(cmd[-1]) as f:
-                    answers.append(f.read().split('\n')[:-1])
-    return sec, min(sample_reads, len(batches[0][1][1]) - 1), cells, kind
-
-
-def parity_gate(records_per_batch, answers_per_batch, format_record):
-    """SURVEY 8(d) parity gate: the engine's records of the sampled pairs, rendered as the reference's result string,
-    must equal the CPU reference's strings.  (An empty alignment is compared on its first field only: the reference
-    leaves the others uninitialised.)  Returns {'checked': n, 'mismatches': k}."""
-    checked = bad = 0
-    for rec, ans in zip(records_per_batch, answers_per_batch):
-        for r, a in zip(rec[:len(ans)], ans):
-            g = format_record(r)
-            ok = (g == a) or (a.startswith('-1,') and g.startswith('-1,'))
-            checked += 1
-            bad += 0 if ok else 1
-    return {'checked': checked, 'mismatches': bad}
+        buf, off = wl.synth_reads_fast(n, yt, yb, seed=seed, chimera_p=0.05, out=big(n * 8400 + (4 << 20)) if n > 50000 else None)
+        batches = [('middle', buf, off, [yt, yb])]
+        desc = '%d synthetic full reads (~8 kb lognormal, 5%% chimeras) x {Y_Top, Y_Bottom}, middle-adapter scan' % nom
+    return Workload(name, desc, n, nom, batches)
 
 
 def host_cores():
@@ -217,85 +217,189 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def cpu_info():
+    model, quota = None, None
+    try:
+        with open('/proc/cpuinfo') as f:
+            for line in f:
+                if line.startswith('model name'):
+                    model = line.split(':', 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    for p in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+        try:
+            with open(p) as f:
+                quota = f.read().strip()
+                break
+        except OSError:
+            pass
+    return {'model': model, 'nproc': os.cpu_count(), 'affinity': host_cores(), 'cgroup_cpu_max': quota}
+
+
 # ------------------------------------------------------------------------------------------------------------------
-def main():
-    args = parse_args()
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    from porechop_b200 import workloads as wl
-    scoring = wl.DEFAULT_SCORING
+def harness_paths():
+    lib = os.path.join(ROOT, 'oracle', '_ref', 'cpp_functions.so')
+    kind = 'reference'
+    if not os.path.exists(lib):
+        lib = os.path.join(ROOT, 'oracle', 'liboracle.so')
+        kind = 'port'
+    harness = os.path.join(ROOT, 'oracle', '_ref', 'ref_harness')
+    if not os.path.exists(harness) or not os.path.exists(lib):
+        subprocess.check_call(['make', '-s', '-C', os.path.join(ROOT, 'oracle'), 'liboracle.so', 'harness', 'ref'])
+    return harness, lib, kind
 
-    if args.impl == 'reference':
-        if rank != 0:
-            return 0
-        n, batches, desc = make_workload(args, 0)
-        cores = host_cores()
-        per_read_cells = sum(batch_cells(b) for b in batches) / n
-        # bounded sample: ~3 core-seconds per core per step at ~0.08 GCUPS/core
-        sample = args.cpu_sample_reads or int(max(64, min(n, 0.08e9 * 1.5 * cores / per_read_cells)))
-        times = []
-        cells = 0
-        for s in range(args.warmup + args.steps):
-            sec, reads, cells, kind = run_reference_harness(batches, scoring, sample, cores)
-            if s >= args.warmup:
-                times.append(sec)
-        t = float(np.mean(times))
-        value = sample / t
-        line = {'impl': 'reference', 'metric': 'reads/sec', 'value': value, 'unit': 'reads/s', 'n_gpus': args.gpus,
-                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic',
-                'gcups': cells / t / 1e9,
-                'config': {'workload': desc, 'sample': 'first %d reads of the batch per step' % sample},
-                'cpu_baseline': {'value': value, 'unit': 'reads/s', 'cores': cores, 'kind': kind,
-                                 'sample': 'first %d reads (%d alignments) per step, %d threads, native harness over the reference C-ABI' %
-                                           (sample, sample * int(round(per_read_cells / 7500 * 2)) if args.workload == 'endtrim' else sample, cores)},
-                'e2e': {'value': value, 'unit': 'reads/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
-        return 0
 
+class HarnessFiles:
+    """The first `reads` reads of every batch of a workload, written once as harness input files."""
+
+    def __init__(self, workload, reads_per_batch):
+        wl = _wl()
+        self.dir = tempfile.TemporaryDirectory()
+        self.files, self.reads, self.cells = [], 0, 0
+        for (name, buf, off, ads), k in zip(workload.batches, reads_per_batch):
+            k = min(int(k), len(off) - 1)
+            abuf, aoff = wl.pack_adapters(ads)
+            p = os.path.join(self.dir.name, name + '.bin')
+            base = int(off[0])
+            wl.write_harness_file(p, buf[base:int(off[k])], off[:k + 1] - base, abuf, aoff, wl.DEFAULT_SCORING)
+            self.files.append((name, p, k))
+            self.reads += k
+            self.cells += int(off[k] - off[0]) * sum(len(a) for a in ads)
+
+    def run(self, threads, procs=1, answers=None):
+        """-> seconds over all batches.  answers: list that receives, per batch, the result strings (pair order)."""
+        harness, lib, kind = harness_paths()
+        sec = 0.0
+        env = dict(os.environ)
+        if procs > 1:
+            env['REF_HARNESS_PROCS'] = str(procs)
+        for name, p, k in self.files:
+            cmd = [harness, lib, p, str(threads)]
+            if answers is not None:
+                cmd.append(p + '.answers')
+            info = json.loads(subprocess.check_output(cmd, env=env).decode())
+            sec += info['seconds']
+            if answers is not None:
+                with open(cmd[-1]) as f:
+                    answers.append(f.read().split('\n')[:-1])
+        return sec
+
+
+def sample_sizes(workload, cores, seconds, per_core_gcups=0.06):
+    """reads per batch such that the all-core run takes about `seconds` (the reference runs ~0.08 GCUPS per core alone)."""
+    out = []
+    total_cells = max(workload.cells, 1)
+    for name, buf, off, ads in workload.batches:
+        n = len(off) - 1
+        cells_per_read = max(1.0, (int(off[-1] - off[0]) / max(n, 1)) * sum(len(a) for a in ads))
+        share = (int(off[-1] - off[0]) * sum(len(a) for a in ads)) / total_cells
+        out.append(int(max(8, min(n, share * seconds * per_core_gcups * 1e9 * cores / cells_per_read))))
+    return out
+
+
+def cpu_baseline(workload, sample_reads=0, sweep=True, seconds=3.0, want_answers=True):
+    """1-thread and all-core numbers of the reference CPU path on a bounded sample.
+    Returns (dict, answers per batch or None, reads per batch)."""
+    cores = host_cores()
+    harness, lib, kind = harness_paths()
+    sizes = [min(sample_reads, len(off) - 1) for _, _, off, _ in workload.batches] if sample_reads else sample_sizes(workload, cores, seconds)
+    files = HarnessFiles(workload, sizes)
+    # reads/s of the WORKLOAD: a sample may hold different fractions of the batches, so scale by cells
+    cells_per_read = workload.cells / max(workload.n, 1)
+    answers = [] if want_answers else None
+    runs = []
+    sec = files.run(cores, 1, answers)
+    runs.append({'threads': cores, 'procs': 1, 'seconds': sec})
+    if sweep and cores >= 4:
+        for t in sorted({max(1, cores // 4), max(1, cores // 2)}):
+            runs.append({'threads': t, 'procs': 1, 'seconds': files.run(t)})
+    if cores >= 2:
+        runs.append({'threads': 1, 'procs': cores, 'seconds': files.run(1, cores)})
+    for r in runs:
+        r['gcups'] = files.cells / r['seconds'] / 1e9
+        r['reads_per_s'] = files.cells / r['seconds'] / cells_per_read
+    best = max(runs, key=lambda r: r['gcups'])
+    # one thread: a 1/cores share of the sample (about the same wall time)
+    one = HarnessFiles(workload, [max(1, k // max(cores // 2, 1)) for k in sizes])
+    sec1 = one.run(1)
+    d = {'value': best['reads_per_s'], 'unit': 'reads/s', 'cores': best['threads'] * best['procs'], 'kind': kind,
+         'gcups': best['gcups'], 'mode': '%d threads x %d processes' % (best['threads'], best['procs']),
+         'one_thread': {'value': one.cells / sec1 / cells_per_read, 'unit': 'reads/s', 'gcups': one.cells / sec1 / 1e9,
+                        'sample_reads': one.reads},
+         'sweep': runs, 'host': cpu_info(),
+         'sample': 'first %s reads of the batches (%d alignment cells x 1e6), native harness over the reference C-ABI '
+                   '(adapterAlignment+freeCString); reads/s scaled by cells to the whole workload' % (sizes, files.cells // 1000000)}
+    return d, answers, sizes
+
+
+def parity_gate(records_per_batch, answers_per_batch, format_record):
+    """SURVEY 8(d) parity gate: the engine's records of the sampled pairs, rendered as the reference's result string,
+    must equal the CPU reference's strings.  (An empty alignment is compared on its first field only: the reference
+    leaves the others uninitialised.)  Returns {'checked': n, 'mismatches': k}."""
+    checked = bad = 0
+    for rec, ans in zip(records_per_batch, answers_per_batch):
+        assert len(rec) >= len(ans), 'parity sample larger than the kept records'
+        for r, a in zip(rec[:len(ans)], ans):
+            g = format_record(r)
+            ok = (g == a) or (a.startswith('-1,') and g.startswith('-1,'))
+            checked += 1
+            bad += 0 if ok else 1
+    return {'checked': checked, 'mismatches': bad}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def sass_counts():
+    p = os.path.join(ROOT, 'profiles', 'sass_counts.json')
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def measure_gpu(workload, args, ctx, K, Wm, main):
+    """value / e2e / roofline of one workload on this rank's GPU; rank 0 gets the complete dict."""
     import torch
     import torch.distributed as dist
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    from porechop_b200 import cpp_function_wrappers as W
+    W, wl, world, rank, sampler = ctx['W'], _wl(), ctx['world'], ctx['rank'], ctx['sampler']
+    scoring = wl.DEFAULT_SCORING
+    keep = ctx['keep']
 
-    n, batches, desc = make_workload(args, rank)
-    K, Wm = args.steps, args.warmup
-    for kv in args.opt:
-        name, _, val = kv.partition('=')
-        W.set_option(name, val)
-
-    # ---- host (pinned) and device copies of the inputs ----
-    host, dev = [], []
-    for name, (buf, off), ads in batches:
-        abuf, aoff = wl.pack_adapters(ads)
-        hb = torch.empty(len(buf), dtype=torch.uint8, pin_memory=True)
-        hb.numpy()[:] = buf
-        ho = torch.empty(len(off), dtype=torch.int64, pin_memory=True)
-        ho.numpy()[:] = off
-        n_pairs = (len(off) - 1) * len(ads)
-        hout = torch.empty((n_pairs, 9), dtype=torch.int32, pin_memory=True)
-        host.append((hb, ho, abuf, aoff, hout))
-        db, do = hb.cuda(non_blocking=True), ho.cuda(non_blocking=True)
-        dout = torch.empty((n_pairs, 9), dtype=torch.int32, device='cuda')
-        max_len = int(np.max(np.diff(off))) if len(off) > 1 else 0
-        dev.append((db, do, abuf, aoff, dout, max_len))
-    torch.cuda.synchronize()
-    in_bytes = sum(h[0].numel() + h[1].numel() * 8 + len(h[2]) + len(h[3]) * 4 for h in host)
-    out_bytes = sum(h[4].numel() * 4 for h in host)
-    cells_per_step = sum(batch_cells(b) for b in batches)
+    def pinned(shape, dtype):
+        t = torch.empty(shape, dtype=dtype, pin_memory=True)
+        keep.append(t)
+        return t
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # the device-resident path runs on an explicit (non-default) stream; the CUDA events that time it are recorded on
-    # the same stream.  (Handle 0 = "NULL" means "the library's own stream" to the C-ABI.)
-    bench_stream = torch.cuda.Stream()
+    # ---- host (pinned) and device copies of the inputs ----
+    host, dev = [], []
+    for name, buf, off, ads in workload.batches:
+        abuf, aoff = wl.pack_adapters(ads)
+        hb = torch.from_numpy(buf)
+        if not hb.is_pinned():
+            hb = pinned(len(buf), torch.uint8)
+            hb.numpy()[:] = buf
+        ho = pinned(len(off), torch.int64)
+        ho.numpy()[:] = off
+        n_reads = len(off) - 1
+        chunk = max(1, min(n_reads, OUT_CAP_BYTES // (36 * len(ads))))
+        out0 = pinned((chunk * len(ads), 9), torch.int32)                # records of the first chunk are kept (parity gate)
+        out1 = pinned((chunk * len(ads), 9), torch.int32) if chunk < n_reads else out0
+        host.append((hb, ho, abuf, aoff, chunk, out0, out1))
+        db, do = hb.cuda(non_blocking=True), ho.cuda(non_blocking=True)
+        dout = torch.empty((n_reads * len(ads), 9), dtype=torch.int32, device='cuda')
+        max_len = int(np.max(np.diff(off))) if n_reads else 0
+        dev.append((db, do, abuf, aoff, dout, max_len))
+    torch.cuda.synchronize()
+    in_bytes = sum(h[0].numel() + h[1].numel() * 8 + len(h[2]) + len(h[3]) * 4 for h in host)
+    out_bytes = sum((h[1].numel() - 1) * (len(h[3]) - 1) * 36 for h in host)
+
+    bench_stream = ctx['stream']
 
     def step_device():
         s = bench_stream.cuda_stream
@@ -304,37 +408,34 @@ def main():
             W.adapter_alignment_batch_device(db.data_ptr(), do.data_ptr(), do.numel() - 1, db.numel(), max_len, abuf, aoff,
                                              scoring, dout.data_ptr(), s)
 
+    # e2e: one Multi submit per step when everything fits the record cap, else read chunks per batch
+    calls = []
+    single = all(h[4] >= h[1].numel() - 1 for h in host)
+    if single:
+        calls.append([(hb.numpy(), ho.numpy(), abuf, aoff, out0.numpy()) for hb, ho, abuf, aoff, chunk, out0, out1 in host])
+    else:
+        for hb, ho, abuf, aoff, chunk, out0, out1 in host:
+            n_reads = ho.numel() - 1
+            for s0 in range(0, n_reads, chunk):
+                s1 = min(n_reads, s0 + chunk)
+                o = (out0 if s0 == 0 else out1).numpy()[:(s1 - s0) * (len(aoff) - 1)]
+                calls.append([(hb.numpy(), ho.numpy()[s0:s1 + 1], abuf, aoff, o)])
+
     dec_out = None
-    if args.e2e_decisions:
-        assert args.workload in ('endtrim', 'demux'), '--e2e-decisions applies to the end-window workloads'
-        dec_out = []
-        for (name, _, ads), (hb, ho, abuf, aoff, hout) in zip(batches, host):
-            nw, na = ho.numel() - 1, len(ads)
-            dec_out.append((torch.empty(nw, dtype=torch.int32, pin_memory=True),
-                            torch.empty((nw, na, 2), dtype=torch.uint16, pin_memory=True)))
-        out_bytes_dec = sum(t.numel() * 4 + p.numel() * 2 for t, p in dec_out)
+    if args.e2e_decisions and workload.name in ('endtrim', 'demux'):
+        dec_out = [(pinned(h[1].numel() - 1, torch.int32), pinned((h[1].numel() - 1, len(h[3]) - 1, 2), torch.uint16)) for h in host]
 
     def step_e2e():
-        # every rank pushes its own shard through the host-buffer C-ABI over its own PCIe link; the records stay
-        # rank-local (no data-path collective, prompt (5)); the optional re-gather to a writer rank is timed separately
-        if args.e2e_decisions:
-            # every adapter is a score column (upper bound of what barcode calling needs)
-            W.adapter_end_decisions([(hb.numpy(), ho.numpy(), abuf, aoff, b[0] == 'start', list(range(len(b[2]))))
-                                     for b, (hb, ho, abuf, aoff, hout) in zip(batches, host)], scoring, wl.END_SIZE, 2, 75.0, 4,
+        if dec_out is not None:
+            W.adapter_end_decisions([(h[0].numpy(), h[1].numpy(), h[2], h[3], b[0] == 'start', list(range(len(b[3]))))
+                                     for b, h in zip(workload.batches, host)], scoring, wl.END_SIZE, 2, 75.0, 4,
                                     out_arrays=[(t.numpy(), p.numpy(), None) for t, p in dec_out])
             return
-        if args.e2e_multi:
-            W.adapter_alignment_batch_multi([(hb.numpy(), ho.numpy(), abuf, aoff, hout.numpy()) for hb, ho, abuf, aoff, hout in host],
-                                            scoring)
-            return
-        for hb, ho, abuf, aoff, hout in host:
-            W.adapter_alignment_batch(hb.numpy(), ho.numpy(), abuf, aoff, scoring, out=hout.numpy())
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+        for c in calls:
+            W.adapter_alignment_batch_multi(c, scoring)
 
     # ---- value: device-resident ----
-    for _ in range(max(Wm, 3)):
+    for _ in range(max(Wm, 1)):
         step_device()
     barrier()
     W.synchronize()
@@ -342,6 +443,7 @@ def main():
     W.timing_read(reset=True)
     l0 = W.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.take()
     sampler.active = True
     barrier()
     ev0.record(bench_stream)
@@ -353,11 +455,12 @@ def main():
     launches = W.kernel_launches() - l0
     dev_ms = ev0.elapsed_time(ev1)
     W.synchronize()
-    dp_ms, dp_n = W.timing_read(reset=True)
+    kinds = W.timing_read_kinds(reset=True)
     W.timing_enable(False)
+    clocks_value = sampler.take()
 
     # ---- e2e: host buffers through the C-ABI ----
-    for _ in range(max(Wm, 3)):
+    for _ in range(max(Wm, 1)):
         step_e2e()
     barrier()
     sampler.active = True
@@ -367,114 +470,320 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     sampler.active = False
-    sampler.stop_flag = True
-    if args.e2e_decisions:
-        # the in-run parity gate needs the records themselves: one more (untimed) step through the record call, and the
-        # decisions of the timed steps are checked against the host rule on those records
-        from porechop_b200 import hostio
-        out_bytes = out_bytes_dec
-        dec_bad = 0
-        for b, (hb, ho, abuf, aoff, hout), (t, p) in zip(batches, host, dec_out):
-            W.adapter_alignment_batch(hb.numpy(), ho.numpy(), abuf, aoff, scoring, out=hout.numpy())
-            rec = hout.numpy().reshape(ho.numel() - 1, len(b[2]), 9)
-            exp = hostio.end_trim(rec, b[0] == 'start', wl.END_SIZE, 2, 75.0, 4)
-            dec_bad += int(np.count_nonzero(exp != t.numpy()))
-            dec_bad += int(np.count_nonzero(p.numpy()[:, :, 0] != rec[:, :, 7].astype(np.uint16)))
+    clocks_e2e = sampler.take()
+    if dec_out is not None:
+        out_bytes = sum(t.numel() * 4 + p.numel() * 2 for t, p in dec_out)
+        for c in calls:                                   # the parity gate needs the records: one untimed record step
+            W.adapter_alignment_batch_multi(c, scoring)
 
-    # informational: NCCL re-gather of the 36-byte records of every rank to rank 0 (device -> device over NVLink)
+    # ---- e2e with the NCCL re-gather of every rank's records to rank 0 (north star: "re-gather the output stream") ----
     gather_ms = None
-    if world > 1:
-        db, do, abuf, aoff, dout, max_len = dev[0]
-        bucket = [torch.empty_like(dout) for _ in range(world)] if rank == 0 else None
-        dist.gather(dout, bucket, dst=0)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _, _, _, _, d_o, _ in dev:
-            dist.gather(d_o, [torch.empty_like(d_o) for _ in range(world)] if rank == 0 else None, dst=0)
-        g1.record()
-        barrier()
-        gather_ms = g0.elapsed_time(g1)
+    if world > 1 and main:
+        from porechop_b200.distributed import gather_records
+        counts = []
+        for d in dev:
+            c = [None] * world
+            dist.all_gather_object(c, int(d[4].shape[0]))
+            counts.append(c)
+        hall = [pinned((sum(c), 9), torch.int32) if rank == 0 else None for c in counts]
+        G = max(1, min(K, 3))
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, gather_ms or 0.0], dtype=torch.float64, device='cuda')
+        def step_gather():
+            with torch.cuda.stream(bench_stream):
+                for (hb, ho, *_), (db, do, abuf, aoff, dout, max_len), c, ha in zip(host, dev, counts, hall):
+                    db.copy_(hb, non_blocking=True)
+                    do.copy_(ho, non_blocking=True)
+                    W.adapter_alignment_batch_device(db.data_ptr(), do.data_ptr(), do.numel() - 1, db.numel(), max_len, abuf,
+                                                     aoff, scoring, dout.data_ptr(), bench_stream.cuda_stream)
+                    allrec = gather_records(dout, c, dst=0)
+                    if allrec is not None:
+                        ha.copy_(allrec, non_blocking=True)
+            bench_stream.synchronize()
+        step_gather()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(G):
+            step_gather()
+        barrier()
+        gather_ms = (time.perf_counter() - t0) * 1e3 / G
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, gather_ms or 0.0, float(workload.n), float(workload.cells), float(workload.alg_bytes),
+                      float(in_bytes), float(out_bytes)], dtype=torch.float64, device='cuda')
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, gather_ms = float(t[0]), float(t[1]), (float(t[2]) if world > 1 else None)
-    total_reads = n * world
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms, gather_ms = float(tm[0]), float(tm[1]), float(tm[2])
+        total_reads, total_cells = float(ts[3]), float(ts[4])
+    else:
+        e2e_ms = e2e_s * 1e3
+        total_reads, total_cells = float(workload.n), float(workload.cells)
+    res = {'host': host, 'dev': dev}
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
+        return None, res
 
     value = total_reads * K / (dev_ms / 1e3)
     e2e_value = total_reads * K / (e2e_ms / 1e3)
-    # roofline of the dominant kernel (trace_kernel / score_kernel launches timed by CUDA events in the library)
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     else:
-        peak, peak_src = 6650.0, 'fallback'
-    alg_bytes_step = sum(batch_alg_bytes(b) for b in batches)
-    dp_launch_ms = dp_ms / max(dp_n, 1)
-    launches_per_step = dp_n / K
-    bytes_per_launch = alg_bytes_step / max(launches_per_step, 1e-9)
-    achieved = bytes_per_launch / (dp_launch_ms / 1e3) / 1e9 if dp_n else None
-    traffic = None
-    tp = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tp):
+        peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+    # dominant DP kernel of the step = the kind with the largest CUDA-event time (events recorded by the library around
+    # every DP launch on the launching stream)
+    dom = max(kinds, key=lambda k: kinds[k]['ms']) if kinds else None
+    roof, alu = None, None
+    sm_mhz = clocks_value.get('sm_mhz') or 1965.0
+    if dom and kinds[dom]['n']:
+        kd = kinds[dom]
+        per_step_ms = kd['ms'] / K
+        launch_ms = kd['ms'] / kd['n']
+        launches_per_step = kd['n'] / K
+        bytes_per_launch = workload.alg_bytes / launches_per_step
+        achieved = bytes_per_launch / (launch_ms / 1e3) / 1e9
+        traffic = None
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(workload.name)
         except Exception:
-            traffic = None
-    clocks = sampler.summary()
-    sm_mhz = clocks.get('sm_mhz') or 1965.0
-    gcups_kernel = cells_per_step * K / (dp_ms / 1e3) / 1e9 if dp_n else None
+            pass
+        roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                'peak_source': peak_src, 'kernel': dom, 'launch_ms': launch_ms, 'launches_per_step': launches_per_step,
+                'algorithmic_bytes_per_launch': bytes_per_launch,
+                'kernels_ms_per_step': {k: v['ms'] / K for k, v in kinds.items()},
+                'note': 'algorithmic bytes of the step (sum|H| + sum|V| + 36 B per alignment) / launches of the dominant kernel; '
+                        'the kernel is integer-issue bound by construction (SURVEY 0.7): see roofline_alu'}
+        sc = sass_counts().get(dom, {})
+        cells_kernel = kd.get('cells') or workload.cells * K        # full-sweep kernels process every cell of the step
+        cps = cells_kernel / (kd['ms'] / 1e3)
+        if sc.get('instr_per_cell'):
+            peak_cells = 148 * 4 * 32 * sm_mhz * 1e6 / sc['instr_per_cell']
+            alu = {'kernel': dom, 'instr_per_cell': sc['instr_per_cell'], 'source': sc.get('source'),
+                   'achieved_cells_per_s': cps, 'peak_cells_per_s': peak_cells, 'frac': cps / peak_cells, 'sm_mhz': sm_mhz,
+                   'gcups_kernel': cps / 1e9, 'ms_per_step': per_step_ms}
+        else:
+            alu = {'kernel': dom, 'achieved_cells_per_s': cps, 'gcups_kernel': cps / 1e9, 'sm_mhz': sm_mhz,
+                   'lane_instr_peak_per_s': 148 * 4 * 32 * sm_mhz * 1e6, 'ms_per_step': per_step_ms}
     line = {
         'metric': 'reads/sec', 'value': value, 'unit': 'reads/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
-        'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': dev_ms / K, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'int16 (s16x2 DPX)', 'data': 'synthetic',
-        'gcups': cells_per_step * world * K / (dev_ms / 1e3) / 1e9,
-        'config': {'workload': desc, 'reads_per_gpu': n, 'alignments_per_read': sum(len(b[2]) for b in batches),
-                   'cells_per_read': cells_per_step / n, 'scoring': list(scoring),
-                   'l2': 'inputs %.0f MB per step exceed the 126 MB L2' % (in_bytes / 1e6)},
+        'gcups': total_cells * K / (dev_ms / 1e3) / 1e9,
+        'config': workload.config(args.scaling),
+        'cells_per_read': workload.cells / max(workload.n, 1),
+        'timing': {'l2': 'inputs %.0f MB per step and rank exceed the 126 MB L2' % (in_bytes / 1e6) if in_bytes > 126e6 else
+                         'inputs %.0f MB per step' % (in_bytes / 1e6), 'clock': 'CUDA events on the launching stream (value), '
+                   'host clock around synchronous C-ABI calls (e2e); max over ranks'},
         'e2e': {'value': e2e_value, 'unit': 'reads/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': out_bytes,
-                'ms_per_step': e2e_ms / K, 'gcups': cells_per_step * world * K / (e2e_ms / 1e3) / 1e9,
-                'path': ('adapterEndDecisions (host buffers, pinned), one submit per step per rank, decisions come back' if args.e2e_decisions else
-                         'adapterAlignmentBatchMulti (host buffers, pinned), one submit per step per rank' if args.e2e_multi else
-                         'adapterAlignmentBatch (host buffers, pinned), one call per batch per rank') + '; records stay rank-local',
-                'options': args.opt,
-                'decisions': ({'mismatches_vs_host_rule': dec_bad} if args.e2e_decisions else None),
-                'gather_records_to_rank0_ms': gather_ms},
+                'ms_per_step': e2e_ms / K, 'gcups': total_cells * K / (e2e_ms / 1e3) / 1e9,
+                'path': ('adapterEndDecisions (host buffers, pinned), decisions come back' if dec_out is not None else
+                         'adapterAlignmentBatchMulti (host buffers, pinned), %d submit(s) per step per rank' % len(calls)) +
+                        '; records stay rank-local',
+                'options': args.opt, 'ratio_to_value': e2e_value / value},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                     'frac': (achieved / peak) if achieved else None, 'traffic': traffic, 'peak_source': peak_src,
-                     'kernel': 'trace_kernel (s16x2 wavefront DP + in-kernel traceback)', 'launch_ms': dp_launch_ms,
-                     'launches_per_step': launches_per_step, 'algorithmic_bytes_per_launch': bytes_per_launch,
-                     'note': 'the kernel is integer-ALU (DPX) bound by construction (SURVEY 0.7); see alu'},
-        'alu': {'gcups_kernel': gcups_kernel, 'sm_mhz': sm_mhz,
-                'lane_instr_peak_per_s': 148 * 4 * 32 * sm_mhz * 1e6,
-                'cells_per_lane_instr': (gcups_kernel * 1e9) / (148 * 4 * 32 * sm_mhz * 1e6) if gcups_kernel else None},
-        'clocks': clocks,
+        'roofline': roof, 'roofline_alu': alu,
+        'clocks': clocks_value, 'clocks_e2e': clocks_e2e,
     }
-    if world == 1 and not args.no_cpu_baseline:
-        cores = host_cores()
-        per_read_cells = cells_per_step / n
-        sample = args.cpu_sample_reads or int(max(64, min(n, 0.08e9 * 1.0 * cores * 4 / per_read_cells)))
-        answers = []
-        sec, reads, ccells, kind = run_reference_harness(batches, scoring, sample, cores, answers)
-        try:    # parity gate on the same sample: records of the last e2e step vs the CPU reference's strings
-            line['parity'] = parity_gate([h[4].numpy() for h in host], answers, W.format_record)
-            line['parity']['against'] = kind
-        except Exception as e:      # never lose the bench line to the checker
-            line['parity'] = {'error': repr(e)}
-        line['cpu_baseline'] = {'value': sample / sec, 'unit': 'reads/s', 'cores': cores, 'kind': kind,
-                                'gcups': ccells / sec / 1e9,
-                                'sample': 'first %d reads of the same batch (all their alignments), %d threads, native harness '
-                                          'over the reference C-ABI (adapterAlignment+freeCString)' % (sample, cores)}
-    print(json.dumps(line))
+    if gather_ms:
+        line['e2e_with_gather'] = {'value': total_reads / (gather_ms / 1e3), 'unit': 'reads/s', 'ms_per_step': gather_ms,
+                                   'path': 'per rank: pinned host -> device copy, adapterAlignmentBatchDevice, NCCL gather of the '
+                                           '36-byte records to rank 0, rank 0 device -> host copy of all ranks\' records'}
+    return line, res
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    from porechop_b200 import distributed as D
+    numa = None
+    try:
+        numa = D.bind_host_to_gpu(_pci_bus_id(local_rank), int(os.environ.get('LOCAL_WORLD_SIZE', world)), local_rank)
+    except Exception:
+        numa = None
     if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    from porechop_b200 import cpp_function_wrappers as W
+    for kv in args.opt:
+        name, _, val = kv.partition('=')
+        W.set_option(name, val)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    keep = []
+    ctx = {'W': W, 'world': world, 'rank': rank, 'sampler': sampler, 'keep': keep, 'stream': torch.cuda.Stream()}
+
+    def alloc(nbytes):
+        t = torch.empty(int(nbytes), dtype=torch.uint8, pin_memory=True)
+        keep.append(t)
+        return t.numpy()
+
+    def one(name, K, Wm, main):
+        w = make_workload(name, args, rank, world, main, alloc=alloc)
+        line, res = measure_gpu(w, args, ctx, K, Wm, main)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            try:
+                cb, answers, sizes = cpu_baseline(w, args.cpu_sample_reads if main else 0, sweep=main)
+                line['cpu_baseline'] = cb
+                # parity gate: the records the timed e2e steps left in the first output chunk vs the reference's strings
+                recs = [h[5].numpy() for h in res['host']]
+                line['parity'] = parity_gate(recs, answers, W.format_record)
+                line['parity']['against'] = cb['kind']
+            except Exception as e:
+                line['parity'] = {'error': repr(e)}
+        del res
+        keep.clear()
+        torch.cuda.empty_cache()
+        return line
+
+    line = one(args.workload, args.steps, args.warmup, True)
+    others = [] if args.configs == 'none' else [c for c in (['demux', 'middle', 'sweep'] if args.configs == 'all' else args.configs.split(','))
+                                                 if c and c != args.workload]
+    cfgs = {}
+    for name in others:
+        try:
+            sub = one(name, 2 if name != 'demux' else 1, 1, False)
+        except Exception as e:                      # a failing side config must not lose the headline
+            sub = {'error': repr(e)}
+        if rank == 0:
+            cfgs[name] = sub
+    sampler.stop_flag = True
+    if rank == 0:
+        line['configs'] = cfgs
+        line['numa'] = numa
+        bad = [k for k, v in [('main', line)] + list(cfgs.items()) if isinstance(v, dict) and
+               (v.get('parity', {}).get('mismatches') or 'error' in v.get('parity', {}) or 'error' in v)]
+        if bad:
+            line['invalid'] = 'parity gate failed / errored for: %s' % bad
+        print(json.dumps(line))
+        rc = 1 if bad else 0
+    else:
+        rc = 0
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    return rc
+
+
+def _pci_bus_id(index):
+    import torch
+    p = torch.cuda.get_device_properties(index)
+    if hasattr(p, 'pci_bus_id') and hasattr(p, 'pci_device_id'):
+        return '%04x:%02x:%02x.0' % (getattr(p, 'pci_domain_id', 0), p.pci_bus_id, p.pci_device_id)
+    out = subprocess.check_output(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', str(index)], timeout=20)
+    return out.decode().strip()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def reference_cli_anchor():
+    """BASELINE configs[0]: the unmodified reference CLI (staged copy baseline/_ref, oracle/Makefile `stage`) on
+    test/test_one_adapter_set.fastq, --threads 1: wall seconds (correctness anchor; 9 reads)."""
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    runner, fq = os.path.join(ref, 'porechop-runner.py'), os.path.join(ref, 'test', 'test_one_adapter_set.fastq')
+    if not (os.path.exists(runner) and os.path.exists(fq)):
+        return {'unavailable': 'baseline/_ref not staged (make -C oracle stage, authoring container)'}
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, 'out.fastq')
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            r = subprocess.run([sys.executable, runner, '-i', fq, '-o', out, '--threads', '1'], stdout=subprocess.DEVNULL,
+                               stderr=subprocess.DEVNULL, env=dict(os.environ, PYTHONWARNINGS='ignore'))
+            times.append(time.perf_counter() - t0)
+            if r.returncode != 0:
+                return {'unavailable': 'reference CLI exited %d' % r.returncode}
+        n_out = sum(1 for _ in open(out)) // 4
+    return {'workload': 'reference CLI, test/test_one_adapter_set.fastq, defaults, --threads 1', 'wall_s': min(times),
+            'reads_in': 9, 'reads_out': n_out, 'reads_per_s': 9 / min(times)}
+
+
+def run_reference(args):
+    if int(os.environ.get('RANK', '0')) != 0:
+        return 0
+    wl = _wl()
+    cores = host_cores()
+    harness, lib, kind = harness_paths()
+
+    def one(name, K, Wm, main):
+        # ~2 s of all-core work per step; the generators are prefix-consistent, so this is a prefix of the GPU arm's batch
+        per_read = {'endtrim': 7500.0, 'demux': 150.0 * 17975, 'middle': 8040.0 * 50, 'sweep': 8000.0 * 4608}[name]
+        limit = args.cpu_sample_reads or int(max(64, min(nominal_reads(name, args, main) or 1 << 30, 2.0 * 0.06e9 * cores / per_read)))
+        w = make_workload(name, args, 0, 1, main, limit=limit)
+        sizes = [len(off) - 1 for _, _, off, _ in w.batches]
+        files = HarnessFiles(w, sizes)
+        cells_per_read = w.cells / max(w.n, 1)
+        # mode: threads in one process vs one process per core (separate heaps), best of a warm-up pair
+        modes = [(cores, 1)] + ([(1, cores)] if cores >= 2 else [])
+        trial = {m: files.run(*m) for m in modes}
+        mode = min(trial, key=trial.get)
+        times = []
+        for s in range(Wm + K):
+            sec = files.run(*mode)
+            if s >= Wm:
+                times.append(sec)
+        t = float(np.mean(times))
+        value = files.cells / t / cells_per_read
+        nominal = make_nominal_config(name, args, main)
+        one_t = HarnessFiles(w, [max(1, k // max(cores // 2, 1)) for k in sizes])
+        sec1 = one_t.run(1)
+        return {'impl': 'reference', 'metric': 'reads/sec', 'value': value, 'unit': 'reads/s', 'n_gpus': args.gpus,
+                'steps': K, 'warmup': Wm, 'ms_per_step': t * 1e3, 'higher_is_better': True,
+                'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'int32', 'data': 'synthetic',
+                'gcups': files.cells / t / 1e9, 'config': nominal, 'cells_per_read': cells_per_read,
+                'cpu_baseline': {'value': value, 'unit': 'reads/s', 'cores': mode[0] * mode[1], 'kind': kind,
+                                 'mode': '%d threads x %d processes' % mode,
+                                 'trial_seconds': {'%dx%d' % m: v for m, v in trial.items()},
+                                 'one_thread': {'value': one_t.cells / sec1 / cells_per_read, 'unit': 'reads/s',
+                                                'gcups': one_t.cells / sec1 / 1e9},
+                                 'host': cpu_info(),
+                                 'sample': 'first %s reads of the batches per step (%d alignments), native harness over the '
+                                           'reference C-ABI' % (sizes, sum(k * len(b[3]) for k, b in zip(sizes, w.batches)))},
+                'e2e': {'value': value, 'unit': 'reads/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+    line = one(args.workload, args.steps, args.warmup, True)
+    others = [] if args.configs == 'none' else [c for c in (['demux', 'middle', 'sweep'] if args.configs == 'all' else args.configs.split(','))
+                                                 if c and c != args.workload]
+    line['configs'] = {}
+    for name in others:
+        try:
+            line['configs'][name] = one(name, 2, 1, False)
+        except Exception as e:
+            line['configs'][name] = {'error': repr(e)}
+    line['configs']['cli_anchor'] = reference_cli_anchor()
+    print(json.dumps(line))
     return 0
+
+
+def make_nominal_config(name, args, main):
+    """The `config` dict of Workload.config() without generating the batch (both arms must print identical dicts)."""
+    wl = _wl()
+    nom = nominal_reads(name, args, main)
+    if name == 'endtrim':
+        desc = '%d synthetic ~8kb reads (lognormal, seed %d+rank), SQK-NSK007 (LSK109 Y-adapter), end-trim: 150x28 + 150x22 per read' % (nom, wl.SEED)
+        apr = 2
+    elif name == 'demux':
+        desc = '%d synthetic reads x 356 adapter sequences (119 sets + 12 native-full + 96 rapid-full: 227 start + 129 end), demux end windows' % nom
+        apr = 356
+    elif name == 'sweep':
+        desc = 'read-length sweep %s x 192 forward barcode sequences (24 nt), %.1e bases per length, full-read scan' % (
+            args.sweep_lengths, args.sweep_bases)
+        apr = 192
+        nom = sum(max(1, int(args.sweep_bases // int(x))) for x in args.sweep_lengths.split(','))
+    else:
+        desc = '%d synthetic full reads (~8 kb lognormal, 5%% chimeras) x {Y_Top, Y_Bottom}, middle-adapter scan' % nom
+        apr = 2
+    return {'workload': desc, 'reads_per_gpu' if args.scaling == 'weak' else 'reads_total': nom,
+            'alignments_per_read': apr, 'scoring': list(wl.DEFAULT_SCORING), 'scaling': args.scaling}
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_b200(args)
 
 
 if __name__ == '__main__':

@@ -129,6 +129,11 @@ long long pb200KernelLaunches(void);      /* kernels launched by this library si
  * duration and launch count of the DP kernels (trace_kernel + score_kernel) since the last reset. */
 void pb200TimingEnable(int on);
 int pb200TimingRead(double *dp_kernel_ms, long long *dp_kernel_launches, double *cells, int reset);
+/* The same per kind of DP launch, arrays of PB200_TIMING_KINDS entries: 0 trace_kernel (windows, single pass),
+ * 1 trace_kernel score-only first pass, 2 trace_kernel on the bounded windows of a two-pass class, 3 score_kernel (long
+ * reads).  window_cells = DP cells computed by the launches of kind 2 (the other kinds sweep every cell of their batch). */
+#define PB200_TIMING_KINDS 4
+int pb200TimingReadKinds(double *ms, long long *launches, double *window_cells, int reset);
 /* Tunables (also read from the environment at first use, PB200_<NAME>):
  *   "direct_max"  longest sequence aligned in one pass (default 512; longer ones take score pass + bounded window)
  *   "chunk_tasks" alignments per pipeline chunk of the host-buffer API (default 131072)

@@ -82,6 +82,10 @@ void pbioFullScores(const int32_t *records, int64_t n, int64_t n_adapters, const
 int64_t pbioGzipBound(int64_t n, int64_t block);
 int64_t pbioGzip(const uint8_t *src, int64_t n, int level, int64_t block, uint8_t *dst, int64_t cap);
 
+/* bench / test workloads only: n iid uniform ACGT bytes, a pure function of (seed, n) for any number of threads
+ * (SURVEY 8(d) synthetic reads: the bodies; adapter copies are implanted by porechop_b200/workloads.py) */
+void pbioRandomBases(uint8_t *out, int64_t n, uint64_t seed);
+
 #ifdef __cplusplus
 }
 #endif

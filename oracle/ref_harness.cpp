@@ -7,6 +7,10 @@
 // SURVEY section 6, so the fair multi-core baseline is a native caller).
 //
 // usage: ref_harness <lib.so> <workload.bin> <threads> [answers.txt]
+//   env REF_HARNESS_PROCS=P (P > 1): P forked worker PROCESSES x <threads> threads each pull chunks from one shared
+//   counter -- every process has its own heap, which separates the machine's capacity from glibc-arena contention
+//   (the reference mallocs an (n+1)(m+1) trace matrix per call; round 1 saw 128 threads in one process run 6x slower on
+//   one host than on another).  Answers are only written in the single-process mode.
 //   workload.bin (little endian), written by porechop_b200.workloads.write_harness_file():
 //     int64 n_seqs, n_adapters, n_pairs ; int32 ma, mi, go, ge ; int32 cross, pad
 //     int64 seq_off[n_seqs+1] ; bytes seqs ; int32 ad_off[n_adapters+1] ; bytes adapters
@@ -14,6 +18,9 @@
 //   prints one JSON line: {"seconds":..,"pairs":..,"cells":..,"threads":..}
 //   with answers.txt: also writes one result string per pair (in pair order).
 #include <dlfcn.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
 #include <atomic>
 #include <chrono>
 #include <cstdint>
@@ -67,14 +74,20 @@ int main(int argc, char **argv)
     for (int64_t i = 0; i < n_ad; ++i) A[i].assign(ads.data() + ad_off[i], ad_off[i + 1] - ad_off[i]);
 
     bool want = argc > 4;
+    int procs = getenv("REF_HARNESS_PROCS") ? atoi(getenv("REF_HARNESS_PROCS")) : 1;
+    if (procs < 1 || want) procs = 1;
     std::vector<std::string> answers(want ? n_pairs : 0);
-    std::atomic<int64_t> next(0);
-    std::atomic<long long> cells(0);
+    // the work counter and the cell total live in a shared anonymous mapping so that forked workers can use them too
+    struct Shared { std::atomic<int64_t> next; std::atomic<long long> cells; };
+    Shared *sh = (Shared *)mmap(nullptr, sizeof(Shared), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (sh == MAP_FAILED) { perror("mmap"); return 2; }
+    new (&sh->next) std::atomic<int64_t>(0);
+    new (&sh->cells) std::atomic<long long>(0);
     auto worker = [&]() {
         long long my = 0;
         const int64_t CH = 64;
         for (;;) {
-            int64_t b = next.fetch_add(CH);
+            int64_t b = sh->next.fetch_add(CH);
             if (b >= n_pairs) break;
             int64_t e = b + CH < n_pairs ? b + CH : n_pairs;
             for (int64_t p = b; p < e; ++p) {
@@ -87,13 +100,27 @@ int main(int argc, char **argv)
                 my += (long long)S[s].size() * (long long)A[a].size();
             }
         }
-        cells += my;
+        sh->cells += my;
+    };
+    auto run_threads = [&]() {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+        worker();
+        for (auto &t : pool) t.join();
     };
     auto t0 = std::chrono::steady_clock::now();
-    std::vector<std::thread> pool;
-    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
-    worker();
-    for (auto &t : pool) t.join();
+    if (procs > 1) {
+        std::vector<pid_t> kids;
+        for (int k = 0; k < procs; ++k) {
+            pid_t pid = fork();
+            if (pid < 0) { perror("fork"); break; }
+            if (pid == 0) { run_threads(); _exit(0); }
+            kids.push_back(pid);
+        }
+        for (pid_t pid : kids) { int st = 0; waitpid(pid, &st, 0); }
+    } else {
+        run_threads();
+    }
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (want) {
         FILE *o = fopen(argv[4], "w");
@@ -101,7 +128,7 @@ int main(int argc, char **argv)
         for (auto &s : answers) fprintf(o, "%s\n", s.c_str());
         fclose(o);
     }
-    printf("{\"seconds\": %.6f, \"pairs\": %lld, \"cells\": %lld, \"threads\": %d}\n",
-           sec, (long long)n_pairs, (long long)cells.load(), threads);
+    printf("{\"seconds\": %.6f, \"pairs\": %lld, \"cells\": %lld, \"threads\": %d, \"procs\": %d}\n",
+           sec, (long long)n_pairs, (long long)sh->cells.load(), threads, procs);
     return 0;
 }

@@ -9,23 +9,7 @@ the percentage rounded to 6 decimals by printf and parsed back (SURVEY.md 7.4 "F
 """
 import numpy as np
 
-from .cpp_function_wrappers import adapter_alignment, SCORE_EMPTY
-
-
-def align_adapter(read_seq, adapter_seq, scoring_scheme_vals):
-    """Same contract as the reference function of the same name (nanopore_read.py:476-491)."""
-    alignment_result = adapter_alignment(read_seq, adapter_seq, scoring_scheme_vals)
-    result_parts = alignment_result.split(',')
-    read_start = int(result_parts[0])
-    if read_start == -1:
-        read_end = 0
-        aligned_region_percent_identity = 0.0
-        full_adapter_percent_identity = 0.0
-    else:
-        read_end = int(result_parts[1]) + 1
-        aligned_region_percent_identity = float(result_parts[5])
-        full_adapter_percent_identity = float(result_parts[6])
-    return full_adapter_percent_identity, aligned_region_percent_identity, read_start, read_end
+from .cpp_function_wrappers import SCORE_EMPTY
 
 
 def _percent_exact(count, length):

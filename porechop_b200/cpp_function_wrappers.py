@@ -74,6 +74,8 @@ C_LIB.pb200TimingEnable.argtypes = [c_int]
 C_LIB.pb200TimingEnable.restype = None
 C_LIB.pb200TimingRead.argtypes = [POINTER(c_double), POINTER(c_longlong), POINTER(c_double), c_int]
 C_LIB.pb200TimingRead.restype = c_int
+C_LIB.pb200TimingReadKinds.argtypes = [POINTER(c_double), POINTER(c_longlong), POINTER(c_double), c_int]
+C_LIB.pb200TimingReadKinds.restype = c_int
 C_LIB.pb200SetOption.argtypes = [c_char_p, c_char_p]
 C_LIB.pb200SetOption.restype = c_int
 C_LIB.pb200PackNibbles.argtypes = [c_void_p, c_int64, c_void_p, c_int]
@@ -82,7 +84,8 @@ C_LIB.pb200PackNibbles.restype = c_int
 EXPORTED_SYMBOLS = ['adapterAlignment', 'freeCString', 'adapterAlignmentBatch', 'adapterAlignmentBatchMulti',
                     'adapterAlignmentBatchDevice', 'adapterEndDecisions', 'pb200TrimThresholdTable',
                     'pb200FormatRecord', 'pb200DeviceCount', 'pb200SetDevice', 'pb200Synchronize', 'pb200LastError',
-                    'pb200KernelLaunches', 'pb200TimingEnable', 'pb200TimingRead', 'pb200SetOption', 'pb200PackNibbles']
+                    'pb200KernelLaunches', 'pb200TimingEnable', 'pb200TimingRead', 'pb200TimingReadKinds', 'pb200SetOption',
+                    'pb200PackNibbles']
 
 RECORD_INTS = 9
 SCORE_EMPTY = -2147483648
@@ -276,6 +279,22 @@ def timing_read(reset=True):
     ms, n, cells = c_double(0), c_longlong(0), c_double(0)
     _check(C_LIB.pb200TimingRead(ms, n, cells, 1 if reset else 0))
     return ms.value, n.value
+
+
+TIMING_KINDS = ('trace_kernel', 'trace_kernel<score-only>', 'trace_kernel<window pass>', 'score_kernel')
+
+
+def timing_read_kinds(reset=True):
+    """{kind: {'ms': total CUDA-event ms, 'n': launches[, 'cells': DP cells of the window pass]}} of the timed DP launches"""
+    ms, n, wc = (c_double * 4)(), (c_longlong * 4)(), c_double(0)
+    _check(C_LIB.pb200TimingReadKinds(ms, n, wc, 1 if reset else 0))
+    out = {}
+    for k, name in enumerate(TIMING_KINDS):
+        if n[k]:
+            out[name] = {'ms': ms[k], 'n': int(n[k])}
+            if k == 2:
+                out[name]['cells'] = wc.value
+    return out
 
 
 def pack_nibbles(ascii_buf, threads=0):

@@ -126,7 +126,9 @@ struct ClassPlan {
     int m_max = 0;
 };
 
-struct TimedLaunch { cudaEvent_t a, b; };
+// timed DP launches by kind (pb200TimingReadKinds): which kernel dominates a step, and its per-launch duration
+enum { TK_TRACE = 0, TK_TRACE_SCORE_ONLY = 1, TK_TRACE_WINDOW = 2, TK_SCORE = 3, TK_N = 4 };
+struct TimedLaunch { cudaEvent_t a, b; int kind; };
 
 struct Engine {
     int device = -1;
@@ -151,9 +153,10 @@ struct Engine {
     PlanEntry plans[4];
     unsigned long long plan_clock = 0;
     std::vector<TimedLaunch> timed;
-    double timed_cells = 0.0;
-    double timed_ms_acc = 0.0;
-    long long timed_n_acc = 0;
+    double timed_ms_acc[TK_N] = {0, 0, 0, 0};
+    long long timed_n_acc[TK_N] = {0, 0, 0, 0};
+    int next_trace_kind = TK_TRACE;      // set to TK_TRACE_WINDOW around the second-pass launch of a two-pass class
+    DevBuf wcells;                       // device counter: DP cells of the windowed second passes (window_tasks_kernel)
     bool init_done = false;
     int init() {
         if (init_done) return 0;
@@ -223,9 +226,9 @@ int class_of(const SchemeInfo &s, int m) {
 }
 
 // ---- kernel launch helpers -----------------------------------------------------------------------------
-void timed_begin(Engine &E, cudaStream_t s, TimedLaunch &tl, bool &on) {
+void timed_begin(Engine &E, cudaStream_t s, TimedLaunch &tl, bool &on, int kind) {
     on = g_timing.load() != 0;
-    if (on) { cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); cudaEventRecord(tl.a, s); }
+    if (on) { tl.kind = kind; cudaEventCreate(&tl.a); cudaEventCreate(&tl.b); cudaEventRecord(tl.a, s); }
 }
 void timed_end(Engine &E, cudaStream_t s, TimedLaunch &tl, bool on) {
     if (on) { cudaEventRecord(tl.b, s); E.timed.push_back(tl); }
@@ -269,7 +272,7 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc
         if (int rc = S.gtrace.ensure((size_t)blocks * wpb * gwarp_bytes)) return rc;
     }
     TimedLaunch tl; bool on;
-    timed_begin(E, stream, tl, on);
+    timed_begin(E, stream, tl, on, SO ? TK_TRACE_SCORE_ONLY : E.next_trace_kind);
     kern<<<(unsigned)blocks, wpb * 32, smem_bytes, stream>>>(ts, seq_codes, ad_codes, sc, out,
                                                               SO ? nullptr : S.gtrace.as<uint32_t>(), max_steps, max_n, status, ends);
     timed_end(E, stream, tl, on);
@@ -360,7 +363,7 @@ int launch_score_variant(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsi
     if (blocks <= 0) return 0;
     CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
     TimedLaunch tl; bool on;
-    timed_begin(E, stream, tl, on);
+    timed_begin(E, stream, tl, on, TK_SCORE);
     kern<<<(unsigned)blocks, PB_WARPS_PER_BLOCK * 32, 0, stream>>>(ts, counter, seq_codes, ad_codes, sc, ends);
     timed_end(E, stream, tl, on);
     g_launches++;
@@ -448,13 +451,21 @@ int run_class_tasks(Engine &E, Stage &S, cudaStream_t stream, int cls, int m_max
     }
     {
         int64_t blocks = (n_tasks + 255) / 256;
-        window_tasks_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ts, S.ends.as<EndCell>(), S.tasks2.as<Task>(), si.wnum, si.wden, g_opt.tight_window);
+        if (!E.wcells.p) {
+            if (int rc = E.wcells.ensure(8)) return rc;
+            CK(cudaMemsetAsync(E.wcells.p, 0, 8, stream));
+        }
+        window_tasks_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ts, S.ends.as<EndCell>(), S.tasks2.as<Task>(), si.wnum, si.wden, g_opt.tight_window,
+                                                                   E.wcells.as<unsigned long long>());
         g_launches++;
         CK(cudaGetLastError());
     }
     TaskSrc t2 = ts;
     t2.tasks = S.tasks2.as<Task>();
-    return launch_trace_class(E, S, stream, cls, t2, (int)W, seq_codes, ad_codes, sc, out, status);
+    E.next_trace_kind = TK_TRACE_WINDOW;
+    const int rc2 = launch_trace_class(E, S, stream, cls, t2, (int)W, seq_codes, ad_codes, sc, out, status);
+    E.next_trace_kind = TK_TRACE;
+    return rc2;
 }
 
 // Adapter-side planning shared by all entry points.
@@ -1188,7 +1199,7 @@ const char *pb200LastError(void) { return g_err.c_str(); }
 long long pb200KernelLaunches(void) { return g_launches.load(); }
 void pb200TimingEnable(int on) { g_timing.store(on ? 1 : 0); }
 
-int pb200TimingRead(double *ms, long long *launches, double *cells, int reset) {
+int pb200TimingReadKinds(double *ms, long long *launches, double *window_cells, int reset) {
     Engine *Ep = nullptr;
     if (int rc = get_engine(&Ep)) return rc;
     Engine &E = *Ep;
@@ -1196,15 +1207,33 @@ int pb200TimingRead(double *ms, long long *launches, double *cells, int reset) {
     for (auto &tl : E.timed) {
         float f = 0.f;
         if (cudaEventSynchronize(tl.b) == cudaSuccess && cudaEventElapsedTime(&f, tl.a, tl.b) == cudaSuccess) {
-            E.timed_ms_acc += f; E.timed_n_acc++;
+            E.timed_ms_acc[tl.kind] += f; E.timed_n_acc[tl.kind]++;
         }
         cudaEventDestroy(tl.a); cudaEventDestroy(tl.b);
     }
     E.timed.clear();
-    if (ms) *ms = E.timed_ms_acc;
-    if (launches) *launches = E.timed_n_acc;
-    if (cells) *cells = E.timed_cells;
-    if (reset) { E.timed_ms_acc = 0; E.timed_n_acc = 0; E.timed_cells = 0; }
+    for (int k = 0; k < TK_N; ++k) {
+        if (ms) ms[k] = E.timed_ms_acc[k];
+        if (launches) launches[k] = E.timed_n_acc[k];
+    }
+    unsigned long long wc = 0;
+    if (E.wcells.p) {
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpyAsync(&wc, E.wcells.p, 8, cudaMemcpyDeviceToHost, E.st[0].stream));
+        if (reset) CK(cudaMemsetAsync(E.wcells.p, 0, 8, E.st[0].stream));
+        CK(cudaStreamSynchronize(E.st[0].stream));
+    }
+    if (window_cells) *window_cells = (double)wc;
+    if (reset) for (int k = 0; k < TK_N; ++k) { E.timed_ms_acc[k] = 0; E.timed_n_acc[k] = 0; }
+    return 0;
+}
+
+int pb200TimingRead(double *ms, long long *launches, double *cells, int reset) {
+    double m[TK_N]; long long n[TK_N]; double wc = 0;
+    if (int rc = pb200TimingReadKinds(m, n, &wc, reset)) return rc;
+    if (ms) { *ms = 0; for (int k = 0; k < TK_N; ++k) *ms += m[k]; }
+    if (launches) { *launches = 0; for (int k = 0; k < TK_N; ++k) *launches += n[k]; }
+    if (cells) *cells = wc;
     return 0;
 }
 

@@ -28,9 +28,9 @@ int pbioSetThreads(int n)
 #endif
 }
 
-static inline int is_ws(uint8_t c)            /* what str.strip() removes from an ASCII line */
+static inline int is_ws(uint8_t c)            /* what str.strip() removes from an ASCII line: 9-13, 28-31 and the space */
 {
-    return c == ' ' || (c >= 9 && c <= 13);
+    return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 && c <= 31);
 }
 
 static int64_t count_nl(const uint8_t *p, int64_t n)
@@ -369,3 +369,35 @@ int64_t pbioGzip(const uint8_t *src, int64_t n, int level, int64_t block, uint8_
     return -1;                                          /* built without zlib: callers use Python's gzip */
 }
 #endif
+
+
+/* ---- synthetic workloads (bench.py / workloads.py): iid uniform ACGT, reproducible for any thread count -------------- */
+static inline uint64_t splitmix64(uint64_t *x)
+{
+    uint64_t z = (*x += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+void pbioRandomBases(uint8_t *out, int64_t n, uint64_t seed)
+{
+    static const uint8_t acgt[4] = {'A', 'C', 'G', 'T'};
+    if (n <= 0) return;
+    const int64_t blocks = (n + PBIO_BLOCK - 1) / PBIO_BLOCK;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t b = 0; b < blocks; ++b) {
+        /* one generator per 1 MiB block, keyed by (seed, block): the bytes do not depend on the thread count */
+        uint64_t st = seed * 0xD1342543DE82EF95ull + (uint64_t)b * 0x2545F4914F6CDD1Dull + 1;
+        int64_t lo = b * PBIO_BLOCK, hi = lo + PBIO_BLOCK < n ? lo + PBIO_BLOCK : n;
+        int64_t i = lo;
+        for (; i + 32 <= hi; i += 32) {
+            uint64_t r = splitmix64(&st);
+            for (int k = 0; k < 32; ++k) out[i + k] = acgt[(r >> (2 * k)) & 3];
+        }
+        if (i < hi) {
+            uint64_t r = splitmix64(&st);
+            for (int k = 0; i < hi; ++i, ++k) out[i] = acgt[(r >> (2 * k)) & 3];
+        }
+    }
+}

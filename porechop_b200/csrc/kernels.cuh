@@ -190,26 +190,31 @@ __device__ __forceinline__ Task get_task(const TaskSrc &ts, int64_t idx) {
 // left of its end (DESIGN.md "window bound").  wnum/wden: W = m + (m*wnum)/wden; `tight` = the per-alignment bound
 // of dp_core.cuh window_cols() that also uses the end cell's row and score.
 __global__ void window_tasks_kernel(const TaskSrc ts, const EndCell *__restrict__ ends, Task *__restrict__ out,
-                                    int wnum, int wden, int tight) {
+                                    int wnum, int wden, int tight, unsigned long long *__restrict__ window_cells) {
     const int64_t n_tasks = ts.n_tasks;
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_tasks) return;
-    Task t = get_task(ts, k);
-    EndCell e = ends[k];
-    if (t.n > 0 && t.m > 0) {
-        const int64_t W = window_cols(t.m, e.i, e.score, wnum, wden, tight != 0);
-        int64_t c0 = (int64_t)e.j - W;
-        if (c0 < 0) c0 = 0;
-        t.col0 = (int32_t)c0;
-        t.seq_off += c0;
-        t.n = e.j - (int32_t)c0;
-        t.flags = TASK_END_GIVEN | (c0 > 0 ? TASK_LEFT_INF : 0);
-        t.end_j = t.n; t.end_i = e.i; t.end_corr = e.corr; t.end_score = e.score;
-    } else {
-        // empty read or adapter: no columns to compute, the trace pass only emits the -1 record
-        t.n = 0; t.flags = TASK_END_GIVEN; t.end_j = 0; t.end_i = 0; t.end_corr = 0; t.end_score = PB_SCORE_EMPTY;
+    unsigned long long cells = 0;      // DP cells the second pass will compute (measurement only: pb200TimingReadKinds)
+    if (k < n_tasks) {
+        Task t = get_task(ts, k);
+        EndCell e = ends[k];
+        if (t.n > 0 && t.m > 0) {
+            const int64_t W = window_cols(t.m, e.i, e.score, wnum, wden, tight != 0);
+            int64_t c0 = (int64_t)e.j - W;
+            if (c0 < 0) c0 = 0;
+            t.col0 = (int32_t)c0;
+            t.seq_off += c0;
+            t.n = e.j - (int32_t)c0;
+            t.flags = TASK_END_GIVEN | (c0 > 0 ? TASK_LEFT_INF : 0);
+            t.end_j = t.n; t.end_i = e.i; t.end_corr = e.corr; t.end_score = e.score;
+            cells = (unsigned long long)t.n * (unsigned long long)t.m;
+        } else {
+            // empty read or adapter: no columns to compute, the trace pass only emits the -1 record
+            t.n = 0; t.flags = TASK_END_GIVEN; t.end_j = 0; t.end_i = 0; t.end_corr = 0; t.end_score = PB_SCORE_EMPTY;
+        }
+        out[k] = t;
     }
-    out[k] = t;
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+    if ((threadIdx.x & 31) == 0 && cells && window_cells) atomicAdd(window_cells, cells);
 }
 
 

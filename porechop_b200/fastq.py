@@ -39,7 +39,7 @@ from . import hostio
 from .align import scores_from_records
 
 _WS = np.zeros(256, dtype=bool)
-_WS[[9, 10, 11, 12, 13, 32]] = True            # what str.strip() removes from an ASCII line
+_WS[[9, 10, 11, 12, 13, 28, 29, 30, 31, 32]] = True            # what str.strip() removes from an ASCII line
 
 
 class FastqBatch:

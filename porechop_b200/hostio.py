@@ -4,13 +4,13 @@
 numpy implementations of the same functions (identical results, much slower on long reads).  This is host I/O only --
 the alignment engine itself has no fallback of any kind."""
 import os
-from ctypes import CDLL, c_double, c_int, c_int64, c_void_p
+from ctypes import CDLL, c_double, c_int, c_int64, c_uint64, c_void_p
 
 import numpy as np
 
 _PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libhostio.so')
 EXPORTED_SYMBOLS = ['pbioSetThreads', 'pbioCountLines', 'pbioLineEnds', 'pbioLineSpans', 'pbioFastqIndex', 'pbioGather', 'pbioNormalise', 'pbioEmit', 'pbioScores', 'pbioEndTrim',
-                    'pbioFullScores', 'pbioGzipBound', 'pbioGzip']
+                    'pbioFullScores', 'pbioGzipBound', 'pbioGzip', 'pbioRandomBases']
 
 
 def _load():
@@ -46,6 +46,8 @@ def _load():
     lib.pbioGzipBound.restype = c_int64
     lib.pbioGzip.argtypes = [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64]
     lib.pbioGzip.restype = c_int64
+    lib.pbioRandomBases.argtypes = [c_void_p, c_int64, c_uint64]
+    lib.pbioRandomBases.restype = None
     return lib
 
 
@@ -169,3 +171,30 @@ def gzip_members(payload, level=6, block=4 << 20):
 def set_threads(n=0):
     """set (n > 0) / query the number of worker threads of the C helpers; 1 when the library is absent."""
     return int(LIB.pbioSetThreads(int(n))) if LIB is not None else 1
+
+
+def random_bases(n, seed, out=None):
+    """n iid uniform ACGT bytes, a pure function of (seed, n) (pbioRandomBases: one generator per 1 MiB block, so the
+    bytes do not depend on the thread count); written into `out` (uint8, length >= n) when given.  Workload generator of
+    bench.py / workloads.py, not part of the alignment path."""
+    if out is None:
+        out = np.empty(n, dtype=np.uint8)
+    assert out.dtype == np.uint8 and out.flags.c_contiguous and len(out) >= n
+    if LIB is not None:
+        LIB.pbioRandomBases(_p(out), int(n), int(seed) & 0xFFFFFFFFFFFFFFFF)
+        return out[:n]
+    # numpy restatement of the same generator (splitmix64 per 1 MiB block, 32 bases per draw)
+    acgt = np.frombuffer(b'ACGT', dtype=np.uint8)
+    M = (1 << 64) - 1
+    blk = 1 << 20
+    for b in range((n + blk - 1) // blk):
+        lo, hi = b * blk, min(n, (b + 1) * blk)
+        draws = (hi - lo + 31) // 32
+        st = (int(seed) * 0xD1342543DE82EF95 + b * 0x2545F4914F6CDD1D + 1) & M
+        x = (np.uint64(st) + np.arange(1, draws + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+        z = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        codes = ((z[:, None] >> (np.arange(32, dtype=np.uint64) * np.uint64(2))) & np.uint64(3)).astype(np.uint8).reshape(-1)
+        out[lo:hi] = acgt[codes[:hi - lo]]
+    return out[:n]

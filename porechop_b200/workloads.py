@@ -165,25 +165,84 @@ def synth_reads(n_reads, start_adapter, end_adapter, seed=SEED, chimera_p=0.0, m
     return np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros(0, np.uint8), off
 
 
+def _scatter(buf, starts, mat, pick, lens):
+    """buf[starts[r] : starts[r] + lens[r]] = mat[pick[r], :lens[r]] for every r with lens[r] > 0 (vectorised)."""
+    rows = np.nonzero(lens > 0)[0]
+    if not len(rows):
+        return
+    l = lens[rows].astype(np.int64)
+    tot = int(l.sum())
+    first = np.cumsum(l) - l
+    within = np.arange(tot, dtype=np.int64) - np.repeat(first, l)
+    buf[np.repeat(starts[rows].astype(np.int64), l) + within] = mat[np.repeat(pick[rows], l), within]
+
+
+def synth_reads_fast(n_reads, start_adapter, end_adapter, seed=SEED, chimera_p=0.0, max_len=60000, out=None):
+    """Full synthetic reads of SURVEY 8(d) without a per-read Python loop (10^6+ reads): same length law, implant
+    probabilities, error channel (variant pools) and chimera rule as synth_reads.  Every per-read attribute has its own
+    generator keyed by (seed, attribute) and the bodies are pbioRandomBases(seed), so the first k reads (and their bytes)
+    are the same for every n_reads >= k -- the CPU reference arm times a prefix of exactly the batch the GPU arm aligns.
+    `out`: optional uint8 buffer (e.g. pinned memory) the bases are written into.  Returns (buffer, int64 offsets)."""
+    from . import hostio
+    g = lambda k: np.random.default_rng([int(seed), k])
+    n = int(n_reads)
+    Lb = np.minimum(read_lengths(g(0), n), max_len)
+    zero = np.zeros(n, dtype=np.int64)
+    if start_adapter:
+        smat, slen = _variant_pool(g(1), start_adapter, True)
+        pick_s = g(4).integers(0, POOL, n)
+        ls = np.where(g(3).random(n) < 0.8, slen[pick_s], 0)
+    else:
+        smat, slen, pick_s, ls = None, None, None, zero
+    if end_adapter:
+        emat, elen = _variant_pool(g(2), end_adapter, False)
+        pick_e = g(6).integers(0, POOL, n)
+        le = np.where(g(5).random(n) < 0.5, elen[pick_e], 0)
+    else:
+        emat, elen, pick_e, le = None, None, None, zero
+    lce = lcs = zero
+    if chimera_p and smat is not None and emat is not None:
+        chim = (g(7).random(n) < chimera_p) & (Lb > 2200)
+        pos = 1000 + np.floor(g(8).random(n) * np.maximum(Lb - 2000, 1)).astype(np.int64)
+        ke, ks = g(9).integers(0, POOL, n), g(10).integers(0, POOL, n)
+        lce, lcs = np.where(chim, elen[ke], 0), np.where(chim, slen[ks], 0)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(Lb + ls + le + lce + lcs, out=off[1:])
+    buf = hostio.random_bases(int(off[-1]), seed, out)
+    if smat is not None:
+        _scatter(buf, off[:-1], smat, pick_s, ls)
+    if lce is not zero:
+        _scatter(buf, off[:-1] + ls + pos, emat, ke, lce)
+        _scatter(buf, off[:-1] + ls + pos + lce, smat, ks, lcs)
+    if emat is not None:
+        _scatter(buf, off[1:] - le, emat, pick_e, le)
+    return buf, off
+
+
 def forward_barcode_sequences():
     """Config 5: the 192 sequences (24 nt each) of the 96 forward barcode sets, start sequences then end sequences."""
     sets = [s for s in load_adapter_sets()['sets'] if s['name'].endswith('(forward)')]
     return [s['start'][1] for s in sets] + [s['end'][1] for s in sets]
 
 
-def synth_fixed_length_reads(n_reads, length, barcodes, seed=SEED):
+def synth_fixed_length_reads(n_reads, length, barcodes, seed=SEED, out=None):
     """BASELINE config 5 (read-length sweep): n_reads reads of exactly `length` bases, iid ACGT, each with one randomly
-    chosen barcode sequence written over a random position (so every read has a real hit somewhere)."""
-    rng = np.random.default_rng(seed)
-    buf = _ACGT[rng.integers(0, 4, size=n_reads * length, dtype=np.uint8)]
-    bc = [np.frombuffer(b.encode(), dtype=np.uint8) for b in barcodes]
-    which = rng.integers(0, len(bc), n_reads)
-    for r in range(n_reads):
-        b = bc[int(which[r])]
-        if length >= len(b):
-            p = int(rng.integers(0, length - len(b) + 1))
-            buf[r * length + p: r * length + p + len(b)] = b
-    return np.ascontiguousarray(buf), np.arange(n_reads + 1, dtype=np.int64) * length
+    chosen barcode sequence written over a random position (so every read has a real hit somewhere).  Vectorised;
+    prefix-consistent in n_reads like synth_reads_fast."""
+    from . import hostio
+    n, length = int(n_reads), int(length)
+    buf = hostio.random_bases(n * length, int(seed), out)
+    w = max(len(b) for b in barcodes)
+    mat = np.zeros((len(barcodes), w), dtype=np.uint8)
+    blen = np.zeros(len(barcodes), dtype=np.int64)
+    for k, b in enumerate(barcodes):
+        mat[k, :len(b)] = np.frombuffer(b.encode(), dtype=np.uint8)
+        blen[k] = len(b)
+    which = np.random.default_rng([int(seed), 1]).integers(0, len(barcodes), n)
+    l = np.where(blen[which] <= length, blen[which], 0)
+    p = np.floor(np.random.default_rng([int(seed), 2]).random(n) * (length - l + 1)).astype(np.int64)
+    _scatter(buf, np.arange(n, dtype=np.int64) * length + p, mat, which, l)
+    return buf, np.arange(n + 1, dtype=np.int64) * length
 
 
 def windows_to_batch(windows):
