@@ -309,13 +309,19 @@ def cpu_baseline(workload, sample_reads=0, sweep=True, seconds=3.0, want_answers
     cells_per_read = workload.cells / max(workload.n, 1)
     answers = [] if want_answers else None
     runs = []
-    sec = files.run(cores, 1, answers)
-    runs.append({'threads': cores, 'procs': 1, 'seconds': sec})
+    if sweep or cores < 2:
+        sec = files.run(cores, 1, answers)
+        runs.append({'threads': cores, 'procs': 1, 'seconds': sec})
     if sweep and cores >= 4:
         for t in sorted({max(1, cores // 4), max(1, cores // 2)}):
             runs.append({'threads': t, 'procs': 1, 'seconds': files.run(t)})
     if cores >= 2:
+        # one process per core (separate heaps): the mode that does not depend on the allocator's arena behaviour; the side
+        # configs time only this one (and take the parity answers from a small threaded run)
         runs.append({'threads': 1, 'procs': cores, 'seconds': files.run(1, cores)})
+        if not sweep and want_answers:
+            small = HarnessFiles(workload, [min(k, 512) for k in sizes])
+            small.run(min(cores, 16), 1, answers)
     for r in runs:
         r['gcups'] = files.cells / r['seconds'] / 1e9
         r['reads_per_s'] = files.cells / r['seconds'] / cells_per_read
@@ -601,10 +607,12 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     from porechop_b200 import distributed as D
     numa = None
+    all_cpus = os.sched_getaffinity(0)
     try:
         numa = D.bind_host_to_gpu(_pci_bus_id(local_rank), int(os.environ.get('LOCAL_WORLD_SIZE', world)), local_rank)
     except Exception:
         numa = None
+    gpu_cpus = os.sched_getaffinity(0)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     from porechop_b200 import cpp_function_wrappers as W
@@ -626,7 +634,12 @@ def run_b200(args):
         line, res = measure_gpu(w, args, ctx, K, Wm, main)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             try:
-                cb, answers, sizes = cpu_baseline(w, args.cpu_sample_reads if main else 0, sweep=main)
+                os.sched_setaffinity(0, all_cpus)          # the CPU baseline runs on ALL host cores, not the GPU's NUMA node
+                try:
+                    cb, answers, sizes = cpu_baseline(w, args.cpu_sample_reads if main else 0, sweep=main,
+                                                      seconds=3.0 if main else 2.0)
+                finally:
+                    os.sched_setaffinity(0, gpu_cpus)
                 line['cpu_baseline'] = cb
                 # parity gate: the records the timed e2e steps left in the first output chunk vs the reference's strings
                 recs = [h[5].numpy() for h in res['host']]

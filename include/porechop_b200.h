@@ -130,26 +130,23 @@ long long pb200KernelLaunches(void);      /* kernels launched by this library si
 void pb200TimingEnable(int on);
 int pb200TimingRead(double *dp_kernel_ms, long long *dp_kernel_launches, double *cells, int reset);
 /* The same per kind of DP launch, arrays of PB200_TIMING_KINDS entries: 0 trace_kernel (windows, single pass),
- * 1 trace_kernel score-only first pass, 2 trace_kernel on the bounded windows of a two-pass class, 3 score_kernel (long
- * reads).  window_cells = DP cells computed by the launches of kind 2 (the other kinds sweep every cell of their batch). */
+ * 1 unused, 2 trace_kernel on the bounded windows of a two-pass class, 3 score_kernel (long reads).
+ * window_cells = DP cells computed by the launches of kind 2 (the other kinds sweep every cell of their batch). */
 #define PB200_TIMING_KINDS 4
 int pb200TimingReadKinds(double *ms, long long *launches, double *window_cells, int reset);
-/* Tunables (also read from the environment at first use, PB200_<NAME>):
+/* Tunables (also read from the environment at first use, PB200_<NAME>); none of them changes a result:
  *   "direct_max"  longest sequence aligned in one pass (default 512; longer ones take score pass + bounded window)
  *   "chunk_tasks" alignments per pipeline chunk of the host-buffer API (default 131072)
  *   "scratch_mb"  cap on the resident trace scratch in MB (default 128; 72 keeps it L2-resident)
  *   "hbuf"        staging of a slot's packed bases: "auto" | "smem" | "global"
- *   "rowoff"      1 = score pass in the row-offset arithmetic domain when it fits (default 0; same results)
- *   "h2d_pack"    1 = adapterAlignmentBatch converts the sequences to 4-bit codes on the host cores and uploads half
- *                 the bytes (default 0; same results; "pack_threads" = host threads of the packer, default = hardware threads /
- *                 LOCAL_WORLD_SIZE, at most 32)
- *   "profile"     1 = query profiles in shared memory instead of computing the substitution score per cell (cross-product
- *                 mode only): a table per block for classes with one or two adapters, a table per lane group for larger
- *                 classes, and in the long-read score pass (default 0; same results)
- *   "short2p"     1 = sequences up to direct_max also take two passes: a score-only sweep of the same slot loop finds
- *                 the end cells, then only the bounded window left of each end cell is traced (default 0; same results)
- *   "tight_window" 1 = second-pass windows sized per alignment from the end cell's row and score instead of the
- *                 per-adapter worst case (default 0; same results, fewer traced columns) */
+ *   "h2d_pack"    1 = the host-buffer calls convert the sequences to 4-bit codes on the host cores (a packer thread that
+ *                 runs ahead of the submit loop) and upload half the bytes; "pack_threads" = host threads of the packer
+ *                 (default = hardware threads / LOCAL_WORLD_SIZE, at most 32)
+ *   "profile"     1 (default) = the long-read score pass fetches its substitution operands from a query profile in shared
+ *                 memory when every slot is one read x two adapters (cross-product mode); 0 = always computed
+ *   "tight_window" 1 (default) = second-pass windows sized per alignment from the end cell's row and score; 0 = the
+ *                 per-adapter worst case
+ * (round 2 measured and removed "short2p", "rowoff" and the trace-kernel profiles: profiles/r2_options) */
 int pb200SetOption(const char *name, const char *value);
 
 enum {

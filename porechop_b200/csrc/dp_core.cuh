@@ -145,32 +145,21 @@ struct Scoring {
     int32_t goEff;    // go (linear: ge)
     int32_t linear;   // go == ge : NW recurrence of dp_formula_linear.h, no end-cell correction
     int32_t ma, mi, go, ge;
-    // Row-offset domain of the score pass (ROWOFF): row q of a group carries the extra offset coff*q, chosen so that the
-    // substitution operand (sub - go + coff) is never negative: the diagonal add becomes a plain 32-bit add (FMA pipe)
-    // instead of a packed ALU add.  coff == 0 in the classic domain.
-    int32_t coff;
-    uint32_t c2;      // packed coff
 };
 
-PB_HD int rowoff_c(int mi, int go, int ge) {      // smallest offset step that makes (mismatch - go + c) non-negative
-    const int goE = (go == ge) ? ge : go;
-    return (goE - mi) > 0 ? (goE - mi) : 0;
-}
-PB_HD Scoring make_scoring(int ma, int mi, int go, int ge, bool rowoff = false) {
+PB_HD Scoring make_scoring(int ma, int mi, int go, int ge) {
     Scoring s;
     s.linear = (go == ge) ? 1 : 0;
     s.ma = ma; s.mi = mi; s.go = go; s.ge = ge;
     const int goE = s.linear ? ge : go;
     const int geE = s.linear ? -PB_LINEAR_EXT : ge;
-    const int c = rowoff ? rowoff_c(mi, go, ge) : 0;
-    s.coff = c; s.c2 = pack2(c, c);
     s.goEff = goE;
     s.goMag2 = pack2(-goE, -goE);
     s.geMag2 = pack2(-geE, -geE);
     s.ge2 = pack2(geE, geE);
-    s.subA2 = pack2(ma + 1 - goE + c, ma + 1 - goE + c);
-    s.subF2 = pack2(mi - goE + c, mi - goE + c);
-    s.padF2 = pack2(-goE + c, -goE + c);
+    s.subA2 = pack2(ma + 1 - goE, ma + 1 - goE);
+    s.subF2 = pack2(mi - goE, mi - goE);
+    s.padF2 = pack2(-goE, -goE);
     s.borderX2 = pack2(PB_BIAS + goE, PB_BIAS + goE);
     s.negb2 = pack2(PB_BIAS + PB_NEG16, PB_BIAS + PB_NEG16);
     return s;
@@ -232,7 +221,6 @@ struct Lane {
     uint32_t Hs[R];   // Hs[j-1][row] (biased)
     uint32_t v2[R];   // adapter code << PB_CODE_SHIFT of the owned rows, packed halves
     uint32_t sf2[R];  // per-row mismatch operand (real rows: mi - go, pad rows: -go)
-    int offBase;         // row-offset domain: offset of the row above this lane's top row (coff * g * R); 0 classic
     uint32_t prevRecvX;  // X[j-1][top-1]  (diagonal input of the top row)
     uint32_t botX, botV; // X[j][bottom], Vs[j][bottom] -> shuffled to the next lane
     // scout state: last-row running best (X domain), packed (meaningful in lane G-1 only) ...
@@ -260,23 +248,13 @@ PB_HD uint32_t subm2(uint32_t x, uint32_t P) {
     return x - P;
 }
 
-// x + P per half where both are non-negative and no half overflows 15 bits: one plain 32-bit addition
-PB_HD uint32_t addp2(uint32_t x, uint32_t P) {
-#if !defined(__CUDA_ARCH__) && defined(PB_CHECK_RANGES)
-    if (((x & 0xFFFFu) + (P & 0xFFFFu)) > 0x7FFFu || ((x >> 16) + (P >> 16)) > 0x7FFFu) pb_range_violation();
-#endif
-    return x + P;
-}
-
 template <int R>
 PB_HD void lane_init(Lane<R> &L, int g, int G, const Scoring &sc, const uint8_t *adA, int mA, bool leftInfA,
                      const uint8_t *adB, int mB, bool leftInfB) {
     const int padA = G * R - mA, padB = G * R - mB;
-    // column 0: X = S0 + go + bias with S0 = 0 (border / pad rows) or -inf (real rows of a windowed task); in the
-    // row-offset domain every value of group row q additionally carries coff*q
+    // column 0: X = S0 + go + bias with S0 = 0 (border / pad rows) or -inf (real rows of a windowed task)
     const uint32_t x0 = sc.borderX2;
     const uint32_t xinf = add2(sc.negb2, pack2(sc.goEff, sc.goEff));
-    L.offBase = sc.coff * g * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int q = g * R + r + 1;
@@ -284,20 +262,18 @@ PB_HD void lane_init(Lane<R> &L, int g, int G, const Scoring &sc, const uint8_t 
         const bool realA = iA >= 1, realB = iB >= 1;
         const uint32_t a = realA ? (uint32_t)adA[iA - 1] : (uint32_t)PB_PAD_V;
         const uint32_t b = realB ? (uint32_t)adB[iB - 1] : (uint32_t)PB_PAD_V;
-        const uint32_t oq = pack2(sc.coff * q, sc.coff * q);
         L.v2[r] = (a << 8) | (b << 24);               // code<<4 in a byte -> code<<12 in the half
         L.sf2[r] = ((realA ? sc.subF2 : sc.padF2) & 0xFFFFu) | ((realB ? sc.subF2 : sc.padF2) & 0xFFFF0000u);
-        L.X[r] = add2((((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u), oq);
-        L.Hs[r] = add2(sc.negb2, oq);
+        L.X[r] = (((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u);
+        L.Hs[r] = sc.negb2;
     }
     {   // X[0][row above this lane's top row]
         const int q = g * R;
         const bool realA = (q - padA) >= 1, realB = (q - padB) >= 1;
-        L.prevRecvX = add2((((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u),
-                           pack2(sc.coff * q, sc.coff * q));
+        L.prevRecvX = (((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u);
     }
-    L.botX = L.X[R - 1]; L.botV = add2(sc.negb2, pack2(sc.coff * (g * R + R), sc.coff * (g * R + R)));
-    L.lrBest2 = add2(sc.borderX2, pack2(sc.coff * (g * R + R), sc.coff * (g * R + R)));   // candidate (0, m): S = 0
+    L.botX = L.X[R - 1]; L.botV = sc.negb2;
+    L.lrBest2 = sc.borderX2;   // candidate (0, m): S = 0
     for (int h = 0; h < 2; ++h) {
         L.lrJ[h] = 0; L.lrCorr[h] = 0;
         L.fcBest[h] = -1; L.fcI[h] = 0; L.fcCorr[h] = 0;   // biased X values are >= 0
@@ -336,14 +312,12 @@ PB_HD uint32_t max2acc(uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, ui
 #endif
 }
 
-// Query profile (option "profile").  The substitution operand of group row q depends only on the read bases of the two
-// halves -- six possible codes each (0..4 and the read padding code 5).  When the adapters of the two halves are the same for
-// every slot a kernel sees, the kernels keep those words in shared memory and fetch a column's R operands with two 128-bit
-// loads instead of computing them with LOP3 + VIADDMNMX per row:
-//   score_kernel<.., PROF>   per group, both halves read the same sequence (one read, two adapters): indexed by one base
-//   trace_kernel<.., PPROF>  per block, launch-uniform adapter pair (a class with one or two adapters): indexed by the
-//                            pair (base of half A, base of half B)
-// The word is produced by the very expression lane_step uses, so both paths are identical by construction.
+// Query profile of the score pass (option "profile", default on).  The substitution operand of group row q depends only
+// on the read base -- six possible codes (0..4 and the read padding code 5).  When both halves of a slot read the same
+// sequence (cross mode: one read, two adapters), score_kernel<.., PROF> keeps those words per lane group in shared memory
+// and fetches a column's R operands with two 128-bit loads instead of computing them with LOP3 + VIADDMNMX per row
+// (measured on B200: 15.8 -> 14.6 ms per launch of the middle scan).  The word is produced by the very expression
+// lane_step uses, so both paths are identical by construction.
 // the two base-independent operands of a group row (adapter codes and mismatch operands, as lane_init sets them up) ...
 PB_HD void profile_row(int q, const Scoring &sc, const uint8_t *adA, int mA, int padA, const uint8_t *adB, int mB, int padB,
                        uint32_t &v2, uint32_t &sf2) {
@@ -354,20 +328,17 @@ PB_HD void profile_row(int q, const Scoring &sc, const uint8_t *adA, int mA, int
     v2 = (a << 8) | (b << 24);
     sf2 = ((realA ? sc.subF2 : sc.padF2) & 0xFFFFu) | ((realB ? sc.subF2 : sc.padF2) & 0xFFFF0000u);
 }
-// ... and the operand for one pair of read base codes: exactly lane_step's expression
-PB_HD uint32_t profile_from(uint32_t v2, uint32_t sf2, uint32_t bcodeA, uint32_t bcodeB, const Scoring &sc) {
-    const uint32_t h2 = (((bcodeA & 7u) << 4) << 8) | (((bcodeB & 7u) << 4) << 24);      // encoded bytes (code << 4) per half
+// ... and the operand for a read base code (both halves): exactly lane_step's expression
+PB_HD uint32_t profile_from(uint32_t v2, uint32_t sf2, uint32_t bcode, const Scoring &sc) {
+    const uint32_t e = (bcode & 7u) << 4;                         // encoded byte (code << 4)
+    const uint32_t h2 = (e << 8) | (e << 24);
     return addmax2(xnor2(h2, v2), sc.subA2, sf2);
-}
-PB_HD uint32_t profile_word2(int q, uint32_t bcodeA, uint32_t bcodeB, const Scoring &sc, const uint8_t *adA, int mA, int padA,
-                             const uint8_t *adB, int mB, int padB) {
-    uint32_t v2, sf2;
-    profile_row(q, sc, adA, mA, padA, adB, mB, padB, v2, sf2);
-    return profile_from(v2, sf2, bcodeA, bcodeB, sc);
 }
 PB_HD uint32_t profile_word(int q, uint32_t bcode, const Scoring &sc, const uint8_t *adA, int mA, int padA, const uint8_t *adB,
                             int mB, int padB) {
-    return profile_word2(q, bcode, bcode, sc, adA, mA, padA, adB, mB, padB);
+    uint32_t v2, sf2;
+    profile_row(q, sc, adA, mA, padA, adB, mB, padB, v2, sf2);
+    return profile_from(v2, sf2, bcode, sc);
 }
 
 // R <= 4: one word per step (half A in bits 0..15, half B in bits 16..31); R = 5..8: word 0 = half A, word 1 = half B.
@@ -395,7 +366,7 @@ template <int R> PB_HD int trace_shift(int h, int r) { return (R <= 4) ? (4 * r 
 #endif
 //   PROF / subs : the R substitution operands of this column are given (query profile, see profile_word) instead of being
 //                 computed from h2 -- two ALU-pipe instructions per row less; only when both halves read the same base
-template <int R, bool TRACE, bool KEEPV = false, bool ROWOFF = false, bool PROF = false>
+template <int R, bool TRACE, bool KEEPV = false, bool PROF = false>
 PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, const Scoring &sc, uint32_t *tw,
                      uint32_t *vr = nullptr, const uint32_t *subs = nullptr) {
     uint32_t diagX = L.prevRecvX, upX = recvX, upV = recvV;
@@ -404,8 +375,7 @@ PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, co
     for (int r = 0; r < R; ++r) {
         // substitution (minus go) per half: codes equal -> ~(h^v) == -1 -> max(-1 + ma + 1 - go, mi - go) = ma - go
         const uint32_t sub = PROF ? subs[r] : addmax2(xnor2(h2, L.v2[r]), sc.subA2, L.sf2[r]);
-        // S_diag + sub (biased).  ROWOFF: sub >= 0 by construction -> plain 32-bit add on the FMA pipe
-        const uint32_t d = ROWOFF ? addp2(diagX, sub) : add2(diagX, sub);
+        const uint32_t d = add2(diagX, sub);                        // S_diag + sub (biased)
         uint32_t hs, vs, s;
         if (TRACE) {
             const uint32_t bl = 1u << trace_shift<R>(0, r);
@@ -417,7 +387,6 @@ PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, co
         } else {
             hs = addmax2(L.Hs[r], sc.ge2, L.X[r]);
             vs = addmax2(upV, sc.ge2, upX);
-            if (ROWOFF) vs = addp2(vs, sc.c2);                     // row above -> this row's offset domain
             s = max3(d, vs, hs);
         }
         diagX = L.X[r];
@@ -473,11 +442,10 @@ PB_HD void lane_track_general(Lane<R> &L, int g, int j, const HalfGeom &A, const
             for (int r = 0; r < R; ++r) {
                 const int i = g * R + r + 1 - H.pad;
                 if (i >= 1) {
-                    const int co = half16(L.X[r], h);                       // row-offset domain value
-                    const int c = co - (L.offBase + sc.coff * (r + 1));     // comparable across rows
+                    const int c = half16(L.X[r], h);
                     if (c > L.fcBest[h]) {
                         L.fcBest[h] = c; L.fcI[h] = i;
-                        L.fcCorr[h] = corr_flags(co, half16(vr[r], h), half16(L.Hs[r], h), sc.goEff);
+                        L.fcCorr[h] = corr_flags(c, half16(vr[r], h), half16(L.Hs[r], h), sc.goEff);
                     }
                 }
             }
@@ -493,7 +461,7 @@ PB_HD ScoutCand make_cand(const Lane<R> &L, int h, const Scoring &sc) {
     ScoutCand c;
     c.fcBest = L.fcBest[h] < 0 ? -0x40000000 : L.fcBest[h] - PB_BIAS - sc.goEff;
     c.fcI = L.fcI[h]; c.fcCorr = L.fcCorr[h];
-    c.lrBest = half16(L.lrBest2, h) - PB_BIAS - sc.goEff - (L.offBase + sc.coff * R); c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
+    c.lrBest = half16(L.lrBest2, h) - PB_BIAS - sc.goEff; c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
     return c;
 }
 PB_HD EndCell scout_combine(const ScoutCand *c, int G, const HalfGeom &H) {
@@ -539,11 +507,9 @@ PB_HD int traceback_stats(NibFn nib, EqFn eq, const EndCell &end, bool linear, i
     } else {
         dir = 0;
     }
-#ifdef PB_TRACEBACK_V2
-    // Experimental formulation (compile with -DPB_TRACEBACK_V2; same path, same statistics): ONE path step per loop
-    // iteration with the step kind as data instead of three code paths with inner gap-run loops -- the 16 lanes of a warp
-    // that trace at the same time then run the same instruction stream instead of serialising diagonal / vertical /
-    // horizontal branches and waiting for each other's gap runs.
+    // ONE path step per loop iteration with the step kind as data (no per-direction code paths, no inner gap-run loops):
+    // the lanes of a warp that trace at the same time run the same instruction stream instead of serialising diagonal /
+    // vertical / horizontal branches and waiting for each other's gap runs (measured on B200: trace launch 2.36 -> 2.25 ms).
     while (j > 0 && i > 0) {
         const bool isD = dir == 0, isV = dir == 1;
         const bool consR = !isV, consA = dir != 2;          // the step consumes a read base / an adapter base
@@ -566,42 +532,6 @@ PB_HD int traceback_stats(NibFn nib, EqFn eq, const EndCell &end, bool linear, i
             if (!ext) dir = (b & 1u) ? 0 : ((b & 2u) ? 1 : 2);
         }
     }
-#else
-    while (j > 0 && i > 0) {
-        if (dir == 0) {
-            if (eq(j, i)) ++matches;
-            if (!haveR) { haveR = true; lastR_k = L; lastR_i = i; lastR_uA = 1; }
-            firstR_k = L; firstR_i = i; firstR_uA = 1;
-            if (!haveA) { haveA = true; lastA_k = L; lastA_j = j; lastA_uR = 1; }
-            firstA_k = L; firstA_j = j; firstA_uR = 1;
-            ++L; --j; --i;
-        } else if (dir == 1) {
-            // vertical run: follow while the current cell says "extended" (dp_traceback_impl.h:225-295)
-            bool ext;
-            do {
-                ext = (b & 4u) && (i != 1) && !linear;
-                if (!haveA) { haveA = true; lastA_k = L; lastA_j = j; lastA_uR = 0; }
-                firstA_k = L; firstA_j = j; firstA_uR = 0;
-                ++L; --i;
-                if (i > 0) b = nib(j, i);
-            } while (ext);
-        } else {
-            bool ext;
-            do {
-                ext = (b & 8u) && (j != 1) && !linear;
-                if (!haveR) { haveR = true; lastR_k = L; lastR_i = i; lastR_uA = 0; }
-                firstR_k = L; firstR_i = i; firstR_uA = 0;
-                ++L; --j;
-                if (j > 0) b = nib(j, i);
-            } while (ext);
-        }
-        if (j > 0 && i > 0) {
-            // after a diagonal step the new cell's flags were not loaded yet
-            if (dir == 0) b = nib(j, i);
-            dir = (b & 1u) ? 0 : ((b & 2u) ? 1 : 2);
-        }
-    }
-#endif
     int status = (j == 0 && i > 0 && col0 > 0) ? 1 : 0;
 
     // whole alignment = [H x a][V x bb] . path . [H x c][V x e]   (dp_traceback_impl.h:532-554)

@@ -13,7 +13,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -79,11 +81,9 @@ struct Options {
     int64_t chunk_tasks = 1 << 17; // alignments per pipeline chunk (host-buffer API)
     int64_t device_chunk_tasks = 8 << 20; // alignments per launch group (device-resident API)
     int64_t chunk_bytes = 64ll << 20;   // sequence bytes per pipeline chunk (host-buffer API)
-    int rowoff = 0;                // 1: score pass in the row-offset domain when it fits (measured: no gain)
     int scratch_mb = 128;          // cap on the resident trace scratch (MB); 72 keeps it L2-resident at ~10% lower speed
-    int profile = 0;               // 1: score pass fetches the substitution operands from a shared-memory query profile (same-read slots)
-    int short2p = 0;               // 1: short sequences (<= direct_max) also go score pass -> bounded window (score-only trace_kernel)
-    int tight_window = 0;          // 1: second-pass windows sized per alignment from the end cell's row and score (window_cols)
+    int profile = 1;               // 1: score pass fetches the substitution operands from a shared-memory query profile (same-read slots)
+    int tight_window = 1;          // 1: second-pass windows sized per alignment from the end cell's row and score (window_cols)
     int h2d_pack = 0;              // 1: host-buffer API converts to 4-bit codes on the host cores and uploads half the bytes
     int pack_threads = 0;          // host threads of the packer (default: hardware threads / ranks on the node, at most 32)
     int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
@@ -95,10 +95,8 @@ void load_env_options() {
         if (const char *v = getenv("PB200_DIRECT_MAX")) g_opt.direct_max = atoll(v);
         if (const char *v = getenv("PB200_CHUNK_TASKS")) g_opt.chunk_tasks = std::max(1ll, atoll(v));
         if (const char *v = getenv("PB200_SCRATCH_MB")) g_opt.scratch_mb = std::max(1, atoi(v));
-        if (const char *v = getenv("PB200_ROWOFF")) g_opt.rowoff = atoi(v);
         if (const char *v = getenv("PB200_TIGHT_WINDOW")) g_opt.tight_window = atoi(v);
         if (const char *v = getenv("PB200_H2D_PACK")) g_opt.h2d_pack = atoi(v);
-        if (const char *v = getenv("PB200_SHORT2P")) g_opt.short2p = atoi(v);
         if (const char *v = getenv("PB200_PROFILE")) g_opt.profile = atoi(v);
         if (const char *v = getenv("PB200_PACK_THREADS")) g_opt.pack_threads = atoi(v);
         if (g_opt.pack_threads <= 0) {
@@ -116,7 +114,6 @@ constexpr int NSTAGE = 3;
 struct Stage {
     cudaStream_t stream = nullptr;
     DevBuf seq_raw, seq_codes, seq_off, tasks, tasks2, ends, out, order, bins, pair_seq, pair_ad, gtrace, misc;
-    HostBuf h_pack;                // pinned staging of the packed upload path
     DevBuf dec_trim, dec_pairs;    // per-chunk outputs of decide_kernel
 };
 
@@ -157,6 +154,7 @@ struct Engine {
     long long timed_n_acc[TK_N] = {0, 0, 0, 0};
     int next_trace_kind = TK_TRACE;      // set to TK_TRACE_WINDOW around the second-pass launch of a two-pass class
     DevBuf wcells;                       // device counter: DP cells of the windowed second passes (window_tasks_kernel)
+    std::shared_ptr<void> packer;        // Packer (below): the thread that plans and packs chunks ahead of the submit loop
     bool init_done = false;
     int init() {
         if (init_done) return 0;
@@ -234,24 +232,31 @@ void timed_end(Engine &E, cudaStream_t s, TimedLaunch &tl, bool on) {
     if (on) { cudaEventRecord(tl.b, s); E.timed.push_back(tl); }
 }
 
-template <int G, int R, bool HS, bool SO = false, int PM = 0>
+template <int G, int R, bool HS>
 int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, int max_n,
-                         const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status,
-                         EndCell *ends = nullptr) {
+                         const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
     constexpr int SPW = 32 / G;
     constexpr int WPS = TraceWords<R>::value;
     const int max_steps = max_n + G - 1;
     const int wpb = PB_WARPS_PER_BLOCK;
-    const size_t hb_words = HS ? (PM == 2 ? (((size_t)SPW * max_n + 3) & ~(size_t)3) : (size_t)SPW * max_n) : 0;
-    const size_t smem_bytes = (size_t)wpb * (hb_words + PB_SCRATCH_WORDS + (PM == 2 ? PB_GPROF_WORDS : 0)) * 4;
-    auto kern = trace_kernel<G, R, HS, SO, PM>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    const size_t hb_words = HS ? (size_t)SPW * max_n : 0;
+    const size_t smem_bytes = (size_t)wpb * (hb_words + PB_SCRATCH_WORDS) * 4;
+    auto kern = trace_kernel<G, R, HS>;
+    // per-kernel launch constants (attribute + occupancy) are queried once per (kernel, shared-memory size)
+    static thread_local std::map<std::pair<int, size_t>, int> bps_cache;
     int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem_bytes));
-    if (bps < 1) bps = 1;
-    // (the score-only variant writes no trace: no scratch, the grid is bounded by the occupancy alone)
-    const size_t gwarp_bytes = SO ? 0 : ((size_t)((max_steps + PB_TCHUNK - 1) / PB_TCHUNK) * PB_TCHUNK * WPS * 32 +
-                                         (HS ? 0 : (((size_t)SPW * max_n + 31) & ~(size_t)31))) * 4;   // 128-byte lines per warp (kernels.cuh)
+    const auto key = std::make_pair(E.device, smem_bytes);
+    auto it = bps_cache.find(key);
+    if (it == bps_cache.end()) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem_bytes));
+        if (bps < 1) bps = 1;
+        bps_cache[key] = bps;
+    } else {
+        bps = it->second;
+    }
+    const size_t gwarp_bytes = ((size_t)((max_steps + PB_TCHUNK - 1) / PB_TCHUNK) * PB_TCHUNK * WPS * 32 +
+                                (HS ? 0 : (((size_t)SPW * max_n + 31) & ~(size_t)31))) * 4;   // 128-byte lines per warp (kernels.cuh)
     // The trace scratch of the resident grid is rewritten slot after slot and mostly lives in L2.  `scratch_mb` caps
     // it (whole blocks per SM, never below 2): measured on B200 for 150x28 windows, 72 MB (3 blocks/SM) keeps the
     // trace L2-resident (DRAM traffic 1.9x the algorithmic bytes) at ~10 % lower kernel throughput than the default
@@ -264,71 +269,34 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc
     const int64_t n_wslots = (n_slots + SPW - 1) / SPW;
     int64_t blocks = (n_wslots + wpb - 1) / wpb;
     blocks = std::min<int64_t>(blocks, std::min<int64_t>((int64_t)bps * E.sm_count, max_blocks));
-    if constexpr (!SO) {
-        if ((size_t)blocks * wpb * gwarp_bytes > (24ull << 30)) blocks = std::max<int64_t>(1, (int64_t)((24ull << 30) / (gwarp_bytes * wpb)));
-    }
+    if ((size_t)blocks * wpb * gwarp_bytes > (24ull << 30)) blocks = std::max<int64_t>(1, (int64_t)((24ull << 30) / (gwarp_bytes * wpb)));
     if (blocks <= 0) return 0;
-    if constexpr (!SO) {
-        if (int rc = S.gtrace.ensure((size_t)blocks * wpb * gwarp_bytes)) return rc;
-    }
+    if (int rc = S.gtrace.ensure((size_t)blocks * wpb * gwarp_bytes)) return rc;
     TimedLaunch tl; bool on;
-    timed_begin(E, stream, tl, on, SO ? TK_TRACE_SCORE_ONLY : E.next_trace_kind);
-    kern<<<(unsigned)blocks, wpb * 32, smem_bytes, stream>>>(ts, seq_codes, ad_codes, sc, out,
-                                                              SO ? nullptr : S.gtrace.as<uint32_t>(), max_steps, max_n, status, ends);
+    timed_begin(E, stream, tl, on, E.next_trace_kind);
+    kern<<<(unsigned)blocks, wpb * 32, smem_bytes, stream>>>(ts, seq_codes, ad_codes, sc, out, S.gtrace.as<uint32_t>(), max_steps,
+                                                              max_n, status);
     timed_end(E, stream, tl, on);
     g_launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
-// does a slot's staging of packed bases fit shared memory (the only staging the score-only variant has)?
-template <int G>
-bool hbuf_fits_smem(const Engine &E, int max_n) {
-    constexpr int SPW = 32 / G;
-    return (size_t)SPW * max_n * 4 <= 12288 &&
-           (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + 4 + PB_SCRATCH_WORDS + PB_GPROF_WORDS) * 4 <= E.smem_optin;
-}
-
 template <int G, int R>
 int launch_trace(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc &ts, int max_n,
-                 const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status,
-                 EndCell *ends) {
+                 const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
     constexpr int SPW = 32 / G;
     if (max_n < 1) max_n = 1;
-    // query profiles (option "profile"), cross mode only (also the windowed second pass, which keeps the task order):
-    //   pair profile (1)      the adapter pair is the same for every slot -- a class with one or two adapters, <= 64 rows
-    //   per-group profile (2) every slot is one read x its own two adapters -- an even number of adapters (an odd class is
-    //                         split by run_class_tasks into its paired part and the single-adapter tail); not for the
-    //                         windowed second pass, whose two halves sit at different columns of the read
-    constexpr bool PP_OK = G <= 8;
-    const bool prof = g_opt.profile != 0 && ts.cls_ad != nullptr && ts.n_cls_ad >= 1;
-    const bool pp = prof && PP_OK && ts.n_cls_ad <= 2;
-    const bool gp = prof && !pp && (ts.n_cls_ad % 2) == 0 && ts.tasks == nullptr;    // (windowed halves read different columns)
-    constexpr int PM1 = PP_OK ? 1 : 0;
-    const size_t gp_words = gp ? (size_t)PB_GPROF_WORDS : 0;
-    if (ends) {                                   // score-only first pass of the short two-pass scheme
-        if (!hbuf_fits_smem<G>(E, max_n)) return fail(PB200_ERR_INTERNAL, "score-only pass needs shared-memory staging");
-        if (pp) return launch_trace_variant<G, R, true, true, PM1>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
-        if (gp) return launch_trace_variant<G, R, true, true, 2>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
-        return launch_trace_variant<G, R, true, true>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
-    }
     // packed read bases of a slot are staged in shared memory when they fit (<= 12 KB per warp), else in global scratch
     const bool hs = g_opt.hbuf_mode == 1 ? true : g_opt.hbuf_mode == 2 ? false : ((size_t)SPW * max_n * 4 <= 12288);
-    if (hs && (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + 4 + PB_SCRATCH_WORDS + gp_words) * 4 <= E.smem_optin) {
-        if (pp) return launch_trace_variant<G, R, true, false, PM1>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
-        if (gp) return launch_trace_variant<G, R, true, false, 2>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
+    if (hs && (size_t)PB_WARPS_PER_BLOCK * ((size_t)SPW * max_n + 4 + PB_SCRATCH_WORDS) * 4 <= E.smem_optin)
         return launch_trace_variant<G, R, true>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
-    }
-    if (pp) return launch_trace_variant<G, R, false, false, PM1>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
-    if (gp) return launch_trace_variant<G, R, false, false, 2>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
     return launch_trace_variant<G, R, false>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
 }
 
-// ends != nullptr: score-only pass writing the end cells instead of records (out may be nullptr)
 int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const TaskSrc &ts, int max_n,
-                       const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status,
-                       EndCell *ends = nullptr) {
-#define PB_CASE(K, GG, RR) case K: return launch_trace<GG, RR>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status, ends);
+                       const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, int32_t *out, int *status) {
+#define PB_CASE(K, GG, RR) case K: return launch_trace<GG, RR>(E, S, stream, ts, max_n, seq_codes, ad_codes, sc, out, status);
     switch (cls) {
         PB_CASE(0, 4, 5) PB_CASE(1, 4, 6) PB_CASE(2, 4, 7) PB_CASE(3, 4, 8)
         PB_CASE(4, 8, 5) PB_CASE(5, 8, 6) PB_CASE(6, 8, 7) PB_CASE(7, 8, 8)
@@ -338,23 +306,18 @@ int launch_trace_class(Engine &E, Stage &S, cudaStream_t stream, int cls, const 
 #undef PB_CASE
     return fail(PB200_ERR_INTERNAL, "bad class");
 }
-bool class_hbuf_fits_smem(const Engine &E, int cls, int max_n) {
-    switch (cls / 4) {
-        case 0: return hbuf_fits_smem<4>(E, max_n);
-        case 1: return hbuf_fits_smem<8>(E, max_n);
-        case 2: return hbuf_fits_smem<16>(E, max_n);
-        case 3: return hbuf_fits_smem<32>(E, max_n);
-    }
-    return false;
-}
 
-template <int G, int R, bool RO, bool PROF = false>
+template <int G, int R, bool PROF>
 int launch_score_variant(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsigned long long *counter,
                          const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, EndCell *ends) {
-    auto kern = score_kernel<G, R, RO, PROF>;
-    int bps = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, PB_WARPS_PER_BLOCK * 32, 0));
-    if (bps < 1) bps = 1;
+    auto kern = score_kernel<G, R, PROF>;
+    static thread_local std::map<int, int> bps_cache;
+    int bps = bps_cache[E.device];
+    if (bps == 0) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, PB_WARPS_PER_BLOCK * 32, 0));
+        if (bps < 1) bps = 1;
+        bps_cache[E.device] = bps;
+    }
     constexpr int SPW = 32 / G;
     const int64_t n_tasks = ts.n_tasks;
     const int64_t n_slots = (n_tasks + 1) / 2;
@@ -370,29 +333,22 @@ int launch_score_variant(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsi
     CK(cudaGetLastError());
     return 0;
 }
-// The score pass runs in the row-offset domain when the offsets (coff per group row) still fit the int16 domain.
 template <int G, int R>
 int launch_score(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsigned long long *counter, const uint8_t *seq_codes,
-                 const uint8_t *ad_codes, const Scoring &sc, const SchemeInfo &si, int m_max, EndCell *ends) {
-    const long long c = rowoff_c(sc.mi, sc.go, sc.ge);
+                 const uint8_t *ad_codes, const Scoring &sc, EndCell *ends) {
     // query profile: every slot is (one read, two adapters) -- cross mode with an even number of adapters in the class
     const bool prof = g_opt.profile != 0 && ts.tasks == nullptr && ts.n_cls_ad > 0 && (ts.n_cls_ad % 2) == 0;
-    if (g_opt.rowoff && (long long)si.A * (m_max + 3) + c * G * R <= PB_I16_LIMIT) {
-        const Scoring so = make_scoring(sc.ma, sc.mi, sc.go, sc.ge, true);
-        if (prof) return launch_score_variant<G, R, true, true>(E, stream, ts, counter, seq_codes, ad_codes, so, ends);
-        return launch_score_variant<G, R, true>(E, stream, ts, counter, seq_codes, ad_codes, so, ends);
-    }
-    if (prof) return launch_score_variant<G, R, false, true>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
+    if (prof) return launch_score_variant<G, R, true>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
     return launch_score_variant<G, R, false>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
 }
 int launch_score_class(Engine &E, cudaStream_t stream, int cls, const TaskSrc &ts,
                        unsigned long long *counter, const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc,
-                       const SchemeInfo &si, int m_max, EndCell *ends) {
+                       EndCell *ends) {
     switch (cls / 4) {
-        case 0: return launch_score<4, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, si, m_max, ends);
-        case 1: return launch_score<8, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, si, m_max, ends);
-        case 2: return launch_score<16, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, si, m_max, ends);
-        case 3: return launch_score<32, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, si, m_max, ends);
+        case 0: return launch_score<4, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
+        case 1: return launch_score<8, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
+        case 2: return launch_score<16, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
+        case 3: return launch_score<32, 8>(E, stream, ts, counter, seq_codes, ad_codes, sc, ends);
     }
     return fail(PB200_ERR_INTERNAL, "bad class");
 }
@@ -421,9 +377,11 @@ int run_class_tasks(Engine &E, Stage &S, cudaStream_t stream, int cls, int m_max
                     int32_t *out, int *status, unsigned long long *counter) {
     const int64_t n_tasks = ts.n_tasks;
     if (n_tasks <= 0) return 0;
-    if (g_opt.profile != 0 && ts.tasks == nullptr && ts.cls_ad != nullptr && ts.n_cls_ad >= 3 && (ts.n_cls_ad & 1)) {
-        // profiles need uniform slots: the paired adapters (one read, two adapters per slot) and the odd last adapter (two
-        // reads per slot) run as two launches; cross_task() indexes both exactly as it does inside the whole class
+    if (g_opt.profile != 0 && ts.tasks == nullptr && ts.cls_ad != nullptr && ts.n_cls_ad >= 3 && (ts.n_cls_ad & 1) &&
+        si.bounded && max_n > g_opt.direct_max) {
+        // the score pass's query profile needs same-read slots: the paired adapters (one read, two adapters per slot) and the
+        // odd last adapter (two reads per slot) run as two launch sequences; cross_task() indexes both exactly as it does
+        // inside the whole class
         TaskSrc paired = ts, tail = ts;
         paired.n_cls_ad = ts.n_cls_ad - 1;
         paired.n_tasks = ts.n_seqs * (int64_t)paired.n_cls_ad;
@@ -435,20 +393,10 @@ int run_class_tasks(Engine &E, Stage &S, cudaStream_t stream, int cls, int m_max
     }
     int64_t W = si.bounded ? (int64_t)m_max + ((int64_t)m_max * si.wnum) / si.wden : (int64_t)1 << 40;
     const bool two_pass = si.bounded && max_n > g_opt.direct_max && W + 1 < max_n;
-    // Short two-pass (option "short2p"): windows that would take the single trace pass are first swept score-only by the
-    // same slot loop (7 instead of 18 instructions per row, no trace traffic), then only the bounded window left of each
-    // end cell is traced.  Worth it when the traced window is clearly shorter than the sequence.
-    const bool short2p = !two_pass && g_opt.short2p != 0 && si.bounded && W + 8 < max_n &&
-                         class_hbuf_fits_smem(E, cls, (int)max_n);
-    if (!two_pass && !short2p) return launch_trace_class(E, S, stream, cls, ts, (int)max_n, seq_codes, ad_codes, sc, out, status);
+    if (!two_pass) return launch_trace_class(E, S, stream, cls, ts, (int)max_n, seq_codes, ad_codes, sc, out, status);
     if (int rc = S.ends.ensure((size_t)n_tasks * sizeof(EndCell))) return rc;
     if (int rc = S.tasks2.ensure((size_t)n_tasks * sizeof(Task))) return rc;
-    if (short2p) {
-        if (int rc = launch_trace_class(E, S, stream, cls, ts, (int)max_n, seq_codes, ad_codes, sc, nullptr, status,
-                                        S.ends.as<EndCell>())) return rc;
-    } else {
-        if (int rc = launch_score_class(E, stream, cls, ts, counter, seq_codes, ad_codes, sc, si, m_max, S.ends.as<EndCell>())) return rc;
-    }
+    if (int rc = launch_score_class(E, stream, cls, ts, counter, seq_codes, ad_codes, sc, S.ends.as<EndCell>())) return rc;
     {
         int64_t blocks = (n_tasks + 255) / 256;
         if (!E.wcells.p) {
@@ -686,10 +634,11 @@ int validate_args(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, c
     return 0;
 }
 
-// The pipeline chunk that starts at sequence s0 of a cross-product job: chunk_tasks alignments, at most chunk_bytes of
-// sequence (but enough sequences to fill the GPU), its longest sequence, offsets checked.
-int next_chunk(const int64_t *seq_off, int64_t n_seqs, int32_t n_adapters, int64_t s0, HostChunk &c) {
-    const int64_t max_cnt = std::max<int64_t>(1, g_opt.chunk_tasks / std::max<int32_t>(n_adapters, 1));
+// The pipeline chunk that starts at sequence s0 of a cross-product job: chunk_tasks alignments (at most task_cap: the first
+// chunks of a submit are smaller, see chunk_cap), at most chunk_bytes of sequence (but enough sequences to fill the GPU),
+// its longest sequence, offsets checked.
+int next_chunk(const int64_t *seq_off, int64_t n_seqs, int32_t n_adapters, int64_t s0, HostChunk &c, int64_t task_cap) {
+    const int64_t max_cnt = std::max<int64_t>(1, std::min(g_opt.chunk_tasks, task_cap) / std::max<int32_t>(n_adapters, 1));
     int64_t s1 = std::min(n_seqs, s0 + max_cnt);
     while (s1 - s0 > 32768 && seq_off[s1] - seq_off[s0] > g_opt.chunk_bytes) s1 = s0 + std::max<int64_t>(32768, (s1 - s0) / 2);
     c = HostChunk{s0, s1, 0};
@@ -717,6 +666,120 @@ struct CrossJob {
     int64_t max_seq_len = 0;          // decision jobs: longest window the threshold table covers
 };
 
+// The first chunks of a submit ramp up (1/8, 1/4, 1/2 of chunk_tasks): the pipeline's fill -- pack + H2D of chunk 0 before
+// any DP kernel can start -- costs an eighth of what a full chunk would; only when the submit is large enough to matter.
+int64_t chunk_cap(size_t k, int64_t total_tasks) {
+    if (total_tasks < 4 * g_opt.chunk_tasks || k >= 3) return g_opt.chunk_tasks;
+    return std::max<int64_t>(4096, g_opt.chunk_tasks >> (3 - k));
+}
+
+// One planned (and, with h2d_pack, packed) chunk on its way from the planner to the submit loop.
+struct PackItem {
+    size_t job = 0;
+    HostChunk c{0, 0, 0};
+    int buf = -1;                 // index of the pinned pack buffer holding the chunk's 4-bit codes (-1: not packed)
+    int rc = 0; std::string err;  // planning error (bad offsets): the submit loop stops here
+    bool end = false;             // no more chunks
+};
+
+// Planning of a submit's chunk sequence (the order of run_cross_jobs' loop), shared by the inline path and the packer thread.
+struct ChunkPlanner {
+    const std::vector<CrossJob> *jobs;
+    size_t j = 0, k = 0;
+    int64_t s0 = 0, total_tasks = 0;
+    explicit ChunkPlanner(const std::vector<CrossJob> &J) : jobs(&J) {
+        for (const CrossJob &x : J) total_tasks += x.n_seqs * (int64_t)x.n_adapters;
+    }
+    // next chunk -> item (rc / end set accordingly); errors come back as text because the planner may run on another thread
+    void next(PackItem &it) {
+        it = PackItem();
+        while (j < jobs->size() && ((*jobs)[j].n_seqs <= 0 || (*jobs)[j].n_adapters <= 0 || s0 >= (*jobs)[j].n_seqs)) { ++j; s0 = 0; }
+        if (j >= jobs->size()) { it.end = true; return; }
+        const CrossJob &J = (*jobs)[j];
+        it.job = j;
+        it.rc = next_chunk(J.seq_off, J.n_seqs, J.n_adapters, s0, it.c, chunk_cap(k, total_tasks));
+        if (!it.rc && J.dec && it.c.max_n > J.max_seq_len)
+            it.rc = fail(PB200_ERR_ARG, "decision batches take windows of at most end_size bases");
+        if (it.rc) { it.err = g_err; return; }
+        s0 = it.c.s1;
+        ++k;
+    }
+};
+
+// Packer: a persistent host thread per engine that plans the chunks of a submit and converts them to 4-bit codes (option
+// h2d_pack; hostpack.cpp, OpenMP team of pack_threads) AHEAD of the submit loop, into a ring of NPACK pinned buffers -- the
+// conversion of chunk k+1.. runs while the submit loop enqueues chunk k and the device works on chunk k-1 (round 2: with
+// the packer inside the submit loop the e2e step was bound by the host conversion, profiles/r2_options).
+constexpr int NPACK = NSTAGE + 2;
+struct Packer {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    const std::vector<CrossJob> *jobs = nullptr;   // request: non-null while a run is wanted
+    bool abort = false, stop = false, busy = false;
+    std::deque<PackItem> q;
+    HostBuf buf[NPACK];
+    cudaEvent_t ev[NPACK];
+    enum { FREE = 0, QUEUED = 1, INFLIGHT = 2 };
+    int state[NPACK] = {0, 0, 0, 0, 0};
+    int device = 0;
+    bool ev_made = false;
+
+    void loop() {
+        cudaSetDevice(device);
+        for (;;) {
+            const std::vector<CrossJob> *J;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || (jobs && !busy && q.empty()); });
+                if (stop) return;
+                J = jobs; busy = true;
+            }
+            ChunkPlanner plan(*J);
+            for (size_t k = 0;; ++k) {
+                PackItem it;
+                bool stop_now;
+                { std::lock_guard<std::mutex> lk(mu); stop_now = abort; }
+                if (stop_now) it.end = true; else plan.next(it);
+                const int b = (int)(k % NPACK);
+                if (!it.end && !it.rc) {
+                    bool inflight = false;
+                    {   // the buffer's previous chunk must have been taken by the submit loop and its upload must be complete
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return abort || state[b] != QUEUED; });
+                        if (abort) { it = PackItem(); it.end = true; }
+                        inflight = state[b] == INFLIGHT;
+                    }
+                    if (!it.end) {
+                        if (inflight) cudaEventSynchronize(ev[b]);
+                        const CrossJob &X = (*J)[it.job];
+                        const int64_t base = X.seq_off[it.c.s0], bytes = X.seq_off[it.c.s1] - base;
+                        g_err.clear();
+                        if (bytes > 0 && buf[b].ensure(((size_t)bytes + 1) / 2)) { it.rc = PB200_ERR_CUDA; it.err = g_err; }
+                        else if (bytes > 0) pb_pack_nibbles(X.seqs + base, bytes, buf[b].p, g_opt.pack_threads);
+                        it.buf = b;
+                    }
+                }
+                const bool last = it.end || it.rc != 0;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    if (it.buf >= 0) state[b] = QUEUED;
+                    q.push_back(std::move(it));
+                    if (last) { jobs = nullptr; busy = false; }
+                }
+                cv.notify_all();
+                if (last) break;
+            }
+        }
+    }
+    ~Packer() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+        for (int i = 0; i < NPACK; ++i) if (buf[i].p) { cudaFreeHost(buf[i].p); buf[i].p = nullptr; }
+    }
+};
+
 // Chunks of every job flow through ONE ring of NSTAGE streams (H2D / kernels / D2H of consecutive chunks overlap, also
 // across job boundaries: no fill / drain bubble between the start-window and the end-window batch of an end-trim step).
 // Caller holds E.mu and has run E.init().
@@ -725,7 +788,37 @@ int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int g
         if (int rc = E.st[i].misc.ensure(64)) return rc;
         CK(cudaMemsetAsync(E.st[i].misc.p, 0, 64, E.st[i].stream));
     }
-    auto submit = [&](const CrossJob &J, const AdapterPlan &P, const HostChunk &c, Stage &S) -> int {
+    int64_t total_bytes = 0;
+    for (const CrossJob &J : jobs) if (J.n_seqs > 0 && J.n_adapters > 0) total_bytes += J.seq_off[J.n_seqs] - J.seq_off[0];
+    const bool packed = g_opt.h2d_pack != 0 && total_bytes > 0;
+    Packer *PK = nullptr;
+    if (packed) {
+        if (!E.packer) {
+            auto pk = std::make_shared<Packer>();
+            pk->device = E.device;
+            for (int i = 0; i < NPACK; ++i) CK(cudaEventCreateWithFlags(&pk->ev[i], cudaEventDisableTiming));
+            pk->ev_made = true;
+            pk->th = std::thread([p = pk.get()] { p->loop(); });
+            E.packer = pk;
+        }
+        PK = static_cast<Packer *>(E.packer.get());
+        {
+            std::lock_guard<std::mutex> lk(PK->mu);
+            PK->abort = false;
+            PK->jobs = &jobs;
+        }
+        PK->cv.notify_all();
+    }
+    ChunkPlanner inline_plan(jobs);
+    auto next_item = [&](PackItem &it) {
+        if (!PK) { inline_plan.next(it); return; }
+        std::unique_lock<std::mutex> lk(PK->mu);
+        PK->cv.wait(lk, [&] { return !PK->q.empty(); });
+        it = std::move(PK->q.front());
+        PK->q.pop_front();
+    };
+    auto submit = [&](const CrossJob &J, const AdapterPlan &P, const PackItem &it, Stage &S) -> int {
+        const HostChunk &c = it.c;
         const int64_t s0 = c.s0, cnt = c.s1 - c.s0;
         const int64_t base = J.seq_off[s0];
         const int64_t bytes = J.seq_off[c.s1] - base;
@@ -735,22 +828,19 @@ int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int g
         if (int rc = S.seq_codes.ensure((size_t)bytes + 16)) return rc;
         if (int rc = S.seq_off.ensure((size_t)(cnt + 1) * 8)) return rc;
         if (int rc = S.out.ensure((size_t)cnt * J.n_adapters * PB_REC * 4)) return rc;
-        const bool packed = g_opt.h2d_pack != 0 && bytes > 0;
-        if (packed) {
-            // Dna5 conversion on the host cores, two codes per byte: half the bytes cross PCIe (the e2e bound).  The
-            // host packs chunk k+1 while the device works on chunk k; the stage's pinned buffer is free again because
-            // the stage's stream was synchronised above.
-            const size_t pbytes = ((size_t)bytes + 1) / 2;
-            if (int rc = S.h_pack.ensure(pbytes)) return rc;
-            pb_pack_nibbles(J.seqs + base, bytes, S.h_pack.p, g_opt.pack_threads);
-            CK(cudaMemcpyAsync(S.seq_raw.p, S.h_pack.p, pbytes, cudaMemcpyHostToDevice, stream));
+        if (it.buf >= 0) {
+            // Dna5 conversion was done on the host cores by the packer thread, two codes per byte: half the bytes cross PCIe
+            if (bytes) CK(cudaMemcpyAsync(S.seq_raw.p, PK->buf[it.buf].p, ((size_t)bytes + 1) / 2, cudaMemcpyHostToDevice, stream));
+            CK(cudaEventRecord(PK->ev[it.buf], stream));
+            { std::lock_guard<std::mutex> lk(PK->mu); PK->state[it.buf] = Packer::INFLIGHT; }
+            PK->cv.notify_all();
         } else if (bytes) {
             CK(cudaMemcpyAsync(S.seq_raw.p, J.seqs + base, (size_t)bytes, cudaMemcpyHostToDevice, stream));
         }
         CK(cudaMemcpyAsync(S.seq_off.p, J.seq_off + s0, (size_t)(cnt + 1) * 8, cudaMemcpyHostToDevice, stream));
         rebase_kernel<<<(unsigned)((cnt + 1 + 255) / 256), 256, 0, stream>>>(S.seq_off.as<int64_t>(), cnt + 1, base);
         g_launches++;
-        if (packed) {
+        if (it.buf >= 0) {
             if (int rc = launch_unpack(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
         } else {
             if (int rc = launch_encode(stream, S.seq_raw.as<uint8_t>(), S.seq_codes.as<uint8_t>(), bytes, E.sm_count)) return rc;
@@ -781,29 +871,48 @@ int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int g
         return 0;
     };
     int rc_final = 0;
-    size_t k = 0;
-    for (size_t j = 0; j < jobs.size() && !rc_final; ++j) {
-        const CrossJob &J = jobs[j];
-        if (J.n_seqs <= 0 || J.n_adapters <= 0) continue;
-        // The adapter plan is made (or found in the 4-entry cache) right before the job's first chunk: a miss waits for the
-        // device to go idle before it recycles an entry, so chunks of earlier jobs never lose their adapter copies.
-        AdapterPlan P;
-        rc_final = plan_adapters(E, E.st[k % NSTAGE].stream, J.adapters, J.ad_off, J.n_adapters, ma, mi, go, ge, P);
-        for (int64_t s0 = 0; s0 < J.n_seqs && !rc_final; ++k) {
-            HostChunk c;
-            rc_final = next_chunk(J.seq_off, J.n_seqs, J.n_adapters, s0, c);
-            if (!rc_final && J.dec && c.max_n > J.max_seq_len)
-                rc_final = fail(PB200_ERR_ARG, "decision batches take windows of at most end_size bases");
-            if (!rc_final) rc_final = submit(J, P, c, E.st[k % NSTAGE]);
-            s0 = c.s1;
+    std::string first_err;
+    size_t k = 0, cur_job = (size_t)-1;
+    AdapterPlan P;
+    bool drained = false;
+    while (!rc_final) {
+        PackItem it;
+        next_item(it);
+        if (it.end) { drained = true; break; }
+        if (it.rc) { rc_final = it.rc; first_err = it.err; drained = true; break; }     // planning error ends the planner's run too
+        const CrossJob &J = jobs[it.job];
+        if (it.job != cur_job) {
+            // The adapter plan is made (or found in the 4-entry cache) right before the job's first chunk: a miss waits for the
+            // device to go idle before it recycles an entry, so chunks of earlier jobs never lose their adapter copies.
+            cur_job = it.job;
+            P = AdapterPlan();
+            rc_final = plan_adapters(E, E.st[k % NSTAGE].stream, J.adapters, J.ad_off, J.n_adapters, ma, mi, go, ge, P);
+        }
+        if (!rc_final) rc_final = submit(J, P, it, E.st[k % NSTAGE]);
+        if (rc_final) first_err = g_err;
+        ++k;
+    }
+    if (PK && !drained) {
+        // an error on this side: stop the packer and take its remaining items so that it is idle (and its buffers free) again
+        { std::lock_guard<std::mutex> lk(PK->mu); PK->abort = true; }
+        PK->cv.notify_all();
+        for (;;) {
+            PackItem it;
+            next_item(it);
+            if (it.buf >= 0) { std::lock_guard<std::mutex> lk(PK->mu); PK->state[it.buf] = Packer::FREE; }
+            PK->cv.notify_all();
+            if (it.end || it.rc) break;
         }
     }
     // Whatever happened, nothing may still be writing into the caller's `out` (or reading `seqs`) when we return.
-    const std::string first_err = g_err;
     for (int i = 0; i < NSTAGE; ++i) {
-        if (!rc_final && E.st[i].misc.p) rc_final = check_status(E.st[i], E.st[i].stream);
+        if (!rc_final && E.st[i].misc.p) { rc_final = check_status(E.st[i], E.st[i].stream); if (rc_final) first_err = g_err; }
         cudaError_t e = cudaStreamSynchronize(E.st[i].stream);
-        if (e != cudaSuccess && !rc_final) rc_final = fail(PB200_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+        if (e != cudaSuccess && !rc_final) { rc_final = fail(PB200_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e)); first_err = g_err; }
+    }
+    if (PK) {        // all uploads are complete: the pack buffers are free for the next submit
+        std::lock_guard<std::mutex> lk(PK->mu);
+        for (int i = 0; i < NPACK; ++i) PK->state[i] = Packer::FREE;
     }
     if (rc_final && !first_err.empty()) g_err = first_err;
     return rc_final;
@@ -1261,10 +1370,8 @@ int pb200SetOption(const char *name, const char *value) {
     if (!strcmp(name, "direct_max")) g_opt.direct_max = atoll(value);
     else if (!strcmp(name, "chunk_tasks")) g_opt.chunk_tasks = std::max(1ll, atoll(value));
     else if (!strcmp(name, "scratch_mb")) g_opt.scratch_mb = std::max(1, atoi(value));
-    else if (!strcmp(name, "rowoff")) g_opt.rowoff = atoi(value);
     else if (!strcmp(name, "tight_window")) g_opt.tight_window = atoi(value);
     else if (!strcmp(name, "h2d_pack")) g_opt.h2d_pack = atoi(value);
-    else if (!strcmp(name, "short2p")) g_opt.short2p = atoi(value);
     else if (!strcmp(name, "profile")) g_opt.profile = atoi(value);
     else if (!strcmp(name, "pack_threads")) { if (atoi(value) > 0) g_opt.pack_threads = atoi(value); }
     else if (!strcmp(name, "hbuf")) g_opt.hbuf_mode = !strcmp(value, "smem") ? 1 : !strcmp(value, "global") ? 2 : 0;

@@ -4,7 +4,7 @@
 //   unpack_kernel        host-packed 4-bit codes -> the same code bytes (option h2d_pack)
 //   build_tasks_*        (read, adapter) pairs -> Task records in slot order
 //   trace_kernel<G,R,S>  overlap DP *with* 4-bit trace + in-kernel traceback + statistics (windows)
-//   score_kernel<G,R>    streaming score-only overlap DP with exact scout (long reads), dynamic slot refill
+//   score_kernel<G,R,P>  streaming score-only overlap DP with exact scout (long reads), dynamic slot refill
 //   window_tasks_kernel  end cells of the score pass -> bounded-window tasks for trace_kernel
 //   decide_kernel        records -> per-read end-trim amounts + barcode score pairs (decisions stay on the device)
 //   generic_kernel       int32 thread-serial fallback for scoring schemes / adapters outside the int16 domain
@@ -223,51 +223,71 @@ __device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
     return __byte_perm(bA, bB, 0x4101);
 }
 
+// 16 bytes starting `sh` bytes into the aligned 32-byte pair p[0], p[1] (p[1] only read when `second`), as 4 words
+__device__ __forceinline__ void load_block16(const uint4 *p, unsigned sh, bool first, bool second, uint32_t *w) {
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 a = first ? __ldcs(p) : z, b = (first && second && sh != 0) ? __ldcs(p + 1) : z;
+    const unsigned r = (sh & 3) * 8;
+    uint32_t x0, x1, x2, x3, x4;
+    switch (sh >> 2) {                   // whole-word part of the shift: static register selection per case
+        case 0: x0 = a.x; x1 = a.y; x2 = a.z; x3 = a.w; x4 = b.x; break;
+        case 1: x0 = a.y; x1 = a.z; x2 = a.w; x3 = b.x; x4 = b.y; break;
+        case 2: x0 = a.z; x1 = a.w; x2 = b.x; x3 = b.y; x4 = b.z; break;
+        default: x0 = a.w; x1 = b.x; x2 = b.y; x3 = b.z; x4 = b.w; break;
+    }
+    w[0] = __funnelshift_r(x0, x1, r); w[1] = __funnelshift_r(x1, x2, r);
+    w[2] = __funnelshift_r(x2, x3, r); w[3] = __funnelshift_r(x3, x4, r);
+}
+
+// Stage the packed read bases of a slot's columns: hbuf[c] = pack_bases(A[c], B[c]) for c < nmax, PB_PAD_H past the end
+// of a half.  Each lane of the group builds every G-th column from single-byte loads (PB_STAGE_VEC undefined), or the
+// group walks the window in 16-column blocks, one aligned 128-bit load per half and block (PB_STAGE_VEC, round-2 A/B).
+template <int G>
+__device__ __forceinline__ void stage_columns(uint32_t *hbuf, int g, const uint8_t *seqA, int nA, const uint8_t *seqB, int nB,
+                                              int nmax) {
+#ifdef PB_STAGE_VEC
+    // half X's columns [16b, 16b+16) are source bytes [16b + shX, 16b + shX + 16) of the 16-byte aligned stream that starts
+    // shX = address & 15 bytes before its first base: two aligned 128-bit loads, shifted into place (load_block16)
+    const unsigned shA = (unsigned)(reinterpret_cast<uintptr_t>(seqA) & 15), shB = (unsigned)(reinterpret_cast<uintptr_t>(seqB) & 15);
+    const uint4 *baseA = reinterpret_cast<const uint4 *>(seqA - shA), *baseB = reinterpret_cast<const uint4 *>(seqB - shB);
+    const int nblk = (nmax + 15) >> 4;
+    for (int b = g; b < nblk; b += G) {
+        uint32_t wa[4], wb[4];
+        load_block16(baseA + b, shA, 16 * b < nA, 16 * b + 16 - (int)shA < nA, wa);
+        load_block16(baseB + b, shB, 16 * b < nB, 16 * b + 16 - (int)shB < nB, wb);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int c = 16 * b + k;
+            if (c < nmax) {
+                uint32_t bA = (wa[k >> 2] >> ((k & 3) * 8)) & 0xFFu, bB = (wb[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+                if (c >= nA) bA = (uint32_t)PB_PAD_H;
+                if (c >= nB) bB = (uint32_t)PB_PAD_H;
+                hbuf[c] = pack_bases(bA, bB);
+            }
+        }
+    }
+#else
+    for (int c = g; c < nmax; c += G) {
+        const uint32_t bA = (c < nA) ? (uint32_t)__ldcs(seqA + c) : (uint32_t)PB_PAD_H;
+        const uint32_t bB = (c < nB) ? (uint32_t)__ldcs(seqB + c) : (uint32_t)PB_PAD_H;
+        hbuf[c] = pack_bases(bA, bB);
+    }
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------------
 // trace_kernel: one group of G lanes per slot (two alignments in the s16x2 halves), 32/G slots per warp, R adapter
 // rows per lane (G*R >= adapter length; R = 5..8 so common adapter lengths 22/24/28 waste no rows).
 // Forward wavefront with a 4-bit trace per cell (two 32-bit words per lane per step), then traceback + statistics
 // by two lanes of the group, 9-int record per alignment.  Grid-stride over "warp slots" so the trace scratch is
 // bounded by the resident grid and stays in L2.
-//
-// (score-only variants need fewer registers -- 68-80 -- and are compiled for 6 instead of 5 resident blocks per SM)
-// SCORE_ONLY = the same slot loop without the trace: the forward pass runs the 7-instruction score cell, nothing is
-// written to the scratch, and instead of the traceback the group's scout result goes to `ends` -- the first pass of the
-// short two-pass scheme (option "short2p": end cells first, then only the bounded window left of each end cell is
-// traced; engine.cu run_class_tasks).  Requires HBUF_SMEM (no global scratch is allocated).
-//
-// PPROF = pair profile (dp_core.cuh profile_word2; option "profile"): the launch's adapter pair is the same for every slot
-// (a cross-mode class with one adapter -- two reads per slot -- or two adapters -- one read per slot), so one table per
-// BLOCK, indexed by (base of half A, base of half B), holds the substitution operands of every row: 36 pairs x G lanes x 8
-// words in shared memory, a step fetches its R operands with two 128-bit loads instead of LOP3 + VIADDMNMX per row.  The
-// staged column words then hold the table offset of the column's base pair instead of the packed bases.
-//
-// PMODE: 0 = no profile, 1 = the pair profile above (PPROF), 2 = a profile per GROUP (GPROF): every slot aligns one read
-// against its own two adapters (cross mode, even number of adapters in the launch -- the demux cross product), the group's
-// lanes keep 6 base codes x 8 words each in the warp's dynamic shared memory (6 KB per warp), refilled per slot.
-constexpr int PB_GPROF_WORDS = 6 * 32 * 8;       // per warp: SPW groups x 6 codes x G lanes x 8 words
-template <int G, int R, bool HBUF_SMEM, bool SCORE_ONLY = false, int PMODE = 0>
-__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, SCORE_ONLY ? 6 : PB_TRACE_MIN_BLOCKS)
+// (Measured and removed in round 2, profiles/r2_options: a score-only first pass + bounded trace window for 150-column
+// windows, and shared-memory query profiles for the substitution operands -- neither beat this single pass on B200.)
+template <int G, int R, bool HBUF_SMEM>
+__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_TRACE_MIN_BLOCKS)
 trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
              const uint8_t *__restrict__ ads, Scoring sc, int32_t *__restrict__ out, uint32_t *__restrict__ gtrace,
-             int max_steps, int max_n, int *__restrict__ status, EndCell *__restrict__ ends) {
-    static_assert(!SCORE_ONLY || HBUF_SMEM, "the score-only variant has no global scratch");
-    constexpr bool PPROF = PMODE == 1, GPROF = PMODE == 2, ANYPROF = PMODE != 0;
-    static_assert(!PPROF || G <= 8, "the pair profile is kept for adapters of up to 64 rows");
-    constexpr int PSTRIDE = G * 8;                       // words per base pair: 8 per lane (R <= 8), 32-byte aligned
-    __shared__ __align__(16) uint32_t pprof[PPROF ? 36 * PSTRIDE : 4];
-    if (PPROF) {
-        // the launch-uniform adapter pair = the adapters of tasks 0 and 1 (cross mode; engine.cu launches this variant only
-        // for classes with one or two adapters).  A missing task 1 (a single alignment) leaves half B all padding rows.
-        const Task p0 = get_task(ts, 0), p1 = get_task(ts, 1);
-        for (int idx = threadIdx.x; idx < 36 * PSTRIDE; idx += blockDim.x) {
-            const int pair = idx / PSTRIDE, gg = (idx % PSTRIDE) / 8, r = idx % 8;
-            pprof[idx] = (r < R) ? profile_word2(gg * R + r + 1, (uint32_t)(pair / 6), (uint32_t)(pair % 6), sc, ads + p0.ad_off, p0.m,
-                                                 G * R - p0.m, ads + p1.ad_off, p1.m, G * R - p1.m)
-                                 : 0u;
-        }
-        __syncthreads();
-    }
+             int max_steps, int max_n, int *__restrict__ status) {
     constexpr int SPW = 32 / G;
     constexpr int WPS = TraceWords<R>::value;
     extern __shared__ uint32_t smem[];
@@ -290,27 +310,11 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
     const size_t gwarp_words = trace_words + (HBUF_SMEM ? 0 : (((size_t)SPW * max_n + 31) & ~(size_t)31));
     uint32_t *gw = gtrace + (size_t)wglobal * gwarp_words;
     uint32_t *tr = gw;
-    // (GPROF rounds the staging area up to 16 bytes so that the group tables behind it can be read with 128-bit loads)
-    const int hb_words = HBUF_SMEM ? (GPROF ? ((SPW * max_n + 3) & ~3) : SPW * max_n) : 0;
-    const int per_warp_words = hb_words + PB_SCRATCH_WORDS + (GPROF ? PB_GPROF_WORDS : 0);
+    const int hb_words = HBUF_SMEM ? SPW * max_n : 0;
+    const int per_warp_words = hb_words + PB_SCRATCH_WORDS;
     uint32_t *wsm = smem + (size_t)warp * per_warp_words;
     uint32_t *hbuf = HBUF_SMEM ? (wsm + grp * max_n) : (gw + trace_words + (size_t)grp * max_n);
     ScoutCand *cand = reinterpret_cast<ScoutCand *>(wsm + hb_words);  // [half][lane]
-    // this lane's 8 words per base (pair): block table (PPROF) or the group's table in the warp's shared memory (GPROF)
-    uint32_t *gtab = wsm + hb_words + PB_SCRATCH_WORDS + grp * (6 * PSTRIDE) + g * 8;
-    const uint32_t *myprof = GPROF ? gtab : (pprof + (PPROF ? g * 8 : 0));
-    // one wavefront step of this lane for the staged column word hx (packed bases, or the pair-profile offset)
-#define PB_TRACE_STEP(KEEPV_, hx_, tw_, vr_)                                                                          \
-    do {                                                                                                              \
-        if (ANYPROF) {                                                                                                \
-            const uint4 *pp_ = reinterpret_cast<const uint4 *>(myprof + (hx_));                                       \
-            const uint4 q0_ = pp_[0], q1_ = pp_[1];                                                                   \
-            const uint32_t subs_[8] = {q0_.x, q0_.y, q0_.z, q0_.w, q1_.x, q1_.y, q1_.z, q1_.w};                      \
-            lane_step<R, !SCORE_ONLY, KEEPV_, false, true>(L, recvS, recvV, 0u, sc, tw_, vr_, subs_);                 \
-        } else {                                                                                                      \
-            lane_step<R, !SCORE_ONLY, KEEPV_>(L, recvS, recvV, (hx_), sc, tw_, vr_);                                  \
-        }                                                                                                             \
-    } while (0)
     for (int64_t ws = wglobal; ws < n_wslots; ws += total_warps) {
         const int64_t slot = ws * SPW + grp;
         int nA, nB, mA, mB, nmax, nmin;
@@ -322,31 +326,9 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
             const Task tB = get_task(ts, slot * 2 + 1);
             nA = tA.n; nB = tB.n; mA = tA.m; mB = tB.m;
             nmax = max(nA, nB);
-            const uint8_t *seqA = seq + tA.seq_off, *seqB = seq + tB.seq_off;
-            // stage the packed read bases of the slot's columns (each lane builds every G-th column)
-            for (int c = g; c < nmax; c += G) {
-                uint32_t bA = (c < nA) ? (uint32_t)__ldcs(seqA + c) : (uint32_t)PB_PAD_H;
-                uint32_t bB = (c < nB) ? (uint32_t)__ldcs(seqB + c) : (uint32_t)PB_PAD_H;
-                hbuf[c] = PPROF ? ((bA >> 4) * 6u + (bB >> 4)) * (uint32_t)PSTRIDE
-                                : GPROF ? (bA >> 4) * (uint32_t)PSTRIDE : pack_bases(bA, bB);
-            }
+            stage_columns<G>(hbuf, g, seq + tA.seq_off, nA, seq + tB.seq_off, nB, nmax);
             lane_init<R>(L, g, G, sc, ads + tA.ad_off, mA, (tA.flags & TASK_LEFT_INF) != 0, ads + tB.ad_off, mB,
                          (tB.flags & TASK_LEFT_INF) != 0);
-            if (GPROF) {
-                // both halves read sequence A (same-read slots); every lane fills, and later reads, only its own 48 words
-                // (the adapter pair changes from slot to slot in a grid-stride walk over a cross product, so the table is
-                // rebuilt per slot, ~0.5 % of a 150-column slot's instructions: lane_init has just set up the row operands
-                // (L.v2, L.sf2); per base code 8 words = two 128-bit stores)
-#pragma unroll
-                for (int b = 0; b < 6; ++b) {
-                    uint32_t w[8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) w[r] = (r < R) ? profile_from(L.v2[r < R ? r : 0], L.sf2[r < R ? r : 0], (uint32_t)b, (uint32_t)b, sc) : 0u;
-                    uint4 *dst = reinterpret_cast<uint4 *>(gtab + b * PSTRIDE);
-                    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                }
-            }
             // scout: fast path while both halves are in inner columns; an empty half never limits it
             const bool emptyA = nA <= 0 || mA <= 0, emptyB = nB <= 0 || mB <= 0;
             nmin = emptyA ? nB : (emptyB ? nA : min(nA, nB));
@@ -376,13 +358,11 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                     uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
                     if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
                     const int j = t0 + u - g + 1;
-                    PB_TRACE_STEP(false, hbuf[j - 1], buf[u], nullptr);
+                    lane_step<R, true, false>(L, recvS, recvV, hbuf[j - 1], sc, buf[u]);
                     if (need_track) lane_track_lastrow<R>(L, j, sc);
                 }
-                if (!SCORE_ONLY) {
 #pragma unroll
-                    for (int w = 0; w < WPS; ++w) acc[w] = make_uint4(buf[0][w], buf[1][w], buf[2][w], buf[3][w]);
-                }
+                for (int w = 0; w < WPS; ++w) acc[w] = make_uint4(buf[0][w], buf[1][w], buf[2][w], buf[3][w]);
             } else {
 #pragma unroll
                 for (int w = 0; w < WPS; ++w) acc[w] = make_uint4(0u, 0u, 0u, 0u);
@@ -398,7 +378,7 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                     for (int w = 0; w < WPS; ++w) tw[w] = 0u;
                     if (j >= 1 && j <= nmax) {
                         uint32_t vr[R];
-                        PB_TRACE_STEP(true, hbuf[j - 1], tw, vr);
+                        lane_step<R, true, true>(L, recvS, recvV, hbuf[j - 1], sc, tw, vr);
                         if (need_track) {
                             if (j >= nmin) lane_track_general<R>(L, g, j, make_geom(nA, mA, G, R), make_geom(nB, mB, G, R), vr, sc);
                             else lane_track_lastrow<R>(L, j, sc);
@@ -410,26 +390,14 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                     }
                 }
             }
-            if (!SCORE_ONLY) {
 #pragma unroll
-                for (int w = 0; w < WPS; ++w)
-                    *reinterpret_cast<uint4 *>(tr + (((size_t)(t0 / PB_TCHUNK) * WPS + w) * 32 + lane) * PB_TCHUNK) = acc[w];
-            }
+            for (int w = 0; w < WPS; ++w)
+                *reinterpret_cast<uint4 *>(tr + (((size_t)(t0 / PB_TCHUNK) * WPS + w) * 32 + lane) * PB_TCHUNK) = acc[w];
         }
         // scout candidates -> shared scratch, then lanes g==0 / g==1 finish halves A / B
         cand[lane] = make_cand<R>(L, 0, sc);
         cand[32 + lane] = make_cand<R>(L, 1, sc);
         __syncwarp();
-        if (SCORE_ONLY) {
-            // first pass of the short two-pass scheme: the end cells of the slot's two alignments
-            if (g < 2) {
-                const int64_t ti = slot * 2 + g;
-                if (ti < n_tasks)
-                    ends[ti] = scout_combine(cand + g * 32 + grp * G, G, g ? make_geom(nB, mB, G, R) : make_geom(nA, mA, G, R));
-            }
-            __syncwarp();
-            continue;
-        }
 #ifndef PB_EXPERIMENT_SKIP_TRACEBACK   // (profiling experiments only: measure the forward pass alone)
         if (g < 2) {
             const int h = g;
@@ -460,11 +428,6 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                     return (w >> trace_shift<R>(h, r)) & 15u;
                 };
                 auto eq = [&](int jl, int i) -> bool {   // the slot's staged column words are still in hbuf
-                    if (PPROF) {
-                        const uint32_t pair = hbuf[jl - 1] / (uint32_t)PSTRIDE;
-                        return ((h ? pair % 6u : pair / 6u) << 4) == (uint32_t)__ldg(ad + i - 1);
-                    }
-                    if (GPROF) return ((hbuf[jl - 1] / (uint32_t)PSTRIDE) << 4) == (uint32_t)__ldg(ad + i - 1);
                     return ((hbuf[jl - 1] >> (8 + 16 * h)) & 0xFFu) == (uint32_t)__ldg(ad + i - 1);
                 };
                 int32_t rec[PB_REC];
@@ -485,15 +448,10 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
     }
 }
 
-#undef PB_TRACE_STEP
-
 // ---------------------------------------------------------------------------------------------------
 // score_kernel: streaming score-only pass for long reads.  Same wavefront, no trace (7 instructions per row:
 // 3x VIADDMNMX, LOP3, VIADDMNMX-fused diagonal, VIMNMX, X update), exact scout.  Groups pull slots from a global
 // counter and refill independently, so a warp's groups never wait for each other's read lengths.
-// RO = row-offset domain (dp_core.cuh): the diagonal add is a plain 32-bit add on the FMA pipe, leaving 5 ALU-pipe
-// instructions per row (the ALU pipe is this kernel's bound) -- used whenever the row offsets fit the int16 domain.
-//
 // Read bases are streamed through a per-group shared-memory ring of packed columns (64 entries = two blocks of 32
 // columns).  A block is fetched with aligned 64/32-bit loads (funnel-shifted to the unaligned start) one block
 // ahead of its store, which is itself one block ahead of its use: the L2/HBM latency of the stream is never on the
@@ -537,7 +495,7 @@ template <int G, int R> struct ProfGeom {
     static constexpr int ROWS = G * R;
     static constexpr int STRIDE = 6 * ROWS + 16;        // words per group; +64 B so neighbouring groups start in other banks
 };
-template <int G, int R, bool RO, bool PROF = false>
+template <int G, int R, bool PROF = false>
 __global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_SCORE_MIN_BLOCKS)
 score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
              const uint8_t *__restrict__ seq, const uint8_t *__restrict__ ads, Scoring sc, EndCell *__restrict__ ends) {
@@ -623,7 +581,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                         for (int b = 0; b < 6; ++b) {       // from the row operands lane_init has just set up: two 128-bit stores
                             uint32_t w[8];
 #pragma unroll
-                            for (int r = 0; r < 8; ++r) w[r] = profile_from(L.v2[r], L.sf2[r], (uint32_t)b, (uint32_t)b, sc);
+                            for (int r = 0; r < 8; ++r) w[r] = profile_from(L.v2[r], L.sf2[r], (uint32_t)b, sc);
                             uint4 *dst = reinterpret_cast<uint4 *>(myprof + b * ProfGeom<G, R>::ROWS);
                             dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
                             dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -660,9 +618,9 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                     const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + hx);
                     const uint4 p0 = pp[0], p1 = pp[1];
                     const uint32_t subs[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-                    lane_step<R, false, false, RO, true>(L, recvS, recvV, 0u, sc, nullptr, nullptr, subs);
+                    lane_step<R, false, false, true>(L, recvS, recvV, 0u, sc, nullptr, nullptr, subs);
                 } else {
-                    lane_step<R, false, false, RO>(L, recvS, recvV, hx, sc, nullptr);
+                    lane_step<R, false, false>(L, recvS, recvV, hx, sc, nullptr);
                 }
                 lane_track_lastrow<R>(L, j, sc);
                 ++t;
@@ -681,9 +639,9 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                         const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + h2);
                         const uint4 p0 = pp[0], p1 = pp[1];
                         const uint32_t subs[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-                        lane_step<R, false, true, RO, true>(L, recvS, recvV, 0u, sc, nullptr, vr, subs);
+                        lane_step<R, false, true, true>(L, recvS, recvV, 0u, sc, nullptr, vr, subs);
                     } else {
-                        lane_step<R, false, true, RO>(L, recvS, recvV, h2, sc, nullptr, vr);
+                        lane_step<R, false, true>(L, recvS, recvV, h2, sc, nullptr, vr);
                     }
                     if (j < nmin) lane_track_lastrow<R>(L, j, sc);
                     else lane_track_general<R>(L, g, j, gA, gB, vr, sc);

@@ -96,7 +96,7 @@ void run_trace_group(int G, const Half &A, const Half &B, const Scoring &sc, int
 
 // PROF: the query-profile variant of score_kernel -- per lane a table [6 base codes][R rows] of substitution operands built
 // with profile_word, the step fetches its R operands by the base code of the column (both halves read sequence A).
-template <int R, bool RO, bool PROF = false>
+template <int R, bool PROF = false>
 void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, EndCell *eA, EndCell *eB) {
     const Task &tA = A.t, &tB = B.t;
     HalfGeom gA = make_geom(tA.n, tA.m, G, R), gB = make_geom(tB.n, tB.m, G, R);
@@ -128,11 +128,11 @@ void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, End
                 if (j > tB.n) bB = PB_PAD_H;
                 const uint32_t *subs = PROF ? &prof[((size_t)g * 6 + (bA >> 4)) * R] : nullptr;    // kernel: ring holds (bA >> 4) * ROWS
                 if (j < nmin) {
-                    lane_step<R, false, false, RO, PROF>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, nullptr, subs);
+                    lane_step<R, false, false, PROF>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, nullptr, subs);
                     lane_track_lastrow<R>(L[g], j, sc);
                 } else {
                     uint32_t vr[R];
-                    lane_step<R, false, true, RO, PROF>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, vr, subs);
+                    lane_step<R, false, true, PROF>(L[g], recvS, recvV, (bA << 8) | (bB << 24), sc, nullptr, vr, subs);
                     lane_track_general<R>(L[g], g, j, gA, gB, vr, sc);
                 }
             }
@@ -174,8 +174,8 @@ void to_window(Task &t, const EndCell &e, int wnum, int wden, bool tight) {
 
 extern "C" {
 
-// mode 0: single trace pass; mode 1 / 2: score pass (classic / row-offset domain) + windowed trace pass
-// (W = m + m*wnum/wden); mode | 4: the windows use the per-alignment bound (dp_core.cuh window_cols, tight).
+// mode 0: single trace pass; mode 1: score pass + windowed trace pass (W = m + m*wnum/wden); mode | 4: the windows use the
+// per-alignment bound (dp_core.cuh window_cols, tight); mode | 8: query-profile score pass (R = 8).
 // G in {4,8,16,32}, R in {4..8}; pass nB < 0 to leave half B empty.  Returns the status bit (window violated).
 int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char *seqB, int nB, const char *adB, int mB,
                    int G, int R, int mode, int ma, int mi, int go, int ge, int wnum, int wden, int32_t *recA,
@@ -189,27 +189,15 @@ int emu_align_slot(const char *seqA, int nA, const char *adA, int mA, const char
     mode &= 3;
     if (mode >= 1) {
         EndCell eA, eB;
-        // mode 1: classic score pass; mode 2: row-offset domain (plain-add diagonal), the engine's default when the
-        // offsets fit the int16 domain
-        const Scoring so = make_scoring(ma, mi, go, ge, mode == 2);
         if (prof && R == 8) {
-            if (mode == 2) run_score_group<8, true, true>(G, A, B, so, &eA, &eB);
-            else run_score_group<8, false, true>(G, A, B, so, &eA, &eB);
-        } else if (mode == 2) {
-            switch (R) {
-                case 5: run_score_group<5, true>(G, A, B, so, &eA, &eB); break;
-                case 6: run_score_group<6, true>(G, A, B, so, &eA, &eB); break;
-                case 7: run_score_group<7, true>(G, A, B, so, &eA, &eB); break;
-                case 8: run_score_group<8, true>(G, A, B, so, &eA, &eB); break;
-                default: run_score_group<4, true>(G, A, B, so, &eA, &eB); break;
-            }
+            run_score_group<8, true>(G, A, B, sc, &eA, &eB);
         } else {
             switch (R) {
-                case 5: run_score_group<5, false>(G, A, B, so, &eA, &eB); break;
-                case 6: run_score_group<6, false>(G, A, B, so, &eA, &eB); break;
-                case 7: run_score_group<7, false>(G, A, B, so, &eA, &eB); break;
-                case 8: run_score_group<8, false>(G, A, B, so, &eA, &eB); break;
-                default: run_score_group<4, false>(G, A, B, so, &eA, &eB); break;
+                case 5: run_score_group<5>(G, A, B, sc, &eA, &eB); break;
+                case 6: run_score_group<6>(G, A, B, sc, &eA, &eB); break;
+                case 7: run_score_group<7>(G, A, B, sc, &eA, &eB); break;
+                case 8: run_score_group<8>(G, A, B, sc, &eA, &eB); break;
+                default: run_score_group<4>(G, A, B, sc, &eA, &eB); break;
             }
         }
         to_window(A.t, eA, wnum, wden, tight);

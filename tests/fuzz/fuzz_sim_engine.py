@@ -22,7 +22,7 @@ from test_emulation import _gen, _mut, SCHEMES      # noqa: E402
 seed, seconds = int(sys.argv[1]), float(sys.argv[2])
 rng = random.Random(seed)
 W = sim_engine.load()
-DEFAULTS = {'h2d_pack': 0, 'tight_window': 0, 'short2p': 0, 'profile': 0, 'rowoff': 0, 'direct_max': 512, 'chunk_tasks': 131072,
+DEFAULTS = {'h2d_pack': 0, 'tight_window': 1, 'profile': 1, 'direct_max': 512, 'chunk_tasks': 131072,
             'scratch_mb': 128, 'hbuf': 'auto'}
 
 
@@ -65,7 +65,7 @@ while time.time() - t0 < seconds:
     iters += 1
     sc = rand_scheme()
     opts = {}
-    for k, vals in (('h2d_pack', [1]), ('tight_window', [1]), ('short2p', [1]), ('profile', [1]), ('rowoff', [1]),
+    for k, vals in (('h2d_pack', [1]), ('tight_window', [0]), ('profile', [0]),
                     ('direct_max', [50, 100, 300, 100000]), ('chunk_tasks', [1, 7, 40, 300]), ('scratch_mb', [1]),
                     ('hbuf', ['global', 'smem'])):
         if rng.random() < 0.3:

@@ -20,14 +20,14 @@ sbuf, soff = wl.windows_to_batch(sw); abuf, aoff = wl.pack_adapters([yt])
 def run(opts, fn, label):
     for k,v in opts.items(): W.set_option(k,v)
     got, exp = fn()
-    for k in opts: W.set_option(k, 'auto' if k=='hbuf' else (512 if k=='direct_max' else (131072 if k=='chunk_tasks' else 0)))
+    for k in opts: W.set_option(k, 'auto' if k=='hbuf' else (512 if k=='direct_max' else (131072 if k=='chunk_tasks' else (1 if k in ('profile','tight_window') else 0))))
     print(label, opts, 'equal' if np.array_equal(got, exp) else 'DIFFERENT', flush=True)
 f = lambda: (W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING), oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
-for opts in ({}, {'short2p':1,'tight_window':1}, {'profile':1}, {'profile':1,'short2p':1,'tight_window':1}, {'h2d_pack':1,'chunk_tasks':100}, {'hbuf':'global'}):
+for opts in ({}, {'direct_max':100}, {'direct_max':100,'tight_window':0}, {'h2d_pack':1,'chunk_tasks':100}, {'hbuf':'global'}):
     run(opts, f, 'windows')
 buf, off = wl.synth_reads(5, yt, yb, seed=2, chimera_p=0.5, max_len=3000); a2, o2 = wl.pack_adapters([yt, yb])
 g = lambda: (W.adapter_alignment_batch(buf, off, a2, o2, wl.DEFAULT_SCORING), oracle_batch(buf, off, a2, o2, wl.DEFAULT_SCORING))
-for opts in ({}, {'profile':1,'tight_window':1}, {'rowoff':1}, {'direct_max':100000,'hbuf':'global'}):
+for opts in ({}, {'profile':0,'tight_window':0}, {'profile':0}, {'direct_max':100000,'hbuf':'global'}):
     run(opts, g, 'long')
 starts, ends = wl.demux_adapters()
 _, sw2, _ = wl.synth_end_windows(9, starts[5], ends[5], seed=5)

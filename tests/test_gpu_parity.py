@@ -160,8 +160,9 @@ def test_read_length_sweep_barcodes(W):
     assert np.array_equal(got, oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
 
 
-def test_score_pass_classic_domain_option(W):
-    """The score pass has two arithmetic domains (classic = default, row-offset = option "rowoff"): same records."""
+def test_score_pass_with_and_without_query_profile(W):
+    """The score pass has two substitution paths (query profile = default for same-read slots, computed operands = option
+    profile=0, odd classes, pair lists) and two window bounds (per-alignment = default, per-adapter): same records."""
     from porechop_b200 import workloads as wl
     yt, yb = wl.nsk007()
     buf, off = wl.synth_reads(60, yt, yb, seed=31, chimera_p=0.3, max_len=9000)
@@ -169,15 +170,18 @@ def test_score_pass_classic_domain_option(W):
     exp = oracle_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
     got0 = W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
     try:
-        W.set_option('rowoff', 1)
+        W.set_option('profile', 0)
         got1 = W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
-        # a scheme whose offsets do not fit (large mismatch penalty) silently takes the classic domain
+        W.set_option('tight_window', 0)
+        got2 = W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
+        # a large mismatch penalty (still inside the int16 domain)
         sc = [3, -120, -5, -2]
-        got2 = W.adapter_alignment_batch(buf, off, abuf, aoff, sc)
+        got3 = W.adapter_alignment_batch(buf, off, abuf, aoff, sc)
     finally:
-        W.set_option('rowoff', 0)
-    assert np.array_equal(got0, exp) and np.array_equal(got1, exp)
-    assert np.array_equal(got2, oracle_batch(buf, off, abuf, aoff, sc))
+        W.set_option('profile', 1)
+        W.set_option('tight_window', 1)
+    assert np.array_equal(got0, exp) and np.array_equal(got1, exp) and np.array_equal(got2, exp)
+    assert np.array_equal(got3, oracle_batch(buf, off, abuf, aoff, sc))
 
 
 def test_generic_int32_path(W):

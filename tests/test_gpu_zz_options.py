@@ -1,7 +1,7 @@
-"""GPU tier (pytest -m gpu), opt-in engine options added after the round-1 GPU budget was spent -- their arithmetic is
-covered on the CPU tier (tests/test_emulation.py::test_emu_tight_window_bound_vs_oracle,
-tests/test_host_logic.py::test_packed_upload_path_host_pack_and_device_unpack_equal_encode); these tests are their first
-runs on hardware.  Both options are OFF by default and must not change a single record.  The file sorts last on purpose."""
+"""GPU tier (pytest -m gpu): engine options and the entry points beyond the plain batch call -- packed upload (h2d_pack),
+window bounds (tight_window on / off), query profile of the score pass (profile on / off), global staging (hbuf), the multi
+submit, device decisions, error paths.  No option may change a single record.  (Round 2 measured every opt-in path of
+round 1 on B200 and removed the ones that did not win: profiles/r2_options.)  The file sorts last on purpose."""
 import random
 
 import numpy as np
@@ -20,7 +20,7 @@ def W():
 
 
 def _with(W, opts, fn):
-    defaults = {'hbuf': 'auto', 'h2d_pack': 0, 'tight_window': 0, 'short2p': 0, 'profile': 0, 'rowoff': 0, 'direct_max': 512, 'chunk_tasks': 131072, 'pack_threads': 8}
+    defaults = {'hbuf': 'auto', 'h2d_pack': 0, 'tight_window': 1, 'profile': 1, 'direct_max': 512, 'chunk_tasks': 131072, 'pack_threads': 8}
     try:
         for k, v in opts.items():
             W.set_option(k, v)
@@ -54,7 +54,8 @@ def test_packed_upload_windows_ragged_and_long_reads(W):
 
 
 def test_tight_window_long_reads_and_forced_two_pass_windows(W):
-    """tight_window: second-pass windows sized from the end cell's row and score (dp_core.cuh window_cols).  Long reads
+    """tight_window (default) and the per-adapter bound (tight_window=0): second-pass windows sized from the end cell's row
+    and score (dp_core.cuh window_cols) or from the adapter length alone.  Long reads
     with 22 / 28 / 111-nt adapters, a masked re-alignment round, cheap-gap schemes, and 150-column windows forced
     through the two-pass path (direct_max = 100) -- identical to the oracle, and to the default windows."""
     from porechop_b200 import workloads as wl
@@ -64,22 +65,23 @@ def test_tight_window_long_reads_and_forced_two_pass_windows(W):
     abuf, aoff = wl.pack_adapters([yt, yb, full])
     for sc in (wl.DEFAULT_SCORING, (5, -4, -8, -1), (3, -6, -5, -5)):
         exp = oracle_batch(buf, off, abuf, aoff, sc)
-        got = _with(W, {'tight_window': 1}, lambda: W.adapter_alignment_batch(buf, off, abuf, aoff, sc))
-        assert np.array_equal(got, exp), sc
+        for opts in ({}, {'tight_window': 0}):
+            got = _with(W, opts, lambda: W.adapter_alignment_batch(buf, off, abuf, aoff, sc))
+            assert np.array_equal(got, exp), (sc, opts)
     masked = buf.copy()
     recs = exp.reshape(80, 3, 9)
     for r in range(80):
         rs, re_ = recs[r, 0, 0], recs[r, 0, 1] + 1
         if rs >= 0:
             masked[off[r] + rs: off[r] + re_] = ord('-')
-    got = _with(W, {'tight_window': 1}, lambda: W.adapter_alignment_batch(masked, off, abuf, aoff, (3, -6, -5, -5)))
+    got = W.adapter_alignment_batch(masked, off, abuf, aoff, (3, -6, -5, -5))
     assert np.array_equal(got, oracle_batch(masked, off, abuf, aoff, (3, -6, -5, -5)))
     _, sw, ew = wl.synth_end_windows(20000, yt, yb, seed=9)
     for win, ad in ((sw, yt), (ew, yb)):
         sbuf, soff = wl.windows_to_batch(win)
         a1, o1 = wl.pack_adapters([ad])
         exp = oracle_batch(sbuf, soff, a1, o1, wl.DEFAULT_SCORING)
-        for opts in ({'direct_max': 100}, {'direct_max': 100, 'tight_window': 1}):
+        for opts in ({'direct_max': 100}, {'direct_max': 100, 'tight_window': 0}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, a1, o1, wl.DEFAULT_SCORING))
             assert np.array_equal(got, exp), opts
 
@@ -110,45 +112,9 @@ def test_multi_batch_submit_equals_single_calls(W):
         b = batches[k]
         assert np.array_equal(got[k], oracle_batch(b[0], b[1], b[2], b[3], wl.DEFAULT_SCORING)), k
     # all options together
-    got2 = _with(W, {'h2d_pack': 1, 'tight_window': 1}, lambda: W.adapter_alignment_batch_multi(batches, wl.DEFAULT_SCORING))
+    got2 = _with(W, {'h2d_pack': 1, 'tight_window': 0}, lambda: W.adapter_alignment_batch_multi(batches, wl.DEFAULT_SCORING))
     for a, b in zip(got, got2):
         assert np.array_equal(a, b)
-
-
-def test_short_two_pass_windows_equal_oracle(W):
-    """short2p: 150-column windows go score-only sweep (trace_kernel<.., SCORE_ONLY>) -> bounded windows -> trace pass.
-    End-trim windows, the demux cross product (all 356 adapters: every row-capacity class, paired and odd adapters),
-    ragged / empty / non-ACGT inputs, classic and per-alignment (tight) windows, several scoring schemes."""
-    from porechop_b200 import workloads as wl
-    yt, yb = wl.nsk007()
-    _, sw, ew = wl.synth_end_windows(40000, yt, yb, seed=19)
-    for win, ad in ((sw, yt), (ew, yb)):
-        sbuf, soff = wl.windows_to_batch(win)
-        a1, o1 = wl.pack_adapters([ad])
-        exp = oracle_batch(sbuf, soff, a1, o1, wl.DEFAULT_SCORING)
-        for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}):
-            got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, a1, o1, wl.DEFAULT_SCORING))
-            assert np.array_equal(got, exp), opts
-    starts, ends = wl.demux_adapters()
-    _, sw, ew = wl.synth_end_windows(200, starts[5], ends[5], seed=6)
-    for win, ads in ((sw, starts), (ew, ends)):
-        sbuf, soff = wl.windows_to_batch(win)
-        abuf, aoff = wl.pack_adapters(ads)
-        exp = oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
-        got = _with(W, {'short2p': 1, 'tight_window': 1},
-                    lambda: W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
-        assert np.array_equal(got, exp)
-    rng = random.Random(17)
-    reads = ['', 'A', 'N' * 120, '-' * 130, 'acgu' * 40, yt, 'GG' + yt + 'GG', 'ACGT' * 100]
-    reads += [''.join(rng.choice('ACGTN') for _ in range(rng.randint(1, 500))) for _ in range(300)]
-    ads = ['', 'A', yt, yb, 'ACGT' * 10, 'N' * 5, 'ACGT' * 30]
-    rbuf, roff = W.pack_sequences(reads)
-    abuf, aoff = W.pack_sequences(ads, offset_dtype=np.int32)
-    for sc in ([3, -6, -5, -2], [3, -6, -5, -5], [5, -4, -8, -1]):
-        exp = oracle_batch(rbuf, roff, abuf, aoff, sc)
-        for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}):
-            got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
-            assert np.array_equal(got, exp), (sc, opts)
 
 
 def test_end_decisions_on_device_equal_host_rule(W):
@@ -222,8 +188,8 @@ def test_bad_sequence_offsets_fail_cleanly_mid_pipeline(W):
 
 
 def test_query_profile_score_pass_equals_oracle(W):
-    """profile: score_kernel<.., PROF> (substitution operands from a shared-memory query profile) for classes with an even
-    number of adapters, the classic kernel for the others in the same call; with the row-offset domain and tight windows;
+    """profile (default): score_kernel<.., PROF> (substitution operands from a shared-memory query profile) for classes with
+    an even number of adapters, the computed-operand kernel for the others in the same call; both window bounds;
     ragged lengths incl. reads shorter than a segment; a masked re-alignment round through the pair list (classic path)."""
     from porechop_b200 import workloads as wl
     yt, yb = wl.nsk007()
@@ -239,25 +205,16 @@ def test_query_profile_score_pass_equals_oracle(W):
         abuf, aoff = wl.pack_adapters(ads)
         for sc in (wl.DEFAULT_SCORING, (3, -6, -5, -5)):
             exp = oracle_batch(buf2, off2, abuf, aoff, sc)
-            for opts in ({'profile': 1}, {'profile': 1, 'rowoff': 1, 'tight_window': 1}):
+            for opts in ({}, {'profile': 0}, {'tight_window': 0}):
                 got = _with(W, opts, lambda: W.adapter_alignment_batch(buf2, off2, abuf, aoff, sc))
                 assert np.array_equal(got, exp), (len(ads), sc, opts)
 
 
-def test_pair_profile_trace_kernel_equals_oracle(W):
-    """profile on end windows: trace_kernel<.., PPROF> (block-wide table of substitution operands indexed by the base pair)
-    for classes with one adapter (two reads per slot) and two adapters (one read per slot); single pass, short two-pass with
-    tight windows, global staging; ragged / empty inputs; the config-1 shape at several pipeline chunks."""
+def test_small_and_odd_classes_ragged_inputs_both_stagings(W):
+    """Classes with one adapter (two reads per slot), two adapters (one read per slot), odd classes, an empty adapter, the
+    whole demux cross product; ragged / empty / non-ACGT reads; shared-memory and global staging; forced two-pass."""
     from porechop_b200 import workloads as wl
     yt, yb = wl.nsk007()
-    _, sw, ew = wl.synth_end_windows(30001, yt, yb, seed=29)
-    for win, ads in ((sw, [yt]), (ew, [yb]), (sw, [yt, yb])):
-        sbuf, soff = wl.windows_to_batch(win)
-        abuf, aoff = wl.pack_adapters(ads)
-        exp = oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
-        for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1, 'chunk_tasks': 9000}, {'profile': 1, 'hbuf': 'global'}):
-            got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
-            assert np.array_equal(got, exp), (len(ads), opts)
     rng = random.Random(31)
     reads = ['', 'A', 'N' * 120, '-' * 130, 'acgu' * 40, yt, 'GG' + yt + 'GG', 'ACGT' * 100]
     reads += [''.join(rng.choice('ACGTN') for _ in range(rng.randint(1, 500))) for _ in range(300)]
@@ -266,31 +223,25 @@ def test_pair_profile_trace_kernel_equals_oracle(W):
         abuf, aoff = W.pack_sequences(ads, offset_dtype=np.int32)
         for sc in ([3, -6, -5, -2], [3, -6, -5, -5]):
             exp = oracle_batch(rbuf, roff, abuf, aoff, sc)
-            for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1, 'direct_max': 200}):
+            for opts in ({}, {'hbuf': 'global'}, {'direct_max': 200}, {'direct_max': 200, 'profile': 0}):
                 got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
                 assert np.array_equal(got, exp), (ads, sc, opts)
-
-
-def test_per_group_profile_demux_cross_product_equals_oracle(W):
-    """profile on multi-adapter classes: trace_kernel PMODE 2 (a profile per lane group, rebuilt per slot) for the paired
-    adapters, the pair profile for an odd class's last adapter (run_class_tasks splits the class); the whole demux cross
-    product (227 start / 129 end sequences), small odd and even sets, long reads with an odd number of adapters."""
-    from porechop_b200 import workloads as wl
-    yt, yb = wl.nsk007()
     starts, ends = wl.demux_adapters()
     _, sw, ew = wl.synth_end_windows(300, starts[5], ends[5], seed=6)
     for win, ads in ((sw, starts), (ew, ends), (sw, starts[:4]), (sw, starts[:5]), (ew, [yt, yb, starts[-1]])):
         sbuf, soff = wl.windows_to_batch(win)
         abuf, aoff = wl.pack_adapters(ads)
         exp = oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
-        for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1}, {'profile': 1, 'hbuf': 'global'}):
+        for opts in ({}, {'hbuf': 'global'}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
             assert np.array_equal(got, exp), (len(ads), opts)
     lbuf, loff = wl.synth_reads(30, yt, yb, seed=2, chimera_p=0.5, max_len=9000)
     for ads in ([yt, yb, starts[-1]], starts[:5], starts[:6]):
         abuf, aoff = wl.pack_adapters(ads)
-        got = _with(W, {'profile': 1, 'tight_window': 1}, lambda: W.adapter_alignment_batch(lbuf, loff, abuf, aoff, wl.DEFAULT_SCORING))
-        assert np.array_equal(got, oracle_batch(lbuf, loff, abuf, aoff, wl.DEFAULT_SCORING)), len(ads)
+        exp = oracle_batch(lbuf, loff, abuf, aoff, wl.DEFAULT_SCORING)
+        for opts in ({}, {'profile': 0}):
+            got = _with(W, opts, lambda: W.adapter_alignment_batch(lbuf, loff, abuf, aoff, wl.DEFAULT_SCORING))
+            assert np.array_equal(got, exp), (len(ads), opts)
 
 
 def test_global_staging_under_load_every_window_length_mod_4(W):
@@ -298,7 +249,7 @@ def test_global_staging_under_load_every_window_length_mod_4(W):
     stride must be a whole number of 128-byte lines for every window length -- discard.global.L2 needs aligned
     addresses and must not drop a neighbouring warp's staged bases (round-1 hardware failure at max_n = 150 with the
     stride rounded to 16 bytes only).  >= 30 000 uniform windows so every resident warp loops, window lengths
-    150 / 149 / 151 / 153 / 146 (all residues mod 4), with and without the pair profile, one and two adapters."""
+    150 / 149 / 151 / 153 / 146 (all residues mod 4), one and two adapters."""
     from porechop_b200 import workloads as wl
     yt, yb = wl.nsk007()
     _, sw, ew = wl.synth_end_windows(30011, yt, yb, seed=37)
@@ -308,6 +259,5 @@ def test_global_staging_under_load_every_window_length_mod_4(W):
         for ads in ([yt], [yt, yb]):
             abuf, aoff = wl.pack_adapters(ads)
             exp = oracle_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING)
-            for opts in ({'hbuf': 'global'}, {'hbuf': 'global', 'profile': 1}):
-                got = _with(W, opts, lambda: W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
-                assert np.array_equal(got, exp), (n_cols, len(ads), opts)
+            got = _with(W, {'hbuf': 'global'}, lambda: W.adapter_alignment_batch(sbuf, soff, abuf, aoff, wl.DEFAULT_SCORING))
+            assert np.array_equal(got, exp), (n_cols, len(ads))

@@ -102,25 +102,49 @@ def test_gather_records_gloo_world2():
 
 def test_bench_parity_gate_against_harness_answers():
     """bench.py's parity gate: harness answer strings vs records rendered by pb200FormatRecord.  Here the
-    records come from the oracle (no GPU in this tier); one record is then corrupted to see the gate fire."""
+    records come from the oracle (no GPU in this tier); one record is then corrupted to see the gate fire.  Also the CPU
+    baseline block (1 thread + thread / process sweep) and the identical `config` dicts of the two arms."""
     import sys
     sys.path.insert(0, ROOT)
     import bench
     from porechop_b200 import workloads as wl
     from porechop_b200 import cpp_function_wrappers as W
-    yt, yb = wl.nsk007()
-    L, sw, ew = wl.synth_end_windows(200, yt, yb, seed=7)
-    batches = [('start', wl.windows_to_batch(sw), [yt]), ('end', wl.windows_to_batch(ew), [yb])]
+    sys_argv, sys.argv = sys.argv, ['bench.py', '--reads', '200']
+    try:
+        args = bench.parse_args()
+    finally:
+        sys.argv = sys_argv
+    w = bench.make_workload('endtrim', args, 0, 1, True)
+    assert w.n == 200 and len(w.batches) == 2 and w.cells == 200 * 7500
+    assert w.config('weak') == bench.make_nominal_config('endtrim', args, True)
+    files = bench.HarnessFiles(w, [150, 150])
     answers = []
-    sec, reads, cells, kind = bench.run_reference_harness(batches, wl.DEFAULT_SCORING, 150, 2, answers)
-    assert len(answers) == 2 and len(answers[0]) == 150 and sec > 0
+    sec = files.run(2, 1, answers)
+    assert len(answers) == 2 and len(answers[0]) == 150 and sec > 0 and files.cells == 150 * 7500
+    assert files.run(1, 2) > 0                                   # forked worker processes, no answers
     recs = []
-    for name, (buf, off), ads in batches:
+    for name, buf, off, ads in w.batches:
         abuf, aoff = wl.pack_adapters(ads)
         recs.append(oracle_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING))
     assert bench.parity_gate(recs, answers, W.format_record) == {'checked': 300, 'mismatches': 0}
     recs[1][3, 1] += 1
     assert bench.parity_gate(recs, answers, W.format_record) == {'checked': 300, 'mismatches': 1}
+    cb, ans, sizes = bench.cpu_baseline(w, sample_reads=100, sweep=True)
+    assert cb['kind'] in ('reference', 'port') and cb['value'] > 0 and cb['one_thread']['value'] > 0 and len(cb['sweep']) >= 2
+    assert cb['host']['nproc'] and len(ans) == 2 and sizes == [100, 100]
+    # prefix consistency of the generators the reference arm relies on (same first reads for any batch size)
+    for name in ('middle', 'sweep'):
+        sys.argv = ['bench.py', '--config-reads', 'middle=300', '--sweep-bases', '60000', '--sweep-lengths', '500,2000']
+        try:
+            a2 = bench.parse_args()
+        finally:
+            sys.argv = sys_argv
+        full = bench.make_workload(name, a2, 0, 1, False)
+        part = bench.make_workload(name, a2, 0, 1, False, limit=7)
+        for (n1, b1, o1, _), (n2, b2, o2, _) in zip(full.batches, part.batches):
+            k = len(o2) - 1
+            assert k >= 1 and np.array_equal(o1[:k + 1], o2) and np.array_equal(b1[:o2[-1]], b2[:o2[-1]])
+        assert full.config('weak') == bench.make_nominal_config(name, a2, False)
 
 
 def test_packed_upload_path_host_pack_and_device_unpack_equal_encode():

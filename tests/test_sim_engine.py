@@ -18,7 +18,7 @@ from test_oracle import SURVEY_EDGE, rebuild_fullread_inputs
 
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'sim'))
 
-OPTION_DEFAULTS = {'h2d_pack': 0, 'tight_window': 0, 'short2p': 0, 'profile': 0, 'rowoff': 0, 'direct_max': 512,
+OPTION_DEFAULTS = {'h2d_pack': 0, 'tight_window': 1, 'profile': 1, 'direct_max': 512,
                    'chunk_tasks': 131072, 'pack_threads': 8, 'scratch_mb': 128, 'hbuf': 'auto'}
 
 
@@ -118,7 +118,7 @@ def test_sim_long_reads_two_pass_and_options(W):
         abuf, aoff = wl.pack_adapters(ads)
         for scheme in (wl.DEFAULT_SCORING, (3, -6, -5, -5)):
             exp = oracle_batch(buf, off, abuf, aoff, scheme)
-            for opts in ({}, {'tight_window': 1}, {'rowoff': 1}, {'profile': 1}, {'profile': 1, 'rowoff': 1, 'tight_window': 1},
+            for opts in ({}, {'tight_window': 0}, {'profile': 0}, {'profile': 0, 'tight_window': 0},
                          {'h2d_pack': 1, 'chunk_tasks': 10}):
                 got = _with(W, opts, lambda: W.adapter_alignment_batch(buf, off, abuf, aoff, scheme))
                 assert np.array_equal(got, exp), (len(ads), scheme, opts)
@@ -128,7 +128,7 @@ def test_sim_long_reads_two_pass_and_options(W):
     for L in (500, 2000, 6000):
         b5, f5 = wl.synth_fixed_length_reads(3, L, bcs, seed=L)
         exp = oracle_batch(b5, f5, a5, o5, wl.DEFAULT_SCORING)
-        for opts in ({}, {'profile': 1, 'tight_window': 1}):
+        for opts in ({}, {'profile': 0, 'tight_window': 0}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(b5, f5, a5, o5, wl.DEFAULT_SCORING))
             assert np.array_equal(got, exp), (L, opts)
     # one pass over multi-kb sequences with the bases staged in global scratch (no score pass)
@@ -137,24 +137,24 @@ def test_sim_long_reads_two_pass_and_options(W):
     assert np.array_equal(got, oracle_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING))
 
 
-def test_sim_short_two_pass_and_packed_upload(W):
-    """short2p (trace_kernel<.., SCORE_ONLY> -> windows -> trace) on end windows, the demux cross product and ragged inputs,
-    classic and tight windows; h2d_pack over several chunks."""
+def test_sim_forced_two_pass_windows_small_classes_and_packed_upload(W):
+    """150-column windows forced through the two-pass path (direct_max = 100: score pass -> bounded windows -> trace pass),
+    both window bounds; global staging; h2d_pack over several chunks; one- / two-adapter and odd classes on ragged inputs;
+    the demux cross product."""
     from porechop_b200 import workloads as wl
     yt, yb = wl.nsk007()
     (sb, so), (eb, eo) = _windows(1000, 19)
     for (buf, off), ad in (((sb, so), yt), ((eb, eo), yb)):
         abuf, aoff = wl.pack_adapters([ad])
         exp = oracle_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
-        for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}, {'direct_max': 100}, {'direct_max': 100, 'tight_window': 1},
-                     {'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1}, {'profile': 1, 'hbuf': 'global'},
-                     {'h2d_pack': 1, 'chunk_tasks': 300, 'pack_threads': 3}, {'short2p': 1, 'tight_window': 1, 'h2d_pack': 1}):
+        for opts in ({'direct_max': 100}, {'direct_max': 100, 'tight_window': 0}, {'hbuf': 'global'},
+                     {'h2d_pack': 1, 'chunk_tasks': 300, 'pack_threads': 3}, {'direct_max': 100, 'h2d_pack': 1}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING))
             assert np.array_equal(got, exp), opts
     starts, ends = wl.demux_adapters()
     (sb, so), _ = _windows(24, 6, (starts[5], ends[5]))
     abuf, aoff = wl.pack_adapters(starts)
-    got = _with(W, {'short2p': 1, 'tight_window': 1}, lambda: W.adapter_alignment_batch(sb, so, abuf, aoff, wl.DEFAULT_SCORING))
+    got = W.adapter_alignment_batch(sb, so, abuf, aoff, wl.DEFAULT_SCORING)
     assert np.array_equal(got, oracle_batch(sb, so, abuf, aoff, wl.DEFAULT_SCORING))
     rng = random.Random(17)
     reads = ['', 'A', 'N' * 120, '-' * 130, 'acgu' * 40, yt, 'GG' + yt + 'GG', 'ACGT' * 100]
@@ -164,25 +164,21 @@ def test_sim_short_two_pass_and_packed_upload(W):
     abuf, aoff = W.pack_sequences(ads, offset_dtype=np.int32)
     for sc in ([3, -6, -5, -2], [3, -6, -5, -5], [5, -4, -8, -1]):
         exp = oracle_batch(rbuf, roff, abuf, aoff, sc)
-        for opts in ({'short2p': 1}, {'short2p': 1, 'tight_window': 1}, {'profile': 1, 'short2p': 1}):
+        for opts in ({}, {'direct_max': 120}, {'direct_max': 120, 'profile': 0}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
             assert np.array_equal(got, exp), (sc, opts)
-    # per-group profile (trace_kernel PMODE 2) and the odd-class split: the demux cross product and small odd / even sets
-    starts, ends = wl.demux_adapters()
     (sb5, so5), _ = _windows(12, 6, (starts[5], ends[5]))
-    for ads in (starts, ends[:40], starts[:4], starts[:5], [yt, yb, starts[-1]]):
+    for ads in (ends[:40], starts[:4], starts[:5], [yt, yb, starts[-1]]):
         abuf, aoff = wl.pack_adapters(ads)
         exp = oracle_batch(sb5, so5, abuf, aoff, wl.DEFAULT_SCORING)
-        for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1}):
+        for opts in ({}, {'direct_max': 100}):
             got = _with(W, opts, lambda: W.adapter_alignment_batch(sb5, so5, abuf, aoff, wl.DEFAULT_SCORING))
             assert np.array_equal(got, exp), (len(ads), opts)
-    # pair profile (trace_kernel<.., PPROF>): classes with one adapter (two reads per slot, odd number of reads) and with
-    # two adapters (one read per slot), every row class up to 64 rows, ragged reads, empty adapter / empty reads
     for ads in (['ACGT' * 5], [yt], [yt, yb], ['ACGTTGCA' * 5, 'TTGACCA' * 5], ['ACGT' * 16], [yt, ''], ['N' * 22]):
         abuf, aoff = W.pack_sequences(ads, offset_dtype=np.int32)
         for sc in ([3, -6, -5, -2], [3, -6, -5, -5]):
             exp = oracle_batch(rbuf, roff, abuf, aoff, sc)
-            for opts in ({'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1, 'direct_max': 200}):
+            for opts in ({}, {'direct_max': 200}):
                 got = _with(W, opts, lambda: W.adapter_alignment_batch(rbuf, roff, abuf, aoff, sc))
                 assert np.array_equal(got, exp), (ads, sc, opts)
 
@@ -199,7 +195,7 @@ def test_sim_multi_submit_and_device_resident_api(W):
                (np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int64)) + wl.pack_adapters([yt]),
                (eb2, eo2) + wl.pack_adapters(ends[:13]), (lbuf, loff) + wl.pack_adapters([yt, yb]),
                (sb2, so2) + wl.pack_adapters(starts[40:47])]
-    for opts in ({'chunk_tasks': 500}, {'chunk_tasks': 500, 'h2d_pack': 1, 'tight_window': 1, 'short2p': 1, 'profile': 1}):
+    for opts in ({'chunk_tasks': 500}, {'chunk_tasks': 500, 'h2d_pack': 1, 'tight_window': 0, 'profile': 0}):
         got = _with(W, opts, lambda: W.adapter_alignment_batch_multi(batches, wl.DEFAULT_SCORING))
         for b, g in zip(batches, got):
             assert np.array_equal(g, oracle_batch(b[0], b[1], b[2], b[3], wl.DEFAULT_SCORING)), opts
@@ -241,7 +237,7 @@ def test_sim_end_decisions_and_flat_pipeline(W, monkeypatch):
     erec = W.adapter_alignment_batch(eb, eo, ea, eao, wl.DEFAULT_SCORING).reshape(-1, len(ads_e), 9)
     scols, ecols = [2, 0, 5, 2], [1]
     for end_size, extra, thr, min_trim, opts in ((150, 2, 75.0, 4, {}), (150, 0, 90.0, 1, {'chunk_tasks': 900}),
-                                                 (150, 5, 50.0, 10, {'h2d_pack': 1, 'short2p': 1, 'tight_window': 1})):
+                                                 (150, 5, 50.0, 10, {'h2d_pack': 1})):
         outs = _with(W, opts, lambda: W.adapter_end_decisions(
             [(sb, so, sa, sao, True, scols), (eb, eo, ea, eao, False, ecols)], wl.DEFAULT_SCORING, end_size, extra, thr,
             min_trim, want_records=True))
@@ -271,20 +267,21 @@ def test_sim_end_decisions_and_flat_pipeline(W, monkeypatch):
 GPU_PARITY = ['test_legacy_single_call_strings', 'test_golden_random_pair_list', 'test_golden_windows_cross',
               'test_golden_fullread_two_pass', 'test_synthetic_windows_vs_oracle', 'test_demux_cross_all_adapters_vs_oracle',
               'test_ragged_and_edge_inputs', 'test_long_reads_two_pass_vs_oracle', 'test_read_length_sweep_barcodes',
-              'test_score_pass_classic_domain_option', 'test_generic_int32_path', 'test_single_pass_long_windows_and_global_staging']
+              'test_score_pass_with_and_without_query_profile', 'test_generic_int32_path', 'test_single_pass_long_windows_and_global_staging']
 GPU_OPTIONS = ['test_packed_upload_windows_ragged_and_long_reads', 'test_tight_window_long_reads_and_forced_two_pass_windows',
-               'test_multi_batch_submit_equals_single_calls', 'test_short_two_pass_windows_equal_oracle',
+               'test_multi_batch_submit_equals_single_calls',
                'test_end_decisions_on_device_equal_host_rule', 'test_bad_sequence_offsets_fail_cleanly_mid_pipeline',
-               'test_query_profile_score_pass_equals_oracle', 'test_pair_profile_trace_kernel_equals_oracle', 'test_per_group_profile_demux_cross_product_equals_oracle']
+               'test_query_profile_score_pass_equals_oracle', 'test_small_and_odd_classes_ragged_inputs_both_stagings',
+               'test_global_staging_under_load_every_window_length_mod_4']
 
 
 # the larger ones take minutes in the simulation (10 min for all): run with PB200_SIM_FULL=1; the dedicated tests above
 # cover the same paths at smaller sizes.  Round 1, final build: all 33 tests of this file pass with PB200_SIM_FULL=1
 # PB200_SIM_ASAN=1 (915 s).
 SLOW = {'test_demux_cross_all_adapters_vs_oracle', 'test_multi_batch_submit_equals_single_calls',
-        'test_short_two_pass_windows_equal_oracle', 'test_end_decisions_on_device_equal_host_rule',
+        'test_end_decisions_on_device_equal_host_rule',
         'test_bad_sequence_offsets_fail_cleanly_mid_pipeline', 'test_query_profile_score_pass_equals_oracle',
-        'test_pair_profile_trace_kernel_equals_oracle', 'test_per_group_profile_demux_cross_product_equals_oracle'}
+        'test_small_and_odd_classes_ragged_inputs_both_stagings', 'test_global_staging_under_load_every_window_length_mod_4'}
 FULL = os.environ.get('PB200_SIM_FULL', '0') == '1'
 
 

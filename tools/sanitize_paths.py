@@ -16,7 +16,7 @@ import numpy as np                                  # noqa: E402
 from helpers import oracle_batch                    # noqa: E402
 from porechop_b200 import cpp_function_wrappers as W, workloads as wl    # noqa: E402
 
-DEFAULTS = {'h2d_pack': 0, 'tight_window': 0, 'short2p': 0, 'profile': 0, 'rowoff': 0, 'direct_max': 512, 'chunk_tasks': 131072,
+DEFAULTS = {'h2d_pack': 0, 'tight_window': 1, 'profile': 1, 'direct_max': 512, 'chunk_tasks': 131072,
             'hbuf': 'auto'}
 yt, yb = wl.nsk007()
 _, sw, ew = wl.synth_end_windows(600, yt, yb, seed=1)
@@ -46,16 +46,16 @@ def cross(buf, off, ab, ao):
     return lambda: (W.adapter_alignment_batch(buf, off, ab, ao, wl.DEFAULT_SCORING), oracle_batch(buf, off, ab, ao, wl.DEFAULT_SCORING))
 
 
-for opts in ({}, {'short2p': 1, 'tight_window': 1}, {'profile': 1}, {'profile': 1, 'short2p': 1, 'tight_window': 1},
-             {'h2d_pack': 1, 'chunk_tasks': 200}, {'hbuf': 'global'}):
+for opts in ({}, {'direct_max': 100}, {'direct_max': 100, 'tight_window': 0}, {'h2d_pack': 1, 'chunk_tasks': 200},
+             {'hbuf': 'global'}):
     run('windows', opts, cross(sbuf, soff, a1, o1))
     run('windows2', opts, cross(sbuf, soff, a2, o2))
-for opts in ({}, {'profile': 1, 'tight_window': 1}, {'profile': 1, 'rowoff': 1}, {'direct_max': 100000, 'hbuf': 'global'}):
+for opts in ({}, {'profile': 0, 'tight_window': 0}, {'profile': 0}, {'direct_max': 100000, 'hbuf': 'global'}):
     run('long', opts, cross(lbuf, loff, a2, o2))
 a3, o3 = wl.pack_adapters(starts)
 run('demux', {}, cross(sbuf[:150 * 12], soff[:13], a3, o3))
-run('demux', {'short2p': 1, 'tight_window': 1}, cross(sbuf[:150 * 12], soff[:13], a3, o3))
-run('demux', {'profile': 1, 'short2p': 1, 'tight_window': 1}, cross(sbuf[:150 * 12], soff[:13], a3, o3))
+run('demux', {'direct_max': 100}, cross(sbuf[:150 * 12], soff[:13], a3, o3))
+run('demux', {'hbuf': 'global'}, cross(sbuf[:150 * 12], soff[:13], a3, o3))
 outs = W.adapter_end_decisions([(sbuf, soff, a2, o2, True, [0, 1])], wl.DEFAULT_SCORING, 150, 2, 75.0, 4)
 print('decisions', outs[0][0][:6].tolist(), flush=True)
 got = W.adapter_alignment_batch_multi([(sbuf, soff, a1, o1), (lbuf, loff, a2, o2)], wl.DEFAULT_SCORING)
