@@ -210,11 +210,33 @@ def make_workload(name, args, rank, world, main, limit=None, alloc=None):
     return Workload(name, desc, n, nom, batches)
 
 
-def host_cores():
+def cgroup_cpu_limit():
+    """CPUs the cgroup lets this process use at once (cpu.max = "quota period", v1: cfs_quota_us / cfs_period_us), or None.
+    Round 2: the GPU boxes show nproc = 128 under a quota of 16 CPUs -- threads beyond the quota only get throttled."""
     try:
-        return len(os.sched_getaffinity(0))
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            q, p = f.read().split()[:2]
+        return None if q == 'max' else max(1, int(-(-int(q) // int(p))))
+    except (OSError, ValueError):
+        pass
+    try:
+        with open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us') as f:
+            q = int(f.read())
+        with open('/sys/fs/cgroup/cpu/cpu.cfs_period_us') as f:
+            p = int(f.read())
+        return None if q <= 0 else max(1, -(-q // p))
+    except (OSError, ValueError):
+        return None
+
+
+def host_cores():
+    """host cores this process can really use: the affinity mask, capped by the cgroup CPU quota"""
+    try:
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    lim = cgroup_cpu_limit()
+    return max(1, min(n, lim)) if lim else n
 
 
 def cpu_info():
@@ -234,7 +256,11 @@ def cpu_info():
                 break
         except OSError:
             pass
-    return {'model': model, 'nproc': os.cpu_count(), 'affinity': host_cores(), 'cgroup_cpu_max': quota}
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count()
+    return {'model': model, 'nproc': os.cpu_count(), 'affinity': aff, 'cgroup_cpu_max': quota, 'usable_cores': host_cores()}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -313,7 +339,8 @@ def cpu_baseline(workload, sample_reads=0, sweep=True, seconds=3.0, want_answers
         sec = files.run(cores, 1, answers)
         runs.append({'threads': cores, 'procs': 1, 'seconds': sec})
     if sweep and cores >= 4:
-        for t in sorted({max(1, cores // 4), max(1, cores // 2)}):
+        over = min(2 * cores, os.cpu_count() or cores)      # under a cgroup quota, 2x the quota was the best mode on the round-2 box
+        for t in sorted({max(1, cores // 2), over} - {cores}):
             runs.append({'threads': t, 'procs': 1, 'seconds': files.run(t)})
     if cores >= 2:
         # one process per core (separate heaps): the mode that does not depend on the allocator's arena behaviour; the side
@@ -729,7 +756,8 @@ def run_reference(args):
         files = HarnessFiles(w, sizes)
         cells_per_read = w.cells / max(w.n, 1)
         # mode: threads in one process vs one process per core (separate heaps), best of a warm-up pair
-        modes = [(cores, 1)] + ([(1, cores)] if cores >= 2 else [])
+        modes = [(cores, 1)] + ([(1, cores)] if cores >= 2 else []) + \
+                ([(min(2 * cores, os.cpu_count() or cores), 1)] if 2 * cores <= (os.cpu_count() or cores) else [])
         trial = {m: files.run(*m) for m in modes}
         mode = min(trial, key=trial.get)
         times = []

@@ -89,7 +89,15 @@ typedef struct {
     const int32_t *score_cols;        /* adapter indices whose full-adapter identity is wanted (may be NULL if none) */
     int32_t n_score_cols;
     int32_t *trim;                    /* out: n_seqs */
-    uint16_t *score_pairs;            /* out: n_seqs * n_score_cols * 2 */
+    uint16_t *score_pairs;            /* out: n_seqs * n_score_cols * 2; may be NULL when only top2 is wanted */
+    int32_t *top2;                    /* out, optional (NULL = not wanted): n_seqs * 6 = {position, matchAdapter, lenAdapter}
+                                       * of the best and of the second-best score column -- the first two entries of
+                                       * determine_barcode's `sorted(scores.items(), reverse=True, key=score)`
+                                       * (porechop/nanopore_read.py:404-415): highest full-adapter identity first, equal
+                                       * identities in score_cols order; `position` indexes score_cols (-1, 0, 1 when
+                                       * there are fewer columns).  The caller lists each barcode NAME once in score_cols
+                                       * (the reference's dict keeps a repeated name's last value).  24 bytes per read
+                                       * instead of 4*n_score_cols. */
 } pb200_end_batch_t;
 int adapterEndDecisions(const pb200_end_batch_t *batches, int n_batches, int matchScore, int mismatchScore,
                         int gapOpenScore, int gapExtensionScore);

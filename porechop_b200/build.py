@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         raise RuntimeError('g++ failed on hostpack.cpp:\n' + r.stdout + r.stderr)
     cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
            '-Xcompiler', '-fPIC', '-shared', '-o', TARGET] + os.environ.get('PB200_NVCC_FLAGS', '').split() + SOURCES + \
-          [obj] + (['-lgomp'] if omp else [])
+          [obj] + (['-lgomp'] if omp else []) + ['-ldl']
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')

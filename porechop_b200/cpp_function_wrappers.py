@@ -50,7 +50,7 @@ class EndBatchDesc(Structure):
     """pb200_end_batch_t (include/porechop_b200.h)"""
     _fields_ = [('batch', BatchDesc), ('is_start', c_int32), ('end_size', c_int32), ('extra_trim_size', c_int32),
                 ('min_trim_size', c_int32), ('end_threshold', c_double), ('score_cols', c_void_p), ('n_score_cols', c_int32),
-                ('trim', c_void_p), ('score_pairs', c_void_p)]
+                ('trim', c_void_p), ('score_pairs', c_void_p), ('top2', c_void_p)]
 
 
 C_LIB.adapterEndDecisions.argtypes = [POINTER(EndBatchDesc), c_int, c_int, c_int, c_int, c_int]
@@ -192,13 +192,16 @@ def adapter_alignment_batch_multi(batches, scoring_scheme_vals):
 
 
 def adapter_end_decisions(batches, scoring_scheme_vals, end_size, extra_trim_size, end_threshold, min_trim_size,
-                          want_records=False, out_arrays=None):
+                          want_records=False, out_arrays=None, want_top2=False):
     """
     End-trim decisions on the device (adapterEndDecisions): `batches` is a list of
     (seq_buf, seq_off, ad_buf, ad_off, is_start, score_cols) -- windows x adapters, which trim rule, and the adapter
     indices whose full-adapter identity the host still needs (barcode columns; may be empty).
     Returns one (trim int32[n], pairs uint16[n, n_cols, 2], records or None) per batch.
     out_arrays: optional preallocated [(trim, pairs, records-or-None), ...] (e.g. views of pinned memory) to write into.
+    want_top2: the barcode ranking stays on the device too -- the second element of every result is then int32[n, 6] =
+    (position in score_cols, match_ad, len_ad) of the best and the second-best score column (determine_barcode's sorted order:
+    identity descending, ties in score_cols order; position -1 = no such column) instead of the pairs of all columns.
     """
     descs = (EndBatchDesc * max(len(batches), 1))()
     keep, outs = [], []
@@ -211,11 +214,17 @@ def adapter_end_decisions(batches, scoring_scheme_vals, end_size, extra_trim_siz
         n_seqs, n_ad = len(seq_off) - 1, len(ad_off) - 1
         if out_arrays is not None:
             trim, pairs, rec = out_arrays[k]
-            assert trim.dtype == np.int32 and len(trim) == n_seqs and pairs.dtype == np.uint16 and \
-                pairs.shape == (n_seqs, len(cols), 2) and trim.flags.c_contiguous and pairs.flags.c_contiguous
+            assert trim.dtype == np.int32 and len(trim) == n_seqs and trim.flags.c_contiguous and pairs.flags.c_contiguous
+            if want_top2:
+                assert pairs.dtype == np.int32 and pairs.shape == (n_seqs, 6)
+            else:
+                assert pairs.dtype == np.uint16 and pairs.shape == (n_seqs, len(cols), 2)
         else:
             trim = np.zeros(n_seqs, dtype=np.int32)
-            pairs = np.zeros((n_seqs, len(cols), 2), dtype=np.uint16)
+            if want_top2:
+                pairs = np.tile(np.array([-1, 0, 1], dtype=np.int32), (n_seqs, 2))
+            else:
+                pairs = np.zeros((n_seqs, len(cols), 2), dtype=np.uint16)
             rec = np.empty((n_seqs * n_ad, RECORD_INTS), dtype=np.int32) if want_records else None
         keep.append((seq_buf, seq_off, ad_buf, ad_off, cols))
         outs.append((trim, pairs, rec))
@@ -223,7 +232,8 @@ def adapter_end_decisions(batches, scoring_scheme_vals, end_size, extra_trim_siz
                                           ad_off.ctypes.data, n_ad, rec.ctypes.data if rec is not None else None),
                                 1 if b[4] else 0, int(end_size), int(extra_trim_size), int(min_trim_size), float(end_threshold),
                                 cols.ctypes.data if len(cols) else None, len(cols), trim.ctypes.data,
-                                pairs.ctypes.data if len(cols) else None)
+                                pairs.ctypes.data if (len(cols) and not want_top2) else None,
+                                pairs.ctypes.data if (len(cols) and want_top2) else None)
     ma, mi, go, ge = [int(x) for x in scoring_scheme_vals]
     _check(C_LIB.adapterEndDecisions(descs, len(batches), ma, mi, go, ge))
     return outs

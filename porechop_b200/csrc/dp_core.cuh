@@ -223,9 +223,10 @@ struct Lane {
     uint32_t sf2[R];  // per-row mismatch operand (real rows: mi - go, pad rows: -go)
     uint32_t prevRecvX;  // X[j-1][top-1]  (diagonal input of the top row)
     uint32_t botX, botV; // X[j][bottom], Vs[j][bottom] -> shuffled to the next lane
-    // scout state: last-row running best (X domain), packed (meaningful in lane G-1 only) ...
-    uint32_t lrBest2;
-    int lrJ[2], lrCorr[2];
+    // scout state: last-row running best (X domain), packed, with the Vs / Hs of that cell (the end-cell correction flags
+    // are derived from them once, in make_cand) -- lane G-1 only: the other lanes start at +infinity and never update ...
+    uint32_t lrBest2, lrV2, lrH2;
+    int lrJ[2];
     // ... and the best of this lane's rows in the final column, per half (X domain, biased)
     int fcBest[2], fcI[2], fcCorr[2];
 };
@@ -273,9 +274,14 @@ PB_HD void lane_init(Lane<R> &L, int g, int G, const Scoring &sc, const uint8_t 
         L.prevRecvX = (((realA && leftInfA) ? xinf : x0) & 0xFFFFu) | (((realB && leftInfB) ? xinf : x0) & 0xFFFF0000u);
     }
     L.botX = L.X[R - 1]; L.botV = sc.negb2;
-    L.lrBest2 = sc.borderX2;   // candidate (0, m): S = 0
+    // candidate (0, m): S = 0, no correction.  Only the bottom row of lane G-1 is the last row: every other lane starts from
+    // +infinity, so its compare never fires and the scout branch of the step loops is taken for real candidates only
+    // (round 2, ncu source view: with all 32 lanes tracking their own bottom rows the "rare" branch ran in most steps and
+    // made up 14 % of the trace kernel's dynamic instructions).
+    L.lrBest2 = (g == G - 1) ? sc.borderX2 : 0x7FFF7FFFu;
+    L.lrV2 = sc.negb2; L.lrH2 = sc.negb2;
     for (int h = 0; h < 2; ++h) {
-        L.lrJ[h] = 0; L.lrCorr[h] = 0;
+        L.lrJ[h] = 0;
         L.fcBest[h] = -1; L.fcI[h] = 0; L.fcCorr[h] = 0;   // biased X values are >= 0
     }
 }
@@ -415,10 +421,11 @@ template <int R>
 PB_HD void lane_track_lastrow(Lane<R> &L, int j, const Scoring &sc) {
     bool plo, phi;
     const uint32_t nb = max2p(L.lrBest2, L.botX, plo, phi);     // p = (old best >= candidate): strict '>' replaces
+    (void)sc;
     if (!(plo && phi)) {
-        L.lrBest2 = nb;
-        if (!plo) { L.lrJ[0] = j; L.lrCorr[0] = corr_flags(half16(L.botX, 0), half16(L.botV, 0), half16(L.Hs[R - 1], 0), sc.goEff); }
-        if (!phi) { L.lrJ[1] = j; L.lrCorr[1] = corr_flags(half16(L.botX, 1), half16(L.botV, 1), half16(L.Hs[R - 1], 1), sc.goEff); }
+        L.lrBest2 = nb;          // the improved half of nb IS botX's half: only column, Vs and Hs remain to be noted
+        if (!plo) { L.lrJ[0] = j; L.lrV2 = (L.lrV2 & 0xFFFF0000u) | (L.botV & 0xFFFFu); L.lrH2 = (L.lrH2 & 0xFFFF0000u) | (L.Hs[R - 1] & 0xFFFFu); }
+        if (!phi) { L.lrJ[1] = j; L.lrV2 = (L.lrV2 & 0xFFFFu) | (L.botV & 0xFFFF0000u); L.lrH2 = (L.lrH2 & 0xFFFFu) | (L.Hs[R - 1] & 0xFFFF0000u); }
     }
 }
 
@@ -433,9 +440,11 @@ PB_HD void lane_track_general(Lane<R> &L, int g, int j, const HalfGeom &A, const
         if (j < H.n) {
             const int c = half16(L.botX, h);
             if (c > half16(L.lrBest2, h)) {
-                L.lrBest2 = h ? ((L.lrBest2 & 0xFFFFu) | (L.botX & 0xFFFF0000u)) : ((L.lrBest2 & 0xFFFF0000u) | (L.botX & 0xFFFFu));
+                const uint32_t keep = h ? 0xFFFFu : 0xFFFF0000u;
+                L.lrBest2 = (L.lrBest2 & keep) | (L.botX & ~keep);
+                L.lrV2 = (L.lrV2 & keep) | (L.botV & ~keep);
+                L.lrH2 = (L.lrH2 & keep) | (L.Hs[R - 1] & ~keep);
                 L.lrJ[h] = j;
-                L.lrCorr[h] = corr_flags(c, half16(L.botV, h), half16(L.Hs[R - 1], h), sc.goEff);
             }
         } else if (j == H.n) {
 #pragma unroll
@@ -461,7 +470,8 @@ PB_HD ScoutCand make_cand(const Lane<R> &L, int h, const Scoring &sc) {
     ScoutCand c;
     c.fcBest = L.fcBest[h] < 0 ? -0x40000000 : L.fcBest[h] - PB_BIAS - sc.goEff;
     c.fcI = L.fcI[h]; c.fcCorr = L.fcCorr[h];
-    c.lrBest = half16(L.lrBest2, h) - PB_BIAS - sc.goEff; c.lrJ = L.lrJ[h]; c.lrCorr = L.lrCorr[h];
+    c.lrBest = half16(L.lrBest2, h) - PB_BIAS - sc.goEff; c.lrJ = L.lrJ[h];
+    c.lrCorr = L.lrJ[h] > 0 ? corr_flags(half16(L.lrBest2, h), half16(L.lrV2, h), half16(L.lrH2, h), sc.goEff) : 0;
     return c;
 }
 PB_HD EndCell scout_combine(const ScoutCand *c, int G, const HalfGeom &H) {

@@ -26,6 +26,13 @@
 #include "../../include/porechop_b200.h"
 #include "kernels.cuh"
 
+// NVTX ranges around submit / H2D / DP / D2H (SURVEY 5 "tracing"): header-only NVTX3, a no-op unless a profiler is attached.
+// The host simulator (tests/sim) and -DPB_NO_NVTX build without it.
+#if defined(__CUDACC__) && !defined(PB_NO_NVTX)
+#include <nvtx3/nvToolsExt.h>
+#define PB_NVTX 1
+#endif
+
 using namespace pb;
 
 // hostpack.cpp (g++): ASCII -> two 4-bit Dna5 codes per byte on the host cores
@@ -38,6 +45,17 @@ std::atomic<long long> g_launches{0};
 std::atomic<int> g_timing{0};
 
 int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+struct NvtxRange {          // RAII range on the calling host thread
+#ifdef PB_NVTX
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+#else
+    explicit NvtxRange(const char *) {}
+#endif
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 #define CK(call)                                                                                     \
     do {                                                                                             \
@@ -102,7 +120,17 @@ void load_env_options() {
         if (g_opt.pack_threads <= 0) {
             // packer threads: the host's hardware threads shared by the ranks of this node (torchrun exports
             // LOCAL_WORLD_SIZE, and OMP_NUM_THREADS=1 -- which would otherwise leave the packer single-threaded), at most 32
-            const unsigned hw = std::thread::hardware_concurrency();
+            // -- and no more than the cgroup CPU quota allows to run at once (round 2: the GPU boxes show 128 hardware threads
+            // under a quota of 16 CPUs; a team larger than the quota is only throttled)
+            unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+            if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+                char q[64]; long long period = 0;
+                if (fscanf(f, "%63s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0) {
+                    const long long quota = atoll(q);
+                    if (quota > 0) hw = (unsigned)std::min<long long>(hw, std::max<long long>(1, (quota + period - 1) / period));
+                }
+                fclose(f);
+            }
             const int lw = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
             g_opt.pack_threads = (int)std::min<unsigned>(32u, std::max<unsigned>(1u, hw / (unsigned)lw));
         }
@@ -114,7 +142,7 @@ constexpr int NSTAGE = 3;
 struct Stage {
     cudaStream_t stream = nullptr;
     DevBuf seq_raw, seq_codes, seq_off, tasks, tasks2, ends, out, order, bins, pair_seq, pair_ad, gtrace, misc;
-    DevBuf dec_trim, dec_pairs;    // per-chunk outputs of decide_kernel
+    DevBuf dec_trim, dec_pairs, dec_top2;    // per-chunk outputs of decide_kernel
 };
 
 struct ClassPlan {
@@ -155,6 +183,26 @@ struct Engine {
     int next_trace_kind = TK_TRACE;      // set to TK_TRACE_WINDOW around the second-pass launch of a two-pass class
     DevBuf wcells;                       // device counter: DP cells of the windowed second passes (window_tasks_kernel)
     std::shared_ptr<void> packer;        // Packer (below): the thread that plans and packs chunks ahead of the submit loop
+    // launch constants, queried once per (kernel, dynamic shared-memory size); all users hold `mu`.  The opt-in shared-memory
+    // limit is a property of the KERNEL, not of a launch: it is only ever raised (a launch with less is always valid).
+    std::map<std::pair<const void *, size_t>, int> bps_cache;
+    std::map<const void *, size_t> smem_attr;
+    int blocks_per_sm(const void *kern, int threads, size_t smem_bytes, int *bps) {
+        const auto key = std::make_pair(kern, smem_bytes);
+        auto it = bps_cache.find(key);
+        if (it != bps_cache.end()) { *bps = it->second; return 0; }
+        size_t &have = smem_attr[kern];
+        if (smem_bytes > have) {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+            have = smem_bytes;
+        }
+        int b = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, threads, smem_bytes));
+        if (b < 1) b = 1;
+        bps_cache[key] = b;
+        *bps = b;
+        return 0;
+    }
     bool init_done = false;
     int init() {
         if (init_done) return 0;
@@ -242,19 +290,8 @@ int launch_trace_variant(Engine &E, Stage &S, cudaStream_t stream, const TaskSrc
     const size_t hb_words = HS ? (size_t)SPW * max_n : 0;
     const size_t smem_bytes = (size_t)wpb * (hb_words + PB_SCRATCH_WORDS) * 4;
     auto kern = trace_kernel<G, R, HS>;
-    // per-kernel launch constants (attribute + occupancy) are queried once per (kernel, shared-memory size)
-    static thread_local std::map<std::pair<int, size_t>, int> bps_cache;
     int bps = 0;
-    const auto key = std::make_pair(E.device, smem_bytes);
-    auto it = bps_cache.find(key);
-    if (it == bps_cache.end()) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, wpb * 32, smem_bytes));
-        if (bps < 1) bps = 1;
-        bps_cache[key] = bps;
-    } else {
-        bps = it->second;
-    }
+    if (int rc = E.blocks_per_sm(reinterpret_cast<const void *>(kern), wpb * 32, smem_bytes, &bps)) return rc;
     const size_t gwarp_bytes = ((size_t)((max_steps + PB_TCHUNK - 1) / PB_TCHUNK) * PB_TCHUNK * WPS * 32 +
                                 (HS ? 0 : (((size_t)SPW * max_n + 31) & ~(size_t)31))) * 4;   // 128-byte lines per warp (kernels.cuh)
     // The trace scratch of the resident grid is rewritten slot after slot and mostly lives in L2.  `scratch_mb` caps
@@ -311,13 +348,8 @@ template <int G, int R, bool PROF>
 int launch_score_variant(Engine &E, cudaStream_t stream, const TaskSrc &ts, unsigned long long *counter,
                          const uint8_t *seq_codes, const uint8_t *ad_codes, const Scoring &sc, EndCell *ends) {
     auto kern = score_kernel<G, R, PROF>;
-    static thread_local std::map<int, int> bps_cache;
-    int bps = bps_cache[E.device];
-    if (bps == 0) {
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, PB_WARPS_PER_BLOCK * 32, 0));
-        if (bps < 1) bps = 1;
-        bps_cache[E.device] = bps;
-    }
+    int bps = 0;
+    if (int rc = E.blocks_per_sm(reinterpret_cast<const void *>(kern), PB_WARPS_PER_BLOCK * 32, 0, &bps)) return rc;
     constexpr int SPW = 32 / G;
     const int64_t n_tasks = ts.n_tasks;
     const int64_t n_slots = (n_tasks + 1) / 2;
@@ -756,7 +788,7 @@ struct Packer {
                         const int64_t base = X.seq_off[it.c.s0], bytes = X.seq_off[it.c.s1] - base;
                         g_err.clear();
                         if (bytes > 0 && buf[b].ensure(((size_t)bytes + 1) / 2)) { it.rc = PB200_ERR_CUDA; it.err = g_err; }
-                        else if (bytes > 0) pb_pack_nibbles(X.seqs + base, bytes, buf[b].p, g_opt.pack_threads);
+                        else if (bytes > 0) { NvtxRange r("pb200:host_pack"); pb_pack_nibbles(X.seqs + base, bytes, buf[b].p, g_opt.pack_threads); }
                         it.buf = b;
                     }
                 }
@@ -784,6 +816,7 @@ struct Packer {
 // across job boundaries: no fill / drain bubble between the start-window and the end-window batch of an end-trim step).
 // Caller holds E.mu and has run E.init().
 int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int go, int ge) {
+    NvtxRange submit_range("pb200:submit");
     for (int i = 0; i < NSTAGE; ++i) {
         if (int rc = E.st[i].misc.ensure(64)) return rc;
         CK(cudaMemsetAsync(E.st[i].misc.p, 0, 64, E.st[i].stream));
@@ -823,11 +856,17 @@ int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int g
         const int64_t base = J.seq_off[s0];
         const int64_t bytes = J.seq_off[c.s1] - base;
         cudaStream_t stream = S.stream;
-        CK(cudaStreamSynchronize(stream));   // previous use of this stage's buffers is complete
+        NvtxRange chunk_range("pb200:chunk");
+        {
+            NvtxRange r("pb200:stage_wait");
+            CK(cudaStreamSynchronize(stream));   // previous use of this stage's buffers is complete
+        }
         if (int rc = S.seq_raw.ensure((size_t)bytes + 16)) return rc;
         if (int rc = S.seq_codes.ensure((size_t)bytes + 16)) return rc;
         if (int rc = S.seq_off.ensure((size_t)(cnt + 1) * 8)) return rc;
         if (int rc = S.out.ensure((size_t)cnt * J.n_adapters * PB_REC * 4)) return rc;
+        {
+        NvtxRange r("pb200:h2d");
         if (it.buf >= 0) {
             // Dna5 conversion was done on the host cores by the packer thread, two codes per byte: half the bytes cross PCIe
             if (bytes) CK(cudaMemcpyAsync(S.seq_raw.p, PK->buf[it.buf].p, ((size_t)bytes + 1) / 2, cudaMemcpyHostToDevice, stream));
@@ -838,6 +877,8 @@ int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int g
             CK(cudaMemcpyAsync(S.seq_raw.p, J.seqs + base, (size_t)bytes, cudaMemcpyHostToDevice, stream));
         }
         CK(cudaMemcpyAsync(S.seq_off.p, J.seq_off + s0, (size_t)(cnt + 1) * 8, cudaMemcpyHostToDevice, stream));
+        }
+        NvtxRange dp_range("pb200:dp");
         rebase_kernel<<<(unsigned)((cnt + 1 + 255) / 256), 256, 0, stream>>>(S.seq_off.as<int64_t>(), cnt + 1, base);
         g_launches++;
         if (it.buf >= 0) {
@@ -855,19 +896,29 @@ int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int g
             a.records = S.out.as<int32_t>(); a.n = cnt; a.n_adapters = J.n_adapters;
             a.is_start = D.is_start; a.end_size = D.end_size; a.extra_trim = D.extra_trim_size; a.min_trim = D.min_trim_size;
             a.cmin = J.d_cmin; a.cmin_len = J.cmin_len; a.cols = J.d_cols; a.n_cols = D.n_score_cols;
-            a.trim = S.dec_trim.as<int32_t>(); a.pairs = S.dec_pairs.as<uint32_t>();
+            a.trim = S.dec_trim.as<int32_t>();
+            a.pairs = (D.score_pairs && D.n_score_cols > 0) ? S.dec_pairs.as<uint32_t>() : nullptr;
+            a.top2 = nullptr;
+            if (D.top2) {
+                if (int rc = S.dec_top2.ensure((size_t)cnt * 6 * 4)) return rc;
+                a.top2 = S.dec_top2.as<int32_t>();
+            }
             const int64_t blocks = std::min<int64_t>((cnt + 3) / 4, (int64_t)E.sm_count * 16);
             decide_kernel<<<(unsigned)blocks, 128, 0, stream>>>(a, S.misc.as<int>());
             g_launches++;
             CK(cudaGetLastError());
             CK(cudaMemcpyAsync(D.trim + s0, S.dec_trim.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, stream));
-            if (D.n_score_cols > 0)
+            if (a.pairs)
                 CK(cudaMemcpyAsync(D.score_pairs + (size_t)s0 * D.n_score_cols * 2, S.dec_pairs.p,
                                    (size_t)cnt * D.n_score_cols * 4, cudaMemcpyDeviceToHost, stream));
+            if (a.top2)
+                CK(cudaMemcpyAsync(D.top2 + (size_t)s0 * 6, S.dec_top2.p, (size_t)cnt * 6 * 4, cudaMemcpyDeviceToHost, stream));
         }
-        if (J.out)
+        if (J.out) {
+            NvtxRange r("pb200:d2h");
             CK(cudaMemcpyAsync(J.out + (size_t)s0 * J.n_adapters * PB_REC, S.out.p, (size_t)cnt * J.n_adapters * PB_REC * 4,
                                cudaMemcpyDeviceToHost, stream));
+        }
         return 0;
     };
     int rc_final = 0;
@@ -947,6 +998,7 @@ int batch_host(const uint8_t *seqs, const int64_t *seq_off, int64_t n_seqs, cons
 
     // ---- pair-list mode: all sequences resident, pairs ordered per class on the host ----
     auto run_pairs = [&]() -> int {
+    NvtxRange submit_range("pb200:submit_pairs");
     Stage &S = E.st[0];
     cudaStream_t stream = S.stream;
     const int64_t bytes = seq_off[n_seqs];
@@ -1119,12 +1171,13 @@ int batch_end_decisions(const pb200_end_batch_t *batches, int n_batches, int ma,
         const pb200_batch_t &B = D.batch;
         if (B.n_seqs < 0 || B.n_adapters < 0 || D.n_score_cols < 0) return fail(PB200_ERR_ARG, "negative count");
         if (B.n_seqs == 0) continue;
-        if (!D.trim || (D.n_score_cols > 0 && (!D.score_pairs || !D.score_cols))) return fail(PB200_ERR_ARG, "NULL pointer");
+        if (!D.trim || (D.n_score_cols > 0 && ((!D.score_pairs && !D.top2) || !D.score_cols))) return fail(PB200_ERR_ARG, "NULL pointer");
         if (!(D.end_threshold >= 0.0)) return fail(PB200_ERR_ARG, "end_threshold must be >= 0 for the device decisions");
         for (int32_t k = 0; k < D.n_score_cols; ++k)
             if (D.score_cols[k] < 0 || D.score_cols[k] >= B.n_adapters) return fail(PB200_ERR_ARG, "score column out of range");
         if (B.n_adapters == 0) {                 // no adapters: nothing aligns, nothing is trimmed
             memset(D.trim, 0, (size_t)B.n_seqs * 4);
+            if (D.top2) for (int64_t s = 0; s < B.n_seqs; ++s) { int32_t *o = D.top2 + s * 6; o[0] = o[3] = -1; o[1] = o[4] = 0; o[2] = o[5] = 1; }
             continue;
         }
         if (!B.seq_off || !B.ad_off) return fail(PB200_ERR_ARG, "NULL pointer");
@@ -1137,6 +1190,8 @@ int batch_end_decisions(const pb200_end_batch_t *batches, int n_batches, int ma,
         int64_t m_max = 0;
         for (int32_t a = 0; a < B.n_adapters; ++a) m_max = std::max<int64_t>(m_max, B.ad_off[a + 1] - B.ad_off[a]);
         if ((int64_t)D.end_size + m_max + 2 > 65535) return fail(PB200_ERR_ARG, "windows too long for the device decisions (use the record API)");
+        if (D.top2 && ((int64_t)D.end_size + m_max + 2 > 4095 || D.n_score_cols >= 0xFFFF))
+            return fail(PB200_ERR_ARG, "windows too long / too many score columns for the device barcode ranking (use score_pairs)");
         J.dec = &D;
         J.max_seq_len = D.end_size;
         J.cmin_len = (int32_t)(D.end_size + m_max + 2);
@@ -1178,6 +1233,7 @@ int batch_device(const uint8_t *d_seqs, const int64_t *d_seq_off, int64_t n_seqs
     if (int rc = E.init()) return rc;
     Stage &S = E.st[0];
     cudaStream_t stream = user_stream ? (cudaStream_t)user_stream : S.stream;
+    NvtxRange submit_range("pb200:submit_device");
     AdapterPlan P;
     if (int rc = plan_adapters(E, stream, adapters, ad_off, n_adapters, ma, mi, go, ge, P)) return rc;
     if (int rc = S.seq_codes.ensure((size_t)total_seq_bytes + 16)) return rc;

@@ -662,7 +662,21 @@ struct DecideArgs {
     const int32_t *cmin; int32_t cmin_len;
     const int32_t *cols; int32_t n_cols;
     int32_t *trim; uint32_t *pairs;
+    int32_t *top2;            // optional: 6 int32 per read (best / second-best score column), see barcode_key
 };
+// Ordering key of a barcode score column for determine_barcode's `sorted(..., reverse=True, key=score)`
+// (porechop/nanopore_read.py:404-407): larger full-adapter identity first, equal identities keep their column order (Python's
+// sort is stable).  The identity is float("%f" % (100.0 * c / l)); for l < 4096 two different fractions differ by more than
+// 2^-24, far more than the 1e-6 of "%f", and equal fractions print identically, so ordering the fractions orders the floats:
+// key = [valid | floor(c * 2^32 / l) | 0xFFFF - position], compared as one unsigned 64-bit number.
+__device__ __forceinline__ unsigned long long barcode_key(uint32_t pair, int pos) {
+    const unsigned long long c = pair & 0xFFFFu, l = pair >> 16;
+    return (1ull << 62) | (((c << 32) / (l ? l : 1ull)) << 16) | (unsigned long long)(0xFFFF - pos);
+}
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
 __global__ void decide_kernel(const DecideArgs a, int *__restrict__ status) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -679,12 +693,42 @@ __global__ void decide_kernel(const DecideArgs a, int *__restrict__ status) {
         }
         best = __reduce_max_sync(0xffffffffu, best);
         if (lane == 0) a.trim[i] = best;
+        unsigned long long b1 = 0, b2 = 0;          // this lane's best and second-best column keys (0 = none)
         for (int32_t k = lane; k < a.n_cols; k += 32) {
             const int32_t *r = rec + (size_t)a.cols[k] * PB_REC;
             int32_t rr[PB_REC];
 #pragma unroll
             for (int q = 0; q < PB_REC; ++q) rr[q] = r[q];
-            a.pairs[(size_t)i * a.n_cols + k] = score_pair(rr, &ovf);
+            const uint32_t pr = score_pair(rr, &ovf);
+            if (a.pairs) a.pairs[(size_t)i * a.n_cols + k] = pr;
+            if (a.top2) {
+                if ((pr >> 16) >= 4096u || k >= 0xFFFF) ovf = 1;         // outside the key's exactness domain (never for end windows)
+                const unsigned long long key = barcode_key(pr, k);
+                if (key > b1) { b2 = b1; b1 = key; } else if (key > b2) b2 = key;
+            }
+        }
+        if (a.top2) {
+            // best of the warp, then the best of what is left (the winner's lane offers its own second)
+            const unsigned long long w1 = warp_max_u64(b1);
+            const unsigned long long w2 = warp_max_u64(b1 == w1 ? b2 : b1);
+            if (lane == 0) {
+                int32_t *o = a.top2 + (size_t)i * 6;
+                const unsigned long long w[2] = {w1, w2};
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    if (w[t]) {
+                        const int pos = 0xFFFF - (int)(w[t] & 0xFFFFull);
+                        const int32_t *r = rec + (size_t)a.cols[pos] * PB_REC;
+                        int32_t rr[PB_REC];
+#pragma unroll
+                        for (int q = 0; q < PB_REC; ++q) rr[q] = r[q];
+                        const uint32_t pr = score_pair(rr, &ovf);
+                        o[3 * t] = pos; o[3 * t + 1] = (int32_t)(pr & 0xFFFFu); o[3 * t + 2] = (int32_t)(pr >> 16);
+                    } else {
+                        o[3 * t] = -1; o[3 * t + 1] = 0; o[3 * t + 2] = 1;
+                    }
+                }
+            }
         }
     }
     if (ovf) atomicOr(status, 2);

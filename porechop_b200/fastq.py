@@ -293,11 +293,13 @@ class PairScores:
 
 
 def trim_end_adapters(batch, start_adapters, end_adapters, scoring_scheme_vals, end_size=150, extra_trim_size=2,
-                      end_threshold=75.0, min_trim_size=4, device_decisions=None, score_cols=None):
+                      end_threshold=75.0, min_trim_size=4, device_decisions=None, score_cols=None, rank_names=None):
     """Phase B for a FastqBatch and fixed adapter lists (sequences): returns (start_trim, end_trim, start_records,
     end_records).  Two batched engine calls, no per-read Python.
     device_decisions (default: the module switch DEVICE_DECISIONS): one adapterEndDecisions submit instead -- the trim
-    rule runs on the device and the last two results are PairScores for score_cols = (start columns, end columns)."""
+    rule runs on the device and the last two results are PairScores for score_cols = (start columns, end columns) -- or, with
+    rank_names = (start names, end names) (one unique barcode name per score column), Top2Scores: the barcode ranking of
+    determine_barcode is done on the device as well and 24 bytes per window come back instead of 4 per score column."""
     (sbuf, soff), (ebuf, eoff) = end_windows(batch.seq, batch.seq_off, end_size)
     n = len(batch)
     if device_decisions is None:
@@ -308,7 +310,9 @@ def trim_end_adapters(batch, start_adapters, end_adapters, scoring_scheme_vals, 
         ea, eo = W.pack_sequences(end_adapters, offset_dtype=np.int32)
         (st, sp, _), (et, ep, _) = W.adapter_end_decisions(
             [(sbuf, soff, sa, so, True, list(scols)), (ebuf, eoff, ea, eo, False, list(ecols))], scoring_scheme_vals,
-            end_size, extra_trim_size, end_threshold, min_trim_size)
+            end_size, extra_trim_size, end_threshold, min_trim_size, want_top2=rank_names is not None)
+        if rank_names is not None:
+            return st.astype(np.int64), et.astype(np.int64), Top2Scores(rank_names[0], sp), Top2Scores(rank_names[1], ep)
         return st.astype(np.int64), et.astype(np.int64), PairScores(scols, sp), PairScores(ecols, ep)
 
     def run(buf, off, adapters):
@@ -568,7 +572,7 @@ def _middle_adapters(sets):
 
 
 def _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim, end_threshold, min_trim_size, no_split,
-              middle_threshold, good_side, bad_side, score_cols=None):
+              middle_threshold, good_side, bad_side, score_cols=None, rank_names=None):
     t0 = time.perf_counter()
     batch = data if isinstance(data, FastqBatch) else parse_fastq(data)
     t1 = time.perf_counter()
@@ -576,7 +580,7 @@ def _run_trim(data, matching_sets, scoring_scheme_vals, end_size, extra_end_trim
     starts = [s[1] for _, s, _ in sets if s]
     ends = [e[1] for _, _, e in sets if e]
     st, et, srec, erec = trim_end_adapters(batch, starts, ends, scoring_scheme_vals, end_size, extra_end_trim,
-                                           end_threshold, min_trim_size, score_cols=score_cols)
+                                           end_threshold, min_trim_size, score_cols=score_cols, rank_names=rank_names)
     t2 = time.perf_counter()
     middle = {}
     if not no_split:
@@ -666,6 +670,76 @@ def call_barcodes(start_scores, start_names, end_scores, end_names, barcode_thre
     return calls
 
 
+class Top2Scores:
+    """Barcode ranking as the device returns it (adapterEndDecisions, `top2`): per read the (position, match_ad, len_ad) of the
+    best and the second-best score column -- positions index `names` (every barcode name once, in score-column order)."""
+
+    def __init__(self, names, top2):
+        self.names = list(names)
+        self.top2 = np.asarray(top2, dtype=np.int32).reshape(-1, 6)
+
+    def ranked(self):
+        """(pos1, score1, pos2, score2): positions (-1 = none) and the exact doubles the reference parses (0.0 for none)."""
+        from .align import _percent_exact
+        t = self.top2
+        s1 = np.where(t[:, 0] >= 0, _percent_exact(t[:, 1], np.maximum(t[:, 2], 1)), 0.0)
+        s2 = np.where(t[:, 3] >= 0, _percent_exact(t[:, 4], np.maximum(t[:, 5], 1)), 0.0)
+        return t[:, 0].astype(np.int64), s1, t[:, 3].astype(np.int64), s2
+
+
+def top2_from_scores(scores):
+    """Host statement of the device ranking (tests, and the record path when only the ranking is wanted): float[n, k] ->
+    (pos1, score1, pos2, score2) with ties going to the earlier column, -1 / 0.0 where there is no such column."""
+    M = np.asarray(scores, dtype=np.float64)
+    n, k = M.shape
+    if k == 0:
+        return np.full(n, -1), np.zeros(n), np.full(n, -1), np.zeros(n)
+    order = np.argsort(-M, axis=1, kind='stable')
+    p1 = order[:, 0]
+    s1 = M[np.arange(n), p1]
+    if k == 1:
+        return p1, s1, np.full(n, -1), np.zeros(n)
+    p2 = order[:, 1]
+    return p1, s1, p2, M[np.arange(n), p2]
+
+
+def call_barcodes_top2(start, end, barcode_threshold=75.0, barcode_diff=5.0, require_two_barcodes=False,
+                       albacore_calls=None):
+    """determine_barcode (nanopore_read.py:399-470) from the per-side rankings alone: `start` / `end` are
+    (unique names, (pos1, score1, pos2, score2)) -- Top2Scores.ranked() or top2_from_scores() over the dict-deduplicated
+    columns.  A barcode name occurs at most once per side, so the best and second-best of the merged list
+    (nanopore_read.py:441-456) are always among the two best of each side."""
+    (s_names, (sp1, ss1, sp2, ss2)), (e_names, (ep1, es1, ep2, es2)) = start, end
+    n = len(sp1)
+    all_names = list(dict.fromkeys(list(s_names) + list(e_names)))
+    idx = {nm: i for i, nm in enumerate(all_names)}
+    none_id = len(all_names)
+    name_arr = np.array(all_names + ['none'], dtype=object)
+    s_ids = np.array([idx[nm] for nm in s_names] + [none_id], dtype=np.int64)     # position -1 -> 'none'
+    e_ids = np.array([idx[nm] for nm in e_names] + [none_id], dtype=np.int64)
+    sn1, sn2, en1, en2 = s_ids[sp1], s_ids[sp2], e_ids[ep1], e_ids[ep2]
+    if require_two_barcodes:
+        ok = (ss1 >= barcode_threshold) & (es1 >= barcode_threshold) & (ss1 >= ss2 + barcode_diff) & \
+             (es1 >= es2 + barcode_diff) & (sn1 == en1)
+        calls = np.where(ok, name_arr[sn1], 'none')
+    else:
+        have_s, have_e = sp1 >= 0, ep1 >= 0
+        s_first = have_s & (~have_e | (ss1 >= es1))                    # stable sort: the start list comes first on ties
+        best_id = np.where(s_first, sn1, np.where(have_e, en1, none_id))
+        best = np.where(s_first, ss1, np.where(have_e, es1, 0.0))
+        # best entry of each side whose name differs from the winner's (its first or its second entry)
+        s_other = np.where(have_s & (sn1 != best_id), ss1, np.where((sp2 >= 0) & (sn2 != best_id), ss2, -np.inf))
+        e_other = np.where(have_e & (en1 != best_id), es1, np.where((ep2 >= 0) & (en2 != best_id), es2, -np.inf))
+        second = np.maximum(s_other, e_other)
+        second = np.where(np.isfinite(second), second, 0.0)
+        ok = (best >= barcode_threshold) & (best >= second + barcode_diff)
+        calls = np.where(ok, name_arr[best_id], 'none')
+    calls = [str(c) for c in calls]
+    if albacore_calls is not None:
+        calls = [c if (a is None or a == c) else 'none' for c, a in zip(calls, albacore_calls)]
+    return calls if n else []
+
+
 def demux_fastq(data, matching_sets, scoring_scheme_vals, forward_or_reverse='forward', end_size=150, extra_end_trim=2,
                 end_threshold=75.0, min_trim_size=4, no_split=False, middle_threshold=85.0,
                 extra_middle_trim_good_side=10, extra_middle_trim_bad_side=100, min_split_read_size=1000,
@@ -682,10 +756,16 @@ def demux_fastq(data, matching_sets, scoring_scheme_vals, forward_or_reverse='fo
     e_sets = [t for t in sets if t[2]]
     s_cols = [j for j, (name, s, e) in enumerate(s_sets) if is_bc(name, s)]
     e_cols = [j for j, (name, s, e) in enumerate(e_sets) if is_bc(name, s)]
+    s_names = [_barcode_name(*s_sets[j]) for j in s_cols]
+    e_names = [_barcode_name(*e_sets[j]) for j in e_cols]
+    # the reference's score dicts hold every barcode name once (first position, last value): rank exactly those columns
+    (su, sk), (eu, ek) = _dict_columns(s_names), _dict_columns(e_names)
+    s_cols, e_cols = [s_cols[k] for k in sk], [e_cols[k] for k in ek]
     batch, sets, st, et, srec, erec, middle, seconds = _run_trim(data, matching_sets, scoring_scheme_vals, end_size,
                                                                  extra_end_trim, end_threshold, min_trim_size, no_split,
                                                                  middle_threshold, extra_middle_trim_good_side,
-                                                                 extra_middle_trim_bad_side, score_cols=(s_cols, e_cols))
+                                                                 extra_middle_trim_bad_side, score_cols=(s_cols, e_cols),
+                                                                 rank_names=(su, eu))
     t0 = time.perf_counter()
     n = len(batch)
 
@@ -698,9 +778,12 @@ def demux_fastq(data, matching_sets, scoring_scheme_vals, forward_or_reverse='fo
             return hostio.full_scores(rec, cols)
         f, _, _, _ = scores_from_records(rec[:, cols, :].reshape(-1, 9))
         return f.reshape(n, len(cols))
-    calls = call_barcodes(full(srec, s_cols), [_barcode_name(*s_sets[j]) for j in s_cols],
-                          full(erec, e_cols), [_barcode_name(*e_sets[j]) for j in e_cols],
-                          barcode_threshold, barcode_diff, require_two_barcodes, albacore_calls)
+    if isinstance(srec, Top2Scores):                  # the ranking came from the device too
+        calls = call_barcodes_top2((su, srec.ranked()), (eu, erec.ranked()), barcode_threshold, barcode_diff,
+                                   require_two_barcodes, albacore_calls)
+    else:
+        calls = call_barcodes(full(srec, s_cols), su, full(erec, e_cols), eu, barcode_threshold, barcode_diff,
+                              require_two_barcodes, albacore_calls)
     calls_arr = np.array(calls, dtype=object)
     bins = {}
     for name in dict.fromkeys(calls):

@@ -136,15 +136,16 @@ def find_adapters_in_read_middles(reads, adapters, middle_threshold, extra_middl
             rec = W.adapter_alignment_batch(sbuf, soff, abuf, aoff, scoring_scheme_vals)   # cross product
             pair_index, stride = None, n_ad
         else:
-            ps, pa, pos = [], [], {}
-            for k, i in enumerate(active):
-                for a in range(next_adapter[i], n_ad):
-                    pos[(k, a)] = len(ps)
-                    ps.append(k)
-                    pa.append(a)
-            rec = W.adapter_alignment_batch(sbuf, soff, abuf, aoff, scoring_scheme_vals, np.array(ps, dtype=np.int32),
-                                            np.array(pa, dtype=np.int32))
-            pair_index, stride = pos, None
+            # pair list without per-pair Python objects: read k's block holds adapters next_adapter .. n_ad-1 and starts
+            # at base[k]; pair (k, a) sits at base[k] + a - next_adapter (same construction as fastq.find_middle_hits)
+            first_ad = np.array([next_adapter[i] for i in active], dtype=np.int64)
+            counts = n_ad - first_ad
+            base = np.zeros(len(active) + 1, dtype=np.int64)
+            np.cumsum(counts, out=base[1:])
+            ps = np.repeat(np.arange(len(active), dtype=np.int32), counts)
+            pa = (np.arange(base[-1], dtype=np.int64) - np.repeat(base[:-1] - first_ad, counts)).astype(np.int32)
+            rec = W.adapter_alignment_batch(sbuf, soff, abuf, aoff, scoring_scheme_vals, ps, pa)
+            pair_index, stride = (base, first_ad), None
         full, _, rs, re_ = scores_from_records(rec)
         still = []
         for k, i in enumerate(active):
@@ -152,7 +153,7 @@ def find_adapters_in_read_middles(reads, adapters, middle_threshold, extra_middl
             a = next_adapter[i]
             hit = False
             while a < n_ad:
-                p = (k * stride + a) if stride is not None else pair_index[(k, a)]
+                p = (k * stride + a) if stride is not None else int(pair_index[0][k] + a - pair_index[1][k])
                 full_score, read_start, read_end = float(full[p]), int(rs[p]), int(re_[p])
                 if full_score >= middle_threshold:
                     name = adapters[a][0]

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <functional>
+#include <map>
 #include <vector>
 
 // ---- vector types / qualifiers ---------------------------------------------------------------------------
@@ -41,12 +42,14 @@ struct dim3 {
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
-enum { cudaSuccess = 0 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 struct cudaDeviceProp { int major, minor, multiProcessorCount; size_t sharedMemPerBlockOptin; };
 inline const char *cudaGetErrorString(cudaError_t) { return "simulated CUDA error"; }
-inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+// launch-configuration errors are reported the CUDA way: the launch does nothing and cudaGetLastError() returns the error once
+inline cudaError_t &pbsim_last_error() { static thread_local cudaError_t e = cudaSuccess; return e; }
+inline cudaError_t cudaGetLastError() { cudaError_t e = pbsim_last_error(); pbsim_last_error() = cudaSuccess; return e; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
@@ -73,7 +76,14 @@ inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
-template <class F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the KERNEL (last value set wins); a launch asking for more
+// dynamic shared memory than the attribute (48 KB if never set) fails with "invalid argument" on the device -- reproduced here
+// (round 2: a per-size cache of the attribute call let a later, smaller value stand while a larger launch followed).
+inline std::map<const void *, size_t> &pbsim_smem_attr() { static std::map<const void *, size_t> m; return m; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F f, int, int v) {
+    pbsim_smem_attr()[reinterpret_cast<const void *>(f)] = (size_t)v;
+    return cudaSuccess;
+}
 template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) {
     *n = getenv("PBSIM_BLOCKS_PER_SM") ? atoi(getenv("PBSIM_BLOCKS_PER_SM")) : 2;
     return cudaSuccess;
@@ -121,6 +131,11 @@ void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<void()> &b
 
 template <class F, class... Args>
 inline void launch(F f, dim3 grid, dim3 block, size_t smem, cudaStream_t, Args... args) {
+    {   // the kernel's dynamic shared-memory limit: 48 KB unless the attribute was set -- then exactly that value
+        auto it = pbsim_smem_attr().find(reinterpret_cast<const void *>(f));
+        const size_t limit = it == pbsim_smem_attr().end() ? (size_t)48 * 1024 : it->second;
+        if (smem > limit) { pbsim_last_error() = cudaErrorInvalidValue; return; }
+    }
     run_grid(grid, block, smem, [=]() { f(args...); });
 }
 

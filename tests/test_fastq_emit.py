@@ -42,7 +42,7 @@ def _oracle_decisions(monkeypatch):
     emu.emu_decide.restype = ctypes.c_int
     calls = []
 
-    def fake(batches, scoring, end_size, extra_trim_size, end_threshold, min_trim_size, want_records=False):
+    def fake(batches, scoring, end_size, extra_trim_size, end_threshold, min_trim_size, want_records=False, want_top2=False):
         outs = []
         for seq_buf, seq_off, ad_buf, ad_off, is_start, cols in batches:
             seq_off, ad_off = np.asarray(seq_off, dtype=np.int64), np.asarray(ad_off, dtype=np.int32)
@@ -58,6 +58,16 @@ def _oracle_decisions(monkeypatch):
                                      cmin.ctypes.data, L, cols.ctypes.data, len(cols), trim.ctypes.data, pairs.ctypes.data)
                 assert ovf == 0
             p16 = np.stack([(pairs & 0xFFFF).astype(np.uint16), (pairs >> 16).astype(np.uint16)], axis=-1)
+            if want_top2:
+                # the device ranking restated with exact fractions: identity descending, ties in column order
+                from fractions import Fraction
+                top2 = np.tile(np.array([-1, 0, 1], dtype=np.int32), (n, 2))
+                for i in range(n):
+                    order = sorted(range(len(cols)), key=lambda k: (-Fraction(int(p16[i, k, 0]), max(int(p16[i, k, 1]), 1)), k))
+                    for t, k in enumerate(order[:2]):
+                        top2[i, 3 * t:3 * t + 3] = (k, p16[i, k, 0], p16[i, k, 1])
+                outs.append((trim, top2, None))
+                continue
             outs.append((trim, p16, None))
         calls.append(len(batches))
         return outs

@@ -153,6 +153,19 @@ def test_end_decisions_on_device_equal_host_rule(W):
             assert np.array_equal(trim.astype(np.int64), hostio.end_trim(full_rec, is_start, end_size, extra, thr, min_trim))
             got = _percent_exact(pairs[:, :, 0], pairs[:, :, 1])
             assert np.array_equal(got, hostio.full_scores(full_rec, cols), equal_nan=True)
+    # barcode ranking on the device (top2): best / second-best score column = the first two entries of determine_barcode's
+    # stable descending sort, for 0, 1, 2 and many columns (ties are frequent: failed alignments all score 0.0)
+    from porechop_b200.fastq import Top2Scores, top2_from_scores
+    for scols, ecols, opts in (([2, 0, 5, 1, 3], [1], {}), ([4, 3, 2, 1, 0, 5], [0, 2, 1], {'chunk_tasks': 50000}), ([3], [], {})):
+        outs = _with(W, opts, lambda: W.adapter_end_decisions(
+            [(sb, so, sa, sao, True, scols), (eb, eo, ea, eao, False, ecols)], wl.DEFAULT_SCORING, 150, 2, 75.0, 4,
+            want_top2=True))
+        for (trim, top2, _), full_rec, is_start, cols in ((outs[0], srec, True, scols), (outs[1], erec, False, ecols)):
+            assert np.array_equal(trim.astype(np.int64), hostio.end_trim(full_rec, is_start, 150, 2, 75.0, 4))
+            exp = top2_from_scores(hostio.full_scores(full_rec, cols) if cols else np.zeros((len(full_rec), 0)))
+            got = Top2Scores([str(c) for c in cols], top2).ranked()
+            for g, e in zip(got, exp):
+                assert np.array_equal(g, e)
 
 
 def test_flat_pipeline_with_device_decisions_matches_reference_cli(W, monkeypatch):

@@ -79,13 +79,18 @@ PB200_NVCC_FLAGS=-DPB_STAGE_VEC python -m porechop_b200.build --force > $out/bui
 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > $out/pytest_stagevec.log 2>&1; echo "gpu parity with PB_STAGE_VEC rc=$?" | tee -a $out/summary.txt
 run endtrim_stagevec
 run demux_stagevec --workload demux --reads 65536
+run middle_stagevec --workload middle --config-reads middle=262144
+PB200_NVCC_FLAGS=-DPB_TRACE_MIN_BLOCKS=6 python -m porechop_b200.build --force > $out/build_minblocks6.log 2>&1
+run endtrim_minblocks6
+run endtrim_minblocks6_scratch160 --opt scratch_mb=160
+run demux_minblocks6 --workload demux --reads 65536
 python -m porechop_b200.build --force > /dev/null 2>&1
 run demux_bytes --workload demux --reads 65536
 fi
 if stage ncu; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_endtrim.csv \
     python bench.py --steps 2 --warmup 1 --configs none --no-cpu-baseline > $out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 4 -c 2 -o $out/trace_kernel -f \
+ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 2 -c 2 -o $out/trace_kernel -f \
     python bench.py --steps 1 --warmup 1 --configs none --no-cpu-baseline > $out/trace_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:score_kernel -s 1 -c 1 -o $out/score_kernel -f \
     python bench.py --steps 1 --warmup 1 --configs none --no-cpu-baseline --workload middle --reads 262144 > $out/score_under_ncu.log 2>&1
