@@ -297,26 +297,49 @@ PB_HD uint32_t xnor2(uint32_t a, uint32_t b) {
 #endif
 }
 
-// max(a, b) per half; adds `clo` / `chi` to acc when a >= b in the low / high half ("first operand wins ties").
-// Device: ptxas fuses this into one VIMNMX.S16x2 with two predicate outputs plus two predicated adds.
-PB_HD uint32_t max2acc(uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, uint32_t &accHi, uint32_t chi) {
+// max(a, b) per half; sets the bits `clo` / `chi` in acc when a >= b in the low / high half ("first operand wins ties").
+// Device: ptxas fuses this into one VIMNMX.S16x2 with two predicate outputs plus two predicated accumulations.
+// USE_OR picks the PIPE of the two accumulations: the flag bits of a step are disjoint, so `add` and `or` give the same word,
+// but a predicated add issues on the FMA-heavy pipe (VIADD / IMAD.IADD) and a predicated or on the ALU pipe (LOP3).  Both
+// pipes take one warp instruction per two cycles and scheduler (round 2, ncu: sm__pipe_fmaheavy_cycles_active 72 % vs ALU
+// 57 % with every accumulation an add -- the packed VIADD.16x2 adds of the cell run on the heavy pipe too), so the trace
+// pass is bound by whichever pipe gets more than half of its instructions: lane_step mixes the two forms (PB_FLAG_OR_*).
+// (use_or is a constant after unrolling: the dead form is eliminated)
+PB_HD uint32_t max2acc(bool use_or, uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, uint32_t &accHi, uint32_t chi) {
 #if defined(__CUDA_ARCH__)
     uint32_t val;
-    asm("{\n\t.reg .pred plo, phi;\n\t.reg .s16 a0, a1, b0, b1;\n\t"
-        "max.s16x2 %0, %3, %4;\n\t"
-        "mov.b32 {a0, a1}, %0;\n\tmov.b32 {b0, b1}, %3;\n\t"
-        "setp.eq.s16 plo, a0, b0;\n\tsetp.eq.s16 phi, a1, b1;\n\t"
-        "@plo add.u32 %1, %1, %5;\n\t@phi add.u32 %2, %2, %6;\n\t}"
-        : "=r"(val), "+r"(accLo), "+r"(accHi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+    if (use_or) {
+        asm("{\n\t.reg .pred plo, phi;\n\t.reg .s16 a0, a1, b0, b1;\n\t"
+            "max.s16x2 %0, %3, %4;\n\t"
+            "mov.b32 {a0, a1}, %0;\n\tmov.b32 {b0, b1}, %3;\n\t"
+            "setp.eq.s16 plo, a0, b0;\n\tsetp.eq.s16 phi, a1, b1;\n\t"
+            "@plo xor.b32 %1, %1, %5;\n\t@phi xor.b32 %2, %2, %6;\n\t}"
+            : "=r"(val), "+r"(accLo), "+r"(accHi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+    } else {
+        asm("{\n\t.reg .pred plo, phi;\n\t.reg .s16 a0, a1, b0, b1;\n\t"
+            "max.s16x2 %0, %3, %4;\n\t"
+            "mov.b32 {a0, a1}, %0;\n\tmov.b32 {b0, b1}, %3;\n\t"
+            "setp.eq.s16 plo, a0, b0;\n\tsetp.eq.s16 phi, a1, b1;\n\t"
+            "@plo add.u32 %1, %1, %5;\n\t@phi add.u32 %2, %2, %6;\n\t}"
+            : "=r"(val), "+r"(accLo), "+r"(accHi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+    }
     return val;
 #else
     bool plo, phi;
     uint32_t v = max2p(a, b, plo, phi);
-    if (plo) accLo += clo;
-    if (phi) accHi += chi;
+    if (plo) accLo = use_or ? (accLo | clo) : (accLo + clo);
+    if (phi) accHi = use_or ? (accHi | chi) : (accHi + chi);
     return v;
 #endif
 }
+// which of a cell's four flag accumulations use the ALU-pipe form: bit 0 tH, 1 tV, 2 tM, 3 tD; _A for even rows of a lane,
+// _B for odd rows (default decided on hardware, profiles/r2_pipes)
+#ifndef PB_FLAG_OR_A
+#define PB_FLAG_OR_A 0x0
+#endif
+#ifndef PB_FLAG_OR_B
+#define PB_FLAG_OR_B 0x0
+#endif
 
 // Query profile of the score pass (option "profile", default on).  The substitution operand of group row q depends only
 // on the read base -- six possible codes (0..4 and the read padding code 5).  When both halves of a slot read the same
@@ -340,6 +363,18 @@ PB_HD uint32_t profile_from(uint32_t v2, uint32_t sf2, uint32_t bcode, const Sco
     const uint32_t h2 = (e << 8) | (e << 24);
     return addmax2(xnor2(h2, v2), sc.subA2, sf2);
 }
+// E2 (round 2, -DPB_PROF_PLAIN_ADD): the profile word in a form that a PLAIN 32-bit add applies to both halves at once.
+// A packed s16x2 addend whose low half is negative carries 1 into the high half when added as one 32-bit number (the low
+// half of a biased X is always larger than the addend's magnitude), so that 1 is taken off the high half up front; a
+// non-negative low half never carries (biased values stay below 2^15 + |addend|).  The diagonal term S_diag + sub then is
+// an ordinary integer add -- which ptxas cannot fuse into a VIADDMNMX on the ALU pipe, the pipe that bounds the score pass
+// (ncu: ALU 65 %, FMA-heavy 22 % of their peaks) -- and the cell's maximum becomes one three-input VIMNMX3.
+PB_HD uint32_t profile_plain(uint32_t sub2) { return (sub2 & 0x8000u) ? sub2 - 0x10000u : sub2; }
+#ifdef PB_PROF_PLAIN_ADD
+#define PB_PROF_ENCODE(x) profile_plain(x)
+#else
+#define PB_PROF_ENCODE(x) (x)
+#endif
 PB_HD uint32_t profile_word(int q, uint32_t bcode, const Scoring &sc, const uint8_t *adA, int mA, int padA, const uint8_t *adB,
                             int mB, int padB) {
     uint32_t v2, sf2;
@@ -381,15 +416,20 @@ PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, co
     for (int r = 0; r < R; ++r) {
         // substitution (minus go) per half: codes equal -> ~(h^v) == -1 -> max(-1 + ma + 1 - go, mi - go) = ma - go
         const uint32_t sub = PROF ? subs[r] : addmax2(xnor2(h2, L.v2[r]), sc.subA2, L.sf2[r]);
+#ifdef PB_PROF_PLAIN_ADD
+        const uint32_t d = PROF ? diagX + sub : add2(diagX, sub);   // S_diag + sub (biased); PROF: carry-compensated word, plain add
+#else
         const uint32_t d = add2(diagX, sub);                        // S_diag + sub (biased)
+#endif
         uint32_t hs, vs, s;
         if (TRACE) {
             const uint32_t bl = 1u << trace_shift<R>(0, r);
             const uint32_t bh = 1u << trace_shift<R>(1, r);
-            hs = max2acc(PB_EXT(L.Hs[r]), L.X[r], accLo, bl << 3, accHi, bh << 3);   // ext vs open (= X left)
-            vs = max2acc(PB_EXT(upV), upX, accLo, bl << 2, accHi, bh << 2);          // ext vs open (= X up)
-            const uint32_t gmx = max2acc(vs, hs, accLo, bl << 1, accHi, bh << 1);
-            s = max2acc(d, gmx, accLo, bl, accHi, bh);
+            const int orm = (r & 1) ? (PB_FLAG_OR_B) : (PB_FLAG_OR_A);
+            hs = max2acc((orm & 1) != 0, PB_EXT(L.Hs[r]), L.X[r], accLo, bl << 3, accHi, bh << 3);   // ext vs open (= X left)
+            vs = max2acc((orm & 2) != 0, PB_EXT(upV), upX, accLo, bl << 2, accHi, bh << 2);          // ext vs open (= X up)
+            const uint32_t gmx = max2acc((orm & 4) != 0, vs, hs, accLo, bl << 1, accHi, bh << 1);
+            s = max2acc((orm & 8) != 0, d, gmx, accLo, bl, accHi, bh);
         } else {
             hs = addmax2(L.Hs[r], sc.ge2, L.X[r]);
             vs = addmax2(upV, sc.ge2, upX);
@@ -487,13 +527,24 @@ PB_HD EndCell scout_combine(const ScoutCand *c, int G, const HalfGeom &H) {
 }
 
 // ---- traceback + statistics ---------------------------------------------------------------------------
-// NibFn(jl, i) -> 4 trace flags of cell (local column jl >= 1, row i >= 1)
-// EqFn(jl, i)  -> read base of local column jl equals adapter base of row i (code equality, N == N)
+// Cursor: walks the trace.  cur.flags() = 4 trace flags of the current cell, cur.move(consR, consA) steps to the cell one
+// column left (consR) and / or one row up (consA), cur.eq() = read base of the current column equals the adapter base of the
+// current row (code equality, N == N).  The kernels keep incremental addresses in the cursor (trace_kernel) or index a plain
+// array (generic_kernel, tests); RandomCursor adapts a pair of (column, row) functions.
+template <class NibFn, class EqFn>
+struct RandomCursor {
+    NibFn nib; EqFn eqf; int j, i;
+    PB_HD RandomCursor(NibFn n, EqFn e, int j0, int i0) : nib(n), eqf(e), j(j0), i(i0) {}
+    PB_HD uint32_t flags() { return nib(j, i); }
+    PB_HD bool eq() { return eqf(j, i); }
+    PB_HD void move(bool consR, bool consA) { j -= consR ? 1 : 0; i -= consA ? 1 : 0; }
+};
+
 // Writes the 9-int record.  Returns 0, or 1 if the path ran into the left edge of a window with
 // col0 > 0 (window too small -- must never happen when the window bound of DESIGN.md holds).
-template <class NibFn, class EqFn>
-PB_HD int traceback_stats(NibFn nib, EqFn eq, const EndCell &end, bool linear, int col0, int n_total, int m,
-                          int32_t *rec) {
+// `cur` must be positioned on the end cell (end.j, end.i) when both are > 0.
+template <class Cursor>
+PB_HD int traceback_stats_cur(Cursor &cur, const EndCell &end, bool linear, int col0, int n_total, int m, int32_t *rec) {
     if (end.score == PB_SCORE_EMPTY) {
         rec[0] = -1; rec[1] = 0; rec[2] = -1; rec[3] = 0; rec[4] = PB_SCORE_EMPTY;
         rec[5] = 0; rec[6] = 0; rec[7] = 0; rec[8] = 0;
@@ -501,47 +552,52 @@ PB_HD int traceback_stats(NibFn nib, EqFn eq, const EndCell &end, bool linear, i
     }
     int j = end.j, i = end.i;      // local column, row
     int L = 0, matches = 0;
-    // events: first/last (in forward order) path operation that consumes a read / adapter base
-    bool haveR = false, haveA = false;
-    int lastR_k = 0, lastR_i = 0, lastR_uA = 0, firstR_k = 0, firstR_i = 0, firstR_uA = 0;
-    int lastA_k = 0, lastA_j = 0, lastA_uR = 0, firstA_k = 0, firstA_j = 0, firstA_uR = 0;
+    // The statistics need the first / last (in forward order) path operation that consumes a read base and the first / last
+    // that consumes an adapter base.  Walking backwards these are: the first step that is not vertical (it follows a prefix
+    // of `pv` vertical steps), the first that is not horizontal (prefix `ph`), and the last non-vertical / non-horizontal step
+    // (followed by a run of `tv` vertical / `th` horizontal steps up to the path's start) -- four run lengths and whether the
+    // step that ends each run is a diagonal; coordinates follow from the run lengths.  No per-step event records.
+    int pv = 0, ph = 0, tv = 0, th = 0;
+    int dPV = 0, dPH = 0, dTV = 0, dTH = 0;
     // direction of the current cell: 0 diag, 1 vertical, 2 horizontal
-    int dir;
+    int dir = 0;
     uint32_t b = 0;
     if (j > 0 && i > 0) {
-        b = nib(j, i);
+        b = cur.flags();
         dir = (b & 1u) ? 0 : ((b & 2u) ? 1 : 2);
         if (!linear) {                                  // dp_algorithm_impl.h:1354-1369
             if (end.corr & 1) dir = 1; else if (end.corr & 2) dir = 2;
         }
-    } else {
-        dir = 0;
     }
     // ONE path step per loop iteration with the step kind as data (no per-direction code paths, no inner gap-run loops):
     // the lanes of a warp that trace at the same time run the same instruction stream instead of serialising diagonal /
     // vertical / horizontal branches and waiting for each other's gap runs (measured on B200: trace launch 2.36 -> 2.25 ms).
     while (j > 0 && i > 0) {
-        const bool isD = dir == 0, isV = dir == 1;
-        const bool consR = !isV, consA = dir != 2;          // the step consumes a read base / an adapter base
-        if (isD && eq(j, i)) ++matches;
-        if (consR) {
-            if (!haveR) { haveR = true; lastR_k = L; lastR_i = i; lastR_uA = isD ? 1 : 0; }
-            firstR_k = L; firstR_i = i; firstR_uA = isD ? 1 : 0;
-        }
-        if (consA) {
-            if (!haveA) { haveA = true; lastA_k = L; lastA_j = j; lastA_uR = isD ? 1 : 0; }
-            firstA_k = L; firstA_j = j; firstA_uR = isD ? 1 : 0;
-        }
+        const bool isD = dir == 0, isV = dir == 1, isH = dir == 2;
+        const bool consR = !isV, consA = !isH;              // the step consumes a read base / an adapter base
+        if (isD && cur.eq()) ++matches;
+        const bool inPV = pv == L, inPH = ph == L;          // every step so far was vertical / horizontal
+        if (inPV) { if (isV) ++pv; else dPV = isD ? 1 : 0; }
+        if (inPH) { if (isH) ++ph; else dPH = isD ? 1 : 0; }
+        if (isV) ++tv; else { tv = 0; dTV = isD ? 1 : 0; }
+        if (isH) ++th; else { th = 0; dTH = isD ? 1 : 0; }
         // a gap run continues while the current cell says "extended" (dp_traceback_impl.h:225-341)
-        const bool ext = !linear && (isV ? ((b & 4u) && i != 1) : (dir == 2 && (b & 8u) && j != 1));
+        const bool ext = !linear && (isV ? ((b & 4u) && i != 1) : (isH && (b & 8u) && j != 1));
         ++L;
         if (consR) --j;
         if (consA) --i;
+        cur.move(consR, consA);
         if (j > 0 && i > 0) {
-            b = nib(j, i);
+            b = cur.flags();
             if (!ext) dir = (b & 1u) ? 0 : ((b & 2u) ? 1 : 2);
         }
     }
+    // the event records of the path (k = step index counted backwards from the end cell)
+    const bool haveR = pv < L, haveA = ph < L;
+    const int lastR_k = pv, lastR_i = end.i - pv, lastR_uA = dPV;
+    const int lastA_k = ph, lastA_j = end.j - ph, lastA_uR = dPH;
+    const int firstR_k = L - 1 - tv, firstR_i = i + tv + dTV, firstR_uA = dTV;
+    const int firstA_k = L - 1 - th, firstA_j = j + th + dTH, firstA_uR = dTH;
     int status = (j == 0 && i > 0 && col0 > 0) ? 1 : 0;
 
     // whole alignment = [H x a][V x bb] . path . [H x c][V x e]   (dp_traceback_impl.h:532-554)
@@ -575,6 +631,14 @@ PB_HD int traceback_stats(NibFn nib, EqFn eq, const EndCell &end, bool linear, i
     rec[0] = rs; rec[1] = re; rec[2] = as; rec[3] = ae; rec[4] = end.score;
     rec[5] = matches; rec[6] = endc - start + 1; rec[7] = matches; rec[8] = a1 - a0 + 1;
     return status;
+}
+
+// NibFn(jl, i) -> 4 trace flags of cell (local column jl >= 1, row i >= 1); EqFn(jl, i) -> bases equal
+template <class NibFn, class EqFn>
+PB_HD int traceback_stats(NibFn nib, EqFn eq, const EndCell &end, bool linear, int col0, int n_total, int m,
+                          int32_t *rec) {
+    RandomCursor<NibFn, EqFn> cur(nib, eq, end.j, end.i);
+    return traceback_stats_cur(cur, end, linear, col0, n_total, m, rec);
 }
 
 // ---- end-trim decisions on the device ------------------------------------------------------

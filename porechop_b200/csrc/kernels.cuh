@@ -411,27 +411,35 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
                 } else {
                     end = scout_combine(cand + h * 32 + grp * G, G, gh);
                 }
-                const uint8_t *ad = ads + tk.ad_off;
-                const int lane_base = grp * G;
-                int cached_c = -1, cached_g = -1;
-                uint4 cv = make_uint4(0u, 0u, 0u, 0u);
-                auto nib = [&](int jl, int i) -> uint32_t {
-                    const int q = i + gh.pad - 1;
-                    const int gg = q / R, r = q % R;
-                    const int t = jl - 1 + gg;
-                    const int c = t / PB_TCHUNK, u = t % PB_TCHUNK;
-                    if (c != cached_c || gg != cached_g) {     // one load serves up to PB_TCHUNK path steps
-                        cv = *reinterpret_cast<const uint4 *>(tr + (((size_t)c * WPS + trace_word<R>(h, r)) * 32 + lane_base + gg) * PB_TCHUNK);
-                        cached_c = c; cached_g = gg;
+                // cursor over the slot's trace: incremental addresses (lane of the row, row within the lane, step index) instead
+                // of a division per path step; one 128-bit load serves up to PB_TCHUNK consecutive steps of a lane
+                struct Cursor {
+                    const uint32_t *base;      // trace words of this half, lane 0 of the group, chunk 0
+                    const uint32_t *hp;        // staged column word of the current column
+                    const uint8_t *ap;         // adapter code of the current row
+                    int gg, r, t, key, h;
+                    uint4 cv;
+                    __device__ __forceinline__ uint32_t flags() {
+                        const int k = (t >> 2) * (WPS * 32) + gg;
+                        if (k != key) { cv = *reinterpret_cast<const uint4 *>(base + (size_t)k * PB_TCHUNK); key = k; }
+                        const uint32_t lo = (t & 1) ? cv.y : cv.x, hi = (t & 1) ? cv.w : cv.z;
+                        return (((t & 2) ? hi : lo) >> trace_shift<R>(h, r)) & 15u;
                     }
-                    const uint32_t w = (u == 0) ? cv.x : (u == 1) ? cv.y : (u == 2) ? cv.z : cv.w;
-                    return (w >> trace_shift<R>(h, r)) & 15u;
-                };
-                auto eq = [&](int jl, int i) -> bool {   // the slot's staged column words are still in hbuf
-                    return ((hbuf[jl - 1] >> (8 + 16 * h)) & 0xFFu) == (uint32_t)__ldg(ad + i - 1);
-                };
+                    __device__ __forceinline__ bool eq() { return ((*hp >> (8 + 16 * h)) & 0xFFu) == (uint32_t)__ldg(ap); }
+                    __device__ __forceinline__ void move(bool consR, bool consA) {
+                        if (consA) { --ap; if (r == 0) { r = R - 1; --gg; --t; } else --r; }
+                        if (consR) { --t; --hp; }
+                    }
+                } cur;
+                {
+                    const int q = max(end.i + gh.pad - 1, 0);
+                    cur.gg = q / R; cur.r = q % R; cur.t = end.j - 1 + cur.gg; cur.key = -1; cur.h = h;
+                    cur.base = tr + ((size_t)trace_word<R>(h, 0) * 32 + grp * G) * PB_TCHUNK;
+                    cur.hp = hbuf + end.j - 1; cur.ap = ads + tk.ad_off + end.i - 1;
+                    cur.cv = make_uint4(0u, 0u, 0u, 0u);
+                }
                 int32_t rec[PB_REC];
-                int st = traceback_stats(nib, eq, end, sc.linear != 0, tk.col0, tk.n_total, tk.m, rec);
+                int st = traceback_stats_cur(cur, end, sc.linear != 0, tk.col0, tk.n_total, tk.m, rec);
                 if (st) atomicOr(status, 1);
                 int32_t *o = out + (size_t)tk.out_idx * PB_REC;
 #pragma unroll
@@ -581,7 +589,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                         for (int b = 0; b < 6; ++b) {       // from the row operands lane_init has just set up: two 128-bit stores
                             uint32_t w[8];
 #pragma unroll
-                            for (int r = 0; r < 8; ++r) w[r] = profile_from(L.v2[r], L.sf2[r], (uint32_t)b, sc);
+                            for (int r = 0; r < 8; ++r) w[r] = PB_PROF_ENCODE(profile_from(L.v2[r], L.sf2[r], (uint32_t)b, sc));
                             uint4 *dst = reinterpret_cast<uint4 *>(myprof + b * ProfGeom<G, R>::ROWS);
                             dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
                             dst[1] = make_uint4(w[4], w[5], w[6], w[7]);

@@ -194,16 +194,39 @@ def main():
     search = [a for a in P.ADAPTERS if '(full sequence)' not in a.name]                     # porechop.py:296
     as_tuple = lambda a: (a.name, tuple(a.start_sequence) or None, tuple(a.end_sequence) or None)   # noqa: E731
     read_type = 'fastq'
+    # PB200_CHECK_ALL_READS=1 (opt-in; the reference's README suggests a larger --check_reads when adapters
+    # are rare): Phase A looks at EVERY read instead of the first --check_reads -- one extra streaming pass over the input
+    # in the same bounded chunks; a set's best score is a maximum, so chunks (and ranks) combine exactly.
+    check_all = os.environ.get('PB200_CHECK_ALL_READS', '0') == '1'
+    sets_a = [as_tuple(a) for a in search]
+
+    def note(best_s, best_e):
+        for a, s, e in zip(search, best_s, best_e):
+            a.best_start_score, a.best_end_score = max(a.best_start_score, float(s)), max(a.best_end_score, float(e))
+    chunk_no = 0
     for path in inputs:
+        if check_all:
+            for kind, data in _record_chunks(path, chunk_bytes, 0):
+                if len(inputs) == 1:
+                    read_type = kind
+                if chunk_no % world == rank:
+                    batch = parsers[kind](data)
+                    note(*fastq.search_adapter_sets(batch, sets_a, scoring, len(batch), args.end_size))
+                chunk_no += 1
+            continue
         kind, first = next(_record_chunks(path, chunk_bytes, check_per_file))
         if len(inputs) == 1:
             read_type = kind
         if check_per_file <= 0:
             continue
-        best_s, best_e = fastq.search_adapter_sets(parsers[kind](first), [as_tuple(a) for a in search], scoring,
-                                                   check_per_file, args.end_size)
-        for a, s, e in zip(search, best_s, best_e):
-            a.best_start_score, a.best_end_score = max(a.best_start_score, float(s)), max(a.best_end_score, float(e))
+        note(*fastq.search_adapter_sets(parsers[kind](first), sets_a, scoring, check_per_file, args.end_size))
+    if check_all and world > 1:          # every rank saw its own chunks: the per-set maxima are combined (host-side, gloo)
+        mine = [(a.best_start_score, a.best_end_score) for a in search]
+        every = [None] * world
+        dist.all_gather_object(every, mine)
+        for k, a in enumerate(search):
+            a.best_start_score = max(r[k][0] for r in every)
+            a.best_end_score = max(r[k][1] for r in every)
     matching = [a for a in search if a.best_start_or_end_score() >= args.adapter_threshold]  # porechop.py:327
     matching = P.fix_up_1d2_sets(matching)
     null = open(os.devnull, 'w')

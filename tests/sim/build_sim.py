@@ -37,7 +37,12 @@ def build(force=False):
     srcs = [os.path.join(CSRC, f) for f in ('engine.cu', 'kernels.cuh', 'dp_core.cuh', 'hostpack.cpp')] + \
            [os.path.join(HERE, f) for f in ('pbsim_cuda.h', 'pbsim.cpp', 'build_sim.py')] + \
            [os.path.join(ROOT, 'include', 'porechop_b200.h')]
-    if not force and os.path.exists(TARGET) and all(os.path.getmtime(s) <= os.path.getmtime(TARGET) for s in srcs):
+    # PB200_SIM_FLAGS: extra -D switches of the product sources (the compile-time A/B options, e.g. -DPB_PROF_PLAIN_ADD); the
+    # library is rebuilt whenever they differ from the ones it was built with
+    flags = os.environ.get('PB200_SIM_FLAGS', '').split()
+    stamp = os.path.join(BUILD, 'flags.txt')
+    same_flags = os.path.exists(stamp) and open(stamp).read().split() == flags
+    if not force and same_flags and os.path.exists(TARGET) and all(os.path.getmtime(s) <= os.path.getmtime(TARGET) for s in srcs):
         return TARGET
     os.makedirs(os.path.join(BUILD, 'porechop_b200', 'csrc'), exist_ok=True)
     os.makedirs(os.path.join(BUILD, 'include'), exist_ok=True)
@@ -50,14 +55,16 @@ def build(force=False):
     assert launches >= 14, 'kernel launch sites not found'
     with open(os.path.join(BUILD, 'include', 'porechop_b200.h'), 'w') as o:
         o.write(open(os.path.join(ROOT, 'include', 'porechop_b200.h')).read())
-    cmd = ['g++', '-O2', '-g', '-std=c++17', '-fPIC', '-shared', '-fopenmp', '-Wno-unknown-pragmas', '-Wno-unused-value',
-           '-I', HERE, '-o', TARGET + '.tmp%d' % os.getpid(),
+    cmd = ['g++', '-O2', '-g', '-std=c++17', '-fPIC', '-shared', '-fopenmp', '-Wno-unknown-pragmas', '-Wno-unused-value'] + flags + \
+          ['-I', HERE, '-o', TARGET + '.tmp%d' % os.getpid(),
            os.path.join(BUILD, 'porechop_b200', 'csrc', 'engine_sim.cpp'), os.path.join(HERE, 'pbsim.cpp'),
            os.path.join(CSRC, 'hostpack.cpp')]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('g++ failed on the simulated engine:\n' + r.stdout + r.stderr[-6000:])
     os.replace(TARGET + '.tmp%d' % os.getpid(), TARGET)      # atomic: a concurrent loader never sees a half-written library
+    with open(stamp, 'w') as o:
+        o.write(' '.join(flags))
     return TARGET
 
 

@@ -97,6 +97,36 @@ def test_flat_cli_streams_in_chunks(chunk, input_name, argv, porechop_modules, m
     test_flat_cli_writes_the_reference_cli_files('chunked', input_name, argv, porechop_modules, monkeypatch, tmp_path)
 
 
+@pytest.mark.parametrize('chunk', [3000, 1 << 20])
+@pytest.mark.parametrize('input_name,argv', [('test_barcodes.fastq', ['-b', '{out}/bins']),
+                                             ('test_two_adapter_sets.fastq', ['-o', '{out}/o.fastq']),
+                                             ('GOLDEN:input_fastq', ['-o', '{out}/o.fastq', '--min_split_read_size', '50'])])
+def test_flat_cli_phase_a_over_all_reads(chunk, input_name, argv, porechop_modules, monkeypatch, tmp_path):  # noqa: F811
+    """PB200_CHECK_ALL_READS=1 (opt-in): Phase A streams over every read in bounded chunks -- same files as the reference
+    CLI told to check more reads than the input holds; the flat CLI itself is given a --check_reads of 1, which the switch
+    must override."""
+    porechop, P, A = porechop_modules
+    if input_name.startswith('GOLDEN:'):
+        inp = str(tmp_path / 'in.fastq')
+        with open(inp, 'w', newline='') as f:
+            f.write(load_golden('golden_emit.json')[input_name.split(':')[1]])
+    else:
+        inp = os.path.join(REF, 'test', input_name)
+
+    def args_for(out, check):
+        return ['-i', inp, '-v', '0', '-t', '1', '--check_reads', str(check)] + [a.replace('{out}', out) for a in argv]
+    _, base = _run_cli(P, A, args_for(str(tmp_path / 'a'), 1000000), str(tmp_path / 'a'))
+    _oracle_engine(monkeypatch)
+    monkeypatch.syspath_prepend(REF)
+    monkeypatch.setenv('PB200_FLAT_CHUNK_BYTES', str(chunk))
+    monkeypatch.setenv('PB200_CHECK_ALL_READS', '1')
+    got = _flat_cli(A, args_for(str(tmp_path / 'b'), 1), str(tmp_path / 'b'))
+    base, got = _plain(base), _plain(got)
+    assert sorted(got) == sorted(base) and len(base) >= 1
+    for k in base:
+        assert got[k] == base[k], k
+
+
 def _rank_worker(rank, world, port, argv, q):
     """one torchrun-style rank of the flat CLI on CPU: gloo for the barrier, the oracle as the engine (tests only)."""
     import numpy as np
@@ -119,15 +149,19 @@ def _rank_worker(rank, world, port, argv, q):
         q.put((rank, repr(e)))
 
 
-@pytest.mark.parametrize('argv', [['-b', '{out}/bins', '--check_reads', '5'], ['-o', '{out}/o.fastq.gz', '--check_reads', '5']],
-                         ids=['bins', 'single_gz'])
-def test_flat_cli_two_ranks_gloo(argv, porechop_modules, tmp_path):  # noqa: F811
+@pytest.mark.parametrize('argv', [['-b', '{out}/bins', '--check_reads', '5'], ['-o', '{out}/o.fastq.gz', '--check_reads', '5'],
+                                  ['-b', '{out}/bins', '--check_reads', '1000000', 'ALL_READS']],
+                         ids=['bins', 'single_gz', 'bins_phase_a_all_reads'])
+def test_flat_cli_two_ranks_gloo(argv, porechop_modules, tmp_path, monkeypatch):  # noqa: F811
     """world_size 2 on CPU (gloo): chunks alternate between the ranks, rank 0 stitches the pieces -- same files as the
     reference CLI, no leftovers."""
     import socket
     import torch.multiprocessing as mp
     porechop, P, A = porechop_modules
     inp = os.path.join(REF, 'test', 'test_barcodes.fastq')
+    if 'ALL_READS' in argv:         # Phase A over every read: the ranks combine their per-set maxima (spawned ranks inherit the env)
+        argv = [a for a in argv if a != 'ALL_READS']
+        monkeypatch.setenv('PB200_CHECK_ALL_READS', '1')
 
     def args_for(out):
         return ['-i', inp, '-v', '0', '-t', '1'] + [a.replace('{out}', out) for a in argv]
