@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 TARGET = os.path.join(HERE, 'cpp_functions.so')
 SOURCES = [os.path.join(CSRC, 'engine.cu')]
-HOSTPACK = os.path.join(CSRC, 'hostpack.cpp')       # host half of the packed upload path: plain C++ (g++, AVX2 + OpenMP)
+HOSTPACK = os.path.join(CSRC, 'hostpack.cpp')       # host half of the packed upload path: plain C++ (g++, AVX-512 / AVX2, own thread team)
 DEPS = SOURCES + [HOSTPACK, os.path.join(CSRC, 'kernels.cuh'), os.path.join(CSRC, 'dp_core.cuh'),
                   os.path.join(os.path.dirname(HERE), 'include', 'porechop_b200.h')]
 
@@ -37,18 +37,13 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return TARGET
     obj = os.path.join(CSRC, 'hostpack.o')
-    omp = True
-    for flags in (['-fopenmp'], []):                # a g++ without libgomp still builds it (single-threaded packer)
-        r = subprocess.run([shutil.which('g++') or 'g++', '-O3', '-std=c++17', '-fPIC', '-Wall', '-Wextra'] + flags +
-                           ['-c', '-o', obj, HOSTPACK], capture_output=True, text=True)
-        if r.returncode == 0:
-            omp = bool(flags)
-            break
-    else:
+    r = subprocess.run([shutil.which('g++') or 'g++', '-O3', '-std=c++17', '-fPIC', '-pthread', '-Wall', '-Wextra', '-c', '-o', obj,
+                        HOSTPACK], capture_output=True, text=True)
+    if r.returncode != 0:
         raise RuntimeError('g++ failed on hostpack.cpp:\n' + r.stdout + r.stderr)
     cmd = [nvcc_path(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
            '-Xcompiler', '-fPIC', '-shared', '-o', TARGET] + os.environ.get('PB200_NVCC_FLAGS', '').split() + SOURCES + \
-          [obj] + (['-lgomp'] if omp else []) + ['-ldl']
+          [obj, '-lpthread', '-ldl']
     if verbose:
         cmd.insert(1, '-Xptxas')
         cmd.insert(2, '-v')

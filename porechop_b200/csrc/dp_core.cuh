@@ -299,11 +299,13 @@ PB_HD uint32_t xnor2(uint32_t a, uint32_t b) {
 
 // max(a, b) per half; sets the bits `clo` / `chi` in acc when a >= b in the low / high half ("first operand wins ties").
 // Device: ptxas fuses this into one VIMNMX.S16x2 with two predicate outputs plus two predicated accumulations.
-// USE_OR picks the PIPE of the two accumulations: the flag bits of a step are disjoint, so `add` and `or` give the same word,
-// but a predicated add issues on the FMA-heavy pipe (VIADD / IMAD.IADD) and a predicated or on the ALU pipe (LOP3).  Both
-// pipes take one warp instruction per two cycles and scheduler (round 2, ncu: sm__pipe_fmaheavy_cycles_active 72 % vs ALU
-// 57 % with every accumulation an add -- the packed VIADD.16x2 adds of the cell run on the heavy pipe too), so the trace
-// pass is bound by whichever pipe gets more than half of its instructions: lane_step mixes the two forms (PB_FLAG_OR_*).
+// use_or picks the PIPE of the two accumulations: the flag bits of a step are disjoint, so add / or / xor give the same word,
+// but a predicated add issues on the FMA-heavy pipe (VIADD / IMAD.IADD) and a predicated logic op on the ALU pipe (LOP3).
+// Both pipes take one warp instruction per two cycles and scheduler and the FMA-lite pipe takes no integer work
+// (tools/ubench_pipes.cu under ncu, profiles/r2_pipes: VIMNMX / VIADDMNMX / VIMNMX3 / LOP3 -> ALU; VIADD.16x2 / IMAD /
+// VIADD -> FMA-heavy; alone each sustains 0.5 warp instructions per clock, alternating they reach 1.0).  With every
+// accumulation an add the trace pass had 12 heavy and 6 ALU instructions per row (ncu: fmaheavy 72 %, ALU 57 % busy) and
+// was bound by the heavy pipe; lane_step mixes the two forms (PB_FLAG_OR_*).
 // (use_or is a constant after unrolling: the dead form is eliminated)
 PB_HD uint32_t max2acc(bool use_or, uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, uint32_t &accHi, uint32_t chi) {
 #if defined(__CUDA_ARCH__)
@@ -313,7 +315,7 @@ PB_HD uint32_t max2acc(bool use_or, uint32_t a, uint32_t b, uint32_t &accLo, uin
             "max.s16x2 %0, %3, %4;\n\t"
             "mov.b32 {a0, a1}, %0;\n\tmov.b32 {b0, b1}, %3;\n\t"
             "setp.eq.s16 plo, a0, b0;\n\tsetp.eq.s16 phi, a1, b1;\n\t"
-            "@plo xor.b32 %1, %1, %5;\n\t@phi xor.b32 %2, %2, %6;\n\t}"
+            "@plo xor.b32 %1, %1, %5;\n\t@phi xor.b32 %2, %2, %6;\n\t}"      // xor, not or: ptxas turns an `or` of provably disjoint bits back into an add
             : "=r"(val), "+r"(accLo), "+r"(accHi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
     } else {
         asm("{\n\t.reg .pred plo, phi;\n\t.reg .s16 a0, a1, b0, b1;\n\t"
@@ -333,12 +335,14 @@ PB_HD uint32_t max2acc(bool use_or, uint32_t a, uint32_t b, uint32_t &accLo, uin
 #endif
 }
 // which of a cell's four flag accumulations use the ALU-pipe form: bit 0 tH, 1 tV, 2 tM, 3 tD; _A for even rows of a lane,
-// _B for odd rows (default decided on hardware, profiles/r2_pipes)
+// _B for odd rows.  Measured on B200 (profiles/r2_pipes, end-trim launch of 1 M 150x28 alignments): none 2.083 ms, tH only
+// (2 of the 8 accumulations per row) 1.976 ms, tH+tV on even rows 1.990, tH+tV 2.053, tH+tV+tM 2.248 -- the minimum is where
+// the hot loop's ALU and FMA-heavy instruction counts are equal (279 / 286 per 4 steps x 7 rows).
 #ifndef PB_FLAG_OR_A
-#define PB_FLAG_OR_A 0x0
+#define PB_FLAG_OR_A 0x1
 #endif
 #ifndef PB_FLAG_OR_B
-#define PB_FLAG_OR_B 0x0
+#define PB_FLAG_OR_B 0x1
 #endif
 
 // Query profile of the score pass (option "profile", default on).  The substitution operand of group row q depends only

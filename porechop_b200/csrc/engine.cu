@@ -132,7 +132,9 @@ void load_env_options() {
                 fclose(f);
             }
             const int lw = getenv("LOCAL_WORLD_SIZE") ? std::max(1, atoi(getenv("LOCAL_WORLD_SIZE"))) : 1;
-            g_opt.pack_threads = (int)std::min<unsigned>(32u, std::max<unsigned>(1u, hw / (unsigned)lw));
+            unsigned team = std::max<unsigned>(1u, hw / (unsigned)lw);
+            if (team > 4) team -= 2;         // the submit thread and the driver's threads need CPUs of the same quota
+            g_opt.pack_threads = (int)std::min<unsigned>(32u, team);
         }
         if (const char *v = getenv("PB200_HBUF")) g_opt.hbuf_mode = !strcmp(v, "smem") ? 1 : !strcmp(v, "global") ? 2 : 0;
     });

@@ -6,17 +6,24 @@
 // host cores instead and packs two 4-bit codes per byte: half the bytes over the link, and the device unpacks
 // (kernels.cuh unpack_kernel) into exactly the code bytes encode_kernel would have produced.
 //
-// Plain C++ (g++), linked into cpp_functions.so by build.py; AVX-512BW / AVX2 body selected at run time, scalar table otherwise.
+// Plain C++ (g++), linked into cpp_functions.so by build.py; AVX-512BW / AVX2 body selected at run time, scalar table otherwise;
+// its own sleeping thread team (no OpenMP: see PackTeam).
 // No alignment arithmetic here -- only the alphabet conversion.
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <stdio.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+#include <vector>
+
 #if defined(__x86_64__)
 #include <immintrin.h>
-#endif
-#if defined(_OPENMP)
-#include <omp.h>
 #endif
 
 namespace {
@@ -101,24 +108,91 @@ void pack_range(const uint8_t *in, int64_t i0, int64_t i1, int64_t n, uint8_t *o
     pack_scalar(in, i0, i1, n, out);
 }
 
+// A small persistent team for the packer.  Round 2: under OpenMP the team's idle threads spin after every parallel region;
+// the GPU boxes run inside a cgroup CPU quota (16 CPUs under 128 hardware threads), a spinning team eats the quota and the
+// whole process gets throttled (a 64-thread team: 74 ms instead of 6 ms per step).  These workers sleep on a condition
+// variable between calls and take 64-KB blocks from a shared counter while a call runs.
+class PackTeam {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::mutex call_mu;                      // one pack call at a time (concurrent callers take turns)
+    const uint8_t *in = nullptr; uint8_t *out = nullptr;
+    int64_t n = 0, nblk = 0;
+    std::atomic<int64_t> next{0};
+    int use = 0, pending = 0;
+    uint64_t gen = 0;
+    static constexpr int64_t BLK = 1 << 16;  // bytes per work item (even)
+
+    void blocks() {
+        for (;;) {
+            const int64_t b = next.fetch_add(1, std::memory_order_relaxed);
+            if (b >= nblk) return;
+            pack_range(in, b * BLK, (b + 1) * BLK < n ? (b + 1) * BLK : n, n, out);
+        }
+    }
+    void loop(int idx, uint64_t seen) {          // seen = the job generation at creation: only LATER jobs are this worker's
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_work.wait(lk, [&] { return gen != seen; });
+            seen = gen;
+            const bool mine = idx < use;
+            lk.unlock();
+            if (mine) blocks();
+            lk.lock();
+            if (--pending == 0) cv_done.notify_one();
+        }
+    }
+
+public:
+    void pack(const uint8_t *src, int64_t count, uint8_t *dst, int threads) {
+        std::lock_guard<std::mutex> call(call_mu);
+        const int64_t blocks_total = (count + BLK - 1) / BLK;
+        int nt = threads;
+        if ((int64_t)nt > blocks_total) nt = (int)blocks_total;
+        if (nt <= 1) { pack_range(src, 0, count, count, dst); return; }
+        while ((int)workers.size() < nt - 1) {
+            const int idx = (int)workers.size();
+            uint64_t g0;
+            { std::lock_guard<std::mutex> lk(mu); g0 = gen; }
+            workers.emplace_back([this, idx, g0] { loop(idx, g0); });
+            workers.back().detach();             // process-lifetime team (the library is never unloaded while a call runs)
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            in = src; out = dst; n = count; nblk = blocks_total;
+            next.store(0, std::memory_order_relaxed);
+            use = nt - 1; pending = (int)workers.size();
+            ++gen;
+        }
+        cv_work.notify_all();
+        blocks();                                // the caller is the team's last member
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
+};
+PackTeam *g_team = new PackTeam;                 // intentionally leaked: detached workers may outlive static destructors
+
 }  // namespace
 
 // n ASCII bytes -> (n+1)/2 bytes, base 2k in the low nibble and base 2k+1 in the high nibble of byte k (a missing last
-// base packs as 0).  threads <= 0: the OpenMP default.  Safe to call concurrently on different buffers.
+// base packs as 0).  threads <= 0: the hardware threads, capped by the cgroup CPU quota (see PackTeam).  Safe to call
+// concurrently on different buffers (calls take turns).
 extern "C" void pb_pack_nibbles(const uint8_t *in, int64_t n, uint8_t *out, int threads) {
     if (n <= 0) return;
-    const int64_t BLK = 1 << 16;                      // bytes per work item (even)
-    const int64_t nblk = (n + BLK - 1) / BLK;
-#if defined(_OPENMP)
-    int nt = threads > 0 ? threads : omp_get_max_threads();
-    if ((int64_t)nt > nblk) nt = (int)nblk;
-    if (nt > 1) {
-#pragma omp parallel for schedule(static) num_threads(nt)
-        for (int64_t b = 0; b < nblk; ++b) pack_range(in, b * BLK, (b + 1) * BLK < n ? (b + 1) * BLK : n, n, out);
-        return;
+    if (threads <= 0) {
+        static const int dflt = [] {
+            long hw = (long)std::thread::hardware_concurrency();
+            if (hw < 1) hw = 1;
+            if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+                char q[64]; long long period = 0;
+                if (fscanf(f, "%63s %lld", q, &period) == 2 && strcmp(q, "max") != 0 && period > 0 && atoll(q) > 0)
+                    hw = std::min<long>(hw, (long)std::max<long long>(1, (atoll(q) + period - 1) / period));
+                fclose(f);
+            }
+            return (int)hw;
+        }();
+        threads = dflt;
     }
-#else
-    (void)threads; (void)nblk;
-#endif
-    pack_range(in, 0, n, n, out);
+    g_team->pack(in, n, out, threads);
 }

@@ -223,56 +223,19 @@ __device__ __forceinline__ uint32_t pack_bases(uint32_t bA, uint32_t bB) {
     return __byte_perm(bA, bB, 0x4101);
 }
 
-// 16 bytes starting `sh` bytes into the aligned 32-byte pair p[0], p[1] (p[1] only read when `second`), as 4 words
-__device__ __forceinline__ void load_block16(const uint4 *p, unsigned sh, bool first, bool second, uint32_t *w) {
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    const uint4 a = first ? __ldcs(p) : z, b = (first && second && sh != 0) ? __ldcs(p + 1) : z;
-    const unsigned r = (sh & 3) * 8;
-    uint32_t x0, x1, x2, x3, x4;
-    switch (sh >> 2) {                   // whole-word part of the shift: static register selection per case
-        case 0: x0 = a.x; x1 = a.y; x2 = a.z; x3 = a.w; x4 = b.x; break;
-        case 1: x0 = a.y; x1 = a.z; x2 = a.w; x3 = b.x; x4 = b.y; break;
-        case 2: x0 = a.z; x1 = a.w; x2 = b.x; x3 = b.y; x4 = b.z; break;
-        default: x0 = a.w; x1 = b.x; x2 = b.y; x3 = b.z; x4 = b.w; break;
-    }
-    w[0] = __funnelshift_r(x0, x1, r); w[1] = __funnelshift_r(x1, x2, r);
-    w[2] = __funnelshift_r(x2, x3, r); w[3] = __funnelshift_r(x3, x4, r);
-}
-
 // Stage the packed read bases of a slot's columns: hbuf[c] = pack_bases(A[c], B[c]) for c < nmax, PB_PAD_H past the end
-// of a half.  Each lane of the group builds every G-th column from single-byte loads (PB_STAGE_VEC undefined), or the
-// group walks the window in 16-column blocks, one aligned 128-bit load per half and block (PB_STAGE_VEC, round-2 A/B).
+// of a half.  Each lane of the group builds every G-th column from single-byte streaming loads.
+// (Round 2 A/B on B200, profiles/r2_options: walking the window in 16-column blocks with one aligned 128-bit load per half
+// and block, funnel-shifted into place, was SLOWER -- end-trim launch 2.229 vs 2.180 ms, demux 5.420 vs 5.351 ms: the shift /
+// extract / bounds work per column outweighs the saved LSU instructions (LSU pipe 7 %), so the byte loads stay.)
 template <int G>
 __device__ __forceinline__ void stage_columns(uint32_t *hbuf, int g, const uint8_t *seqA, int nA, const uint8_t *seqB, int nB,
                                               int nmax) {
-#ifdef PB_STAGE_VEC
-    // half X's columns [16b, 16b+16) are source bytes [16b + shX, 16b + shX + 16) of the 16-byte aligned stream that starts
-    // shX = address & 15 bytes before its first base: two aligned 128-bit loads, shifted into place (load_block16)
-    const unsigned shA = (unsigned)(reinterpret_cast<uintptr_t>(seqA) & 15), shB = (unsigned)(reinterpret_cast<uintptr_t>(seqB) & 15);
-    const uint4 *baseA = reinterpret_cast<const uint4 *>(seqA - shA), *baseB = reinterpret_cast<const uint4 *>(seqB - shB);
-    const int nblk = (nmax + 15) >> 4;
-    for (int b = g; b < nblk; b += G) {
-        uint32_t wa[4], wb[4];
-        load_block16(baseA + b, shA, 16 * b < nA, 16 * b + 16 - (int)shA < nA, wa);
-        load_block16(baseB + b, shB, 16 * b < nB, 16 * b + 16 - (int)shB < nB, wb);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int c = 16 * b + k;
-            if (c < nmax) {
-                uint32_t bA = (wa[k >> 2] >> ((k & 3) * 8)) & 0xFFu, bB = (wb[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
-                if (c >= nA) bA = (uint32_t)PB_PAD_H;
-                if (c >= nB) bB = (uint32_t)PB_PAD_H;
-                hbuf[c] = pack_bases(bA, bB);
-            }
-        }
-    }
-#else
     for (int c = g; c < nmax; c += G) {
         const uint32_t bA = (c < nA) ? (uint32_t)__ldcs(seqA + c) : (uint32_t)PB_PAD_H;
         const uint32_t bB = (c < nB) ? (uint32_t)__ldcs(seqB + c) : (uint32_t)PB_PAD_H;
         hbuf[c] = pack_bases(bA, bB);
     }
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -556,6 +519,10 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
     };
 
     for (;;) {
+        // every read of the previous segment is ordered before the ring stores below.  (The lanes cannot drift apart anyway --
+        // each step's full-mask shuffle joins them, and a block is overwritten 25+ steps after its last read -- but a shuffle
+        // is not a memory barrier: compute-sanitizer racecheck reported the write-after-read pair in round 2.)
+        __syncwarp();
         if (!exhausted) {
             if (t >= T) {                      // group-uniform: this group's slot is finished (or none yet)
                 if (slot >= 0) {

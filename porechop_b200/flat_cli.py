@@ -174,7 +174,7 @@ def main():
             W.set_device(int(os.environ.get('LOCAL_RANK', rank)) % n_dev)
         dist.init_process_group('gloo')                   # host-side barrier only; the data path has no collective
         local_world = int(os.environ.get('LOCAL_WORLD_SIZE', world))
-        hostio.set_threads(max(1, (os.cpu_count() or 1) // max(local_world, 1)))    # torchrun exports OMP_NUM_THREADS=1
+        hostio.set_threads(max(1, hostio.usable_cpus() // max(local_world, 1)))    # torchrun exports OMP_NUM_THREADS=1
     if os.path.isdir(args.input):
         # an Albacore output directory (porechop.py:241-266): every *.fastq[.gz] below it in sorted order, the check
         # reads spread over the files, and Albacore's own bin (from the path) must agree with the barcode call

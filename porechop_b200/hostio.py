@@ -13,9 +13,28 @@ EXPORTED_SYMBOLS = ['pbioSetThreads', 'pbioCountLines', 'pbioLineEnds', 'pbioLin
                     'pbioFullScores', 'pbioGzipBound', 'pbioGzip', 'pbioRandomBases']
 
 
+def usable_cpus():
+    """CPUs this process can really run on at once: the affinity mask capped by the cgroup CPU quota (the GPU boxes of round 2
+    show 128 hardware threads under a quota of 16 CPUs; a larger team only gets the whole process throttled)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        n = os.cpu_count() or 1
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            q, p = f.read().split()[:2]
+        if q != 'max' and int(p) > 0:
+            n = min(n, max(1, -(-int(q) // int(p))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def _load():
     if not os.path.exists(_PATH) or os.environ.get('PB200_NO_HOSTIO'):
         return None
+    # idle OpenMP threads sleep instead of spinning (must be set before libgomp is loaded): spinning burns the CPU quota
+    os.environ.setdefault('OMP_WAIT_POLICY', 'passive')
     try:
         lib = CDLL(_PATH)
     except OSError:                 # e.g. built against a libgomp / libz this machine lacks: numpy + gzip module instead
@@ -48,6 +67,8 @@ def _load():
     lib.pbioGzip.restype = c_int64
     lib.pbioRandomBases.argtypes = [c_void_p, c_int64, c_uint64]
     lib.pbioRandomBases.restype = None
+    if not os.environ.get('OMP_NUM_THREADS'):
+        lib.pbioSetThreads(usable_cpus())
     return lib
 
 

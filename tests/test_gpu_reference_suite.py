@@ -33,12 +33,16 @@ def test_reference_unittest_suite_on_the_cuda_engine_matches_the_baseline():
     finally:
         sys.path.pop(0)
     from test_reference_suite import REPORT_TESTS
-    jobs = max(1, min(12, (os.cpu_count() or 2) // 2))
+    jobs = max(2, min(16, (os.cpu_count() or 2) // 2))
     base = R.run_mode('reference', 'oracle', REF, '', jobs)
     assert len(base) == 85
     assert sorted(k for k, v in base.items() if v != 'ok') == KNOWN_FAILING
-    patch = R.run_mode('patch', 'cuda', REF, '', jobs)
-    flat = R.run_mode('flat', 'cuda', REF, '', jobs)
+    # the two drop-ins run side by side (85 CLI-level tests each; most of the time is process start + CUDA context creation)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(2) as ex:
+        f_patch = ex.submit(R.run_mode, 'patch', 'cuda', REF, '', max(1, jobs // 2))
+        f_flat = ex.submit(R.run_mode, 'flat', 'cuda', REF, '', max(1, jobs // 2))
+        patch, flat = f_patch.result(), f_flat.result()
     out = os.path.join(ROOT, 'gpurun_out')
     if os.path.isdir(out):
         with open(os.path.join(out, 'results_r2_gpu.json'), 'w') as f:

@@ -35,4 +35,16 @@ except Exception as e:
 PY
 done
 python -m porechop_b200.build --force > /dev/null 2>&1
+if [ "${FLAT:-0}" = "1" ]; then      # flat FASTQ pipeline (bytes -> trimmed bytes) on this host + GPU, per-stage seconds
+    timeout 600 python tools/flat_pipeline_bench.py --reads ${FLAT_READS:-200000} --repeat 3 > $out/flat_pipeline.json 2> $out/flat_pipeline.err
+    echo "flat pipeline: $(cat $out/flat_pipeline.json | head -c 600)" | tee -a $out/summary.txt
+fi
+if [ "${NCU:-0}" = "1" ]; then       # launch list + full captures of the default build (never a bench value)
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_endtrim.csv \
+        python bench.py --steps 2 --warmup 1 --configs none --no-cpu-baseline > $out/bench_under_ncu.log 2>&1
+    ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 2 -c 2 -o $out/trace_kernel -f \
+        python bench.py --steps 1 --warmup 1 --configs none --no-cpu-baseline > $out/trace_under_ncu.log 2>&1
+    ncu --set full --clock-control none --import-source on -k regex:score_kernel -s 1 -c 1 -o $out/score_kernel -f \
+        python bench.py --steps 1 --warmup 1 --configs none --no-cpu-baseline --workload middle --reads 262144 > $out/score_under_ncu.log 2>&1
+fi
 cat $out/summary.txt

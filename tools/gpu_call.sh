@@ -4,7 +4,7 @@
 #   tests     smoke + the whole GPU tier (incl. the reference's own 85 CLI tests on the CUDA engine)
 #   sanitize  compute-sanitizer memcheck + racecheck over every engine path (tools/sanitize_paths.py)
 #   bench     the driver's bench line (N = 1, all configs) + the reference arm
-#   ab        A/B runs of the headline config: packed upload, vector staging (rebuilds the library; keep late)
+#   ab        run-time A/B of the headline config: packed upload, chunk sizes (compile-time A/B: tools/gpu_ab.sh)
 #   ncu       launch list of the bench command + `--set full` captures of the DP kernels (never a bench value)
 set -u
 STAGES="${STAGES:-tests bench}"
@@ -75,15 +75,6 @@ run endtrim_chunk256k --opt chunk_tasks=262144
 run endtrim_pack_chunk256k --opt h2d_pack=1 --opt chunk_tasks=262144
 run middle_default --workload middle --config-reads middle=262144
 run middle_pack --workload middle --opt h2d_pack=1
-PB200_NVCC_FLAGS=-DPB_STAGE_VEC python -m porechop_b200.build --force > $out/build_stagevec.log 2>&1
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > $out/pytest_stagevec.log 2>&1; echo "gpu parity with PB_STAGE_VEC rc=$?" | tee -a $out/summary.txt
-run endtrim_stagevec
-run demux_stagevec --workload demux --reads 65536
-run middle_stagevec --workload middle --config-reads middle=262144
-PB200_NVCC_FLAGS=-DPB_TRACE_MIN_BLOCKS=6 python -m porechop_b200.build --force > $out/build_minblocks6.log 2>&1
-run endtrim_minblocks6
-run endtrim_minblocks6_scratch160 --opt scratch_mb=160
-run demux_minblocks6 --workload demux --reads 65536
 python -m porechop_b200.build --force > /dev/null 2>&1
 run demux_bytes --workload demux --reads 65536
 fi
