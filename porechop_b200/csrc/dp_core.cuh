@@ -335,14 +335,15 @@ PB_HD uint32_t max2acc(bool use_or, uint32_t a, uint32_t b, uint32_t &accLo, uin
 #endif
 }
 // which of a cell's four flag accumulations use the ALU-pipe form: bit 0 tH, 1 tV, 2 tM, 3 tD; _A for even rows of a lane,
-// _B for odd rows.  Measured on B200 (profiles/r2_pipes, end-trim launch of 1 M 150x28 alignments): none 2.083 ms, tH only
-// (2 of the 8 accumulations per row) 1.976 ms, tH+tV on even rows 1.990, tH+tV 2.053, tH+tV+tM 2.248 -- the minimum is where
-// the hot loop's ALU and FMA-heavy instruction counts are equal (279 / 286 per 4 steps x 7 rows).
+// _B for odd rows.  Measured on B200 (profiles/r2_pipes, end-trim launch of 1 M 150x28 alignments): none 2.083 ms; one of the
+// four (2 of the 8 accumulations per row): tD 1.958, tH 1.976, tH on even rows only 2.037; tH+tV on even rows 1.990, tH+tV
+// 2.053, tH+tV+tM 2.248 -- the minimum is where the hot loop's ALU and FMA-heavy instruction counts are equal (279 / 286 per
+// 4 steps x 7 rows; ncu afterwards: both pipes 69-70 % busy, issue slots 78 %).
 #ifndef PB_FLAG_OR_A
-#define PB_FLAG_OR_A 0x1
+#define PB_FLAG_OR_A 0x8
 #endif
 #ifndef PB_FLAG_OR_B
-#define PB_FLAG_OR_B 0x1
+#define PB_FLAG_OR_B 0x8
 #endif
 
 // Query profile of the score pass (option "profile", default on).  The substitution operand of group row q depends only
@@ -367,18 +368,15 @@ PB_HD uint32_t profile_from(uint32_t v2, uint32_t sf2, uint32_t bcode, const Sco
     const uint32_t h2 = (e << 8) | (e << 24);
     return addmax2(xnor2(h2, v2), sc.subA2, sf2);
 }
-// E2 (round 2, -DPB_PROF_PLAIN_ADD): the profile word in a form that a PLAIN 32-bit add applies to both halves at once.
-// A packed s16x2 addend whose low half is negative carries 1 into the high half when added as one 32-bit number (the low
-// half of a biased X is always larger than the addend's magnitude), so that 1 is taken off the high half up front; a
-// non-negative low half never carries (biased values stay below 2^15 + |addend|).  The diagonal term S_diag + sub then is
-// an ordinary integer add -- which ptxas cannot fuse into a VIADDMNMX on the ALU pipe, the pipe that bounds the score pass
-// (ncu: ALU 65 %, FMA-heavy 22 % of their peaks) -- and the cell's maximum becomes one three-input VIMNMX3.
+// The profile word in a form that a PLAIN 32-bit add applies to both halves at once.  A packed s16x2 addend whose low half is
+// negative carries 1 into the high half when added as one 32-bit number (the low half of a biased X is always larger than
+// the addend's magnitude), so that 1 is taken off the high half up front; a non-negative low half never carries (biased
+// values stay below 2^15 + |addend|).  The diagonal term S_diag + sub then is an ordinary integer add (FMA-heavy pipe) --
+// which ptxas cannot fuse into a VIADDMNMX on the ALU pipe, the busier pipe of the score pass (ncu round 2: ALU 65 %,
+// FMA-heavy 22 %) -- and the cell's maximum becomes one three-input VIMNMX3: 3 ALU + 2 heavy instructions per row instead
+// of 4 + 1 (middle scan 28.16 -> 27.89 ms per launch on its own; 107 instead of 115 registers).
 PB_HD uint32_t profile_plain(uint32_t sub2) { return (sub2 & 0x8000u) ? sub2 - 0x10000u : sub2; }
-#ifdef PB_PROF_PLAIN_ADD
 #define PB_PROF_ENCODE(x) profile_plain(x)
-#else
-#define PB_PROF_ENCODE(x) (x)
-#endif
 PB_HD uint32_t profile_word(int q, uint32_t bcode, const Scoring &sc, const uint8_t *adA, int mA, int padA, const uint8_t *adB,
                             int mB, int padB) {
     uint32_t v2, sf2;
@@ -420,10 +418,9 @@ PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, co
     for (int r = 0; r < R; ++r) {
         // substitution (minus go) per half: codes equal -> ~(h^v) == -1 -> max(-1 + ma + 1 - go, mi - go) = ma - go
         const uint32_t sub = PROF ? subs[r] : addmax2(xnor2(h2, L.v2[r]), sc.subA2, L.sf2[r]);
-#ifdef PB_PROF_PLAIN_ADD
         const uint32_t d = PROF ? diagX + sub : add2(diagX, sub);   // S_diag + sub (biased); PROF: carry-compensated word, plain add
-#else
-        const uint32_t d = add2(diagX, sub);                        // S_diag + sub (biased)
+#if !defined(__CUDA_ARCH__) && defined(PB_CHECK_RANGES)
+        if (PROF && d != add2(diagX, (sub & 0x8000u) ? sub + 0x10000u : sub)) pb_range_violation();   // the plain add IS the packed add
 #endif
         uint32_t hs, vs, s;
         if (TRACE) {

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -121,7 +122,7 @@ class PackTeam {
     int64_t n = 0, nblk = 0;
     std::atomic<int64_t> next{0};
     int use = 0, pending = 0;
-    uint64_t gen = 0;
+    std::atomic<uint64_t> gen{0};
     static constexpr int64_t BLK = 1 << 16;  // bytes per work item (even)
 
     void blocks() {
@@ -133,9 +134,18 @@ class PackTeam {
     }
     void loop(int idx, uint64_t seen) {          // seen = the job generation at creation: only LATER jobs are this worker's
         for (;;) {
+            bool got = false;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (unsigned i = 1;; ++i) {                     // bounded polling, then sleep
+                if (gen.load(std::memory_order_acquire) != seen) { got = true; break; }
+                if ((i & 127u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) break;
+#if defined(__x86_64__)
+                _mm_pause();
+#endif
+            }
             std::unique_lock<std::mutex> lk(mu);
-            cv_work.wait(lk, [&] { return gen != seen; });
-            seen = gen;
+            if (!got) cv_work.wait(lk, [&] { return gen.load(std::memory_order_acquire) != seen; });
+            seen = gen.load(std::memory_order_acquire);
             const bool mine = idx < use;
             lk.unlock();
             if (mine) blocks();
@@ -154,7 +164,7 @@ public:
         while ((int)workers.size() < nt - 1) {
             const int idx = (int)workers.size();
             uint64_t g0;
-            { std::lock_guard<std::mutex> lk(mu); g0 = gen; }
+            { std::lock_guard<std::mutex> lk(mu); g0 = gen.load(); }
             workers.emplace_back([this, idx, g0] { loop(idx, g0); });
             workers.back().detach();             // process-lifetime team (the library is never unloaded while a call runs)
         }
@@ -163,7 +173,7 @@ public:
             in = src; out = dst; n = count; nblk = blocks_total;
             next.store(0, std::memory_order_relaxed);
             use = nt - 1; pending = (int)workers.size();
-            ++gen;
+            gen.fetch_add(1, std::memory_order_release);
         }
         cv_work.notify_all();
         blocks();                                // the caller is the team's last member

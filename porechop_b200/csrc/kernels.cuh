@@ -430,6 +430,17 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
 // only between segments.
 constexpr int PB_RING = 64;
 constexpr int PB_BLK = 32;
+// Ring entries: the packed bases of a column (byte 0 = half A, byte 1 = half B) or the column's profile-table offset -- 16 bits
+// with -DPB_RING16 (half the ring's shared memory: the profile variant then fits 6 blocks per SM; expanded with one PRMT).
+#ifdef PB_RING16
+typedef uint16_t ring_t;
+__device__ __forceinline__ ring_t ring_pack(uint32_t bA, uint32_t bB) { return (ring_t)(bA | (bB << 8)); }
+__device__ __forceinline__ uint32_t ring_bases(uint32_t x) { return __byte_perm(x, 0u, 0x1404); }   // byte1 <- A, byte3 <- B
+#else
+typedef uint32_t ring_t;
+__device__ __forceinline__ ring_t ring_pack(uint32_t bA, uint32_t bB) { return pack_bases(bA, bB); }
+__device__ __forceinline__ uint32_t ring_bases(uint32_t x) { return x; }
+#endif
 
 // CPL consecutive encoded bytes starting at an arbitrary address, in the low bytes of the result
 template <int CPL>
@@ -454,8 +465,11 @@ __device__ __forceinline__ uint64_t load_cols(const uint8_t *p) {
     }
 }
 
+// 5 blocks per SM (<= 102 registers; the profile variant needs 87-95 without spills, 40 KB of shared memory per block): the
+// score pass is latency-bound ("wait" 2.6 + shared-memory scoreboard 2.1 stall cycles per issued instruction at 4 warps per
+// scheduler, ncu round 2), so the fifth warp per scheduler pays: middle scan 28.16 -> 26.27 ms per launch on B200.
 #ifndef PB_SCORE_MIN_BLOCKS
-#define PB_SCORE_MIN_BLOCKS 4
+#define PB_SCORE_MIN_BLOCKS 5
 #endif
 // PROF = query profile (dp_core.cuh profile_word; option "profile"): every slot aligns ONE read against two adapters
 // (cross mode, even number of adapters in the class), so the R substitution operands of a column are fetched from a
@@ -474,7 +488,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
     constexpr int CPL = PB_BLK / G;          // columns of a block each lane fetches
     static_assert(!PROF || R == 8, "the profile variant fetches 8 operands per step");
     __shared__ ScoutCand scratch[PB_WARPS_PER_BLOCK][2 * 32];
-    __shared__ uint32_t rings[PB_WARPS_PER_BLOCK][SPW][PB_RING];
+    __shared__ ring_t rings[PB_WARPS_PER_BLOCK][SPW][PB_RING];
     __shared__ __align__(16) uint32_t profs[PROF ? PB_WARPS_PER_BLOCK * SPW * ProfGeom<G, R>::STRIDE : 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, g = lane % G;
@@ -482,7 +496,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
     const int64_t n_tasks = ts.n_tasks;
     const int64_t n_slots = (n_tasks + 1) / 2;
     ScoutCand *cand = scratch[warp];
-    uint32_t *ring = rings[warp][grp];
+    ring_t *ring = rings[warp][grp];
     // this lane's rows of the group's profile table (PROF): word [b * ROWS + r] = operand of row g*R + r + 1 for base code b
     uint32_t *myprof = profs + (PROF ? ((size_t)(warp * SPW + grp) * ProfGeom<G, R>::STRIDE + g * R) : 0);
 
@@ -496,7 +510,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
     gA = make_geom(0, 0, G, R); gB = gA;
     L.botX = sc.borderX2; L.botV = sc.negb2;
     if (PROF) {      // a group that never gets a slot still runs the hot segments on dead state: its ring must hold valid offsets
-        for (int c = g; c < PB_RING; c += G) ring[c] = 0u;
+        for (int c = g; c < PB_RING; c += G) ring[c] = (ring_t)0;
         __syncwarp();
     }
 
@@ -514,7 +528,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
             const int col = c0 + c;
             const uint32_t bA = (col < nA) ? (uint32_t)((pendA >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H;
             const uint32_t bB = (col < nB) ? (uint32_t)((pendB >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H;
-            ring[col & (PB_RING - 1)] = PROF ? (bA >> 4) * (uint32_t)ProfGeom<G, R>::ROWS : pack_bases(bA, bB);
+            ring[col & (PB_RING - 1)] = PROF ? (ring_t)((bA >> 4) * (uint32_t)ProfGeom<G, R>::ROWS) : ring_pack(bA, bB);
         }
     };
 
@@ -582,21 +596,44 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
         // all 32 steps: straight-line code, fast scout only.  Exhausted groups just compute on dead state.
         const bool hot = __all_sync(0xffffffffu, exhausted || (t >= G - 1 && t + PB_BLK < nmin));
         if (hot) {
+#ifdef PB_SCORE_PREFETCH
+            // (round-2 experiment) the profile operands of step k+1 are fetched while step k computes: the ring load and the two
+            // dependent 128-bit loads (~60 cycles of shared-memory latency) leave the head of every step's dependency chain
+            uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+            if (PROF) {
+                const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + ring[(t - g) & (PB_RING - 1)]);
+                n0 = pp[0]; n1 = pp[1];
+            }
+#endif
 #pragma unroll 4
             for (int k = 0; k < PB_BLK; ++k) {
                 uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
                 uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
                 if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
                 const int j = t - g + 1;
-                const uint32_t hx = ring[(j - 1) & (PB_RING - 1)];      // packed bases, or (PROF) the table offset of the base
+#ifdef PB_SCORE_PREFETCH
+                if (PROF) {
+                    const uint4 p0 = n0, p1 = n1;
+                    if (k + 1 < PB_BLK) {      // the next segment's first column is published at the boundary, not before
+                        const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + ring[j & (PB_RING - 1)]);
+                        n0 = pp[0]; n1 = pp[1];
+                    }
+                    const uint32_t subs[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                    lane_step<R, false, false, true>(L, recvS, recvV, 0u, sc, nullptr, nullptr, subs);
+                } else {
+                    lane_step<R, false, false>(L, recvS, recvV, ring_bases(ring[(j - 1) & (PB_RING - 1)]), sc, nullptr);
+                }
+#else
+                const uint32_t hx = ring[(j - 1) & (PB_RING - 1)];      // packed bases (ring form), or (PROF) the table offset of the base
                 if (PROF) {
                     const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + hx);
                     const uint4 p0 = pp[0], p1 = pp[1];
                     const uint32_t subs[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
                     lane_step<R, false, false, true>(L, recvS, recvV, 0u, sc, nullptr, nullptr, subs);
                 } else {
-                    lane_step<R, false, false>(L, recvS, recvV, hx, sc, nullptr);
+                    lane_step<R, false, false>(L, recvS, recvV, ring_bases(hx), sc, nullptr);
                 }
+#endif
                 lane_track_lastrow<R>(L, j, sc);
                 ++t;
             }
@@ -608,7 +645,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                 if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
                 const int j = t - g + 1;
                 if (j >= 1 && j <= nmax) {          // nmax == 0 for exhausted groups
-                    const uint32_t h2 = ring[(j - 1) & (PB_RING - 1)];
+                    const uint32_t h2 = ring[(j - 1) & (PB_RING - 1)];          // ring form: see ring_bases
                     uint32_t vr[R];
                     if (PROF) {
                         const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + h2);
@@ -616,7 +653,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                         const uint32_t subs[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
                         lane_step<R, false, true, true>(L, recvS, recvV, 0u, sc, nullptr, vr, subs);
                     } else {
-                        lane_step<R, false, true>(L, recvS, recvV, h2, sc, nullptr, vr);
+                        lane_step<R, false, true>(L, recvS, recvV, ring_bases(h2), sc, nullptr, vr);
                     }
                     if (j < nmin) lane_track_lastrow<R>(L, j, sc);
                     else lane_track_general<R>(L, g, j, gA, gB, vr, sc);

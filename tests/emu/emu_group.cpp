@@ -113,8 +113,8 @@ void run_score_group(int G, const Half &A, const Half &B, const Scoring &sc, End
         for (int g = 0; g < G; ++g)
             for (int b = 0; b < 6; ++b)
                 for (int r = 0; r < R; ++r)
-                    prof[((size_t)g * 6 + b) * R + r] = profile_word(g * R + r + 1, (uint32_t)b, sc, A.ad.data() + tA.ad_off, tA.m,
-                                                                     gA.pad, B.ad.data() + tB.ad_off, tB.m, gB.pad);
+                    prof[((size_t)g * 6 + b) * R + r] = PB_PROF_ENCODE(profile_word(g * R + r + 1, (uint32_t)b, sc, A.ad.data() + tA.ad_off,
+                                                                                    tA.m, gA.pad, B.ad.data() + tB.ad_off, tB.m, gB.pad));
     std::vector<uint32_t> sS((size_t)G), sV((size_t)G);
     for (int t = 0; t < T; ++t) {
         for (int g = 0; g < G; ++g) { sS[g] = L[g].botX; sV[g] = L[g].botV; }

@@ -37,7 +37,7 @@ def build(force=False):
     srcs = [os.path.join(CSRC, f) for f in ('engine.cu', 'kernels.cuh', 'dp_core.cuh', 'hostpack.cpp')] + \
            [os.path.join(HERE, f) for f in ('pbsim_cuda.h', 'pbsim.cpp', 'build_sim.py')] + \
            [os.path.join(ROOT, 'include', 'porechop_b200.h')]
-    # PB200_SIM_FLAGS: extra -D switches of the product sources (the compile-time A/B options, e.g. -DPB_PROF_PLAIN_ADD); the
+    # PB200_SIM_FLAGS: extra -D switches of the product sources (the compile-time A/B options, e.g. -DPB_SCORE_PREFETCH); the
     # library is rebuilt whenever they differ from the ones it was built with
     flags = os.environ.get('PB200_SIM_FLAGS', '').split()
     stamp = os.path.join(BUILD, 'flags.txt')
