@@ -430,6 +430,11 @@ def measure_gpu(workload, args, ctx, K, Wm, main):
         dev.append((db, do, abuf, aoff, dout, max_len))
     torch.cuda.synchronize()
     in_bytes = sum(h[0].numel() + h[1].numel() * 8 + len(h[2]) + len(h[3]) * 4 for h in host)
+    # bytes that really cross PCIe: with the packed upload (h2d_pack, "auto" resolves per host) the sequences travel as 4-bit codes
+    # (a submit = one chunk of every batch; the engine packs submits of >= 32 MB)
+    per_submit = sum(h[0].numel() * min(1.0, h[4] / max(h[1].numel() - 1, 1)) for h in host)
+    packed_upload = W.get_option('h2d_pack') == 1 or (bool(W.get_option('h2d_pack_large_submit')) and per_submit >= (32 << 20))
+    h2d_bytes = in_bytes - sum(h[0].numel() // 2 for h in host) if packed_upload else in_bytes
     out_bytes = sum((h[1].numel() - 1) * (len(h[3]) - 1) * 36 for h in host)
 
     bench_stream = ctx['stream']
@@ -607,7 +612,10 @@ def measure_gpu(workload, args, ctx, K, Wm, main):
         'timing': {'l2': 'inputs %.0f MB per step and rank exceed the 126 MB L2' % (in_bytes / 1e6) if in_bytes > 126e6 else
                          'inputs %.0f MB per step' % (in_bytes / 1e6), 'clock': 'CUDA events on the launching stream (value), '
                    'host clock around synchronous C-ABI calls (e2e); max over ranks'},
-        'e2e': {'value': e2e_value, 'unit': 'reads/s', 'h2d_bytes_per_step': in_bytes, 'd2h_bytes_per_step': out_bytes,
+        'e2e': {'value': e2e_value, 'unit': 'reads/s', 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': out_bytes,
+                'host_input_bytes_per_step': in_bytes,
+                'upload': ('4-bit codes packed by %d host threads (h2d_pack=%d)' % (W.get_option('pack_threads'), W.get_option('h2d_pack')))
+                          if packed_upload else 'ASCII bytes as they cross the ABI (h2d_pack=%d)' % W.get_option('h2d_pack'),
                 'ms_per_step': e2e_ms / K, 'gcups': total_cells * K / (e2e_ms / 1e3) / 1e9,
                 'path': ('adapterEndDecisions (host buffers, pinned), decisions come back' if dec_out is not None else
                          'adapterAlignmentBatchMulti (host buffers, pinned), %d submit(s) per step per rank' % len(calls)) +

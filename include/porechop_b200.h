@@ -122,8 +122,9 @@ int pb200FormatRecord(const int32_t *record, char *buf, int buflen);
 
 /* Host-side Dna5 conversion of the packed upload path (option "h2d_pack"): n ASCII bases -> (n+1)/2 bytes, the code
  * of base 2k (A/a=0 C/c=1 G/g=2 T/t/U/u=3, anything else 4: seqan/basic/alphabet_residue_tabs.h:113-140) in the low
- * nibble of byte k and base 2k+1 in the high nibble.  Pure host code (AVX2 when the CPU has it, OpenMP; threads <= 0 =
- * the OpenMP default); exported so that tests and hosts that already hold packed reads can use the same packer. */
+ * nibble of byte k and base 2k+1 in the high nibble.  Pure host code (AVX-512BW / AVX2 when the CPU has it, its own thread
+ * team; threads <= 0 = the hardware threads the cgroup CPU quota allows); exported so that tests and hosts that already hold
+ * packed reads can use the same packer. */
 int pb200PackNibbles(const uint8_t *ascii, int64_t n, uint8_t *packed, int threads);
 
 /* ---- device / diagnostics ------------------------------------------------------------------------------ */
@@ -148,14 +149,20 @@ int pb200TimingReadKinds(double *ms, long long *launches, double *window_cells, 
  *   "scratch_mb"  cap on the resident trace scratch in MB (default 128; 72 keeps it L2-resident)
  *   "hbuf"        staging of a slot's packed bases: "auto" | "smem" | "global"
  *   "h2d_pack"    1 = the host-buffer calls convert the sequences to 4-bit codes on the host cores (a packer thread that
- *                 runs ahead of the submit loop) and upload half the bytes; "pack_threads" = host threads of the packer
- *                 (default = hardware threads / LOCAL_WORLD_SIZE, at most 32)
+ *                 runs ahead of the submit loop) and upload half the bytes; 0 = never; -1 (default) = auto: submits of at
+ *                 least 32 MB when the packer team has 12 or more threads; "pack_threads" = host threads of the packer
+ *                 (default = the hardware threads the cgroup CPU quota allows / LOCAL_WORLD_SIZE, minus two for the submit
+ *                 and driver threads, at most 32)
  *   "profile"     1 (default) = the long-read score pass fetches its substitution operands from a query profile in shared
  *                 memory when every slot is one read x two adapters (cross-product mode); 0 = always computed
  *   "tight_window" 1 (default) = second-pass windows sized per alignment from the end cell's row and score; 0 = the
  *                 per-adapter worst case
  * (round 2 measured and removed "short2p", "rowoff" and the trace-kernel profiles: profiles/r2_options) */
 int pb200SetOption(const char *name, const char *value);
+/* Current value of an integer tunable ("h2d_pack", "pack_threads", "tight_window", "profile", "scratch_mb", "direct_max",
+ * "chunk_tasks", "hbuf" as 0/1/2), or "h2d_pack_large_submit": what h2d_pack = auto resolves to for a large submit on this
+ * host (1 = packed).  -1 for an unknown name. */
+int pb200GetOption(const char *name);
 
 enum {
     PB200_OK = 0,

@@ -85,7 +85,7 @@ EXPORTED_SYMBOLS = ['adapterAlignment', 'freeCString', 'adapterAlignmentBatch', 
                     'adapterAlignmentBatchDevice', 'adapterEndDecisions', 'pb200TrimThresholdTable',
                     'pb200FormatRecord', 'pb200DeviceCount', 'pb200SetDevice', 'pb200Synchronize', 'pb200LastError',
                     'pb200KernelLaunches', 'pb200TimingEnable', 'pb200TimingRead', 'pb200TimingReadKinds', 'pb200SetOption',
-                    'pb200PackNibbles']
+                    'pb200GetOption', 'pb200PackNibbles']
 
 RECORD_INTS = 9
 SCORE_EMPTY = -2147483648
@@ -317,3 +317,10 @@ def pack_nibbles(ascii_buf, threads=0):
 
 def set_option(name, value):
     _check(C_LIB.pb200SetOption(name.encode(), str(value).encode()))
+
+
+def get_option(name):
+    """current integer value of a tunable (pb200GetOption); 'h2d_pack_large_submit' = what h2d_pack=auto resolves to here"""
+    C_LIB.pb200GetOption.argtypes = [c_char_p]
+    C_LIB.pb200GetOption.restype = c_int
+    return int(C_LIB.pb200GetOption(name.encode()))

@@ -102,7 +102,8 @@ struct Options {
     int scratch_mb = 128;          // cap on the resident trace scratch (MB); 72 keeps it L2-resident at ~10% lower speed
     int profile = 1;               // 1: score pass fetches the substitution operands from a shared-memory query profile (same-read slots)
     int tight_window = 1;          // 1: second-pass windows sized per alignment from the end cell's row and score (window_cols)
-    int h2d_pack = 0;              // 1: host-buffer API converts to 4-bit codes on the host cores and uploads half the bytes
+    int h2d_pack = -1;             // 1: host-buffer API converts to 4-bit codes on the host cores and uploads half the bytes; 0: never;
+                                   // -1 (default) = auto: for submits of >= 32 MB when the packer team has >= 12 threads (pack_wanted)
     int pack_threads = 0;          // host threads of the packer (default: hardware threads / ranks on the node, at most 32)
     int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
 };
@@ -707,6 +708,17 @@ int64_t chunk_cap(size_t k, int64_t total_tasks) {
     return std::max<int64_t>(4096, g_opt.chunk_tasks >> (3 - k));
 }
 
+// Packed upload or not for a submit of `total_bytes` of sequence.  Measured on B200 + Xeon 8562Y+ under a 16-CPU quota
+// (round 2, 316 MB per step): the packed path is bound by the host conversion, ~51 GB/s with a 14-thread team = 6.2 ms per
+// step against 6.8 ms for the plain upload (PCIe) and 4.2 ms of kernels; with 8 threads or fewer it is slower than PCIe.  So
+// "auto" packs only large submits and only when the team is large enough (one rank per GPU on a box with few CPUs per rank --
+// e.g. 8 ranks under that quota -- uploads the ASCII bytes as they are).
+bool pack_wanted(int64_t total_bytes) {
+    if (total_bytes <= 0 || g_opt.h2d_pack == 0) return false;
+    if (g_opt.h2d_pack > 0) return true;
+    return g_opt.pack_threads >= 12 && total_bytes >= (32ll << 20);
+}
+
 // One planned (and, with h2d_pack, packed) chunk on its way from the planner to the submit loop.
 struct PackItem {
     size_t job = 0;
@@ -825,7 +837,7 @@ int run_cross_jobs(Engine &E, std::vector<CrossJob> &jobs, int ma, int mi, int g
     }
     int64_t total_bytes = 0;
     for (const CrossJob &J : jobs) if (J.n_seqs > 0 && J.n_adapters > 0) total_bytes += J.seq_off[J.n_seqs] - J.seq_off[0];
-    const bool packed = g_opt.h2d_pack != 0 && total_bytes > 0;
+    const bool packed = pack_wanted(total_bytes);
     Packer *PK = nullptr;
     if (packed) {
         if (!E.packer) {
@@ -1420,6 +1432,21 @@ int pb200Synchronize(void) {
         CK(cudaStreamSynchronize(E.st[i].stream));
     }
     return rc_final;
+}
+
+int pb200GetOption(const char *name) {
+    load_env_options();
+    if (!name) return -1;
+    if (!strcmp(name, "h2d_pack")) return g_opt.h2d_pack;
+    if (!strcmp(name, "h2d_pack_large_submit")) return pack_wanted(1ll << 40) ? 1 : 0;   // what "auto" resolves to for a large submit
+    if (!strcmp(name, "pack_threads")) return g_opt.pack_threads;
+    if (!strcmp(name, "tight_window")) return g_opt.tight_window;
+    if (!strcmp(name, "profile")) return g_opt.profile;
+    if (!strcmp(name, "scratch_mb")) return g_opt.scratch_mb;
+    if (!strcmp(name, "hbuf")) return g_opt.hbuf_mode;
+    if (!strcmp(name, "direct_max")) return (int)std::min<int64_t>(g_opt.direct_max, INT_MAX);
+    if (!strcmp(name, "chunk_tasks")) return (int)std::min<int64_t>(g_opt.chunk_tasks, INT_MAX);
+    return -1;
 }
 
 int pb200SetOption(const char *name, const char *value) {

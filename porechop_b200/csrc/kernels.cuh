@@ -430,9 +430,10 @@ trace_kernel(const TaskSrc ts, const uint8_t *__restrict__ seq,
 // only between segments.
 constexpr int PB_RING = 64;
 constexpr int PB_BLK = 32;
-// Ring entries: the packed bases of a column (byte 0 = half A, byte 1 = half B) or the column's profile-table offset -- 16 bits
-// with -DPB_RING16 (half the ring's shared memory: the profile variant then fits 6 blocks per SM; expanded with one PRMT).
-#ifdef PB_RING16
+// Ring entries: the packed bases of a column (byte 0 = half A, byte 1 = half B, expanded with one PRMT) or the column's
+// profile-table offset, 16 bits each: with 4 KB of ring per block the profile variant (36 KB) fits 6 blocks per SM.
+// (-DPB_RING32: the round-1 layout, 32-bit entries in pack_bases form.)
+#ifndef PB_RING32
 typedef uint16_t ring_t;
 __device__ __forceinline__ ring_t ring_pack(uint32_t bA, uint32_t bB) { return (ring_t)(bA | (bB << 8)); }
 __device__ __forceinline__ uint32_t ring_bases(uint32_t x) { return __byte_perm(x, 0u, 0x1404); }   // byte1 <- A, byte3 <- B
@@ -465,11 +466,16 @@ __device__ __forceinline__ uint64_t load_cols(const uint8_t *p) {
     }
 }
 
-// 5 blocks per SM (<= 102 registers; the profile variant needs 87-95 without spills, 40 KB of shared memory per block): the
-// score pass is latency-bound ("wait" 2.6 + shared-memory scoreboard 2.1 stall cycles per issued instruction at 4 warps per
-// scheduler, ncu round 2), so the fifth warp per scheduler pays: middle scan 28.16 -> 26.27 ms per launch on B200.
+// 6 blocks per SM (<= 85 registers: the profile variant compiles to 79-84 without spills; 36 KB of shared memory per block
+// with 16-bit ring entries): the score pass is latency-bound ("wait" 2.6 + shared-memory scoreboard 2.1 stall cycles per
+// issued instruction at 4 warps per scheduler, ncu round 2), so more resident warps pay -- middle scan on B200: 28.16 ms per
+// launch at 4 blocks, 26.27 at 5, 24.28 at 6.  (Fetching the profile operands one step ahead did not: 26.27 / 24.33.)
 #ifndef PB_SCORE_MIN_BLOCKS
-#define PB_SCORE_MIN_BLOCKS 5
+#define PB_SCORE_MIN_BLOCKS 6
+#endif
+// the computed-operand variant keeps the row operands (16 more registers): 5 blocks per SM (96 registers) without spilling
+#ifndef PB_SCORE_MIN_BLOCKS_NOPROF
+#define PB_SCORE_MIN_BLOCKS_NOPROF 5
 #endif
 // PROF = query profile (dp_core.cuh profile_word; option "profile"): every slot aligns ONE read against two adapters
 // (cross mode, even number of adapters in the class), so the R substitution operands of a column are fetched from a
@@ -481,7 +487,7 @@ template <int G, int R> struct ProfGeom {
     static constexpr int STRIDE = 6 * ROWS + 16;        // words per group; +64 B so neighbouring groups start in other banks
 };
 template <int G, int R, bool PROF = false>
-__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PB_SCORE_MIN_BLOCKS)
+__global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PROF ? PB_SCORE_MIN_BLOCKS : PB_SCORE_MIN_BLOCKS_NOPROF)
 score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
              const uint8_t *__restrict__ seq, const uint8_t *__restrict__ ads, Scoring sc, EndCell *__restrict__ ends) {
     constexpr int SPW = 32 / G;
@@ -514,20 +520,31 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
         __syncwarp();
     }
 
-    // fetch this lane's CPL columns of block `blk` (raw bytes; columns past the end are fixed up when stored)
+    // fetch this lane's CPL columns of block `blk` (raw bytes; columns past the end are fixed up when stored).  PROF: both
+    // halves read sequence A, only its bytes are fetched.
+    // (Round 2, ncu source view of the middle scan: fetch + store were 4.2 % of the kernel's instructions and 1.4 % of its
+    // stall samples, the loads alone 0.9 % -- the most a TMA bulk copy into the ring could remove, since the byte -> ring
+    // entry conversion and the shared-memory stores stay; not built.  Skipping half B and the per-column bounds tests of
+    // interior blocks in the profile variant removes about a third of it.)
     auto fetch = [&](int blk) {
         const int c0 = blk * PB_BLK + g * CPL;
         pendA = (c0 < nA) ? load_cols<CPL>(seqA + c0) : 0ull;
-        pendB = (c0 < nB) ? load_cols<CPL>(seqB + c0) : 0ull;
+        if (!PROF) pendB = (c0 < nB) ? load_cols<CPL>(seqB + c0) : 0ull;
     };
     // store the pending block into the ring as packed columns
     auto store = [&](int blk) {
         const int c0 = blk * PB_BLK + g * CPL;
+        if (PROF && c0 + CPL <= nA) {        // interior block: every column is a real base of sequence A
+#pragma unroll
+            for (int c = 0; c < CPL; ++c)
+                ring[(c0 + c) & (PB_RING - 1)] = (ring_t)((uint32_t)((pendA >> (8 * c + 4)) & 0xFu) * (uint32_t)ProfGeom<G, R>::ROWS);
+            return;
+        }
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             const int col = c0 + c;
             const uint32_t bA = (col < nA) ? (uint32_t)((pendA >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H;
-            const uint32_t bB = (col < nB) ? (uint32_t)((pendB >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H;
+            const uint32_t bB = PROF ? bA : ((col < nB) ? (uint32_t)((pendB >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H);
             ring[col & (PB_RING - 1)] = PROF ? (ring_t)((bA >> 4) * (uint32_t)ProfGeom<G, R>::ROWS) : ring_pack(bA, bB);
         }
     };
@@ -596,34 +613,12 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
         // all 32 steps: straight-line code, fast scout only.  Exhausted groups just compute on dead state.
         const bool hot = __all_sync(0xffffffffu, exhausted || (t >= G - 1 && t + PB_BLK < nmin));
         if (hot) {
-#ifdef PB_SCORE_PREFETCH
-            // (round-2 experiment) the profile operands of step k+1 are fetched while step k computes: the ring load and the two
-            // dependent 128-bit loads (~60 cycles of shared-memory latency) leave the head of every step's dependency chain
-            uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
-            if (PROF) {
-                const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + ring[(t - g) & (PB_RING - 1)]);
-                n0 = pp[0]; n1 = pp[1];
-            }
-#endif
 #pragma unroll 4
             for (int k = 0; k < PB_BLK; ++k) {
                 uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
                 uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
                 if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
                 const int j = t - g + 1;
-#ifdef PB_SCORE_PREFETCH
-                if (PROF) {
-                    const uint4 p0 = n0, p1 = n1;
-                    if (k + 1 < PB_BLK) {      // the next segment's first column is published at the boundary, not before
-                        const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + ring[j & (PB_RING - 1)]);
-                        n0 = pp[0]; n1 = pp[1];
-                    }
-                    const uint32_t subs[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-                    lane_step<R, false, false, true>(L, recvS, recvV, 0u, sc, nullptr, nullptr, subs);
-                } else {
-                    lane_step<R, false, false>(L, recvS, recvV, ring_bases(ring[(j - 1) & (PB_RING - 1)]), sc, nullptr);
-                }
-#else
                 const uint32_t hx = ring[(j - 1) & (PB_RING - 1)];      // packed bases (ring form), or (PROF) the table offset of the base
                 if (PROF) {
                     const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + hx);
@@ -633,7 +628,6 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                 } else {
                     lane_step<R, false, false>(L, recvS, recvV, ring_bases(hx), sc, nullptr);
                 }
-#endif
                 lane_track_lastrow<R>(L, j, sc);
                 ++t;
             }
