@@ -149,7 +149,7 @@ int pb200TimingReadKinds(double *ms, long long *launches, double *window_cells, 
  *   "scratch_mb"  cap on the resident trace scratch in MB (default 128; 72 keeps it L2-resident)
  *   "hbuf"        staging of a slot's packed bases: "auto" | "smem" | "global"
  *   "h2d_pack"    1 = the host-buffer calls convert the sequences to 4-bit codes on the host cores (a packer thread that
- *                 runs ahead of the submit loop) and upload half the bytes; 0 = never; -1 (default) = auto: submits of at
+ *                 runs ahead of the submit loop) and upload half the bytes; 0 (default) = never; -1 = auto: submits of at
  *                 least 32 MB when the packer team has 12 or more threads; "pack_threads" = host threads of the packer
  *                 (default = the hardware threads the cgroup CPU quota allows / LOCAL_WORLD_SIZE, minus two for the submit
  *                 and driver threads, at most 32)

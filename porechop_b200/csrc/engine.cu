@@ -102,8 +102,8 @@ struct Options {
     int scratch_mb = 128;          // cap on the resident trace scratch (MB); 72 keeps it L2-resident at ~10% lower speed
     int profile = 1;               // 1: score pass fetches the substitution operands from a shared-memory query profile (same-read slots)
     int tight_window = 1;          // 1: second-pass windows sized per alignment from the end cell's row and score (window_cols)
-    int h2d_pack = -1;             // 1: host-buffer API converts to 4-bit codes on the host cores and uploads half the bytes; 0: never;
-                                   // -1 (default) = auto: for submits of >= 32 MB when the packer team has >= 12 threads (pack_wanted)
+    int h2d_pack = 0;              // 1: host-buffer API converts to 4-bit codes on the host cores and uploads half the bytes; 0 (default):
+                                   // never; -1 = auto: for submits of >= 32 MB when the packer team has >= 12 threads (pack_wanted)
     int pack_threads = 0;          // host threads of the packer (default: hardware threads / ranks on the node, at most 32)
     int hbuf_mode = 0;             // 0 auto, 1 shared memory, 2 global scratch (staging of a slot's packed bases)
 };
@@ -712,7 +712,10 @@ int64_t chunk_cap(size_t k, int64_t total_tasks) {
 // (round 2, 316 MB per step): the packed path is bound by the host conversion, ~51 GB/s with a 14-thread team = 6.2 ms per
 // step against 6.8 ms for the plain upload (PCIe) and 4.2 ms of kernels; with 8 threads or fewer it is slower than PCIe.  So
 // "auto" packs only large submits and only when the team is large enough (one rank per GPU on a box with few CPUs per rank --
-// e.g. 8 ranks under that quota -- uploads the ASCII bytes as they are).
+// e.g. 8 ranks under that quota -- uploads the ASCII bytes as they are).  The gain depends on how many host cycles the
+// process really gets: repeated runs on the same box gave 6.2-6.7 ms packed (once 8.2 ms inside a longer bench run) against
+// a steady 6.8 ms plain, and non-temporal stores in the packer made it slower (7.06 vs 6.66 ms: the DMA engine then reads
+// the codes from DRAM instead of the last-level cache) -- so the default stays the plain upload and packing is an option.
 bool pack_wanted(int64_t total_bytes) {
     if (total_bytes <= 0 || g_opt.h2d_pack == 0) return false;
     if (g_opt.h2d_pack > 0) return true;

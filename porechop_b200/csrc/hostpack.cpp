@@ -86,7 +86,8 @@ __attribute__((target("avx512f,avx512bw"))) void pack_avx512(const uint8_t *in, 
     int64_t i = i0;
     // the packed bytes are only read back by the DMA engine: non-temporal stores skip the read-for-ownership of the output
     // lines (a third of the loop's memory traffic) when the destination is 32-byte aligned (the engine's pinned buffers are)
-    const bool stream = ((reinterpret_cast<uintptr_t>(out) + (uintptr_t)(i0 >> 1)) & 31) == 0;
+    static const bool want_stream = getenv("PB200_PACK_NT") && atoi(getenv("PB200_PACK_NT")) != 0;   // A/B switch (round 2), default off
+    const bool stream = want_stream && ((reinterpret_cast<uintptr_t>(out) + (uintptr_t)(i0 >> 1)) & 31) == 0;
     for (; i + 64 <= i1; i += 64) {
         const __m512i x = _mm512_loadu_si512(reinterpret_cast<const void *>(in + i));
         const __m512i f = _mm512_and_si512(x, fold);
