@@ -399,14 +399,12 @@ template <int R> PB_HD int trace_shift(int h, int r) { return (R <= 4) ? (4 * r 
 //       bit3 tH : horizontal gap extended  (h_ext >= h_open, ties -> extend)
 //   vr          : KEEPV only -- Vs[j][row] of every owned row (the final-column scout needs it for the end-cell
 //                 correction flags); the hot path does not keep these registers alive
-// Pipe balance of the trace pass (per row, sm_100a): VIMNMX x4, VIADDMNMX, LOP3, VIADD.16x2 run on the ALU pipe;
-// the 8 predicated flag adds and plain 32-bit subtractions run on the FMA pipe.  The two gap extensions use the
-// packed ALU add, the X update the plain subtraction: 9 ALU + 9 FMA instructions per row.
-#ifndef PB_EXT_ON_FMA
+// Pipe balance of the trace pass (per row, sm_100a; measured in round 2, see max2acc): VIMNMX x4, VIADDMNMX, LOP3 and the
+// two xor flag ops run on the ALU pipe (8); the three packed adds (VIADD.16x2), the six predicated flag adds and the X
+// update run on the FMA-heavy pipe (10); the per-step overhead (selects, scout, index arithmetic) is mostly ALU work, which
+// evens the two out over a chunk.  (The gap extension as a plain subtraction instead of the packed add -- both are
+// FMA-heavy work -- measured the same: 2.075 vs 2.083 ms.)
 #define PB_EXT(x) add2((x), sc.ge2)
-#else
-#define PB_EXT(x) subm2((x), sc.geMag2)
-#endif
 //   PROF / subs : the R substitution operands of this column are given (query profile, see profile_word) instead of being
 //                 computed from h2 -- two ALU-pipe instructions per row less; only when both halves read the same base
 template <int R, bool TRACE, bool KEEPV = false, bool PROF = false>

@@ -482,9 +482,20 @@ __device__ __forceinline__ uint64_t load_cols(const uint8_t *p) {
 // per-group table in shared memory (6 base codes x G*R rows, two 128-bit loads per step) instead of being computed
 // (LOP3 + VIADDMNMX per row): 5 instead of 7 instructions per row, 4 instead of 6 on the ALU pipe -- the pipe that bounds
 // this kernel.  The ring then holds the table offset of a column's base instead of the packed bases.
+// Shared-memory layout (round 2, ncu: the shared-memory data pipe of this kernel was 97 % busy with 2.6x the ideal number of
+// wavefronts -- bank conflicts, not bytes, bounded the score pass):
+//   profile table   per group and base code two PLANES of G x 4 words: plane 0 holds the operands of every lane's rows 0..3,
+//                   plane 1 those of rows 4..7, lane g's four words at g*4.  A 128-bit load of 8 consecutive lanes then reads 32
+//                   consecutive words (one wavefront); with G = 4 the two groups of a quarter-warp sit 16 banks apart
+//                   (STRIDE = 16 mod 32).  (Round 1 kept a lane's 8 words together: the first load of 8 lanes touched only
+//                   half the banks, twice.)
+//   ring            every group's ring is padded to 64 + 2G entries = 32 + G words: all groups of a warp read the same ring index
+//                   in the same instruction, and unpadded rings put that index in the same bank for every group (8-way).
 template <int G, int R> struct ProfGeom {
     static constexpr int ROWS = G * R;
-    static constexpr int STRIDE = 6 * ROWS + 16;        // words per group; +64 B so neighbouring groups start in other banks
+    static constexpr int PLANE = 4 * G;                 // words per plane
+    static constexpr int STRIDE = 6 * ROWS + 16;        // words per group; = 16 mod 32
+    static constexpr int RING = PB_RING + 2 * G;        // ring entries per group incl. padding (entries 64.. are never used)
 };
 template <int G, int R, bool PROF = false>
 __global__ void __launch_bounds__(PB_WARPS_PER_BLOCK * 32, PROF ? PB_SCORE_MIN_BLOCKS : PB_SCORE_MIN_BLOCKS_NOPROF)
@@ -494,7 +505,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
     constexpr int CPL = PB_BLK / G;          // columns of a block each lane fetches
     static_assert(!PROF || R == 8, "the profile variant fetches 8 operands per step");
     __shared__ ScoutCand scratch[PB_WARPS_PER_BLOCK][2 * 32];
-    __shared__ ring_t rings[PB_WARPS_PER_BLOCK][SPW][PB_RING];
+    __shared__ __align__(16) ring_t rings[PB_WARPS_PER_BLOCK][SPW][ProfGeom<G, R>::RING];
     __shared__ __align__(16) uint32_t profs[PROF ? PB_WARPS_PER_BLOCK * SPW * ProfGeom<G, R>::STRIDE : 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, g = lane % G;
@@ -504,7 +515,7 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
     ScoutCand *cand = scratch[warp];
     ring_t *ring = rings[warp][grp];
     // this lane's rows of the group's profile table (PROF): word [b * ROWS + r] = operand of row g*R + r + 1 for base code b
-    uint32_t *myprof = profs + (PROF ? ((size_t)(warp * SPW + grp) * ProfGeom<G, R>::STRIDE + g * R) : 0);
+    uint32_t *myprof = profs + (PROF ? ((size_t)(warp * SPW + grp) * ProfGeom<G, R>::STRIDE + g * 4) : 0);
 
     Lane<R> L;
     HalfGeom gA, gB;
@@ -531,22 +542,34 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
         pendA = (c0 < nA) ? load_cols<CPL>(seqA + c0) : 0ull;
         if (!PROF) pendB = (c0 < nB) ? load_cols<CPL>(seqB + c0) : 0ull;
     };
-    // store the pending block into the ring as packed columns
+    // store the pending block into the ring as packed columns: this lane's CPL entries with ONE store (16 / 8 / 4 / 2 bytes;
+    // the group rings and a lane's first entry are aligned to that size)
     auto store = [&](int blk) {
         const int c0 = blk * PB_BLK + g * CPL;
+        uint32_t e[CPL];
         if (PROF && c0 + CPL <= nA) {        // interior block: every column is a real base of sequence A
 #pragma unroll
-            for (int c = 0; c < CPL; ++c)
-                ring[(c0 + c) & (PB_RING - 1)] = (ring_t)((uint32_t)((pendA >> (8 * c + 4)) & 0xFu) * (uint32_t)ProfGeom<G, R>::ROWS);
-            return;
-        }
+            for (int c = 0; c < CPL; ++c) e[c] = (uint32_t)((pendA >> (8 * c + 4)) & 0xFu) * (uint32_t)ProfGeom<G, R>::ROWS;
+        } else {
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) {
-            const int col = c0 + c;
-            const uint32_t bA = (col < nA) ? (uint32_t)((pendA >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H;
-            const uint32_t bB = PROF ? bA : ((col < nB) ? (uint32_t)((pendB >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H);
-            ring[col & (PB_RING - 1)] = PROF ? (ring_t)((bA >> 4) * (uint32_t)ProfGeom<G, R>::ROWS) : ring_pack(bA, bB);
+            for (int c = 0; c < CPL; ++c) {
+                const int col = c0 + c;
+                const uint32_t bA = (col < nA) ? (uint32_t)((pendA >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H;
+                const uint32_t bB = PROF ? bA : ((col < nB) ? (uint32_t)((pendB >> (8 * c)) & 0xFFu) : (uint32_t)PB_PAD_H);
+                e[c] = PROF ? (bA >> 4) * (uint32_t)ProfGeom<G, R>::ROWS : (uint32_t)ring_pack(bA, bB);
+            }
         }
+        ring_t *dst = ring + (c0 & (PB_RING - 1));
+#ifndef PB_RING32
+        if (CPL == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(e[0] | (e[1 % CPL] << 16), e[2 % CPL] | (e[3 % CPL] << 16),
+                                                                    e[4 % CPL] | (e[5 % CPL] << 16), e[6 % CPL] | (e[7 % CPL] << 16));
+        else if (CPL == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(e[0] | (e[1 % CPL] << 16), e[2 % CPL] | (e[3 % CPL] << 16));
+        else if (CPL == 2) *reinterpret_cast<uint32_t *>(dst) = e[0] | (e[1 % CPL] << 16);
+        else dst[0] = (ring_t)e[0];
+#else
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) dst[c] = (ring_t)e[c];
+#endif
     };
 
     for (;;) {
@@ -588,9 +611,9 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                             uint32_t w[8];
 #pragma unroll
                             for (int r = 0; r < 8; ++r) w[r] = PB_PROF_ENCODE(profile_from(L.v2[r], L.sf2[r], (uint32_t)b, sc));
-                            uint4 *dst = reinterpret_cast<uint4 *>(myprof + b * ProfGeom<G, R>::ROWS);
-                            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                            uint32_t *dst = myprof + b * ProfGeom<G, R>::ROWS;
+                            *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                            *reinterpret_cast<uint4 *>(dst + ProfGeom<G, R>::PLANE) = make_uint4(w[4], w[5], w[6], w[7]);
                         }
                     }
                     const bool emptyA = tA.n <= 0 || tA.m <= 0, emptyB = tB.n <= 0 || tB.m <= 0;
@@ -621,8 +644,8 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                 const int j = t - g + 1;
                 const uint32_t hx = ring[(j - 1) & (PB_RING - 1)];      // packed bases (ring form), or (PROF) the table offset of the base
                 if (PROF) {
-                    const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + hx);
-                    const uint4 p0 = pp[0], p1 = pp[1];
+                    const uint4 p0 = *reinterpret_cast<const uint4 *>(myprof + hx);
+                    const uint4 p1 = *reinterpret_cast<const uint4 *>(myprof + hx + ProfGeom<G, R>::PLANE);
                     const uint32_t subs[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
                     lane_step<R, false, false, true>(L, recvS, recvV, 0u, sc, nullptr, nullptr, subs);
                 } else {
@@ -642,8 +665,8 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
                     const uint32_t h2 = ring[(j - 1) & (PB_RING - 1)];          // ring form: see ring_bases
                     uint32_t vr[R];
                     if (PROF) {
-                        const uint4 *pp = reinterpret_cast<const uint4 *>(myprof + h2);
-                        const uint4 p0 = pp[0], p1 = pp[1];
+                        const uint4 p0 = *reinterpret_cast<const uint4 *>(myprof + h2);
+                        const uint4 p1 = *reinterpret_cast<const uint4 *>(myprof + h2 + ProfGeom<G, R>::PLANE);
                         const uint32_t subs[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
                         lane_step<R, false, true, true>(L, recvS, recvV, 0u, sc, nullptr, vr, subs);
                     } else {
