@@ -526,6 +526,9 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
     uint64_t pendA = 0, pendB = 0;           // raw bytes of the block that will be stored at the next block boundary
     gA = make_geom(0, 0, G, R); gB = gA;
     L.botX = sc.borderX2; L.botV = sc.negb2;
+    uint32_t top_keep = g != 0 ? 1u : 0u;
+    const uint32_t top_addS = g == 0 ? sc.borderX2 : 0u, top_addV = g == 0 ? sc.negb2 : 0u;
+    asm volatile("" : "+r"(top_keep));      // opaque: keeps `x * top_keep + add` a multiply-add (the compiler would fold it back into a select)
     if (PROF) {      // a group that never gets a slot still runs the hot segments on dead state: its ring must hold valid offsets
         for (int c = g; c < PB_RING; c += G) ring[c] = (ring_t)0;
         __syncwarp();
@@ -640,7 +643,10 @@ score_kernel(const TaskSrc ts, unsigned long long *__restrict__ counter,
             for (int k = 0; k < PB_BLK; ++k) {
                 uint32_t recvS = __shfl_up_sync(0xffffffffu, L.botX, 1, G);
                 uint32_t recvV = __shfl_up_sync(0xffffffffu, L.botV, 1, G);
-                if (g == 0) { recvS = sc.borderX2; recvV = sc.negb2; }
+                // lane 0 of a group takes the border instead: as a multiply-add (x * 0 + border / x * 1 + 0) the two selects are
+                // FMA-heavy work -- the ALU pipe is the busier one in this kernel (72 % vs 47 % after the bank-conflict fix)
+                recvS = recvS * top_keep + top_addS;
+                recvV = recvV * top_keep + top_addV;
                 const int j = t - g + 1;
                 const uint32_t hx = ring[(j - 1) & (PB_RING - 1)];      // packed bases (ring form), or (PROF) the table offset of the base
                 if (PROF) {
