@@ -582,7 +582,21 @@ def measure_gpu(workload, args, ctx, K, Wm, main):
         per_step_ms = kd['ms'] / K
         launch_ms = kd['ms'] / kd['n']
         launches_per_step = kd['n'] / K
-        bytes_per_launch = workload.alg_bytes / launches_per_step
+        # what the dominant kind really processes: sequences up to direct_max take the single-pass trace kernel, longer ones
+        # the score pass (+ a bounded window pass that reports its own cells) -- a mixed workload (the length sweep) must not
+        # credit one kernel with the whole step
+        dmax = W.get_option('direct_max')
+        share_cells = share_bytes = 0.0
+        for _, _, off, ads in workload.batches:
+            lens = np.diff(np.asarray(off))
+            sel = lens <= dmax if dom == 'trace_kernel' else lens > dmax
+            if dom not in ('trace_kernel', 'score_kernel'):
+                sel = np.ones(len(lens), dtype=bool)
+            ad_bases = sum(len(a) for a in ads)
+            share_cells += float(lens[sel].sum()) * ad_bases
+            share_bytes += float(lens[sel].sum()) + (ad_bases if sel.any() else 0) + 36.0 * float(sel.sum()) * len(ads)
+        frac_cells = share_cells / max(workload.cells, 1)
+        bytes_per_launch = (share_bytes if share_cells else workload.alg_bytes) / launches_per_step
         achieved = bytes_per_launch / (launch_ms / 1e3) / 1e9
         traffic = None
         try:
@@ -596,7 +610,7 @@ def measure_gpu(workload, args, ctx, K, Wm, main):
                 'note': 'algorithmic bytes of the step (sum|H| + sum|V| + 36 B per alignment) / launches of the dominant kernel; '
                         'the kernel is integer-issue bound by construction (SURVEY 0.7): see roofline_alu'}
         sc = sass_counts().get(dom, {})
-        cells_kernel = kd.get('cells') or workload.cells * K        # full-sweep kernels process every cell of the step
+        cells_kernel = kd.get('cells') or workload.cells * K * (frac_cells if share_cells else 1.0)   # full-sweep kernels: every cell of their share
         cps = cells_kernel / (kd['ms'] / 1e3)
         if sc.get('instr_per_cell'):
             peak_cells = 148 * 4 * 32 * sm_mhz * 1e6 / sc['instr_per_cell']
