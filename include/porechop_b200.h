@@ -163,6 +163,10 @@ int pb200SetOption(const char *name, const char *value);
  * "chunk_tasks", "hbuf" as 0/1/2), or "h2d_pack_large_submit": what h2d_pack = auto resolves to for a large submit on this
  * host (1 = packed).  -1 for an unknown name. */
 int pb200GetOption(const char *name);
+/* Pinned (page-locked) staging memory for host callers that assemble a batch before submitting it: slot 0..3, at least `bytes`
+ * long, owned by the library and valid until the next call for the same slot; NULL when there is no device.  Uploads from it
+ * are asynchronous DMA; the buffer is reused call after call. */
+void *pb200HostBuffer(int slot, size_t bytes);
 
 enum {
     PB200_OK = 0,

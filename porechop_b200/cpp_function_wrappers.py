@@ -85,7 +85,7 @@ EXPORTED_SYMBOLS = ['adapterAlignment', 'freeCString', 'adapterAlignmentBatch', 
                     'adapterAlignmentBatchDevice', 'adapterEndDecisions', 'pb200TrimThresholdTable',
                     'pb200FormatRecord', 'pb200DeviceCount', 'pb200SetDevice', 'pb200Synchronize', 'pb200LastError',
                     'pb200KernelLaunches', 'pb200TimingEnable', 'pb200TimingRead', 'pb200TimingReadKinds', 'pb200SetOption',
-                    'pb200GetOption', 'pb200PackNibbles']
+                    'pb200GetOption', 'pb200HostBuffer', 'pb200PackNibbles']
 
 RECORD_INTS = 9
 SCORE_EMPTY = -2147483648
@@ -317,6 +317,18 @@ def pack_nibbles(ascii_buf, threads=0):
 
 def set_option(name, value):
     _check(C_LIB.pb200SetOption(name.encode(), str(value).encode()))
+
+
+def pinned_buffer(slot, nbytes):
+    """uint8[nbytes] view of the library's pinned staging buffer `slot` (pb200HostBuffer), or None without a device.  The
+    view is valid until the next call for the same slot."""
+    import ctypes
+    C_LIB.pb200HostBuffer.argtypes = [c_int, ctypes.c_size_t]
+    C_LIB.pb200HostBuffer.restype = c_void_p
+    p = C_LIB.pb200HostBuffer(int(slot), int(max(nbytes, 1)))
+    if not p:
+        return None
+    return np.ctypeslib.as_array(cast(p, POINTER(ctypes.c_uint8)), shape=(int(max(nbytes, 1)),))[:int(nbytes)]
 
 
 def get_option(name):

@@ -1446,6 +1446,21 @@ int pb200Synchronize(void) {
     return rc_final;
 }
 
+// Pinned staging memory for host callers (fastq.py gathers the trimmed reads of a chunk before the middle scan): `slot` 0..3,
+// grown on demand, owned by the library, valid until the next call for the same slot.  NULL without a device (callers then
+// use ordinary memory).  A pinned source makes the engine's uploads asynchronous DMA at PCIe speed and is reused chunk after
+// chunk instead of page-faulting in a fresh gigabyte every time.
+void *pb200HostBuffer(int slot, size_t bytes) {
+    static HostBuf bufs[4];
+    static std::mutex mu;
+    if (slot < 0 || slot >= 4) return nullptr;
+    Engine *Ep = nullptr;
+    if (get_engine(&Ep)) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (bufs[slot].ensure(bytes ? bytes : 1)) return nullptr;
+    return bufs[slot].p;
+}
+
 int pb200GetOption(const char *name) {
     load_env_options();
     if (!name) return -1;

@@ -216,11 +216,12 @@ def _ramp(lens):
     return np.arange(total, dtype=np.int64) - first[seg], seg
 
 
-def _gather_ranges(buf, a, b):
-    """concatenate buf[a[i]:b[i]] for all i -> (flat uint8, int64 offsets) without a Python loop."""
+def _gather_ranges(buf, a, b, alloc=None):
+    """concatenate buf[a[i]:b[i]] for all i -> (flat uint8, int64 offsets) without a Python loop.
+    alloc: optional allocator of the flat result (hostio.gather)."""
     lens = np.maximum(np.asarray(b, dtype=np.int64) - np.asarray(a, dtype=np.int64), 0)
     if hostio.LIB is not None and buf.dtype == np.uint8 and buf.flags.c_contiguous:
-        return hostio.gather(buf, a, lens)
+        return hostio.gather(buf, a, lens, alloc=alloc)
     off = np.zeros(len(lens) + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
     if int(off[-1]) == 0:
@@ -350,7 +351,12 @@ def find_middle_hits(batch, start_trim, end_trim, adapters, middle_threshold, sc
     if n == 0 or n_ad == 0:
         return hits
     a, b = trimmed_ranges(batch.lengths(), start_trim, end_trim)
-    tbuf, toff = _gather_ranges(batch.seq, batch.seq_off[:-1] + a, batch.seq_off[:-1] + b)
+    # the trimmed reads of the chunk go into the engine's pinned staging buffer (reused chunk after chunk, uploaded by DMA at
+    # PCIe speed) when there is one -- round 2 on the B200 host: the gather into fresh pageable memory + its upload were most of
+    # the 0.53 s the middle scan of 200 k reads took, the device needing 0.03 s
+    pinned = getattr(W, 'pinned_buffer', None)
+    tbuf, toff = _gather_ranges(batch.seq, batch.seq_off[:-1] + a, batch.seq_off[:-1] + b,
+                                alloc=(lambda nbytes: pinned(0, nbytes)) if pinned is not None else None)
     abuf, aoff = W.pack_sequences([x[1] for x in adapters], offset_dtype=np.int32)
     rec = W.adapter_alignment_batch(tbuf, toff, abuf, aoff, scoring_scheme_vals)
     full, _, rs, re_ = (x.reshape(n, n_ad) for x in scores_from_records(rec))

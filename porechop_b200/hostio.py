@@ -114,12 +114,15 @@ def line_spans(buf):
     return a, ln
 
 
-def gather(src, src_a, lens, src_len=None, fill=0):
-    """concatenate src[src_a[i] : src_a[i]+lens[i]] (short sources padded with `fill`) -> (flat uint8, int64 offsets)."""
+def gather(src, src_a, lens, src_len=None, fill=0, alloc=None):
+    """concatenate src[src_a[i] : src_a[i]+lens[i]] (short sources padded with `fill`) -> (flat uint8, int64 offsets).
+    alloc(nbytes) -> uint8 array or None: where the result goes (e.g. the engine's pinned staging buffer)."""
     lens = _i64(lens)
     off = np.zeros(len(lens) + 1, dtype=np.int64)
     np.cumsum(lens, out=off[1:])
-    dst = np.empty(int(off[-1]), dtype=np.uint8)
+    dst = alloc(int(off[-1])) if alloc is not None else None
+    if dst is None:
+        dst = np.empty(int(off[-1]), dtype=np.uint8)
     src_a = _i64(src_a)
     sl = _i64(src_len) if src_len is not None else None
     LIB.pbioGather(_p(dst), _p(off), _p(src), _p(src_a), _p(sl), int(fill), len(lens))
