@@ -144,7 +144,7 @@ int pb200TimingRead(double *dp_kernel_ms, long long *dp_kernel_launches, double 
 #define PB200_TIMING_KINDS 4
 int pb200TimingReadKinds(double *ms, long long *launches, double *window_cells, int reset);
 /* Tunables (also read from the environment at first use, PB200_<NAME>); none of them changes a result:
- *   "direct_max"  longest sequence aligned in one pass (default 512; longer ones take score pass + bounded window)
+ *   "direct_max"  longest sequence aligned in one pass (default 160; longer ones take score pass + bounded window)
  *   "chunk_tasks" alignments per pipeline chunk of the host-buffer API (default 131072)
  *   "scratch_mb"  cap on the resident trace scratch in MB (default 128; 72 keeps it L2-resident)
  *   "hbuf"        staging of a slot's packed bases: "auto" | "smem" | "global"

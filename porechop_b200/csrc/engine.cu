@@ -95,7 +95,9 @@ struct HostBuf {
 };
 
 struct Options {
-    int64_t direct_max = 512;      // longest sequence aligned in a single (trace) pass
+    int64_t direct_max = 160;      // longest sequence aligned in a single (trace) pass.  Round 2 on B200: 150-column windows are 6 % faster in one
+                                   // pass, 500-column reads 2.9x faster in two (the one-pass trace of a long window is 10.5 instead of 3.7
+                                   // instructions per cell and its scratch, 129 KB per warp at 500 columns, leaves 2 blocks per SM)
     int64_t chunk_tasks = 1 << 17; // alignments per pipeline chunk (host-buffer API)
     int64_t device_chunk_tasks = 8 << 20; // alignments per launch group (device-resident API)
     int64_t chunk_bytes = 64ll << 20;   // sequence bytes per pipeline chunk (host-buffer API)

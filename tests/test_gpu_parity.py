@@ -209,7 +209,7 @@ def test_single_pass_long_windows_and_global_staging(W):
         got = W.adapter_alignment_batch(buf, off, abuf, aoff, wl.DEFAULT_SCORING)
     finally:
         W.set_option('hbuf', 'auto')
-        W.set_option('direct_max', 512)
+        W.set_option('direct_max', 160)
     assert np.array_equal(got, exp)
 
 

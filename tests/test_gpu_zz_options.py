@@ -20,7 +20,7 @@ def W():
 
 
 def _with(W, opts, fn):
-    defaults = {'hbuf': 'auto', 'h2d_pack': 0, 'tight_window': 1, 'profile': 1, 'direct_max': 512, 'chunk_tasks': 131072, 'pack_threads': 8}
+    defaults = {'hbuf': 'auto', 'h2d_pack': 0, 'tight_window': 1, 'profile': 1, 'direct_max': 160, 'chunk_tasks': 131072, 'pack_threads': 8}
     try:
         for k, v in opts.items():
             W.set_option(k, v)

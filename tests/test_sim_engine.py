@@ -18,7 +18,7 @@ from test_oracle import SURVEY_EDGE, rebuild_fullread_inputs
 
 sys.path.insert(0, os.path.join(ROOT, 'tests', 'sim'))
 
-OPTION_DEFAULTS = {'h2d_pack': 0, 'tight_window': 1, 'profile': 1, 'direct_max': 512,
+OPTION_DEFAULTS = {'h2d_pack': 0, 'tight_window': 1, 'profile': 1, 'direct_max': 160,
                    'chunk_tasks': 131072, 'pack_threads': 8, 'scratch_mb': 128, 'hbuf': 'auto'}
 
 

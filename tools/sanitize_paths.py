@@ -16,7 +16,7 @@ import numpy as np                                  # noqa: E402
 from helpers import oracle_batch                    # noqa: E402
 from porechop_b200 import cpp_function_wrappers as W, workloads as wl    # noqa: E402
 
-DEFAULTS = {'h2d_pack': 0, 'tight_window': 1, 'profile': 1, 'direct_max': 512, 'chunk_tasks': 131072,
+DEFAULTS = {'h2d_pack': 0, 'tight_window': 1, 'profile': 1, 'direct_max': 160, 'chunk_tasks': 131072,
             'hbuf': 'auto'}
 yt, yb = wl.nsk007()
 _, sw, ew = wl.synth_end_windows(600, yt, yb, seed=1)
