@@ -299,18 +299,18 @@ PB_HD uint32_t xnor2(uint32_t a, uint32_t b) {
 
 // max(a, b) per half; sets the bits `clo` / `chi` in acc when a >= b in the low / high half ("first operand wins ties").
 // Device: ptxas fuses this into one VIMNMX.S16x2 with two predicate outputs plus two predicated accumulations.
-// use_or picks the PIPE of the two accumulations: the flag bits of a step are disjoint, so add / or / xor give the same word,
+// on_alu picks the PIPE of the two accumulations: the flag bits of a step are disjoint, so add / or / xor give the same word,
 // but a predicated add issues on the FMA-heavy pipe (VIADD / IMAD.IADD) and a predicated logic op on the ALU pipe (LOP3).
 // Both pipes take one warp instruction per two cycles and scheduler and the FMA-lite pipe takes no integer work
 // (tools/ubench_pipes.cu under ncu, profiles/r2_pipes: VIMNMX / VIADDMNMX / VIMNMX3 / LOP3 -> ALU; VIADD.16x2 / IMAD /
 // VIADD -> FMA-heavy; alone each sustains 0.5 warp instructions per clock, alternating they reach 1.0).  With every
 // accumulation an add the trace pass had 12 heavy and 6 ALU instructions per row (ncu: fmaheavy 72 %, ALU 57 % busy) and
-// was bound by the heavy pipe; lane_step mixes the two forms (PB_FLAG_OR_*).
-// (use_or is a constant after unrolling: the dead form is eliminated)
-PB_HD uint32_t max2acc(bool use_or, uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, uint32_t &accHi, uint32_t chi) {
+// was bound by the heavy pipe; lane_step mixes the two forms (PB_FLAG_ALU_*).
+// (on_alu is a constant after unrolling: the dead form is eliminated)
+PB_HD uint32_t max2acc(bool on_alu, uint32_t a, uint32_t b, uint32_t &accLo, uint32_t clo, uint32_t &accHi, uint32_t chi) {
 #if defined(__CUDA_ARCH__)
     uint32_t val;
-    if (use_or) {
+    if (on_alu) {
         asm("{\n\t.reg .pred plo, phi;\n\t.reg .s16 a0, a1, b0, b1;\n\t"
             "max.s16x2 %0, %3, %4;\n\t"
             "mov.b32 {a0, a1}, %0;\n\tmov.b32 {b0, b1}, %3;\n\t"
@@ -329,8 +329,8 @@ PB_HD uint32_t max2acc(bool use_or, uint32_t a, uint32_t b, uint32_t &accLo, uin
 #else
     bool plo, phi;
     uint32_t v = max2p(a, b, plo, phi);
-    if (plo) accLo = use_or ? (accLo | clo) : (accLo + clo);
-    if (phi) accHi = use_or ? (accHi | chi) : (accHi + chi);
+    if (plo) accLo = on_alu ? (accLo ^ clo) : (accLo + clo);
+    if (phi) accHi = on_alu ? (accHi ^ chi) : (accHi + chi);
     return v;
 #endif
 }
@@ -339,11 +339,11 @@ PB_HD uint32_t max2acc(bool use_or, uint32_t a, uint32_t b, uint32_t &accLo, uin
 // four (2 of the 8 accumulations per row): tD 1.958, tH 1.976, tH on even rows only 2.037; tH+tV on even rows 1.990, tH+tV
 // 2.053, tH+tV+tM 2.248 -- the minimum is where the hot loop's ALU and FMA-heavy instruction counts are equal (279 / 286 per
 // 4 steps x 7 rows; ncu afterwards: both pipes 69-70 % busy, issue slots 78 %).
-#ifndef PB_FLAG_OR_A
-#define PB_FLAG_OR_A 0x8
+#ifndef PB_FLAG_ALU_A
+#define PB_FLAG_ALU_A 0x8
 #endif
-#ifndef PB_FLAG_OR_B
-#define PB_FLAG_OR_B 0x8
+#ifndef PB_FLAG_ALU_B
+#define PB_FLAG_ALU_B 0x8
 #endif
 
 // Query profile of the score pass (option "profile", default on).  The substitution operand of group row q depends only
@@ -424,11 +424,11 @@ PB_HD void lane_step(Lane<R> &L, uint32_t recvX, uint32_t recvV, uint32_t h2, co
         if (TRACE) {
             const uint32_t bl = 1u << trace_shift<R>(0, r);
             const uint32_t bh = 1u << trace_shift<R>(1, r);
-            const int orm = (r & 1) ? (PB_FLAG_OR_B) : (PB_FLAG_OR_A);
-            hs = max2acc((orm & 1) != 0, PB_EXT(L.Hs[r]), L.X[r], accLo, bl << 3, accHi, bh << 3);   // ext vs open (= X left)
-            vs = max2acc((orm & 2) != 0, PB_EXT(upV), upX, accLo, bl << 2, accHi, bh << 2);          // ext vs open (= X up)
-            const uint32_t gmx = max2acc((orm & 4) != 0, vs, hs, accLo, bl << 1, accHi, bh << 1);
-            s = max2acc((orm & 8) != 0, d, gmx, accLo, bl, accHi, bh);
+            const int alu_sites = (r & 1) ? (PB_FLAG_ALU_B) : (PB_FLAG_ALU_A);
+            hs = max2acc((alu_sites & 1) != 0, PB_EXT(L.Hs[r]), L.X[r], accLo, bl << 3, accHi, bh << 3);   // ext vs open (= X left)
+            vs = max2acc((alu_sites & 2) != 0, PB_EXT(upV), upX, accLo, bl << 2, accHi, bh << 2);          // ext vs open (= X up)
+            const uint32_t gmx = max2acc((alu_sites & 4) != 0, vs, hs, accLo, bl << 1, accHi, bh << 1);
+            s = max2acc((alu_sites & 8) != 0, d, gmx, accLo, bl, accHi, bh);
         } else {
             hs = addmax2(L.Hs[r], sc.ge2, L.X[r]);
             vs = addmax2(upV, sc.ge2, upX);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Compile-time A/B on the GPU box: every VARIANT = "name|nvcc flags|bench.py arguments" rebuilds cpp_functions.so with the
 # flags (PB200_NVCC_FLAGS), optionally runs the GPU parity tests (PARITY=1) and prints the bench line's key numbers.
-#   gpurun --timeout 1500 -- 'TAG=r2d PARITY=1 bash tools/gpu_ab.sh "base||" "or11|-DPB_FLAG_OR_A=0x1 -DPB_FLAG_OR_B=0x1|"'
+#   gpurun --timeout 1500 -- 'TAG=r2d PARITY=1 bash tools/gpu_ab.sh "base||" "or11|-DPB_FLAG_ALU_A=0x1 -DPB_FLAG_ALU_B=0x1|"'
 # UBENCH=1 first builds tools/ubench_pipes.cu, runs it plain and under ncu (pipe counters of every kernel).
 set -u
 TAG="${TAG:-ab}"
