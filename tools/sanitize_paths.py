@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Small runs of every engine path (default + opt-in) for compute-sanitizer on the GPU box:
 
-    compute-sanitizer --tool memcheck  python tools/r2_sanitize.py
-    compute-sanitizer --tool racecheck python tools/r2_sanitize.py      (shared-memory hazards: staging rings, profiles)
+    compute-sanitizer --tool memcheck  python tools/sanitize_paths.py
+    compute-sanitizer --tool racecheck python tools/sanitize_paths.py      (shared-memory hazards: staging rings, profiles)
 
 Inputs are tiny (the tools slow kernels down by 10-100x); results are compared with the oracle so a run also fails on
 wrong records.  The host simulation (tests/sim) already runs the same paths under AddressSanitizer and with shuffled lane
