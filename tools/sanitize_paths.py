@@ -58,6 +58,17 @@ run('demux', {'direct_max': 100}, cross(sbuf[:150 * 12], soff[:13], a3, o3))
 run('demux', {'hbuf': 'global'}, cross(sbuf[:150 * 12], soff[:13], a3, o3))
 outs = W.adapter_end_decisions([(sbuf, soff, a2, o2, True, [0, 1])], wl.DEFAULT_SCORING, 150, 2, 75.0, 4)
 print('decisions', outs[0][0][:6].tolist(), flush=True)
+# barcode ranking on the device (top2) over a many-column class, checked against the host ranking of the same records
+from porechop_b200 import hostio
+from porechop_b200.fastq import Top2Scores, top2_from_scores
+cols = list(range(0, len(starts), 7))
+(trim, top2, rec), = W.adapter_end_decisions([(sbuf[:150 * 40], soff[:41], a3, o3, True, cols)], wl.DEFAULT_SCORING, 150, 2, 75.0, 4,
+                                             want_top2=True, want_records=True)
+exp = top2_from_scores(hostio.full_scores(rec.reshape(40, len(starts), 9), cols)) if hostio.LIB is not None else None
+got = Top2Scores([str(c) for c in cols], top2).ranked()
+ok = exp is None or all(np.array_equal(g, e) for g, e in zip(got, exp))
+bad += 0 if ok else 1
+print('top2      %s' % ('ok' if ok else 'DIFFERENT'), flush=True)
 got = W.adapter_alignment_batch_multi([(sbuf, soff, a1, o1), (lbuf, loff, a2, o2)], wl.DEFAULT_SCORING)
 bad += 0 if np.array_equal(got[1], oracle_batch(lbuf, loff, a2, o2, wl.DEFAULT_SCORING)) else 1
 print('SANITIZE RUN COMPLETE, %d wrong' % bad, flush=True)
