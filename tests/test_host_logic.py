@@ -277,3 +277,32 @@ def test_simulated_engine_results_do_not_depend_on_lane_interleaving():
                             'long_reads_two_pass_and_options or multi_submit'], env=env, capture_output=True,
                            text=True, cwd=ROOT)
         assert r.returncode == 0 and '2 passed' in r.stdout, order + '\n' + r.stdout[-2000:]
+
+
+def test_cpu_quota_is_respected_by_the_cpu_baseline_sizing_and_hostio(monkeypatch, tmp_path):
+    """Round 2: the GPU boxes show 128 hardware threads under a cgroup quota of 16 CPUs.  bench.py sizes the CPU baseline and
+    hostio its OpenMP team by what the quota allows, not by the visible threads."""
+    import builtins
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module('bench')
+    from porechop_b200 import hostio
+    real_open = builtins.open
+
+    def fake_open(quota):
+        def _open(path, *a, **k):
+            if path == '/sys/fs/cgroup/cpu.max':
+                p = tmp_path / 'cpu.max'
+                p.write_text(quota)
+                return real_open(p, *a, **k)
+            return real_open(path, *a, **k)
+        return _open
+    monkeypatch.setattr(os, 'sched_getaffinity', lambda pid: set(range(128)), raising=False)
+    monkeypatch.setattr(builtins, 'open', fake_open('1600000 100000\n'))
+    assert bench.cgroup_cpu_limit() == 16 and bench.host_cores() == 16 and hostio.usable_cpus() == 16
+    monkeypatch.setattr(builtins, 'open', fake_open('max 100000\n'))
+    assert bench.cgroup_cpu_limit() is None and bench.host_cores() == 128 and hostio.usable_cpus() == 128
+    monkeypatch.setattr(builtins, 'open', fake_open('150000 100000\n'))         # 1.5 CPUs -> 2
+    assert bench.cgroup_cpu_limit() == 2 and bench.host_cores() == 2
